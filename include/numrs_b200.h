@@ -1,0 +1,138 @@
+/*
+ * numrs_b200.h -- C ABI of libnumrs_b200.so: the B200-native (sm_100a) implementation of the
+ * numrs FFT hot path (four1 / fourn / realft / rlft3 / convlv / correl).
+ *
+ * This header is the drop-in boundary.  The reference
+ * (SciRustaceans/numrs) is a pure-Rust crate with no FFI of its own; each entry point below
+ * is what the reference's public Rust function of the same name would bind through
+ * `extern "C"` (see INTEGRATION.md for the Rust shim).  Signatures use plain pointers and
+ * sizes only.  All citations are file:line in /root/reference/src.
+ *
+ * Conventions (identical to the reference):
+ *   - complex data is interleaved f64: data[2k] = Re, data[2k+1] = Im;
+ *   - isign = +1 uses exp(+2*pi*i*j*k/N), isign = -1 uses exp(-2*pi*i*j*k/N);
+ *   - no normalisation in either direction (four1/fourn round trip = N*x,
+ *     realft round trip = (n/2)*x, rlft3 round trip = (nn1*nn2*nn3/2)*x);
+ *   - sizes are powers of two (the reference never validates this; this library returns
+ *     NRB_ERR_NOT_POW2 instead of computing garbage).
+ *
+ * Host-slice entry points take HOST pointers (caller-owned, not retained), run the transform
+ * on the current device (nrb_set_device) and block until the result is back in host memory.
+ * They are thread-safe (per-thread stream and staging; plan cache behind a mutex).
+ * There is no CPU fallback: without a CUDA device every compute entry point returns
+ * NRB_ERR_CUDA.
+ */
+#ifndef NUMRS_B200_H
+#define NUMRS_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes (mapped by the Rust shim to ConvlvError / CorrelError /
+ *      io::ErrorKind::InvalidInput / panic) ---- */
+#define NRB_OK                     0
+#define NRB_ERR_EMPTY_INPUT       -1   /* Convolve.rs:13-15, Correlation.rs:11-13 */
+#define NRB_ERR_RESPONSE_TOO_LONG -2   /* Convolve.rs:16-18 */
+#define NRB_ERR_INVALID_ISIGN     -3   /* Convolve.rs:19-21, Fourn.rs:371-373, Real_FT3.rs:17 */
+#define NRB_ERR_LENGTH_MISMATCH   -4   /* Correlation.rs:14-16 */
+#define NRB_ERR_INVALID_DIMS      -5   /* Fourn.rs:368-370,374-376, Real_FT.rs:5 (n odd) */
+#define NRB_ERR_NOT_POW2          -6   /* not validated by the reference */
+#define NRB_ERR_UNSUPPORTED       -7   /* shape outside what this build implements */
+#define NRB_ERR_CUDA              -10
+#define NRB_ERR_NCCL              -11
+#define NRB_ERR_OOM               -12
+
+/* convlv response padding (SURVEY.md 8c ledger L1) */
+#define NRB_PAD_LITERAL 0              /* Convolve.rs:41-63 as written (default) */
+#define NRB_PAD_NR      1              /* Numerical Recipes convlv wrap-around */
+
+/* ---- library ---- */
+const char *nrb_version(void);
+const char *nrb_last_error(void);      /* thread-local, never NULL */
+int  nrb_device_count(void);           /* number of CUDA devices, 0 if none */
+int  nrb_set_device(int device);       /* device used by the calling thread */
+int  nrb_shutdown(void);               /* frees cached plans / scratch of all threads */
+/* Planner tunables (affect plans created afterwards; cached host-call plans are dropped):
+ *   "col_max_log2"   longest strided-axis FFT done in one pass          (default 10)
+ *   "row_max_log2"   longest contiguous FFT done in one pass            (default 13)
+ *   "l2_group_bytes" working-set target of L2-resident pass groups      (default 32 MiB)
+ * Environment overrides at load time: NRB_COL_MAX_LOG2, NRB_ROW_MAX_LOG2, NRB_L2_GROUP_MB. */
+int  nrb_set_option(const char *name, long value);
+/* pinned host memory, so host-slice calls copy at full PCIe rate (optional) */
+void *nrb_host_alloc(size_t bytes);
+void  nrb_host_free(void *p);
+
+/* ---- host-slice drop-in entry points ---- */
+
+/* FFT_1.rs:5  pub fn four1(data: &mut [f64], nn: usize, isign: i32); data has 2*nn doubles */
+int nrb_four1(double *data, size_t nn, int isign);
+/* FFT_1.rs:185 FFTProcessor::fft_batch(&self, batches: &mut [&mut [f64]], isign): `count`
+ * independent transforms, slice b has 2*nn[b] doubles; slices need not be contiguous. */
+int nrb_four1_batch(double *const *ptrs, const size_t *nn, size_t count, int isign);
+/* Real_FT3.rs:35 call shape `Fourn(&mut flat, &nn, ndim, isign)` (NR in-memory fourn, the
+ * reference's Fourn.rs has no in-memory body); validation as Fourn.rs:367-378.
+ * data has 2*prod(nn[0..ndim]) doubles, row-major, nn[ndim-1] fastest. */
+int nrb_fourn(double *data, const size_t *nn, size_t ndim, int isign);
+/* Real_FT.rs:4  pub fn realft(data: &mut [f64], n: usize, isign: i32); isign == 1 forward,
+ * anything else inverse (Real_FT.rs:10,15).  Packed output: data[0]=F_0, data[1]=F_{n/2}. */
+int nrb_realft(double *data, size_t n, int isign);
+/* Real_FT.rs:365 RealFTProcessor::process_batch: `count` real transforms of length n each */
+int nrb_realft_batch(double *const *ptrs, size_t n, size_t count, int isign);
+/* Real_FT3.rs:8 rlft3(data: Array3 [nn1][nn2][nn3], speq: Array2 [nn1][2*nn2], .., isign) */
+int nrb_rlft3(double *data, double *speq, size_t nn1, size_t nn2, size_t nn3, int isign);
+/* Convolve.rs:8 convlv(data, respns, isign) -> Array1 of length n, written to ans[0..n) */
+int nrb_convlv(const double *data, size_t n, const double *respns, size_t m, int isign,
+               int pad_mode, double *ans);
+/* Convolve.rs:241 convlv_batch: `count` signals of length n, one response */
+int nrb_convlv_batch(const double *const *data, size_t count, size_t n, const double *respns,
+                     size_t m, int isign, int pad_mode, double *const *ans);
+/* Correlation.rs:8 correl(data1, data2) -> Array1 of length n1, written to ans[0..n1) */
+int nrb_correl(const double *data1, size_t n1, const double *data2, size_t n2, double *ans);
+/* Correlation.rs:273 correl_batch: `count` pairs, each of length n */
+int nrb_correl_batch(const double *const *data1, const double *const *data2, size_t count,
+                     size_t n, double *const *ans);
+
+/* ---- device-resident plan API (what the benchmark times; pointers are DEVICE memory) ---- */
+typedef struct nrb_plan_s *nrb_plan_t;
+
+#define NRB_KIND_FOUR1  1   /* dims = {nn};            io = batch x 2*nn doubles            */
+#define NRB_KIND_FOURN  2   /* dims = nn[0..ndim);     io = batch x 2*prod(nn) doubles      */
+#define NRB_KIND_REALFT 3   /* dims = {n};             io = batch x n doubles               */
+#define NRB_KIND_RLFT3  4   /* dims = {nn1,nn2,nn3};   io = data, aux = speq                */
+#define NRB_KIND_CONVLV 5   /* dims = {n, m};          io = batch x n signals (read only),
+                               aux = m response taps, out = batch x n doubles              */
+#define NRB_KIND_CORREL 6   /* dims = {n};             io = data1, aux = data2 (batch x n,
+                               read only), out = batch x n doubles; n > 32                 */
+
+int    nrb_plan_create(int kind, const size_t *dims, size_t ndim, size_t batch, nrb_plan_t *plan);
+size_t nrb_plan_workspace_bytes(nrb_plan_t plan);
+int    nrb_plan_num_launches(nrb_plan_t plan, int isign);  /* kernels per exec */
+/* Enqueue on `stream` (a cudaStream_t, NULL = default stream); does not synchronise.
+ * `arg` is pad_mode for CONVLV and ignored otherwise. */
+int    nrb_plan_exec(nrb_plan_t plan, double *d_io, double *d_aux, double *d_out, int isign,
+                     int arg, void *stream);
+int    nrb_plan_destroy(nrb_plan_t plan);
+
+/* ---- slab-decomposed rlft3 across the GPUs of one box (one process per GPU) ----
+ * Forward: rank r holds the nn2-slab data[:, r*nn2/G:(r+1)*nn2/G, :] as a contiguous
+ * [nn1][nn2/G][nn3] array.  stage 0 = z real transform + x transform on the slab (output
+ * in exchange layout: G blocks [nn1/G][nn2/G][nn3/2] complex, block p goes to rank p);
+ * the caller exchanges blocks (all-to-all over NCCL/NVLink); stage 1 = y transform reading
+ * the received blocks and writing the nn1-slab [nn1/G][nn2][nn3] plus speq [nn1/G][2*nn2].
+ * Inverse (isign=-1) runs the mirror image: stage 0 on the nn1-slab, exchange, stage 1. */
+typedef struct nrb_slab_s *nrb_slab_t;
+int    nrb_slab_create(size_t nn1, size_t nn2, size_t nn3, int nranks, int rank, nrb_slab_t *plan);
+size_t nrb_slab_local_doubles(nrb_slab_t plan);   /* doubles in one slab (data)           */
+size_t nrb_slab_speq_doubles(nrb_slab_t plan);    /* doubles in the local speq part        */
+size_t nrb_slab_xchg_doubles(nrb_slab_t plan);    /* doubles in the exchange buffer        */
+int    nrb_slab_stage(nrb_slab_t plan, int stage, int isign, double *d_slab, double *d_speq,
+                      double *d_send, double *d_recv, void *stream);
+int    nrb_slab_destroy(nrb_slab_t plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NUMRS_B200_H */

@@ -1,0 +1,260 @@
+"""ctypes binding of the C ABI declared in include/numrs_b200.h.
+
+`Library(path)` wraps one shared object.  The product package binds
+numrs_b200/libnumrs_b200.so (CUDA, sm_100a) and nothing else; the CPU-only test tier binds
+tests/emu/libnrb_emu.so through this same class to validate planner/index logic.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_sz = ctypes.c_size_t
+_vp = ctypes.c_void_p
+
+# error codes of include/numrs_b200.h
+NRB_OK = 0
+NRB_ERR_EMPTY_INPUT = -1
+NRB_ERR_RESPONSE_TOO_LONG = -2
+NRB_ERR_INVALID_ISIGN = -3
+NRB_ERR_LENGTH_MISMATCH = -4
+NRB_ERR_INVALID_DIMS = -5
+NRB_ERR_NOT_POW2 = -6
+NRB_ERR_UNSUPPORTED = -7
+NRB_ERR_CUDA = -10
+NRB_ERR_NCCL = -11
+NRB_ERR_OOM = -12
+
+NRB_PAD_LITERAL = 0
+NRB_PAD_NR = 1
+
+KIND_FOUR1, KIND_FOURN, KIND_REALFT, KIND_RLFT3, KIND_CONVLV, KIND_CORREL = 1, 2, 3, 4, 5, 6
+
+# every symbol include/numrs_b200.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "nrb_version", "nrb_last_error", "nrb_device_count", "nrb_set_device", "nrb_shutdown",
+    "nrb_set_option", "nrb_host_alloc", "nrb_host_free",
+    "nrb_four1", "nrb_four1_batch", "nrb_fourn", "nrb_realft", "nrb_realft_batch", "nrb_rlft3",
+    "nrb_convlv", "nrb_convlv_batch", "nrb_correl", "nrb_correl_batch",
+    "nrb_plan_create", "nrb_plan_workspace_bytes", "nrb_plan_num_launches", "nrb_plan_exec", "nrb_plan_destroy",
+    "nrb_slab_create", "nrb_slab_local_doubles", "nrb_slab_speq_doubles", "nrb_slab_xchg_doubles",
+    "nrb_slab_stage", "nrb_slab_destroy",
+]
+
+
+class NrbError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"numrs_b200 error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+def _f64(a):
+    if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]):
+        raise TypeError("expected a C-contiguous float64 numpy array")
+    return a.ctypes.data_as(_dp)
+
+
+class Library:
+    def __init__(self, path):
+        if not os.path.exists(path):
+            raise ImportError(
+                f"{path} not found: the numrs_b200 CUDA library is not built "
+                "(run `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback.")
+        self.path = path
+        L = self.L = ctypes.CDLL(path)
+        L.nrb_version.restype = ctypes.c_char_p
+        L.nrb_last_error.restype = ctypes.c_char_p
+        L.nrb_device_count.restype = ctypes.c_int
+        L.nrb_set_device.argtypes = [ctypes.c_int]
+        L.nrb_set_option.argtypes = [ctypes.c_char_p, ctypes.c_long]
+        L.nrb_host_alloc.argtypes = [_sz]
+        L.nrb_host_alloc.restype = _vp
+        L.nrb_host_free.argtypes = [_vp]
+        L.nrb_host_free.restype = None
+        L.nrb_four1.argtypes = [_dp, _sz, ctypes.c_int]
+        L.nrb_four1_batch.argtypes = [ctypes.POINTER(_dp), ctypes.POINTER(_sz), _sz, ctypes.c_int]
+        L.nrb_fourn.argtypes = [_dp, ctypes.POINTER(_sz), _sz, ctypes.c_int]
+        L.nrb_realft.argtypes = [_dp, _sz, ctypes.c_int]
+        L.nrb_realft_batch.argtypes = [ctypes.POINTER(_dp), _sz, _sz, ctypes.c_int]
+        L.nrb_rlft3.argtypes = [_dp, _dp, _sz, _sz, _sz, ctypes.c_int]
+        L.nrb_convlv.argtypes = [_dp, _sz, _dp, _sz, ctypes.c_int, ctypes.c_int, _dp]
+        L.nrb_convlv_batch.argtypes = [ctypes.POINTER(_dp), _sz, _sz, _dp, _sz, ctypes.c_int, ctypes.c_int,
+                                       ctypes.POINTER(_dp)]
+        L.nrb_correl.argtypes = [_dp, _sz, _dp, _sz, _dp]
+        L.nrb_correl_batch.argtypes = [ctypes.POINTER(_dp), ctypes.POINTER(_dp), _sz, _sz, ctypes.POINTER(_dp)]
+        L.nrb_plan_create.argtypes = [ctypes.c_int, ctypes.POINTER(_sz), _sz, _sz, ctypes.POINTER(_vp)]
+        L.nrb_plan_workspace_bytes.argtypes = [_vp]
+        L.nrb_plan_workspace_bytes.restype = _sz
+        L.nrb_plan_num_launches.argtypes = [_vp, ctypes.c_int]
+        L.nrb_plan_exec.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp]
+        L.nrb_plan_destroy.argtypes = [_vp]
+        L.nrb_slab_create.argtypes = [_sz, _sz, _sz, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]
+        for n in ("nrb_slab_local_doubles", "nrb_slab_speq_doubles", "nrb_slab_xchg_doubles"):
+            getattr(L, n).argtypes = [_vp]
+            getattr(L, n).restype = _sz
+        L.nrb_slab_stage.argtypes = [_vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp]
+        L.nrb_slab_destroy.argtypes = [_vp]
+
+    # ---- helpers
+    def last_error(self):
+        return self.L.nrb_last_error().decode()
+
+    def check(self, rc):
+        if rc != 0:
+            raise NrbError(rc, self.last_error())
+
+    def version(self):
+        return self.L.nrb_version().decode()
+
+    def device_count(self):
+        return self.L.nrb_device_count()
+
+    def set_device(self, dev):
+        self.check(self.L.nrb_set_device(dev))
+
+    def set_option(self, name, value):
+        self.check(self.L.nrb_set_option(name.encode(), int(value)))
+
+    def shutdown(self):
+        self.L.nrb_shutdown()
+
+    def pinned_empty(self, count):
+        """float64 numpy array of `count` elements in pinned host memory (nrb_host_alloc).
+        The memory stays allocated until pinned_free(arr) or process exit."""
+        p = self.L.nrb_host_alloc(max(8, count * 8))
+        if not p:
+            raise MemoryError("nrb_host_alloc failed")
+        buf = (ctypes.c_double * count).from_address(p)
+        arr = np.frombuffer(buf, dtype=np.float64, count=count)
+        _PINNED[arr.ctypes.data] = p
+        return arr
+
+    def pinned_free(self, arr):
+        p = _PINNED.pop(arr.ctypes.data, None)
+        if p:
+            self.L.nrb_host_free(p)
+
+    # ---- raw host-slice calls (return the C return code)
+    def four1(self, data, nn, isign):
+        return self.L.nrb_four1(_f64(data), nn, isign)
+
+    def four1_batch(self, arrays, isign, nn=None):
+        cnt = len(arrays)
+        ptrs = (_dp * max(cnt, 1))(*[_f64(a) for a in arrays])
+        sizes = (_sz * max(cnt, 1))(*([a.size // 2 for a in arrays] if nn is None else nn))
+        return self.L.nrb_four1_batch(ptrs, sizes, cnt, isign)
+
+    def fourn(self, data, nn, ndim, isign):
+        nn_c = (_sz * max(len(nn), 1))(*nn)
+        return self.L.nrb_fourn(_f64(data), nn_c, ndim, isign)
+
+    def realft(self, data, n, isign):
+        return self.L.nrb_realft(_f64(data), n, isign)
+
+    def realft_batch(self, arrays, n, isign):
+        cnt = len(arrays)
+        ptrs = (_dp * max(cnt, 1))(*[_f64(a) for a in arrays])
+        return self.L.nrb_realft_batch(ptrs, n, cnt, isign)
+
+    def rlft3(self, data, speq, nn1, nn2, nn3, isign):
+        return self.L.nrb_rlft3(_f64(data), _f64(speq), nn1, nn2, nn3, isign)
+
+    def convlv(self, data, respns, isign, pad_mode=NRB_PAD_LITERAL):
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        respns = np.ascontiguousarray(respns, dtype=np.float64)
+        ans = np.zeros(max(1, data.size), dtype=np.float64)
+        d = data if data.size else np.zeros(1)
+        r = respns if respns.size else np.zeros(1)
+        rc = self.L.nrb_convlv(_f64(d), data.size, _f64(r), respns.size, isign, pad_mode, _f64(ans))
+        return rc, ans[:data.size]
+
+    def convlv_batch(self, signals, respns, isign, pad_mode=NRB_PAD_LITERAL, outs=None):
+        cnt = len(signals)
+        n = signals[0].size if cnt else 0
+        respns = np.ascontiguousarray(respns, dtype=np.float64)
+        if outs is None:
+            outs = [np.zeros(n, dtype=np.float64) for _ in range(cnt)]
+        ip = (_dp * max(cnt, 1))(*[_f64(s) for s in signals])
+        op = (_dp * max(cnt, 1))(*[_f64(o) for o in outs])
+        rc = self.L.nrb_convlv_batch(ip, cnt, n, _f64(respns), respns.size, isign, pad_mode, op)
+        return rc, outs
+
+    def correl(self, d1, d2):
+        d1 = np.ascontiguousarray(d1, dtype=np.float64)
+        d2 = np.ascontiguousarray(d2, dtype=np.float64)
+        ans = np.zeros(max(1, d1.size), dtype=np.float64)
+        a = d1 if d1.size else np.zeros(1)
+        b = d2 if d2.size else np.zeros(1)
+        rc = self.L.nrb_correl(_f64(a), d1.size, _f64(b), d2.size, _f64(ans))
+        return rc, ans[:d1.size]
+
+    def correl_batch(self, a_list, b_list, outs=None):
+        cnt = len(a_list)
+        n = a_list[0].size if cnt else 0
+        if outs is None:
+            outs = [np.zeros(n, dtype=np.float64) for _ in range(cnt)]
+        ap = (_dp * max(cnt, 1))(*[_f64(a) for a in a_list])
+        bp = (_dp * max(cnt, 1))(*[_f64(b) for b in b_list])
+        op = (_dp * max(cnt, 1))(*[_f64(o) for o in outs])
+        rc = self.L.nrb_correl_batch(ap, bp, cnt, n, op)
+        return rc, outs
+
+    # ---- device-resident plan API (pointers are integers: device addresses)
+    def plan_create(self, kind, dims, batch=1):
+        h = _vp()
+        dims_c = (_sz * max(len(dims), 1))(*dims)
+        self.check(self.L.nrb_plan_create(kind, dims_c, len(dims), batch, ctypes.byref(h)))
+        return Plan(self, h)
+
+    def slab_create(self, nn1, nn2, nn3, nranks, rank):
+        h = _vp()
+        self.check(self.L.nrb_slab_create(nn1, nn2, nn3, nranks, rank, ctypes.byref(h)))
+        return SlabPlan(self, h)
+
+
+_PINNED = {}
+
+
+class Plan:
+    def __init__(self, lib, handle):
+        self.lib, self.h = lib, handle
+
+    def workspace_bytes(self):
+        return self.lib.L.nrb_plan_workspace_bytes(self.h)
+
+    def num_launches(self, isign):
+        return self.lib.L.nrb_plan_num_launches(self.h, isign)
+
+    def exec(self, d_io, d_aux=0, d_out=0, isign=1, arg=0, stream=0):
+        self.lib.check(self.lib.L.nrb_plan_exec(self.h, d_io, d_aux or None, d_out or None, isign, arg,
+                                                stream or None))
+
+    def destroy(self):
+        if self.h:
+            self.lib.L.nrb_plan_destroy(self.h)
+            self.h = None
+
+
+class SlabPlan:
+    def __init__(self, lib, handle):
+        self.lib, self.h = lib, handle
+
+    def local_doubles(self):
+        return self.lib.L.nrb_slab_local_doubles(self.h)
+
+    def speq_doubles(self):
+        return self.lib.L.nrb_slab_speq_doubles(self.h)
+
+    def xchg_doubles(self):
+        return self.lib.L.nrb_slab_xchg_doubles(self.h)
+
+    def stage(self, stage, isign, d_slab, d_speq, d_send, d_recv, stream=0):
+        self.lib.check(self.lib.L.nrb_slab_stage(self.h, stage, isign, d_slab, d_speq, d_send or None,
+                                                 d_recv or None, stream or None))
+
+    def destroy(self):
+        if self.h:
+            self.lib.L.nrb_slab_destroy(self.h)
+            self.h = None

@@ -1,0 +1,376 @@
+// api.cpp -- the C ABI of include/numrs_b200.h: device-resident plan API and the host-slice
+// drop-in entry points (H2D copy, transform on the device, D2H copy, blocking).
+#include <string.h>
+
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/numrs_b200.h"
+#include "plan.h"
+
+using namespace nrb;
+
+struct nrb_plan_s {
+    Plan plan;
+    std::mutex mu;   // serialises exec of one plan (its workspace is shared)
+};
+struct nrb_slab_s {
+    SlabPlan plan;
+};
+
+namespace {
+
+// ---- per-thread host-call context ----
+struct DevBuf {
+    void *p;
+    size_t cap;
+    DevBuf() : p(nullptr), cap(0) {}
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) be_free(p);
+        p = nullptr; cap = 0;
+        if (be_malloc(&p, bytes) != 0) return -1;
+        cap = bytes;
+        return 0;
+    }
+    void release() { if (p) be_free(p); p = nullptr; cap = 0; }
+};
+
+struct ThreadCtx {
+    void *stream;
+    int device;
+    DevBuf io, aux, out;
+    ThreadCtx() : stream(nullptr), device(-1) {}
+    ~ThreadCtx() {}   // device memory is reclaimed by nrb_shutdown / process exit
+};
+thread_local ThreadCtx t_ctx;
+
+std::mutex g_cache_mu;
+std::map<std::string, std::shared_ptr<nrb_plan_s>> g_plan_cache;
+
+int fail(int code, const std::string &msg) { set_error(msg); return code; }
+
+int ensure_ctx()
+{
+    if (be_device_count() <= 0) return fail(NRB_ERR_CUDA, "no CUDA device available (numrs_b200 has no CPU fallback)");
+    const int dev = be_current_device();
+    if (dev < 0) return fail(NRB_ERR_CUDA, std::string("cannot query CUDA device: ") + be_last_error());
+    if (t_ctx.stream && t_ctx.device != dev) {   // thread moved to another device
+        be_stream_destroy(t_ctx.stream);
+        t_ctx.stream = nullptr;
+        t_ctx.io.release(); t_ctx.aux.release(); t_ctx.out.release();
+    }
+    if (!t_ctx.stream) {
+        if (be_stream_create(&t_ctx.stream) != 0) return fail(NRB_ERR_CUDA, std::string("stream creation failed: ") + be_last_error());
+        t_ctx.device = dev;
+    }
+    return NRB_OK;
+}
+
+std::shared_ptr<nrb_plan_s> cached_plan(int kind, const size_t *dims, size_t ndim, size_t batch, int *rc)
+{
+    std::string key = std::to_string(be_current_device()) + ":" + std::to_string(kind) + ":" + std::to_string(batch);
+    for (size_t d = 0; d < ndim; ++d) key += ":" + std::to_string(dims[d]);
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    auto it = g_plan_cache.find(key);
+    if (it != g_plan_cache.end()) { *rc = NRB_OK; return it->second; }
+    std::shared_ptr<nrb_plan_s> h(new nrb_plan_s());
+    *rc = build_plan(h->plan, kind, dims, ndim, batch);
+    if (*rc != NRB_OK) return nullptr;
+    if (g_plan_cache.size() >= 64) {           // bounded cache: drop everything, rebuildable
+        for (auto &kv : g_plan_cache) if (kv.second.use_count() == 1 && kv.second->plan.ws) be_free(kv.second->plan.ws);
+        g_plan_cache.clear();
+    }
+    g_plan_cache[key] = h;
+    return h;
+}
+
+int copy_fail(const char *what) { return fail(NRB_ERR_CUDA, std::string(what) + " failed: " + be_last_error()); }
+
+// in-place transform of `count` host slices of `doubles` doubles each
+int run_inplace(int kind, const size_t *dims, size_t ndim, double *const *ptrs, size_t count, size_t doubles,
+                int isign, double *speq, size_t speq_doubles)
+{
+    int rc = ensure_ctx();
+    if (rc) return rc;
+    auto h = cached_plan(kind, dims, ndim, count, &rc);
+    if (!h) return rc;
+    const size_t bytes = doubles * sizeof(double);
+    if (t_ctx.io.ensure(bytes * count) != 0) return fail(NRB_ERR_OOM, std::string("device allocation failed: ") + be_last_error());
+    if (speq && t_ctx.aux.ensure(speq_doubles * sizeof(double)) != 0) return fail(NRB_ERR_OOM, "device allocation failed");
+    void *s = t_ctx.stream;
+    char *dio = (char *)t_ctx.io.p;
+    // coalesce runs of host slices that are contiguous in memory into one copy
+    for (size_t b = 0; b < count;) {
+        size_t e = b + 1;
+        while (e < count && ptrs[e] == ptrs[b] + (e - b) * doubles) ++e;
+        if (be_h2d(dio + b * bytes, ptrs[b], bytes * (e - b), s) != 0) return copy_fail("host-to-device copy");
+        b = e;
+    }
+    // rlft3 inverse reads speq; forward overwrites it
+    if (speq && isign != 1 && be_h2d(t_ctx.aux.p, speq, speq_doubles * sizeof(double), s) != 0) return copy_fail("host-to-device copy");
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        rc = exec_plan(h->plan, (double *)t_ctx.io.p, (double *)t_ctx.aux.p, nullptr, isign == 1 ? 1 : -1, 0, s);
+        if (rc == NRB_OK && be_sync(s) != 0) rc = copy_fail("kernel execution");
+    }
+    if (rc) return rc;
+    for (size_t b = 0; b < count;) {
+        size_t e = b + 1;
+        while (e < count && ptrs[e] == ptrs[b] + (e - b) * doubles) ++e;
+        if (be_d2h(ptrs[b], dio + b * bytes, bytes * (e - b), s) != 0) return copy_fail("device-to-host copy");
+        b = e;
+    }
+    if (speq && isign == 1 && be_d2h(speq, t_ctx.aux.p, speq_doubles * sizeof(double), s) != 0) return copy_fail("device-to-host copy");
+    if (be_sync(s) != 0) return copy_fail("device-to-host copy");
+    return NRB_OK;
+}
+
+// out-of-place batch: io (count x n), aux (aux_count x aux_n), out (count x n)
+int run_outofplace(int kind, const size_t *dims, size_t ndim, const double *const *in, const double *const *aux,
+                   size_t aux_count, size_t aux_n, double *const *out, size_t count, size_t n, int isign, int arg)
+{
+    int rc = ensure_ctx();
+    if (rc) return rc;
+    auto h = cached_plan(kind, dims, ndim, count, &rc);
+    if (!h) return rc;
+    const size_t bytes = n * sizeof(double);
+    if (t_ctx.io.ensure(bytes * count) != 0 || t_ctx.out.ensure(bytes * count) != 0 ||
+        t_ctx.aux.ensure(aux_n * sizeof(double) * aux_count) != 0)
+        return fail(NRB_ERR_OOM, std::string("device allocation failed: ") + be_last_error());
+    void *s = t_ctx.stream;
+    for (size_t b = 0; b < count; ++b)
+        if (be_h2d((char *)t_ctx.io.p + b * bytes, in[b], bytes, s) != 0) return copy_fail("host-to-device copy");
+    for (size_t b = 0; b < aux_count; ++b)
+        if (be_h2d((char *)t_ctx.aux.p + b * aux_n * sizeof(double), aux[b], aux_n * sizeof(double), s) != 0)
+            return copy_fail("host-to-device copy");
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        rc = exec_plan(h->plan, (double *)t_ctx.io.p, (double *)t_ctx.aux.p, (double *)t_ctx.out.p, isign, arg, s);
+        if (rc == NRB_OK && be_sync(s) != 0) rc = copy_fail("kernel execution");
+    }
+    if (rc) return rc;
+    for (size_t b = 0; b < count; ++b)
+        if (be_d2h(out[b], (char *)t_ctx.out.p + b * bytes, bytes, s) != 0) return copy_fail("device-to-host copy");
+    if (be_sync(s) != 0) return copy_fail("device-to-host copy");
+    return NRB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *nrb_version(void) { return "numrs_b200 0.1.0 (sm_100a)"; }
+const char *nrb_last_error(void) { return get_error().c_str(); }
+int nrb_device_count(void) { return be_device_count(); }
+int nrb_set_device(int device)
+{
+    if (be_set_device(device) != 0) return fail(NRB_ERR_CUDA, std::string("cudaSetDevice failed: ") + be_last_error());
+    return NRB_OK;
+}
+int nrb_shutdown(void)
+{
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (auto &kv : g_plan_cache) if (kv.second->plan.ws) { be_free(kv.second->plan.ws); kv.second->plan.ws = nullptr; }
+    g_plan_cache.clear();
+    t_ctx.io.release(); t_ctx.aux.release(); t_ctx.out.release();
+    if (t_ctx.stream) { be_stream_destroy(t_ctx.stream); t_ctx.stream = nullptr; }
+    release_tables();
+    return NRB_OK;
+}
+int nrb_set_option(const char *name, long value)
+{
+    if (set_tunable(name, value) != 0) return fail(NRB_ERR_INVALID_DIMS, "unknown option");
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (auto &kv : g_plan_cache) if (kv.second->plan.ws) { be_free(kv.second->plan.ws); kv.second->plan.ws = nullptr; }
+    g_plan_cache.clear();
+    return NRB_OK;
+}
+void *nrb_host_alloc(size_t bytes) { return be_host_alloc(bytes); }
+void nrb_host_free(void *p) { if (p) be_host_free(p); }
+
+// ------------------------------------------------------------------ plan API
+int nrb_plan_create(int kind, const size_t *dims, size_t ndim, size_t batch, nrb_plan_t *plan)
+{
+    if (!plan) return fail(NRB_ERR_INVALID_DIMS, "plan pointer is NULL");
+    *plan = nullptr;
+    if (be_device_count() <= 0) return fail(NRB_ERR_CUDA, "no CUDA device available (numrs_b200 has no CPU fallback)");
+    nrb_plan_s *h = new nrb_plan_s();
+    const int rc = build_plan(h->plan, kind, dims, ndim, batch);
+    if (rc != NRB_OK) { delete h; return rc; }
+    *plan = h;
+    return NRB_OK;
+}
+size_t nrb_plan_workspace_bytes(nrb_plan_t plan) { return plan ? plan->plan.ws_elems * sizeof(double2) : 0; }
+int nrb_plan_num_launches(nrb_plan_t plan, int isign)
+{
+    return plan ? (int)plan->plan.prog[isign == 1 ? 0 : 1].steps.size() : 0;
+}
+int nrb_plan_exec(nrb_plan_t plan, double *d_io, double *d_aux, double *d_out, int isign, int arg, void *stream)
+{
+    if (!plan) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
+    return exec_plan(plan->plan, d_io, d_aux, d_out, isign, arg, stream);
+}
+int nrb_plan_destroy(nrb_plan_t plan)
+{
+    if (!plan) return NRB_OK;
+    if (plan->plan.ws) be_free(plan->plan.ws);
+    delete plan;
+    return NRB_OK;
+}
+
+// ------------------------------------------------------------------ slab API
+int nrb_slab_create(size_t nn1, size_t nn2, size_t nn3, int nranks, int rank, nrb_slab_t *plan)
+{
+    if (!plan) return fail(NRB_ERR_INVALID_DIMS, "plan pointer is NULL");
+    *plan = nullptr;
+    if (be_device_count() <= 0) return fail(NRB_ERR_CUDA, "no CUDA device available (numrs_b200 has no CPU fallback)");
+    nrb_slab_s *h = new nrb_slab_s();
+    const int rc = build_slab_plan(h->plan, nn1, nn2, nn3, nranks, rank);
+    if (rc != NRB_OK) { delete h; return rc; }
+    *plan = h;
+    return NRB_OK;
+}
+size_t nrb_slab_local_doubles(nrb_slab_t p) { return p ? p->plan.nn1 * p->plan.nn2 * p->plan.nn3 / (size_t)p->plan.nranks : 0; }
+size_t nrb_slab_speq_doubles(nrb_slab_t p) { return p ? 2 * p->plan.nn1 * p->plan.nn2 / (size_t)p->plan.nranks : 0; }
+size_t nrb_slab_xchg_doubles(nrb_slab_t p)
+{
+    if (!p) return 0;
+    const size_t G = (size_t)p->plan.nranks;
+    return 2 * G * (p->plan.nn1 / G) * (p->plan.nn2 / G) * (p->plan.nn3 / 2 + 1);
+}
+int nrb_slab_stage(nrb_slab_t p, int stage, int isign, double *d_slab, double *d_speq, double *d_send, double *d_recv,
+                   void *stream)
+{
+    if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
+    return exec_slab_stage(p->plan, stage, isign, d_slab, d_speq, d_send, d_recv, stream);
+}
+int nrb_slab_destroy(nrb_slab_t p)
+{
+    if (!p) return NRB_OK;
+    if (p->plan.ws) be_free(p->plan.ws);
+    delete p;
+    return NRB_OK;
+}
+
+// ------------------------------------------------------------------ host-slice entry points
+int nrb_four1(double *data, size_t nn, int isign)
+{
+    double *ptrs[1] = {data};
+    size_t sizes[1] = {nn};
+    return nrb_four1_batch(ptrs, sizes, 1, isign);
+}
+
+int nrb_four1_batch(double *const *ptrs, const size_t *nn, size_t count, int isign)
+{
+    if (isign != 1 && isign != -1) return fail(NRB_ERR_INVALID_ISIGN, "isign must be 1 or -1");
+    if (count == 0) return NRB_OK;
+    if (!ptrs || !nn) return fail(NRB_ERR_EMPTY_INPUT, "null batch");
+    // group slices by length; each group is one batched plan
+    std::map<size_t, std::vector<double *>> groups;
+    for (size_t b = 0; b < count; ++b) {
+        if (nn[b] <= 1) continue;                 // FFT_1.rs:5-44 is the identity for nn <= 1
+        if (!is_pow2(nn[b])) return fail(NRB_ERR_NOT_POW2, "four1: nn must be a power of two");
+        if (!ptrs[b]) return fail(NRB_ERR_EMPTY_INPUT, "null slice");
+        groups[nn[b]].push_back(ptrs[b]);
+    }
+    for (auto &g : groups) {
+        const size_t dims[1] = {g.first};
+        const int rc = run_inplace(NRB_KIND_FOUR1, dims, 1, g.second.data(), g.second.size(), 2 * g.first, isign,
+                                   nullptr, 0);
+        if (rc) return rc;
+    }
+    return NRB_OK;
+}
+
+int nrb_fourn(double *data, const size_t *nn, size_t ndim, int isign)
+{
+    // Fourn.rs:367-378 validation order
+    if (ndim == 0 || !nn) return fail(NRB_ERR_INVALID_DIMS, "Invalid dimensions");
+    if (isign != 1 && isign != -1) return fail(NRB_ERR_INVALID_ISIGN, "isign must be 1 or -1");
+    size_t total = 1;
+    for (size_t d = 0; d < ndim; ++d) {
+        if (nn[d] <= 1) return fail(NRB_ERR_INVALID_DIMS, "Invalid dimension size");
+        total *= nn[d];
+    }
+    if (!data) return fail(NRB_ERR_EMPTY_INPUT, "null data");
+    double *ptrs[1] = {data};
+    return run_inplace(NRB_KIND_FOURN, nn, ndim, ptrs, 1, 2 * total, isign, nullptr, 0);
+}
+
+int nrb_realft(double *data, size_t n, int isign)
+{
+    double *ptrs[1] = {data};
+    return nrb_realft_batch(ptrs, n, 1, isign);
+}
+
+int nrb_realft_batch(double *const *ptrs, size_t n, size_t count, int isign)
+{
+    if (n % 2 != 0) return fail(NRB_ERR_INVALID_DIMS, "n must be even");          // Real_FT.rs:5
+    if (n == 0) return fail(NRB_ERR_EMPTY_INPUT, "data length must be at least n"); // Real_FT.rs:6 / :43
+    if (!is_pow2(n)) return fail(NRB_ERR_NOT_POW2, "realft: n must be a power of two");
+    if (count == 0) return NRB_OK;
+    if (!ptrs) return fail(NRB_ERR_EMPTY_INPUT, "null batch");
+    const size_t dims[1] = {n};
+    // Real_FT.rs:10,15: isign == 1 is forward, anything else inverse
+    return run_inplace(NRB_KIND_REALFT, dims, 1, ptrs, count, n, isign == 1 ? 1 : -1, nullptr, 0);
+}
+
+int nrb_rlft3(double *data, double *speq, size_t nn1, size_t nn2, size_t nn3, int isign)
+{
+    if (isign != 1 && isign != -1) return fail(NRB_ERR_INVALID_ISIGN, "isign must be 1 or -1");   // Real_FT3.rs:17
+    if (nn1 == 0 || nn2 == 0 || nn3 < 2) return fail(NRB_ERR_INVALID_DIMS, "data dimensions mismatch");
+    if (!data || !speq) return fail(NRB_ERR_EMPTY_INPUT, "null data");
+    const size_t dims[3] = {nn1, nn2, nn3};
+    double *ptrs[1] = {data};
+    return run_inplace(NRB_KIND_RLFT3, dims, 3, ptrs, 1, nn1 * nn2 * nn3, isign, speq, 2 * nn1 * nn2);
+}
+
+int nrb_convlv(const double *data, size_t n, const double *respns, size_t m, int isign, int pad_mode, double *ans)
+{
+    const double *in[1] = {data};
+    double *out[1] = {ans};
+    return nrb_convlv_batch(in, 1, n, respns, m, isign, pad_mode, out);
+}
+
+int nrb_convlv_batch(const double *const *data, size_t count, size_t n, const double *respns, size_t m, int isign,
+                     int pad_mode, double *const *ans)
+{
+    // Convolve.rs:13-21 check order
+    if (n == 0 || m == 0) return fail(NRB_ERR_EMPTY_INPUT, "Input arrays cannot be empty");
+    if (m > n) return fail(NRB_ERR_RESPONSE_TOO_LONG, "Response function longer than data");
+    if (isign != 1 && isign != -1) return fail(NRB_ERR_INVALID_ISIGN, "isign must be 1 (convolution) or -1 (deconvolution)");
+    if (n < 2 || !is_pow2(n)) return fail(NRB_ERR_NOT_POW2, "convlv: n must be a power of two >= 2");
+    if (pad_mode != NRB_PAD_LITERAL && pad_mode != NRB_PAD_NR) return fail(NRB_ERR_INVALID_DIMS, "unknown pad_mode");
+    if (count == 0) return NRB_OK;
+    if (!data || !respns || !ans) return fail(NRB_ERR_EMPTY_INPUT, "null pointer");
+    const size_t dims[2] = {n, m};
+    const double *aux[1] = {respns};
+    return run_outofplace(NRB_KIND_CONVLV, dims, 2, data, aux, 1, m, ans, count, n, isign, pad_mode);
+}
+
+int nrb_correl(const double *data1, size_t n1, const double *data2, size_t n2, double *ans)
+{
+    // Correlation.rs:11-16 check order
+    if (n1 == 0) return fail(NRB_ERR_EMPTY_INPUT, "Input arrays cannot be empty");
+    if (n2 != n1) return fail(NRB_ERR_LENGTH_MISMATCH, "Input arrays must have the same length");
+    const double *a[1] = {data1}, *b[1] = {data2};
+    double *o[1] = {ans};
+    return nrb_correl_batch(a, b, 1, n1, o);
+}
+
+int nrb_correl_batch(const double *const *data1, const double *const *data2, size_t count, size_t n, double *const *ans)
+{
+    if (n == 0) return fail(NRB_ERR_EMPTY_INPUT, "Input arrays cannot be empty");
+    if (n > 32 && !is_pow2(n)) return fail(NRB_ERR_NOT_POW2, "correl: n > 32 must be a power of two");
+    if (count == 0) return NRB_OK;
+    if (!data1 || !data2 || !ans) return fail(NRB_ERR_EMPTY_INPUT, "null pointer");
+    const size_t dims[1] = {n};
+    return run_outofplace(NRB_KIND_CORREL, dims, 1, data1, data2, count, n, ans, count, n, 1, 0);
+}
+
+} // extern "C"

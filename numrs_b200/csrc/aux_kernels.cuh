@@ -1,0 +1,136 @@
+// aux_kernels.cuh -- elementwise kernels around the FFT passes (all HBM/L2-bound streaming).
+//   untangle      : standalone NR realft untangling for lines longer than one CTA tile
+//                   (Real_FT.rs:49-80,145-176) and for N == 1
+//   spectral      : packed-spectrum multiply / divide / conj-multiply with the 1/no2 scale
+//                   (Convolve.rs:96,112-129; Correlation.rs:73-74,91-92)
+//   pad_response  : response placement (Convolve.rs:41-63 literal, or NR wrap-around)
+//   correl_direct : linear-lag direct correlation for n <= 32 (Correlation.rs:37-50)
+// Bodies are written grid-stride over a flat item index so the CUDA wrapper and the host
+// emulation used by the tests share them.
+#pragma once
+#include "fft_pass.cuh"
+
+namespace nrb {
+
+NRB_DEV double2 two_level_tw(const double2 *lo, const double2 *hi, int h, u64 m)
+{
+    return cmul(NRB_LDG(lo + (m & ((1ull << h) - 1ull))), NRB_LDG(hi + (m >> h)));
+}
+
+// items: count * max(N/2, 1); item (line, k).  In/out may alias (each pair is owned by one item).
+NRB_DEV void aux_untangle(const AuxParams &A, u64 gtid, u64 gthreads)
+{
+    const u64 N = A.n;
+    const u64 half = N >= 2 ? N / 2 : 1;
+    const u64 items = A.count * half;
+    for (u64 it = gtid; it < items; it += gthreads) {
+        const u64 k = it % half, line = it / half;
+        const double2 *src = A.a + (i64)line * A.a_stride;
+        double2 *dst = A.out + (i64)line * A.out_stride;
+        if (k == 0) {
+            const double2 g0 = src[0];
+            const double2 mid = N >= 2 ? src[N / 2] : make_double2(0.0, 0.0);
+            if (A.dir > 0) {
+                const double f0 = g0.x + g0.y, fn = g0.x - g0.y;
+                if (A.op == REAL_SPEQ) { dst[0] = make_double2(f0, 0.0); A.speq[line] = make_double2(fn, 0.0); }
+                else dst[0] = make_double2(f0, fn);
+            } else {
+                if (A.op == REAL_SPEQ) dst[0] = dc_inverse_speq(g0, A.speq[line]);
+                else dst[0] = make_double2(0.5 * (g0.x + g0.y), 0.5 * (g0.x - g0.y));
+            }
+            if (N >= 2) dst[N / 2] = mid;
+        } else {
+            const double2 a = src[k], b = src[N - k];
+            const double2 t = two_level_tw(A.rtw_lo, A.rtw_hi, A.rtw_h, k);
+            double2 oa, ob;
+            if (A.dir > 0) untangle_pair<1>(a, b, t, oa, ob);
+            else untangle_pair<-1>(a, b, t, oa, ob);
+            dst[k] = oa;
+            dst[N - k] = ob;
+        }
+    }
+}
+
+// packed spectra of real length n: element 0 = (F_0, F_{n/2}) both real, element k = F_k.
+// items: count * n/2.  out may alias a.
+NRB_DEV void aux_spectral(const AuxParams &A, u64 gtid, u64 gthreads)
+{
+    const u64 half = A.n / 2;
+    const u64 items = A.count * half;
+    const double inv = 1.0 / (double)half;      // 1/no2; n is a power of two -> exact
+    for (u64 it = gtid; it < items; it += gthreads) {
+        const u64 k = it % half, sig = it / half;
+        const double2 d = A.a[(i64)sig * A.a_stride + (i64)k];
+        const double2 r = A.b[(i64)sig * A.b_stride + (i64)k];
+        double2 o;
+        if (A.op == SPEC_CONV_MUL) {
+            if (k == 0) o = make_double2(d.x * r.x * inv, d.y * r.y * inv);
+            else o = make_double2((d.x * r.x - d.y * r.y) * inv, (d.x * r.y + d.y * r.x) * inv);
+        } else if (A.op == SPEC_CORREL) {
+            if (k == 0) o = make_double2(d.x * r.x * inv, d.y * r.y * inv);
+            else o = make_double2((d.x * r.x + d.y * r.y) * inv, (d.y * r.x - d.x * r.y) * inv);
+        } else { // SPEC_CONV_DIV, guard mag2 < 1e-12 -> 0 (Convolve.rs:118-122)
+            if (k == 0) {
+                const double m0 = r.x * r.x, m1 = r.y * r.y;
+                o.x = m0 < 1e-12 ? 0.0 : d.x * r.x / m0 * inv;
+                o.y = m1 < 1e-12 ? 0.0 : d.y * r.y / m1 * inv;
+            } else {
+                const double mag2 = r.x * r.x + r.y * r.y;
+                if (mag2 < 1e-12) o = make_double2(0.0, 0.0);
+                else o = make_double2((d.x * r.x + d.y * r.y) / mag2 * inv, (d.y * r.x - d.x * r.y) / mag2 * inv);
+            }
+        }
+        A.out[(i64)sig * A.out_stride + (i64)k] = o;
+    }
+}
+
+// a = response taps (m doubles), out = padded response (n doubles).  items: n.
+NRB_DEV void aux_pad_response(const AuxParams &A, u64 gtid, u64 gthreads)
+{
+    const double *r = reinterpret_cast<const double *>(A.a);
+    double *p = reinterpret_cast<double *>(A.out);
+    const u64 n = A.n, m = A.m;
+    for (u64 i = gtid; i < n; i += gthreads) {
+        double v = 0.0;
+        if (A.op == 0) {
+            const u64 mid = (m - 1) / 2;
+            if (i < mid) v = r[m - mid + i];
+            else if (i < m) v = r[i];
+            else if (i < n - mid) v = 0.0;
+            else v = r[i - (n - mid)];
+        } else {
+            const u64 half = (m - 1) / 2;
+            if (i < (m + 1) / 2) v = r[i];
+            else if (i >= n - half) v = r[m - (n - i)];
+        }
+        p[i] = v;
+    }
+}
+
+// a, b = signals (count x n doubles), out = count x n doubles; n <= 32.  items: count * n (lag).
+NRB_DEV void aux_correl_direct(const AuxParams &A, u64 gtid, u64 gthreads)
+{
+    const double *d1 = reinterpret_cast<const double *>(A.a);
+    const double *d2 = reinterpret_cast<const double *>(A.b);
+    double *out = reinterpret_cast<double *>(A.out);
+    const u64 n = A.n, items = A.count * n;
+    for (u64 it = gtid; it < items; it += gthreads) {
+        const u64 lag = it % n, sig = it / n;
+        const double *x = d1 + (i64)sig * A.a_stride, *y = d2 + (i64)sig * A.b_stride;
+        double sum = 0.0;
+        for (u64 i = 0; i + lag < n; ++i) sum += x[i + lag] * y[i];
+        out[(i64)sig * A.out_stride + (i64)lag] = sum;
+    }
+}
+
+NRB_DEV void aux_body(const AuxParams &A, u64 gtid, u64 gthreads)
+{
+    switch (A.kind) {
+    case AUX_UNTANGLE: aux_untangle(A, gtid, gthreads); break;
+    case AUX_SPECTRAL: aux_spectral(A, gtid, gthreads); break;
+    case AUX_PAD_RESPONSE: aux_pad_response(A, gtid, gthreads); break;
+    default: aux_correl_direct(A, gtid, gthreads); break;
+    }
+}
+
+} // namespace nrb

@@ -1,0 +1,149 @@
+// backend_cuda.cu -- CUDA backend of the planner: kernel dispatch table, the elementwise
+// kernel, memory and stream helpers.  There is deliberately no other backend in the product.
+#include <mutex>
+#include <string>
+
+#include "kernels_inst.cuh"
+
+namespace nrb {
+
+void register_row_a(PassTable &);
+void register_row_b(PassTable &);
+void register_row_c(PassTable &);
+void register_col_a(PassTable &);
+void register_col_b(PassTable &);
+void register_col_c(PassTable &);
+
+PassTable &pass_table()
+{
+    static PassTable t;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        memset(&t, 0, sizeof(t));
+        register_row_a(t); register_row_b(t); register_row_c(t);
+        register_col_a(t); register_col_b(t); register_col_c(t);
+    });
+    return t;
+}
+
+static thread_local std::string g_be_err;
+static int fail(cudaError_t e)
+{
+    g_be_err = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e);
+    return (int)e;
+}
+const char *be_last_error() { return g_be_err.c_str(); }
+
+int be_launch_pass(const KernelKey &key, const PassParams &p, u64 ntiles, void *stream)
+{
+    if (key.log2n < 1 || key.log2n > kMaxLog2N || key.layout < 0 || key.layout > 1 || key.variant < 0 || key.variant > 2) {
+        g_be_err = "no such kernel";
+        return -1;
+    }
+    PassLaunchFn fn = pass_table().fn[key.log2n][key.layout][key.dir > 0 ? 1 : 0][key.variant];
+    if (!fn) { g_be_err = "kernel variant not built"; return -1; }
+    if (ntiles > 0x7fffffffull) { g_be_err = "grid too large"; return -1; }
+    const int rc = fn(p, ntiles, (cudaStream_t)stream);
+    if (rc != 0) return fail((cudaError_t)rc);
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) aux_kernel(const __grid_constant__ AuxParams A)
+{
+    aux_body(A, (u64)blockIdx.x * blockDim.x + threadIdx.x, (u64)gridDim.x * blockDim.x);
+}
+
+int be_launch_aux(const AuxParams &a, void *stream)
+{
+    u64 items = 0;
+    switch (a.kind) {
+    case AUX_UNTANGLE: items = a.count * (a.n >= 2 ? a.n / 2 : 1); break;
+    case AUX_SPECTRAL: items = a.count * (a.n / 2); break;
+    case AUX_PAD_RESPONSE: items = a.n; break;
+    default: items = a.count * a.n; break;
+    }
+    if (items == 0) return 0;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    u64 blocks = (items + 255) / 256;
+    const u64 cap = (u64)sms * 8 * 4;     // grid-stride beyond 4 waves of 8 CTAs/SM
+    if (blocks > cap) blocks = cap;
+    aux_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : fail(e);
+}
+
+int be_malloc(void **p, size_t bytes)
+{
+    cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+    return e == cudaSuccess ? 0 : fail(e);
+}
+int be_free(void *p)
+{
+    cudaError_t e = cudaFree(p);
+    return e == cudaSuccess ? 0 : fail(e);
+}
+int be_h2d(void *dst, const void *src, size_t bytes, void *stream)
+{
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail(e);
+}
+int be_d2h(void *dst, const void *src, size_t bytes, void *stream)
+{
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail(e);
+}
+int be_d2d(void *dst, const void *src, size_t bytes, void *stream)
+{
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail(e);
+}
+int be_sync(void *stream)
+{
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail(e);
+}
+int be_device_count()
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int be_set_device(int dev)
+{
+    cudaError_t e = cudaSetDevice(dev);
+    return e == cudaSuccess ? 0 : fail(e);
+}
+int be_stream_create(void **stream)
+{
+    cudaStream_t s;
+    cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return fail(e);
+    *stream = (void *)s;
+    return 0;
+}
+int be_stream_destroy(void *stream)
+{
+    cudaError_t e = cudaStreamDestroy((cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail(e);
+}
+void *be_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void be_host_free(void *p) { cudaFreeHost(p); }
+int be_current_device()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    return dev;
+}
+
+} // namespace nrb

@@ -1,0 +1,388 @@
+// fft_pass.cuh -- the batched shared-memory Stockham FFT pass (f64, complex interleaved).
+//
+// One CTA transforms a tile of L = TILE/N lines of N = 2^LOG2N points (TILE = 4096 points,
+// 8192 for N = 8192) with TILE/16 threads; every thread owns 16 points per stage, i.e.
+// 16/R radix-R butterflies.  Stockham autosort: stage s reads x[j + r*N/R], multiplies by
+// exp(-2 pi i (j mod Ns) r / (Ns R)), does an R-point DFT and writes
+// y[(j - j mod Ns)*R + (j mod Ns) + r*Ns]; the first stage reads global memory directly
+// and the last one writes it directly, so an NST-stage transform makes NST-1 round trips
+// through shared memory.
+//
+// Two thread/shared-memory layouts:
+//   ROW  lines are contiguous in global memory.  thread -> (j fastest, then line);
+//        smem [line][n + n/8] (one pad element per 8 keeps every Stockham write pattern
+//        of radix 2/4/8/16 stages conflict-free for 16-byte accesses).
+//   COL  consecutive lines are adjacent in global memory (element stride >= #lines).
+//        thread -> (line fastest, then j); smem [n][line]: the 8 threads of a 16-byte
+//        shared-memory phase always touch 8 consecutive elements -> conflict-free with no
+//        padding, and every global access is a run of L*16 bytes.
+//
+// Replaces (reference, /root/reference/src): four1 bit reversal + Danielson-Lanczos stages
+// FFT_1.rs:8-43; the per-dimension loops of NR fourn (call shape Real_FT3.rs:35); the realft
+// untangling loops Real_FT.rs:49-80,145-176 and DC/Nyquist handling :43-45,:133-135; the
+// z-direction part of the rlft3 loop nest Real_FT3.rs:60-127.
+//
+// Direction: the core always computes exp(-2 pi i jk/N).  dir = +1 (the reference's
+// isign = +1, exp(+...)) is obtained by swapping re/im on the way in and out (free: it is a
+// compile-time register renaming).
+#pragma once
+#include "nrb_common.h"
+
+namespace nrb {
+
+// ------------------------------------------------------------------ complex helpers
+NRB_DEV double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+NRB_DEV double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+NRB_DEV double2 cmul(double2 a, double2 b)
+{
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+NRB_DEV double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
+NRB_DEV double2 cswap(double2 a) { return make_double2(a.y, a.x); }
+NRB_DEV double2 mul_mi(double2 a) { return make_double2(a.y, -a.x); }  // a * (-i)
+template <int DIR> NRB_DEV double2 io_swap(double2 a) { return DIR > 0 ? cswap(a) : a; }
+
+// ------------------------------------------------------------------ butterflies (forward, e^{-})
+template <int R> struct Bfly;
+
+template <> struct Bfly<2> {
+    NRB_DEVM static void run(double2 *v)
+    {
+        double2 t = v[0];
+        v[0] = cadd(t, v[1]);
+        v[1] = csub(t, v[1]);
+    }
+};
+
+NRB_DEV void bfly4(double2 &v0, double2 &v1, double2 &v2, double2 &v3)
+{
+    double2 a = cadd(v0, v2), b = csub(v0, v2), c = cadd(v1, v3), d = mul_mi(csub(v1, v3));
+    v0 = cadd(a, c);
+    v1 = cadd(b, d);
+    v2 = csub(a, c);
+    v3 = csub(b, d);
+}
+
+template <> struct Bfly<4> {
+    NRB_DEVM static void run(double2 *v) { bfly4(v[0], v[1], v[2], v[3]); }
+};
+
+template <> struct Bfly<8> {
+    NRB_DEVM static void run(double2 *v)
+    {
+        const double h = 0.70710678118654752440;
+        bfly4(v[0], v[2], v[4], v[6]);   // even: E[k] in v[0],v[2],v[4],v[6]
+        bfly4(v[1], v[3], v[5], v[7]);   // odd : O[k] in v[1],v[3],v[5],v[7]
+        double2 o1 = make_double2((v[3].x + v[3].y) * h, (v[3].y - v[3].x) * h);   // * W8^1
+        double2 o2 = mul_mi(v[5]);                                                 // * W8^2
+        double2 o3 = make_double2((v[7].y - v[7].x) * h, -(v[7].x + v[7].y) * h);  // * W8^3
+        double2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1];
+        v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+        v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+        v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+        v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+    }
+};
+
+template <> struct Bfly<16> {
+    NRB_DEVM static void run(double2 *v)
+    {
+        // n = 4a + b, k = k1 + 4 k2
+        const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173;  // cos/sin(pi/8)
+        const double h = 0.70710678118654752440;
+        // step 1: for each b, DFT4 over a: inputs v[b], v[4+b], v[8+b], v[12+b] -> u_b[k1] in place
+        bfly4(v[0], v[4], v[8], v[12]);
+        bfly4(v[1], v[5], v[9], v[13]);
+        bfly4(v[2], v[6], v[10], v[14]);
+        bfly4(v[3], v[7], v[11], v[15]);
+        // step 2: u_b[k1] *= W16^(b*k1); u_b[k1] sits in v[4*k1 + b]
+        v[5] = cmul(v[5], make_double2(c1, -s1));                                  // W^1
+        v[6] = make_double2((v[6].x + v[6].y) * h, (v[6].y - v[6].x) * h);         // W^2
+        v[7] = cmul(v[7], make_double2(s1, -c1));                                  // W^3
+        v[9] = make_double2((v[9].x + v[9].y) * h, (v[9].y - v[9].x) * h);         // W^2
+        v[10] = mul_mi(v[10]);                                                     // W^4
+        v[11] = make_double2((v[11].y - v[11].x) * h, -(v[11].x + v[11].y) * h);   // W^6
+        v[13] = cmul(v[13], make_double2(s1, -c1));                                // W^3
+        v[14] = make_double2((v[14].y - v[14].x) * h, -(v[14].x + v[14].y) * h);   // W^6
+        v[15] = cmul(v[15], make_double2(-c1, s1));                                // W^9
+        // step 3: for each k1, DFT4 over b: v[4k1+0..3] -> X[k1 + 4 k2] at v[4k1 + k2]
+        bfly4(v[0], v[1], v[2], v[3]);
+        bfly4(v[4], v[5], v[6], v[7]);
+        bfly4(v[8], v[9], v[10], v[11]);
+        bfly4(v[12], v[13], v[14], v[15]);
+        // now v[4k1 + k2] = X[k1 + 4k2]; transpose to natural order v[k1 + 4k2]
+        double2 t;
+        t = v[1];  v[1] = v[4];   v[4] = t;
+        t = v[2];  v[2] = v[8];   v[8] = t;
+        t = v[3];  v[3] = v[12];  v[12] = t;
+        t = v[6];  v[6] = v[9];   v[9] = t;
+        t = v[7];  v[7] = v[13];  v[13] = t;
+        t = v[11]; v[11] = v[14]; v[14] = t;
+    }
+};
+
+// ------------------------------------------------------------------ compile-time geometry
+template <int LOG2N, int LAYOUT, int VARIANT> struct Geo {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int TL = tile_log2(LOG2N);
+    static constexpr int TILE = 1 << TL;
+    static constexpr int L = TILE / N;                 // lines per tile
+    static constexpr int NT = cta_threads(LOG2N);      // threads per CTA
+    static constexpr int PPT = kPointsPerThread;
+    static constexpr int NST = radix_plan(LOG2N).nst;
+    static constexpr int LP = row_line_pitch(LOG2N);   // ROW: line pitch
+    static constexpr int CP = col_pitch(LOG2N, VARIANT); // COL: pitch of one n
+    NRB_DEVM static int phys(int l, int n)
+    {
+        return LAYOUT == LAYOUT_ROW ? l * LP + n + (n >> 3) : n * CP + l;
+    }
+};
+
+NRB_DEV i64 line_base(u64 q, i64 s0, i64 s1, i64 s2, int logA, int logB)
+{
+    const u64 q2 = q & ((1ull << logB) - 1ull);
+    const u64 q1 = (q >> logB) & ((1ull << logA) - 1ull);
+    const u64 q0 = q >> (logA + logB);
+    return (i64)q0 * s0 + (i64)q1 * s1 + (i64)q2 * s2;
+}
+
+NRB_DEV i64 elem_off(int n, i64 es, int eshift, i64 es_hi)
+{
+    return (i64)(n & ((1 << eshift) - 1)) * es + (i64)(n >> eshift) * es_hi;
+}
+
+// four-step twiddle exp(-2 pi i m / M), m = q1 * k, from the two-level table
+NRB_DEV double2 fourstep_tw(const PassParams &P, u64 q, unsigned k)
+{
+    const unsigned q1 = (unsigned)((q >> P.logB) & ((1ull << P.logA) - 1ull));
+    const unsigned m = q1 * k;
+    const double2 lo = NRB_LDG(P.tw_lo + (m & ((1u << P.tw_h) - 1u)));
+    const double2 hi = NRB_LDG(P.tw_hi + (m >> P.tw_h));
+    return cmul(lo, hi);
+}
+
+// ------------------------------------------------------------------ one Stockham stage
+// SRC_G: inputs come from global memory (else shared); DST_G: outputs go to global memory.
+template <int LOG2N, int LAYOUT, int DIR, int VARIANT, int S, bool SRC_G, bool DST_G>
+NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
+{
+    typedef Geo<LOG2N, LAYOUT, VARIANT> G;
+    constexpr int R = radix_plan(LOG2N).r[S];
+    constexpr int NS = stage_ns(LOG2N, S);
+    constexpr int NB = G::N / R;           // butterflies per line
+    constexpr int BPT = G::PPT / R;        // butterflies per thread
+    static_assert(BPT >= 1, "radix larger than points per thread");
+
+    double2 v[BPT][R];
+    int ln[BPT], jj[BPT];
+
+#pragma unroll
+    for (int i = 0; i < BPT; ++i) {
+        const int b = tid + i * G::NT;
+        if (LAYOUT == LAYOUT_COL) { ln[i] = b & (G::L - 1); jj[i] = b / G::L; }
+        else                      { jj[i] = b & (NB - 1);   ln[i] = b / NB; }
+    }
+
+    // ---- gather
+#pragma unroll
+    for (int i = 0; i < BPT; ++i) {
+        if (SRC_G) {
+            const u64 q = P.q_begin + (u64)tile * G::L + (u64)ln[i];
+            const bool ok = q < P.q_end;
+            const double2 *src = P.in + line_base(q, P.in_s0, P.in_s1, P.in_s2, P.logA, P.logB);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                double2 x = make_double2(0.0, 0.0);
+                if (ok) x = src[elem_off(jj[i] + r * NB, P.in_es, P.in_eshift, P.in_es_hi)];
+                v[i][r] = io_swap<DIR>(x);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[i][r] = sm[G::phys(ln[i], jj[i] + r * NB)];
+        }
+    }
+
+    // ---- twiddle + butterfly
+#pragma unroll
+    for (int i = 0; i < BPT; ++i) {
+        if (NS > 1) {
+            const int jm = jj[i] & (NS - 1);
+            const double2 *tp = P.tw + stage_tw_off(LOG2N, S) + jm * (R - 1);
+#pragma unroll
+            for (int r = 1; r < R; ++r) v[i][r] = cmul(v[i][r], NRB_LDG(tp + (r - 1)));
+        }
+        Bfly<R>::run(v[i]);
+    }
+
+    if (!SRC_G && !DST_G) NRB_SYNC();   // everyone has read before anyone overwrites
+
+    // ---- scatter
+#pragma unroll
+    for (int i = 0; i < BPT; ++i) {
+        const int jm = jj[i] & (NS - 1);
+        const int kb = (jj[i] - jm) * R + jm;
+        if (DST_G) {
+            const u64 q = P.q_begin + (u64)tile * G::L + (u64)ln[i];
+            if (q < P.q_end) {
+                double2 *dst = P.out + line_base(q, P.out_s0, P.out_s1, P.out_s2, P.logA, P.logB);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int k = kb + r * NS;
+                    double2 y = v[i][r];
+                    if (P.tw_on) y = cmul(y, fourstep_tw(P, q, (unsigned)k));
+                    dst[elem_off(k, P.out_es, P.out_eshift, P.out_es_hi)] = io_swap<DIR>(y);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) sm[G::phys(ln[i], kb + r * NS)] = v[i][r];
+        }
+    }
+}
+
+// run stages FIRST..NST-1; stage FIRST reads global iff SRC_G0, the last stage writes global
+// iff DST_GL.  Barriers: after every stage that wrote shared memory.
+template <int LOG2N, int LAYOUT, int DIR, int VARIANT, int S, bool SRC_G0, bool DST_GL>
+struct StageRunner {
+    NRB_DEVM static void run(const PassParams &P, double2 *sm, unsigned tile, int tid)
+    {
+        constexpr int NST = radix_plan(LOG2N).nst;
+        constexpr bool last = (S == NST - 1);
+        constexpr bool src_g = (S == 0) && SRC_G0;
+        constexpr bool dst_g = last && DST_GL;
+        fft_stage<LOG2N, LAYOUT, DIR, VARIANT, S, src_g, dst_g>(P, sm, tile, tid);
+        if (!dst_g) NRB_SYNC();
+        StageRunner<LOG2N, LAYOUT, DIR, VARIANT, last ? -1 : S + 1, SRC_G0, DST_GL>::run(P, sm, tile, tid);
+    }
+};
+template <int LOG2N, int LAYOUT, int DIR, int VARIANT, bool SRC_G0, bool DST_GL>
+struct StageRunner<LOG2N, LAYOUT, DIR, VARIANT, -1, SRC_G0, DST_GL> {
+    NRB_DEVM static void run(const PassParams &, double2 *, unsigned, int) {}
+};
+
+// ------------------------------------------------------------------ real untangle (NR realft)
+// Forward (c2 = -0.5, w = exp(+i pi k/N)):  h1 = (Zk + conj Zm)/2, h2 = -(i/2)(Zk - conj Zm),
+//   Fk = h1 + w h2, Fm = conj(h1 - w h2)               [Real_FT.rs:66-74 with 0-based pairs]
+// Inverse (c2 = +0.5, w = exp(-i pi k/N)):  h2 = +(i/2)(Fk - conj Fm), same recombination
+//                                                       [Real_FT.rs:162-170]
+template <int DIR>
+NRB_DEV void untangle_pair(double2 a, double2 b, double2 t /* exp(-i pi k/N) */, double2 &oa, double2 &ob)
+{
+    const double2 w = DIR > 0 ? cconj(t) : t;
+    const double c2 = DIR > 0 ? -0.5 : 0.5;
+    const double h1r = 0.5 * (a.x + b.x), h1i = 0.5 * (a.y - b.y);
+    const double h2r = -c2 * (a.y + b.y), h2i = c2 * (a.x - b.x);
+    const double tr = w.x * h2r - w.y * h2i, ti = w.x * h2i + w.y * h2r;
+    oa = make_double2(h1r + tr, h1i + ti);
+    ob = make_double2(h1r - tr, -h1i + ti);
+}
+
+// DC / Nyquist element.  Forward: Z0 = (a, b) -> F0 = a + b, FN = a - b  (Real_FT.rs:43-45).
+// Inverse packed: (F0, FN) -> Z0 = ((F0+FN)/2, (F0-FN)/2)               (Real_FT.rs:133-135).
+// Inverse speq (rlft3): g0, gN complex planes -> Z0 = [(1+i) g0 + (1-i) conj(gN)] / 2, which
+// is what NR's i3 == 1 branch (Real_FT3.rs:73-87) followed by the x/y transforms amounts to.
+NRB_DEV double2 dc_inverse_speq(double2 g0, double2 gn)
+{
+    return make_double2(0.5 * ((g0.x - g0.y) + (gn.x - gn.y)), 0.5 * ((g0.x + g0.y) - (gn.x + gn.y)));
+}
+
+// ------------------------------------------------------------------ the pass body
+template <int LOG2N, int LAYOUT, int DIR, int VARIANT>
+NRB_DEV void fft_pass_body(const PassParams &P, double2 *sm, unsigned tile, int tid)
+{
+    typedef Geo<LOG2N, LAYOUT, VARIANT> G;
+
+    if (VARIANT == VAR_PLAIN) {
+        StageRunner<LOG2N, LAYOUT, DIR, VARIANT, 0, true, true>::run(P, sm, tile, tid);
+        return;
+    }
+
+    if (VARIANT == VAR_XPOSE) {
+        // COL layout; last stage to shared memory, then row-like (line-contiguous) store
+        StageRunner<LOG2N, LAYOUT, DIR, VARIANT, 0, true, false>::run(P, sm, tile, tid);
+#pragma unroll
+        for (int i = 0; i < G::PPT; ++i) {
+            const int idx = tid + i * G::NT;
+            const int k = idx & (G::N - 1), l = idx >> LOG2N;
+            const u64 q = P.q_begin + (u64)tile * G::L + (u64)l;
+            if (q < P.q_end) {
+                double2 y = sm[G::phys(l, k)];
+                if (P.tw_on) y = cmul(y, fourstep_tw(P, q, (unsigned)k));
+                double2 *dst = P.out + line_base(q, P.out_s0, P.out_s1, P.out_s2, P.logA, P.logB);
+                dst[(i64)k * P.out_es] = io_swap<DIR>(y);
+            }
+        }
+        return;
+    }
+
+    if (VARIANT == VAR_REAL) {
+        constexpr int HALF = G::N / 2;   // pair items per line (k = 0 handles DC, Nyquist, middle)
+        constexpr int ITEMS = (G::L * HALF + G::NT - 1) / G::NT;
+        if (DIR > 0) {
+            // c2c (swapped domain) -> shared memory -> untangle -> global
+            StageRunner<LOG2N, LAYOUT, DIR, VARIANT, 0, true, false>::run(P, sm, tile, tid);
+#pragma unroll 4
+            for (int i = 0; i < ITEMS; ++i) {
+                const int idx = tid + i * G::NT;
+                if (idx >= G::L * HALF) break;
+                const int k = idx & (HALF - 1), l = idx / HALF;
+                const u64 q = P.q_begin + (u64)tile * G::L + (u64)l;
+                if (q >= P.q_end) continue;
+                double2 *dst = P.out + line_base(q, P.out_s0, P.out_s1, P.out_s2, P.logA, P.logB);
+                if (k == 0) {
+                    const double2 z0 = cswap(sm[G::phys(l, 0)]);
+                    const double f0 = z0.x + z0.y, fn = z0.x - z0.y;
+                    if (P.real_mode == REAL_SPEQ) {
+                        dst[0] = make_double2(f0, 0.0);
+                        P.speq[q] = make_double2(fn, 0.0);
+                    } else {
+                        dst[0] = make_double2(f0, fn);
+                    }
+                    if (HALF >= 1 && G::N >= 2) dst[(i64)HALF * P.out_es] = cswap(sm[G::phys(l, HALF)]);
+                } else {
+                    const double2 a = cswap(sm[G::phys(l, k)]), b = cswap(sm[G::phys(l, G::N - k)]);
+                    double2 oa, ob;
+                    untangle_pair<DIR>(a, b, NRB_LDG(P.rtw + k), oa, ob);
+                    dst[(i64)k * P.out_es] = oa;
+                    dst[(i64)(G::N - k) * P.out_es] = ob;
+                }
+            }
+        } else {
+            // global -> untangle -> shared memory -> c2c -> global
+#pragma unroll 4
+            for (int i = 0; i < ITEMS; ++i) {
+                const int idx = tid + i * G::NT;
+                if (idx >= G::L * HALF) break;
+                const int k = idx & (HALF - 1), l = idx / HALF;
+                const u64 q = P.q_begin + (u64)tile * G::L + (u64)l;
+                const bool ok = q < P.q_end;
+                const double2 *src = P.in + line_base(q, P.in_s0, P.in_s1, P.in_s2, P.logA, P.logB);
+                const double2 zero = make_double2(0.0, 0.0);
+                if (k == 0) {
+                    double2 z0 = zero, zm = zero;
+                    if (ok) {
+                        const double2 g0 = src[0];
+                        if (P.real_mode == REAL_SPEQ) z0 = dc_inverse_speq(g0, P.speq[q]);
+                        else z0 = make_double2(0.5 * (g0.x + g0.y), 0.5 * (g0.x - g0.y));
+                        if (G::N >= 2) zm = src[(i64)HALF * P.in_es];
+                    }
+                    sm[G::phys(l, 0)] = z0;
+                    if (G::N >= 2) sm[G::phys(l, HALF)] = zm;
+                } else {
+                    double2 oa = zero, ob = zero;
+                    if (ok) {
+                        const double2 a = src[(i64)k * P.in_es], b = src[(i64)(G::N - k) * P.in_es];
+                        untangle_pair<DIR>(a, b, NRB_LDG(P.rtw + k), oa, ob);
+                    }
+                    sm[G::phys(l, k)] = oa;
+                    sm[G::phys(l, G::N - k)] = ob;
+                }
+            }
+            NRB_SYNC();
+            StageRunner<LOG2N, LAYOUT, DIR, VARIANT, 0, false, true>::run(P, sm, tile, tid);
+        }
+        return;
+    }
+}
+
+} // namespace nrb

@@ -1,0 +1,178 @@
+// nrb_common.h -- shared definitions for the numrs_b200 device code and host planner.
+//
+// The device code in fft_pass.cuh / aux_kernels.cuh is written against a tiny portability
+// layer (NRB_DEV, NRB_SYNC, NRB_LDG, double2) so the very same source can also be compiled
+// with g++ under -DNRB_EMU, where a CTA is emulated by a pool of host threads.  The emulation
+// exists only so that tests/ can validate the index arithmetic of every kernel in a container
+// without a GPU; it is never built into libnumrs_b200.so and the product has no CPU path.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(NRB_EMU)
+struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
+namespace nrb_emu { void barrier(); }
+#define NRB_DEV inline
+#define NRB_DEVM inline
+#define NRB_HD inline
+#define NRB_SYNC() nrb_emu::barrier()
+#define NRB_LDG(p) (*(p))
+#else
+#include <cuda_runtime.h>
+#define NRB_DEV __device__ __forceinline__
+#define NRB_DEVM __device__ __forceinline__
+#define NRB_HD __host__ __device__ __forceinline__
+#define NRB_SYNC() __syncthreads()
+#define NRB_LDG(p) __ldg(p)
+#endif
+
+namespace nrb {
+
+typedef long long i64;
+typedef unsigned long long u64;
+
+// ---- kernel selection keys ----
+enum Layout { LAYOUT_ROW = 0, LAYOUT_COL = 1 };
+// PLAIN: first stage loads from global, last stage stores to global (both fused).
+// REAL : ROW only. dir=+1: c2c then real untangle (post) ; dir=-1: untangle (pre) then c2c.
+// XPOSE: COL only. last stage goes through shared memory and is stored row-like
+//        (each line contiguous), with the four-step twiddle applied on the way out.
+enum Variant { VAR_PLAIN = 0, VAR_REAL = 1, VAR_XPOSE = 2 };
+
+enum RealMode { REAL_NONE = 0, REAL_PACKED = 1, REAL_SPEQ = 2 };
+
+constexpr int kMaxLog2N = 13;       // longest line one CTA transforms in shared memory
+constexpr int kPointsPerThread = 16;
+
+// ---- radix plan per log2(N): stage radices, first stage first ----
+constexpr int kMaxStages = 5;
+struct RadixPlan { int nst; int r[kMaxStages]; };
+
+#ifndef NRB_RADIX16
+#define NRB_RADIX16 0
+#endif
+
+NRB_HD constexpr RadixPlan radix_plan(int log2n)
+{
+#if NRB_RADIX16
+    return log2n == 1 ? RadixPlan{1, {2, 1, 1, 1, 1}}
+         : log2n == 2 ? RadixPlan{1, {4, 1, 1, 1, 1}}
+         : log2n == 3 ? RadixPlan{1, {8, 1, 1, 1, 1}}
+         : log2n == 4 ? RadixPlan{1, {16, 1, 1, 1, 1}}
+         : log2n == 5 ? RadixPlan{2, {4, 8, 1, 1, 1}}
+         : log2n == 6 ? RadixPlan{2, {8, 8, 1, 1, 1}}
+         : log2n == 7 ? RadixPlan{2, {8, 16, 1, 1, 1}}
+         : log2n == 8 ? RadixPlan{2, {16, 16, 1, 1, 1}}
+         : log2n == 9 ? RadixPlan{3, {8, 8, 8, 1, 1}}
+         : log2n == 10 ? RadixPlan{3, {8, 8, 16, 1, 1}}
+         : log2n == 11 ? RadixPlan{3, {8, 16, 16, 1, 1}}
+         : log2n == 12 ? RadixPlan{3, {16, 16, 16, 1, 1}}
+         : RadixPlan{4, {8, 8, 8, 16, 1}};
+#else
+    return log2n == 1 ? RadixPlan{1, {2, 1, 1, 1, 1}}
+         : log2n == 2 ? RadixPlan{1, {4, 1, 1, 1, 1}}
+         : log2n == 3 ? RadixPlan{1, {8, 1, 1, 1, 1}}
+         : log2n == 4 ? RadixPlan{2, {2, 8, 1, 1, 1}}
+         : log2n == 5 ? RadixPlan{2, {4, 8, 1, 1, 1}}
+         : log2n == 6 ? RadixPlan{2, {8, 8, 1, 1, 1}}
+         : log2n == 7 ? RadixPlan{3, {2, 8, 8, 1, 1}}
+         : log2n == 8 ? RadixPlan{3, {4, 8, 8, 1, 1}}
+         : log2n == 9 ? RadixPlan{3, {8, 8, 8, 1, 1}}
+         : log2n == 10 ? RadixPlan{4, {2, 8, 8, 8, 1}}
+         : log2n == 11 ? RadixPlan{4, {4, 8, 8, 8, 1}}
+         : log2n == 12 ? RadixPlan{4, {8, 8, 8, 8, 1}}
+         : RadixPlan{5, {2, 8, 8, 8, 8}};
+#endif
+}
+
+// Ns of stage s = product of the radices of the stages before it
+NRB_HD constexpr int stage_ns(int log2n, int s)
+{
+    int ns = 1;
+    for (int t = 0; t < s; ++t) ns *= radix_plan(log2n).r[t];
+    return ns;
+}
+// offset (in double2) of stage s inside the packed per-size stage-twiddle table:
+// stage t >= 1 stores Ns(t) * (R(t)-1) entries, entry [jm*(R-1) + (r-1)] = exp(-2 pi i jm r / (Ns R))
+NRB_HD constexpr int stage_tw_off(int log2n, int s)
+{
+    int off = 0;
+    for (int t = 1; t < s; ++t) off += stage_ns(log2n, t) * (radix_plan(log2n).r[t] - 1);
+    return off;
+}
+NRB_HD constexpr int stage_tw_total(int log2n)
+{
+    return stage_tw_off(log2n, radix_plan(log2n).nst);
+}
+
+// tile geometry: a CTA transforms L = TILE/N lines of N points
+NRB_HD constexpr int tile_log2(int log2n) { return log2n > 12 ? log2n : 12; }
+NRB_HD constexpr int cta_threads(int log2n) { return (1 << tile_log2(log2n)) / kPointsPerThread; }
+
+// shared-memory footprint in double2 elements
+NRB_HD constexpr int row_line_pitch(int log2n) { return (1 << log2n) + ((1 << log2n) >> 3); }
+NRB_HD constexpr int col_line_count(int log2n) { return (1 << tile_log2(log2n)) >> log2n; }
+NRB_HD constexpr int col_pitch(int log2n, int variant)
+{
+    return col_line_count(log2n) + ((variant == VAR_XPOSE && col_line_count(log2n) > 1) ? 1 : 0);
+}
+NRB_HD constexpr size_t smem_elems(int log2n, int layout, int variant)
+{
+    return layout == LAYOUT_ROW
+               ? (size_t)col_line_count(log2n) * (size_t)row_line_pitch(log2n)
+               : (size_t)(1 << log2n) * (size_t)col_pitch(log2n, variant);
+}
+
+// ---- parameters of one FFT pass (one kernel launch) ----
+// A pass transforms lines q in [q_begin, q_end).  Line q decomposes as
+//   q2 = q & (2^logB - 1), q1 = (q >> logB) & (2^logA - 1), q0 = q >> (logA + logB)
+// and its element n lives at  base + q0*s0 + q1*s1 + q2*s2 + n*es  (units: complex elements).
+struct PassParams {
+    const double2 *in;
+    double2 *out;
+    const double2 *tw;      // packed stage twiddles of this log2n
+    const double2 *tw_lo;   // four-step twiddle, exp(-2 pi i m / M): low / high tables
+    const double2 *tw_hi;
+    const double2 *rtw;     // VAR_REAL: exp(-i pi k / N), k < max(N/2, 1)
+    double2 *speq;          // VAR_REAL + REAL_SPEQ: Nyquist plane, element q
+    i64 in_s0, in_s1, in_s2, in_es;
+    i64 out_s0, out_s1, out_s2, out_es;
+    // two-level element index (slab exchange layouts): element n sits at
+    //   (n & (2^eshift - 1)) * es + (n >> eshift) * es_hi ; eshift = 31 disables the split
+    i64 in_es_hi, out_es_hi;
+    int in_eshift, out_eshift;
+    u64 q_begin, q_end;
+    int logA, logB;
+    int tw_on;              // multiply output k of line q by exp(-/+ 2 pi i q1 k / M)
+    int tw_h;               // m = (hi << tw_h) | lo
+    int real_mode;
+};
+
+// ---- elementwise kernels ----
+enum AuxKind {
+    AUX_UNTANGLE = 0,     // standalone real untangle (large lines / N == 1)
+    AUX_SPECTRAL = 1,     // convlv multiply / divide, correl conj-multiply on packed spectra
+    AUX_PAD_RESPONSE = 2, // Convolve.rs:41-63 response placement
+    AUX_CORREL_DIRECT = 3 // Correlation.rs:37-50, n <= 32
+};
+enum SpectralOp { SPEC_CONV_MUL = 0, SPEC_CONV_DIV = 1, SPEC_CORREL = 2 };
+
+struct AuxParams {
+    int kind;
+    int op;               // SpectralOp / pad_mode / real_mode
+    int dir;              // untangle: +1 forward (post), -1 inverse (pre)
+    const double2 *a;     // primary input
+    const double2 *b;     // second operand
+    double2 *out;
+    double2 *speq;
+    const double2 *rtw_lo; // untangle twiddle exp(-i pi k / N) two-level tables
+    const double2 *rtw_hi;
+    int rtw_h;
+    u64 n;                // untangle: complex line length N ; spectral: real length n ; pad: n
+    u64 m;                // pad: taps
+    u64 count;            // lines / signals
+    i64 a_stride, b_stride, out_stride; // per line / signal, in complex elements (doubles for pad/direct)
+};
+
+} // namespace nrb

@@ -1,0 +1,704 @@
+// plan.cpp -- host planner for the numrs_b200 FFT hot path (see plan.h).
+//
+// Every transform is expressed as a sequence of launches of one generic kernel family
+// (fft_pass.cuh) plus a few elementwise kernels (aux_kernels.cuh):
+//   * an FFT along one axis of a row-major view [outer][N][inner] is one pass when N fits a CTA
+//     tile, otherwise a multi-step ("four-step") decomposition N = F1*F2*..: pass t transforms
+//     the F_t-long sub-axis, multiplies by exp(-+2 pi i n_rest k / N_cur) and stores
+//     transposed, so the remaining sub-axis becomes an ordinary strided axis again;
+//   * real transforms (realft, the z axis of rlft3) are a c2c pass with NR's untangling fused
+//     in (VAR_REAL), or c2c passes + a standalone untangle kernel for lines longer than a tile;
+//   * rlft3 is evaluated separably (z real pass, then y and x complex passes on data and on
+//     the speq plane), which is algebraically identical to NR's "fourn then untangle"
+//     (Real_FT3.rs:31-127) because the untangling is linear and the mirror in (i1,i2) commutes
+//     with the y/x transforms.  z and y passes run on groups of x-planes sized to stay
+//     L2-resident so the pair costs one HBM round trip.
+#include "plan.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+
+#include "../../include/numrs_b200.h"
+
+namespace nrb {
+
+// ------------------------------------------------------------------ errors / tunables
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+const std::string &get_error() { return g_err; }
+
+static int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+static Tunables &tunables_mut()
+{
+    static Tunables t = [] {
+        Tunables x;
+        x.col_max_log2 = env_int("NRB_COL_MAX_LOG2", 10);
+        x.row_max_log2 = env_int("NRB_ROW_MAX_LOG2", 13);
+        x.l2_group_bytes = (u64)env_int("NRB_L2_GROUP_MB", 32) << 20;
+        return x;
+    }();
+    if (t.col_max_log2 < 1) t.col_max_log2 = 1;
+    if (t.col_max_log2 > 12) t.col_max_log2 = 12;
+    if (t.row_max_log2 < 1) t.row_max_log2 = 1;
+    if (t.row_max_log2 > kMaxLog2N) t.row_max_log2 = kMaxLog2N;
+    if (t.l2_group_bytes < 1024) t.l2_group_bytes = 1024;
+    return t;
+}
+const Tunables &tunables() { return tunables_mut(); }
+
+int set_tunable(const char *name, long value)
+{
+    Tunables &t = tunables_mut();
+    const std::string n(name ? name : "");
+    if (n == "col_max_log2") t.col_max_log2 = (int)value;
+    else if (n == "row_max_log2") t.row_max_log2 = (int)value;
+    else if (n == "l2_group_bytes") t.l2_group_bytes = (u64)value;
+    else return -1;
+    tunables_mut();   // re-clamp
+    return 0;
+}
+
+// ------------------------------------------------------------------ twiddle tables
+namespace {
+struct TableKey {
+    int dev, kind, log;
+    bool operator<(const TableKey &o) const
+    {
+        if (dev != o.dev) return dev < o.dev;
+        if (kind != o.kind) return kind < o.kind;
+        return log < o.log;
+    }
+};
+std::mutex g_tab_mu;
+std::map<TableKey, void *> g_tables;
+
+// exp(-2 pi i num / den) with long double trigonometry
+double2 unit_root(u64 num, u64 den)
+{
+    const long double pi2 = 6.283185307179586476925286766559005768L;
+    // reduce to the first octant for accuracy
+    num %= den;
+    const long double a = pi2 * (long double)num / (long double)den;
+    double2 r;
+    r.x = (double)cosl(a);
+    r.y = (double)(-sinl(a));
+    // exact values on the axes
+    if (num == 0) { r.x = 1.0; r.y = 0.0; }
+    else if (num * 4 == den) { r.x = 0.0; r.y = -1.0; }
+    else if (num * 2 == den) { r.x = -1.0; r.y = 0.0; }
+    else if (num * 4 == den * 3) { r.x = 0.0; r.y = 1.0; }
+    return r;
+}
+
+const void *get_table(int kind, int log, std::vector<double2> (*gen)(int))
+{
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    TableKey key{be_current_device(), kind, log};
+    auto it = g_tables.find(key);
+    if (it != g_tables.end()) return it->second;
+    std::vector<double2> host = gen(log);
+    if (host.empty()) host.push_back(unit_root(0, 1));
+    void *d = nullptr;
+    if (be_malloc(&d, host.size() * sizeof(double2)) != 0) return nullptr;
+    if (be_h2d(d, host.data(), host.size() * sizeof(double2), nullptr) != 0 || be_sync(nullptr) != 0) return nullptr;
+    g_tables[key] = d;
+    return d;
+}
+
+std::vector<double2> gen_stage(int log2n)
+{
+    const RadixPlan rp = radix_plan(log2n);
+    std::vector<double2> t((size_t)stage_tw_total(log2n));
+    for (int s = 1; s < rp.nst; ++s) {
+        const int R = rp.r[s], NS = stage_ns(log2n, s), off = stage_tw_off(log2n, s);
+        for (int jm = 0; jm < NS; ++jm)
+            for (int r = 1; r < R; ++r)
+                t[(size_t)off + (size_t)jm * (R - 1) + (r - 1)] = unit_root((u64)jm * r, (u64)NS * R);
+    }
+    return t;
+}
+int fourstep_h(int log2m) { return (log2m + 1) / 2; }
+std::vector<double2> gen_fs_lo(int log2m)
+{
+    const int h = fourstep_h(log2m);
+    std::vector<double2> t((size_t)1 << h);
+    for (u64 i = 0; i < t.size(); ++i) t[i] = unit_root(i, 1ull << log2m);
+    return t;
+}
+std::vector<double2> gen_fs_hi(int log2m)
+{
+    const int h = fourstep_h(log2m);
+    std::vector<double2> t((size_t)1 << (log2m - h));
+    for (u64 i = 0; i < t.size(); ++i) t[i] = unit_root(i << h, 1ull << log2m);
+    return t;
+}
+std::vector<double2> gen_real(int log2n)
+{
+    const u64 N = 1ull << log2n;
+    std::vector<double2> t((size_t)(N >= 2 ? N / 2 : 1));
+    for (u64 k = 0; k < t.size(); ++k) t[k] = unit_root(k, 2 * N);
+    return t;
+}
+} // namespace
+
+const double2 *stage_twiddles(int log2n) { return (const double2 *)get_table(0, log2n, gen_stage); }
+FourStepTable fourstep_table(int log2m)
+{
+    FourStepTable f;
+    f.lo = (const double2 *)get_table(1, log2m, gen_fs_lo);
+    f.hi = (const double2 *)get_table(2, log2m, gen_fs_hi);
+    f.h = fourstep_h(log2m);
+    return f;
+}
+const double2 *real_twiddles(int log2n) { return (const double2 *)get_table(3, log2n, gen_real); }
+
+void release_tables()
+{
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    for (auto &kv : g_tables) be_free(kv.second);
+    g_tables.clear();
+}
+
+// ------------------------------------------------------------------ program builder
+namespace {
+
+struct AxisMap {        // custom addressing for one side of a single-pass axis
+    bool on;
+    i64 s0;             // stride of the outer index
+    i64 es;             // stride of the low part of the element index
+    int eshift;         // element index split
+    i64 es_hi;          // stride of the high part
+    AxisMap() : on(false), s0(0), es(0), eshift(30), es_hi(0) {}
+};
+
+struct Builder {
+    Program *prog;
+    size_t ws_used;     // workspace high-water mark (complex elements)
+    int rc;
+    explicit Builder(Program *p) : prog(p), ws_used(0), rc(NRB_OK) {}
+    void need_ws(size_t end) { if (end > ws_used) ws_used = end; }
+};
+
+void init_pass(PassParams &pp)
+{
+    memset(&pp, 0, sizeof(pp));
+    pp.in_eshift = 30;
+    pp.out_eshift = 30;
+    pp.logA = 0;
+    pp.logB = 40;
+}
+
+u64 tiles_for(int log2n, u64 lines)
+{
+    const u64 L = (u64)col_line_count(log2n);
+    return (lines + L - 1) / L;
+}
+
+// split log2(N) into per-pass factors
+std::vector<int> choose_factors(int p, u64 inner)
+{
+    const Tunables &T = tunables();
+    std::vector<int> f;
+    const int single_max = (inner == 1) ? T.row_max_log2 : T.col_max_log2;
+    if (p <= single_max) { f.push_back(p); return f; }
+    const int cm = T.col_max_log2;
+    const int m = (p + cm - 1) / cm;
+    const int base = p / m, rem = p % m;
+    for (int i = 0; i < m; ++i) f.push_back(base + (i < rem ? 1 : 0));
+    return f;
+}
+
+// complex FFT of length 2^p along the middle axis of the view [outer][2^p][inner] living in
+// `src`, result in `dst` (same layout; src may equal dst).  Only outer indices
+// [o_begin, o_end) are processed.  `tmp` is scratch for multi-step axes (must not alias).
+void emit_axis(Builder &B, BufRef src, BufRef dst, BufRef tmp, u64 outer, u64 o_begin, u64 o_end, int p,
+               u64 inner, int dir, const AxisMap *in_map = nullptr, const AxisMap *out_map = nullptr)
+{
+    (void)outer;
+    if (p == 0 || o_begin >= o_end) return;
+    const u64 N = 1ull << p;
+    const std::vector<int> fac = choose_factors(p, inner);
+    const int m = (int)fac.size();
+    const int logI = ilog2((size_t)inner);
+
+    if (m == 1) {
+        Step st;
+        init_pass(st.pp);
+        PassParams &pp = st.pp;
+        if (inner == 1) {
+            st.key = KernelKey{p, LAYOUT_ROW, dir, VAR_PLAIN};
+            pp.q_begin = o_begin; pp.q_end = o_end;
+            pp.logA = 0; pp.logB = 40;
+            pp.in_s2 = (i64)N; pp.in_es = 1;
+            pp.out_s2 = (i64)N; pp.out_es = 1;
+        } else {
+            st.key = KernelKey{p, LAYOUT_COL, dir, VAR_PLAIN};
+            pp.q_begin = o_begin * inner; pp.q_end = o_end * inner;
+            pp.logA = 0; pp.logB = logI;
+            pp.in_s0 = (i64)(N * inner); pp.in_s2 = 1; pp.in_es = (i64)inner;
+            pp.out_s0 = (i64)(N * inner); pp.out_s2 = 1; pp.out_es = (i64)inner;
+        }
+        if (in_map && in_map->on) {
+            if (inner == 1) pp.in_s2 = in_map->s0; else pp.in_s0 = in_map->s0;
+            pp.in_es = in_map->es; pp.in_eshift = in_map->eshift; pp.in_es_hi = in_map->es_hi;
+        }
+        if (out_map && out_map->on) {
+            if (inner == 1) pp.out_s2 = out_map->s0; else pp.out_s0 = out_map->s0;
+            pp.out_es = out_map->es; pp.out_eshift = out_map->eshift; pp.out_es_hi = out_map->es_hi;
+        }
+        pp.tw = stage_twiddles(p);
+        st.in = src; st.out = dst;
+        st.ntiles = tiles_for(p, pp.q_end - pp.q_begin);
+        B.prog->steps.push_back(st);
+        return;
+    }
+
+    if ((in_map && in_map->on) || (out_map && out_map->on)) { B.rc = NRB_ERR_UNSUPPORTED; return; }
+
+    // multi-step: transposing passes 0..m-2, then a final strided pass
+    const u64 seg = N * inner;                       // elements per outer index
+    B.need_ws((size_t)(tmp.off + (i64)(o_end * seg)));  // tmp mirrors the layout of src/dst
+    int pcur = p;
+    u64 inn = inner;
+    BufRef cur = src;
+    for (int t = 0; t < m - 1; ++t) {
+        const int f = fac[t];
+        const u64 F = 1ull << f, rest = 1ull << (pcur - f);
+        const BufRef nxt = (t % 2 == 0) ? tmp : dst;
+        Step st;
+        init_pass(st.pp);
+        PassParams &pp = st.pp;
+        const bool xpose = (inn == 1);
+        st.key = KernelKey{f, LAYOUT_COL, dir, xpose ? VAR_XPOSE : VAR_PLAIN};
+        pp.logB = ilog2((size_t)inn);
+        pp.logA = pcur - f;
+        pp.q_begin = o_begin * rest * inn; pp.q_end = o_end * rest * inn;
+        pp.in_s0 = (i64)seg; pp.in_s1 = (i64)inn; pp.in_s2 = 1; pp.in_es = (i64)(rest * inn);
+        pp.out_s0 = (i64)seg; pp.out_s1 = (i64)(F * inn); pp.out_s2 = 1; pp.out_es = (i64)inn;
+        const FourStepTable fs = fourstep_table(pcur);
+        pp.tw_on = 1; pp.tw_lo = fs.lo; pp.tw_hi = fs.hi; pp.tw_h = fs.h;
+        pp.tw = stage_twiddles(f);
+        st.in = cur; st.out = nxt;
+        st.ntiles = tiles_for(f, pp.q_end - pp.q_begin);
+        B.prog->steps.push_back(st);
+        cur = nxt;
+        pcur -= f;
+        inn *= F;
+    }
+    {
+        Step st;
+        init_pass(st.pp);
+        PassParams &pp = st.pp;
+        st.key = KernelKey{pcur, LAYOUT_COL, dir, VAR_PLAIN};
+        const u64 Nl = 1ull << pcur;
+        pp.logA = 0; pp.logB = ilog2((size_t)inn);
+        // view [outer * (N / Nl / ... )]: after the transposes the layout is [o][Nl][inn] with inn = seg / Nl
+        pp.q_begin = o_begin * inn; pp.q_end = o_end * inn;
+        pp.in_s0 = (i64)seg; pp.in_s2 = 1; pp.in_es = (i64)inn;
+        pp.out_s0 = (i64)seg; pp.out_s2 = 1; pp.out_es = (i64)inn;
+        (void)Nl;
+        pp.tw = stage_twiddles(pcur);
+        st.in = cur; st.out = dst;
+        st.ntiles = tiles_for(pcur, pp.q_end - pp.q_begin);
+        B.prog->steps.push_back(st);
+    }
+}
+
+// real transform of `lines` lines of n = 2N real points (N = 2^p complex), line l at
+// src + l*N.  dir=+1: forward (NR realft isign=1), dir=-1: inverse.  real_mode selects where
+// the Nyquist bin lives (packed into element 0, or the speq plane).
+void emit_real(Builder &B, BufRef src, BufRef dst, BufRef tmp, u64 l_begin, u64 l_end, int p, int dir,
+               int real_mode, BufRef speq)
+{
+    if (l_begin >= l_end) return;
+    const u64 N = 1ull << p;
+    if (p >= 1 && p <= tunables().row_max_log2) {
+        Step st;
+        init_pass(st.pp);
+        PassParams &pp = st.pp;
+        st.key = KernelKey{p, LAYOUT_ROW, dir, VAR_REAL};
+        pp.q_begin = l_begin; pp.q_end = l_end;
+        pp.logA = 0; pp.logB = 40;
+        pp.in_s2 = (i64)N; pp.in_es = 1;
+        pp.out_s2 = (i64)N; pp.out_es = 1;
+        pp.tw = stage_twiddles(p);
+        pp.rtw = real_twiddles(p);
+        pp.real_mode = real_mode;
+        st.in = src; st.out = dst; st.speq = speq;
+        st.ntiles = tiles_for(p, l_end - l_begin);
+        B.prog->steps.push_back(st);
+        return;
+    }
+    // standalone untangle (+ c2c passes when N > 1)
+    Step un;
+    un.is_aux = true;
+    memset(&un.ap, 0, sizeof(un.ap));
+    un.ap.kind = AUX_UNTANGLE;
+    un.ap.op = real_mode;
+    un.ap.dir = dir;
+    un.ap.n = N;
+    un.ap.count = l_end - l_begin;
+    un.ap.a_stride = un.ap.out_stride = (i64)N;
+    const FourStepTable rt = fourstep_table(p + 1);   // exp(-2 pi i k / 2N) = exp(-i pi k / N)
+    un.ap.rtw_lo = rt.lo; un.ap.rtw_hi = rt.hi; un.ap.rtw_h = rt.h;
+    un.speq = (speq.id == BUF_NONE) ? speq : speq + (i64)l_begin;
+    if (dir > 0) {
+        emit_axis(B, src, dst, tmp, l_end, l_begin, l_end, p, 1, +1);
+        un.in = (p == 0 ? src : dst) + (i64)(l_begin * N);
+        un.out = dst + (i64)(l_begin * N);
+        B.prog->steps.push_back(un);
+    } else {
+        un.in = src + (i64)(l_begin * N);
+        un.out = dst + (i64)(l_begin * N);
+        B.prog->steps.push_back(un);
+        emit_axis(B, dst, dst, tmp, l_end, l_begin, l_end, p, 1, -1);
+    }
+}
+
+Step make_spectral(int op, BufRef a, BufRef b, BufRef out, u64 n, u64 count, i64 a_stride, i64 b_stride,
+                   i64 out_stride)
+{
+    Step st;
+    st.is_aux = true;
+    memset(&st.ap, 0, sizeof(st.ap));
+    st.ap.kind = AUX_SPECTRAL;
+    st.ap.op = op;
+    st.ap.n = n;
+    st.ap.count = count;
+    st.ap.a_stride = a_stride; st.ap.b_stride = b_stride; st.ap.out_stride = out_stride;
+    st.in = a; st.b = b; st.out = out;
+    return st;
+}
+
+int check_pow2_dims(const size_t *dims, size_t ndim)
+{
+    for (size_t d = 0; d < ndim; ++d)
+        if (!is_pow2(dims[d])) { set_error("dimension is not a power of two"); return NRB_ERR_NOT_POW2; }
+    return NRB_OK;
+}
+
+// ---- per-kind program construction ----
+int build_four1(Plan &pl, Builder &B, int dir)
+{
+    const int p = ilog2(pl.dims[0]);
+    emit_axis(B, BufRef(BUF_IO, 0), BufRef(BUF_IO, 0), BufRef(BUF_WS, 0), pl.batch, 0, pl.batch, p, 1, dir);
+    return B.rc;
+}
+
+int build_fourn(Plan &pl, Builder &B, int dir)
+{
+    const size_t nd = pl.dims.size();
+    u64 total = 1;
+    for (size_t d = 0; d < nd; ++d) total *= pl.dims[d];
+    u64 inner = 1;
+    for (size_t dd = nd; dd-- > 0;) {
+        const u64 N = pl.dims[dd];
+        const u64 outer = pl.batch * (total / (N * inner));
+        emit_axis(B, BufRef(BUF_IO, 0), BufRef(BUF_IO, 0), BufRef(BUF_WS, 0), outer, 0, outer, ilog2((size_t)N),
+                  inner, dir);
+        inner *= N;
+    }
+    return B.rc;
+}
+
+int build_realft(Plan &pl, Builder &B, int dir)
+{
+    const int p = ilog2(pl.dims[0]) - 1;
+    emit_real(B, BufRef(BUF_IO, 0), BufRef(BUF_IO, 0), BufRef(BUF_WS, 0), 0, pl.batch, p, dir, REAL_PACKED,
+              BufRef());
+    return B.rc;
+}
+
+int build_rlft3(Plan &pl, Builder &B, int dir)
+{
+    const u64 nn1 = pl.dims[0], nn2 = pl.dims[1], N3 = pl.dims[2] / 2;
+    const int p1 = ilog2((size_t)nn1), p2 = ilog2((size_t)nn2), p3 = ilog2((size_t)N3);
+    const BufRef D(BUF_IO, 0), S(BUF_AUX, 0), W(BUF_WS, 0);
+    const u64 plane_bytes = nn2 * N3 * 16;
+    u64 g = tunables().l2_group_bytes / (plane_bytes ? plane_bytes : 1);
+    if (g < 1) g = 1;
+    if (g > nn1) g = nn1;
+    if (nn1 * plane_bytes <= 2 * tunables().l2_group_bytes) g = nn1;
+    if (dir > 0) {
+        for (u64 x0 = 0; x0 < nn1; x0 += g) {
+            const u64 x1 = (x0 + g < nn1) ? x0 + g : nn1;
+            emit_real(B, D, D, W, x0 * nn2, x1 * nn2, p3, +1, REAL_SPEQ, S);
+            emit_axis(B, D, D, W, nn1, x0, x1, p2, N3, +1);
+        }
+        emit_axis(B, S, S, W, nn1, 0, nn1, p2, 1, +1);
+        emit_axis(B, D, D, W, 1, 0, 1, p1, nn2 * N3, +1);
+        emit_axis(B, S, S, W, 1, 0, 1, p1, nn2, +1);
+    } else {
+        emit_axis(B, S, S, W, 1, 0, 1, p1, nn2, -1);
+        emit_axis(B, D, D, W, 1, 0, 1, p1, nn2 * N3, -1);
+        emit_axis(B, S, S, W, nn1, 0, nn1, p2, 1, -1);
+        for (u64 x0 = 0; x0 < nn1; x0 += g) {
+            const u64 x1 = (x0 + g < nn1) ? x0 + g : nn1;
+            emit_axis(B, D, D, W, nn1, x0, x1, p2, N3, -1);
+            emit_real(B, D, D, W, x0 * nn2, x1 * nn2, p3, -1, REAL_SPEQ, S);
+        }
+    }
+    return B.rc;
+}
+
+// convlv: dims = {n, m}.  io = signals (read only), aux = response taps, out = answers.
+// workspace: [0, n/2) response spectrum, [n/2, n/2 + gs*n/2) multi-step scratch.
+int build_convlv(Plan &pl, Builder &B, int dir)
+{
+    const u64 n = pl.dims[0], m = pl.dims[1];
+    const u64 N = n / 2;
+    const int p = ilog2((size_t)N);
+    const BufRef R(BUF_WS, 0), T(BUF_WS, (i64)N);
+    B.need_ws((size_t)N);
+    // response: pad (Convolve.rs:41-63) then forward realft, once per batch
+    {
+        Step st;
+        st.is_aux = true;
+        memset(&st.ap, 0, sizeof(st.ap));
+        st.ap.kind = AUX_PAD_RESPONSE;
+        st.ap.n = n; st.ap.m = m; st.ap.count = 1;
+        st.in = BufRef(BUF_AUX, 0); st.out = R;
+        st.patch_pad_mode = true;
+        B.prog->steps.push_back(st);
+    }
+    emit_real(B, R, R, T, 0, 1, p, +1, REAL_PACKED, BufRef());
+    // signals in L2-sized groups: forward, spectral op, inverse
+    u64 gs = tunables().l2_group_bytes / (n * 8 * 2);
+    if (gs < 1) gs = 1;
+    if (gs > pl.batch) gs = pl.batch;
+    for (u64 b0 = 0; b0 < pl.batch; b0 += gs) {
+        const u64 b1 = (b0 + gs < pl.batch) ? b0 + gs : pl.batch;
+        const BufRef in(BUF_IO, (i64)(b0 * N)), out(BUF_OUT, (i64)(b0 * N));
+        emit_real(B, in, out, T, 0, b1 - b0, p, +1, REAL_PACKED, BufRef());
+        B.prog->steps.push_back(make_spectral(dir > 0 ? SPEC_CONV_MUL : SPEC_CONV_DIV, out, R, out, n, b1 - b0,
+                                              (i64)N, 0, (i64)N));
+        emit_real(B, out, out, T, 0, b1 - b0, p, -1, REAL_PACKED, BufRef());
+    }
+    return B.rc;
+}
+
+// correl: dims = {n}.  io = data1, aux = data2 (read only), out = answers.
+int build_correl(Plan &pl, Builder &B)
+{
+    const u64 n = pl.dims[0];
+    if (n <= 32) {   // Correlation.rs:19-21 direct branch (linear lags)
+        Step st;
+        st.is_aux = true;
+        memset(&st.ap, 0, sizeof(st.ap));
+        st.ap.kind = AUX_CORREL_DIRECT;
+        st.ap.n = n; st.ap.count = pl.batch;
+        st.ap.a_stride = st.ap.b_stride = st.ap.out_stride = (i64)n;   // in doubles
+        st.in = BufRef(BUF_IO, 0); st.b = BufRef(BUF_AUX, 0); st.out = BufRef(BUF_OUT, 0);
+        B.prog->steps.push_back(st);
+        return B.rc;
+    }
+    const u64 N = n / 2;
+    const int p = ilog2((size_t)N);
+    u64 gs = tunables().l2_group_bytes / (n * 8 * 3);
+    if (gs < 1) gs = 1;
+    if (gs > pl.batch) gs = pl.batch;
+    const BufRef F2(BUF_WS, 0), T(BUF_WS, (i64)(gs * N));
+    B.need_ws((size_t)(gs * N));
+    for (u64 b0 = 0; b0 < pl.batch; b0 += gs) {
+        const u64 b1 = (b0 + gs < pl.batch) ? b0 + gs : pl.batch;
+        const BufRef a(BUF_IO, (i64)(b0 * N)), b(BUF_AUX, (i64)(b0 * N)), out(BUF_OUT, (i64)(b0 * N));
+        emit_real(B, a, out, T, 0, b1 - b0, p, +1, REAL_PACKED, BufRef());
+        emit_real(B, b, F2, T, 0, b1 - b0, p, +1, REAL_PACKED, BufRef());
+        B.prog->steps.push_back(make_spectral(SPEC_CORREL, out, F2, out, n, b1 - b0, (i64)N, (i64)N, (i64)N));
+        emit_real(B, out, out, T, 0, b1 - b0, p, -1, REAL_PACKED, BufRef());
+    }
+    return B.rc;
+}
+
+} // namespace
+
+int build_plan(Plan &pl, int kind, const size_t *dims, size_t ndim, size_t batch)
+{
+    if (!dims || ndim == 0) { set_error("no dimensions"); return NRB_ERR_INVALID_DIMS; }
+    if (batch == 0) { set_error("empty batch"); return NRB_ERR_EMPTY_INPUT; }
+    pl.kind = kind;
+    pl.dims.assign(dims, dims + ndim);
+    pl.batch = batch;
+    pl.device = be_current_device();
+    int rc = NRB_OK;
+    switch (kind) {
+    case NRB_KIND_FOUR1:
+        if (ndim != 1 || dims[0] == 0) { set_error("four1: nn must be >= 1"); return NRB_ERR_INVALID_DIMS; }
+        if ((rc = check_pow2_dims(dims, 1))) return rc;
+        break;
+    case NRB_KIND_FOURN:
+        for (size_t d = 0; d < ndim; ++d)
+            if (dims[d] <= 1) { set_error("Invalid dimension size"); return NRB_ERR_INVALID_DIMS; } // Fourn.rs:374
+        if ((rc = check_pow2_dims(dims, ndim))) return rc;
+        break;
+    case NRB_KIND_REALFT:
+        if (ndim != 1 || dims[0] < 2 || (dims[0] & 1)) { set_error("realft: n must be even"); return NRB_ERR_INVALID_DIMS; }
+        if ((rc = check_pow2_dims(dims, 1))) return rc;
+        break;
+    case NRB_KIND_RLFT3:
+        if (ndim != 3 || dims[0] == 0 || dims[1] == 0 || dims[2] < 2) { set_error("rlft3: bad dimensions"); return NRB_ERR_INVALID_DIMS; }
+        if ((rc = check_pow2_dims(dims, 3))) return rc;
+        break;
+    case NRB_KIND_CONVLV:
+        if (ndim != 2) { set_error("convlv: dims = {n, m}"); return NRB_ERR_INVALID_DIMS; }
+        if (dims[0] == 0 || dims[1] == 0) { set_error("Input arrays cannot be empty"); return NRB_ERR_EMPTY_INPUT; }
+        if (dims[1] > dims[0]) { set_error("Response function longer than data"); return NRB_ERR_RESPONSE_TOO_LONG; }
+        if (dims[0] < 2 || !is_pow2(dims[0])) { set_error("convlv: n must be a power of two >= 2"); return NRB_ERR_NOT_POW2; }
+        break;
+    case NRB_KIND_CORREL:
+        if (ndim != 1 || dims[0] == 0) { set_error("Input arrays cannot be empty"); return NRB_ERR_EMPTY_INPUT; }
+        if (dims[0] > 32 && !is_pow2(dims[0])) { set_error("correl: n > 32 must be a power of two"); return NRB_ERR_NOT_POW2; }
+        break;
+    default:
+        set_error("unknown plan kind");
+        return NRB_ERR_INVALID_DIMS;
+    }
+    size_t ws = 0;
+    for (int s = 0; s < 2; ++s) {
+        const int dir = s == 0 ? +1 : -1;
+        Builder B(&pl.prog[s]);
+        switch (kind) {
+        case NRB_KIND_FOUR1: rc = build_four1(pl, B, dir); break;
+        case NRB_KIND_FOURN: rc = build_fourn(pl, B, dir); break;
+        case NRB_KIND_REALFT: rc = build_realft(pl, B, dir); break;
+        case NRB_KIND_RLFT3: rc = build_rlft3(pl, B, dir); break;
+        case NRB_KIND_CONVLV: rc = build_convlv(pl, B, dir); break;
+        case NRB_KIND_CORREL: rc = build_correl(pl, B); break;
+        }
+        if (rc != NRB_OK) { set_error("shape not supported by this build"); return rc; }
+        for (const Step &st : pl.prog[s].steps) {
+            if (!st.is_aux && (!st.pp.tw && radix_plan(st.key.log2n).nst > 1)) { set_error(be_last_error()); return NRB_ERR_CUDA; }
+        }
+        if (B.ws_used > ws) ws = B.ws_used;
+    }
+    pl.ws_elems = ws;
+    pl.ws = nullptr;
+    if (ws) {
+        const int mrc = be_malloc(&pl.ws, ws * sizeof(double2));
+        if (mrc != 0) { set_error(std::string("workspace allocation failed: ") + be_last_error()); return NRB_ERR_OOM; }
+    }
+    return NRB_OK;
+}
+
+static int run_program(Program &prog, double2 *const base[4], int arg, void *stream)
+{
+    for (Step &st : prog.steps) {
+        int rc;
+        if (st.is_aux) {
+            AuxParams ap = st.ap;
+            ap.a = st.in.id == BUF_NONE ? nullptr : base[st.in.id] + st.in.off;
+            ap.b = st.b.id == BUF_NONE ? nullptr : base[st.b.id] + st.b.off;
+            ap.out = st.out.id == BUF_NONE ? nullptr : base[st.out.id] + st.out.off;
+            ap.speq = st.speq.id == BUF_NONE ? nullptr : base[st.speq.id] + st.speq.off;
+            if (st.patch_pad_mode) ap.op = arg;
+            rc = be_launch_aux(ap, stream);
+        } else {
+            PassParams pp = st.pp;
+            pp.in = base[st.in.id] + st.in.off;
+            pp.out = base[st.out.id] + st.out.off;
+            pp.speq = st.speq.id == BUF_NONE ? nullptr : base[st.speq.id] + st.speq.off;
+            rc = be_launch_pass(st.key, pp, st.ntiles, stream);
+        }
+        if (rc != 0) { set_error(std::string("kernel launch failed: ") + be_last_error()); return NRB_ERR_CUDA; }
+    }
+    return NRB_OK;
+}
+
+int exec_plan(Plan &pl, double *d_io, double *d_aux, double *d_out, int isign, int arg, void *stream)
+{
+    if (isign != 1 && isign != -1) { set_error("isign must be 1 or -1"); return NRB_ERR_INVALID_ISIGN; }
+    double2 *const base[4] = {(double2 *)d_io, (double2 *)d_aux, (double2 *)d_out, (double2 *)pl.ws};
+    return run_program(pl.prog[isign == 1 ? 0 : 1], base, arg, stream);
+}
+
+// ------------------------------------------------------------------ slab-decomposed rlft3
+// Rank r of G.  X = nn1/G, Y = nn2/G, N3 = nn3/2, BLK = X*Y*(N3 + 1) complex per exchange
+// block (data part X*Y*N3 followed by the speq part X*Y).
+//   forward stage 0 : slab [nn1][Y][nn3] real -> z real pass (speq -> ws [nn1][Y]) ->
+//                     x pass writing block p = x / X of `send` (data + speq parts)
+//   exchange        : all-to-all of BLK-sized blocks (caller; NCCL over NVLink)
+//   forward stage 1 : y pass reading the G received blocks (element y -> block y / Y),
+//                     writing the nn1-slab [X][nn2][N3] complex and speq [X][nn2]
+//   inverse         : mirror image (stage 0 = y pass into blocks, stage 1 = x pass + z c2r).
+// buffers: BUF_IO = slab, BUF_AUX = local speq, BUF_OUT = send (stage 0) / recv (stage 1).
+int build_slab_plan(SlabPlan &sp, size_t nn1, size_t nn2, size_t nn3, int nranks, int rank)
+{
+    if (!is_pow2(nn1) || !is_pow2(nn2) || !is_pow2(nn3) || nn3 < 2) { set_error("slab: dims must be powers of two"); return NRB_ERR_NOT_POW2; }
+    if (nranks < 1 || !is_pow2((size_t)nranks) || (size_t)nranks > nn1 || (size_t)nranks > nn2 || rank < 0 || rank >= nranks) {
+        set_error("slab: nranks must be a power of two dividing nn1 and nn2");
+        return NRB_ERR_INVALID_DIMS;
+    }
+    sp.nn1 = nn1; sp.nn2 = nn2; sp.nn3 = nn3; sp.nranks = nranks; sp.rank = rank;
+    const u64 G = (u64)nranks, X = nn1 / G, Y = nn2 / G, N3 = nn3 / 2;
+    const int p1 = ilog2(nn1), p2 = ilog2(nn2), p3 = ilog2((size_t)N3);
+    if (p1 > tunables().col_max_log2 || p2 > tunables().col_max_log2 || p3 > tunables().row_max_log2 || p3 < 1) {
+        set_error("slab: axis too long for a single pass");
+        return NRB_ERR_UNSUPPORTED;
+    }
+    const i64 BLK = (i64)(X * Y * (N3 + 1));
+    const i64 SPQ = (i64)(X * Y * N3);      // offset of the speq part inside a block
+    const BufRef SLAB(BUF_IO, 0), SPEQ(BUF_AUX, 0), XCH(BUF_OUT, 0), WSPEQ(BUF_WS, 0);
+    sp.ws_elems = (size_t)(nn1 * Y);        // speq of the nn2-slab: [nn1][Y]
+    int rc = NRB_OK;
+
+    AxisMap x_blocks;   // x index -> block x / X ; data part, lines (y, z)
+    x_blocks.on = true; x_blocks.s0 = 0; x_blocks.es = (i64)(Y * N3); x_blocks.eshift = ilog2((size_t)X); x_blocks.es_hi = BLK;
+    AxisMap x_blocks_speq = x_blocks;   // speq part, lines (y)
+    x_blocks_speq.es = (i64)Y;
+    AxisMap y_blocks;   // y index -> block y / Y ; data part, lines (xl, z)
+    y_blocks.on = true; y_blocks.s0 = (i64)(Y * N3); y_blocks.es = (i64)N3; y_blocks.eshift = ilog2((size_t)Y); y_blocks.es_hi = BLK;
+    AxisMap y_blocks_speq;   // speq part: lines xl, contiguous yl
+    y_blocks_speq.on = true; y_blocks_speq.s0 = (i64)Y; y_blocks_speq.es = 1; y_blocks_speq.eshift = ilog2((size_t)Y); y_blocks_speq.es_hi = BLK;
+
+    {   // forward stage 0
+        Builder B(&sp.prog[0][0]);
+        emit_real(B, SLAB, SLAB, BufRef(), 0, nn1 * Y, p3, +1, REAL_SPEQ, WSPEQ);
+        emit_axis(B, SLAB, XCH, BufRef(), 1, 0, 1, p1, Y * N3, +1, nullptr, &x_blocks);
+        emit_axis(B, WSPEQ, XCH + SPQ, BufRef(), 1, 0, 1, p1, Y, +1, nullptr, &x_blocks_speq);
+        rc = B.rc ? B.rc : rc;
+    }
+    {   // forward stage 1
+        Builder B(&sp.prog[0][1]);
+        emit_axis(B, XCH, SLAB, BufRef(), X, 0, X, p2, N3, +1, &y_blocks, nullptr);
+        emit_axis(B, XCH + SPQ, SPEQ, BufRef(), X, 0, X, p2, 1, +1, &y_blocks_speq, nullptr);
+        rc = B.rc ? B.rc : rc;
+    }
+    {   // inverse stage 0
+        Builder B(&sp.prog[1][0]);
+        emit_axis(B, SLAB, XCH, BufRef(), X, 0, X, p2, N3, -1, nullptr, &y_blocks);
+        emit_axis(B, SPEQ, XCH + SPQ, BufRef(), X, 0, X, p2, 1, -1, nullptr, &y_blocks_speq);
+        rc = B.rc ? B.rc : rc;
+    }
+    {   // inverse stage 1
+        Builder B(&sp.prog[1][1]);
+        emit_axis(B, XCH + SPQ, WSPEQ, BufRef(), 1, 0, 1, p1, Y, -1, &x_blocks_speq, nullptr);
+        emit_axis(B, XCH, SLAB, BufRef(), 1, 0, 1, p1, Y * N3, -1, &x_blocks, nullptr);
+        emit_real(B, SLAB, SLAB, BufRef(), 0, nn1 * Y, p3, -1, REAL_SPEQ, WSPEQ);
+        rc = B.rc ? B.rc : rc;
+    }
+    if (rc != NRB_OK) { set_error("slab: shape not supported"); return rc; }
+    sp.ws = nullptr;
+    if (be_malloc(&sp.ws, sp.ws_elems * sizeof(double2)) != 0) { set_error("slab: workspace allocation failed"); return NRB_ERR_OOM; }
+    return NRB_OK;
+}
+
+int exec_slab_stage(SlabPlan &sp, int stage, int isign, double *d_slab, double *d_speq, double *d_send,
+                    double *d_recv, void *stream)
+{
+    if (isign != 1 && isign != -1) { set_error("isign must be 1 or -1"); return NRB_ERR_INVALID_ISIGN; }
+    if (stage != 0 && stage != 1) { set_error("stage must be 0 or 1"); return NRB_ERR_INVALID_DIMS; }
+    double2 *const base[4] = {(double2 *)d_slab, (double2 *)d_speq, (double2 *)(stage == 0 ? d_send : d_recv),
+                              (double2 *)sp.ws};
+    return run_program(sp.prog[isign == 1 ? 0 : 1][stage], base, 0, stream);
+}
+
+} // namespace nrb

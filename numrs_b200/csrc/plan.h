@@ -1,0 +1,107 @@
+// plan.h -- host-side planner: turns a transform request into a list of kernel launches.
+// Backend-agnostic (the CUDA backend lives in kernels.cu; tests/emu provides a host-thread
+// emulation of the same kernels for index-math validation only).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "nrb_common.h"
+
+namespace nrb {
+
+// ---- backend interface ----
+struct KernelKey { int log2n, layout, dir, variant; };
+int be_launch_pass(const KernelKey &key, const PassParams &p, u64 ntiles, void *stream);
+int be_launch_aux(const AuxParams &a, void *stream);
+int be_malloc(void **p, size_t bytes);
+int be_free(void *p);
+int be_h2d(void *dst, const void *src, size_t bytes, void *stream);
+int be_d2h(void *dst, const void *src, size_t bytes, void *stream);
+int be_d2d(void *dst, const void *src, size_t bytes, void *stream);
+int be_sync(void *stream);
+int be_current_device();
+int be_device_count();
+int be_set_device(int dev);
+int be_stream_create(void **stream);
+int be_stream_destroy(void *stream);
+void *be_host_alloc(size_t bytes);
+void be_host_free(void *p);
+const char *be_last_error();
+
+void set_error(const std::string &msg);   // thread-local message behind nrb_last_error()
+const std::string &get_error();
+
+// ---- buffers a program can refer to ----
+enum BufId { BUF_IO = 0, BUF_AUX = 1, BUF_OUT = 2, BUF_WS = 3, BUF_NONE = 4 };
+struct BufRef {
+    int id;
+    i64 off;   // in complex (double2) elements
+    BufRef() : id(BUF_NONE), off(0) {}
+    BufRef(int i, i64 o) : id(i), off(o) {}
+    BufRef operator+(i64 d) const { return BufRef(id, off + d); }
+    bool same(const BufRef &o) const { return id == o.id && off == o.off; }
+};
+
+struct Step {
+    bool is_aux;
+    KernelKey key;
+    PassParams pp;
+    AuxParams ap;
+    u64 ntiles;
+    BufRef in, out, speq, b;
+    bool patch_pad_mode;   // AUX_PAD_RESPONSE: op comes from exec's `arg`
+    Step() : is_aux(false), key{0, 0, 0, 0}, pp(), ap(), ntiles(0), patch_pad_mode(false) {}
+};
+
+struct Program {
+    std::vector<Step> steps;
+};
+
+// device-resident twiddle tables, cached per device for the life of the process
+struct FourStepTable { const double2 *lo, *hi; int h; };
+const double2 *stage_twiddles(int log2n);          // packed per-stage tables (nrb_common.h layout)
+FourStepTable fourstep_table(int log2m);           // exp(-2 pi i m / 2^log2m), two-level
+const double2 *real_twiddles(int log2n);           // exp(-i pi k / 2^log2n), k < max(N/2,1)
+void release_tables();
+
+// tunables (environment overrides, read once)
+struct Tunables {
+    int col_max_log2;      // longest strided-axis FFT done in one pass (NRB_COL_MAX_LOG2, default 10)
+    int row_max_log2;      // longest contiguous FFT done in one pass   (NRB_ROW_MAX_LOG2, default 13)
+    u64 l2_group_bytes;    // working-set target for L2-resident pass groups (NRB_L2_GROUP_MB, default 32)
+};
+const Tunables &tunables();
+int set_tunable(const char *name, long value);   // returns 0 if the name is known
+
+struct Plan {
+    int kind;
+    std::vector<size_t> dims;
+    size_t batch;
+    Program prog[2];       // [0]: isign = +1, [1]: isign = -1
+    size_t ws_elems;       // workspace size in complex elements
+    void *ws;              // device workspace (owned)
+    int device;
+    Plan() : kind(0), batch(1), ws_elems(0), ws(nullptr), device(0) {}
+};
+
+// builders; return NRB_* codes
+int build_plan(Plan &pl, int kind, const size_t *dims, size_t ndim, size_t batch);
+int exec_plan(Plan &pl, double *d_io, double *d_aux, double *d_out, int isign, int arg, void *stream);
+
+// slab-decomposed rlft3 (one rank's share)
+struct SlabPlan {
+    size_t nn1, nn2, nn3;
+    int nranks, rank;
+    Program prog[2][2];    // [isign index][stage]
+    size_t ws_elems;
+    void *ws;
+    SlabPlan() : nn1(0), nn2(0), nn3(0), nranks(1), rank(0), ws_elems(0), ws(nullptr) {}
+};
+int build_slab_plan(SlabPlan &sp, size_t nn1, size_t nn2, size_t nn3, int nranks, int rank);
+int exec_slab_stage(SlabPlan &sp, int stage, int isign, double *d_slab, double *d_speq, double *d_send,
+                    double *d_recv, void *stream);
+
+inline bool is_pow2(size_t n) { return n && !(n & (n - 1)); }
+inline int ilog2(size_t n) { int l = 0; while ((size_t(1) << l) < n) ++l; return l; }
+
+} // namespace nrb

@@ -1,0 +1,174 @@
+// emu_backend.cpp -- TEST-ONLY host emulation of the numrs_b200 kernels.
+//
+// Compiles the very same device source (fft_pass.cuh, aux_kernels.cuh) with -DNRB_EMU and
+// runs every CTA as a set of cooperative fibers (ucontext) whose __syncthreads() is a
+// round-robin yield.  It exists so the CPU-only test tier can validate the planner and the
+// index arithmetic of every kernel variant in a container without a GPU.  It is built into
+// tests/emu/libnrb_emu.so only; the product library has no such path and the numrs_b200
+// Python package never loads this file's output.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ucontext.h>
+
+#include <string>
+#include <vector>
+
+#include "../../numrs_b200/csrc/aux_kernels.cuh"
+#include "../../numrs_b200/csrc/plan.h"
+
+namespace nrb_emu {
+
+struct Cta {
+    ucontext_t main_ctx;
+    std::vector<ucontext_t> fibers;
+    std::vector<char> stacks;
+    std::vector<char> done;
+    std::vector<double2> smem;
+    int current;
+    void (*body)(const void *, double2 *, unsigned, int);
+    const void *params;
+    unsigned tile;
+};
+static thread_local Cta *t_cta = nullptr;
+
+void barrier()
+{
+    Cta *c = t_cta;
+    swapcontext(&c->fibers[c->current], &c->main_ctx);
+}
+
+static void fiber_entry()
+{
+    Cta *c = t_cta;
+    const int tid = c->current;
+    c->body(c->params, c->smem.data(), c->tile, tid);
+    c->done[tid] = 1;
+    swapcontext(&c->fibers[tid], &c->main_ctx);
+}
+
+static const size_t kStack = 64 * 1024;
+
+static void run_cta(Cta &c, int nthreads)
+{
+    t_cta = &c;
+    for (int t = 0; t < nthreads; ++t) {
+        getcontext(&c.fibers[t]);
+        c.fibers[t].uc_stack.ss_sp = c.stacks.data() + (size_t)t * kStack;
+        c.fibers[t].uc_stack.ss_size = kStack;
+        c.fibers[t].uc_link = nullptr;
+        makecontext(&c.fibers[t], fiber_entry, 0);
+        c.done[t] = 0;
+    }
+    int remaining = nthreads;
+    while (remaining > 0) {
+        remaining = 0;
+        for (int t = 0; t < nthreads; ++t) {
+            if (c.done[t]) continue;
+            c.current = t;
+            swapcontext(&c.main_ctx, &c.fibers[t]);
+            if (!c.done[t]) ++remaining;
+        }
+    }
+}
+
+template <int LOG2N, int LAYOUT, int DIR, int VARIANT>
+static void body_tpl(const void *p, double2 *sm, unsigned tile, int tid)
+{
+    nrb::fft_pass_body<LOG2N, LAYOUT, DIR, VARIANT>(*(const nrb::PassParams *)p, sm, tile, tid);
+}
+
+typedef void (*BodyFn)(const void *, double2 *, unsigned, int);
+struct Entry { BodyFn fn; int nthreads; size_t smem; };
+static Entry g_table[nrb::kMaxLog2N + 1][2][2][3];
+
+template <int LOG2N, int LAYOUT> static void reg()
+{
+    using namespace nrb;
+    const int nt = cta_threads(LOG2N);
+    if (LAYOUT == LAYOUT_ROW) {
+        g_table[LOG2N][0][1][VAR_PLAIN] = Entry{body_tpl<LOG2N, LAYOUT_ROW, 1, VAR_PLAIN>, nt, smem_elems(LOG2N, LAYOUT_ROW, VAR_PLAIN)};
+        g_table[LOG2N][0][0][VAR_PLAIN] = Entry{body_tpl<LOG2N, LAYOUT_ROW, -1, VAR_PLAIN>, nt, smem_elems(LOG2N, LAYOUT_ROW, VAR_PLAIN)};
+        g_table[LOG2N][0][1][VAR_REAL] = Entry{body_tpl<LOG2N, LAYOUT_ROW, 1, VAR_REAL>, nt, smem_elems(LOG2N, LAYOUT_ROW, VAR_REAL)};
+        g_table[LOG2N][0][0][VAR_REAL] = Entry{body_tpl<LOG2N, LAYOUT_ROW, -1, VAR_REAL>, nt, smem_elems(LOG2N, LAYOUT_ROW, VAR_REAL)};
+    } else {
+        g_table[LOG2N][1][1][VAR_PLAIN] = Entry{body_tpl<LOG2N, LAYOUT_COL, 1, VAR_PLAIN>, nt, smem_elems(LOG2N, LAYOUT_COL, VAR_PLAIN)};
+        g_table[LOG2N][1][0][VAR_PLAIN] = Entry{body_tpl<LOG2N, LAYOUT_COL, -1, VAR_PLAIN>, nt, smem_elems(LOG2N, LAYOUT_COL, VAR_PLAIN)};
+        g_table[LOG2N][1][1][VAR_XPOSE] = Entry{body_tpl<LOG2N, LAYOUT_COL, 1, VAR_XPOSE>, nt, smem_elems(LOG2N, LAYOUT_COL, VAR_XPOSE)};
+        g_table[LOG2N][1][0][VAR_XPOSE] = Entry{body_tpl<LOG2N, LAYOUT_COL, -1, VAR_XPOSE>, nt, smem_elems(LOG2N, LAYOUT_COL, VAR_XPOSE)};
+    }
+}
+
+static void init_table()
+{
+    static bool done = false;
+    if (done) return;
+    done = true;
+    using namespace nrb;
+    reg<1, 0>(); reg<2, 0>(); reg<3, 0>(); reg<4, 0>(); reg<5, 0>(); reg<6, 0>(); reg<7, 0>();
+    reg<8, 0>(); reg<9, 0>(); reg<10, 0>(); reg<11, 0>(); reg<12, 0>(); reg<13, 0>();
+    reg<1, 1>(); reg<2, 1>(); reg<3, 1>(); reg<4, 1>(); reg<5, 1>(); reg<6, 1>(); reg<7, 1>();
+    reg<8, 1>(); reg<9, 1>(); reg<10, 1>(); reg<11, 1>(); reg<12, 1>();
+}
+
+} // namespace nrb_emu
+
+namespace nrb {
+
+static thread_local std::string g_emu_err;
+const char *be_last_error() { return g_emu_err.c_str(); }
+
+static long g_pass_launches = 0, g_aux_launches = 0;
+
+int be_launch_pass(const KernelKey &key, const PassParams &p, u64 ntiles, void *)
+{
+    nrb_emu::init_table();
+    if (key.log2n < 1 || key.log2n > kMaxLog2N) { g_emu_err = "no such kernel"; return -1; }
+    const nrb_emu::Entry e = nrb_emu::g_table[key.log2n][key.layout][key.dir > 0 ? 1 : 0][key.variant];
+    if (!e.fn) { g_emu_err = "kernel variant not built"; return -1; }
+    ++g_pass_launches;
+#pragma omp parallel
+    {
+        nrb_emu::Cta c;
+        c.fibers.resize(e.nthreads);
+        c.stacks.resize((size_t)e.nthreads * nrb_emu::kStack);
+        c.done.resize(e.nthreads);
+        c.smem.assign(e.smem, make_double2(0.0, 0.0));
+        c.body = e.fn;
+        c.params = &p;
+#pragma omp for schedule(dynamic)
+        for (long long t = 0; t < (long long)ntiles; ++t) {
+            c.tile = (unsigned)t;
+            // poison shared memory so reads of never-written cells show up as NaN
+            for (size_t i = 0; i < c.smem.size(); ++i) c.smem[i] = make_double2(__builtin_nan(""), __builtin_nan(""));
+            nrb_emu::run_cta(c, e.nthreads);
+        }
+    }
+    return 0;
+}
+
+int be_launch_aux(const AuxParams &a, void *)
+{
+    ++g_aux_launches;
+    const u64 nthreads = 977;   // deliberately odd: exercises the grid-stride loops
+    for (u64 t = 0; t < nthreads; ++t) aux_body(a, t, nthreads);
+    return 0;
+}
+
+int be_malloc(void **p, size_t bytes) { *p = malloc(bytes ? bytes : 16); return *p ? 0 : -1; }
+int be_free(void *p) { free(p); return 0; }
+int be_h2d(void *d, const void *s, size_t n, void *) { memcpy(d, s, n); return 0; }
+int be_d2h(void *d, const void *s, size_t n, void *) { memcpy(d, s, n); return 0; }
+int be_d2d(void *d, const void *s, size_t n, void *) { memmove(d, s, n); return 0; }
+int be_sync(void *) { return 0; }
+int be_current_device() { return 0; }
+int be_device_count() { return 1; }
+int be_set_device(int dev) { return dev == 0 ? 0 : -1; }
+int be_stream_create(void **s) { *s = (void *)1; return 0; }
+int be_stream_destroy(void *) { return 0; }
+void *be_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 16); }
+void be_host_free(void *p) { free(p); }
+
+} // namespace nrb
+
+extern "C" long nrb_emu_launch_count(int aux) { return aux ? nrb::g_aux_launches : nrb::g_pass_launches; }
