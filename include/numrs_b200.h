@@ -115,6 +115,17 @@ int    nrb_plan_num_launches(nrb_plan_t plan, int isign);  /* kernels per exec *
 int    nrb_plan_exec(nrb_plan_t plan, double *d_io, double *d_aux, double *d_out, int isign,
                      int arg, void *stream);
 int    nrb_plan_destroy(nrb_plan_t plan);
+/* Measurement helpers.  nrb_plan_profile runs the plan once with CUDA events around every
+ * launch and returns ms[i] for launch i (blocks until done); nrb_plan_describe_launch gives
+ * launch i's kernel name and the bytes it has to read + write (its algorithmic traffic). */
+int    nrb_plan_profile(nrb_plan_t plan, double *d_io, double *d_aux, double *d_out, int isign,
+                        int arg, void *stream, float *ms, int cap);
+int    nrb_plan_describe_launch(nrb_plan_t plan, int isign, int idx, char *name, size_t cap,
+                                double *bytes);
+/* Synthetic input: out[i] = uniform[-1,1) from splitmix64(seed*phi+offset+i),
+ * written to DEVICE memory; bit-identical to the generator in oracle/ and in Python. */
+int    nrb_fill_uniform_device(double *d_out, unsigned long long seed, unsigned long long offset,
+                               size_t count, void *stream);
 
 /* ---- slab-decomposed rlft3 across the GPUs of one box (one process per GPU) ----
  * Forward: rank r holds the nn2-slab data[:, r*nn2/G:(r+1)*nn2/G, :] as a contiguous

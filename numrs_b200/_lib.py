@@ -1,8 +1,7 @@
 """ctypes binding of the C ABI declared in include/numrs_b200.h.
 
-`Library(path)` wraps one shared object.  The product package binds
-numrs_b200/libnumrs_b200.so (CUDA, sm_100a) and nothing else; the CPU-only test tier binds
-tests/emu/libnrb_emu.so through this same class to validate planner/index logic.
+`Library(path)` wraps one shared object exporting that ABI.  The product package binds
+numrs_b200/libnumrs_b200.so (CUDA, sm_100a) and nothing else (see numrs_b200/__init__.py).
 """
 import ctypes
 import os
@@ -38,6 +37,7 @@ ABI_SYMBOLS = [
     "nrb_four1", "nrb_four1_batch", "nrb_fourn", "nrb_realft", "nrb_realft_batch", "nrb_rlft3",
     "nrb_convlv", "nrb_convlv_batch", "nrb_correl", "nrb_correl_batch",
     "nrb_plan_create", "nrb_plan_workspace_bytes", "nrb_plan_num_launches", "nrb_plan_exec", "nrb_plan_destroy",
+    "nrb_plan_profile", "nrb_plan_describe_launch", "nrb_fill_uniform_device",
     "nrb_slab_create", "nrb_slab_local_doubles", "nrb_slab_speq_doubles", "nrb_slab_xchg_doubles",
     "nrb_slab_stage", "nrb_slab_destroy",
 ]
@@ -90,6 +90,10 @@ class Library:
         L.nrb_plan_num_launches.argtypes = [_vp, ctypes.c_int]
         L.nrb_plan_exec.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp]
         L.nrb_plan_destroy.argtypes = [_vp]
+        L.nrb_plan_profile.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp,
+                                       ctypes.POINTER(ctypes.c_float), ctypes.c_int]
+        L.nrb_plan_describe_launch.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, _sz, _dp]
+        L.nrb_fill_uniform_device.argtypes = [_vp, ctypes.c_ulonglong, ctypes.c_ulonglong, _sz, _vp]
         L.nrb_slab_create.argtypes = [_sz, _sz, _sz, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]
         for n in ("nrb_slab_local_doubles", "nrb_slab_speq_doubles", "nrb_slab_xchg_doubles"):
             getattr(L, n).argtypes = [_vp]
@@ -201,6 +205,9 @@ class Library:
         rc = self.L.nrb_correl_batch(ap, bp, cnt, n, op)
         return rc, outs
 
+    def fill_uniform_device(self, d_ptr, seed, offset, count, stream=0):
+        self.check(self.L.nrb_fill_uniform_device(d_ptr, seed, offset, count, stream or None))
+
     # ---- device-resident plan API (pointers are integers: device addresses)
     def plan_create(self, kind, dims, batch=1):
         h = _vp()
@@ -230,6 +237,20 @@ class Plan:
     def exec(self, d_io, d_aux=0, d_out=0, isign=1, arg=0, stream=0):
         self.lib.check(self.lib.L.nrb_plan_exec(self.h, d_io, d_aux or None, d_out or None, isign, arg,
                                                 stream or None))
+
+    def profile(self, d_io, d_aux=0, d_out=0, isign=1, arg=0, stream=0):
+        """Run once with events around every launch; returns [(name, algorithmic_bytes, ms)]."""
+        n = self.num_launches(isign)
+        ms = (ctypes.c_float * max(n, 1))()
+        self.lib.check(self.lib.L.nrb_plan_profile(self.h, d_io, d_aux or None, d_out or None, isign, arg,
+                                                   stream or None, ms, n))
+        out = []
+        for i in range(n):
+            name = ctypes.create_string_buffer(128)
+            b = ctypes.c_double()
+            self.lib.L.nrb_plan_describe_launch(self.h, isign, i, name, 128, ctypes.byref(b))
+            out.append((name.value.decode(), b.value, float(ms[i])))
+        return out
 
     def destroy(self):
         if self.h:

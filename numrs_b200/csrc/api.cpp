@@ -8,7 +8,9 @@
 #include <string>
 #include <vector>
 
+#pragma GCC visibility push(default)
 #include "../../include/numrs_b200.h"
+#pragma GCC visibility pop
 #include "plan.h"
 
 using namespace nrb;
@@ -214,6 +216,22 @@ int nrb_plan_exec(nrb_plan_t plan, double *d_io, double *d_aux, double *d_out, i
 {
     if (!plan) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
     return exec_plan(plan->plan, d_io, d_aux, d_out, isign, arg, stream);
+}
+int nrb_plan_profile(nrb_plan_t plan, double *d_io, double *d_aux, double *d_out, int isign, int arg, void *stream,
+                     float *ms, int cap)
+{
+    if (!plan || !ms) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
+    return profile_plan(plan->plan, d_io, d_aux, d_out, isign, arg, stream, ms, cap);
+}
+int nrb_plan_describe_launch(nrb_plan_t plan, int isign, int idx, char *name, size_t cap, double *bytes)
+{
+    if (!plan) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
+    return describe_launch(plan->plan, isign, idx, name, cap, bytes);
+}
+int nrb_fill_uniform_device(double *d_out, unsigned long long seed, unsigned long long offset, size_t count, void *stream)
+{
+    if (be_device_count() <= 0) return fail(NRB_ERR_CUDA, "no CUDA device available (numrs_b200 has no CPU fallback)");
+    return fill_uniform_device(d_out, seed, offset, count, stream);
 }
 int nrb_plan_destroy(nrb_plan_t plan)
 {

@@ -123,12 +123,27 @@ NRB_DEV void aux_correl_direct(const AuxParams &A, u64 gtid, u64 gthreads)
     }
 }
 
+// u(i) = splitmix64(seed * 0x9E3779B97F4A7C15 + offset + i), x = (u >> 11) * 2^-52 - 1 in [-1, 1)
+NRB_DEV void aux_fill(const AuxParams &A, u64 gtid, u64 gthreads)
+{
+    double *out = reinterpret_cast<double *>(A.out);
+    const u64 base = A.m * 0x9E3779B97F4A7C15ull + A.count;
+    for (u64 i = gtid; i < A.n; i += gthreads) {
+        u64 x = base + i + 0x9E3779B97F4A7C15ull;
+        x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+        x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+        x = x ^ (x >> 31);
+        out[i] = (double)(x >> 11) * (1.0 / 4503599627370496.0) - 1.0;
+    }
+}
+
 NRB_DEV void aux_body(const AuxParams &A, u64 gtid, u64 gthreads)
 {
     switch (A.kind) {
     case AUX_UNTANGLE: aux_untangle(A, gtid, gthreads); break;
     case AUX_SPECTRAL: aux_spectral(A, gtid, gthreads); break;
     case AUX_PAD_RESPONSE: aux_pad_response(A, gtid, gthreads); break;
+    case AUX_FILL: aux_fill(A, gtid, gthreads); break;
     default: aux_correl_direct(A, gtid, gthreads); break;
     }
 }

@@ -60,6 +60,7 @@ int be_launch_aux(const AuxParams &a, void *stream)
     case AUX_UNTANGLE: items = a.count * (a.n >= 2 ? a.n / 2 : 1); break;
     case AUX_SPECTRAL: items = a.count * (a.n / 2); break;
     case AUX_PAD_RESPONSE: items = a.n; break;
+    case AUX_FILL: items = a.n; break;
     default: items = a.count * a.n; break;
     }
     if (items == 0) return 0;
@@ -108,6 +109,21 @@ int be_sync(void *stream)
     cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
     return e == cudaSuccess ? 0 : fail(e);
 }
+void *be_event_record(void *stream)
+{
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    cudaEventRecord(e, (cudaStream_t)stream);
+    return (void *)e;
+}
+float be_event_elapsed_ms(void *a, void *b)
+{
+    float ms = 0.f;
+    cudaEventSynchronize((cudaEvent_t)b);
+    cudaEventElapsedTime(&ms, (cudaEvent_t)a, (cudaEvent_t)b);
+    return ms;
+}
+void be_event_destroy(void *e) { cudaEventDestroy((cudaEvent_t)e); }
 int be_device_count()
 {
     int n = 0;

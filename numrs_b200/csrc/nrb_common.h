@@ -154,7 +154,8 @@ enum AuxKind {
     AUX_UNTANGLE = 0,     // standalone real untangle (large lines / N == 1)
     AUX_SPECTRAL = 1,     // convlv multiply / divide, correl conj-multiply on packed spectra
     AUX_PAD_RESPONSE = 2, // Convolve.rs:41-63 response placement
-    AUX_CORREL_DIRECT = 3 // Correlation.rs:37-50, n <= 32
+    AUX_CORREL_DIRECT = 3,// Correlation.rs:37-50, n <= 32
+    AUX_FILL = 4          // synthetic input generator: n doubles, seed in m, offset in count
 };
 enum SpectralOp { SPEC_CONV_MUL = 0, SPEC_CONV_DIV = 1, SPEC_CORREL = 2 };
 

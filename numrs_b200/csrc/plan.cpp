@@ -17,6 +17,7 @@
 
 #include <math.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 
 #include <map>
@@ -589,8 +590,9 @@ int build_plan(Plan &pl, int kind, const size_t *dims, size_t ndim, size_t batch
     return NRB_OK;
 }
 
-static int run_program(Program &prog, double2 *const base[4], int arg, void *stream)
+static int run_program(Program &prog, double2 *const base[4], int arg, void *stream, std::vector<void *> *events = nullptr)
 {
+    if (events) events->push_back(be_event_record(stream));
     for (Step &st : prog.steps) {
         int rc;
         if (st.is_aux) {
@@ -609,6 +611,7 @@ static int run_program(Program &prog, double2 *const base[4], int arg, void *str
             rc = be_launch_pass(st.key, pp, st.ntiles, stream);
         }
         if (rc != 0) { set_error(std::string("kernel launch failed: ") + be_last_error()); return NRB_ERR_CUDA; }
+        if (events) events->push_back(be_event_record(stream));
     }
     return NRB_OK;
 }
@@ -618,6 +621,60 @@ int exec_plan(Plan &pl, double *d_io, double *d_aux, double *d_out, int isign, i
     if (isign != 1 && isign != -1) { set_error("isign must be 1 or -1"); return NRB_ERR_INVALID_ISIGN; }
     double2 *const base[4] = {(double2 *)d_io, (double2 *)d_aux, (double2 *)d_out, (double2 *)pl.ws};
     return run_program(pl.prog[isign == 1 ? 0 : 1], base, arg, stream);
+}
+
+int profile_plan(Plan &pl, double *d_io, double *d_aux, double *d_out, int isign, int arg, void *stream, float *ms,
+                 int cap)
+{
+    if (isign != 1 && isign != -1) { set_error("isign must be 1 or -1"); return NRB_ERR_INVALID_ISIGN; }
+    double2 *const base[4] = {(double2 *)d_io, (double2 *)d_aux, (double2 *)d_out, (double2 *)pl.ws};
+    std::vector<void *> ev;
+    const int rc = run_program(pl.prog[isign == 1 ? 0 : 1], base, arg, stream, &ev);
+    if (be_sync(stream) != 0 && rc == NRB_OK) { set_error(std::string("kernel execution failed: ") + be_last_error()); return NRB_ERR_CUDA; }
+    for (size_t i = 0; i + 1 < ev.size(); ++i)
+        if ((int)i < cap && ev[i] && ev[i + 1]) ms[i] = be_event_elapsed_ms(ev[i], ev[i + 1]);
+    for (void *e : ev) if (e) be_event_destroy(e);
+    return rc;
+}
+
+int describe_launch(const Plan &pl, int isign, int idx, char *name, size_t cap, double *bytes)
+{
+    const Program &prog = pl.prog[isign == 1 ? 0 : 1];
+    if (idx < 0 || (size_t)idx >= prog.steps.size()) return NRB_ERR_INVALID_DIMS;
+    const Step &st = prog.steps[(size_t)idx];
+    char buf[128];
+    double b = 0.0;
+    if (st.is_aux) {
+        static const char *names[] = {"untangle", "spectral", "pad_response", "correl_direct", "fill"};
+        snprintf(buf, sizeof(buf), "aux_%s", names[st.ap.kind]);
+        switch (st.ap.kind) {
+        case AUX_UNTANGLE: b = 2.0 * 16.0 * (double)st.ap.count * (double)st.ap.n; break;
+        case AUX_SPECTRAL: b = (double)st.ap.count * (double)st.ap.n * 8.0 * (st.ap.b_stride ? 3.0 : 2.0) + (st.ap.b_stride ? 0.0 : 8.0 * (double)st.ap.n); break;
+        case AUX_PAD_RESPONSE: b = 8.0 * ((double)st.ap.n + (double)st.ap.m); break;
+        default: b = 3.0 * 8.0 * (double)st.ap.count * (double)st.ap.n; break;
+        }
+    } else {
+        static const char *var[] = {"plain", "real", "xpose"};
+        snprintf(buf, sizeof(buf), "fft_%s_%s_n%d_%s", st.key.layout == LAYOUT_ROW ? "row" : "col", var[st.key.variant],
+                 1 << st.key.log2n, st.key.dir > 0 ? "p" : "m");
+        const double lines = (double)(st.pp.q_end - st.pp.q_begin);
+        b = 2.0 * 16.0 * lines * (double)(1 << st.key.log2n);
+        if (st.key.variant == VAR_REAL && st.pp.real_mode == REAL_SPEQ) b += 16.0 * lines;
+    }
+    if (name && cap) { strncpy(name, buf, cap - 1); name[cap - 1] = 0; }
+    if (bytes) *bytes = b;
+    return NRB_OK;
+}
+
+int fill_uniform_device(double *d_out, u64 seed, u64 offset, u64 count, void *stream)
+{
+    AuxParams ap;
+    memset(&ap, 0, sizeof(ap));
+    ap.kind = AUX_FILL;
+    ap.out = (double2 *)d_out;
+    ap.n = count; ap.m = seed; ap.count = offset;
+    if (be_launch_aux(ap, stream) != 0) { set_error(std::string("kernel launch failed: ") + be_last_error()); return NRB_ERR_CUDA; }
+    return NRB_OK;
 }
 
 // ------------------------------------------------------------------ slab-decomposed rlft3

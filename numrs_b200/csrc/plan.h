@@ -26,6 +26,9 @@ int be_stream_create(void **stream);
 int be_stream_destroy(void *stream);
 void *be_host_alloc(size_t bytes);
 void be_host_free(void *p);
+void *be_event_record(void *stream);
+float be_event_elapsed_ms(void *a, void *b);
+void be_event_destroy(void *e);
 const char *be_last_error();
 
 void set_error(const std::string &msg);   // thread-local message behind nrb_last_error()
@@ -87,6 +90,12 @@ struct Plan {
 // builders; return NRB_* codes
 int build_plan(Plan &pl, int kind, const size_t *dims, size_t ndim, size_t batch);
 int exec_plan(Plan &pl, double *d_io, double *d_aux, double *d_out, int isign, int arg, void *stream);
+// same as exec_plan but brackets every launch with events; ms[i] = duration of launch i (blocks)
+int profile_plan(Plan &pl, double *d_io, double *d_aux, double *d_out, int isign, int arg, void *stream, float *ms,
+                 int cap);
+// description of launch i: kernel name and the bytes it must read + write (algorithmic)
+int describe_launch(const Plan &pl, int isign, int idx, char *name, size_t cap, double *bytes);
+int fill_uniform_device(double *d_out, u64 seed, u64 offset, u64 count, void *stream);
 
 // slab-decomposed rlft3 (one rank's share)
 struct SlabPlan {

@@ -1,0 +1,125 @@
+"""Parity cases shared by the CPU tier (emulated kernels) and the GPU tier (CUDA library).
+
+Every check compares the library under test, called through the C ABI (host-slice entry
+points of include/numrs_b200.h via numrs_b200's mirror of the reference interface), against
+the CPU oracle (oracle/nr_oracle.c) on the same seeded input.
+
+Tolerance (BASELINE.json north_star): relative L2 error <= 1e-12 * log2(N).
+"""
+import math
+
+import numpy as np
+
+import numrs_b200 as nb
+import oracle as O
+
+
+def tol(npoints):
+    return 1e-12 * max(1.0, math.log2(max(2, npoints)))
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64).ravel()
+    b = np.asarray(b, dtype=np.float64).ravel()
+    nb_ = np.linalg.norm(b)
+    return float(np.linalg.norm(a - b) / (nb_ if nb_ > 0 else 1.0))
+
+
+def gen(seed, count, offset=0):
+    return O.fill_uniform(seed, offset, count)
+
+
+def check_four1(L, nn, seed=1001):
+    x = gen(seed, 2 * nn)
+    for isign in (1, -1):
+        ref = O.four1(x.copy(), nn, isign)
+        got = x.copy()
+        nb.four1(got, nn, isign, L)
+        assert rel(got, ref) <= tol(nn), (nn, isign, rel(got, ref))
+    # round trip: inverse(forward(x)) = nn * x   (FFT_1.rs:246-267)
+    y = x.copy()
+    nb.four1(y, nn, 1, L)
+    nb.four1(y, nn, -1, L)
+    assert rel(y / nn, x) <= tol(nn)
+
+
+def check_four1_batch(L, nn, count, seed=1002, scattered=False):
+    big = gen(seed, 2 * nn * count)
+    arrs = [big[2 * nn * b:2 * nn * (b + 1)] for b in range(count)]
+    if scattered:
+        arrs = [a.copy() for a in arrs]
+    refs = [O.four1(a.copy(), nn, 1) for a in arrs]
+    nb.FFTProcessor(L).fft_batch(arrs, 1)
+    for a, r in zip(arrs, refs):
+        assert rel(a, r) <= tol(nn)
+
+
+def check_fourn(L, shape, seed=1003):
+    n = int(np.prod(shape))
+    x = gen(seed, 2 * n)
+    for isign in (1, -1):
+        ref = O.fourn(x.copy(), list(shape), isign)
+        got = x.copy()
+        nb.fourn(got, list(shape), len(shape), isign, L)
+        assert rel(got, ref) <= tol(n), (shape, isign, rel(got, ref))
+
+
+def check_realft(L, n, seed=1004):
+    x = gen(seed, n)
+    ref = O.realft(x.copy(), n, 1)
+    got = x.copy()
+    nb.realft(got, n, 1, L)
+    assert rel(got, ref) <= tol(n), (n, rel(got, ref))
+    # inverse on an arbitrary packed spectrum, and the (n/2)*x round trip
+    s = gen(seed + 100, n)
+    ref_i = O.realft(s.copy(), n, -1)
+    got_i = s.copy()
+    nb.realft(got_i, n, -1, L)
+    assert rel(got_i, ref_i) <= tol(n)
+    nb.realft(got, n, -1, L)
+    assert rel(got * (2.0 / n), x) <= tol(n)
+
+
+def check_rlft3(L, shape, seed=1006):
+    nn1, nn2, nn3 = shape
+    n = nn1 * nn2 * nn3
+    x = gen(seed, n).reshape(shape)
+    rd, rs = O.rlft3(x.copy(), np.zeros((nn1, 2 * nn2)), 1)
+    d, s = x.copy(), np.zeros((nn1, 2 * nn2))
+    nb.rlft3(d, s, nn1, nn2, nn3, 1, L)
+    assert rel(d, rd) <= tol(n), (shape, "data", rel(d, rd))
+    assert rel(s, rs) <= tol(n), (shape, "speq", rel(s, rs))
+    # inverse of an arbitrary (not Hermitian-consistent) spectrum
+    xi = gen(seed + 100, n).reshape(shape)
+    si = gen(seed + 200, 2 * nn1 * nn2).reshape(nn1, 2 * nn2)
+    ri, _ = O.rlft3(xi.copy(), si.copy(), -1)
+    gi, gs = xi.copy(), si.copy()
+    nb.rlft3(gi, gs, nn1, nn2, nn3, -1, L)
+    assert rel(gi, ri) <= tol(n), (shape, "inverse", rel(gi, ri))
+    # round trip = (nn1*nn2*nn3/2) * x
+    nb.rlft3(d, s, nn1, nn2, nn3, -1, L)
+    assert rel(d * (2.0 / n), x) <= tol(n)
+
+
+def check_convlv(L, n, m, seed=1004):
+    a = gen(seed, n)
+    r = gen(seed + 1, m) / 64.0
+    for pad in (nb.NRB_PAD_LITERAL, nb.NRB_PAD_NR):
+        rc, ref = O.convlv(a, r, 1, pad)
+        assert rc == 0
+        got = nb.convlv(a, r, 1, pad, L)
+        assert rel(got, ref) <= tol(n), (n, m, pad, rel(got, ref))
+    # deconvolution on a well-conditioned response
+    rw = 0.5 ** np.arange(min(m, 40))
+    rc, ref = O.convlv(a, rw, -1, 0)
+    got = nb.convlv(a, rw, -1, 0, L)
+    assert rel(got, ref) <= 1e-10, (n, m, "deconv", rel(got, ref))
+
+
+def check_correl(L, n, seed=1004):
+    a = gen(seed, n)
+    b = gen(seed + 7, n)
+    rc, ref = O.correl(a, b)
+    assert rc == 0
+    got = nb.correl(a, b, L)
+    assert rel(got, ref) <= tol(n), (n, rel(got, ref))

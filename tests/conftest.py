@@ -1,0 +1,43 @@
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def emu():
+    """TEST-ONLY host emulation of the kernels (tests/emu); validates planner + index math on CPU."""
+    from numrs_b200 import _lib
+    d = os.path.join(ROOT, "tests", "emu")
+    subprocess.check_call(["make", "-C", d, "-s"])
+    return _lib.Library(os.path.join(d, "libnrb_emu.so"))
+
+
+@pytest.fixture(scope="session")
+def gpu():
+    """The product CUDA library on a real device.  No device => hard failure (no CPU fallback)."""
+    import numrs_b200
+    L = numrs_b200.lib()
+    if L.device_count() <= 0:
+        pytest.fail("no CUDA device visible: numrs_b200 has no CPU fallback")
+    return L
+
+
+@pytest.fixture(autouse=True)
+def _reset_options(request):
+    yield
+    for name in ("emu", "gpu"):
+        if name in request.fixturenames:
+            L = request.getfixturevalue(name)
+            L.set_option("col_max_log2", 10)
+            L.set_option("row_max_log2", 13)
+            L.set_option("l2_group_bytes", 32 << 20)

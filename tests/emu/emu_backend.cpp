@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <ucontext.h>
 
 #include <string>
@@ -155,6 +156,18 @@ int be_launch_aux(const AuxParams &a, void *)
     return 0;
 }
 
+void *be_event_record(void *)
+{
+    struct timespec *ts = new timespec;
+    clock_gettime(CLOCK_MONOTONIC, ts);
+    return ts;
+}
+float be_event_elapsed_ms(void *a, void *b)
+{
+    const timespec *x = (const timespec *)a, *y = (const timespec *)b;
+    return (float)((y->tv_sec - x->tv_sec) * 1e3 + (y->tv_nsec - x->tv_nsec) * 1e-6);
+}
+void be_event_destroy(void *e) { delete (timespec *)e; }
 int be_malloc(void **p, size_t bytes) { *p = malloc(bytes ? bytes : 16); return *p ? 0 : -1; }
 int be_free(void *p) { free(p); return 0; }
 int be_h2d(void *d, const void *s, size_t n, void *) { memcpy(d, s, n); return 0; }

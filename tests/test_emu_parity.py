@@ -1,0 +1,228 @@
+"""CPU tier: planner + kernel index arithmetic, validated by running the device source under
+the TEST-ONLY host emulation (tests/emu) through the same C ABI, against the oracle.
+This does not measure or ship anything; GPU parity proper is tests/test_gpu_parity.py."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import numrs_b200 as nb
+import oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = np.load(os.path.join(HERE, "golden", "golden_small.npz"))
+KNOWN = json.load(open(os.path.join(HERE, "golden", "reference_known_answers.json")))
+
+
+@pytest.mark.parametrize("nn", [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192])
+def test_four1_single_pass(emu, nn):
+    cases.check_four1(emu, nn)
+
+
+@pytest.mark.parametrize("nn", [1 << 14, 1 << 16])
+def test_four1_four_step(emu, nn):
+    cases.check_four1(emu, nn)
+
+
+@pytest.mark.parametrize("nn", [64, 512, 4096, 1 << 13])
+def test_four1_multi_step_three_factors(emu, nn):
+    emu.set_option("row_max_log2", 4)
+    emu.set_option("col_max_log2", 3)
+    cases.check_four1(emu, nn)
+
+
+def test_four1_identity_sizes_and_errors(emu):
+    x = np.array([3.0, 4.0])
+    nb.four1(x, 1, 1, emu)                      # nn = 1 is the identity (FFT_1.rs:5-44)
+    assert list(x) == [3.0, 4.0]
+    assert emu.four1(np.zeros(12), 6, 1) == nb._lib.NRB_ERR_NOT_POW2
+    assert emu.four1(np.zeros(16), 8, 0) == nb._lib.NRB_ERR_INVALID_ISIGN
+
+
+def test_four1_batch(emu):
+    cases.check_four1_batch(emu, 256, 37)                   # contiguous slices, ragged tile
+    cases.check_four1_batch(emu, 64, 5, scattered=True)     # separate allocations
+    # mixed lengths in one call (FFT_1.rs:185-189 allows any slice lengths)
+    arrs = [O.fill_uniform(5, 0, 2 * n) for n in (8, 64, 8, 1024, 1)]
+    refs = [O.four1(a.copy(), a.size // 2, -1) for a in arrs]
+    nb.FFTProcessor(emu).fft_batch(arrs, -1)
+    for a, r in zip(arrs, refs):
+        assert cases.rel(a, r) <= cases.tol(a.size)
+
+
+@pytest.mark.parametrize("shape", [(2,), (4, 8, 2), (8, 16), (16,), (2, 2), (32, 4, 8), (64, 64), (8, 8, 8, 4),
+                                   (2, 1024), (1024, 2), (128, 32), (2048, 4), (4, 4096)])
+def test_fourn(emu, shape):
+    cases.check_fourn(emu, shape)
+
+
+@pytest.mark.parametrize("shape", [(64, 64), (16, 32, 8), (256, 4)])
+def test_fourn_multi_step_axes(emu, shape):
+    emu.set_option("row_max_log2", 3)
+    emu.set_option("col_max_log2", 2)
+    cases.check_fourn(emu, shape)
+
+
+def test_fourn_validation(emu):
+    for case in KNOWN["fourn_validation"]["cases"]:
+        n = int(np.prod(case["nn"]))
+        if case["ok"]:
+            nb.fourn(np.zeros(2 * n), case["nn"], case["ndim"], case["isign"], emu)
+        else:
+            with pytest.raises(ValueError):
+                nb.fourn(np.zeros(2 * n), case["nn"], case["ndim"], case["isign"], emu)
+    with pytest.raises(ValueError):
+        nb.fourn(np.zeros(4), [2], 0, 1, emu)       # ndim == 0
+    with pytest.raises(ValueError):
+        nb.fourn(np.zeros(4), [2], 2, 1, emu)       # ndim > nn.len()
+
+
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 32, 64, 256, 1024, 4096, 1 << 14, 1 << 15])
+def test_realft(emu, n):
+    cases.check_realft(emu, n)
+
+
+@pytest.mark.parametrize("n", [16, 256, 4096])
+def test_realft_large_line_path(emu, n):
+    emu.set_option("row_max_log2", 2)       # forces c2c passes + standalone untangle kernel
+    emu.set_option("col_max_log2", 3)
+    cases.check_realft(emu, n)
+
+
+def test_realft_asserts_and_batch(emu):
+    with pytest.raises(AssertionError):
+        nb.realft(np.zeros(6), 5, 1, emu)            # Real_FT.rs:5
+    with pytest.raises(AssertionError):
+        nb.realft(np.zeros(4), 8, 1, emu)            # Real_FT.rs:6
+    xs = [O.fill_uniform(9, i * 512, 512) for i in range(5)]
+    refs = [O.realft(x.copy(), 512, 1) for x in xs]
+    nb.RealFTProcessor(emu).process_batch([(x, 512, 1) for x in xs])
+    for x, r in zip(xs, refs):
+        assert cases.rel(x, r) <= cases.tol(512)
+    # isign other than 1 means inverse (Real_FT.rs:10,15)
+    a, b = refs[0].copy(), refs[0].copy()
+    nb.realft(a, 512, -1, emu)
+    nb.realft(b, 512, 7, emu)
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("shp", [(8, 8, 8), (4, 16, 8), (1, 4, 4), (2, 2, 2), (16, 8, 32), (1, 1, 2), (2, 1, 4),
+                                 (32, 32, 32), (4, 4, 2), (8, 64, 16), (1, 1, 64), (64, 1, 2)])
+def test_rlft3(emu, shp):
+    cases.check_rlft3(emu, shp)
+
+
+def test_rlft3_grouped_and_multi_step(emu):
+    emu.set_option("l2_group_bytes", 4096)   # several x-plane groups
+    cases.check_rlft3(emu, (16, 16, 16))
+    emu.set_option("col_max_log2", 2)
+    emu.set_option("row_max_log2", 2)
+    cases.check_rlft3(emu, (16, 32, 32))
+
+
+def test_rlft3_asserts(emu):
+    d, s = np.zeros((4, 4, 4)), np.zeros((4, 8))
+    with pytest.raises(AssertionError):
+        nb.rlft3(d, s, 4, 4, 4, 0, emu)              # Real_FT3.rs:17
+    with pytest.raises(AssertionError):
+        nb.rlft3(d, s, 4, 4, 8, 1, emu)              # Real_FT3.rs:18
+    with pytest.raises(AssertionError):
+        nb.rlft3(d, np.zeros((4, 4)), 4, 4, 4, 1, emu)   # Real_FT3.rs:19
+
+
+@pytest.mark.parametrize("n,m", [(4, 2), (2, 1), (2, 2), (64, 5), (64, 64), (256, 9), (1024, 33), (1 << 14, 100),
+                                 (1 << 15, 4096)])
+def test_convlv(emu, n, m):
+    cases.check_convlv(emu, n, m)
+
+
+def test_convlv_reference_known_answers(emu):
+    ka = KNOWN["convlv_basic"]
+    y = nb.convlv(ka["data"], ka["respns"], ka["isign"], _L=emu)
+    for idx, val in ka["expect_at"].items():
+        assert abs(y[int(idx)] - val) < ka["abs_tol"]
+    assert abs(nb.ConvlvProcessor(emu).process(ka["data"], ka["respns"], 1)[1] - 3.0) < 1e-10   # Convolve.rs:445-454
+    for case in KNOWN["convlv_errors"]["cases"]:
+        with pytest.raises(nb.ConvlvError) as ei:
+            nb.convlv(case["data"], case["respns"], case["isign"], _L=emu)
+        assert ei.value.kind == case["err"]
+    with pytest.raises(nb.ConvlvError) as ei:      # odd n: the reference panics in realft (Convolve.rs:427-442)
+        nb.convlv([1.0, 2.0, 3.0], [1.0, 1.0], 1, _L=emu)
+    assert ei.value.kind == nb.ConvlvError.FftError
+
+
+def test_convlv_batch(emu):
+    sigs = [O.fill_uniform(1004, i * 1024, 1024) for i in range(7)]
+    r = O.fill_uniform(1005, 0, 17) / 64
+    emu.set_option("l2_group_bytes", 3 * 1024 * 16)   # several signal groups
+    outs = nb.convlv_batch(sigs, r, 1, _L=emu)
+    for s, o in zip(sigs, outs):
+        assert cases.rel(o, O.convlv(s, r, 1)[1]) <= cases.tol(1024)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 7, 32, 64, 128, 1024, 1 << 14])
+def test_correl(emu, n):
+    cases.check_correl(emu, n)
+
+
+def test_correl_reference_known_answers(emu):
+    y = nb.correl(KNOWN["correl_basic"]["a"], KNOWN["correl_basic"]["b"], emu)
+    assert y[0] == 30.0 and y[0] > y[1]
+    assert list(nb.correl([1.0, 2.0], [1.0, 2.0], emu)) == KNOWN["correl_direct_small"]["expect"]
+    assert nb.autocorrel([1.0, 2.0, 1.0, 2.0], emu)[0] == 10.0
+    outs = nb.correl_batch([(np.array(a, float), np.array(b, float)) for a, b in KNOWN["correl_batch"]["pairs"]], emu)
+    assert [o[0] for o in outs] == KNOWN["correl_batch"]["expect0"]
+    for case in KNOWN["correl_errors"]["cases"]:
+        with pytest.raises(nb.CorrelError) as ei:
+            nb.correl(case["a"], case["b"], emu)
+        assert ei.value.kind == case["err"]
+
+
+def test_correl_batch_large(emu):
+    a = [O.fill_uniform(1, i * 256, 256) for i in range(5)]
+    b = [O.fill_uniform(2, i * 256, 256) for i in range(5)]
+    emu.set_option("l2_group_bytes", 2 * 256 * 8 * 3)
+    outs = nb.correl_batch(list(zip(a, b)), emu)
+    for x, y, o in zip(a, b, outs):
+        assert cases.rel(o, O.correl(x, y)[1]) <= cases.tol(256)
+
+
+def test_golden_fixtures(emu):
+    for nn in (8, 64, 1024):
+        for s, t in ((1, "p"), (-1, "m")):
+            x = G[f"four1_{nn}_in"].copy()
+            nb.four1(x, nn, s, emu)
+            assert cases.rel(x, G[f"four1_{nn}_{t}"]) <= cases.tol(nn)
+    for shp in ((8, 8, 8), (4, 16, 8), (2, 4, 32)):
+        tag = "x".join(map(str, shp))
+        d, s = G[f"rlft3_{tag}_in"].copy(), np.zeros((shp[0], 2 * shp[1]))
+        nb.rlft3(d, s, *shp, 1, emu)
+        assert cases.rel(d, G[f"rlft3_{tag}_data"]) <= cases.tol(d.size)
+        assert cases.rel(s, G[f"rlft3_{tag}_speq"]) <= cases.tol(d.size)
+
+
+def test_plan_api_device_pointers(emu):
+    """Device-resident plan API (under emulation 'device' pointers are host pointers)."""
+    n = 4096
+    x = O.fill_uniform(3, 0, 2 * n * 3)
+    ref = np.concatenate([O.four1(x[2 * n * b:2 * n * (b + 1)].copy(), n, 1) for b in range(3)])
+    plan = emu.plan_create(nb.KIND_FOUR1, [n], batch=3)
+    assert plan.num_launches(1) == 1 and plan.workspace_bytes() == 0
+    plan.exec(x.ctypes.data, isign=1)
+    assert cases.rel(x, ref) <= cases.tol(n)
+    prof = plan.profile(x.ctypes.data, isign=-1)
+    assert prof[0][0] == "fft_row_plain_n4096_m" and prof[0][1] == 2 * 16 * n * 3
+    plan.destroy()
+    big = emu.plan_create(nb.KIND_FOUR1, [1 << 16], batch=1)
+    assert big.num_launches(1) == 2 and big.workspace_bytes() == (1 << 16) * 16
+    big.destroy()
+    with pytest.raises(nb.NrbError):
+        emu.plan_create(nb.KIND_FOURN, [8, 1], batch=1)
+
+
+def test_device_fill_matches_generator(emu):
+    out = np.zeros(5000)
+    emu.fill_uniform_device(out.ctypes.data, 1006, 77, out.size)
+    assert np.array_equal(out, O.fill_uniform(1006, 77, out.size))

@@ -1,0 +1,266 @@
+"""GPU tier: the CUDA library (numrs_b200/libnumrs_b200.so), called through the C ABI, against the
+CPU oracle on the same seeded inputs, the committed golden vectors, and -- at BASELINE.json's
+full sizes -- size-independent properties (round trips, linearity, Parseval, shift theorem).
+
+Tolerance (BASELINE.json north_star): relative L2 <= 1e-12 * log2(N)."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import numrs_b200 as nb
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = np.load(os.path.join(HERE, "golden", "golden_small.npz"))
+KNOWN = json.load(open(os.path.join(HERE, "golden", "reference_known_answers.json")))
+
+
+# ------------------------------------------------------------------ oracle parity
+@pytest.mark.parametrize("nn", [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 1 << 14, 1 << 17, 1 << 20])
+def test_four1(gpu, nn):
+    cases.check_four1(gpu, nn)
+
+
+def test_four1_multi_step_three_factors(gpu):
+    gpu.set_option("row_max_log2", 6)
+    gpu.set_option("col_max_log2", 5)
+    cases.check_four1(gpu, 1 << 14)
+    cases.check_four1(gpu, 1 << 16)
+
+
+def test_four1_batch(gpu):
+    cases.check_four1_batch(gpu, 4096, 64)                   # config C2 shape, reduced batch
+    cases.check_four1_batch(gpu, 256, 37)
+    cases.check_four1_batch(gpu, 64, 5, scattered=True)
+    arrs = [O.fill_uniform(5, 0, 2 * n) for n in (8, 64, 8, 1024, 1)]
+    refs = [O.four1(a.copy(), a.size // 2, -1) for a in arrs]
+    nb.FFTProcessor().fft_batch(arrs, -1)
+    for a, r in zip(arrs, refs):
+        assert cases.rel(a, r) <= cases.tol(a.size)
+
+
+@pytest.mark.parametrize("shape", [(2,), (4, 8, 2), (8, 16), (2, 2), (32, 4, 8), (64, 64), (8, 8, 8, 4), (2, 1024),
+                                   (1024, 2), (2048, 4), (4, 4096), (512, 512), (64, 128, 32), (2048, 1024), (16384, 16)])
+def test_fourn(gpu, shape):
+    cases.check_fourn(gpu, shape)
+
+
+def test_fourn_validation(gpu):
+    for case in KNOWN["fourn_validation"]["cases"]:
+        n = int(np.prod(case["nn"]))
+        if case["ok"]:
+            nb.fourn(np.zeros(2 * n), case["nn"], case["ndim"], case["isign"])
+        else:
+            with pytest.raises(ValueError):
+                nb.fourn(np.zeros(2 * n), case["nn"], case["ndim"], case["isign"])
+
+
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 64, 256, 1024, 4096, 1 << 14, 1 << 15, 1 << 18, 1 << 21])
+def test_realft(gpu, n):
+    cases.check_realft(gpu, n)
+
+
+def test_realft_large_line_path(gpu):
+    gpu.set_option("row_max_log2", 5)
+    gpu.set_option("col_max_log2", 5)
+    cases.check_realft(gpu, 1 << 14)
+
+
+@pytest.mark.parametrize("shp", [(8, 8, 8), (4, 16, 8), (1, 4, 4), (2, 2, 2), (16, 8, 32), (1, 1, 2), (2, 1, 4),
+                                 (32, 32, 32), (4, 4, 2), (8, 64, 16), (64, 64, 64), (128, 128, 128), (16, 256, 512),
+                                 (2, 2048, 64)])
+def test_rlft3(gpu, shp):
+    cases.check_rlft3(gpu, shp)
+
+
+def test_rlft3_grouped(gpu):
+    gpu.set_option("l2_group_bytes", 1 << 20)      # 128^3: many x-plane groups
+    cases.check_rlft3(gpu, (128, 128, 128))
+
+
+@pytest.mark.parametrize("n,m", [(4, 2), (2, 1), (64, 5), (64, 64), (1024, 33), (1 << 14, 100), (1 << 16, 4096),
+                                 (1 << 20, 4096)])
+def test_convlv(gpu, n, m):
+    cases.check_convlv(gpu, n, m)
+
+
+def test_convlv_reference_known_answers(gpu):
+    ka = KNOWN["convlv_basic"]
+    y = nb.convlv(ka["data"], ka["respns"], ka["isign"])
+    for idx, val in ka["expect_at"].items():
+        assert abs(y[int(idx)] - val) < ka["abs_tol"]
+    for case in KNOWN["convlv_errors"]["cases"]:
+        with pytest.raises(nb.ConvlvError) as ei:
+            nb.convlv(case["data"], case["respns"], case["isign"])
+        assert ei.value.kind == case["err"]
+
+
+def test_convlv_batch(gpu):
+    sigs = [O.fill_uniform(1004, i << 16, 1 << 16) for i in range(9)]
+    r = O.fill_uniform(1005, 0, 4096) / 64
+    outs = nb.convlv_batch(sigs, r, 1)
+    for s, o in zip(sigs, outs):
+        assert cases.rel(o, O.convlv(s, r, 1)[1]) <= cases.tol(1 << 16)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 32, 64, 1024, 1 << 14, 1 << 20])
+def test_correl(gpu, n):
+    cases.check_correl(gpu, n)
+
+
+def test_correl_reference_known_answers(gpu):
+    y = nb.correl(KNOWN["correl_basic"]["a"], KNOWN["correl_basic"]["b"])
+    assert y[0] == 30.0 and y[0] > y[1]
+    assert list(nb.correl([1.0, 2.0], [1.0, 2.0])) == KNOWN["correl_direct_small"]["expect"]
+    outs = nb.correl_batch([(np.array(a, float), np.array(b, float)) for a, b in KNOWN["correl_batch"]["pairs"]])
+    assert [o[0] for o in outs] == KNOWN["correl_batch"]["expect0"]
+    for case in KNOWN["correl_errors"]["cases"]:
+        with pytest.raises(nb.CorrelError) as ei:
+            nb.correl(case["a"], case["b"])
+        assert ei.value.kind == case["err"]
+
+
+def test_golden_fixtures(gpu):
+    for nn in (8, 64, 1024):
+        for s, t in ((1, "p"), (-1, "m")):
+            x = G[f"four1_{nn}_in"].copy()
+            nb.four1(x, nn, s)
+            assert cases.rel(x, G[f"four1_{nn}_{t}"]) <= cases.tol(nn)
+    for shape in ((4, 8, 2), (8, 16), (16, 4, 8)):
+        tag = "x".join(map(str, shape))
+        for s, t in ((1, "p"), (-1, "m")):
+            x = G[f"fourn_{tag}_in"].copy()
+            nb.fourn(x, list(shape), len(shape), s)
+            assert cases.rel(x, G[f"fourn_{tag}_{t}"]) <= cases.tol(x.size)
+    for n in (8, 256, 2048):
+        x = G[f"realft_{n}_in"].copy()
+        nb.realft(x, n, 1)
+        assert cases.rel(x, G[f"realft_{n}_fwd"]) <= cases.tol(n)
+    for shp in ((8, 8, 8), (4, 16, 8), (2, 4, 32)):
+        tag = "x".join(map(str, shp))
+        d, s = G[f"rlft3_{tag}_in"].copy(), np.zeros((shp[0], 2 * shp[1]))
+        nb.rlft3(d, s, *shp, 1)
+        assert cases.rel(d, G[f"rlft3_{tag}_data"]) <= cases.tol(d.size)
+        assert cases.rel(s, G[f"rlft3_{tag}_speq"]) <= cases.tol(d.size)
+    assert cases.rel(nb.convlv(G["convlv_128_9_in"], G["convlv_128_9_resp"], 1), G["convlv_128_9_out"]) <= cases.tol(128)
+    assert cases.rel(nb.correl(G["correl_128_a"], G["correl_128_b"]), G["correl_128_out"]) <= cases.tol(128)
+
+
+def test_device_fill_matches_generator(gpu):
+    import torch
+    t = torch.empty(100003, dtype=torch.float64, device="cuda")
+    gpu.fill_uniform_device(t.data_ptr(), 1006, 77, t.numel(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(t.cpu().numpy(), O.fill_uniform(1006, 77, t.numel()))
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_full_size_four1_2pow20_round_trip_and_oracle(gpu):
+    """BASELINE config 1: four1 N = 2^20 forward + inverse (oracle finishes in < 1 s)."""
+    nn = 1 << 20
+    x = O.fill_uniform(1001, 0, 2 * nn)
+    y = x.copy()
+    nb.four1(y, nn, 1)
+    assert cases.rel(y, O.four1(x.copy(), nn, 1, mt=True)) <= cases.tol(nn)
+    nb.four1(y, nn, -1)
+    assert cases.rel(y / nn, x) <= cases.tol(nn)
+
+
+def test_full_size_batched_four1_4096x4096(gpu):
+    """BASELINE config 2 at full size: 4096 transforms of N = 4096 -- oracle on a sample of the
+    batch, Parseval and round trip on all of it."""
+    nn, cnt = 4096, 4096
+    x = O.fill_uniform(1002, 0, 2 * nn * cnt)
+    y = x.copy()
+    arrs = [y[2 * nn * b:2 * nn * (b + 1)] for b in range(cnt)]
+    nb.FFTProcessor().fft_batch(arrs, 1)
+    for b in (0, 1, 17, 2048, 4095):
+        assert cases.rel(arrs[b], O.four1(x[2 * nn * b:2 * nn * (b + 1)].copy(), nn, 1)) <= cases.tol(nn)
+    e_in = (x.reshape(cnt, -1) ** 2).sum(axis=1)
+    e_out = (y.reshape(cnt, -1) ** 2).sum(axis=1)
+    assert np.max(np.abs(e_out / (nn * e_in) - 1.0)) < 1e-12          # Parseval, unnormalised
+    nb.FFTProcessor().fft_batch(arrs, -1)
+    assert cases.rel(y / nn, x) <= cases.tol(nn)
+
+
+def test_full_size_fourn_8192x8192_properties(gpu):
+    """BASELINE config 3: fourn 8192 x 8192 (1 GiB).  Oracle-free checks: impulse response,
+    round trip, Parseval."""
+    n = 8192
+    x = O.fill_uniform(1003, 0, 2 * n * n)
+    e_in = float(np.dot(x, x))
+    y = x.copy()
+    nb.fourn(y, [n, n], 2, 1)
+    assert abs(float(np.dot(y, y)) / (n * n * e_in) - 1.0) < 1e-12
+    # DC bin = plain sum of the input
+    assert abs(y[0] - x[0::2].sum()) <= 1e-9 * n and abs(y[1] - x[1::2].sum()) <= 1e-9 * n
+    nb.fourn(y, [n, n], 2, -1)
+    y /= float(n * n)
+    assert cases.rel(y, x) <= cases.tol(n * n)
+    # shifted impulse -> pure phase ramp exp(+2 pi i (a*k1/n + b*k2/n))
+    imp = np.zeros(2 * n * n)
+    a, b = 3, 5
+    imp[2 * (a * n + b)] = 1.0
+    nb.fourn(imp, [n, n], 2, 1)
+    k1 = np.array([0, 1, 17, 4096, 8191])
+    k2 = np.array([0, 2, 33, 4097, 8190])
+    for i in k1:
+        ph = 2 * np.pi * ((a * i) % n / n + (b * k2) % n / n)
+        got = imp[2 * (i * n + k2)] + 1j * imp[2 * (i * n + k2) + 1]
+        assert np.max(np.abs(got - np.exp(1j * ph))) < 1e-12
+
+
+def test_full_size_rlft3_512_properties(gpu):
+    """BASELINE config 5 at full size (512^3, 1 GiB): round trip, Parseval, DC bin, and oracle
+    parity on the same algorithm at 128^3 happens in test_rlft3."""
+    n = 512
+    x = O.fill_uniform(1006, 0, n ** 3).reshape(n, n, n)
+    d, s = x.copy(), np.zeros((n, 2 * n))
+    nb.rlft3(d, s, n, n, n, 1)
+    assert abs(d[0, 0, 0] - x.sum()) <= 1e-8 * n and d[0, 0, 1] == 0.0
+    # Parseval with Hermitian weights: bins k3 = 1..n/2-1 count twice
+    dd = d.reshape(n, n, n // 2, 2)
+    p = (dd[:, :, 0] ** 2).sum() + 2.0 * (dd[:, :, 1:] ** 2).sum() + (s ** 2).sum()
+    assert abs(p / (float(n) ** 3 * float((x ** 2).sum())) - 1.0) < 1e-12
+    nb.rlft3(d, s, n, n, n, -1)
+    d *= 2.0 / float(n) ** 3
+    assert cases.rel(d, x) <= cases.tol(n ** 3)
+
+
+def test_full_size_convlv_correl_2pow22(gpu):
+    """BASELINE config 4 shape (n = 2^22, m = 4096), reduced batch: oracle parity per signal."""
+    n, m, cnt = 1 << 22, 4096, 3
+    sigs = [O.fill_uniform(1004, i * n, n) for i in range(cnt)]
+    r = O.fill_uniform(1005, 0, m) / 64
+    outs = nb.convlv_batch(sigs, r, 1)
+    for sgl, o in zip(sigs, outs):
+        assert cases.rel(o, O.convlv(sgl, r, 1)[1]) <= cases.tol(n)
+    tmpl = [np.concatenate([O.fill_uniform(1005, 0, m), np.zeros(n - m)]) for _ in range(cnt)]
+    outs = nb.correl_batch(list(zip(sigs, tmpl)))
+    for sgl, t, o in zip(sigs, tmpl, outs):
+        assert cases.rel(o, O.correl(sgl, t)[1]) <= cases.tol(n)
+
+
+def test_linearity_and_plan_api_device_resident(gpu):
+    """Device-resident plan API with torch-allocated buffers on the current stream."""
+    import torch
+    n = 1 << 18
+    a = torch.from_numpy(O.fill_uniform(1, 0, 2 * n)).cuda()
+    b = torch.from_numpy(O.fill_uniform(2, 0, 2 * n)).cuda()
+    c = (2.0 * a - 3.0 * b).clone()
+    plan = gpu.plan_create(nb.KIND_FOUR1, [n], batch=1)
+    st = torch.cuda.current_stream().cuda_stream
+    for t in (a, b, c):
+        plan.exec(t.data_ptr(), isign=1, stream=st)
+    torch.cuda.synchronize()
+    lin = 2.0 * a - 3.0 * b
+    assert float(torch.linalg.norm(c - lin) / torch.linalg.norm(lin)) <= cases.tol(n)
+    prof = plan.profile(a.data_ptr(), isign=-1, stream=st)
+    assert len(prof) == plan.num_launches(-1) and all(ms > 0 for _, _, ms in prof)
+    plan.destroy()

@@ -1,0 +1,177 @@
+"""CPU tier: pins the oracle (oracle/nr_oracle.c) against numpy, a 50-digit mpmath DFT, the
+committed golden vectors and the known answers held by the reference's own unit tests."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = np.load(os.path.join(HERE, "golden", "golden_small.npz"))
+KNOWN = json.load(open(os.path.join(HERE, "golden", "reference_known_answers.json")))
+
+
+def rel(a, b):
+    return np.linalg.norm(np.ravel(a) - np.ravel(b)) / np.linalg.norm(np.ravel(b))
+
+
+def c(z):
+    return z[0::2] + 1j * z[1::2]
+
+
+def test_generator_c_equals_numpy():
+    assert np.array_equal(O.fill_uniform(1001, 12345, 4096), O.fill_uniform_py(1001, 12345, 4096))
+    x = O.fill_uniform(1006, 0, 1 << 16)
+    assert x.min() >= -1.0 and x.max() < 1.0 and abs(x.mean()) < 0.02
+
+
+@pytest.mark.parametrize("nn", [1, 2, 4, 8, 256, 1024, 4096, 1 << 15])
+def test_four1_vs_numpy(nn):
+    x = O.fill_uniform(1001, 0, 2 * nn)
+    for isign, ref in ((1, np.fft.ifft(c(x)) * nn), (-1, np.fft.fft(c(x)))):
+        for fn in (O.four1, O.four1_optimized):
+            assert rel(c(fn(x.copy(), nn, isign)), ref) < 1e-13 * max(1, np.log2(max(nn, 2)))
+    assert np.allclose(O.four1(x.copy(), nn, 1, mt=True), O.four1(x.copy(), nn, 1), rtol=0, atol=0)
+
+
+def test_four1_vs_mpmath():
+    import mpmath as mp
+    mp.mp.dps = 50
+    nn = 32
+    x = O.fill_uniform(1001, 7, 2 * nn)
+    z = [mp.mpc(x[2 * k], x[2 * k + 1]) for k in range(nn)]
+    ref = [sum(z[j] * mp.e ** (2j * mp.pi * j * k / nn) for j in range(nn)) for k in range(nn)]
+    got = c(O.four1(x.copy(), nn, 1))
+    err = max(abs(complex(r) - g) for r, g in zip(ref, got))
+    assert err < 1e-13
+
+
+def test_four1_reference_round_trip():
+    # FFT_1.rs:246-267
+    n = 1024
+    t = np.arange(n) / n
+    sig = np.sin(2 * np.pi * 5 * t) + 0.5 * np.cos(2 * np.pi * 20 * t)
+    z = np.zeros(2 * n)
+    z[0::2] = sig
+    O.four1(z, n, 1)
+    O.four1(z, n, -1)
+    assert np.max(np.abs(z[0::2] / n - sig)) < KNOWN["four1_round_trip"]["abs_tol"]
+
+
+@pytest.mark.parametrize("shape", [(4, 8, 2), (8, 16), (16,), (2, 2), (32, 4, 8), (64, 64)])
+def test_fourn_vs_numpy(shape):
+    n = int(np.prod(shape))
+    x = O.fill_uniform(1003, 0, 2 * n)
+    for isign in (1, -1):
+        ref = np.fft.ifftn(c(x).reshape(shape)) * n if isign == 1 else np.fft.fftn(c(x).reshape(shape))
+        assert rel(c(O.fourn(x.copy(), list(shape), isign)), ref.ravel()) < 1e-13 * np.log2(n)
+        assert np.array_equal(O.fourn(x.copy(), list(shape), isign, mt=True), O.fourn(x.copy(), list(shape), isign))
+
+
+def test_fourn_validation_rules():
+    for case in KNOWN["fourn_validation"]["cases"]:
+        rc = O.fourn_validate(case["nn"], case["ndim"], case["isign"])
+        assert (rc == 0) == case["ok"]
+
+
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 256, 4096, 1 << 14])
+def test_realft_vs_numpy(n):
+    x = O.fill_uniform(1004, 0, n)
+    y = O.realft(x.copy(), n, 1)
+    F = np.conj(np.fft.rfft(x))
+    assert abs(y[0] - F[0].real) < 1e-12 and abs(y[1] - F[n // 2].real) < 1e-12
+    if n > 2:
+        assert rel(y[2::2] + 1j * y[3::2], F[1:n // 2]) < 1e-13 * np.log2(n)
+    assert rel(O.realft(y.copy(), n, -1) * 2 / n, x) < 1e-13 * np.log2(n)   # round trip = (n/2) x
+
+
+@pytest.mark.parametrize("shp", [(8, 8, 8), (4, 16, 8), (1, 4, 4), (2, 2, 2), (16, 8, 32)])
+def test_rlft3_vs_numpy(shp):
+    x = O.fill_uniform(1006, 0, int(np.prod(shp))).reshape(shp)
+    d, s = O.rlft3(x.copy(), np.zeros((shp[0], 2 * shp[1])), 1)
+    F = np.conj(np.fft.rfftn(x))
+    dd = d.reshape(shp[0], shp[1], shp[2] // 2, 2)
+    ss = s.reshape(shp[0], shp[1], 2)
+    assert rel(dd[..., 0] + 1j * dd[..., 1], F[..., :shp[2] // 2]) < 1e-13 * np.log2(x.size)
+    assert rel(ss[..., 0] + 1j * ss[..., 1], F[..., shp[2] // 2]) < 1e-13 * np.log2(x.size)
+    d2, _ = O.rlft3(d.copy(), s.copy(), -1)
+    assert rel(d2 * 2 / x.size, x) < 1e-13 * np.log2(x.size)               # round trip = N/2 * x
+
+
+def test_rlft3_reference_ramp_round_trip():
+    # Real_FT3.rs:268-311 uses the ramp (i+j+k) on 8^3; the true factor is N/2 (ledger D8)
+    i, j, k = np.meshgrid(np.arange(8), np.arange(8), np.arange(8), indexing="ij")
+    x = (i + j + k).astype(np.float64)
+    d, s = O.rlft3(x.copy(), np.zeros((8, 16)), 1)
+    d, s = O.rlft3(d, s, -1)
+    assert np.allclose(d / (8 * 8 * 8 / 2), x, atol=1e-10)
+
+
+def test_convlv_known_answers_and_errors():
+    ka = KNOWN["convlv_basic"]
+    rc, y = O.convlv(ka["data"], ka["respns"], ka["isign"])
+    assert rc == 0
+    for idx, val in ka["expect_at"].items():
+        assert abs(y[int(idx)] - val) < ka["abs_tol"]
+    codes = {"EmptyInput": -1, "ResponseTooLong": -2, "InvalidIsign": -3}
+    for case in KNOWN["convlv_errors"]["cases"]:
+        rc, _ = O.convlv(case["data"], case["respns"], case["isign"])
+        assert rc == codes[case["err"]]
+
+
+@pytest.mark.parametrize("n,m", [(64, 5), (256, 2), (1024, 33), (4096, 4096)])
+def test_convlv_vs_numpy(n, m):
+    a = O.fill_uniform(1004, 0, n)
+    r = O.fill_uniform(1005, 0, m) / 64
+    for pad in (0, 1):
+        rc, y = O.convlv(a, r, 1, pad)
+        p = O.pad_response(r, n, pad)
+        assert rc == 0 and rel(y, np.fft.irfft(np.fft.rfft(a) * np.fft.rfft(p), n)) < 1e-13 * np.log2(n)
+    # NR padding really is NR's wrap-around
+    p = O.pad_response(np.arange(1.0, 6.0), 16, 1)
+    assert list(p[:3]) == [1, 2, 3] and list(p[-2:]) == [4, 5] and not p[3:-2].any()
+    # literal padding, m = 2 and m = 3 (SURVEY.md ledger L1)
+    assert list(O.pad_response([7.0, 9.0], 4, 0)) == [7, 9, 0, 0]
+    assert list(O.pad_response([1.0, 2.0, 3.0], 6, 0)) == [3, 2, 3, 0, 0, 1]
+
+
+def test_correl_known_answers_and_errors():
+    rc, y = O.correl(KNOWN["correl_basic"]["a"], KNOWN["correl_basic"]["b"])
+    assert rc == 0 and y[0] == 30.0 and y[0] > y[1]
+    rc, y = O.correl(*[KNOWN["correl_direct_small"][k] for k in ("a", "b")])
+    assert list(y) == KNOWN["correl_direct_small"]["expect"]
+    rc, y = O.correl(KNOWN["autocorrel"]["a"], KNOWN["autocorrel"]["a"])
+    assert y[0] == 10.0
+    for (a, b), e in zip(KNOWN["correl_batch"]["pairs"], KNOWN["correl_batch"]["expect0"]):
+        assert O.correl(a, b)[1][0] == e
+    codes = {"EmptyInput": -1, "LengthMismatch": -4}
+    for case in KNOWN["correl_errors"]["cases"]:
+        assert O.correl(case["a"], case["b"])[0] == codes[case["err"]]
+
+
+@pytest.mark.parametrize("n", [64, 1024, 1 << 14])
+def test_correl_vs_numpy(n):
+    a = O.fill_uniform(1004, 0, n)
+    b = O.fill_uniform(1011, 0, n)
+    rc, y = O.correl(a, b)
+    assert rc == 0 and rel(y, np.fft.irfft(np.fft.rfft(a) * np.conj(np.fft.rfft(b)), n)) < 1e-13 * np.log2(n)
+
+
+def test_oracle_matches_golden_fixtures():
+    for nn in (8, 64, 1024):
+        for s, t in ((1, "p"), (-1, "m")):
+            assert np.array_equal(O.four1(G[f"four1_{nn}_in"].copy(), nn, s), G[f"four1_{nn}_{t}"])
+    for shape in ((4, 8, 2), (8, 16), (16, 4, 8)):
+        tag = "x".join(map(str, shape))
+        for s, t in ((1, "p"), (-1, "m")):
+            assert np.array_equal(O.fourn(G[f"fourn_{tag}_in"].copy(), list(shape), s), G[f"fourn_{tag}_{t}"])
+    for n in (8, 256, 2048):
+        assert np.array_equal(O.realft(G[f"realft_{n}_in"].copy(), n, 1), G[f"realft_{n}_fwd"])
+    for shp in ((8, 8, 8), (4, 16, 8), (2, 4, 32)):
+        tag = "x".join(map(str, shp))
+        d, s = O.rlft3(G[f"rlft3_{tag}_in"].copy(), np.zeros((shp[0], 2 * shp[1])), 1)
+        assert np.array_equal(d, G[f"rlft3_{tag}_data"]) and np.array_equal(s, G[f"rlft3_{tag}_speq"])
+    assert np.array_equal(O.convlv(G["convlv_128_9_in"], G["convlv_128_9_resp"], 1)[1], G["convlv_128_9_out"])
+    assert np.array_equal(O.correl(G["correl_128_a"], G["correl_128_b"])[1], G["correl_128_out"])
