@@ -1,0 +1,646 @@
+#!/usr/bin/env python
+"""bench.py -- numrs_b200 headline benchmark (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl ours|reference] [--workload NAME]
+
+Default workload = BASELINE.json configs[4] (the configuration the metric is quoted on):
+rlft3 3-D real f64 512^3, one step = forward + inverse transform (isign=+1 then -1).
+  N = 1 : single-GPU plan (device-resident, nrb_plan_exec).
+  N > 1 : the volume is slab-decomposed across the N ranks (one process per GPU, launched by
+          torchrun); one NCCL all-to-all per direction.  Strong scaling: the total work is fixed.
+`value` = algorithmic HBM GB/s of the whole job: bytes every input element is read once and every
+output element written once (2 151 677 952 B per direction at 512^3) / time.
+
+Other workloads (not driver defaults; used for BASELINE.md section 5): four1_batch (configs[1]),
+four1_1m (configs[0] batched x64), fourn2d (configs[2]), convlv, correl (configs[3]).
+These shard by batch across ranks with no communication ("scaling": "weak" when --gpus > 1).
+
+--impl reference times the reference's CPU path: the reference (Rust) cannot be compiled in
+this image, so this is the oracle port (oracle/nr_oracle.c, which keeps the reference's
+algorithm and loop structure) with all host threads, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+HBM_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
+NVLINK_GBS = 770.0          # measured peer copy per direction (profiling guide)
+
+
+def rlft3_bytes(n1, n2, n3):
+    return 8.0 * n1 * n2 * n3 * 2 + 16.0 * n1 * n2      # one direction: read + write data, speq
+
+
+def rlft3_flops(n1, n2, n3):
+    n = float(n1) * n2 * n3
+    return 2.5 * n * np.log2(n)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], None, [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "samples": len(sm),
+                "power_w_max": max(power) if power else None, "reasons": sorted(reasons)}
+
+
+# =============================================================================== reference arm
+def run_reference(args, rank, world):
+    """Reference CPU path (oracle port, all host threads) on a bounded sample."""
+    if rank != 0:
+        return
+    import oracle as O
+    cores = O.num_threads()
+    wl = args.workload
+    if wl == "rlft3_512":
+        n = 256
+        x = O.fill_uniform(1006, 0, n ** 3).reshape(n, n, n)
+        s = np.zeros((n, 2 * n))
+        bytes_step = 2 * rlft3_bytes(n, n, n)
+
+        def step():
+            O.rlft3(x, s, 1, mt=True)
+            O.rlft3(x, s, -1, mt=True)
+        sample = f"rlft3 {n}^3 forward+inverse per step (1/8 of the 512^3 volume), oracle port with the reference's loop structure, {cores} OpenMP threads"
+    elif wl in ("four1_batch", "four1_1m"):
+        nn, cnt = (4096, 1024) if wl == "four1_batch" else (1 << 20, 4)
+        arrs = [O.fill_uniform(1002, b * 2 * nn, 2 * nn) for b in range(cnt)]
+        bytes_step = 2 * 32.0 * nn * cnt
+
+        def step():
+            O.fft_batch(arrs, 1, mt=True)
+            O.fft_batch(arrs, -1, mt=True)
+        sample = f"fft_batch {cnt} x four1({nn}) forward+inverse per step, {cores} threads (one transform per thread, FFT_1.rs:186)"
+    elif wl == "fourn2d":
+        n = 2048
+        x = O.fill_uniform(1003, 0, 2 * n * n)
+        bytes_step = 2 * 32.0 * n * n
+
+        def step():
+            O.fourn(x, [n, n], 1, mt=True)
+            O.fourn(x, [n, n], -1, mt=True)
+        sample = f"fourn {n}x{n} forward+inverse per step, {cores} threads"
+    else:
+        n, m, cnt = 1 << 20, 4096, max(2, cores)
+        sigs = [O.fill_uniform(1004, b * n, n) for b in range(cnt)]
+        r = O.fill_uniform(1005, 0, m) / 64
+        if wl == "convlv":
+            bytes_step = 16.0 * n * cnt + 8.0 * n
+
+            def step():
+                O.convlv_batch(sigs, r, 1, mt=True)
+        else:
+            tm = [np.concatenate([O.fill_uniform(1005, 0, m), np.zeros(n - m)]) for _ in range(cnt)]
+            bytes_step = 24.0 * n * cnt
+
+            def step():
+                O.correl_batch(sigs, tm, mt=True)
+        sample = f"{wl}_batch {cnt} x n=2^20, m=4096 per step, {cores} threads (one signal per thread)"
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = bytes_step * args.steps / dt / 1e9
+    line = {"impl": "reference", "metric": METRIC[wl], "value": val, "unit": "GB/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": SCALING[wl], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_for(wl, args.gpus),
+            "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+METRIC = {
+    "rlft3_512": "rlft3 f64 512^3 forward+inverse algorithmic HBM GB/s",
+    "four1_batch": "batched four1 f64 4096x4096 forward+inverse algorithmic HBM GB/s",
+    "four1_1m": "batched four1 f64 64 x 2^20 forward+inverse algorithmic HBM GB/s",
+    "fourn2d": "fourn f64 8192x8192 forward+inverse algorithmic HBM GB/s",
+    "convlv": "convlv_batch f64 n=2^22 m=4096 algorithmic HBM GB/s",
+    "correl": "correl_batch f64 n=2^22 algorithmic HBM GB/s",
+}
+SCALING = {"rlft3_512": "strong", "four1_batch": "weak", "four1_1m": "weak", "fourn2d": "weak", "convlv": "weak",
+           "correl": "weak"}
+
+
+def config_for(wl, gpus):
+    base = {
+        "rlft3_512": {"workload": "rlft3 3D real f64 512^3 (BASELINE configs[4]), step = forward + inverse",
+                      "dims": [512, 512, 512],
+                      "parallelism": "single GPU" if gpus == 1 else f"slab decomposition over {gpus} GPUs, one NCCL all-to-all per direction"},
+        "four1_batch": {"workload": "batched four1 f64 (BASELINE configs[1]): 4096 transforms of N=4096 per GPU, step = forward + inverse",
+                        "parallelism": "batch-sharded, no communication"},
+        "four1_1m": {"workload": "batched four1 f64: 64 transforms of N=2^20 per GPU (BASELINE configs[0] batched), step = forward + inverse",
+                     "parallelism": "batch-sharded, no communication"},
+        "fourn2d": {"workload": "fourn 2D complex f64 8192x8192 (BASELINE configs[2]), step = forward + inverse",
+                    "parallelism": "replicas only"},
+        "convlv": {"workload": "convlv_batch f64 (BASELINE configs[3]): 64 signals of n=2^22 per GPU, m=4096, isign=+1",
+                   "parallelism": "batch-sharded, no communication"},
+        "correl": {"workload": "correl_batch f64 (BASELINE configs[3]): 64 pairs of n=2^22 per GPU",
+                   "parallelism": "batch-sharded, no communication"},
+    }[wl]
+    base["l2"] = "inputs larger than L2; every timed step works on a buffer not touched since the warm-up"
+    return base
+
+
+# =============================================================================== our arm
+class Workload:
+    """Device-resident workload: a pool of independent input buffers, one step = one buffer."""
+
+    def __init__(self, lib, torch, name, pool):
+        self.lib, self.torch, self.name = lib, torch, name
+        import numrs_b200 as nb
+        t = torch
+        st = lambda: t.cuda.current_stream().cuda_stream  # noqa: E731
+        self.stream = st
+        f64 = dict(dtype=t.float64, device="cuda")
+        if name == "four1_batch":
+            nn, cnt = 4096, 4096
+            self.plan = lib.plan_create(nb.KIND_FOUR1, [nn], batch=cnt)
+            self.bufs = [t.empty(2 * nn * cnt, **f64) for _ in range(pool)]
+            self.bytes_step = 2 * 32.0 * nn * cnt
+            self.flops_step = 2 * 5.0 * nn * np.log2(nn) * cnt
+            self.seed, self.scale = 1002, float(nn)
+        elif name == "four1_1m":
+            nn, cnt = 1 << 20, 64
+            self.plan = lib.plan_create(nb.KIND_FOUR1, [nn], batch=cnt)
+            self.bufs = [t.empty(2 * nn * cnt, **f64) for _ in range(pool)]
+            self.bytes_step = 2 * 32.0 * nn * cnt
+            self.flops_step = 2 * 5.0 * nn * 20 * cnt
+            self.seed, self.scale = 1001, float(nn)
+        elif name == "fourn2d":
+            n = 8192
+            self.plan = lib.plan_create(nb.KIND_FOURN, [n, n], batch=1)
+            self.bufs = [t.empty(2 * n * n, **f64) for _ in range(pool)]
+            self.bytes_step = 2 * 32.0 * n * n
+            self.flops_step = 2 * 5.0 * n * n * 26
+            self.seed, self.scale = 1003, float(n * n)
+        elif name in ("convlv", "correl"):
+            n, m, cnt = 1 << 22, 4096, 64
+            self.n, self.cnt = n, cnt
+            pool = min(pool, 4)
+            self.bufs = [t.empty(n * cnt, **f64) for _ in range(pool)]
+            self.out = t.empty(n * cnt, **f64)
+            if name == "convlv":
+                self.plan = lib.plan_create(nb.KIND_CONVLV, [n, m], batch=cnt)
+                self.aux = t.empty(m, **f64)
+                lib.fill_uniform_device(self.aux.data_ptr(), 1005, 0, m, st())
+                self.aux /= 64.0
+                self.bytes_step = 16.0 * n * cnt + 8.0 * n
+                self.flops_step = cnt * (2 * 2.5 * n * 22 + 3.0 * n)
+            else:
+                self.plan = lib.plan_create(nb.KIND_CORREL, [n], batch=cnt)
+                self.aux = t.zeros(n * cnt, **f64)
+                tm = t.empty(m, **f64)
+                lib.fill_uniform_device(tm.data_ptr(), 1005, 0, m, st())
+                self.aux.view(cnt, n)[:, :m] = tm
+                self.bytes_step = 24.0 * n * cnt
+                self.flops_step = cnt * (3 * 2.5 * n * 22 + 3.0 * n)
+            self.seed, self.scale = 1004, None
+        else:
+            raise SystemExit(f"unknown workload {name}")
+        for i, b in enumerate(self.bufs):
+            lib.fill_uniform_device(b.data_ptr(), self.seed, 0, b.numel(), st())
+        t.cuda.synchronize()
+        self.launches_step = (self.plan.num_launches(1) + self.plan.num_launches(-1)) if self.scale else self.plan.num_launches(1)
+
+    def step(self, i):
+        b = self.bufs[i % len(self.bufs)]
+        if self.scale:
+            self.plan.exec(b.data_ptr(), isign=1, stream=self.stream())
+            self.plan.exec(b.data_ptr(), isign=-1, stream=self.stream())
+        else:
+            self.plan.exec(b.data_ptr(), self.aux.data_ptr(), self.out.data_ptr(), isign=1, stream=self.stream())
+
+    def profile(self, i):
+        b = self.bufs[i % len(self.bufs)]
+        if self.scale:
+            return (self.plan.profile(b.data_ptr(), isign=1, stream=self.stream()) +
+                    self.plan.profile(b.data_ptr(), isign=-1, stream=self.stream()))
+        return self.plan.profile(b.data_ptr(), self.aux.data_ptr(), self.out.data_ptr(), isign=1, stream=self.stream())
+
+
+def dominant_kernel(prof_runs):
+    """prof_runs: list of [(name, bytes, ms)] -> (name, avg bytes/launch, avg ms/launch, share of step)."""
+    agg = {}
+    total = 0.0
+    for run in prof_runs:
+        for name, b, ms in run:
+            a = agg.setdefault(name, [0.0, 0.0, 0])
+            a[0] += b
+            a[1] += ms
+            a[2] += 1
+            total += ms
+    name = max(agg, key=lambda k: agg[k][1])
+    b, ms, cnt = agg[name]
+    table = {k: {"launches_per_step": v[2] / len(prof_runs), "ms_per_step": v[1] / len(prof_runs),
+                 "algorithmic_GBps": (v[0] / v[1] / 1e6) if v[1] > 0 else None} for k, v in agg.items()}
+    return name, b / cnt, ms / cnt, ms / total, table
+
+
+def ncu_traffic(kernel_name):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return d.get(kernel_name, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import numrs_b200 as nb
+    lib = nb.lib()
+    if not torch.cuda.is_available() or lib.device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device; numrs_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    lib.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    K, W = args.steps, args.warmup
+    wl = args.workload
+    peak, peak_src = measured_peak()
+    st = lambda: torch.cuda.current_stream().cuda_stream  # noqa: E731
+    f64 = dict(dtype=torch.float64, device="cuda")
+
+    extra = {}
+    if wl == "rlft3_512":
+        n1 = n2 = n3 = 512
+        vol = n1 * n2 * n3
+        bytes_step = 2 * rlft3_bytes(n1, n2, n3)
+        flops_step = 2 * rlft3_flops(n1, n2, n3)
+        pool = max(2, min(K + W, 24))
+        if world == 1:
+            plan = lib.plan_create(nb.KIND_RLFT3, [n1, n2, n3])
+            bufs = [torch.empty(vol, **f64) for _ in range(pool)]
+            speqs = [torch.empty(2 * n1 * n2, **f64) for _ in range(pool)]
+            for b in bufs:
+                lib.fill_uniform_device(b.data_ptr(), 1006, 0, vol, st())
+            launches_step = plan.num_launches(1) + plan.num_launches(-1)
+
+            def step(i):
+                b, s = bufs[i % pool], speqs[i % pool]
+                plan.exec(b.data_ptr(), s.data_ptr(), isign=1, stream=st())
+                plan.exec(b.data_ptr(), s.data_ptr(), isign=-1, stream=st())
+
+            def profile(i):
+                b, s = bufs[i % pool], speqs[i % pool]
+                return (plan.profile(b.data_ptr(), s.data_ptr(), isign=1, stream=st()) +
+                        plan.profile(b.data_ptr(), s.data_ptr(), isign=-1, stream=st()))
+
+            def verify():
+                ref = torch.empty(vol, **f64)
+                lib.fill_uniform_device(ref.data_ptr(), 1006, 0, vol, st())
+                chk = torch.empty(vol, **f64)
+                chk.copy_(ref)
+                sp = torch.empty(2 * n1 * n2, **f64)
+                plan.exec(chk.data_ptr(), sp.data_ptr(), isign=1, stream=st())
+                plan.exec(chk.data_ptr(), sp.data_ptr(), isign=-1, stream=st())
+                chk.mul_(2.0 / vol)
+                return float(torch.linalg.norm(chk - ref) / torch.linalg.norm(ref))
+        else:
+            G = world
+            slab = lib.slab_create(n1, n2, n3, G, rank)
+            ld, sd, xd = slab.local_doubles(), slab.speq_doubles(), slab.xchg_doubles()
+            bufs = [torch.empty(ld, **f64) for _ in range(pool)]
+            speq = torch.empty(sd, **f64)
+            send = torch.empty(xd, **f64)
+            recv = torch.empty(xd, **f64)
+            for b in bufs:   # synthetic slab: rank r's share of the seed-1006 sequence
+                lib.fill_uniform_device(b.data_ptr(), 1006, rank * ld, ld, st())
+            launches_step = 0
+            extra["a2a_bytes_per_gpu_per_direction"] = 8.0 * xd * (G - 1) / G
+
+            def one_direction(b, isign):
+                slab.stage(0, isign, b.data_ptr(), speq.data_ptr(), send.data_ptr(), 0, st())
+                dist.all_to_all_single(recv, send)
+                slab.stage(1, isign, b.data_ptr(), speq.data_ptr(), 0, recv.data_ptr(), st())
+
+            def step(i):
+                b = bufs[i % pool]
+                one_direction(b, 1)
+                one_direction(b, -1)
+
+            profile = None
+
+            def verify():
+                ref = torch.empty(ld, **f64)
+                lib.fill_uniform_device(ref.data_ptr(), 1006, rank * ld, ld, st())
+                chk = ref.clone()
+                one_direction(chk, 1)
+                one_direction(chk, -1)
+                chk.mul_(2.0 / vol)
+                num = (chk - ref).pow(2).sum()
+                den = ref.pow(2).sum()
+                t = torch.stack([num, den])
+                dist.all_reduce(t)
+                return float(torch.sqrt(t[0] / t[1]))
+        shard = 1
+    else:
+        pool = max(2, min(K + W, 12))
+        w = Workload(lib, torch, wl, pool)
+        bytes_step, flops_step, launches_step = w.bytes_step, w.flops_step, w.launches_step
+        step, profile = w.step, w.profile
+        shard = world          # every rank runs its own shard: weak scaling
+
+        def verify():
+            if not w.scale:
+                return None
+            b = torch.empty_like(w.bufs[0])
+            lib.fill_uniform_device(b.data_ptr(), w.seed, 0, b.numel(), st())
+            ref = b.clone()
+            w.plan.exec(b.data_ptr(), isign=1, stream=st())
+            w.plan.exec(b.data_ptr(), isign=-1, stream=st())
+            b.mul_(1.0 / w.scale)
+            return float(torch.linalg.norm(b - ref) / torch.linalg.norm(ref))
+
+    torch.cuda.synchronize()
+    err = verify()
+
+    # ---- timed region: W warm-up steps, then exactly K steps between barriers
+    for i in range(W):
+        step(i)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        step(W + i)
+    e1.record()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist:
+        tms = torch.tensor([ms], device="cuda")
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms[0])
+    value = bytes_step * shard * K / (ms * 1e-3) / 1e9
+
+    # ---- per-kernel roofline (events around every launch, N = 1 plans)
+    roof = None
+    kern_table = None
+    if profile is not None:
+        runs = [profile(W + K + i) for i in range(min(K, 6))]
+        name, b_l, ms_l, share, kern_table = dominant_kernel(runs[1:] if len(runs) > 1 else runs)
+        ach = b_l / (ms_l * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": ncu_traffic(name), "peak_source": peak_src, "algorithmic_bytes_per_launch": b_l,
+                "ms_per_launch": ms_l, "share_of_step": share}
+    elif wl == "rlft3_512":
+        roof = {"bound": "hbm", "kernel": "slab pipeline (z+x pass | all-to-all | y pass)", "achieved": value / world,
+                "peak": peak, "unit": "GB/s", "frac": value / world / peak, "traffic": None, "peak_source": peak_src,
+                "note": "per-GPU algorithmic GB/s of the whole step; NVLink all-to-all included"}
+
+    # ---- end to end through the host-slice C ABI (pinned host buffers, copies inside the timed region)
+    e2e = None
+    if wl == "rlft3_512":
+        Ke = max(1, min(K, 8))
+        if world == 1:
+            h = lib.pinned_empty(vol)
+            hs = lib.pinned_empty(2 * n1 * n2)
+            hv = h.reshape(n1, n2, n3)
+            hsv = hs.reshape(n1, 2 * n2)
+            tmp = torch.empty(vol, **f64)
+            lib.fill_uniform_device(tmp.data_ptr(), 1006, 0, vol, st())
+            hv[...] = tmp.cpu().numpy().reshape(n1, n2, n3)
+            del tmp
+            nb.rlft3(hv, hsv, n1, n2, n3, 1)
+            nb.rlft3(hv, hsv, n1, n2, n3, -1)
+            hv *= 2.0 / vol
+            t0 = time.perf_counter()
+            for _ in range(Ke):
+                nb.rlft3(hv, hsv, n1, n2, n3, 1)
+                nb.rlft3(hv, hsv, n1, n2, n3, -1)
+                hv[0, 0, 0] *= 1.0   # result is in host memory here
+            dt = time.perf_counter() - t0
+            e2e = {"value": bytes_step * Ke / dt / 1e9, "unit": "GB/s", "steps": Ke,
+                   "h2d_bytes_per_step": 2 * 8 * vol + 16 * n1 * n2, "d2h_bytes_per_step": 2 * 8 * vol + 16 * n1 * n2,
+                   "ms_per_step": dt / Ke * 1e3, "api": "nrb_rlft3 (host slices, pinned), forward + inverse"}
+        else:
+            hb = torch.empty(ld, dtype=torch.float64).pin_memory()
+            hb.copy_(bufs[0].cpu())
+            dev = bufs[0]
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(Ke):
+                dev.copy_(hb, non_blocking=True)
+                one_direction(dev, 1)
+                one_direction(dev, -1)
+                hb.copy_(dev, non_blocking=True)
+                torch.cuda.synchronize()
+            dist.barrier()
+            dt = time.perf_counter() - t0
+            tdt = torch.tensor([dt], device="cuda")
+            dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+            dt = float(tdt[0])
+            e2e = {"value": bytes_step * Ke / dt / 1e9, "unit": "GB/s", "steps": Ke, "h2d_bytes_per_step": 8 * ld,
+                   "d2h_bytes_per_step": 8 * ld, "ms_per_step": dt / Ke * 1e3,
+                   "api": "per-rank pinned slab -> nrb_slab_stage x2 + NCCL all-to-all, forward + inverse -> pinned slab"}
+    else:
+        e2e = run_e2e_batch(lib, nb, wl, world)
+
+    # ---- CPU baseline (rank 0, N = 1): oracle port on a bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(wl)
+
+    if rank == 0:
+        line = {"metric": METRIC[wl], "value": value, "unit": "GB/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": SCALING[wl], "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config_for(wl, world),
+                "gflops": flops_step * shard * K / (ms * 1e-3) / 1e9,
+                "frac_of_hbm_peak": value / world / peak, "roundtrip_rel_l2": err,
+                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+                "gpu_launches": launches_step * K if launches_step else None, "kernels": kern_table}
+        if world > 1 and wl == "rlft3_512":
+            line["gpu_launches"] = K * 2 * 5
+            line.update(extra)
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+def run_e2e_batch(lib, nb, wl, world):
+    """End-to-end for the batch workloads: host-slice C ABI on a reduced batch (pinned)."""
+    import torch
+    if wl == "four1_batch":
+        nn, cnt = 4096, 4096
+        h = lib.pinned_empty(2 * nn * cnt)
+        tmp = torch.empty(h.size, dtype=torch.float64, device="cuda")
+        lib.fill_uniform_device(tmp.data_ptr(), 1002, 0, h.size, torch.cuda.current_stream().cuda_stream)
+        h[:] = tmp.cpu().numpy()
+        del tmp
+        arrs = [h[2 * nn * b:2 * nn * (b + 1)] for b in range(cnt)]
+        proc = nb.FFTProcessor()
+        proc.fft_batch(arrs, 1)
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            proc.fft_batch(arrs, 1)
+            proc.fft_batch(arrs, -1)
+        dt = time.perf_counter() - t0
+        return {"value": 2 * 32.0 * nn * cnt * reps / dt / 1e9, "unit": "GB/s", "steps": reps,
+                "h2d_bytes_per_step": 2 * 16 * nn * cnt, "d2h_bytes_per_step": 2 * 16 * nn * cnt,
+                "api": "nrb_four1_batch (host slices, pinned), forward + inverse"}
+    return None
+
+
+def cpu_baseline(wl):
+    import oracle as O
+    cores = O.num_threads()
+    if wl == "rlft3_512":
+        n = 256
+        x = O.fill_uniform(1006, 0, n ** 3).reshape(n, n, n)
+        s = np.zeros((n, 2 * n))
+        O.rlft3(x, s, 1, mt=True)
+        O.rlft3(x, s, -1, mt=True)
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < 10.0 and reps < 40:
+            O.rlft3(x, s, 1, mt=True)
+            O.rlft3(x, s, -1, mt=True)
+            reps += 1
+        dt = time.perf_counter() - t0
+        return {"value": 2 * rlft3_bytes(n, n, n) * reps / dt / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
+                "sample": f"{reps} x rlft3 {n}^3 forward+inverse (1/8 of the 512^3 volume), oracle port of the reference loop structure, {cores} OpenMP threads"}
+    if wl in ("four1_batch", "four1_1m"):
+        nn, cnt = (4096, 1024) if wl == "four1_batch" else (1 << 20, 4)
+        arrs = [O.fill_uniform(1002, b * 2 * nn, 2 * nn) for b in range(cnt)]
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < 8.0 and reps < 50:
+            O.fft_batch(arrs, 1, mt=True)
+            O.fft_batch(arrs, -1, mt=True)
+            reps += 1
+        dt = time.perf_counter() - t0
+        return {"value": 2 * 32.0 * nn * cnt * reps / dt / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
+                "sample": f"{reps} x fft_batch({cnt} x {nn}) forward+inverse, {cores} threads"}
+    if wl == "fourn2d":
+        n = 2048
+        x = O.fill_uniform(1003, 0, 2 * n * n)
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < 8.0 and reps < 50:
+            O.fourn(x, [n, n], 1, mt=True)
+            O.fourn(x, [n, n], -1, mt=True)
+            reps += 1
+        dt = time.perf_counter() - t0
+        return {"value": 2 * 32.0 * n * n * reps / dt / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
+                "sample": f"{reps} x fourn {n}x{n} forward+inverse, {cores} threads"}
+    n, m, cnt = 1 << 20, 4096, max(2, cores)
+    sigs = [O.fill_uniform(1004, b * n, n) for b in range(cnt)]
+    r = O.fill_uniform(1005, 0, m) / 64
+    t0 = time.perf_counter()
+    reps = 0
+    if wl == "convlv":
+        while time.perf_counter() - t0 < 8.0 and reps < 50:
+            O.convlv_batch(sigs, r, 1, mt=True)
+            reps += 1
+        b = 16.0 * n * cnt + 8.0 * n
+    else:
+        tm = [np.concatenate([O.fill_uniform(1005, 0, m), np.zeros(n - m)]) for _ in range(cnt)]
+        while time.perf_counter() - t0 < 8.0 and reps < 50:
+            O.correl_batch(sigs, tm, mt=True)
+            reps += 1
+        b = 24.0 * n * cnt
+    dt = time.perf_counter() - t0
+    return {"value": b * reps / dt / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
+            "sample": f"{reps} x {wl}_batch({cnt} x n=2^20, m=4096), {cores} threads"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="rlft3_512", choices=sorted(METRIC))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("bench.py: --gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -15,7 +15,8 @@ from ._lib import (NRB_PAD_LITERAL, NRB_PAD_NR, NrbError, KIND_FOUR1, KIND_FOURN
                    KIND_CONVLV, KIND_CORREL)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnumrs_b200.so")
+# NUMRS_B200_LIB may point at another build of the same CUDA library (tuning experiments)
+LIB_PATH = os.environ.get("NUMRS_B200_LIB") or os.path.join(_HERE, "libnumrs_b200.so")
 _LIB = None
 
 

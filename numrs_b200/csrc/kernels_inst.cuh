@@ -7,8 +7,13 @@
 #include "aux_kernels.cuh"
 #include "plan.h"
 
-#ifndef NRB_MIN_BLOCKS
-#define NRB_MIN_BLOCKS (NRB_RADIX16 ? 2 : 3)
+// resident CTAs per SM the register allocator targets for the 4096-point tiles
+// (3 -> 80 registers/thread, 2 -> 128).  ROW kernels carry per-thread twiddles and spill at 80.
+#ifndef NRB_MIN_BLOCKS_ROW
+#define NRB_MIN_BLOCKS_ROW 2
+#endif
+#ifndef NRB_MIN_BLOCKS_COL
+#define NRB_MIN_BLOCKS_COL (NRB_RADIX16 ? 2 : 3)
 #endif
 
 namespace nrb {
@@ -19,7 +24,7 @@ struct PassTable { PassLaunchFn fn[kMaxLog2N + 1][2][2][3]; };
 PassTable &pass_table();
 
 template <int LOG2N, int LAYOUT, int DIR, int VARIANT>
-__global__ void __launch_bounds__(cta_threads(LOG2N), (tile_log2(LOG2N) == 12 ? NRB_MIN_BLOCKS : 1))
+__global__ void __launch_bounds__(cta_threads(LOG2N), (tile_log2(LOG2N) == 12 ? (LAYOUT == LAYOUT_ROW ? NRB_MIN_BLOCKS_ROW : NRB_MIN_BLOCKS_COL) : 1))
 fft_pass_kernel(const __grid_constant__ PassParams P)
 {
     extern __shared__ double2 nrb_smem[];

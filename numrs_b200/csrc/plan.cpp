@@ -697,7 +697,7 @@ int build_slab_plan(SlabPlan &sp, size_t nn1, size_t nn2, size_t nn3, int nranks
     sp.nn1 = nn1; sp.nn2 = nn2; sp.nn3 = nn3; sp.nranks = nranks; sp.rank = rank;
     const u64 G = (u64)nranks, X = nn1 / G, Y = nn2 / G, N3 = nn3 / 2;
     const int p1 = ilog2(nn1), p2 = ilog2(nn2), p3 = ilog2((size_t)N3);
-    if (p1 > tunables().col_max_log2 || p2 > tunables().col_max_log2 || p3 > tunables().row_max_log2 || p3 < 1) {
+    if (p1 > tunables().col_max_log2 || p2 > tunables().col_max_log2 || p3 > tunables().row_max_log2) {
         set_error("slab: axis too long for a single pass");
         return NRB_ERR_UNSUPPORTED;
     }

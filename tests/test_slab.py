@@ -1,0 +1,124 @@
+"""CPU tier: slab-decomposed rlft3 (multi-GPU path).  The per-rank stages run under the
+TEST-ONLY kernel emulation; the exchange is (a) simulated in one process for G = 2, 4, 8 and
+(b) a real torch.distributed all_to_all_single over gloo with world_size 2."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import cases
+import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def slab_of(x, r, G):
+    Y = x.shape[1] // G
+    return np.ascontiguousarray(x[:, r * Y:(r + 1) * Y, :])
+
+
+def run_simulated(L, x, G, isign, speq_in=None):
+    """All G ranks in one process; returns per-rank (slab, speq) after one direction."""
+    nn1, nn2, nn3 = x.shape
+    X, Y = nn1 // G, nn2 // G
+    plans = [L.slab_create(nn1, nn2, nn3, G, r) for r in range(G)]
+    xd = plans[0].xchg_doubles()
+    blk = xd // G
+    if isign == 1:
+        slabs = [slab_of(x, r, G).ravel().copy() for r in range(G)]
+        speqs = [np.zeros(plans[r].speq_doubles()) for r in range(G)]
+    else:
+        slabs = [np.ascontiguousarray(x[r * X:(r + 1) * X]).ravel().copy() for r in range(G)]
+        speqs = [np.ascontiguousarray(speq_in[r * X:(r + 1) * X]).ravel().copy() for r in range(G)]
+    sends = [np.zeros(xd) for _ in range(G)]
+    recvs = [np.zeros(xd) for _ in range(G)]
+    for r in range(G):
+        plans[r].stage(0, isign, slabs[r].ctypes.data, speqs[r].ctypes.data, sends[r].ctypes.data, 0)
+    for r in range(G):          # all-to-all: block p of rank r's send -> block r of rank p's recv
+        for p in range(G):
+            recvs[p][r * blk:(r + 1) * blk] = sends[r][p * blk:(p + 1) * blk]
+    for r in range(G):
+        plans[r].stage(1, isign, slabs[r].ctypes.data, speqs[r].ctypes.data, 0, recvs[r].ctypes.data)
+    for p in plans:
+        p.destroy()
+    return slabs, speqs
+
+
+@pytest.mark.parametrize("shape,G", [((8, 8, 8), 2), ((16, 16, 8), 4), ((8, 16, 32), 8), ((32, 8, 4), 8), ((4, 4, 2), 4),
+                                     ((16, 16, 16), 1)])
+def test_slab_simulated_ranks(emu, shape, G):
+    nn1, nn2, nn3 = shape
+    X, Y = nn1 // G, nn2 // G
+    x = O.fill_uniform(1006, 0, nn1 * nn2 * nn3).reshape(shape)
+    rd, rs = O.rlft3(x.copy(), np.zeros((nn1, 2 * nn2)), 1)
+    slabs, speqs = run_simulated(emu, x, G, 1)
+    for r in range(G):      # forward output: nn1-slabs = contiguous row ranges of the reference layout
+        assert cases.rel(slabs[r], rd[r * X:(r + 1) * X]) <= cases.tol(x.size), (r, "data")
+        assert cases.rel(speqs[r], rs[r * X:(r + 1) * X]) <= cases.tol(x.size), (r, "speq")
+    # inverse from the spectrum: output nn2-slabs, round trip = N/2 * x
+    back, _ = run_simulated(emu, rd, G, -1, rs)
+    for r in range(G):
+        assert cases.rel(back[r] * (2.0 / x.size), slab_of(x, r, G)) <= cases.tol(x.size), (r, "round trip")
+
+
+def test_slab_rejects_bad_rank_counts(emu):
+    import numrs_b200 as nb
+    for args in ((8, 8, 8, 3, 0), (8, 8, 8, 16, 0), (8, 8, 8, 2, 2), (8, 6, 8, 2, 0)):
+        with pytest.raises(nb.NrbError):
+            emu.slab_create(*args)
+
+
+def _gloo_worker(rank, world, port, shape, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    from numrs_b200 import _lib
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    L = _lib.Library(os.path.join(ROOT, "tests", "emu", "libnrb_emu.so"))
+    nn1, nn2, nn3 = shape
+    x = O.fill_uniform(1006, 0, nn1 * nn2 * nn3).reshape(shape)
+    plan = L.slab_create(nn1, nn2, nn3, world, rank)
+    slab = torch.from_numpy(slab_of(x, rank, world).ravel().copy())
+    speq = torch.zeros(plan.speq_doubles(), dtype=torch.float64)
+    send = torch.zeros(plan.xchg_doubles(), dtype=torch.float64)
+    recv = torch.zeros(plan.xchg_doubles(), dtype=torch.float64)
+    for isign in (1, -1):
+        plan.stage(0, isign, slab.data_ptr(), speq.data_ptr(), send.data_ptr(), 0)
+        dist.all_to_all_single(recv, send)
+        plan.stage(1, isign, slab.data_ptr(), speq.data_ptr(), 0, recv.data_ptr())
+        if isign == 1:
+            fwd, fsp = slab.numpy().copy(), speq.numpy().copy()
+    q.put((rank, fwd, fsp, slab.numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_slab_gloo_world_size_2(emu):
+    import torch.multiprocessing as mp
+    shape, world = (8, 16, 16), 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, shape, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(world):
+        rank, fwd, fsp, back = q.get(timeout=120)
+        res[rank] = (fwd, fsp, back)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    nn1, nn2, nn3 = shape
+    x = O.fill_uniform(1006, 0, nn1 * nn2 * nn3).reshape(shape)
+    rd, rs = O.rlft3(x.copy(), np.zeros((nn1, 2 * nn2)), 1)
+    X = nn1 // world
+    for r in range(world):
+        fwd, fsp, back = res[r]
+        assert cases.rel(fwd, rd[r * X:(r + 1) * X]) <= cases.tol(x.size)
+        assert cases.rel(fsp, rs[r * X:(r + 1) * X]) <= cases.tol(x.size)
+        assert cases.rel(back * (2.0 / x.size), slab_of(x, r, world)) <= cases.tol(x.size)
