@@ -18,7 +18,7 @@ for g in 8 16 64; do
   NRB_L2_GROUP_MB=$g timeout 200 python tools/kernel_table.py rlft3_512 > gpurun_out/ktable_l2g$g.log 2>&1
 done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_rlft3.csv python tools/profile_rlft3.py 512 > gpurun_out/ncu_launch.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:fft_pass_kernel -s 70 -c 12 -o gpurun_out/prof_rlft3 -f python tools/profile_rlft3.py 512 > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:fft_pass_kernel -s 62 -c 10 -o gpurun_out/prof_rlft3 -f python tools/profile_rlft3.py 512 > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out
 tail -3 gpurun_out/smoke.log gpurun_out/pytest_gpu.log gpurun_out/bench.err
 cat gpurun_out/bench.json | head -c 3000
