@@ -1,0 +1,240 @@
+// num_rs.hpp -- C++ host-side mirror of the reference's public interface for the FFT hot path.
+//
+// The reference is a Rust crate (num_rs); its toolchain is not available in this image, so the
+// host side above the C ABI is provided in C++ (the Rust shim a maintainer would add is in
+// rust/ and INTEGRATION.md).  Names, argument meaning and error behaviour follow
+// /root/reference/src/{FFT_1,Fourn,Real_FT,Real_FT3,Convolve,Correlation}.rs:
+//   * functions returning () in Rust and panicking on misuse (four1, realft, rlft3) throw
+//     num_rs::Panic here;
+//   * functions returning Result<_, ConvlvError | CorrelError | io::Error> throw the matching
+//     exception type carrying the same variant.
+// Header-only; link with -lnumrs_b200.
+#pragma once
+#include <cstddef>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/numrs_b200.h"
+
+namespace num_rs {
+
+struct Panic : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+inline void panic_on(int rc)
+{
+    if (rc != NRB_OK) throw Panic(std::string("numrs_b200: ") + nrb_last_error());
+}
+
+// ------------------------------------------------------------------ FFT_1.rs
+namespace FFT_1 {
+
+// FFT_1.rs:5
+inline void four1(double *data, std::size_t data_len, std::size_t nn, int isign)
+{
+    if (data_len < 2 * nn) throw Panic("index out of bounds: data.len() < 2*nn");
+    panic_on(nrb_four1(data, nn, isign));
+}
+inline void four1(std::vector<double> &data, std::size_t nn, int isign) { four1(data.data(), data.size(), nn, isign); }
+// FFT_1.rs:110
+inline void four1_optimized(std::vector<double> &data, std::size_t nn, int isign) { four1(data, nn, isign); }
+
+// FFT_1.rs:143-190
+class FFTProcessor {
+  public:
+    FFTProcessor() : max_threads_(1), use_optimized_(true) {}
+    FFTProcessor &with_threads(std::size_t t) { max_threads_ = t; return *this; }
+    FFTProcessor &with_optimized(bool b) { use_optimized_ = b; return *this; }
+    void fft(std::vector<double> &data, int isign) const { four1(data, data.size() / 2, isign); }
+    // batches: mutable slices (pointer, length in doubles)
+    void fft_batch(const std::vector<std::pair<double *, std::size_t>> &batches, int isign) const
+    {
+        std::vector<double *> ptrs;
+        std::vector<std::size_t> nn;
+        for (const auto &b : batches) { ptrs.push_back(b.first); nn.push_back(b.second / 2); }
+        panic_on(nrb_four1_batch(ptrs.data(), nn.data(), ptrs.size(), isign));
+    }
+
+  private:
+    std::size_t max_threads_;
+    bool use_optimized_;
+};
+
+// FFT_1.rs:193-228 (host-side helpers)
+inline std::vector<double> real_to_complex(const std::vector<double> &re)
+{
+    std::vector<double> c(2 * re.size(), 0.0);
+    for (std::size_t i = 0; i < re.size(); ++i) c[2 * i] = re[i];
+    return c;
+}
+inline std::vector<double> complex_to_real(const std::vector<double> &c)
+{
+    std::vector<double> r((c.size() + 1) / 2);
+    for (std::size_t i = 0; i < r.size(); ++i) r[i] = c[2 * i];
+    return r;
+}
+inline std::vector<double> power_spectrum(const std::vector<double> &c)
+{
+    std::vector<double> p((c.size() + 1) / 2, 0.0);
+    for (std::size_t i = 0; 2 * i + 1 < c.size(); ++i) p[i] = c[2 * i] * c[2 * i] + c[2 * i + 1] * c[2 * i + 1];
+    return p;
+}
+
+} // namespace FFT_1
+
+// ------------------------------------------------------------------ Fourn.rs / Real_FT3.rs:35
+namespace Fourn {
+
+struct InvalidInput : std::invalid_argument {   // io::ErrorKind::InvalidInput, Fourn.rs:367-378
+    using std::invalid_argument::invalid_argument;
+};
+
+// the in-memory call shape of Real_FT3.rs:35: Fourn(&mut flat, &nn, ndim, isign)
+inline void fourn(std::vector<double> &data, const std::vector<std::size_t> &nn, std::size_t ndim, int isign)
+{
+    if (ndim == 0 || ndim > nn.size()) throw InvalidInput("Invalid dimensions");
+    std::size_t total = 1;
+    for (std::size_t d = 0; d < ndim; ++d) total *= nn[d];
+    const int rc = nrb_fourn(data.data(), nn.data(), ndim, isign);
+    if (rc == NRB_ERR_INVALID_DIMS || rc == NRB_ERR_INVALID_ISIGN) throw InvalidInput(nrb_last_error());
+    if (rc == NRB_OK && data.size() < 2 * total) throw Panic("data.len() < 2*prod(nn)");
+    panic_on(rc);
+}
+
+} // namespace Fourn
+
+// ------------------------------------------------------------------ Real_FT.rs
+namespace Real_FT {
+
+// Real_FT.rs:4 (asserts :5-6)
+inline void realft(std::vector<double> &data, std::size_t n, int isign)
+{
+    if (n % 2 != 0) throw Panic("n must be even");
+    if (data.size() < n) throw Panic("data length must be at least n");
+    panic_on(nrb_realft(data.data(), n, isign));
+}
+inline void realft_optimized(std::vector<double> &data, std::size_t n, int isign) { realft(data, n, isign); }
+
+} // namespace Real_FT
+
+// ------------------------------------------------------------------ Real_FT3.rs
+namespace Real_FT3 {
+
+// Real_FT3.rs:8; data is [nn1][nn2][nn3] row-major, speq is [nn1][2*nn2] (asserts :17-19)
+inline void rlft3(std::vector<double> &data, std::vector<double> &speq, std::size_t nn1, std::size_t nn2,
+                  std::size_t nn3, int isign)
+{
+    if (isign != 1 && isign != -1) throw Panic("isign must be 1 or -1");
+    if (data.size() != nn1 * nn2 * nn3) throw Panic("data dimensions mismatch");
+    if (speq.size() != nn1 * 2 * nn2) throw Panic("speq dimensions mismatch");
+    panic_on(nrb_rlft3(data.data(), speq.data(), nn1, nn2, nn3, isign));
+}
+
+} // namespace Real_FT3
+
+// ------------------------------------------------------------------ Convolve.rs
+namespace Convolve {
+
+struct ConvlvError : std::runtime_error {   // Convolve.rs:226-238
+    enum Kind { EmptyInput, ResponseTooLong, InvalidIsign, DivisionByZero, FftError } kind;
+    ConvlvError(Kind k, const std::string &m) : std::runtime_error(m), kind(k) {}
+};
+
+inline void raise(int rc)
+{
+    switch (rc) {
+    case NRB_OK: return;
+    case NRB_ERR_EMPTY_INPUT: throw ConvlvError(ConvlvError::EmptyInput, "Input arrays cannot be empty");
+    case NRB_ERR_RESPONSE_TOO_LONG: throw ConvlvError(ConvlvError::ResponseTooLong, "Response function longer than data");
+    case NRB_ERR_INVALID_ISIGN: throw ConvlvError(ConvlvError::InvalidIsign, "isign must be 1 (convolution) or -1 (deconvolution)");
+    default: throw ConvlvError(ConvlvError::FftError, std::string("FFT computation error: ") + nrb_last_error());
+    }
+}
+
+// Convolve.rs:8
+inline std::vector<double> convlv(const std::vector<double> &data, const std::vector<double> &respns, int isign,
+                                  int pad_mode = NRB_PAD_LITERAL)
+{
+    std::vector<double> ans(data.size());
+    raise(nrb_convlv(data.data(), data.size(), respns.data(), respns.size(), isign, pad_mode, ans.data()));
+    return ans;
+}
+
+// Convolve.rs:241
+inline std::vector<std::vector<double>> convlv_batch(const std::vector<std::vector<double>> &batch,
+                                                     const std::vector<double> &respns, int isign)
+{
+    std::vector<std::vector<double>> out;
+    if (batch.empty()) return out;
+    const std::size_t n = batch[0].size();
+    bool uniform = true;
+    for (const auto &b : batch) uniform = uniform && b.size() == n;
+    if (!uniform) {
+        for (const auto &b : batch) out.push_back(convlv(b, respns, isign));
+        return out;
+    }
+    std::vector<const double *> in;
+    std::vector<double *> o;
+    out.assign(batch.size(), std::vector<double>(n));
+    for (std::size_t i = 0; i < batch.size(); ++i) { in.push_back(batch[i].data()); o.push_back(out[i].data()); }
+    raise(nrb_convlv_batch(in.data(), in.size(), n, respns.data(), respns.size(), isign, NRB_PAD_LITERAL, o.data()));
+    return out;
+}
+
+// Convolve.rs:253-339
+class ConvlvProcessor {
+  public:
+    ConvlvProcessor() : use_optimized_(true), threshold_(1024) {}
+    ConvlvProcessor &with_optimized(bool b) { use_optimized_ = b; return *this; }
+    ConvlvProcessor &with_threshold(std::size_t t) { threshold_ = t; return *this; }
+    std::vector<double> process(const std::vector<double> &d, const std::vector<double> &r, int isign) const { return convlv(d, r, isign); }
+
+  private:
+    bool use_optimized_;
+    std::size_t threshold_;
+};
+
+} // namespace Convolve
+
+// ------------------------------------------------------------------ Correlation.rs
+namespace Correlation {
+
+struct CorrelError : std::runtime_error {   // Correlation.rs:389-399
+    enum Kind { EmptyInput, LengthMismatch, FftError, ZeroStdDev } kind;
+    CorrelError(Kind k, const std::string &m) : std::runtime_error(m), kind(k) {}
+};
+
+inline void raise(int rc)
+{
+    switch (rc) {
+    case NRB_OK: return;
+    case NRB_ERR_EMPTY_INPUT: throw CorrelError(CorrelError::EmptyInput, "Input arrays cannot be empty");
+    case NRB_ERR_LENGTH_MISMATCH: throw CorrelError(CorrelError::LengthMismatch, "Input arrays must have the same length");
+    default: throw CorrelError(CorrelError::FftError, std::string("FFT computation error: ") + nrb_last_error());
+    }
+}
+
+// Correlation.rs:8
+inline std::vector<double> correl(const std::vector<double> &a, const std::vector<double> &b)
+{
+    std::vector<double> ans(a.size());
+    raise(nrb_correl(a.data(), a.size(), b.data(), b.size(), ans.data()));
+    return ans;
+}
+// Correlation.rs:281
+inline std::vector<double> autocorrel(const std::vector<double> &a) { return correl(a, a); }
+
+// Correlation.rs:273
+inline std::vector<std::vector<double>> correl_batch(const std::vector<std::pair<std::vector<double>, std::vector<double>>> &pairs)
+{
+    std::vector<std::vector<double>> out;
+    for (const auto &p : pairs) out.push_back(correl(p.first, p.second));
+    return out;
+}
+
+} // namespace Correlation
+
+} // namespace num_rs

@@ -1,0 +1,39 @@
+//! 1:1 declaration of include/numrs_b200.h (host-slice entry points only).
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_double, c_int};
+
+pub const NRB_OK: c_int = 0;
+pub const NRB_ERR_EMPTY_INPUT: c_int = -1;
+pub const NRB_ERR_RESPONSE_TOO_LONG: c_int = -2;
+pub const NRB_ERR_INVALID_ISIGN: c_int = -3;
+pub const NRB_ERR_LENGTH_MISMATCH: c_int = -4;
+pub const NRB_ERR_INVALID_DIMS: c_int = -5;
+pub const NRB_PAD_LITERAL: c_int = 0;
+
+extern "C" {
+    pub fn nrb_last_error() -> *const c_char;
+    pub fn nrb_four1(data: *mut c_double, nn: usize, isign: c_int) -> c_int;
+    pub fn nrb_four1_batch(ptrs: *const *mut c_double, nn: *const usize, count: usize, isign: c_int) -> c_int;
+    pub fn nrb_fourn(data: *mut c_double, nn: *const usize, ndim: usize, isign: c_int) -> c_int;
+    pub fn nrb_realft(data: *mut c_double, n: usize, isign: c_int) -> c_int;
+    pub fn nrb_realft_batch(ptrs: *const *mut c_double, n: usize, count: usize, isign: c_int) -> c_int;
+    pub fn nrb_rlft3(data: *mut c_double, speq: *mut c_double, nn1: usize, nn2: usize, nn3: usize, isign: c_int) -> c_int;
+    pub fn nrb_convlv(data: *const c_double, n: usize, respns: *const c_double, m: usize, isign: c_int,
+                      pad_mode: c_int, ans: *mut c_double) -> c_int;
+    pub fn nrb_convlv_batch(data: *const *const c_double, count: usize, n: usize, respns: *const c_double, m: usize,
+                            isign: c_int, pad_mode: c_int, ans: *const *mut c_double) -> c_int;
+    pub fn nrb_correl(d1: *const c_double, n1: usize, d2: *const c_double, n2: usize, ans: *mut c_double) -> c_int;
+    pub fn nrb_correl_batch(d1: *const *const c_double, d2: *const *const c_double, count: usize, n: usize,
+                            ans: *const *mut c_double) -> c_int;
+}
+
+pub fn last_error() -> String {
+    unsafe { std::ffi::CStr::from_ptr(nrb_last_error()).to_string_lossy().into_owned() }
+}
+
+/// four1 / realft / rlft3 return `()` in the reference and signal misuse by panicking.
+pub fn panic_on(rc: c_int) {
+    if rc != NRB_OK {
+        panic!("numrs_b200: {}", last_error());
+    }
+}

@@ -1,0 +1,79 @@
+// test_host.cpp -- exercises the C++ host mirror (numrs_b200/host/num_rs.hpp) the way the
+// reference's own unit tests exercise the Rust API.  argv[1] == "gpu": run the numeric tests
+// (needs a device); otherwise only the argument-validation paths, which must behave like the
+// reference before any device is touched.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "../../numrs_b200/host/num_rs.hpp"
+
+using namespace num_rs;
+
+static int failures = 0;
+#define CHECK(c) do { if (!(c)) { std::printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #c); ++failures; } } while (0)
+
+template <class E, class F> static bool throws(F f)
+{
+    try { f(); } catch (const E &) { return true; } catch (...) { return false; }
+    return false;
+}
+
+int main(int argc, char **argv)
+{
+    const bool gpu = argc > 1 && !std::strcmp(argv[1], "gpu");
+    // Convolve.rs:406-424
+    try { Convolve::convlv({}, {1.0}, 1); CHECK(false); } catch (const Convolve::ConvlvError &e) { CHECK(e.kind == Convolve::ConvlvError::EmptyInput); }
+    try { Convolve::convlv({1.0, 2.0}, {1.0, 2.0, 3.0}, 1); CHECK(false); } catch (const Convolve::ConvlvError &e) { CHECK(e.kind == Convolve::ConvlvError::ResponseTooLong); }
+    try { Convolve::convlv({1.0, 2.0}, {1.0}, 0); CHECK(false); } catch (const Convolve::ConvlvError &e) { CHECK(e.kind == Convolve::ConvlvError::InvalidIsign); }
+    // Correlation.rs:453-462
+    try { Correlation::correl({}, {1.0}); CHECK(false); } catch (const Correlation::CorrelError &e) { CHECK(e.kind == Correlation::CorrelError::EmptyInput); }
+    try { Correlation::correl({1.0, 2.0}, {1.0}); CHECK(false); } catch (const Correlation::CorrelError &e) { CHECK(e.kind == Correlation::CorrelError::LengthMismatch); }
+    // Fourn.rs:467-476
+    { std::vector<double> d(2); CHECK(throws<Fourn::InvalidInput>([&] { Fourn::fourn(d, {1}, 1, 1); })); }
+    { std::vector<double> d(16); CHECK(throws<Fourn::InvalidInput>([&] { Fourn::fourn(d, {8}, 1, 0); })); }
+    // Real_FT.rs:5-6, Real_FT3.rs:17-19
+    { std::vector<double> d(6); CHECK(throws<Panic>([&] { Real_FT::realft(d, 5, 1); })); }
+    { std::vector<double> d(64), s(32); CHECK(throws<Panic>([&] { Real_FT3::rlft3(d, s, 4, 4, 4, 0); })); }
+    { std::vector<double> d(64), s(16); CHECK(throws<Panic>([&] { Real_FT3::rlft3(d, s, 4, 4, 4, 1); })); }
+    if (gpu) {
+        // FFT_1.rs:246-267
+        const std::size_t n = 1024;
+        std::vector<double> sig(n);
+        for (std::size_t i = 0; i < n; ++i) { double t = (double)i / n; sig[i] = std::sin(2 * M_PI * 5 * t) + 0.5 * std::cos(2 * M_PI * 20 * t); }
+        auto c = FFT_1::real_to_complex(sig);
+        FFT_1::four1(c, n, 1);
+        FFT_1::four1(c, n, -1);
+        for (std::size_t i = 0; i < n; ++i) CHECK(std::fabs(c[2 * i] / n - sig[i]) < 1e-10);
+        // Convolve.rs:347-360 (indices 1..3), :445-454
+        auto y = Convolve::convlv({1, 2, 3, 4}, {1, 1}, 1);
+        CHECK(std::fabs(y[1] - 3) < 1e-10 && std::fabs(y[2] - 5) < 1e-10 && std::fabs(y[3] - 7) < 1e-10);
+        CHECK(std::fabs(Convolve::ConvlvProcessor().process({1, 2, 3, 4}, {1, 1}, 1)[1] - 3.0) < 1e-10);
+        // Correlation.rs:407-418, :494-502
+        auto r = Correlation::correl({1, 2, 3, 4}, {1, 2, 3, 4});
+        CHECK(r[0] == 30.0 && r[0] > r[1]);
+        auto r2 = Correlation::correl({1, 2}, {1, 2});
+        CHECK(r2[0] == 5.0 && r2[1] == 2.0);
+        // Real_FT3.rs:268-311 with the true factor N/2
+        std::vector<double> d(512), s(128, 0.0), o(512);
+        for (int i = 0; i < 8; ++i) for (int j = 0; j < 8; ++j) for (int k = 0; k < 8; ++k) o[(i * 8 + j) * 8 + k] = d[(i * 8 + j) * 8 + k] = i + j + k;
+        Real_FT3::rlft3(d, s, 8, 8, 8, 1);
+        Real_FT3::rlft3(d, s, 8, 8, 8, -1);
+        for (int i = 0; i < 512; ++i) CHECK(std::fabs(d[i] / 256.0 - o[i]) < 1e-10);
+        // realft round trip = (n/2) x
+        std::vector<double> x(256), x0;
+        for (int i = 0; i < 256; ++i) x[i] = std::sin(0.1 * i);
+        x0 = x;
+        Real_FT::realft(x, 256, 1);
+        Real_FT::realft(x, 256, -1);
+        for (int i = 0; i < 256; ++i) CHECK(std::fabs(x[i] / 128.0 - x0[i]) < 1e-10);
+    } else {
+        // no device: compute calls must fail loudly, never fall back
+        if (nrb_device_count() == 0) {
+            std::vector<double> c(16, 1.0);
+            CHECK(throws<Panic>([&] { FFT_1::four1(c, 8, 1); }));
+        }
+    }
+    std::printf(failures ? "host mirror: %d failures\n" : "host mirror: ok\n", failures);
+    return failures ? 1 : 0;
+}
