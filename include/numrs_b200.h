@@ -58,8 +58,10 @@ int  nrb_shutdown(void);               /* frees cached plans / scratch of all th
 /* Planner tunables (affect plans created afterwards; cached host-call plans are dropped):
  *   "col_max_log2"   longest strided-axis FFT done in one pass          (default 10)
  *   "row_max_log2"   longest contiguous FFT done in one pass            (default 13)
- *   "l2_group_bytes" working-set target of L2-resident pass groups      (default 32 MiB)
- * Environment overrides at load time: NRB_COL_MAX_LOG2, NRB_ROW_MAX_LOG2, NRB_L2_GROUP_MB. */
+ *   "l2_group_bytes"    rlft3: bytes of x-planes per z/y launch pair    (default: whole volume)
+ *   "batch_group_bytes" convlv/correl: bytes of signals per launch group (default 512 MiB)
+ * Environment overrides at load time: NRB_COL_MAX_LOG2, NRB_ROW_MAX_LOG2, NRB_L2_GROUP_MB,
+ * NRB_BATCH_GROUP_MB. */
 int  nrb_set_option(const char *name, long value);
 /* pinned host memory, so host-slice calls copy at full PCIe rate (optional) */
 void *nrb_host_alloc(size_t bytes);

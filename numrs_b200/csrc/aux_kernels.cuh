@@ -40,7 +40,7 @@ NRB_DEV void aux_untangle(const AuxParams &A, u64 gtid, u64 gthreads)
             }
             if (N >= 2) dst[N / 2] = mid;
         } else {
-            const double2 a = src[k], b = src[N - k];
+            const double2 a = NRB_LDS(src + k), b = NRB_LDS(src + (N - k));
             const double2 t = two_level_tw(A.rtw_lo, A.rtw_hi, A.rtw_h, k);
             double2 oa, ob;
             if (A.dir > 0) untangle_pair<1>(a, b, t, oa, ob);
@@ -60,8 +60,8 @@ NRB_DEV void aux_spectral(const AuxParams &A, u64 gtid, u64 gthreads)
     const double inv = 1.0 / (double)half;      // 1/no2; n is a power of two -> exact
     for (u64 it = gtid; it < items; it += gthreads) {
         const u64 k = it % half, sig = it / half;
-        const double2 d = A.a[(i64)sig * A.a_stride + (i64)k];
-        const double2 r = A.b[(i64)sig * A.b_stride + (i64)k];
+        const double2 d = NRB_LDS(A.a + (i64)sig * A.a_stride + (i64)k);
+        const double2 r = A.b_stride ? NRB_LDS(A.b + (i64)sig * A.b_stride + (i64)k) : NRB_LDG(A.b + (i64)k);
         double2 o;
         if (A.op == SPEC_CONV_MUL) {
             if (k == 0) o = make_double2(d.x * r.x * inv, d.y * r.y * inv);

@@ -127,8 +127,8 @@ template <int LOG2N, int LAYOUT, int VARIANT> struct Geo {
     static constexpr int TL = tile_log2(LOG2N);
     static constexpr int TILE = 1 << TL;
     static constexpr int L = TILE / N;                 // lines per tile
-    static constexpr int NT = cta_threads(LOG2N);      // threads per CTA
-    static constexpr int PPT = kPointsPerThread;
+    static constexpr int NT = cta_threads(LOG2N, LAYOUT);      // threads per CTA
+    static constexpr int PPT = points_per_thread(LAYOUT, LOG2N);
     static constexpr int NST = radix_plan(LOG2N).nst;
     static constexpr int LP = row_line_pitch(LOG2N);   // ROW: line pitch
     static constexpr int CP = col_pitch(LOG2N, VARIANT); // COL: pitch of one n
@@ -193,7 +193,7 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 double2 x = make_double2(0.0, 0.0);
-                if (ok) x = src[elem_off(jj[i] + r * NB, P.in_es, P.in_eshift, P.in_es_hi)];
+                if (ok) x = NRB_LDS(src + elem_off(jj[i] + r * NB, P.in_es, P.in_eshift, P.in_es_hi));
                 v[i][r] = io_swap<DIR>(x);
             }
         } else {
@@ -203,6 +203,7 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
     }
 
     // ---- twiddle + butterfly
+#ifndef NRB_SKIP_MATH   /* timing experiments only: memory skeleton of the pass */
 #pragma unroll
     for (int i = 0; i < BPT; ++i) {
         if (NS > 1) {
@@ -213,6 +214,7 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
         }
         Bfly<R>::run(v[i]);
     }
+#endif
 
     if (!SRC_G && !DST_G) NRB_SYNC();   // everyone has read before anyone overwrites
 
@@ -230,7 +232,7 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
                     const int k = kb + r * NS;
                     double2 y = v[i][r];
                     if (P.tw_on) y = cmul(y, fourstep_tw(P, q, (unsigned)k));
-                    dst[elem_off(k, P.out_es, P.out_eshift, P.out_es_hi)] = io_swap<DIR>(y);
+                    NRB_STS(dst + elem_off(k, P.out_es, P.out_eshift, P.out_es_hi), io_swap<DIR>(y));
                 }
             }
         } else {
@@ -309,7 +311,7 @@ NRB_DEV void fft_pass_body(const PassParams &P, double2 *sm, unsigned tile, int 
                 double2 y = sm[G::phys(l, k)];
                 if (P.tw_on) y = cmul(y, fourstep_tw(P, q, (unsigned)k));
                 double2 *dst = P.out + line_base(q, P.out_s0, P.out_s1, P.out_s2, P.logA, P.logB);
-                dst[(i64)k * P.out_es] = io_swap<DIR>(y);
+                NRB_STS(dst + (i64)k * P.out_es, io_swap<DIR>(y));
             }
         }
         return;
@@ -343,37 +345,43 @@ NRB_DEV void fft_pass_body(const PassParams &P, double2 *sm, unsigned tile, int 
                     const double2 a = cswap(sm[G::phys(l, k)]), b = cswap(sm[G::phys(l, G::N - k)]);
                     double2 oa, ob;
                     untangle_pair<DIR>(a, b, NRB_LDG(P.rtw + k), oa, ob);
-                    dst[(i64)k * P.out_es] = oa;
-                    dst[(i64)(G::N - k) * P.out_es] = ob;
+                    NRB_STS(dst + (i64)k * P.out_es, oa);
+                    NRB_STS(dst + (i64)(G::N - k) * P.out_es, ob);
                 }
             }
         } else {
-            // global -> untangle -> shared memory -> c2c -> global
-#pragma unroll 4
+            // global -> untangle -> shared memory -> c2c -> global.  All pair loads are issued
+            // before any is used (k = 0 pairs element 0 with the untouched middle element N/2).
+            double2 a[ITEMS], b[ITEMS];
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                const int idx = tid + i * G::NT;
+                const int k = idx & (HALF - 1), l = idx / HALF;
+                const u64 q = P.q_begin + (u64)tile * G::L + (u64)l;
+                const bool ok = (idx < G::L * HALF) && (q < P.q_end);
+                const double2 *src = P.in + line_base(q, P.in_s0, P.in_s1, P.in_s2, P.logA, P.logB);
+                a[i] = make_double2(0.0, 0.0);
+                b[i] = make_double2(0.0, 0.0);
+                if (ok) {
+                    a[i] = NRB_LDS(src + (i64)k * P.in_es);
+                    if (G::N >= 2) b[i] = NRB_LDS(src + (i64)(k == 0 ? HALF : G::N - k) * P.in_es);
+                }
+            }
+#pragma unroll
             for (int i = 0; i < ITEMS; ++i) {
                 const int idx = tid + i * G::NT;
                 if (idx >= G::L * HALF) break;
                 const int k = idx & (HALF - 1), l = idx / HALF;
-                const u64 q = P.q_begin + (u64)tile * G::L + (u64)l;
-                const bool ok = q < P.q_end;
-                const double2 *src = P.in + line_base(q, P.in_s0, P.in_s1, P.in_s2, P.logA, P.logB);
-                const double2 zero = make_double2(0.0, 0.0);
                 if (k == 0) {
-                    double2 z0 = zero, zm = zero;
-                    if (ok) {
-                        const double2 g0 = src[0];
-                        if (P.real_mode == REAL_SPEQ) z0 = dc_inverse_speq(g0, P.speq[q]);
-                        else z0 = make_double2(0.5 * (g0.x + g0.y), 0.5 * (g0.x - g0.y));
-                        if (G::N >= 2) zm = src[(i64)HALF * P.in_es];
-                    }
+                    const u64 q = P.q_begin + (u64)tile * G::L + (u64)l;
+                    double2 z0 = make_double2(0.5 * (a[i].x + a[i].y), 0.5 * (a[i].x - a[i].y));
+                    if (P.real_mode == REAL_SPEQ)
+                        z0 = (q < P.q_end) ? dc_inverse_speq(a[i], P.speq[q]) : make_double2(0.0, 0.0);
                     sm[G::phys(l, 0)] = z0;
-                    if (G::N >= 2) sm[G::phys(l, HALF)] = zm;
+                    if (G::N >= 2) sm[G::phys(l, HALF)] = b[i];
                 } else {
-                    double2 oa = zero, ob = zero;
-                    if (ok) {
-                        const double2 a = src[(i64)k * P.in_es], b = src[(i64)(G::N - k) * P.in_es];
-                        untangle_pair<DIR>(a, b, NRB_LDG(P.rtw + k), oa, ob);
-                    }
+                    double2 oa, ob;
+                    untangle_pair<DIR>(a[i], b[i], NRB_LDG(P.rtw + k), oa, ob);
                     sm[G::phys(l, k)] = oa;
                     sm[G::phys(l, G::N - k)] = ob;
                 }

@@ -44,7 +44,8 @@ static Tunables &tunables_mut()
         Tunables x;
         x.col_max_log2 = env_int("NRB_COL_MAX_LOG2", 10);
         x.row_max_log2 = env_int("NRB_ROW_MAX_LOG2", 13);
-        x.l2_group_bytes = (u64)env_int("NRB_L2_GROUP_MB", 32) << 20;
+        x.l2_group_bytes = (u64)env_int("NRB_L2_GROUP_MB", 1 << 20) << 20;
+        x.batch_group_bytes = (u64)env_int("NRB_BATCH_GROUP_MB", 512) << 20;
         return x;
     }();
     if (t.col_max_log2 < 1) t.col_max_log2 = 1;
@@ -52,6 +53,7 @@ static Tunables &tunables_mut()
     if (t.row_max_log2 < 1) t.row_max_log2 = 1;
     if (t.row_max_log2 > kMaxLog2N) t.row_max_log2 = kMaxLog2N;
     if (t.l2_group_bytes < 1024) t.l2_group_bytes = 1024;
+    if (t.batch_group_bytes < 1024) t.batch_group_bytes = 1024;
     return t;
 }
 const Tunables &tunables() { return tunables_mut(); }
@@ -63,6 +65,7 @@ int set_tunable(const char *name, long value)
     if (n == "col_max_log2") t.col_max_log2 = (int)value;
     else if (n == "row_max_log2") t.row_max_log2 = (int)value;
     else if (n == "l2_group_bytes") t.l2_group_bytes = (u64)value;
+    else if (n == "batch_group_bytes") t.batch_group_bytes = (u64)value;
     else return -1;
     tunables_mut();   // re-clamp
     return 0;
@@ -473,7 +476,7 @@ int build_convlv(Plan &pl, Builder &B, int dir)
     }
     emit_real(B, R, R, T, 0, 1, p, +1, REAL_PACKED, BufRef());
     // signals in L2-sized groups: forward, spectral op, inverse
-    u64 gs = tunables().l2_group_bytes / (n * 8 * 2);
+    u64 gs = tunables().batch_group_bytes / (n * 8);
     if (gs < 1) gs = 1;
     if (gs > pl.batch) gs = pl.batch;
     for (u64 b0 = 0; b0 < pl.batch; b0 += gs) {
@@ -504,7 +507,7 @@ int build_correl(Plan &pl, Builder &B)
     }
     const u64 N = n / 2;
     const int p = ilog2((size_t)N);
-    u64 gs = tunables().l2_group_bytes / (n * 8 * 3);
+    u64 gs = tunables().batch_group_bytes / (n * 8);
     if (gs < 1) gs = 1;
     if (gs > pl.batch) gs = pl.batch;
     const BufRef F2(BUF_WS, 0), T(BUF_WS, (i64)(gs * N));

@@ -71,7 +71,8 @@ void release_tables();
 struct Tunables {
     int col_max_log2;      // longest strided-axis FFT done in one pass (NRB_COL_MAX_LOG2, default 10)
     int row_max_log2;      // longest contiguous FFT done in one pass   (NRB_ROW_MAX_LOG2, default 13)
-    u64 l2_group_bytes;    // working-set target for L2-resident pass groups (NRB_L2_GROUP_MB, default 32)
+    u64 l2_group_bytes;    // rlft3: bytes of x-planes handled per z/y launch pair (NRB_L2_GROUP_MB; default: whole volume)
+    u64 batch_group_bytes; // convlv/correl: bytes of signals handled per launch group (NRB_BATCH_GROUP_MB, default 512)
 };
 const Tunables &tunables();
 int set_tunable(const char *name, long value);   // returns 0 if the name is known

@@ -40,4 +40,5 @@ def _reset_options(request):
             L = request.getfixturevalue(name)
             L.set_option("col_max_log2", 10)
             L.set_option("row_max_log2", 13)
-            L.set_option("l2_group_bytes", 32 << 20)
+            L.set_option("l2_group_bytes", 1 << 40)
+            L.set_option("batch_group_bytes", 512 << 20)

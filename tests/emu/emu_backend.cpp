@@ -86,7 +86,7 @@ static Entry g_table[nrb::kMaxLog2N + 1][2][2][3];
 template <int LOG2N, int LAYOUT> static void reg()
 {
     using namespace nrb;
-    const int nt = cta_threads(LOG2N);
+    const int nt = cta_threads(LOG2N, LAYOUT);
     if (LAYOUT == LAYOUT_ROW) {
         g_table[LOG2N][0][1][VAR_PLAIN] = Entry{body_tpl<LOG2N, LAYOUT_ROW, 1, VAR_PLAIN>, nt, smem_elems(LOG2N, LAYOUT_ROW, VAR_PLAIN)};
         g_table[LOG2N][0][0][VAR_PLAIN] = Entry{body_tpl<LOG2N, LAYOUT_ROW, -1, VAR_PLAIN>, nt, smem_elems(LOG2N, LAYOUT_ROW, VAR_PLAIN)};

@@ -156,7 +156,7 @@ def test_convlv_reference_known_answers(emu):
 def test_convlv_batch(emu):
     sigs = [O.fill_uniform(1004, i * 1024, 1024) for i in range(7)]
     r = O.fill_uniform(1005, 0, 17) / 64
-    emu.set_option("l2_group_bytes", 3 * 1024 * 16)   # several signal groups
+    emu.set_option("batch_group_bytes", 3 * 1024 * 8)   # several signal groups
     outs = nb.convlv_batch(sigs, r, 1, _L=emu)
     for s, o in zip(sigs, outs):
         assert cases.rel(o, O.convlv(s, r, 1)[1]) <= cases.tol(1024)
@@ -183,7 +183,7 @@ def test_correl_reference_known_answers(emu):
 def test_correl_batch_large(emu):
     a = [O.fill_uniform(1, i * 256, 256) for i in range(5)]
     b = [O.fill_uniform(2, i * 256, 256) for i in range(5)]
-    emu.set_option("l2_group_bytes", 2 * 256 * 8 * 3)
+    emu.set_option("batch_group_bytes", 2 * 256 * 8)
     outs = nb.correl_batch(list(zip(a, b)), emu)
     for x, y, o in zip(a, b, outs):
         assert cases.rel(o, O.correl(x, y)[1]) <= cases.tol(256)

@@ -98,7 +98,6 @@ def main():
         out[wl] = {"step_ms": tot, "alg_GBps": alg / tot / 1e6, "kernels": [
             {"name": name, "ms_per_step": ms, "launches": cnt, "GBps": gbs, "frac": frac} for ms, name, cnt, gbs, frac in rows]}
         plan.destroy()
-        del bufs
         torch.cuda.empty_cache()
     tag = os.path.splitext(os.path.basename(nb.LIB_PATH))[0]
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
