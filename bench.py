@@ -171,7 +171,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 METRIC = {
@@ -364,22 +364,21 @@ def run_ours(args, rank, world, local_rank):
                 chk.mul_(2.0 / vol)
                 return float(torch.linalg.norm(chk - ref) / torch.linalg.norm(ref))
         else:
+            from numrs_b200.dist_rlft3 import SlabRlft3
             G = world
-            slab = lib.slab_create(n1, n2, n3, G, rank)
-            ld, sd, xd = slab.local_doubles(), slab.speq_doubles(), slab.xchg_doubles()
+            slab = SlabRlft3(lib, n1, n2, n3, mode=args.exchange)
+            ld, sd, xd = slab.local_doubles, slab.speq_doubles, slab.xchg_doubles
             bufs = [torch.empty(ld, **f64) for _ in range(pool)]
             speq = torch.empty(sd, **f64)
-            send = torch.empty(xd, **f64)
-            recv = torch.empty(xd, **f64)
             for b in bufs:   # synthetic slab: rank r's share of the seed-1006 sequence
                 lib.fill_uniform_device(b.data_ptr(), 1006, rank * ld, ld, st())
             launches_step = 0
-            extra["a2a_bytes_per_gpu_per_direction"] = 8.0 * xd * (G - 1) / G
+            extra["a2a_bytes_per_gpu_per_direction"] = slab.a2a_bytes_per_gpu()
+            extra["exchange"] = ("fused: stage-0 kernels store into peer receive buffers over NVLink (CUDA IPC), 1-element NCCL all-reduce as barrier"
+                                 if args.exchange == "fused" else "NCCL all_to_all_single")
 
             def one_direction(b, isign):
-                slab.stage(0, isign, b.data_ptr(), speq.data_ptr(), send.data_ptr(), 0, st())
-                dist.all_to_all_single(recv, send)
-                slab.stage(1, isign, b.data_ptr(), speq.data_ptr(), 0, recv.data_ptr(), st())
+                slab.transform(b, speq, isign)
 
             def step(i):
                 b = bufs[i % pool]
@@ -508,7 +507,7 @@ def run_ours(args, rank, world, local_rank):
             dt = float(tdt[0])
             e2e = {"value": bytes_step * Ke / dt / 1e9, "unit": "GB/s", "steps": Ke, "h2d_bytes_per_step": 8 * ld,
                    "d2h_bytes_per_step": 8 * ld, "ms_per_step": dt / Ke * 1e3,
-                   "api": "per-rank pinned slab -> nrb_slab_stage x2 + NCCL all-to-all, forward + inverse -> pinned slab"}
+                   "api": "per-rank pinned slab -> nrb_slab_stage x2 + exchange, forward + inverse -> pinned slab"}
     else:
         e2e = run_e2e_batch(lib, nb, wl, world)
 
@@ -528,7 +527,7 @@ def run_ours(args, rank, world, local_rank):
         if world > 1 and wl == "rlft3_512":
             line["gpu_launches"] = K * 2 * 5
             line.update(extra)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist:
         dist.destroy_process_group()
 
@@ -621,7 +620,24 @@ def cpu_baseline(wl):
             "sample": f"{reps} x {wl}_batch({cnt} x n=2^20, m=4096), {cores} threads"}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The JSON line goes to the real stdout; everything else (NCCL banners, warnings) to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)          # libraries that print to fd 1 (NCCL version banner) must not pollute the JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -629,6 +645,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="rlft3_512", choices=sorted(METRIC))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"], help="multi-GPU rlft3 exchange")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -143,7 +143,20 @@ size_t nrb_slab_speq_doubles(nrb_slab_t plan);    /* doubles in the local speq p
 size_t nrb_slab_xchg_doubles(nrb_slab_t plan);    /* doubles in the exchange buffer        */
 int    nrb_slab_stage(nrb_slab_t plan, int stage, int isign, double *d_slab, double *d_speq,
                       double *d_send, double *d_recv, void *stream);
+/* Fused exchange over NVLink peer memory: give the plan every rank's receive buffer (each at least
+ * nrb_slab_xchg_doubles() doubles, allocated with nrb_device_alloc and mapped into this process with
+ * nrb_ipc_export / nrb_ipc_import; peer_recv[rank] is the local one).  Stage 0 then stores its output
+ * DIRECTLY into the owning peer's buffer from the FFT kernel's epilogue (no send buffer, no NCCL
+ * all-to-all: d_send / d_recv are ignored); the caller only has to put a cross-rank barrier between
+ * stage 0 and stage 1.  Passing NULL returns the plan to the explicit send/recv mode. */
+int    nrb_slab_set_peers(nrb_slab_t plan, void *const *peer_recv, int count);
 int    nrb_slab_destroy(nrb_slab_t plan);
+/* raw device memory + CUDA IPC plumbing for the above */
+int    nrb_device_alloc(size_t bytes, void **dptr);
+int    nrb_device_free(void *dptr);
+int    nrb_ipc_export(void *dptr, unsigned char handle[64]);
+int    nrb_ipc_import(const unsigned char handle[64], void **dptr);
+int    nrb_ipc_release(void *dptr);
 
 #ifdef __cplusplus
 }

@@ -39,7 +39,8 @@ ABI_SYMBOLS = [
     "nrb_plan_create", "nrb_plan_workspace_bytes", "nrb_plan_num_launches", "nrb_plan_exec", "nrb_plan_destroy",
     "nrb_plan_profile", "nrb_plan_describe_launch", "nrb_fill_uniform_device",
     "nrb_slab_create", "nrb_slab_local_doubles", "nrb_slab_speq_doubles", "nrb_slab_xchg_doubles",
-    "nrb_slab_stage", "nrb_slab_destroy",
+    "nrb_slab_stage", "nrb_slab_destroy", "nrb_slab_set_peers",
+    "nrb_device_alloc", "nrb_device_free", "nrb_ipc_export", "nrb_ipc_import", "nrb_ipc_release",
 ]
 
 
@@ -100,6 +101,12 @@ class Library:
             getattr(L, n).restype = _sz
         L.nrb_slab_stage.argtypes = [_vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp]
         L.nrb_slab_destroy.argtypes = [_vp]
+        L.nrb_slab_set_peers.argtypes = [_vp, ctypes.POINTER(_vp), ctypes.c_int]
+        L.nrb_device_alloc.argtypes = [_sz, ctypes.POINTER(_vp)]
+        L.nrb_device_free.argtypes = [_vp]
+        L.nrb_ipc_export.argtypes = [_vp, ctypes.c_char_p]
+        L.nrb_ipc_import.argtypes = [ctypes.c_char_p, ctypes.POINTER(_vp)]
+        L.nrb_ipc_release.argtypes = [_vp]
 
     # ---- helpers
     def last_error(self):
@@ -208,6 +215,27 @@ class Library:
     def fill_uniform_device(self, d_ptr, seed, offset, count, stream=0):
         self.check(self.L.nrb_fill_uniform_device(d_ptr, seed, offset, count, stream or None))
 
+    def device_alloc(self, nbytes):
+        p = _vp()
+        self.check(self.L.nrb_device_alloc(nbytes, ctypes.byref(p)))
+        return p.value
+
+    def device_free(self, ptr):
+        self.L.nrb_device_free(ptr)
+
+    def ipc_export(self, ptr):
+        buf = ctypes.create_string_buffer(64)
+        self.check(self.L.nrb_ipc_export(ptr, buf))
+        return buf.raw
+
+    def ipc_import(self, handle):
+        p = _vp()
+        self.check(self.L.nrb_ipc_import(handle, ctypes.byref(p)))
+        return p.value
+
+    def ipc_release(self, ptr):
+        self.check(self.L.nrb_ipc_release(ptr))
+
     # ---- device-resident plan API (pointers are integers: device addresses)
     def plan_create(self, kind, dims, batch=1):
         h = _vp()
@@ -270,6 +298,14 @@ class SlabPlan:
 
     def xchg_doubles(self):
         return self.lib.L.nrb_slab_xchg_doubles(self.h)
+
+    def set_peers(self, peer_ptrs):
+        """Fused exchange: peer_ptrs[i] = rank i's receive buffer mapped into this process (None to disable)."""
+        if peer_ptrs is None:
+            self.lib.check(self.lib.L.nrb_slab_set_peers(self.h, None, 0))
+            return
+        arr = (_vp * len(peer_ptrs))(*peer_ptrs)
+        self.lib.check(self.lib.L.nrb_slab_set_peers(self.h, arr, len(peer_ptrs)))
 
     def stage(self, stage, isign, d_slab, d_speq, d_send, d_recv, stream=0):
         self.lib.check(self.lib.L.nrb_slab_stage(self.h, stage, isign, d_slab, d_speq, d_send or None,

@@ -267,6 +267,34 @@ int nrb_slab_stage(nrb_slab_t p, int stage, int isign, double *d_slab, double *d
     if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
     return exec_slab_stage(p->plan, stage, isign, d_slab, d_speq, d_send, d_recv, stream);
 }
+int nrb_slab_set_peers(nrb_slab_t p, void *const *peer_recv, int count)
+{
+    if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
+    return slab_set_peers(p->plan, peer_recv, count);
+}
+int nrb_device_alloc(size_t bytes, void **dptr)
+{
+    if (!dptr) return fail(NRB_ERR_INVALID_DIMS, "null pointer");
+    if (be_device_count() <= 0) return fail(NRB_ERR_CUDA, "no CUDA device available (numrs_b200 has no CPU fallback)");
+    if (be_malloc(dptr, bytes) != 0) return fail(NRB_ERR_OOM, std::string("device allocation failed: ") + be_last_error());
+    return NRB_OK;
+}
+int nrb_device_free(void *dptr) { if (dptr) be_free(dptr); return NRB_OK; }
+int nrb_ipc_export(void *dptr, unsigned char handle[64])
+{
+    if (be_ipc_export(dptr, handle) != 0) return fail(NRB_ERR_CUDA, std::string("cudaIpcGetMemHandle failed: ") + be_last_error());
+    return NRB_OK;
+}
+int nrb_ipc_import(const unsigned char handle[64], void **dptr)
+{
+    if (be_ipc_import(handle, dptr) != 0) return fail(NRB_ERR_CUDA, std::string("cudaIpcOpenMemHandle failed: ") + be_last_error());
+    return NRB_OK;
+}
+int nrb_ipc_release(void *dptr)
+{
+    if (be_ipc_release(dptr) != 0) return fail(NRB_ERR_CUDA, std::string("cudaIpcCloseMemHandle failed: ") + be_last_error());
+    return NRB_OK;
+}
 int nrb_slab_destroy(nrb_slab_t p)
 {
     if (!p) return NRB_OK;

@@ -89,6 +89,27 @@ int be_free(void *p)
     cudaError_t e = cudaFree(p);
     return e == cudaSuccess ? 0 : fail(e);
 }
+int be_ipc_export(void *dptr, unsigned char handle[64])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, dptr);
+    if (e != cudaSuccess) return fail(e);
+    memcpy(handle, &h, 64);
+    return 0;
+}
+int be_ipc_import(const unsigned char handle[64], void **dptr)
+{
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess);
+    return e == cudaSuccess ? 0 : fail(e);
+}
+int be_ipc_release(void *dptr)
+{
+    cudaError_t e = cudaIpcCloseMemHandle(dptr);
+    return e == cudaSuccess ? 0 : fail(e);
+}
 int be_h2d(void *dst, const void *src, size_t bytes, void *stream)
 {
     cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream);

@@ -226,13 +226,20 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
         if (DST_G) {
             const u64 q = P.q_begin + (u64)tile * G::L + (u64)ln[i];
             if (q < P.q_end) {
-                double2 *dst = P.out + line_base(q, P.out_s0, P.out_s1, P.out_s2, P.logA, P.logB);
+                const i64 lb = line_base(q, P.out_s0, P.out_s1, P.out_s2, P.logA, P.logB);
+                double2 *dst = P.out + lb;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const int k = kb + r * NS;
                     double2 y = v[i][r];
                     if (P.tw_on) y = cmul(y, fourstep_tw(P, q, (unsigned)k));
-                    NRB_STS(dst + elem_off(k, P.out_es, P.out_eshift, P.out_es_hi), io_swap<DIR>(y));
+                    if (P.out_peer_on) {   // store straight into the owning peer's receive buffer (NVLink)
+                        double2 *pd = P.out_peer[k >> P.out_eshift] + P.out_peer_off + lb +
+                                      (i64)(k & ((1 << P.out_eshift) - 1)) * P.out_es;
+                        NRB_STS(pd, io_swap<DIR>(y));
+                    } else {
+                        NRB_STS(dst + elem_off(k, P.out_es, P.out_eshift, P.out_es_hi), io_swap<DIR>(y));
+                    }
                 }
             }
         } else {

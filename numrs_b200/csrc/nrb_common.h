@@ -174,6 +174,12 @@ struct PassParams {
     //   (n & (2^eshift - 1)) * es + (n >> eshift) * es_hi ; eshift = 31 disables the split
     i64 in_es_hi, out_es_hi;
     int in_eshift, out_eshift;
+    // fused exchange (slab rlft3 over NVLink): when out_peer_on, the high part of the output element
+    // index selects a PEER GPU's receive buffer (mapped through CUDA IPC) instead of a stride:
+    //   address = out_peer[n >> out_eshift] + out_peer_off + line offset + (n & mask) * out_es
+    double2 *out_peer[8];
+    i64 out_peer_off;
+    int out_peer_on;
     u64 q_begin, q_end;
     int logA, logB;
     int tw_on;              // multiply output k of line q by exp(-/+ 2 pi i q1 k / M)

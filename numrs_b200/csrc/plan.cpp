@@ -593,7 +593,10 @@ int build_plan(Plan &pl, int kind, const size_t *dims, size_t ndim, size_t batch
     return NRB_OK;
 }
 
-static int run_program(Program &prog, double2 *const base[4], int arg, void *stream, std::vector<void *> *events = nullptr)
+struct PeerExchange { double2 *const *peers; i64 off; };
+
+static int run_program(Program &prog, double2 *const base[4], int arg, void *stream, std::vector<void *> *events = nullptr,
+                       const PeerExchange *px = nullptr)
 {
     if (events) events->push_back(be_event_record(stream));
     for (Step &st : prog.steps) {
@@ -611,6 +614,11 @@ static int run_program(Program &prog, double2 *const base[4], int arg, void *str
             pp.in = base[st.in.id] + st.in.off;
             pp.out = base[st.out.id] + st.out.off;
             pp.speq = st.speq.id == BUF_NONE ? nullptr : base[st.speq.id] + st.speq.off;
+            if (px && st.out.id == BUF_OUT) {   // exchange output: write into the peers' receive buffers
+                pp.out_peer_on = 1;
+                pp.out_peer_off = px->off;
+                for (int i = 0; i < 8; ++i) pp.out_peer[i] = px->peers[i] ? px->peers[i] + st.out.off : nullptr;
+            }
             rc = be_launch_pass(st.key, pp, st.ntiles, stream);
         }
         if (rc != 0) { set_error(std::string("kernel launch failed: ") + be_last_error()); return NRB_ERR_CUDA; }
@@ -751,11 +759,29 @@ int build_slab_plan(SlabPlan &sp, size_t nn1, size_t nn2, size_t nn3, int nranks
     return NRB_OK;
 }
 
+int slab_set_peers(SlabPlan &sp, void *const *peer_recv, int count)
+{
+    if (!peer_recv) { sp.fused = false; return NRB_OK; }
+    if (count != sp.nranks || count > 8) { set_error("slab: need one receive buffer per rank (at most 8)"); return NRB_ERR_INVALID_DIMS; }
+    for (int i = 0; i < 8; ++i) sp.peers[i] = i < count ? (double2 *)peer_recv[i] : nullptr;
+    for (int i = 0; i < count; ++i) if (!sp.peers[i]) { set_error("slab: null peer buffer"); return NRB_ERR_INVALID_DIMS; }
+    sp.fused = true;
+    return NRB_OK;
+}
+
 int exec_slab_stage(SlabPlan &sp, int stage, int isign, double *d_slab, double *d_speq, double *d_send,
                     double *d_recv, void *stream)
 {
     if (isign != 1 && isign != -1) { set_error("isign must be 1 or -1"); return NRB_ERR_INVALID_ISIGN; }
     if (stage != 0 && stage != 1) { set_error("stage must be 0 or 1"); return NRB_ERR_INVALID_DIMS; }
+    if (sp.fused) {
+        // stage 0 stores go straight to the peers; stage 1 reads the local receive buffer
+        const u64 G = (u64)sp.nranks;
+        const i64 BLK = (i64)((sp.nn1 / G) * (sp.nn2 / G) * (sp.nn3 / 2 + 1));
+        double2 *const base[4] = {(double2 *)d_slab, (double2 *)d_speq, sp.peers[sp.rank], (double2 *)sp.ws};
+        PeerExchange px{sp.peers, (i64)sp.rank * BLK};
+        return run_program(sp.prog[isign == 1 ? 0 : 1][stage], base, 0, stream, nullptr, stage == 0 ? &px : nullptr);
+    }
     double2 *const base[4] = {(double2 *)d_slab, (double2 *)d_speq, (double2 *)(stage == 0 ? d_send : d_recv),
                               (double2 *)sp.ws};
     return run_program(sp.prog[isign == 1 ? 0 : 1][stage], base, 0, stream);

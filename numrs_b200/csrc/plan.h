@@ -15,6 +15,9 @@ int be_launch_pass(const KernelKey &key, const PassParams &p, u64 ntiles, void *
 int be_launch_aux(const AuxParams &a, void *stream);
 int be_malloc(void **p, size_t bytes);
 int be_free(void *p);
+int be_ipc_export(void *dptr, unsigned char handle[64]);
+int be_ipc_import(const unsigned char handle[64], void **dptr);
+int be_ipc_release(void *dptr);
 int be_h2d(void *dst, const void *src, size_t bytes, void *stream);
 int be_d2h(void *dst, const void *src, size_t bytes, void *stream);
 int be_d2d(void *dst, const void *src, size_t bytes, void *stream);
@@ -105,9 +108,12 @@ struct SlabPlan {
     Program prog[2][2];    // [isign index][stage]
     size_t ws_elems;
     void *ws;
-    SlabPlan() : nn1(0), nn2(0), nn3(0), nranks(1), rank(0), ws_elems(0), ws(nullptr) {}
+    double2 *peers[8];     // peer receive buffers (fused exchange); peers[rank] is the local one
+    bool fused;
+    SlabPlan() : nn1(0), nn2(0), nn3(0), nranks(1), rank(0), ws_elems(0), ws(nullptr), peers{}, fused(false) {}
 };
 int build_slab_plan(SlabPlan &sp, size_t nn1, size_t nn2, size_t nn3, int nranks, int rank);
+int slab_set_peers(SlabPlan &sp, void *const *peer_recv, int count);
 int exec_slab_stage(SlabPlan &sp, int stage, int isign, double *d_slab, double *d_speq, double *d_send,
                     double *d_recv, void *stream);
 

@@ -1,0 +1,79 @@
+"""Slab-decomposed rlft3 across the GPUs of one box: one process per GPU (torch.distributed, NCCL).
+
+Forward (isign=+1): rank r passes its nn2-slab data[:, r*nn2/G:(r+1)*nn2/G, :] (contiguous
+[nn1][nn2/G][nn3] real) and gets back, in the same buffer, its nn1-slab of the spectrum
+([nn1/G][nn2][nn3/2] complex = rows r*nn1/G.. of the reference's layout) plus speq [nn1/G][2*nn2].
+Inverse (isign=-1) is the mirror image.  Exactly one exchange per direction:
+
+  mode "fused" (default): the last FFT pass of stage 0 stores its output straight into the owning
+      peer's receive buffer through NVLink (CUDA IPC mapped peer memory) from the kernel epilogue,
+      so the transfer overlaps the transform tile by tile; a stream-ordered 1-element NCCL
+      all-reduce is the only collective (the barrier between stage 0 and stage 1).
+  mode "nccl": stage 0 writes a send buffer, torch.distributed.all_to_all_single moves the blocks.
+"""
+import torch
+import torch.distributed as dist
+
+
+class SlabRlft3:
+    def __init__(self, lib, nn1, nn2, nn3, mode="fused"):
+        self.lib = lib
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.dims = (nn1, nn2, nn3)
+        self.plan = lib.slab_create(nn1, nn2, nn3, self.world, self.rank)
+        self.local_doubles = self.plan.local_doubles()
+        self.speq_doubles = self.plan.speq_doubles()
+        self.xchg_doubles = self.plan.xchg_doubles()
+        self.mode = mode
+        self._flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+        self._call = 0
+        if mode == "fused":
+            # two receive buffers, alternated per call, so a peer still reading call k's data in its
+            # stage 1 is never overwritten by call k+1's stage 0 (ordered by call k+1's barrier)
+            self._own, self._peers = [], []
+            for _ in range(2):
+                own = lib.device_alloc(self.xchg_doubles * 8)
+                handle = lib.ipc_export(own)
+                handles = [None] * self.world
+                dist.all_gather_object(handles, handle)
+                peers = [own if r == self.rank else lib.ipc_import(h) for r, h in enumerate(handles)]
+                self._own.append(own)
+                self._peers.append(peers)
+            dist.barrier()
+        elif mode == "nccl":
+            self.send = torch.empty(self.xchg_doubles, dtype=torch.float64, device="cuda")
+            self.recv = torch.empty(self.xchg_doubles, dtype=torch.float64, device="cuda")
+        else:
+            raise ValueError(mode)
+
+    def a2a_bytes_per_gpu(self):
+        return 8.0 * self.xchg_doubles * (self.world - 1) / self.world
+
+    def transform(self, slab, speq, isign):
+        """slab, speq: torch float64 CUDA tensors (local_doubles / speq_doubles); in place; enqueues on
+        the current stream."""
+        st = torch.cuda.current_stream().cuda_stream
+        if self.mode == "fused":
+            peers = self._peers[self._call & 1]
+            self._call += 1
+            self.plan.set_peers(peers)
+            self.plan.stage(0, isign, slab.data_ptr(), speq.data_ptr(), 0, 0, st)
+            dist.all_reduce(self._flag)      # stream-ordered barrier: every rank's stage-0 stores have landed
+            self.plan.stage(1, isign, slab.data_ptr(), speq.data_ptr(), 0, 0, st)
+        else:
+            self.plan.stage(0, isign, slab.data_ptr(), speq.data_ptr(), self.send.data_ptr(), 0, st)
+            dist.all_to_all_single(self.recv, self.send)
+            self.plan.stage(1, isign, slab.data_ptr(), speq.data_ptr(), 0, self.recv.data_ptr(), st)
+
+    def close(self):
+        torch.cuda.synchronize()
+        dist.barrier()
+        if self.mode == "fused":
+            for own, peers in zip(self._own, self._peers):
+                for r, p in enumerate(peers):
+                    if r != self.rank:
+                        self.lib.ipc_release(p)
+            dist.barrier()
+            for own in self._own:
+                self.lib.device_free(own)
+        self.plan.destroy()

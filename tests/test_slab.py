@@ -18,8 +18,9 @@ def slab_of(x, r, G):
     return np.ascontiguousarray(x[:, r * Y:(r + 1) * Y, :])
 
 
-def run_simulated(L, x, G, isign, speq_in=None):
-    """All G ranks in one process; returns per-rank (slab, speq) after one direction."""
+def run_simulated(L, x, G, isign, speq_in=None, fused=False):
+    """All G ranks in one process; returns per-rank (slab, speq) after one direction.
+    fused=True: stage 0 stores straight into the peers' receive buffers (no explicit exchange)."""
     nn1, nn2, nn3 = x.shape
     X, Y = nn1 // G, nn2 // G
     plans = [L.slab_create(nn1, nn2, nn3, G, r) for r in range(G)]
@@ -33,11 +34,15 @@ def run_simulated(L, x, G, isign, speq_in=None):
         speqs = [np.ascontiguousarray(speq_in[r * X:(r + 1) * X]).ravel().copy() for r in range(G)]
     sends = [np.zeros(xd) for _ in range(G)]
     recvs = [np.zeros(xd) for _ in range(G)]
+    if fused:
+        for r in range(G):
+            plans[r].set_peers([rv.ctypes.data for rv in recvs])
     for r in range(G):
         plans[r].stage(0, isign, slabs[r].ctypes.data, speqs[r].ctypes.data, sends[r].ctypes.data, 0)
     for r in range(G):          # all-to-all: block p of rank r's send -> block r of rank p's recv
         for p in range(G):
-            recvs[p][r * blk:(r + 1) * blk] = sends[r][p * blk:(p + 1) * blk]
+            if not fused:
+                recvs[p][r * blk:(r + 1) * blk] = sends[r][p * blk:(p + 1) * blk]
     for r in range(G):
         plans[r].stage(1, isign, slabs[r].ctypes.data, speqs[r].ctypes.data, 0, recvs[r].ctypes.data)
     for p in plans:
@@ -45,19 +50,20 @@ def run_simulated(L, x, G, isign, speq_in=None):
     return slabs, speqs
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("shape,G", [((8, 8, 8), 2), ((16, 16, 8), 4), ((8, 16, 32), 8), ((32, 8, 4), 8), ((4, 4, 2), 4),
                                      ((16, 16, 16), 1)])
-def test_slab_simulated_ranks(emu, shape, G):
+def test_slab_simulated_ranks(emu, shape, G, fused):
     nn1, nn2, nn3 = shape
     X, Y = nn1 // G, nn2 // G
     x = O.fill_uniform(1006, 0, nn1 * nn2 * nn3).reshape(shape)
     rd, rs = O.rlft3(x.copy(), np.zeros((nn1, 2 * nn2)), 1)
-    slabs, speqs = run_simulated(emu, x, G, 1)
+    slabs, speqs = run_simulated(emu, x, G, 1, fused=fused)
     for r in range(G):      # forward output: nn1-slabs = contiguous row ranges of the reference layout
         assert cases.rel(slabs[r], rd[r * X:(r + 1) * X]) <= cases.tol(x.size), (r, "data")
         assert cases.rel(speqs[r], rs[r * X:(r + 1) * X]) <= cases.tol(x.size), (r, "speq")
     # inverse from the spectrum: output nn2-slabs, round trip = N/2 * x
-    back, _ = run_simulated(emu, rd, G, -1, rs)
+    back, _ = run_simulated(emu, rd, G, -1, rs, fused=fused)
     for r in range(G):
         assert cases.rel(back[r] * (2.0 / x.size), slab_of(x, r, G)) <= cases.tol(x.size), (r, "round trip")
 
