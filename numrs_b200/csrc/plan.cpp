@@ -666,9 +666,9 @@ int describe_launch(const Plan &pl, int isign, int idx, char *name, size_t cap, 
         }
     } else {
         static const char *var[] = {"plain", "real", "xpose"};
-        snprintf(buf, sizeof(buf), "fft_%s_%s_n%d_%s", st.key.layout == LAYOUT_ROW ? "row" : "col", var[st.key.variant],
-                 1 << st.key.log2n, st.key.dir > 0 ? "p" : "m");
         const double lines = (double)(st.pp.q_end - st.pp.q_begin);
+        snprintf(buf, sizeof(buf), "fft_%s_%s_n%d_%s_L%llu", st.key.layout == LAYOUT_ROW ? "row" : "col", var[st.key.variant],
+                 1 << st.key.log2n, st.key.dir > 0 ? "p" : "m", (unsigned long long)(st.pp.q_end - st.pp.q_begin));
         b = 2.0 * 16.0 * lines * (double)(1 << st.key.log2n);
         if (st.key.variant == VAR_REAL && st.pp.real_mode == REAL_SPEQ) b += 16.0 * lines;
     }

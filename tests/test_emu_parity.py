@@ -213,7 +213,7 @@ def test_plan_api_device_pointers(emu):
     plan.exec(x.ctypes.data, isign=1)
     assert cases.rel(x, ref) <= cases.tol(n)
     prof = plan.profile(x.ctypes.data, isign=-1)
-    assert prof[0][0] == "fft_row_plain_n4096_m" and prof[0][1] == 2 * 16 * n * 3
+    assert prof[0][0] == "fft_row_plain_n4096_m_L3" and prof[0][1] == 2 * 16 * n * 3
     plan.destroy()
     big = emu.plan_create(nb.KIND_FOUR1, [1 << 16], batch=1)
     assert big.num_launches(1) == 2 and big.workspace_bytes() == (1 << 16) * 16

@@ -1,8 +1,8 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-for n in 4 8; do
-    timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 295$n$n tools/slab_breakdown.py 512 fused 2>&1 | grep -E "==|   |Error|error" | head -20
-    timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 296$n$n bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/bench_n$n.json 2> gpurun_out/bench_n$n.err; echo "bench exit $?"; python -c "import sys,json; d=json.loads(open('gpurun_out/bench_n$n.json').read()); print('bench n=%d value %.0f GB/s  ms/step %.3f  e2e %.1f GB/s err %.2e' % (d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], d['roundtrip_rel_l2']))"
-done
-timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29777 tools/slab_breakdown.py 1024 fused 2>&1 | grep -E "==|   |Error|error" | head -20
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:fft_pass_kernel -s 10 -c 10 -o gpurun_out/r01_rlft3_full -f python tools/profile_rlft3.py 512 > gpurun_out/ncu_full.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fft_pass_kernel -s 2 -c 2 -o gpurun_out/r01_four1_20 -f python tools/profile_generic.py four1_20_64 > gpurun_out/ncu_four1_20.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fft_pass_kernel -s 1 -c 1 -o gpurun_out/r01_four1_12 -f python tools/profile_generic.py four1_12_4096 > gpurun_out/ncu_four1_12.log 2>&1
+tail -2 gpurun_out/ncu_full.log gpurun_out/ncu_four1_20.log gpurun_out/ncu_four1_12.log
+ls -la gpurun_out/*.ncu-rep
