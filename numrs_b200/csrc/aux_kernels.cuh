@@ -84,6 +84,66 @@ NRB_DEV void aux_spectral(const AuxParams &A, u64 gtid, u64 gthreads)
     }
 }
 
+// Fused spectral step for transforms whose real untangling is a separate pass (lines longer than a CTA
+// tile): a = raw c2c output Z of the data (N = n/2 complex per signal), b = either the packed, already
+// untangled response spectrum shared by all signals (b_stride == 0, convlv) or the raw c2c output of the
+// second signal (b_stride != 0, correl).  Per pair (k, N-k): forward untangle (Real_FT.rs:49-80), the
+// spectral op with the 1/no2 scale (Convolve.rs:112-129 / Correlation.rs:91-92), inverse untangle
+// (Real_FT.rs:145-176) -- out is ready for the inverse c2c.  Saves two (convlv) / three (correl) full
+// passes over the data.  items: count * max(N/2, 1).
+NRB_DEV double2 spectral_op(int op, double2 d, double2 r, double inv)
+{
+    if (op == SPEC_CONV_MUL) return make_double2((d.x * r.x - d.y * r.y) * inv, (d.x * r.y + d.y * r.x) * inv);
+    if (op == SPEC_CORREL) return make_double2((d.x * r.x + d.y * r.y) * inv, (d.y * r.x - d.x * r.y) * inv);
+    const double mag2 = r.x * r.x + r.y * r.y;
+    if (mag2 < 1e-12) return make_double2(0.0, 0.0);
+    return make_double2((d.x * r.x + d.y * r.y) / mag2 * inv, (d.y * r.x - d.x * r.y) / mag2 * inv);
+}
+NRB_DEV double spectral_op_real(int op, double d, double r, double inv)
+{
+    if (op == SPEC_CONV_DIV) { const double m = r * r; return m < 1e-12 ? 0.0 : d * r / m * inv; }
+    return d * r * inv;
+}
+
+NRB_DEV void aux_spectral_z(const AuxParams &A, u64 gtid, u64 gthreads)
+{
+    const u64 N = A.n / 2;
+    const u64 half = N >= 2 ? N / 2 : 1;
+    const u64 items = A.count * half;
+    const double inv = 1.0 / (double)N;
+    const bool b_raw = A.b_stride != 0;
+    for (u64 it = gtid; it < items; it += gthreads) {
+        const u64 k = it % half, sig = it / half;
+        const double2 *za = A.a + (i64)sig * A.a_stride;
+        const double2 *zb = A.b + (i64)sig * A.b_stride;
+        double2 *out = A.out + (i64)sig * A.out_stride;
+        if (k == 0) {
+            const double2 a0 = NRB_LDS(za);
+            double2 r0 = b_raw ? NRB_LDS(zb) : NRB_LDG(zb);
+            if (b_raw) r0 = make_double2(r0.x + r0.y, r0.x - r0.y);       // (B_0, B_N)
+            const double g0 = spectral_op_real(A.op, a0.x + a0.y, r0.x, inv);
+            const double gn = spectral_op_real(A.op, a0.x - a0.y, r0.y, inv);
+            out[0] = make_double2(0.5 * (g0 + gn), 0.5 * (g0 - gn));
+            if (N >= 2) {   // middle bin: untangling is the identity there
+                const double2 am = NRB_LDS(za + N / 2);
+                const double2 rm = b_raw ? NRB_LDS(zb + N / 2) : NRB_LDG(zb + N / 2);
+                out[N / 2] = spectral_op(A.op, am, rm, inv);
+            }
+        } else {
+            const double2 t = two_level_tw(A.rtw_lo, A.rtw_hi, A.rtw_h, k);
+            double2 fa, fm, ra, rm;
+            untangle_pair<1>(NRB_LDS(za + k), NRB_LDS(za + (N - k)), t, fa, fm);
+            if (b_raw) untangle_pair<1>(NRB_LDS(zb + k), NRB_LDS(zb + (N - k)), t, ra, rm);
+            else { ra = NRB_LDG(zb + k); rm = NRB_LDG(zb + (N - k)); }
+            const double2 ga = spectral_op(A.op, fa, ra, inv), gm = spectral_op(A.op, fm, rm, inv);
+            double2 oa, ob;
+            untangle_pair<-1>(ga, gm, t, oa, ob);
+            out[k] = oa;
+            out[N - k] = ob;
+        }
+    }
+}
+
 // a = response taps (m doubles), out = padded response (n doubles).  items: n.
 NRB_DEV void aux_pad_response(const AuxParams &A, u64 gtid, u64 gthreads)
 {
@@ -144,6 +204,7 @@ NRB_DEV void aux_body(const AuxParams &A, u64 gtid, u64 gthreads)
     case AUX_SPECTRAL: aux_spectral(A, gtid, gthreads); break;
     case AUX_PAD_RESPONSE: aux_pad_response(A, gtid, gthreads); break;
     case AUX_FILL: aux_fill(A, gtid, gthreads); break;
+    case AUX_SPECTRAL_Z: aux_spectral_z(A, gtid, gthreads); break;
     default: aux_correl_direct(A, gtid, gthreads); break;
     }
 }

@@ -61,6 +61,7 @@ int be_launch_aux(const AuxParams &a, void *stream)
     case AUX_SPECTRAL: items = a.count * (a.n / 2); break;
     case AUX_PAD_RESPONSE: items = a.n; break;
     case AUX_FILL: items = a.n; break;
+    case AUX_SPECTRAL_Z: items = a.count * (a.n >= 8 ? a.n / 4 : 1); break;
     default: items = a.count * a.n; break;
     }
     if (items == 0) return 0;

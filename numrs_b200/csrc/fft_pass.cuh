@@ -134,7 +134,15 @@ template <int LOG2N, int LAYOUT, int VARIANT> struct Geo {
     static constexpr int CP = col_pitch(LOG2N, VARIANT); // COL: pitch of one n
     NRB_DEVM static int phys(int l, int n)
     {
-        return LAYOUT == LAYOUT_ROW ? l * LP + n + (n >> 3) : n * CP + l;
+        if (LAYOUT == LAYOUT_ROW) return l * LP + n + (n >> 3);
+        if (VARIANT == VAR_XPOSE && L > 1 && L < 8) {
+            // 8-thread phases of the stages touch an aligned run of 8 elements (a >> 3 constant), the
+            // line-contiguous read-back touches a = n*L + l for 8 consecutive n: XOR the missing bits
+            // of n into the low 3 bits so both patterns hit 8 distinct 16-byte bank groups
+            const int a = n * L + l;
+            return a ^ ((a >> 3) & (L == 4 ? 3 : 1));
+        }
+        return n * CP + l;
     }
 };
 
@@ -159,6 +167,18 @@ NRB_DEV double2 fourstep_tw(const PassParams &P, u64 q, unsigned k)
     const double2 lo = NRB_LDG(P.tw_lo + (m & ((1u << P.tw_h) - 1u)));
     const double2 hi = NRB_LDG(P.tw_hi + (m >> P.tw_h));
     return cmul(lo, hi);
+}
+
+// exp(-2 pi i m / M) for an explicit exponent m < M
+NRB_DEV double2 fourstep_tw_m(const PassParams &P, unsigned m)
+{
+    const double2 lo = NRB_LDG(P.tw_lo + (m & ((1u << P.tw_h) - 1u)));
+    const double2 hi = NRB_LDG(P.tw_hi + (m >> P.tw_h));
+    return cmul(lo, hi);
+}
+NRB_DEV unsigned line_q1(const PassParams &P, u64 q)
+{
+    return (unsigned)((q >> P.logB) & ((1ull << P.logA) - 1ull));
 }
 
 // ------------------------------------------------------------------ one Stockham stage
@@ -228,11 +248,19 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
             if (q < P.q_end) {
                 const i64 lb = line_base(q, P.out_s0, P.out_s1, P.out_s2, P.logA, P.logB);
                 double2 *dst = P.out + lb;
+                // four-step twiddle W^(q1*k), k = kb + r*NS: geometric in r -> two table look-ups
+                // (base and ratio) and R-1 complex multiplies instead of R look-ups
+                double2 tw = make_double2(1.0, 0.0), tw_step = make_double2(1.0, 0.0);
+                if (P.tw_on) {
+                    const unsigned q1 = line_q1(P, q);
+                    tw = fourstep_tw_m(P, q1 * (unsigned)kb);
+                    tw_step = fourstep_tw_m(P, q1 * (unsigned)NS);
+                }
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const int k = kb + r * NS;
                     double2 y = v[i][r];
-                    if (P.tw_on) y = cmul(y, fourstep_tw(P, q, (unsigned)k));
+                    if (P.tw_on) { y = cmul(y, tw); tw = cmul(tw, tw_step); }
                     if (P.out_peer_on) {   // store straight into the owning peer's receive buffer (NVLink)
                         double2 *pd = P.out_peer[k >> P.out_eshift] + P.out_peer_off + lb +
                                       (i64)(k & ((1 << P.out_eshift) - 1)) * P.out_es;
@@ -307,18 +335,36 @@ NRB_DEV void fft_pass_body(const PassParams &P, double2 *sm, unsigned tile, int 
     }
 
     if (VARIANT == VAR_XPOSE) {
-        // COL layout; last stage to shared memory, then row-like (line-contiguous) store
+        // COL layout; last stage to shared memory, then row-like (line-contiguous) store with the
+        // four-step twiddle W^(q1(l)*k).  A thread's elements share k (C distinct values when N > NT)
+        // and walk the lines with a fixed step D, so the twiddle is a geometric sequence per k.
         StageRunner<LOG2N, LAYOUT, DIR, VARIANT, 0, true, false>::run(P, sm, tile, tid);
+        constexpr int C = (G::N > G::NT) ? G::N / G::NT : 1;
+        constexpr int D = (G::NT >= G::N) ? G::NT / G::N : 1;
+        constexpr int E = G::PPT / C;
+        const u64 q_tile = P.q_begin + (u64)tile * G::L;
+        const bool geometric = P.tw_on && P.logB == 0 && ((1ull << P.logA) >= (u64)G::L);   // no wrap of q1 inside the tile
 #pragma unroll
-        for (int i = 0; i < G::PPT; ++i) {
-            const int idx = tid + i * G::NT;
-            const int k = idx & (G::N - 1), l = idx >> LOG2N;
-            const u64 q = P.q_begin + (u64)tile * G::L + (u64)l;
-            if (q < P.q_end) {
-                double2 y = sm[G::phys(l, k)];
-                if (P.tw_on) y = cmul(y, fourstep_tw(P, q, (unsigned)k));
-                double2 *dst = P.out + line_base(q, P.out_s0, P.out_s1, P.out_s2, P.logA, P.logB);
-                NRB_STS(dst + (i64)k * P.out_es, io_swap<DIR>(y));
+        for (int c = 0; c < C; ++c) {
+            const int idx0 = tid + c * G::NT;
+            const int k = idx0 & (G::N - 1), l0 = idx0 >> LOG2N;
+            double2 tw = make_double2(1.0, 0.0), tw_step = make_double2(1.0, 0.0);
+            if (geometric) {
+                tw = fourstep_tw_m(P, line_q1(P, q_tile + (u64)l0) * (unsigned)k);
+                tw_step = fourstep_tw_m(P, (unsigned)(D * k));
+            }
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int l = l0 + e * D;
+                const u64 q = q_tile + (u64)l;
+                if (q < P.q_end) {
+                    double2 y = sm[G::phys(l, k)];
+                    if (geometric) y = cmul(y, tw);
+                    else if (P.tw_on) y = cmul(y, fourstep_tw(P, q, (unsigned)k));
+                    double2 *dst = P.out + line_base(q, P.out_s0, P.out_s1, P.out_s2, P.logA, P.logB);
+                    NRB_STS(dst + (i64)k * P.out_es, io_swap<DIR>(y));
+                }
+                tw = cmul(tw, tw_step);
             }
         }
         return;

@@ -147,7 +147,9 @@ NRB_HD constexpr int row_line_pitch(int log2n) { return (1 << log2n) + ((1 << lo
 NRB_HD constexpr int col_line_count(int log2n) { return (1 << tile_log2(log2n)) >> log2n; }
 NRB_HD constexpr int col_pitch(int log2n, int variant)
 {
-    return col_line_count(log2n) + ((variant == VAR_XPOSE && col_line_count(log2n) > 1) ? 1 : 0);
+    // XPOSE reads the tile back line-contiguously: pitch L+1 keeps that conflict-free for L >= 8;
+    // for L = 2, 4 an XOR swizzle is used instead (Geo::phys), no padding
+    return col_line_count(log2n) + ((variant == VAR_XPOSE && col_line_count(log2n) >= 8) ? 1 : 0);
 }
 NRB_HD constexpr size_t smem_elems(int log2n, int layout, int variant)
 {
@@ -193,7 +195,8 @@ enum AuxKind {
     AUX_SPECTRAL = 1,     // convlv multiply / divide, correl conj-multiply on packed spectra
     AUX_PAD_RESPONSE = 2, // Convolve.rs:41-63 response placement
     AUX_CORREL_DIRECT = 3,// Correlation.rs:37-50, n <= 32
-    AUX_FILL = 4          // synthetic input generator: n doubles, seed in m, offset in count
+    AUX_FILL = 4,         // synthetic input generator: n doubles, seed in m, offset in count
+    AUX_SPECTRAL_Z = 5    // untangle + spectral op + inverse untangle in one pass on raw c2c outputs
 };
 enum SpectralOp { SPEC_CONV_MUL = 0, SPEC_CONV_DIV = 1, SPEC_CORREL = 2 };
 

@@ -368,6 +368,26 @@ void emit_real(Builder &B, BufRef src, BufRef dst, BufRef tmp, u64 l_begin, u64 
     }
 }
 
+// c2c part only of a long real transform (lines longer than a CTA tile): the untangling is left to
+// the fused spectral kernel (AUX_SPECTRAL_Z)
+bool real_needs_separate_untangle(int p) { return p > tunables().row_max_log2; }
+
+Step make_spectral_z(int op, BufRef a, BufRef b, BufRef out, u64 n, u64 count, i64 a_stride, i64 b_stride, i64 out_stride)
+{
+    Step st;
+    st.is_aux = true;
+    memset(&st.ap, 0, sizeof(st.ap));
+    st.ap.kind = AUX_SPECTRAL_Z;
+    st.ap.op = op;
+    st.ap.n = n;
+    st.ap.count = count;
+    st.ap.a_stride = a_stride; st.ap.b_stride = b_stride; st.ap.out_stride = out_stride;
+    const FourStepTable rt = fourstep_table(ilog2((size_t)n));   // exp(-2 pi i k / n) = exp(-i pi k / N)
+    st.ap.rtw_lo = rt.lo; st.ap.rtw_hi = rt.hi; st.ap.rtw_h = rt.h;
+    st.in = a; st.b = b; st.out = out;
+    return st;
+}
+
 Step make_spectral(int op, BufRef a, BufRef b, BufRef out, u64 n, u64 count, i64 a_stride, i64 b_stride,
                    i64 out_stride)
 {
@@ -482,10 +502,18 @@ int build_convlv(Plan &pl, Builder &B, int dir)
     for (u64 b0 = 0; b0 < pl.batch; b0 += gs) {
         const u64 b1 = (b0 + gs < pl.batch) ? b0 + gs : pl.batch;
         const BufRef in(BUF_IO, (i64)(b0 * N)), out(BUF_OUT, (i64)(b0 * N));
-        emit_real(B, in, out, T, 0, b1 - b0, p, +1, REAL_PACKED, BufRef());
-        B.prog->steps.push_back(make_spectral(dir > 0 ? SPEC_CONV_MUL : SPEC_CONV_DIV, out, R, out, n, b1 - b0,
-                                              (i64)N, 0, (i64)N));
-        emit_real(B, out, out, T, 0, b1 - b0, p, -1, REAL_PACKED, BufRef());
+        if (real_needs_separate_untangle(p)) {
+            // c2c -> [untangle + multiply + inverse untangle in one pass] -> inverse c2c
+            emit_axis(B, in, out, T, b1 - b0, 0, b1 - b0, p, 1, +1);
+            B.prog->steps.push_back(make_spectral_z(dir > 0 ? SPEC_CONV_MUL : SPEC_CONV_DIV, out, R, out, n, b1 - b0,
+                                                    (i64)N, 0, (i64)N));
+            emit_axis(B, out, out, T, b1 - b0, 0, b1 - b0, p, 1, -1);
+        } else {
+            emit_real(B, in, out, T, 0, b1 - b0, p, +1, REAL_PACKED, BufRef());
+            B.prog->steps.push_back(make_spectral(dir > 0 ? SPEC_CONV_MUL : SPEC_CONV_DIV, out, R, out, n, b1 - b0,
+                                                  (i64)N, 0, (i64)N));
+            emit_real(B, out, out, T, 0, b1 - b0, p, -1, REAL_PACKED, BufRef());
+        }
     }
     return B.rc;
 }
@@ -515,10 +543,17 @@ int build_correl(Plan &pl, Builder &B)
     for (u64 b0 = 0; b0 < pl.batch; b0 += gs) {
         const u64 b1 = (b0 + gs < pl.batch) ? b0 + gs : pl.batch;
         const BufRef a(BUF_IO, (i64)(b0 * N)), b(BUF_AUX, (i64)(b0 * N)), out(BUF_OUT, (i64)(b0 * N));
-        emit_real(B, a, out, T, 0, b1 - b0, p, +1, REAL_PACKED, BufRef());
-        emit_real(B, b, F2, T, 0, b1 - b0, p, +1, REAL_PACKED, BufRef());
-        B.prog->steps.push_back(make_spectral(SPEC_CORREL, out, F2, out, n, b1 - b0, (i64)N, (i64)N, (i64)N));
-        emit_real(B, out, out, T, 0, b1 - b0, p, -1, REAL_PACKED, BufRef());
+        if (real_needs_separate_untangle(p)) {
+            emit_axis(B, a, out, T, b1 - b0, 0, b1 - b0, p, 1, +1);
+            emit_axis(B, b, F2, T, b1 - b0, 0, b1 - b0, p, 1, +1);
+            B.prog->steps.push_back(make_spectral_z(SPEC_CORREL, out, F2, out, n, b1 - b0, (i64)N, (i64)N, (i64)N));
+            emit_axis(B, out, out, T, b1 - b0, 0, b1 - b0, p, 1, -1);
+        } else {
+            emit_real(B, a, out, T, 0, b1 - b0, p, +1, REAL_PACKED, BufRef());
+            emit_real(B, b, F2, T, 0, b1 - b0, p, +1, REAL_PACKED, BufRef());
+            B.prog->steps.push_back(make_spectral(SPEC_CORREL, out, F2, out, n, b1 - b0, (i64)N, (i64)N, (i64)N));
+            emit_real(B, out, out, T, 0, b1 - b0, p, -1, REAL_PACKED, BufRef());
+        }
     }
     return B.rc;
 }
@@ -656,12 +691,13 @@ int describe_launch(const Plan &pl, int isign, int idx, char *name, size_t cap, 
     char buf[128];
     double b = 0.0;
     if (st.is_aux) {
-        static const char *names[] = {"untangle", "spectral", "pad_response", "correl_direct", "fill"};
+        static const char *names[] = {"untangle", "spectral", "pad_response", "correl_direct", "fill", "spectral_z"};
         snprintf(buf, sizeof(buf), "aux_%s", names[st.ap.kind]);
         switch (st.ap.kind) {
         case AUX_UNTANGLE: b = 2.0 * 16.0 * (double)st.ap.count * (double)st.ap.n; break;
         case AUX_SPECTRAL: b = (double)st.ap.count * (double)st.ap.n * 8.0 * (st.ap.b_stride ? 3.0 : 2.0) + (st.ap.b_stride ? 0.0 : 8.0 * (double)st.ap.n); break;
         case AUX_PAD_RESPONSE: b = 8.0 * ((double)st.ap.n + (double)st.ap.m); break;
+        case AUX_SPECTRAL_Z: b = (double)st.ap.count * (double)st.ap.n * 8.0 * (st.ap.b_stride ? 3.0 : 2.0) + (st.ap.b_stride ? 0.0 : 8.0 * (double)st.ap.n); break;
         default: b = 3.0 * 8.0 * (double)st.ap.count * (double)st.ap.n; break;
         }
     } else {

@@ -138,6 +138,22 @@ def test_convlv(emu, n, m):
     cases.check_convlv(emu, n, m)
 
 
+@pytest.mark.parametrize("n,m", [(16, 3), (64, 5), (1024, 33), (4096, 100)])
+def test_convlv_correl_fused_spectral_path(emu, n, m):
+    """Long-line path: c2c passes + one fused untangle/multiply/untangle kernel (AUX_SPECTRAL_Z)."""
+    emu.set_option("row_max_log2", 2)
+    emu.set_option("col_max_log2", 3)
+    cases.check_convlv(emu, n, m)
+    if n > 32:
+        cases.check_correl(emu, n)
+
+
+@pytest.mark.parametrize("nn", [1 << 18, 1 << 20])
+def test_four1_four_step_small_line_counts(emu, nn):
+    """XPOSE tiles with 8 and 4 lines (XOR-swizzled shared memory for L < 8)."""
+    cases.check_four1(emu, nn)
+
+
 def test_convlv_reference_known_answers(emu):
     ka = KNOWN["convlv_basic"]
     y = nb.convlv(ka["data"], ka["respns"], ka["isign"], _L=emu)
