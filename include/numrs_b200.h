@@ -60,6 +60,9 @@ int  nrb_shutdown(void);               /* frees cached plans / scratch of all th
  *   "row_max_log2"   longest contiguous FFT done in one pass            (default 13)
  *   "l2_group_bytes"    rlft3: bytes of x-planes per z/y launch pair    (default: whole volume)
  *   "batch_group_bytes" convlv/correl: bytes of signals per launch group (default 512 MiB)
+ *   "fuse_zy"           rlft3: run the z and y passes of every x-plane in one persistent launch so the
+ *                       y pass reads the z pass's output from L2 (default 0: measured 3-6 % slower on B200); "fuse_lag" = planes the y
+ *                       tiles trail behind the z tiles (default 16)
  * Environment overrides at load time: NRB_COL_MAX_LOG2, NRB_ROW_MAX_LOG2, NRB_L2_GROUP_MB,
  * NRB_BATCH_GROUP_MB. */
 int  nrb_set_option(const char *name, long value);

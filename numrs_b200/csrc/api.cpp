@@ -237,6 +237,7 @@ int nrb_plan_destroy(nrb_plan_t plan)
 {
     if (!plan) return NRB_OK;
     if (plan->plan.ws) be_free(plan->plan.ws);
+    if (plan->plan.sched) be_free(plan->plan.sched);
     delete plan;
     return NRB_OK;
 }

@@ -1,5 +1,6 @@
 // backend_cuda.cu -- CUDA backend of the planner: kernel dispatch table, the elementwise
 // kernel, memory and stream helpers.  There is deliberately no other backend in the product.
+#include <map>
 #include <mutex>
 #include <string>
 
@@ -26,6 +27,25 @@ PassTable &pass_table()
     return t;
 }
 
+void register_fused_a();
+void register_fused_b();
+void register_fused_c();
+static std::map<unsigned long long, FusedLaunchFn> &fused_table()
+{
+    static std::map<unsigned long long, FusedLaunchFn> t;
+    return t;
+}
+void register_fused(unsigned long long key, FusedLaunchFn fn) { fused_table()[key] = fn; }
+static void init_fused()
+{
+    static std::once_flag once;
+    std::call_once(once, [] { register_fused_a(); register_fused_b(); register_fused_c(); });
+}
+static unsigned long long key_of(const KernelKey &a, const KernelKey &b)
+{
+    return fused_key(a.log2n, a.layout, a.variant, b.log2n, b.layout, b.variant, a.dir);
+}
+
 static thread_local std::string g_be_err;
 static int fail(cudaError_t e)
 {
@@ -44,6 +64,23 @@ int be_launch_pass(const KernelKey &key, const PassParams &p, u64 ntiles, void *
     if (!fn) { g_be_err = "kernel variant not built"; return -1; }
     if (ntiles > 0x7fffffffull) { g_be_err = "grid too large"; return -1; }
     const int rc = fn(p, ntiles, (cudaStream_t)stream);
+    if (rc != 0) return fail((cudaError_t)rc);
+    return 0;
+}
+
+bool be_fused_available(const KernelKey &a, const KernelKey &b)
+{
+    init_fused();
+    return a.dir == b.dir && fused_table().count(key_of(a, b)) != 0;
+}
+
+int be_launch_fused(const KernelKey &ka, const PassParams &pa, const KernelKey &kb, const PassParams &pb, const FuseSched &fs,
+                    void *stream)
+{
+    init_fused();
+    auto it = fused_table().find(key_of(ka, kb));
+    if (it == fused_table().end()) { g_be_err = "fused kernel pair not built"; return -1; }
+    const int rc = it->second(pa, pb, fs, (cudaStream_t)stream);
     if (rc != 0) return fail((cudaError_t)rc);
     return 0;
 }

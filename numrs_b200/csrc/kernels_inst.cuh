@@ -66,6 +66,105 @@ int launch_pass_t(const PassParams &p, u64 ntiles, cudaStream_t s)
     return (int)cudaGetLastError();
 }
 
+// ---- two dependent passes in one persistent launch (see FuseSched in nrb_common.h) ----
+typedef int (*FusedLaunchFn)(const PassParams &, const PassParams &, const FuseSched &, cudaStream_t);
+NRB_HD constexpr unsigned long long fused_key(int la, int lya, int va, int lb, int lyb, int vb, int dir)
+{
+    return ((unsigned long long)la << 40) | ((unsigned long long)lya << 36) | ((unsigned long long)va << 32) |
+           ((unsigned long long)lb << 24) | ((unsigned long long)lyb << 20) | ((unsigned long long)vb << 16) | (dir > 0 ? 1ull : 0ull);
+}
+void register_fused(unsigned long long key, FusedLaunchFn fn);
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int LA, int LYA, int VA, int LB, int LYB, int VB, int DIR>
+__global__ void __launch_bounds__(cta_threads(LA, LYA), 2)
+fused_pass_kernel(const __grid_constant__ PassParams PA, const __grid_constant__ PassParams PB, const FuseSched F)
+{
+    static_assert(cta_threads(LA, LYA) == cta_threads(LB, LYB), "fused passes must use the same CTA size");
+    extern __shared__ double2 nrb_smem[];
+    __shared__ unsigned long long s_ticket;
+    const int tid = (int)threadIdx.x;
+    const unsigned long long per = (unsigned long long)F.ta + F.tb;
+    const unsigned long long head = (unsigned long long)F.lag * F.ta;                    // A-only tickets
+    const unsigned long long mid = (unsigned long long)(F.units - F.lag) * per;          // interleaved
+    const unsigned long long total = (unsigned long long)F.units * per;
+    for (;;) {
+        if (tid == 0) s_ticket = atomicAdd(F.ticket, 1ull);
+        __syncthreads();
+        const unsigned long long t = s_ticket;
+        __syncthreads();
+        if (t >= total) break;
+        bool is_a;
+        unsigned unit, r;
+        if (t < head) { is_a = true; unit = (unsigned)(t / F.ta); r = (unsigned)(t % F.ta); }
+        else if (t < head + mid) {
+            const unsigned long long u = t - head;
+            const unsigned i = F.lag + (unsigned)(u / per);
+            const unsigned rr = (unsigned)(u % per);
+            if (rr < F.ta) { is_a = true; unit = i; r = rr; }
+            else { is_a = false; unit = i - F.lag; r = rr - F.ta; }
+        } else {
+            const unsigned long long u = t - head - mid;
+            is_a = false; unit = F.units - F.lag + (unsigned)(u / F.tb); r = (unsigned)(u % F.tb);
+        }
+        if (is_a) {
+            fft_pass_body<LA, LYA, DIR, VA>(PA, nrb_smem, unit * F.ta + r, tid);
+            __threadfence();                      // this thread's stores are visible device-wide ...
+            __syncthreads();                      // ... for every thread of the CTA ...
+            if (tid == 0) atomicAdd(&F.done[unit], 1u);   // ... before the tile is published
+        } else {
+            if (tid == 0) {
+                while (ld_acquire_u32(&F.done[unit]) < F.ta) __nanosleep(64);
+            }
+            __syncthreads();
+            fft_pass_body<LB, LYB, DIR, VB>(PB, nrb_smem, unit * F.tb + r, tid);
+        }
+    }
+}
+
+template <int LA, int LYA, int VA, int LB, int LYB, int VB, int DIR>
+int launch_fused_t(const PassParams &pa, const PassParams &pb, const FuseSched &fs, cudaStream_t s)
+{
+    constexpr size_t sa = smem_elems(LA, LYA, VA) * sizeof(double2), sb = smem_elems(LB, LYB, VB) * sizeof(double2);
+    constexpr size_t smem = sa > sb ? sa : sb;
+    constexpr int NT = cta_threads(LA, LYA);
+    auto kern = fused_pass_kernel<LA, LYA, VA, LB, LYB, VB, DIR>;
+    static int resident[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!resident[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        int per_sm = 0, sms = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
+        if (e != cudaSuccess) return (int)e;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        resident[dev & 63] = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
+    }
+    cudaError_t e = cudaMemsetAsync(fs.ticket, 0, 16 + 4 * (size_t)((fs.units + 3) & ~3u), s);   // ticket + done[] are contiguous
+    if (e != cudaSuccess) return (int)e;
+    unsigned long long total = (unsigned long long)fs.units * ((unsigned long long)fs.ta + fs.tb);
+    unsigned grid = (unsigned)(total < (unsigned long long)resident[dev & 63] ? total : (unsigned long long)resident[dev & 63]);
+    if (grid == 0) return 0;
+    kern<<<grid, NT, smem, s>>>(pa, pb, fs);
+    return (int)cudaGetLastError();
+}
+
+// rlft3: z real pass (ROW REAL, 2^LZ) + y pass (COL PLAIN, 2^LY); forward = z then y, inverse = y then z
+template <int LZ, int LY> void register_fused_zy()
+{
+    register_fused(fused_key(LZ, LAYOUT_ROW, VAR_REAL, LY, LAYOUT_COL, VAR_PLAIN, +1),
+                   launch_fused_t<LZ, LAYOUT_ROW, VAR_REAL, LY, LAYOUT_COL, VAR_PLAIN, +1>);
+    register_fused(fused_key(LY, LAYOUT_COL, VAR_PLAIN, LZ, LAYOUT_ROW, VAR_REAL, -1),
+                   launch_fused_t<LY, LAYOUT_COL, VAR_PLAIN, LZ, LAYOUT_ROW, VAR_REAL, -1>);
+}
+
 template <int LOG2N, int LAYOUT> void register_size(PassTable &t)
 {
     if constexpr (LAYOUT == LAYOUT_ROW) {

@@ -189,6 +189,19 @@ struct PassParams {
     int real_mode;
 };
 
+// ---- two dependent passes fused into one persistent launch (rlft3 z + y through L2) ----
+// Work is cut into `units` (x-planes).  Pass A's tiles of unit u must all finish before any tile
+// of pass B on unit u starts.  CTAs pull tickets in order; the ticket sequence is
+//   A(0) .. A(lag-1), then A(i) B(i-lag) for i = lag .. units-1, then B(units-lag) .. B(units-1)
+// so B runs `lag` units behind A: its inputs were produced recently (still in L2) and long enough
+// ago that the wait is normally already satisfied.  Earlier tickets never wait on later ones, so
+// the scheme cannot deadlock whatever the number of resident CTAs.
+struct FuseSched {
+    unsigned long long *ticket;   // zeroed before every launch
+    unsigned *done;               // [units] completed pass-A tiles, zeroed before every launch
+    unsigned units, ta, tb, lag;  // ta / tb = tiles of pass A / B per unit
+};
+
 // ---- elementwise kernels ----
 enum AuxKind {
     AUX_UNTANGLE = 0,     // standalone real untangle (large lines / N == 1)

@@ -46,6 +46,8 @@ static Tunables &tunables_mut()
         x.row_max_log2 = env_int("NRB_ROW_MAX_LOG2", 13);
         x.l2_group_bytes = (u64)env_int("NRB_L2_GROUP_MB", 1 << 20) << 20;
         x.batch_group_bytes = (u64)env_int("NRB_BATCH_GROUP_MB", 512) << 20;
+        x.fuse_zy = env_int("NRB_FUSE_ZY", 0);
+        x.fuse_lag = env_int("NRB_FUSE_LAG", 16);
         return x;
     }();
     if (t.col_max_log2 < 1) t.col_max_log2 = 1;
@@ -54,6 +56,7 @@ static Tunables &tunables_mut()
     if (t.row_max_log2 > kMaxLog2N) t.row_max_log2 = kMaxLog2N;
     if (t.l2_group_bytes < 1024) t.l2_group_bytes = 1024;
     if (t.batch_group_bytes < 1024) t.batch_group_bytes = 1024;
+    if (t.fuse_lag < 1) t.fuse_lag = 1;
     return t;
 }
 const Tunables &tunables() { return tunables_mut(); }
@@ -66,6 +69,8 @@ int set_tunable(const char *name, long value)
     else if (n == "row_max_log2") t.row_max_log2 = (int)value;
     else if (n == "l2_group_bytes") t.l2_group_bytes = (u64)value;
     else if (n == "batch_group_bytes") t.batch_group_bytes = (u64)value;
+    else if (n == "fuse_zy") t.fuse_zy = (int)value;
+    else if (n == "fuse_lag") t.fuse_lag = (int)value;
     else return -1;
     tunables_mut();   // re-clamp
     return 0;
@@ -187,8 +192,9 @@ struct AxisMap {        // custom addressing for one side of a single-pass axis
 struct Builder {
     Program *prog;
     size_t ws_used;     // workspace high-water mark (complex elements)
+    size_t sched_used;  // fused-launch counter scratch (bytes)
     int rc;
-    explicit Builder(Program *p) : prog(p), ws_used(0), rc(NRB_OK) {}
+    explicit Builder(Program *p) : prog(p), ws_used(0), sched_used(0), rc(NRB_OK) {}
     void need_ws(size_t end) { if (end > ws_used) ws_used = end; }
 };
 
@@ -452,11 +458,44 @@ int build_rlft3(Plan &pl, Builder &B, int dir)
     if (g < 1) g = 1;
     if (g > nn1) g = nn1;
     if (nn1 * plane_bytes <= 2 * tunables().l2_group_bytes) g = nn1;
+    // Fused z+y: one persistent launch runs the z pass and the y pass of every x-plane with the
+    // y tiles trailing `lag` planes behind, so the y pass reads the z pass's output from L2.
+    const bool fusable = tunables().fuse_zy && g == nn1 && nn1 >= 2 && p3 >= 1 && p3 <= tunables().row_max_log2 &&
+                         p2 >= 1 && p2 <= tunables().col_max_log2 && N3 >= (u64)col_line_count(p2) &&
+                         nn2 >= (u64)col_line_count(p3);
+    auto emit_fused = [&](int d) -> bool {
+        const KernelKey kz{p3, LAYOUT_ROW, d, VAR_REAL}, ky{p2, LAYOUT_COL, d, VAR_PLAIN};
+        if (!fusable || !be_fused_available(d > 0 ? kz : ky, d > 0 ? ky : kz)) return false;
+        Program tmp;
+        Builder TB(&tmp);
+        emit_real(TB, D, D, W, 0, nn1 * nn2, p3, d, REAL_SPEQ, S);
+        emit_axis(TB, D, D, W, nn1, 0, nn1, p2, N3, d);
+        if (tmp.steps.size() != 2 || TB.rc != NRB_OK) return false;
+        const Step &z = tmp.steps[0], &y = tmp.steps[1];
+        const Step &a = d > 0 ? z : y, &b = d > 0 ? y : z;
+        Step st = a;
+        st.is_fused = true;
+        st.key2 = b.key; st.pp2 = b.pp; st.in2 = b.in; st.out2 = b.out; st.speq2 = b.speq;
+        const u64 tz = nn2 / (u64)col_line_count(p3), ty = N3 / (u64)col_line_count(p2);
+        st.fs.units = (unsigned)nn1;
+        st.fs.ta = (unsigned)(d > 0 ? tz : ty);
+        st.fs.tb = (unsigned)(d > 0 ? ty : tz);
+        u64 lag = (u64)tunables().fuse_lag;
+        if (lag > nn1) lag = nn1;
+        st.fs.lag = (unsigned)lag;
+        st.sched_off = B.sched_used;
+        B.sched_used += 16 + 4 * ((nn1 + 3) & ~(u64)3);
+        st.ntiles = nn1 * (tz + ty);
+        B.prog->steps.push_back(st);
+        return true;
+    };
     if (dir > 0) {
-        for (u64 x0 = 0; x0 < nn1; x0 += g) {
-            const u64 x1 = (x0 + g < nn1) ? x0 + g : nn1;
-            emit_real(B, D, D, W, x0 * nn2, x1 * nn2, p3, +1, REAL_SPEQ, S);
-            emit_axis(B, D, D, W, nn1, x0, x1, p2, N3, +1);
+        if (!emit_fused(+1)) {
+            for (u64 x0 = 0; x0 < nn1; x0 += g) {
+                const u64 x1 = (x0 + g < nn1) ? x0 + g : nn1;
+                emit_real(B, D, D, W, x0 * nn2, x1 * nn2, p3, +1, REAL_SPEQ, S);
+                emit_axis(B, D, D, W, nn1, x0, x1, p2, N3, +1);
+            }
         }
         emit_axis(B, S, S, W, nn1, 0, nn1, p2, 1, +1);
         emit_axis(B, D, D, W, 1, 0, 1, p1, nn2 * N3, +1);
@@ -465,10 +504,12 @@ int build_rlft3(Plan &pl, Builder &B, int dir)
         emit_axis(B, S, S, W, 1, 0, 1, p1, nn2, -1);
         emit_axis(B, D, D, W, 1, 0, 1, p1, nn2 * N3, -1);
         emit_axis(B, S, S, W, nn1, 0, nn1, p2, 1, -1);
-        for (u64 x0 = 0; x0 < nn1; x0 += g) {
-            const u64 x1 = (x0 + g < nn1) ? x0 + g : nn1;
-            emit_axis(B, D, D, W, nn1, x0, x1, p2, N3, -1);
-            emit_real(B, D, D, W, x0 * nn2, x1 * nn2, p3, -1, REAL_SPEQ, S);
+        if (!emit_fused(-1)) {
+            for (u64 x0 = 0; x0 < nn1; x0 += g) {
+                const u64 x1 = (x0 + g < nn1) ? x0 + g : nn1;
+                emit_axis(B, D, D, W, nn1, x0, x1, p2, N3, -1);
+                emit_real(B, D, D, W, x0 * nn2, x1 * nn2, p3, -1, REAL_SPEQ, S);
+            }
         }
     }
     return B.rc;
@@ -602,6 +643,7 @@ int build_plan(Plan &pl, int kind, const size_t *dims, size_t ndim, size_t batch
         return NRB_ERR_INVALID_DIMS;
     }
     size_t ws = 0;
+    pl.sched_bytes = 0;
     for (int s = 0; s < 2; ++s) {
         const int dir = s == 0 ? +1 : -1;
         Builder B(&pl.prog[s]);
@@ -618,6 +660,7 @@ int build_plan(Plan &pl, int kind, const size_t *dims, size_t ndim, size_t batch
             if (!st.is_aux && (!st.pp.tw && radix_plan(st.key.log2n).nst > 1)) { set_error(be_last_error()); return NRB_ERR_CUDA; }
         }
         if (B.ws_used > ws) ws = B.ws_used;
+        if (B.sched_used > pl.sched_bytes) pl.sched_bytes = B.sched_used;
     }
     pl.ws_elems = ws;
     pl.ws = nullptr;
@@ -625,18 +668,30 @@ int build_plan(Plan &pl, int kind, const size_t *dims, size_t ndim, size_t batch
         const int mrc = be_malloc(&pl.ws, ws * sizeof(double2));
         if (mrc != 0) { set_error(std::string("workspace allocation failed: ") + be_last_error()); return NRB_ERR_OOM; }
     }
+    pl.sched = nullptr;
+    if (pl.sched_bytes && be_malloc(&pl.sched, pl.sched_bytes) != 0) { set_error("scheduler scratch allocation failed"); return NRB_ERR_OOM; }
     return NRB_OK;
 }
 
 struct PeerExchange { double2 *const *peers; i64 off; };
 
 static int run_program(Program &prog, double2 *const base[4], int arg, void *stream, std::vector<void *> *events = nullptr,
-                       const PeerExchange *px = nullptr)
+                       const PeerExchange *px = nullptr, void *sched = nullptr)
 {
     if (events) events->push_back(be_event_record(stream));
     for (Step &st : prog.steps) {
         int rc;
-        if (st.is_aux) {
+        if (st.is_fused) {
+            PassParams pa = st.pp, pb = st.pp2;
+            pa.in = base[st.in.id] + st.in.off; pa.out = base[st.out.id] + st.out.off;
+            pa.speq = st.speq.id == BUF_NONE ? nullptr : base[st.speq.id] + st.speq.off;
+            pb.in = base[st.in2.id] + st.in2.off; pb.out = base[st.out2.id] + st.out2.off;
+            pb.speq = st.speq2.id == BUF_NONE ? nullptr : base[st.speq2.id] + st.speq2.off;
+            FuseSched fs = st.fs;
+            fs.ticket = (unsigned long long *)((char *)sched + st.sched_off);
+            fs.done = (unsigned *)((char *)sched + st.sched_off + 16);
+            rc = be_launch_fused(st.key, pa, st.key2, pb, fs, stream);
+        } else if (st.is_aux) {
             AuxParams ap = st.ap;
             ap.a = st.in.id == BUF_NONE ? nullptr : base[st.in.id] + st.in.off;
             ap.b = st.b.id == BUF_NONE ? nullptr : base[st.b.id] + st.b.off;
@@ -666,7 +721,7 @@ int exec_plan(Plan &pl, double *d_io, double *d_aux, double *d_out, int isign, i
 {
     if (isign != 1 && isign != -1) { set_error("isign must be 1 or -1"); return NRB_ERR_INVALID_ISIGN; }
     double2 *const base[4] = {(double2 *)d_io, (double2 *)d_aux, (double2 *)d_out, (double2 *)pl.ws};
-    return run_program(pl.prog[isign == 1 ? 0 : 1], base, arg, stream);
+    return run_program(pl.prog[isign == 1 ? 0 : 1], base, arg, stream, nullptr, nullptr, pl.sched);
 }
 
 int profile_plan(Plan &pl, double *d_io, double *d_aux, double *d_out, int isign, int arg, void *stream, float *ms,
@@ -675,7 +730,7 @@ int profile_plan(Plan &pl, double *d_io, double *d_aux, double *d_out, int isign
     if (isign != 1 && isign != -1) { set_error("isign must be 1 or -1"); return NRB_ERR_INVALID_ISIGN; }
     double2 *const base[4] = {(double2 *)d_io, (double2 *)d_aux, (double2 *)d_out, (double2 *)pl.ws};
     std::vector<void *> ev;
-    const int rc = run_program(pl.prog[isign == 1 ? 0 : 1], base, arg, stream, &ev);
+    const int rc = run_program(pl.prog[isign == 1 ? 0 : 1], base, arg, stream, &ev, nullptr, pl.sched);
     if (be_sync(stream) != 0 && rc == NRB_OK) { set_error(std::string("kernel execution failed: ") + be_last_error()); return NRB_ERR_CUDA; }
     for (size_t i = 0; i + 1 < ev.size(); ++i)
         if ((int)i < cap && ev[i] && ev[i + 1]) ms[i] = be_event_elapsed_ms(ev[i], ev[i + 1]);
@@ -690,7 +745,13 @@ int describe_launch(const Plan &pl, int isign, int idx, char *name, size_t cap, 
     const Step &st = prog.steps[(size_t)idx];
     char buf[128];
     double b = 0.0;
-    if (st.is_aux) {
+    if (st.is_fused) {
+        snprintf(buf, sizeof(buf), "fused_%s_n%d+%s_n%d_%s_U%u", st.key.layout == LAYOUT_ROW ? "row_real" : "col", 1 << st.key.log2n,
+                 st.key2.layout == LAYOUT_ROW ? "row_real" : "col", 1 << st.key2.log2n, st.key.dir > 0 ? "p" : "m", st.fs.units);
+        // the pair reads the volume once and writes it once (the intermediate stays in L2)
+        const double vol = (double)st.fs.units * (double)st.fs.ta * 4096.0;
+        b = 2.0 * 16.0 * vol + 16.0 * (double)(st.key.layout == LAYOUT_ROW ? st.pp.q_end - st.pp.q_begin : st.pp2.q_end - st.pp2.q_begin);
+    } else if (st.is_aux) {
         static const char *names[] = {"untangle", "spectral", "pad_response", "correl_direct", "fill", "spectral_z"};
         snprintf(buf, sizeof(buf), "aux_%s", names[st.ap.kind]);
         switch (st.ap.kind) {

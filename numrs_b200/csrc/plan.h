@@ -13,6 +13,11 @@ namespace nrb {
 struct KernelKey { int log2n, layout, dir, variant; };
 int be_launch_pass(const KernelKey &key, const PassParams &p, u64 ntiles, void *stream);
 int be_launch_aux(const AuxParams &a, void *stream);
+// two dependent passes in one persistent launch; be_fused_available tells the planner whether the
+// backend has that kernel pair built
+bool be_fused_available(const KernelKey &a, const KernelKey &b);
+int be_launch_fused(const KernelKey &ka, const PassParams &pa, const KernelKey &kb, const PassParams &pb, const FuseSched &fs,
+                    void *stream);
 int be_malloc(void **p, size_t bytes);
 int be_free(void *p);
 int be_ipc_export(void *dptr, unsigned char handle[64]);
@@ -56,7 +61,15 @@ struct Step {
     u64 ntiles;
     BufRef in, out, speq, b;
     bool patch_pad_mode;   // AUX_PAD_RESPONSE: op comes from exec's `arg`
-    Step() : is_aux(false), key{0, 0, 0, 0}, pp(), ap(), ntiles(0), patch_pad_mode(false) {}
+    // fused pair: (key, pp, in/out/speq) is pass A, the *2 members are pass B
+    bool is_fused;
+    KernelKey key2;
+    PassParams pp2;
+    BufRef in2, out2, speq2;
+    FuseSched fs;          // counters live in the plan's scheduler scratch (sched_off = element offset)
+    size_t sched_off;
+    Step() : is_aux(false), key{0, 0, 0, 0}, pp(), ap(), ntiles(0), patch_pad_mode(false), is_fused(false),
+             key2{0, 0, 0, 0}, pp2(), fs{nullptr, nullptr, 0, 0, 0, 0}, sched_off(0) {}
 };
 
 struct Program {
@@ -75,6 +88,8 @@ struct Tunables {
     int col_max_log2;      // longest strided-axis FFT done in one pass (NRB_COL_MAX_LOG2, default 10)
     int row_max_log2;      // longest contiguous FFT done in one pass   (NRB_ROW_MAX_LOG2, default 13)
     u64 l2_group_bytes;    // rlft3: bytes of x-planes handled per z/y launch pair (NRB_L2_GROUP_MB; default: whole volume)
+    int fuse_zy;           // rlft3: fuse the z and y passes of each x-plane through L2 (NRB_FUSE_ZY, default 0: measured slower)
+    int fuse_lag;          // planes pass B runs behind pass A (NRB_FUSE_LAG, default 16)
     u64 batch_group_bytes; // convlv/correl: bytes of signals handled per launch group (NRB_BATCH_GROUP_MB, default 512)
 };
 const Tunables &tunables();
@@ -87,8 +102,10 @@ struct Plan {
     Program prog[2];       // [0]: isign = +1, [1]: isign = -1
     size_t ws_elems;       // workspace size in complex elements
     void *ws;              // device workspace (owned)
+    void *sched;           // device scratch for fused-launch counters (owned)
+    size_t sched_bytes;
     int device;
-    Plan() : kind(0), batch(1), ws_elems(0), ws(nullptr), device(0) {}
+    Plan() : kind(0), batch(1), ws_elems(0), ws(nullptr), sched(nullptr), sched_bytes(0), device(0) {}
 };
 
 // builders; return NRB_* codes

@@ -42,3 +42,5 @@ def _reset_options(request):
             L.set_option("row_max_log2", 13)
             L.set_option("l2_group_bytes", 1 << 40)
             L.set_option("batch_group_bytes", 512 << 20)
+            L.set_option("fuse_zy", 0)
+            L.set_option("fuse_lag", 16)

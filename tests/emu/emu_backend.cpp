@@ -148,6 +148,23 @@ int be_launch_pass(const KernelKey &key, const PassParams &p, u64 ntiles, void *
     return 0;
 }
 
+bool be_fused_available(const KernelKey &a, const KernelKey &b)
+{
+    // same set as the CUDA build (k_fused_*.cu): z in {128,256,512} (ROW REAL), y in {256,512,1024} (COL PLAIN)
+    const KernelKey &z = a.layout == LAYOUT_ROW ? a : b, &y = a.layout == LAYOUT_ROW ? b : a;
+    const bool order_ok = (a.dir > 0) == (a.layout == LAYOUT_ROW);
+    return a.dir == b.dir && order_ok && z.layout == LAYOUT_ROW && z.variant == VAR_REAL && y.layout == LAYOUT_COL &&
+           y.variant == VAR_PLAIN && z.log2n >= 7 && z.log2n <= 9 && y.log2n >= 8 && y.log2n <= 10;
+}
+
+int be_launch_fused(const KernelKey &ka, const PassParams &pa, const KernelKey &kb, const PassParams &pb, const FuseSched &fs, void *st)
+{
+    // the dependency structure (all of A's tiles of a unit before B's) is trivially met by running A, then B
+    int rc = be_launch_pass(ka, pa, (u64)fs.units * fs.ta, st);
+    if (rc == 0) rc = be_launch_pass(kb, pb, (u64)fs.units * fs.tb, st);
+    return rc;
+}
+
 int be_launch_aux(const AuxParams &a, void *)
 {
     ++g_aux_launches;

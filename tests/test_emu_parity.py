@@ -122,6 +122,21 @@ def test_rlft3_grouped_and_multi_step(emu):
     cases.check_rlft3(emu, (16, 32, 32))
 
 
+@pytest.mark.parametrize("shp,lag", [((4, 256, 256), 16), ((6 - 2, 256, 512), 1), ((8, 512, 256), 3)])
+def test_rlft3_fused_zy_program(emu, shp, lag):
+    """Shapes that take the fused z+y launch (under emulation the pair runs back to back)."""
+    emu.set_option("fuse_zy", 1)
+    emu.set_option("fuse_lag", lag)
+    cases.check_rlft3(emu, shp)
+    plan = emu.plan_create(nb.KIND_RLFT3, list(shp))
+    assert plan.num_launches(1) == 4 and plan.num_launches(-1) == 4     # fused pair, speq y, x, speq x
+    plan.destroy()
+    emu.set_option("fuse_zy", 0)
+    plan = emu.plan_create(nb.KIND_RLFT3, list(shp))
+    assert plan.num_launches(1) == 5
+    plan.destroy()
+
+
 def test_rlft3_asserts(emu):
     d, s = np.zeros((4, 4, 4)), np.zeros((4, 8))
     with pytest.raises(AssertionError):

@@ -79,6 +79,18 @@ def test_rlft3(gpu, shp):
     cases.check_rlft3(gpu, shp)
 
 
+@pytest.mark.parametrize("shp,lag", [((32, 512, 256), 16), ((8, 1024, 1024), 2), ((64, 256, 256), 1), ((16, 256, 512), 64),
+                                     ((256, 256, 256), 16)])
+def test_rlft3_fused_zy_launch(gpu, shp, lag):
+    """z and y passes in one persistent launch with ticket-ordered dependencies (FuseSched)."""
+    gpu.set_option("fuse_zy", 1)
+    gpu.set_option("fuse_lag", lag)
+    cases.check_rlft3(gpu, shp)
+    plan = gpu.plan_create(nb.KIND_RLFT3, list(shp))
+    assert plan.num_launches(1) == 4
+    plan.destroy()
+
+
 def test_rlft3_grouped(gpu):
     gpu.set_option("l2_group_bytes", 1 << 20)      # 128^3: many x-plane groups
     cases.check_rlft3(gpu, (128, 128, 128))
@@ -264,3 +276,30 @@ def test_linearity_and_plan_api_device_resident(gpu):
     prof = plan.profile(a.data_ptr(), isign=-1, stream=st)
     assert len(prof) == plan.num_launches(-1) and all(ms > 0 for _, _, ms in prof)
     plan.destroy()
+
+
+def test_host_calls_are_thread_safe(gpu):
+    """Reference functions are re-entrant on disjoint data and are called from rayon workers
+    (FFT_1.rs:186, Convolve.rs:246): concurrent host-slice calls must not interfere."""
+    import threading
+    errs = []
+
+    def worker(seed, nn):
+        try:
+            for rep in range(6):
+                x = O.fill_uniform(seed, rep * 2 * nn, 2 * nn)
+                ref = O.four1(x.copy(), nn, 1)
+                got = x.copy()
+                nb.four1(got, nn, 1)
+                assert cases.rel(got, ref) <= cases.tol(nn)
+                a = O.fill_uniform(seed + 50, rep * 4096, 4096)
+                assert cases.rel(nb.convlv(a, a[:9] / 64, 1), O.convlv(a, a[:9] / 64, 1)[1]) <= cases.tol(4096)
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+
+    ts = [threading.Thread(target=worker, args=(10 + i, 1 << (10 + 2 * i))) for i in range(5)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs

@@ -1,6 +1,6 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-W="rlft3_512 four1_12_4096 four1_20_64 fourn2d_8192 convlv_22_16 correl_22_16"
-timeout 300 python tools/kernel_table.py $W 2>&1 | grep -v Traceback
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+for lag in 4 8 16 32 64; do echo "### lag $lag"; NRB_FUSE_LAG=$lag timeout 120 python tools/kernel_table.py rlft3_512 2>&1 | grep -v Traceback; done
+echo "### unfused"; NRB_FUSE_ZY=0 timeout 120 python tools/kernel_table.py rlft3_512 2>&1 | grep -v Traceback
