@@ -18,9 +18,15 @@ using namespace nrb;
 struct nrb_plan_s {
     Plan plan;
     std::mutex mu;   // serialises exec of one plan (its workspace is shared)
+    ~nrb_plan_s()
+    {
+        if (plan.ws) be_free(plan.ws);
+        if (plan.sched) be_free(plan.sched);
+    }
 };
 struct nrb_slab_s {
     SlabPlan plan;
+    ~nrb_slab_s() { if (plan.ws) be_free(plan.ws); }
 };
 
 namespace {
@@ -83,10 +89,7 @@ std::shared_ptr<nrb_plan_s> cached_plan(int kind, const size_t *dims, size_t ndi
     std::shared_ptr<nrb_plan_s> h(new nrb_plan_s());
     *rc = build_plan(h->plan, kind, dims, ndim, batch);
     if (*rc != NRB_OK) return nullptr;
-    if (g_plan_cache.size() >= 64) {           // bounded cache: drop everything, rebuildable
-        for (auto &kv : g_plan_cache) if (kv.second.use_count() == 1 && kv.second->plan.ws) be_free(kv.second->plan.ws);
-        g_plan_cache.clear();
-    }
+    if (g_plan_cache.size() >= 64) g_plan_cache.clear();   // bounded; plans in use stay alive through their shared_ptr
     g_plan_cache[key] = h;
     return h;
 }
@@ -177,7 +180,6 @@ int nrb_set_device(int device)
 int nrb_shutdown(void)
 {
     std::lock_guard<std::mutex> lk(g_cache_mu);
-    for (auto &kv : g_plan_cache) if (kv.second->plan.ws) { be_free(kv.second->plan.ws); kv.second->plan.ws = nullptr; }
     g_plan_cache.clear();
     t_ctx.io.release(); t_ctx.aux.release(); t_ctx.out.release();
     if (t_ctx.stream) { be_stream_destroy(t_ctx.stream); t_ctx.stream = nullptr; }
@@ -188,7 +190,6 @@ int nrb_set_option(const char *name, long value)
 {
     if (set_tunable(name, value) != 0) return fail(NRB_ERR_INVALID_DIMS, "unknown option");
     std::lock_guard<std::mutex> lk(g_cache_mu);
-    for (auto &kv : g_plan_cache) if (kv.second->plan.ws) { be_free(kv.second->plan.ws); kv.second->plan.ws = nullptr; }
     g_plan_cache.clear();
     return NRB_OK;
 }
@@ -235,9 +236,6 @@ int nrb_fill_uniform_device(double *d_out, unsigned long long seed, unsigned lon
 }
 int nrb_plan_destroy(nrb_plan_t plan)
 {
-    if (!plan) return NRB_OK;
-    if (plan->plan.ws) be_free(plan->plan.ws);
-    if (plan->plan.sched) be_free(plan->plan.sched);
     delete plan;
     return NRB_OK;
 }
@@ -298,8 +296,6 @@ int nrb_ipc_release(void *dptr)
 }
 int nrb_slab_destroy(nrb_slab_t p)
 {
-    if (!p) return NRB_OK;
-    if (p->plan.ws) be_free(p->plan.ws);
     delete p;
     return NRB_OK;
 }
