@@ -28,6 +28,10 @@
 #pragma once
 #include "nrb_common.h"
 
+#ifndef NRB_REAL_INV_DIRECT
+#define NRB_REAL_INV_DIRECT 0
+#endif
+
 namespace nrb {
 
 // ------------------------------------------------------------------ complex helpers
@@ -181,6 +185,28 @@ NRB_DEV unsigned line_q1(const PassParams &P, u64 q)
     return (unsigned)((q >> P.logB) & ((1ull << P.logA) - 1ull));
 }
 
+// One bin of NR's realft untangling: out_k from (Z_k, Z_{N-k}) and t = exp(-i pi k / N), valid for every
+// 1 <= k <= N-1 (the pair form `untangle_pair` produces out_k and out_{N-k} together; this form lets each
+// thread finish the bins it already holds in registers).
+template <int DIR>
+NRB_DEV double2 untangle_bin(double2 a, double2 b, double2 t)
+{
+    const double2 w = DIR > 0 ? make_double2(t.x, -t.y) : t;
+    const double c2 = DIR > 0 ? -0.5 : 0.5;
+    const double h1r = 0.5 * (a.x + b.x), h1i = 0.5 * (a.y - b.y);
+    const double h2r = -c2 * (a.y + b.y), h2i = c2 * (a.x - b.x);
+    return make_double2(h1r + w.x * h2r - w.y * h2i, h1i + w.x * h2i + w.y * h2r);
+}
+NRB_DEV double2 dc_inverse_speq(double2 g0, double2 gn);
+
+// forward REAL passes whose last stage has one butterfly per thread and at most 32 butterflies per line
+// untangle in registers: the partner bins N-k live in lane (NB - j) of the same warp (warp shuffles)
+template <int LOG2N, int LAYOUT> NRB_HD constexpr bool real_fwd_in_registers()
+{
+    return LAYOUT == LAYOUT_ROW && radix_plan(LOG2N).r[radix_plan(LOG2N).nst - 1] == points_per_thread(LAYOUT, LOG2N) &&
+           ((1 << LOG2N) / radix_plan(LOG2N).r[radix_plan(LOG2N).nst - 1]) <= 32;
+}
+
 // ------------------------------------------------------------------ one Stockham stage
 // SRC_G: inputs come from global memory (else shared); DST_G: outputs go to global memory.
 template <int LOG2N, int LAYOUT, int DIR, int VARIANT, int S, bool SRC_G, bool DST_G>
@@ -210,11 +236,47 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
             const u64 q = P.q_begin + (u64)tile * G::L + (u64)ln[i];
             const bool ok = q < P.q_end;
             const double2 *src = P.in + line_base(q, P.in_s0, P.in_s1, P.in_s2, P.logA, P.logB);
+            if (VARIANT == VAR_REAL && DIR < 0 && NRB_REAL_INV_DIRECT) {
+                // (measured 10 % slower than the shared-memory pre-pass on B200, kept for reference, off)
+                // inverse real transform: the untangling (Real_FT.rs:145-176) is applied on the way in.
+                // Bin k needs F_k and F_{N-k}: both are read straight from global memory (the partner read
+                // hits L2 -- the same CTA reads it as its own element), so no shared-memory round trip.
+                // (own loads first, then the partner loads in groups of at most 4 to bound register use)
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                double2 x = make_double2(0.0, 0.0);
-                if (ok) x = NRB_LDS(src + elem_off(jj[i] + r * NB, P.in_es, P.in_eshift, P.in_es_hi));
-                v[i][r] = io_swap<DIR>(x);
+                for (int r = 0; r < R; ++r) {
+                    v[i][r] = make_double2(0.0, 0.0);
+                    if (ok) v[i][r] = NRB_LDS(src + (i64)(jj[i] + r * NB) * P.in_es);
+                }
+                constexpr int CH = R < 4 ? R : 4;
+#pragma unroll
+                for (int r0 = 0; r0 < R; r0 += CH) {
+                    double2 pb[CH];
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) {
+                        const int k = jj[i] + (r0 + c) * NB;
+                        pb[c] = make_double2(0.0, 0.0);
+                        if (ok && k != 0) pb[c] = NRB_LDS(src + (i64)(G::N - k) * P.in_es);
+                    }
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) {
+                        const int r = r0 + c;
+                        const int k = jj[i] + r * NB;
+                        if (k == 0) {
+                            const double2 g0 = v[i][r];
+                            if (P.real_mode == REAL_SPEQ) v[i][r] = ok ? dc_inverse_speq(g0, P.speq[q]) : g0;
+                            else v[i][r] = make_double2(0.5 * (g0.x + g0.y), 0.5 * (g0.x - g0.y));
+                        } else {
+                            v[i][r] = untangle_bin<-1>(v[i][r], pb[c], NRB_LDG(P.rtw + k));
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    double2 x = make_double2(0.0, 0.0);
+                    if (ok) x = NRB_LDS(src + elem_off(jj[i] + r * NB, P.in_es, P.in_eshift, P.in_es_hi));
+                    v[i][r] = io_swap<DIR>(x);
+                }
             }
         } else {
 #pragma unroll
@@ -243,7 +305,35 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
     for (int i = 0; i < BPT; ++i) {
         const int jm = jj[i] & (NS - 1);
         const int kb = (jj[i] - jm) * R + jm;
-        if (DST_G) {
+        if (DST_G && VARIANT == VAR_REAL && DIR > 0) {
+            // forward real transform, untangling in registers (see real_fwd_in_registers): this thread holds
+            // Z_k for k = j + r*NB; Z_{N-k} is register R-1-r of lane NB-j (for j = 0: own register R-r).
+            const u64 q = P.q_begin + (u64)tile * G::L + (u64)ln[i];
+            const bool ok = q < P.q_end;
+            const int j = jj[i];
+            const int lane = tid & 31;
+            const int partner = (lane & ~(NB - 1)) | ((NB - j) & (NB - 1));
+            double2 *dst = P.out + line_base(q, P.out_s0, P.out_s1, P.out_s2, P.logA, P.logB);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                // value this lane publishes under index R-1-r; the warp runs in lockstep, so each bin is
+                // exchanged, untangled and stored before the next one (keeps register use at one butterfly)
+                const double2 mine = (j == 0) ? v[i][(R - r) & (R - 1)] : v[i][R - 1 - r];
+                const double2 pz = make_double2(NRB_SHFL(mine.x, partner), NRB_SHFL(mine.y, partner));
+                const int k = j + r * NB;
+                const double2 zk = cswap(v[i][r]);
+                if (k == 0) {
+                    const double f0 = zk.x + zk.y, fn = zk.x - zk.y;
+                    if (ok) {
+                        if (P.real_mode == REAL_SPEQ) { NRB_STS(dst, make_double2(f0, 0.0)); P.speq[q] = make_double2(fn, 0.0); }
+                        else NRB_STS(dst, make_double2(f0, fn));
+                    }
+                } else {
+                    const double2 f = untangle_bin<1>(zk, cswap(pz), NRB_LDG(P.rtw + k));
+                    if (ok) NRB_STS(dst + (i64)k * P.out_es, f);
+                }
+            }
+        } else if (DST_G) {
             const u64 q = P.q_begin + (u64)tile * G::L + (u64)ln[i];
             if (q < P.q_end) {
                 const i64 lb = line_base(q, P.out_s0, P.out_s1, P.out_s2, P.logA, P.logB);
@@ -373,7 +463,10 @@ NRB_DEV void fft_pass_body(const PassParams &P, double2 *sm, unsigned tile, int 
     if (VARIANT == VAR_REAL) {
         constexpr int HALF = G::N / 2;   // pair items per line (k = 0 handles DC, Nyquist, middle)
         constexpr int ITEMS = (G::L * HALF + G::NT - 1) / G::NT;
-        if (DIR > 0) {
+        if (DIR > 0 && real_fwd_in_registers<LOG2N, LAYOUT>()) {
+            // c2c with the untangling done in registers by the last stage
+            StageRunner<LOG2N, LAYOUT, DIR, VARIANT, 0, true, true>::run(P, sm, tile, tid);
+        } else if (DIR > 0) {
             // c2c (swapped domain) -> shared memory -> untangle -> global
             StageRunner<LOG2N, LAYOUT, DIR, VARIANT, 0, true, false>::run(P, sm, tile, tid);
 #pragma unroll 4

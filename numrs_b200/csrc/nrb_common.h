@@ -20,6 +20,8 @@ namespace nrb_emu { void barrier(); }
 #define NRB_LDG(p) (*(p))
 #define NRB_LDS(p) (*(p))
 #define NRB_STS(p, v) (*(p) = (v))
+namespace nrb_emu { double shfl(double v, int src_lane); }
+#define NRB_SHFL(v, lane) nrb_emu::shfl((v), (lane))
 #else
 #include <cuda_runtime.h>
 #define NRB_DEV __device__ __forceinline__
@@ -34,6 +36,7 @@ namespace nrb_emu { void barrier(); }
 #else
 #define NRB_LDS(p) (*(p))
 #endif
+#define NRB_SHFL(v, lane) __shfl_sync(0xffffffffu, (v), (lane))
 #ifdef NRB_STREAM_ST
 #define NRB_STS(p, v) __stcg((p), (v))
 #else
@@ -168,7 +171,7 @@ struct PassParams {
     const double2 *tw;      // packed stage twiddles of this log2n
     const double2 *tw_lo;   // four-step twiddle, exp(-2 pi i m / M): low / high tables
     const double2 *tw_hi;
-    const double2 *rtw;     // VAR_REAL: exp(-i pi k / N), k < max(N/2, 1)
+    const double2 *rtw;     // VAR_REAL: exp(-i pi k / N), k < N
     double2 *speq;          // VAR_REAL + REAL_SPEQ: Nyquist plane, element q
     i64 in_s0, in_s1, in_s2, in_es;
     i64 out_s0, out_s1, out_s2, out_es;

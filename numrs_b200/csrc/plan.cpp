@@ -153,7 +153,7 @@ std::vector<double2> gen_fs_hi(int log2m)
 std::vector<double2> gen_real(int log2n)
 {
     const u64 N = 1ull << log2n;
-    std::vector<double2> t((size_t)(N >= 2 ? N / 2 : 1));
+    std::vector<double2> t((size_t)N);
     for (u64 k = 0; k < t.size(); ++k) t[k] = unit_root(k, 2 * N);
     return t;
 }

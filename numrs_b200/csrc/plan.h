@@ -80,7 +80,7 @@ struct Program {
 struct FourStepTable { const double2 *lo, *hi; int h; };
 const double2 *stage_twiddles(int log2n);          // packed per-stage tables (nrb_common.h layout)
 FourStepTable fourstep_table(int log2m);           // exp(-2 pi i m / 2^log2m), two-level
-const double2 *real_twiddles(int log2n);           // exp(-i pi k / 2^log2n), k < max(N/2,1)
+const double2 *real_twiddles(int log2n);           // exp(-i pi k / 2^log2n), k < N
 void release_tables();
 
 // tunables (environment overrides, read once)

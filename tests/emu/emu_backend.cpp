@@ -20,6 +20,8 @@
 
 namespace nrb_emu {
 
+struct Cta;
+void barrier();
 struct Cta {
     ucontext_t main_ctx;
     std::vector<ucontext_t> fibers;
@@ -32,6 +34,19 @@ struct Cta {
     unsigned tile;
 };
 static thread_local Cta *t_cta = nullptr;
+
+// __shfl_sync for the fibers: publish, CTA-wide barrier, read the source lane of the own warp, barrier
+static thread_local std::vector<double> *t_shfl = nullptr;
+double shfl(double v, int src_lane)
+{
+    Cta *c = t_cta;
+    const int tid = c->current;
+    (*t_shfl)[tid] = v;
+    barrier();
+    const double r = (*t_shfl)[(tid & ~31) | (src_lane & 31)];
+    barrier();
+    return r;
+}
 
 void barrier()
 {
@@ -135,6 +150,8 @@ int be_launch_pass(const KernelKey &key, const PassParams &p, u64 ntiles, void *
         c.stacks.resize((size_t)e.nthreads * nrb_emu::kStack);
         c.done.resize(e.nthreads);
         c.smem.assign(e.smem, make_double2(0.0, 0.0));
+        std::vector<double> shfl_buf(e.nthreads + 32, 0.0);
+        nrb_emu::t_shfl = &shfl_buf;
         c.body = e.fn;
         c.params = &p;
 #pragma omp for schedule(dynamic)
