@@ -153,8 +153,15 @@ int    nrb_slab_stage(nrb_slab_t plan, int stage, int isign, double *d_slab, dou
  * all-to-all: d_send / d_recv are ignored); the caller only has to put a cross-rank barrier between
  * stage 0 and stage 1.  Passing NULL returns the plan to the explicit send/recv mode. */
 int    nrb_slab_set_peers(nrb_slab_t plan, void *const *peer_recv, int count);
+/* Size of one receive buffer for the fused mode: the exchange area plus a small flag array used by
+ * nrb_slab_barrier (nrb_device_alloc returns zeroed memory). */
+size_t nrb_slab_recv_bytes(nrb_slab_t plan);
+/* Collective-free barrier of the fused mode, enqueued on `stream`: phase 0 (after stage 0) publishes
+ * `epoch` into this rank's slot of every peer's flag array; phase 1 (before stage 1) spins on the
+ * device until all ranks have published `epoch` locally.  Epochs must increase per receive buffer. */
+int    nrb_slab_barrier(nrb_slab_t plan, int phase, unsigned long long epoch, void *stream);
 int    nrb_slab_destroy(nrb_slab_t plan);
-/* raw device memory + CUDA IPC plumbing for the above */
+/* raw (zero-initialised) device memory + CUDA IPC plumbing for the above */
 int    nrb_device_alloc(size_t bytes, void **dptr);
 int    nrb_device_free(void *dptr);
 int    nrb_ipc_export(void *dptr, unsigned char handle[64]);

@@ -39,7 +39,7 @@ ABI_SYMBOLS = [
     "nrb_plan_create", "nrb_plan_workspace_bytes", "nrb_plan_num_launches", "nrb_plan_exec", "nrb_plan_destroy",
     "nrb_plan_profile", "nrb_plan_describe_launch", "nrb_fill_uniform_device",
     "nrb_slab_create", "nrb_slab_local_doubles", "nrb_slab_speq_doubles", "nrb_slab_xchg_doubles",
-    "nrb_slab_stage", "nrb_slab_destroy", "nrb_slab_set_peers",
+    "nrb_slab_stage", "nrb_slab_destroy", "nrb_slab_set_peers", "nrb_slab_recv_bytes", "nrb_slab_barrier",
     "nrb_device_alloc", "nrb_device_free", "nrb_ipc_export", "nrb_ipc_import", "nrb_ipc_release",
 ]
 
@@ -102,6 +102,9 @@ class Library:
         L.nrb_slab_stage.argtypes = [_vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp]
         L.nrb_slab_destroy.argtypes = [_vp]
         L.nrb_slab_set_peers.argtypes = [_vp, ctypes.POINTER(_vp), ctypes.c_int]
+        L.nrb_slab_recv_bytes.argtypes = [_vp]
+        L.nrb_slab_recv_bytes.restype = _sz
+        L.nrb_slab_barrier.argtypes = [_vp, ctypes.c_int, ctypes.c_ulonglong, _vp]
         L.nrb_device_alloc.argtypes = [_sz, ctypes.POINTER(_vp)]
         L.nrb_device_free.argtypes = [_vp]
         L.nrb_ipc_export.argtypes = [_vp, ctypes.c_char_p]
@@ -306,6 +309,12 @@ class SlabPlan:
             return
         arr = (_vp * len(peer_ptrs))(*peer_ptrs)
         self.lib.check(self.lib.L.nrb_slab_set_peers(self.h, arr, len(peer_ptrs)))
+
+    def recv_bytes(self):
+        return self.lib.L.nrb_slab_recv_bytes(self.h)
+
+    def barrier(self, phase, epoch, stream=0):
+        self.lib.check(self.lib.L.nrb_slab_barrier(self.h, phase, epoch, stream or None))
 
     def stage(self, stage, isign, d_slab, d_speq, d_send, d_recv, stream=0):
         self.lib.check(self.lib.L.nrb_slab_stage(self.h, stage, isign, d_slab, d_speq, d_send or None,

@@ -271,11 +271,18 @@ int nrb_slab_set_peers(nrb_slab_t p, void *const *peer_recv, int count)
     if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
     return slab_set_peers(p->plan, peer_recv, count);
 }
+int nrb_slab_barrier(nrb_slab_t p, int phase, unsigned long long epoch, void *stream)
+{
+    if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
+    return slab_barrier(p->plan, phase, epoch, stream);
+}
+size_t nrb_slab_recv_bytes(nrb_slab_t p) { return p ? nrb_slab_xchg_doubles(p) * sizeof(double) + 256 : 0; }
 int nrb_device_alloc(size_t bytes, void **dptr)
 {
     if (!dptr) return fail(NRB_ERR_INVALID_DIMS, "null pointer");
     if (be_device_count() <= 0) return fail(NRB_ERR_CUDA, "no CUDA device available (numrs_b200 has no CPU fallback)");
     if (be_malloc(dptr, bytes) != 0) return fail(NRB_ERR_OOM, std::string("device allocation failed: ") + be_last_error());
+    if (be_memset(*dptr, 0, bytes, nullptr) != 0 || be_sync(nullptr) != 0) return fail(NRB_ERR_CUDA, std::string("memset failed: ") + be_last_error());
     return NRB_OK;
 }
 int nrb_device_free(void *dptr) { if (dptr) be_free(dptr); return NRB_OK; }

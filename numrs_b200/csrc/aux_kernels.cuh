@@ -197,6 +197,40 @@ NRB_DEV void aux_fill(const AuxParams &A, u64 gtid, u64 gthreads)
     }
 }
 
+// Cross-GPU barrier of the fused slab exchange, without a collective: after its stage-0 kernels (whose
+// peer stores are complete when the kernel ends) every rank publishes the call's epoch into slot `rank`
+// of each peer's flag array; stage 1 starts after the local array shows the epoch in all slots.
+#if defined(NRB_EMU)
+NRB_DEV void flag_store(unsigned long long *p, unsigned long long v) { *(volatile unsigned long long *)p = v; }
+NRB_DEV unsigned long long flag_load(const unsigned long long *p) { return *(const volatile unsigned long long *)p; }
+NRB_DEV void flag_pause() {}
+#else
+NRB_DEV void flag_store(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+NRB_DEV unsigned long long flag_load(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+NRB_DEV void flag_pause() { __nanosleep(200); }
+#endif
+
+NRB_DEV void aux_signal(const AuxParams &A, u64 gtid, u64)
+{
+    if (gtid < A.count) flag_store(A.peer_flags[gtid] + A.n, A.m);
+}
+NRB_DEV void aux_wait(const AuxParams &A, u64 gtid, u64)
+{
+    if (gtid < A.count) {
+#if !defined(NRB_EMU)
+        while (flag_load(A.peer_flags[0] + gtid) < A.m) flag_pause();
+#endif
+    }
+}
+
 NRB_DEV void aux_body(const AuxParams &A, u64 gtid, u64 gthreads)
 {
     switch (A.kind) {
@@ -205,6 +239,8 @@ NRB_DEV void aux_body(const AuxParams &A, u64 gtid, u64 gthreads)
     case AUX_PAD_RESPONSE: aux_pad_response(A, gtid, gthreads); break;
     case AUX_FILL: aux_fill(A, gtid, gthreads); break;
     case AUX_SPECTRAL_Z: aux_spectral_z(A, gtid, gthreads); break;
+    case AUX_SIGNAL: aux_signal(A, gtid, gthreads); break;
+    case AUX_WAIT: aux_wait(A, gtid, gthreads); break;
     default: aux_correl_direct(A, gtid, gthreads); break;
     }
 }

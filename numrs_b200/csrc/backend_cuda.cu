@@ -99,6 +99,7 @@ int be_launch_aux(const AuxParams &a, void *stream)
     case AUX_PAD_RESPONSE: items = a.n; break;
     case AUX_FILL: items = a.n; break;
     case AUX_SPECTRAL_Z: items = a.count * (a.n >= 8 ? a.n / 4 : 1); break;
+    case AUX_SIGNAL: case AUX_WAIT: items = a.count; break;
     default: items = a.count * a.n; break;
     }
     if (items == 0) return 0;
@@ -125,6 +126,11 @@ int be_malloc(void **p, size_t bytes)
 int be_free(void *p)
 {
     cudaError_t e = cudaFree(p);
+    return e == cudaSuccess ? 0 : fail(e);
+}
+int be_memset(void *p, int value, size_t bytes, void *stream)
+{
+    cudaError_t e = cudaMemsetAsync(p, value, bytes, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : fail(e);
 }
 int be_ipc_export(void *dptr, unsigned char handle[64])

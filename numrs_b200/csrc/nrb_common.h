@@ -212,7 +212,9 @@ enum AuxKind {
     AUX_PAD_RESPONSE = 2, // Convolve.rs:41-63 response placement
     AUX_CORREL_DIRECT = 3,// Correlation.rs:37-50, n <= 32
     AUX_FILL = 4,         // synthetic input generator: n doubles, seed in m, offset in count
-    AUX_SPECTRAL_Z = 5    // untangle + spectral op + inverse untangle in one pass on raw c2c outputs
+    AUX_SPECTRAL_Z = 5,   // untangle + spectral op + inverse untangle in one pass on raw c2c outputs
+    AUX_SIGNAL = 6,       // slab exchange barrier: publish `epoch` (in m) to slot `rank` (in n) of every peer's flag array
+    AUX_WAIT = 7          // slab exchange barrier: spin until the first `count` local flags are >= epoch (in m)
 };
 enum SpectralOp { SPEC_CONV_MUL = 0, SPEC_CONV_DIV = 1, SPEC_CORREL = 2 };
 
@@ -231,6 +233,7 @@ struct AuxParams {
     u64 m;                // pad: taps
     u64 count;            // lines / signals
     i64 a_stride, b_stride, out_stride; // per line / signal, in complex elements (doubles for pad/direct)
+    unsigned long long *peer_flags[8];  // AUX_SIGNAL: every rank's flag array (IPC-mapped); AUX_WAIT: [0] = local
 };
 
 } // namespace nrb

@@ -866,6 +866,23 @@ int slab_set_peers(SlabPlan &sp, void *const *peer_recv, int count)
     return NRB_OK;
 }
 
+int slab_barrier(SlabPlan &sp, int phase, unsigned long long epoch, void *stream)
+{
+    if (!sp.fused) { set_error("slab: the flag barrier needs the fused exchange (nrb_slab_set_peers)"); return NRB_ERR_INVALID_DIMS; }
+    const u64 G = (u64)sp.nranks;
+    const size_t xchg = (size_t)(G * (sp.nn1 / G) * (sp.nn2 / G) * (sp.nn3 / 2 + 1));   // complex elements
+    AuxParams ap;
+    memset(&ap, 0, sizeof(ap));
+    ap.kind = phase == 0 ? AUX_SIGNAL : AUX_WAIT;
+    ap.m = epoch;
+    ap.n = (u64)sp.rank;
+    ap.count = G;
+    for (int i = 0; i < sp.nranks; ++i) ap.peer_flags[i] = (unsigned long long *)(sp.peers[i] + xchg);
+    if (phase != 0) ap.peer_flags[0] = (unsigned long long *)(sp.peers[sp.rank] + xchg);
+    if (be_launch_aux(ap, stream) != 0) { set_error(std::string("kernel launch failed: ") + be_last_error()); return NRB_ERR_CUDA; }
+    return NRB_OK;
+}
+
 int exec_slab_stage(SlabPlan &sp, int stage, int isign, double *d_slab, double *d_speq, double *d_send,
                     double *d_recv, void *stream)
 {

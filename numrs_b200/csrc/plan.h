@@ -20,6 +20,7 @@ int be_launch_fused(const KernelKey &ka, const PassParams &pa, const KernelKey &
                     void *stream);
 int be_malloc(void **p, size_t bytes);
 int be_free(void *p);
+int be_memset(void *p, int value, size_t bytes, void *stream);
 int be_ipc_export(void *dptr, unsigned char handle[64]);
 int be_ipc_import(const unsigned char handle[64], void **dptr);
 int be_ipc_release(void *dptr);
@@ -131,6 +132,8 @@ struct SlabPlan {
 };
 int build_slab_plan(SlabPlan &sp, size_t nn1, size_t nn2, size_t nn3, int nranks, int rank);
 int slab_set_peers(SlabPlan &sp, void *const *peer_recv, int count);
+// flag barrier of the fused exchange (flags live right after the exchange area of each receive buffer)
+int slab_barrier(SlabPlan &sp, int phase /*0 = signal, 1 = wait*/, unsigned long long epoch, void *stream);
 int exec_slab_stage(SlabPlan &sp, int stage, int isign, double *d_slab, double *d_speq, double *d_send,
                     double *d_recv, void *stream);
 

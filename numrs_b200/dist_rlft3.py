@@ -7,8 +7,10 @@ Inverse (isign=-1) is the mirror image.  Exactly one exchange per direction:
 
   mode "fused" (default): the last FFT pass of stage 0 stores its output straight into the owning
       peer's receive buffer through NVLink (CUDA IPC mapped peer memory) from the kernel epilogue,
-      so the transfer overlaps the transform tile by tile; a stream-ordered 1-element NCCL
-      all-reduce is the only collective (the barrier between stage 0 and stage 1).
+      so the transfer overlaps the transform tile by tile; the barrier between stage 0 and stage 1
+      is a pair of one-warp kernels exchanging epoch flags through the same peer mappings
+      (`barrier="flags"`, default: no collective at all on the data path) or a stream-ordered
+      1-element NCCL all-reduce (`barrier="nccl"`).
   mode "nccl": stage 0 writes a send buffer, torch.distributed.all_to_all_single moves the blocks.
 """
 import torch
@@ -16,7 +18,7 @@ import torch.distributed as dist
 
 
 class SlabRlft3:
-    def __init__(self, lib, nn1, nn2, nn3, mode="fused"):
+    def __init__(self, lib, nn1, nn2, nn3, mode="fused", barrier="flags"):
         self.lib = lib
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.dims = (nn1, nn2, nn3)
@@ -25,6 +27,7 @@ class SlabRlft3:
         self.speq_doubles = self.plan.speq_doubles()
         self.xchg_doubles = self.plan.xchg_doubles()
         self.mode = mode
+        self.barrier = barrier
         self._flag = torch.zeros(1, dtype=torch.int32, device="cuda")
         self._call = 0
         if mode == "fused":
@@ -32,7 +35,7 @@ class SlabRlft3:
             # stage 1 is never overwritten by call k+1's stage 0 (ordered by call k+1's barrier)
             self._own, self._peers = [], []
             for _ in range(2):
-                own = lib.device_alloc(self.xchg_doubles * 8)
+                own = lib.device_alloc(self.plan.recv_bytes())     # zeroed: the flag array starts at epoch 0
                 handle = lib.ipc_export(own)
                 handles = [None] * self.world
                 dist.all_gather_object(handles, handle)
@@ -58,7 +61,12 @@ class SlabRlft3:
             self._call += 1
             self.plan.set_peers(peers)
             self.plan.stage(0, isign, slab.data_ptr(), speq.data_ptr(), 0, 0, st)
-            dist.all_reduce(self._flag)      # stream-ordered barrier: every rank's stage-0 stores have landed
+            if self.barrier == "flags":
+                epoch = (self._call + 1) // 2            # per receive buffer: 1, 2, 3, ...
+                self.plan.barrier(0, epoch, st)          # my stage-0 stores have landed everywhere
+                self.plan.barrier(1, epoch, st)          # ... and so have everybody else's here
+            else:
+                dist.all_reduce(self._flag)              # stream-ordered NCCL barrier
             self.plan.stage(1, isign, slab.data_ptr(), speq.data_ptr(), 0, 0, st)
         else:
             self.plan.stage(0, isign, slab.data_ptr(), speq.data_ptr(), self.send.data_ptr(), 0, st)

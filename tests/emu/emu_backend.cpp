@@ -204,6 +204,7 @@ float be_event_elapsed_ms(void *a, void *b)
 void be_event_destroy(void *e) { delete (timespec *)e; }
 int be_malloc(void **p, size_t bytes) { *p = malloc(bytes ? bytes : 16); return *p ? 0 : -1; }
 int be_free(void *p) { free(p); return 0; }
+int be_memset(void *p, int v, size_t n, void *) { memset(p, v, n); return 0; }
 int be_ipc_export(void *p, unsigned char h[64]) { memset(h, 0, 64); memcpy(h, &p, sizeof(p)); return 0; }
 int be_ipc_import(const unsigned char h[64], void **p) { memcpy(p, h, sizeof(*p)); return 0; }
 int be_ipc_release(void *) { return 0; }

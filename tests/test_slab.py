@@ -33,7 +33,7 @@ def run_simulated(L, x, G, isign, speq_in=None, fused=False):
         slabs = [np.ascontiguousarray(x[r * X:(r + 1) * X]).ravel().copy() for r in range(G)]
         speqs = [np.ascontiguousarray(speq_in[r * X:(r + 1) * X]).ravel().copy() for r in range(G)]
     sends = [np.zeros(xd) for _ in range(G)]
-    recvs = [np.zeros(xd) for _ in range(G)]
+    recvs = [np.zeros(plans[0].recv_bytes() // 8) for _ in range(G)]
     if fused:
         for r in range(G):
             plans[r].set_peers([rv.ctypes.data for rv in recvs])
@@ -43,6 +43,12 @@ def run_simulated(L, x, G, isign, speq_in=None, fused=False):
         for p in range(G):
             if not fused:
                 recvs[p][r * blk:(r + 1) * blk] = sends[r][p * blk:(p + 1) * blk]
+    if fused:       # flag barrier: every rank publishes epoch 1, then every rank sees all G flags
+        for r in range(G):
+            plans[r].barrier(0, 1)
+        for r in range(G):
+            plans[r].barrier(1, 1)
+            assert list(recvs[r][xd:xd + G].view(np.uint64)) == [1] * G
     for r in range(G):
         plans[r].stage(1, isign, slabs[r].ctypes.data, speqs[r].ctypes.data, 0, recvs[r].ctypes.data)
     for p in plans:

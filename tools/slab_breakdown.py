@@ -18,6 +18,7 @@ lib.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 from numrs_b200.dist_rlft3 import SlabRlft3  # noqa: E402
 mode = sys.argv[2] if len(sys.argv) > 2 else "nccl"
+barrier = sys.argv[3] if len(sys.argv) > 3 else "flags"
 S = SlabRlft3(lib, n, n, n, mode=mode)
 slab = S.plan
 f64 = dict(dtype=torch.float64, device="cuda")
@@ -44,7 +45,11 @@ def direction(isign, e0, e1, e2, e3, call):
         slab.set_peers(S._peers[call & 1])
         slab.stage(0, isign, buf.data_ptr(), speq.data_ptr(), 0, 0, st)
         e1.record()
-        dist.all_reduce(flag)
+        if barrier == "flags":
+            slab.barrier(0, call // 2 + 1, st)
+            slab.barrier(1, call // 2 + 1, st)
+        else:
+            dist.all_reduce(flag)
         e2.record()
         slab.stage(1, isign, buf.data_ptr(), speq.data_ptr(), 0, 0, st)
     e3.record()
@@ -70,7 +75,7 @@ if rank == 0:
     xn = "all-to-all" if mode == "nccl" else "barrier (stores already landed)"
     names = ["fwd stage0 (z + x)", "fwd " + xn, "fwd stage1 (y)", "inv stage0 (y)", "inv " + xn, "inv stage1 (x + z)", "total step"]
     a2a_bytes = 8.0 * slab.xchg_doubles() * (world - 1) / world
-    print(f"== slab rlft3 {n}^3 on {world} GPUs, exchange={mode} (max over ranks, ms)")
+    print(f"== slab rlft3 {n}^3 on {world} GPUs, exchange={mode} barrier={barrier if mode == "fused" else "-"} (max over ranks, ms)")
     for nm, v in zip(names, t.tolist()):
         extra = f"   {a2a_bytes / v / 1e6:.0f} GB/s per GPU per direction" if "all-to-all" in nm else ""
         print(f"   {v:8.4f}  {nm}{extra}")
