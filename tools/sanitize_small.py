@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""Runs one small instance of every kernel family through the C ABI (for compute-sanitizer memcheck / racecheck)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+
+import cases  # noqa: E402
+import numrs_b200 as nb  # noqa: E402
+
+L = nb.lib()
+for nn in (2, 8, 64, 256, 512, 4096, 8192, 1 << 14):
+    cases.check_four1(L, nn)
+cases.check_four1_batch(L, 256, 37)
+for shape in ((4, 8, 2), (64, 64), (2, 1024), (2048, 4), (8, 8, 8, 4)):
+    cases.check_fourn(L, shape)
+for n in (2, 8, 64, 512, 4096, 1 << 15):
+    cases.check_realft(L, n)
+for shp in ((2, 2, 2), (8, 8, 8), (16, 8, 32), (4, 256, 256), (1, 1, 64)):
+    cases.check_rlft3(L, shp)
+L.set_option("fuse_zy", 1)
+cases.check_rlft3(L, (4, 256, 256))
+L.set_option("fuse_zy", 0)
+L.set_option("row_max_log2", 5)
+L.set_option("col_max_log2", 4)
+cases.check_four1(L, 1 << 12)
+cases.check_realft(L, 1 << 10)
+cases.check_convlv(L, 1 << 10, 33)
+cases.check_correl(L, 1 << 10)
+L.set_option("row_max_log2", 13)
+L.set_option("col_max_log2", 10)
+for n, m in ((4, 2), (64, 5), (1024, 33)):
+    cases.check_convlv(L, n, m)
+for n in (3, 32, 64, 1024):
+    cases.check_correl(L, n)
+print("sanitize_small: all parity checks passed")
