@@ -17,6 +17,15 @@
 
 namespace nrb {
 
+// CTAs per SM the register allocator targets: the 64 K registers of an SM divided by
+// (threads x registers) with 64 registers at 8 points/thread and 128 at 16
+NRB_HD constexpr int min_blocks(int log2n, int layout)
+{
+    return tile_log2(log2n, layout) > 12 ? 1
+         : layout == LAYOUT_ROW ? NRB_MIN_BLOCKS_ROW * (4096 >> tile_log2(log2n, layout))
+                                : NRB_MIN_BLOCKS_COL;
+}
+
 typedef int (*PassLaunchFn)(const PassParams &, u64, cudaStream_t);
 // table[log2n][layout][dir>0][variant]
 struct PassTable { PassLaunchFn fn[kMaxLog2N + 1][2][2][3]; };
@@ -31,7 +40,7 @@ PassTable &pass_table();
 #endif
 
 template <int LOG2N, int LAYOUT, int DIR, int VARIANT>
-__global__ void __launch_bounds__(cta_threads(LOG2N, LAYOUT), (tile_log2(LOG2N) == 12 ? (LAYOUT == LAYOUT_ROW ? NRB_MIN_BLOCKS_ROW : NRB_MIN_BLOCKS_COL) : 1))
+__global__ void __launch_bounds__(cta_threads(LOG2N, LAYOUT), min_blocks(LOG2N, LAYOUT))
 fft_pass_kernel(const __grid_constant__ PassParams P, const unsigned ntiles)
 {
     extern __shared__ double2 nrb_smem[];
@@ -159,10 +168,13 @@ int launch_fused_t(const PassParams &pa, const PassParams &pb, const FuseSched &
 // rlft3: z real pass (ROW REAL, 2^LZ) + y pass (COL PLAIN, 2^LY); forward = z then y, inverse = y then z
 template <int LZ, int LY> void register_fused_zy()
 {
+    if constexpr (cta_threads(LZ, LAYOUT_ROW) != cta_threads(LY, LAYOUT_COL)) return;   // needs equal CTA sizes
+    else {
     register_fused(fused_key(LZ, LAYOUT_ROW, VAR_REAL, LY, LAYOUT_COL, VAR_PLAIN, +1),
                    launch_fused_t<LZ, LAYOUT_ROW, VAR_REAL, LY, LAYOUT_COL, VAR_PLAIN, +1>);
     register_fused(fused_key(LY, LAYOUT_COL, VAR_PLAIN, LZ, LAYOUT_ROW, VAR_REAL, -1),
                    launch_fused_t<LY, LAYOUT_COL, VAR_PLAIN, LZ, LAYOUT_ROW, VAR_REAL, -1>);
+    }
 }
 
 template <int LOG2N, int LAYOUT> void register_size(PassTable &t)

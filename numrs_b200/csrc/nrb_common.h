@@ -17,6 +17,7 @@ namespace nrb_emu { void barrier(); }
 #define NRB_DEVM inline
 #define NRB_HD inline
 #define NRB_SYNC() nrb_emu::barrier()
+#define NRB_SYNCWARP() nrb_emu::barrier()
 #define NRB_LDG(p) (*(p))
 #define NRB_LDS(p) (*(p))
 #define NRB_STS(p, v) (*(p) = (v))
@@ -28,6 +29,7 @@ namespace nrb_emu { double shfl(double v, int src_lane); }
 #define NRB_DEVM __device__ __forceinline__
 #define NRB_HD __host__ __device__ __forceinline__
 #define NRB_SYNC() __syncthreads()
+#define NRB_SYNCWARP() __syncwarp()
 #define NRB_LDG(p) __ldg(p)
 // streaming data: bypass L1 (ld.global.cg) -- every element is touched once per pass, and keeping it
 // out of L1 leaves the cache to the twiddle tables (measured: 5.2 -> 6.3 TB/s on the strided pattern)
@@ -142,12 +144,21 @@ NRB_HD constexpr int stage_tw_total(int log2n)
 }
 
 // tile geometry: a CTA transforms L = TILE/N lines of N points
-NRB_HD constexpr int tile_log2(int log2n) { return log2n > 12 ? log2n : 12; }
-NRB_HD constexpr int cta_threads(int log2n, int layout) { return (1 << tile_log2(log2n)) / points_per_thread(layout, log2n); }
+// ROW lines are contiguous, so a ROW tile may be smaller than a COL tile (whose line count sets the
+// length of every global access run): smaller CTAs, more of them per SM, cheaper barriers.
+#ifndef NRB_TL_ROW
+#define NRB_TL_ROW 10
+#endif
+NRB_HD constexpr int tile_log2(int log2n, int layout)
+{
+    return layout == 0 /* ROW */ ? (log2n > NRB_TL_ROW ? log2n : NRB_TL_ROW) : (log2n > 12 ? log2n : 12);
+}
+NRB_HD constexpr int cta_threads(int log2n, int layout) { return (1 << tile_log2(log2n, layout)) / points_per_thread(layout, log2n); }
 
 // shared-memory footprint in double2 elements
 NRB_HD constexpr int row_line_pitch(int log2n) { return (1 << log2n) + ((1 << log2n) >> 3); }
-NRB_HD constexpr int col_line_count(int log2n) { return (1 << tile_log2(log2n)) >> log2n; }
+NRB_HD constexpr int lines_per_tile(int log2n, int layout) { return (1 << tile_log2(log2n, layout)) >> log2n; }
+NRB_HD constexpr int col_line_count(int log2n) { return lines_per_tile(log2n, 1); }
 NRB_HD constexpr int col_pitch(int log2n, int variant)
 {
     // XPOSE reads the tile back line-contiguously: pitch L+1 keeps that conflict-free for L >= 8;
@@ -157,7 +168,7 @@ NRB_HD constexpr int col_pitch(int log2n, int variant)
 NRB_HD constexpr size_t smem_elems(int log2n, int layout, int variant)
 {
     return layout == LAYOUT_ROW
-               ? (size_t)col_line_count(log2n) * (size_t)row_line_pitch(log2n)
+               ? (size_t)lines_per_tile(log2n, 0) * (size_t)row_line_pitch(log2n)
                : (size_t)(1 << log2n) * (size_t)col_pitch(log2n, variant);
 }
 

@@ -207,9 +207,9 @@ void init_pass(PassParams &pp)
     pp.logB = 40;
 }
 
-u64 tiles_for(int log2n, u64 lines)
+u64 tiles_for(int log2n, int layout, u64 lines)
 {
-    const u64 L = (u64)col_line_count(log2n);
+    const u64 L = (u64)lines_per_tile(log2n, layout);
     return (lines + L - 1) / L;
 }
 
@@ -267,7 +267,7 @@ void emit_axis(Builder &B, BufRef src, BufRef dst, BufRef tmp, u64 outer, u64 o_
         }
         pp.tw = stage_twiddles(p);
         st.in = src; st.out = dst;
-        st.ntiles = tiles_for(p, pp.q_end - pp.q_begin);
+        st.ntiles = tiles_for(p, st.key.layout, pp.q_end - pp.q_begin);
         B.prog->steps.push_back(st);
         return;
     }
@@ -298,7 +298,7 @@ void emit_axis(Builder &B, BufRef src, BufRef dst, BufRef tmp, u64 outer, u64 o_
         pp.tw_on = 1; pp.tw_lo = fs.lo; pp.tw_hi = fs.hi; pp.tw_h = fs.h;
         pp.tw = stage_twiddles(f);
         st.in = cur; st.out = nxt;
-        st.ntiles = tiles_for(f, pp.q_end - pp.q_begin);
+        st.ntiles = tiles_for(f, st.key.layout, pp.q_end - pp.q_begin);
         B.prog->steps.push_back(st);
         cur = nxt;
         pcur -= f;
@@ -318,7 +318,7 @@ void emit_axis(Builder &B, BufRef src, BufRef dst, BufRef tmp, u64 outer, u64 o_
         (void)Nl;
         pp.tw = stage_twiddles(pcur);
         st.in = cur; st.out = dst;
-        st.ntiles = tiles_for(pcur, pp.q_end - pp.q_begin);
+        st.ntiles = tiles_for(pcur, st.key.layout, pp.q_end - pp.q_begin);
         B.prog->steps.push_back(st);
     }
 }
@@ -344,7 +344,7 @@ void emit_real(Builder &B, BufRef src, BufRef dst, BufRef tmp, u64 l_begin, u64 
         pp.rtw = real_twiddles(p);
         pp.real_mode = real_mode;
         st.in = src; st.out = dst; st.speq = speq;
-        st.ntiles = tiles_for(p, l_end - l_begin);
+        st.ntiles = tiles_for(p, st.key.layout, l_end - l_begin);
         B.prog->steps.push_back(st);
         return;
     }
@@ -462,7 +462,7 @@ int build_rlft3(Plan &pl, Builder &B, int dir)
     // y tiles trailing `lag` planes behind, so the y pass reads the z pass's output from L2.
     const bool fusable = tunables().fuse_zy && g == nn1 && nn1 >= 2 && p3 >= 1 && p3 <= tunables().row_max_log2 &&
                          p2 >= 1 && p2 <= tunables().col_max_log2 && N3 >= (u64)col_line_count(p2) &&
-                         nn2 >= (u64)col_line_count(p3);
+                         nn2 >= (u64)lines_per_tile(p3, LAYOUT_ROW);
     auto emit_fused = [&](int d) -> bool {
         const KernelKey kz{p3, LAYOUT_ROW, d, VAR_REAL}, ky{p2, LAYOUT_COL, d, VAR_PLAIN};
         if (!fusable || !be_fused_available(d > 0 ? kz : ky, d > 0 ? ky : kz)) return false;
@@ -476,7 +476,7 @@ int build_rlft3(Plan &pl, Builder &B, int dir)
         Step st = a;
         st.is_fused = true;
         st.key2 = b.key; st.pp2 = b.pp; st.in2 = b.in; st.out2 = b.out; st.speq2 = b.speq;
-        const u64 tz = nn2 / (u64)col_line_count(p3), ty = N3 / (u64)col_line_count(p2);
+        const u64 tz = nn2 / (u64)lines_per_tile(p3, LAYOUT_ROW), ty = N3 / (u64)col_line_count(p2);
         st.fs.units = (unsigned)nn1;
         st.fs.ta = (unsigned)(d > 0 ? tz : ty);
         st.fs.tb = (unsigned)(d > 0 ? ty : tz);
@@ -749,7 +749,7 @@ int describe_launch(const Plan &pl, int isign, int idx, char *name, size_t cap, 
         snprintf(buf, sizeof(buf), "fused_%s_n%d+%s_n%d_%s_U%u", st.key.layout == LAYOUT_ROW ? "row_real" : "col", 1 << st.key.log2n,
                  st.key2.layout == LAYOUT_ROW ? "row_real" : "col", 1 << st.key2.log2n, st.key.dir > 0 ? "p" : "m", st.fs.units);
         // the pair reads the volume once and writes it once (the intermediate stays in L2)
-        const double vol = (double)st.fs.units * (double)st.fs.ta * 4096.0;
+        const double vol = (double)st.fs.units * (double)st.fs.ta * (double)(1 << tile_log2(st.key.log2n, st.key.layout));
         b = 2.0 * 16.0 * vol + 16.0 * (double)(st.key.layout == LAYOUT_ROW ? st.pp.q_end - st.pp.q_begin : st.pp2.q_end - st.pp2.q_begin);
     } else if (st.is_aux) {
         static const char *names[] = {"untangle", "spectral", "pad_response", "correl_direct", "fill", "spectral_z"};

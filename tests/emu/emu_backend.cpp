@@ -171,7 +171,8 @@ bool be_fused_available(const KernelKey &a, const KernelKey &b)
     const KernelKey &z = a.layout == LAYOUT_ROW ? a : b, &y = a.layout == LAYOUT_ROW ? b : a;
     const bool order_ok = (a.dir > 0) == (a.layout == LAYOUT_ROW);
     return a.dir == b.dir && order_ok && z.layout == LAYOUT_ROW && z.variant == VAR_REAL && y.layout == LAYOUT_COL &&
-           y.variant == VAR_PLAIN && z.log2n >= 7 && z.log2n <= 9 && y.log2n >= 8 && y.log2n <= 10;
+           y.variant == VAR_PLAIN && z.log2n >= 7 && z.log2n <= 9 && y.log2n >= 8 && y.log2n <= 10 &&
+           cta_threads(z.log2n, LAYOUT_ROW) == cta_threads(y.log2n, LAYOUT_COL);
 }
 
 int be_launch_fused(const KernelKey &ka, const PassParams &pa, const KernelKey &kb, const PassParams &pb, const FuseSched &fs, void *st)

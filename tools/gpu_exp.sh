@@ -1,6 +1,6 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-mkdir -p gpurun_out
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python tools/sanitize_small.py > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck exit $?"; tail -4 gpurun_out/sanitizer_memcheck.log
-timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 python tools/sanitize_small.py > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck exit $?"; tail -4 gpurun_out/sanitizer_racecheck.log
-timeout 120 python tools/kernel_table.py four1_20_1 four1_12_1 2>&1 | grep -v Traceback
+for rep in 1 2; do
+echo "##### default"; timeout 300 python tools/kernel_table.py rlft3_512 2>&1 | grep -E "real"
+echo "##### preidx"; NUMRS_B200_LIB=$PWD/variants/lib_preidx.so timeout 300 python tools/kernel_table.py rlft3_512 2>&1 | grep -E "real"
+done
