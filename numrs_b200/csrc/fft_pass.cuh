@@ -30,6 +30,12 @@
 
 // REAL inverse pre-pass thread mapping: 1 = the line's own thread group prepares it (warp-level sync
 // after it), 0 = flat index mapping + one CTA barrier.  Measured on B200: 0 is 20 % faster (5.2 vs 4.35 TB/s).
+#ifndef NRB_TW_POWERS
+#define NRB_TW_POWERS 1
+#endif
+#ifndef NRB_TW_POWERS_COL
+#define NRB_TW_POWERS_COL 0
+#endif
 #ifndef NRB_PRE_OWN
 #define NRB_PRE_OWN 0
 #endif
@@ -190,6 +196,22 @@ NRB_DEV unsigned line_q1(const PassParams &P, u64 q)
     return (unsigned)((q >> P.logB) & ((1ull << P.logA) - 1ull));
 }
 
+// cos(m pi / 16), 0 <= m <= 16
+NRB_HD constexpr double cos_pi16(int m)
+{
+    constexpr double c[17] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708, 0.70710678118654752440,
+                              0.55557023301960222474, 0.38268343236508977173, 0.19509032201612826785, 0.0,
+                              -0.19509032201612826785, -0.38268343236508977173, -0.55557023301960222474, -0.70710678118654752440,
+                              -0.83146961230254523708, -0.92387953251128675613, -0.98078528040323044913, -1.0};
+    return c[m];
+}
+// exp(-i pi r / R) for compile-time R (a power of two <= 16) and unrolled r < R
+template <int R> NRB_DEV double2 unit_rot(int r)
+{
+    const int m = r * (16 / R);          // angle = m * pi/16, 0 <= m < 16; sin(m pi/16) = cos(|8 - m| pi/16)
+    return make_double2(cos_pi16(m), -cos_pi16(m < 8 ? 8 - m : m - 8));
+}
+
 // One bin of NR's realft untangling: out_k from (Z_k, Z_{N-k}) and t = exp(-i pi k / N), valid for every
 // 1 <= k <= N-1 (the pair form `untangle_pair` produces out_k and out_{N-k} together; this form lets each
 // thread finish the bins it already holds in registers).
@@ -317,8 +339,29 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
         if (NS > 1) {
             const int jm = jj[i] & (NS - 1);
             const double2 *tp = P.tw + stage_tw_off(LOG2N, S) + jm * (R - 1);
+            if ((LAYOUT == LAYOUT_ROW ? NRB_TW_POWERS : NRB_TW_POWERS_COL) && R >= 4) {
+                // ROW kernels are L1/TEX-bound (every lane needs its own twiddles): load w^1 only and build
+                // the other powers with complex multiplies on the half-idle FP64 pipe (<= 3 products deep)
+                double2 w[R];
+                w[1] = NRB_LDG(tp);
+                w[2] = cmul(w[1], w[1]);
+                w[3] = cmul(w[2], w[1]);
+                if (R >= 8) {
+                    w[4] = cmul(w[2], w[2]);
+                    w[5] = cmul(w[4], w[1]);
+                    w[6] = cmul(w[3], w[3]);
+                    w[7] = cmul(w[4], w[3]);
+                }
+                if (R >= 16) {
 #pragma unroll
-            for (int r = 1; r < R; ++r) v[i][r] = cmul(v[i][r], NRB_LDG(tp + (r - 1)));
+                    for (int r = 8; r < R; ++r) w[r] = cmul(w[r - 4], w[4]);
+                }
+#pragma unroll
+                for (int r = 1; r < R; ++r) v[i][r] = cmul(v[i][r], w[r]);
+            } else {
+#pragma unroll
+                for (int r = 1; r < R; ++r) v[i][r] = cmul(v[i][r], NRB_LDG(tp + (r - 1)));
+            }
         }
         Bfly<R>::run(v[i]);
     }
@@ -340,6 +383,7 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
             const int lane = tid & 31;
             const int partner = (lane & ~(NB - 1)) | ((NB - j) & (NB - 1));
             double2 *dst = P.out + line_base(q, P.out_s0, P.out_s1, P.out_s2, P.logA, P.logB);
+            const double2 rt0 = NRB_LDG(P.rtw + j);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 // value this lane publishes under index R-1-r; the warp runs in lockstep, so each bin is
@@ -355,7 +399,10 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
                         else NRB_STS(dst, make_double2(f0, fn));
                     }
                 } else {
-                    const double2 f = untangle_bin<1>(zk, cswap(pz), NRB_LDG(P.rtw + k));
+                    // exp(-i pi k/N), k = j + r*NB: one table load per thread, the other R-1 by the fixed
+                    // rotations exp(-i pi r/R)
+                    const double2 t = NRB_TW_POWERS ? cmul(rt0, unit_rot<R>(r)) : NRB_LDG(P.rtw + k);
+                    const double2 f = untangle_bin<1>(zk, cswap(pz), t);
                     if (ok) NRB_STS(dst + (i64)k * P.out_es, f);
                 }
             }
