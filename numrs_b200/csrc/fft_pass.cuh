@@ -34,7 +34,7 @@
 #define NRB_TW_POWERS 1
 #endif
 #ifndef NRB_TW_POWERS_COL
-#define NRB_TW_POWERS_COL 0
+#define NRB_TW_POWERS_COL 1
 #endif
 #ifndef NRB_PRE_OWN
 #define NRB_PRE_OWN 0

@@ -147,7 +147,7 @@ NRB_HD constexpr int stage_tw_total(int log2n)
 // ROW lines are contiguous, so a ROW tile may be smaller than a COL tile (whose line count sets the
 // length of every global access run): smaller CTAs, more of them per SM, cheaper barriers.
 #ifndef NRB_TL_ROW
-#define NRB_TL_ROW 10
+#define NRB_TL_ROW 9
 #endif
 NRB_HD constexpr int tile_log2(int log2n, int layout)
 {
