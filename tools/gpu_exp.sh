@@ -1,8 +1,8 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 python tools/sanitize_small.py > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck exit $?"; tail -2 gpurun_out/sanitizer_racecheck.log
-W="rlft3_512 four1_9_32768 four1_10_16384 four1_11_8192 four1_12_4096 four1_13_2048 fourn2d_8192"
-echo "##### default (sub mode)"; timeout 300 python tools/kernel_table.py $W 2>&1 | grep -E "row|^=="
-echo "##### nosub"; NUMRS_B200_LIB=$PWD/variants/lib_nosub.so timeout 300 python tools/kernel_table.py $W 2>&1 | grep -E "row|^=="
+for n in 8 4; do
+  timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2962$n bench.py --gpus $n --steps 20 --warmup 3 > gpurun_out/r01_bench_rlft3_512_n$n.json 2> gpurun_out/bench_n$n.err; echo "bench exit $?"; python -c "import sys,json; d=json.loads(open('gpurun_out/r01_bench_rlft3_512_n$n.json').read()); print('bench n=%d value %.0f GB/s  ms/step %.3f  e2e %.1f GB/s err %.2e clocks %s' % (d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], d['roundtrip_rel_l2'], d['clocks']))"
+done
+timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29518 tools/slab_breakdown.py 512 fused flags 2>&1 | grep -E "==|   |Error|error" | head -20
+timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29519 tools/slab_breakdown.py 1024 fused flags 2>&1 | grep -E "==|   |Error|error" | head -20
