@@ -41,6 +41,7 @@ extern "C" {
 #define NRB_ERR_INVALID_DIMS      -5   /* Fourn.rs:368-370,374-376, Real_FT.rs:5 (n odd) */
 #define NRB_ERR_NOT_POW2          -6   /* not validated by the reference */
 #define NRB_ERR_UNSUPPORTED       -7   /* shape outside what this build implements */
+#define NRB_ERR_ZERO_STDDEV       -8   /* Correlation.rs:214-216,246-248 CorrelError::ZeroStdDev */
 #define NRB_ERR_CUDA              -10
 #define NRB_ERR_NCCL              -11
 #define NRB_ERR_OOM               -12
@@ -100,6 +101,19 @@ int nrb_correl(const double *data1, size_t n1, const double *data2, size_t n2, d
 int nrb_correl_batch(const double *const *data1, const double *const *data2, size_t count,
                      size_t n, double *const *ans);
 
+/* ---- callers on either side of the hot path (SURVEY.md 8f "next" rows N2, N4) ---- */
+/* Correlation.rs:189 correl_normalized (fast = 0) / :226 correl_normalized_fast (fast = 1): population mean / std
+ * of both inputs (two-pass resp. single-pass formulas), NRB_ERR_ZERO_STDDEV when either std is 0, then correl of
+ * the normalised signals (the fast variant's n <= 32 branch also divides by n, Correlation.rs:251-263). */
+int nrb_correl_normalized(const double *data1, size_t n1, const double *data2, size_t n2, int fast, double *ans);
+/* Correlation.rs:286 autocorrel_fast: n <= 32 direct lags, else one forward realft, |F|^2, inverse realft */
+int nrb_autocorrel_fast(const double *data, size_t n, double *ans);
+/* FFT_2.rs:3 twofft(data1, data2, fft1, fft2): spectra of two real signals from one complex four1(+1);
+ * fft1 / fft2 have 2n + 2 doubles (FFT_2.rs:6-7): n complex bins followed by two zero doubles. */
+int nrb_twofft(const double *data1, const double *data2, size_t n, double *fft1, double *fft2);
+/* FFT_1.rs:218 power_spectrum (take_sqrt = 0) / :206 magnitude_spectrum (take_sqrt = 1) of npoints complex points */
+int nrb_power_spectrum(const double *complex_data, size_t npoints, int take_sqrt, double *out);
+
 /* ---- device-resident plan API (what the benchmark times; pointers are DEVICE memory) ---- */
 typedef struct nrb_plan_s *nrb_plan_t;
 
@@ -112,11 +126,19 @@ typedef struct nrb_plan_s *nrb_plan_t;
 #define NRB_KIND_CORREL 6   /* dims = {n};             io = data1, aux = data2 (batch x n,
                                read only), out = batch x n doubles; n > 32                 */
 
+#define NRB_KIND_CORREL_NORM      7  /* dims = {n}; io = data1, aux = data2; out = 2*batch (mean, std) pairs
+                                        (data1's signals, then data2's) followed by batch x n answers    */
+#define NRB_KIND_CORREL_NORM_FAST 8  /* same, single-pass statistics (Correlation.rs:226)                 */
+#define NRB_KIND_AUTOCORREL_FAST  9  /* dims = {n}; io = data, out = batch x n doubles                    */
+#define NRB_KIND_TWOFFT          10  /* dims = {n}; io = data1, aux = data2 (batch x n doubles); out = fft1
+                                        [batch][n+1] complex followed by fft2 [batch][n+1] complex       */
+#define NRB_KIND_POWER           11  /* dims = {npoints}; io = complex points, out = doubles; arg = sqrt  */
+
 int    nrb_plan_create(int kind, const size_t *dims, size_t ndim, size_t batch, nrb_plan_t *plan);
 size_t nrb_plan_workspace_bytes(nrb_plan_t plan);
 int    nrb_plan_num_launches(nrb_plan_t plan, int isign);  /* kernels per exec */
 /* Enqueue on `stream` (a cudaStream_t, NULL = default stream); does not synchronise.
- * `arg` is pad_mode for CONVLV and ignored otherwise. */
+ * `arg` is pad_mode for CONVLV, take_sqrt for POWER and ignored otherwise. */
 int    nrb_plan_exec(nrb_plan_t plan, double *d_io, double *d_aux, double *d_out, int isign,
                      int arg, void *stream);
 int    nrb_plan_destroy(nrb_plan_t plan);

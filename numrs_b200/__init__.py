@@ -12,7 +12,8 @@ import numpy as np
 
 from . import _lib
 from ._lib import (NRB_PAD_LITERAL, NRB_PAD_NR, NrbError, KIND_FOUR1, KIND_FOURN, KIND_REALFT, KIND_RLFT3,
-                   KIND_CONVLV, KIND_CORREL)
+                   KIND_CONVLV, KIND_CORREL, KIND_CORREL_NORM, KIND_CORREL_NORM_FAST, KIND_AUTOCORREL_FAST,
+                   KIND_TWOFFT, KIND_POWER)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # NUMRS_B200_LIB may point at another build of the same CUDA library (tuning experiments)
@@ -63,7 +64,8 @@ def _convlv_raise(L, rc):
 
 def _correl_raise(L, rc):
     kind = {_lib.NRB_ERR_EMPTY_INPUT: CorrelError.EmptyInput,
-            _lib.NRB_ERR_LENGTH_MISMATCH: CorrelError.LengthMismatch}.get(rc, CorrelError.FftError)
+            _lib.NRB_ERR_LENGTH_MISMATCH: CorrelError.LengthMismatch,
+            _lib.NRB_ERR_ZERO_STDDEV: CorrelError.ZeroStdDev}.get(rc, CorrelError.FftError)
     raise CorrelError(kind, L.last_error())
 
 
@@ -117,13 +119,29 @@ def complex_to_real(complex_data):       # FFT_1.rs:202-204
     return np.asarray(complex_data, dtype=np.float64)[0::2].copy()
 
 
-def power_spectrum(complex_data):        # FFT_1.rs:218-228
-    c = np.asarray(complex_data, dtype=np.float64)
-    return c[0::2] ** 2 + c[1::2] ** 2
+def power_spectrum(complex_data, _L=None):        # FFT_1.rs:218-228 (a trailing odd element is dropped)
+    L = _L or lib()
+    rc, out = L.power_spectrum(complex_data, False)
+    _panic(L, rc)
+    return out
 
 
-def magnitude_spectrum(complex_data):    # FFT_1.rs:206-216
-    return np.sqrt(power_spectrum(complex_data))
+def magnitude_spectrum(complex_data, _L=None):    # FFT_1.rs:206-216
+    L = _L or lib()
+    rc, out = L.power_spectrum(complex_data, True)
+    _panic(L, rc)
+    return out
+
+
+# ---------------------------------------------------------------- FFT_2.rs
+def twofft(data1, data2, fft1, fft2, _L=None):
+    """FFT_2.rs:3 `twofft(data1, data2, fft1, fft2)`: asserts as FFT_2.rs:5-7; NR semantics (0-based mirror n - k)."""
+    n = data1.size
+    assert data2.size == n, "data2 length must equal data1 length"
+    assert fft1.size == 2 * n + 2, "fft1 must have length 2*n + 2"
+    assert fft2.size == 2 * n + 2, "fft2 must have length 2*n + 2"
+    L = _L or lib()
+    _panic(L, L.twofft(data1, data2, fft1, fft2))
 
 
 # ---------------------------------------------------------------- Fourn.rs / Real_FT3.rs:35
@@ -277,3 +295,30 @@ def correl_batch(data_pairs, _L=None):
 def autocorrel(data, _L=None):
     """Correlation.rs:281"""
     return correl(data, data, _L)
+
+
+def correl_normalized(data1, data2, _L=None):
+    """Correlation.rs:189: two-pass population statistics, ZeroStdDev, correl of the normalised signals."""
+    L = _L or lib()
+    rc, ans = L.correl_normalized(data1, data2, False)
+    if rc != 0:
+        _correl_raise(L, rc)
+    return ans
+
+
+def correl_normalized_fast(data1, data2, _L=None):
+    """Correlation.rs:226: single-pass statistics; n <= 32 direct lags scaled by 1/(std1 std2 n)."""
+    L = _L or lib()
+    rc, ans = L.correl_normalized(data1, data2, True)
+    if rc != 0:
+        _correl_raise(L, rc)
+    return ans
+
+
+def autocorrel_fast(data, _L=None):
+    """Correlation.rs:286: n <= 32 direct lags; else forward realft, |F|^2, inverse realft (ledger D10)."""
+    L = _L or lib()
+    rc, ans = L.autocorrel_fast(data)
+    if rc != 0:
+        _correl_raise(L, rc)
+    return ans

@@ -21,6 +21,7 @@ NRB_ERR_LENGTH_MISMATCH = -4
 NRB_ERR_INVALID_DIMS = -5
 NRB_ERR_NOT_POW2 = -6
 NRB_ERR_UNSUPPORTED = -7
+NRB_ERR_ZERO_STDDEV = -8
 NRB_ERR_CUDA = -10
 NRB_ERR_NCCL = -11
 NRB_ERR_OOM = -12
@@ -29,6 +30,7 @@ NRB_PAD_LITERAL = 0
 NRB_PAD_NR = 1
 
 KIND_FOUR1, KIND_FOURN, KIND_REALFT, KIND_RLFT3, KIND_CONVLV, KIND_CORREL = 1, 2, 3, 4, 5, 6
+KIND_CORREL_NORM, KIND_CORREL_NORM_FAST, KIND_AUTOCORREL_FAST, KIND_TWOFFT, KIND_POWER = 7, 8, 9, 10, 11
 
 # every symbol include/numrs_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
@@ -36,6 +38,7 @@ ABI_SYMBOLS = [
     "nrb_set_option", "nrb_host_alloc", "nrb_host_free",
     "nrb_four1", "nrb_four1_batch", "nrb_fourn", "nrb_realft", "nrb_realft_batch", "nrb_rlft3",
     "nrb_convlv", "nrb_convlv_batch", "nrb_correl", "nrb_correl_batch",
+    "nrb_correl_normalized", "nrb_autocorrel_fast", "nrb_twofft", "nrb_power_spectrum",
     "nrb_plan_create", "nrb_plan_workspace_bytes", "nrb_plan_num_launches", "nrb_plan_exec", "nrb_plan_destroy",
     "nrb_plan_profile", "nrb_plan_describe_launch", "nrb_fill_uniform_device",
     "nrb_slab_create", "nrb_slab_local_doubles", "nrb_slab_speq_doubles", "nrb_slab_xchg_doubles",
@@ -85,6 +88,10 @@ class Library:
                                        ctypes.POINTER(_dp)]
         L.nrb_correl.argtypes = [_dp, _sz, _dp, _sz, _dp]
         L.nrb_correl_batch.argtypes = [ctypes.POINTER(_dp), ctypes.POINTER(_dp), _sz, _sz, ctypes.POINTER(_dp)]
+        L.nrb_correl_normalized.argtypes = [_dp, _sz, _dp, _sz, ctypes.c_int, _dp]
+        L.nrb_autocorrel_fast.argtypes = [_dp, _sz, _dp]
+        L.nrb_twofft.argtypes = [_dp, _dp, _sz, _dp, _dp]
+        L.nrb_power_spectrum.argtypes = [_dp, _sz, ctypes.c_int, _dp]
         L.nrb_plan_create.argtypes = [ctypes.c_int, ctypes.POINTER(_sz), _sz, _sz, ctypes.POINTER(_vp)]
         L.nrb_plan_workspace_bytes.argtypes = [_vp]
         L.nrb_plan_workspace_bytes.restype = _sz
@@ -214,6 +221,31 @@ class Library:
         op = (_dp * max(cnt, 1))(*[_f64(o) for o in outs])
         rc = self.L.nrb_correl_batch(ap, bp, cnt, n, op)
         return rc, outs
+
+    def correl_normalized(self, d1, d2, fast=False):
+        d1 = np.ascontiguousarray(d1, dtype=np.float64)
+        d2 = np.ascontiguousarray(d2, dtype=np.float64)
+        ans = np.zeros(max(1, d1.size), dtype=np.float64)
+        a = d1 if d1.size else np.zeros(1)
+        b = d2 if d2.size else np.zeros(1)
+        rc = self.L.nrb_correl_normalized(_f64(a), d1.size, _f64(b), d2.size, int(fast), _f64(ans))
+        return rc, ans[:d1.size]
+
+    def autocorrel_fast(self, d):
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        ans = np.zeros(max(1, d.size), dtype=np.float64)
+        rc = self.L.nrb_autocorrel_fast(_f64(d if d.size else np.zeros(1)), d.size, _f64(ans))
+        return rc, ans[:d.size]
+
+    def twofft(self, d1, d2, fft1, fft2):
+        return self.L.nrb_twofft(_f64(d1), _f64(d2), d1.size, _f64(fft1), _f64(fft2))
+
+    def power_spectrum(self, c, take_sqrt=False):
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        out = np.zeros(c.size // 2, dtype=np.float64)
+        rc = self.L.nrb_power_spectrum(_f64(c if c.size else np.zeros(2)), c.size // 2, int(take_sqrt),
+                                       _f64(out if out.size else np.zeros(1)))
+        return rc, out
 
     def fill_uniform_device(self, d_ptr, seed, offset, count, stream=0):
         self.check(self.L.nrb_fill_uniform_device(d_ptr, seed, offset, count, stream or None))

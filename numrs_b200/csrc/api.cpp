@@ -165,6 +165,39 @@ int run_outofplace(int kind, const size_t *dims, size_t ndim, const double *cons
     return NRB_OK;
 }
 
+// general out-of-place call: host inputs -> io / aux, exec, selected ranges of the device `out` buffer -> host
+struct Seg { const void *host; size_t dev_off, doubles; };   // offsets / sizes in doubles
+int run_segments(int kind, const size_t *dims, size_t ndim, size_t batch, const std::vector<Seg> &io, const std::vector<Seg> &aux,
+                 size_t out_doubles, const std::vector<Seg> &outs, int isign, int arg)
+{
+    int rc = ensure_ctx();
+    if (rc) return rc;
+    auto h = cached_plan(kind, dims, ndim, batch, &rc);
+    if (!h) return rc;
+    size_t io_d = 0, aux_d = 0;
+    for (const Seg &g : io) if (g.dev_off + g.doubles > io_d) io_d = g.dev_off + g.doubles;
+    for (const Seg &g : aux) if (g.dev_off + g.doubles > aux_d) aux_d = g.dev_off + g.doubles;
+    if (t_ctx.io.ensure(io_d * sizeof(double)) != 0 || t_ctx.aux.ensure(aux_d * sizeof(double)) != 0 ||
+        t_ctx.out.ensure(out_doubles * sizeof(double)) != 0)
+        return fail(NRB_ERR_OOM, std::string("device allocation failed: ") + be_last_error());
+    void *s = t_ctx.stream;
+    for (const Seg &g : io)
+        if (be_h2d((double *)t_ctx.io.p + g.dev_off, g.host, g.doubles * sizeof(double), s) != 0) return copy_fail("host-to-device copy");
+    for (const Seg &g : aux)
+        if (be_h2d((double *)t_ctx.aux.p + g.dev_off, g.host, g.doubles * sizeof(double), s) != 0) return copy_fail("host-to-device copy");
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        rc = exec_plan(h->plan, (double *)t_ctx.io.p, (double *)t_ctx.aux.p, (double *)t_ctx.out.p, isign, arg, s);
+        if (rc == NRB_OK && be_sync(s) != 0) rc = copy_fail("kernel execution");
+    }
+    if (rc) return rc;
+    for (const Seg &g : outs)
+        if (be_d2h(const_cast<void *>(g.host), (double *)t_ctx.out.p + g.dev_off, g.doubles * sizeof(double), s) != 0)
+            return copy_fail("device-to-host copy");
+    if (be_sync(s) != 0) return copy_fail("device-to-host copy");
+    return NRB_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -421,6 +454,53 @@ int nrb_correl_batch(const double *const *data1, const double *const *data2, siz
     if (!data1 || !data2 || !ans) return fail(NRB_ERR_EMPTY_INPUT, "null pointer");
     const size_t dims[1] = {n};
     return run_outofplace(NRB_KIND_CORREL, dims, 1, data1, data2, count, n, ans, count, n, 1, 0);
+}
+
+// ------------------------------------------------------------------ "next" rows
+int nrb_correl_normalized(const double *data1, size_t n1, const double *data2, size_t n2, int fast, double *ans)
+{
+    // Correlation.rs:190-196 / :227-233 check order
+    if (n1 == 0) return fail(NRB_ERR_EMPTY_INPUT, "Input arrays cannot be empty");
+    if (n2 != n1) return fail(NRB_ERR_LENGTH_MISMATCH, "Input arrays must have the same length");
+    if (n1 > 32 && !is_pow2(n1)) return fail(NRB_ERR_NOT_POW2, "correl: n > 32 must be a power of two");
+    if (!data1 || !data2 || !ans) return fail(NRB_ERR_EMPTY_INPUT, "null pointer");
+    const size_t dims[1] = {n1};
+    double stats[4] = {0, 0, 0, 0};   // (mean1, std1, mean2, std2)
+    // the answers are only copied back when both standard deviations are non-zero: two-step read-back
+    int rc = run_segments(fast ? NRB_KIND_CORREL_NORM_FAST : NRB_KIND_CORREL_NORM, dims, 1, 1, {{data1, 0, n1}}, {{data2, 0, n1}},
+                          4 + n1, {{stats, 0, 4}}, 1, 0);
+    if (rc) return rc;
+    if (stats[1] == 0.0 || stats[3] == 0.0) return fail(NRB_ERR_ZERO_STDDEV, "Zero standard deviation");   // Correlation.rs:214-216
+    if (be_d2h(ans, (double *)t_ctx.out.p + 4, n1 * sizeof(double), t_ctx.stream) != 0 || be_sync(t_ctx.stream) != 0)
+        return copy_fail("device-to-host copy");
+    return NRB_OK;
+}
+
+int nrb_autocorrel_fast(const double *data, size_t n, double *ans)
+{
+    if (n == 0) return fail(NRB_ERR_EMPTY_INPUT, "Input arrays cannot be empty");                 // Correlation.rs:288-290
+    if (n > 32 && !is_pow2(n)) return fail(NRB_ERR_NOT_POW2, "correl: n > 32 must be a power of two");
+    if (!data || !ans) return fail(NRB_ERR_EMPTY_INPUT, "null pointer");
+    const size_t dims[1] = {n};
+    return run_segments(NRB_KIND_AUTOCORREL_FAST, dims, 1, 1, {{data, 0, n}}, {}, n, {{ans, 0, n}}, 1, 0);
+}
+
+int nrb_twofft(const double *data1, const double *data2, size_t n, double *fft1, double *fft2)
+{
+    if (n == 0) return fail(NRB_ERR_EMPTY_INPUT, "twofft: empty input");
+    if (!is_pow2(n)) return fail(NRB_ERR_NOT_POW2, "twofft: n must be a power of two");
+    if (!data1 || !data2 || !fft1 || !fft2) return fail(NRB_ERR_EMPTY_INPUT, "null pointer");
+    const size_t dims[1] = {n};
+    const size_t per = 2 * n + 2;   // FFT_2.rs:6-7
+    return run_segments(NRB_KIND_TWOFFT, dims, 1, 1, {{data1, 0, n}}, {{data2, 0, n}}, 2 * per, {{fft1, 0, per}, {fft2, per, per}}, 1, 0);
+}
+
+int nrb_power_spectrum(const double *complex_data, size_t npoints, int take_sqrt, double *out)
+{
+    if (npoints == 0) return NRB_OK;                           // FFT_1.rs:206-228: empty in, empty out
+    if (!complex_data || !out) return fail(NRB_ERR_EMPTY_INPUT, "null pointer");
+    const size_t dims[1] = {npoints};
+    return run_segments(NRB_KIND_POWER, dims, 1, 1, {{complex_data, 0, 2 * npoints}}, {}, npoints, {{out, 0, npoints}}, 1, take_sqrt ? 1 : 0);
 }
 
 } // extern "C"

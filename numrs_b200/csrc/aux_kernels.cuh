@@ -8,6 +8,8 @@
 // Bodies are written grid-stride over a flat item index so the CUDA wrapper and the host
 // emulation used by the tests share them.
 #pragma once
+#include <math.h>
+
 #include "fft_pass.cuh"
 
 namespace nrb {
@@ -61,11 +63,15 @@ NRB_DEV void aux_spectral(const AuxParams &A, u64 gtid, u64 gthreads)
     for (u64 it = gtid; it < items; it += gthreads) {
         const u64 k = it % half, sig = it / half;
         const double2 d = NRB_LDS(A.a + (i64)sig * A.a_stride + (i64)k);
-        const double2 r = A.b_stride ? NRB_LDS(A.b + (i64)sig * A.b_stride + (i64)k) : NRB_LDG(A.b + (i64)k);
+        double2 r = d;
+        if (A.op != SPEC_AUTOCORREL) r = A.b_stride ? NRB_LDS(A.b + (i64)sig * A.b_stride + (i64)k) : NRB_LDG(A.b + (i64)k);
         double2 o;
         if (A.op == SPEC_CONV_MUL) {
             if (k == 0) o = make_double2(d.x * r.x * inv, d.y * r.y * inv);
             else o = make_double2((d.x * r.x - d.y * r.y) * inv, (d.x * r.y + d.y * r.x) * inv);
+        } else if (A.op == SPEC_AUTOCORREL) {   // |F|^2 (Correlation.rs:306-313): DC and Nyquist real squares
+            if (k == 0) o = make_double2(d.x * d.x * inv, d.y * d.y * inv);
+            else o = make_double2((d.x * d.x + d.y * d.y) * inv, 0.0);
         } else if (A.op == SPEC_CORREL) {
             if (k == 0) o = make_double2(d.x * r.x * inv, d.y * r.y * inv);
             else o = make_double2((d.x * r.x + d.y * r.y) * inv, (d.y * r.x - d.x * r.y) * inv);
@@ -111,31 +117,34 @@ NRB_DEV void aux_spectral_z(const AuxParams &A, u64 gtid, u64 gthreads)
     const u64 half = N >= 2 ? N / 2 : 1;
     const u64 items = A.count * half;
     const double inv = 1.0 / (double)N;
-    const bool b_raw = A.b_stride != 0;
+    const bool self = A.op == SPEC_AUTOCORREL;      // second operand = the first one (|F|^2)
+    const bool b_raw = A.b_stride != 0 && !self;
+    const int op = self ? SPEC_CORREL : A.op;
     for (u64 it = gtid; it < items; it += gthreads) {
         const u64 k = it % half, sig = it / half;
         const double2 *za = A.a + (i64)sig * A.a_stride;
-        const double2 *zb = A.b + (i64)sig * A.b_stride;
+        const double2 *zb = self ? za : A.b + (i64)sig * A.b_stride;
         double2 *out = A.out + (i64)sig * A.out_stride;
         if (k == 0) {
             const double2 a0 = NRB_LDS(za);
-            double2 r0 = b_raw ? NRB_LDS(zb) : NRB_LDG(zb);
-            if (b_raw) r0 = make_double2(r0.x + r0.y, r0.x - r0.y);       // (B_0, B_N)
-            const double g0 = spectral_op_real(A.op, a0.x + a0.y, r0.x, inv);
-            const double gn = spectral_op_real(A.op, a0.x - a0.y, r0.y, inv);
+            double2 r0 = self ? a0 : (b_raw ? NRB_LDS(zb) : NRB_LDG(zb));
+            if (b_raw || self) r0 = make_double2(r0.x + r0.y, r0.x - r0.y);       // (B_0, B_N)
+            const double g0 = spectral_op_real(op, a0.x + a0.y, r0.x, inv);
+            const double gn = spectral_op_real(op, a0.x - a0.y, r0.y, inv);
             out[0] = make_double2(0.5 * (g0 + gn), 0.5 * (g0 - gn));
             if (N >= 2) {   // middle bin: untangling is the identity there
                 const double2 am = NRB_LDS(za + N / 2);
-                const double2 rm = b_raw ? NRB_LDS(zb + N / 2) : NRB_LDG(zb + N / 2);
-                out[N / 2] = spectral_op(A.op, am, rm, inv);
+                const double2 rm = self ? am : (b_raw ? NRB_LDS(zb + N / 2) : NRB_LDG(zb + N / 2));
+                out[N / 2] = spectral_op(op, am, rm, inv);
             }
         } else {
             const double2 t = two_level_tw(A.rtw_lo, A.rtw_hi, A.rtw_h, k);
             double2 fa, fm, ra, rm;
             untangle_pair<1>(NRB_LDS(za + k), NRB_LDS(za + (N - k)), t, fa, fm);
-            if (b_raw) untangle_pair<1>(NRB_LDS(zb + k), NRB_LDS(zb + (N - k)), t, ra, rm);
+            if (self) { ra = fa; rm = fm; }
+            else if (b_raw) untangle_pair<1>(NRB_LDS(zb + k), NRB_LDS(zb + (N - k)), t, ra, rm);
             else { ra = NRB_LDG(zb + k); rm = NRB_LDG(zb + (N - k)); }
-            const double2 ga = spectral_op(A.op, fa, ra, inv), gm = spectral_op(A.op, fm, rm, inv);
+            const double2 ga = spectral_op(op, fa, ra, inv), gm = spectral_op(op, fm, rm, inv);
             double2 oa, ob;
             untangle_pair<-1>(ga, gm, t, oa, ob);
             out[k] = oa;
@@ -171,7 +180,7 @@ NRB_DEV void aux_pad_response(const AuxParams &A, u64 gtid, u64 gthreads)
 NRB_DEV void aux_correl_direct(const AuxParams &A, u64 gtid, u64 gthreads)
 {
     const double *d1 = reinterpret_cast<const double *>(A.a);
-    const double *d2 = reinterpret_cast<const double *>(A.b);
+    const double *d2 = reinterpret_cast<const double *>(A.b) + A.m;   // m: extra offset of b in doubles
     double *out = reinterpret_cast<double *>(A.out);
     const u64 n = A.n, items = A.count * n;
     for (u64 it = gtid; it < items; it += gthreads) {
@@ -195,6 +204,130 @@ NRB_DEV void aux_fill(const AuxParams &A, u64 gtid, u64 gthreads)
         x = x ^ (x >> 31);
         out[i] = (double)(x >> 11) * (1.0 / 4503599627370496.0) - 1.0;
     }
+}
+
+
+// ------------------------------------------------------------------ "next" rows
+// Signals of a two-input launch: s < count/2 comes from a, the rest from b (b == nullptr: all from a).
+NRB_DEV const double *signal_src(const AuxParams &A, u64 s)
+{
+    const double *a = reinterpret_cast<const double *>(A.a), *b = reinterpret_cast<const double *>(A.b);
+    if (!b) return a + (i64)s * A.a_stride;
+    const u64 half = A.count / 2;
+    return s < half ? a + (i64)s * A.a_stride : b + (i64)(s - half) * A.b_stride;
+}
+
+// Deterministic strided partial sums: accumulator (s, c), c < C = A.m, adds the terms i = c, c + C, ... of
+// signal s, so consecutive threads read consecutive addresses.  Terms (op): RED_SUM_SQ (x, x^2) of raw data
+// (Correlation.rs:236-239), RED_CENTERED_SQ ((x - mean)^2, 0) with the mean from the stats array in `speq`
+// (Correlation.rs:207), RED_PARTIALS a previous level's double2 partials.  out[s*C + c].  items: count * C.
+NRB_DEV void aux_reduce(const AuxParams &A, u64 gtid, u64 gthreads)
+{
+    const u64 C = A.m, items = A.count * C;
+    for (u64 it = gtid; it < items; it += gthreads) {
+        const u64 c = it % C, s = it / C;
+        double sx = 0.0, sy = 0.0;
+        if (A.op == RED_PARTIALS) {
+            const double2 *p = A.a + (i64)(s * A.n);
+            for (u64 i = c; i < A.n; i += C) { const double2 v = p[i]; sx += v.x; sy += v.y; }
+        } else {
+            const double *x = signal_src(A, s);
+            if (A.op == RED_SUM_SQ) {
+                for (u64 i = c; i < A.n; i += C) { const double v = x[i]; sx += v; sy += v * v; }
+            } else {
+                const double mean = A.speq[s].x;
+                for (u64 i = c; i < A.n; i += C) { const double v = x[i] - mean; sx += v * v; }
+            }
+        }
+        A.out[it] = make_double2(sx, sy);
+    }
+}
+
+// stats[s] = (mean, std) from the m partials of signal s; n = signal length.  items: count.
+NRB_DEV void aux_stats_final(const AuxParams &A, u64 gtid, u64 gthreads)
+{
+    for (u64 s = gtid; s < A.count; s += gthreads) {
+        double sx = 0.0, sy = 0.0;
+        for (u64 j = 0; j < A.m; ++j) { const double2 v = A.a[s * A.m + j]; sx += v.x; sy += v.y; }
+        const double n = (double)A.n;
+        double2 st = A.out[s];
+        if (A.op == STATS_FAST) { st.x = sx / n; st.y = sqrt(sy / n - st.x * st.x); }   // Correlation.rs:241-244
+        else if (A.op == STATS_MEAN) { st.x = sx / n; st.y = 0.0; }                     // Correlation.rs:200
+        else st.y = sqrt(sx / n);                                                       // Correlation.rs:207
+        A.out[s] = st;
+    }
+}
+
+// out[s][i] = (x[s][i] - mean_s) / std_s, stats in `speq`.  items: count * n.
+NRB_DEV void aux_normalize(const AuxParams &A, u64 gtid, u64 gthreads)
+{
+    double *out = reinterpret_cast<double *>(A.out);
+    const u64 items = A.count * A.n;
+    for (u64 it = gtid; it < items; it += gthreads) {
+        const u64 i = it % A.n, s = it / A.n;
+        const double2 st = A.speq[s];
+        out[(i64)s * A.out_stride + (i64)i] = (signal_src(A, s)[i] - st.x) / st.y;
+    }
+}
+
+// out[i] = |a[i]|^2 (op 0, FFT_1.rs:218-228) or |a[i]| (op 1, FFT_1.rs:206-216).  items: n complex points.
+NRB_DEV void aux_power(const AuxParams &A, u64 gtid, u64 gthreads)
+{
+    double *out = reinterpret_cast<double *>(A.out);
+    for (u64 i = gtid; i < A.n; i += gthreads) {
+        const double2 z = NRB_LDS(A.a + i);
+        const double p = z.x * z.x + z.y * z.y;
+        out[i] = A.op ? sqrt(p) : p;
+    }
+}
+
+// twofft packing (FFT_2.rs:33-37): out[s][j] = (d1[s][j], d2[s][j]).  Strides of a / b in doubles, of out in
+// complex elements.  items: count * n.
+NRB_DEV void aux_pack2(const AuxParams &A, u64 gtid, u64 gthreads)
+{
+    const double *d1 = reinterpret_cast<const double *>(A.a), *d2 = reinterpret_cast<const double *>(A.b);
+    const u64 items = A.count * A.n;
+    for (u64 it = gtid; it < items; it += gthreads) {
+        const u64 j = it % A.n, s = it / A.n;
+        A.out[(i64)s * A.out_stride + (i64)j] = make_double2(d1[(i64)s * A.a_stride + (i64)j], d2[(i64)s * A.b_stride + (i64)j]);
+    }
+}
+
+// twofft separation (FFT_2.rs:53-90 with the 0-based mirror n - k, ledger D9): a = transform of the packed
+// signal (n complex per signal, stride a_stride), out = fft1, speq = fft2 (both stride out_stride >= n + 1;
+// element n is the reference's two extra doubles, FFT_2.rs:6-7, set to 0).  a may alias out when the strides
+// agree: item k owns bins k and n - k.  items: count * (n/2 + 1).
+NRB_DEV void aux_twofft_split(const AuxParams &A, u64 gtid, u64 gthreads)
+{
+    const u64 n = A.n, per = n / 2 + 1, items = A.count * per;
+    for (u64 it = gtid; it < items; it += gthreads) {
+        const u64 k = it % per, s = it / per;
+        const double2 *f = A.a + (i64)s * A.a_stride;
+        double2 *f1 = A.out + (i64)s * A.out_stride, *f2 = A.speq + (i64)s * A.out_stride;
+        if (k == 0) {
+            const double2 z = f[0];
+            f1[0] = make_double2(z.x, 0.0);
+            f2[0] = make_double2(z.y, 0.0);
+            f1[n] = make_double2(0.0, 0.0);
+            f2[n] = make_double2(0.0, 0.0);
+        } else {
+            const u64 m = n - k;
+            const double2 a = f[k], b = f[m];
+            const double rep = 0.5 * (a.x + b.x), rem = 0.5 * (a.x - b.x);
+            const double aip = 0.5 * (a.y + b.y), aim = 0.5 * (a.y - b.y);
+            f1[k] = make_double2(rep, aim);
+            f2[k] = make_double2(aip, -rem);
+            if (m != k) { f1[m] = make_double2(rep, -aim); f2[m] = make_double2(aip, rem); }
+        }
+    }
+}
+
+// out[i] *= 1/m (the 1/n of correl_normalized_fast's direct branch, Correlation.rs:252).  items: n doubles.
+NRB_DEV void aux_scale(const AuxParams &A, u64 gtid, u64 gthreads)
+{
+    double *out = reinterpret_cast<double *>(A.out);
+    const double f = 1.0 / (double)A.m;
+    for (u64 i = gtid; i < A.n; i += gthreads) out[i] *= f;
 }
 
 // Cross-GPU barrier of the fused slab exchange, without a collective: after its stage-0 kernels (whose
@@ -241,6 +374,13 @@ NRB_DEV void aux_body(const AuxParams &A, u64 gtid, u64 gthreads)
     case AUX_SPECTRAL_Z: aux_spectral_z(A, gtid, gthreads); break;
     case AUX_SIGNAL: aux_signal(A, gtid, gthreads); break;
     case AUX_WAIT: aux_wait(A, gtid, gthreads); break;
+    case AUX_REDUCE: aux_reduce(A, gtid, gthreads); break;
+    case AUX_STATS_FINAL: aux_stats_final(A, gtid, gthreads); break;
+    case AUX_NORMALIZE: aux_normalize(A, gtid, gthreads); break;
+    case AUX_POWER: aux_power(A, gtid, gthreads); break;
+    case AUX_PACK2: aux_pack2(A, gtid, gthreads); break;
+    case AUX_TWOFFT_SPLIT: aux_twofft_split(A, gtid, gthreads); break;
+    case AUX_SCALE: aux_scale(A, gtid, gthreads); break;
     default: aux_correl_direct(A, gtid, gthreads); break;
     }
 }

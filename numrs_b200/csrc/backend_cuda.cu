@@ -100,6 +100,11 @@ int be_launch_aux(const AuxParams &a, void *stream)
     case AUX_FILL: items = a.n; break;
     case AUX_SPECTRAL_Z: items = a.count * (a.n >= 8 ? a.n / 4 : 1); break;
     case AUX_SIGNAL: case AUX_WAIT: items = a.count; break;
+    case AUX_REDUCE: items = a.count * a.m; break;
+    case AUX_STATS_FINAL: items = a.count; break;
+    case AUX_NORMALIZE: case AUX_PACK2: items = a.count * a.n; break;
+    case AUX_POWER: case AUX_SCALE: items = a.n; break;
+    case AUX_TWOFFT_SPLIT: items = a.count * (a.n / 2 + 1); break;
     default: items = a.count * a.n; break;
     }
     if (items == 0) return 0;

@@ -225,9 +225,22 @@ enum AuxKind {
     AUX_FILL = 4,         // synthetic input generator: n doubles, seed in m, offset in count
     AUX_SPECTRAL_Z = 5,   // untangle + spectral op + inverse untangle in one pass on raw c2c outputs
     AUX_SIGNAL = 6,       // slab exchange barrier: publish `epoch` (in m) to slot `rank` (in n) of every peer's flag array
-    AUX_WAIT = 7          // slab exchange barrier: spin until the first `count` local flags are >= epoch (in m)
+    AUX_WAIT = 7,         // slab exchange barrier: spin until the first `count` local flags are >= epoch (in m)
+    // ---- "next" rows of SURVEY.md 8f (callers on either side of the hot path) ----
+    AUX_REDUCE = 8,       // strided partial sums: m accumulators per signal (see aux_reduce)
+    AUX_STATS_FINAL = 9,  // partial sums -> (mean, std) per signal (Correlation.rs:200-212 / :236-244)
+    AUX_NORMALIZE = 10,   // (x - mean) / std (Correlation.rs:219-220 / :265-266)
+    AUX_POWER = 11,       // |z|^2 or |z| per complex point (FFT_1.rs:206-228)
+    AUX_PACK2 = 12,       // twofft: two real signals -> one complex signal (FFT_2.rs:33-37)
+    AUX_TWOFFT_SPLIT = 13,// twofft: separate the two spectra (FFT_2.rs:53-90, mirror n-k)
+    AUX_SCALE = 14,       // out[i] *= 1/n (correl_normalized_fast direct branch, Correlation.rs:252)
+    AUX_COSFT = 15,       // cosft1 / cosft2 / sinft pre- and post-processing around realft (Cos_FT.rs, Cos_FT2.rs)
+    AUX_SCAN = 16,        // running sums of the odd (cosft1) / even-from-the-top (cosft2) outputs, three-phase
+    AUX_KIND_COUNT = 17
 };
-enum SpectralOp { SPEC_CONV_MUL = 0, SPEC_CONV_DIV = 1, SPEC_CORREL = 2 };
+enum SpectralOp { SPEC_CONV_MUL = 0, SPEC_CONV_DIV = 1, SPEC_CORREL = 2, SPEC_AUTOCORREL = 3 };
+enum ReduceMode { RED_SUM_SQ = 0, RED_CENTERED_SQ = 1, RED_PARTIALS = 2 };
+enum StatsMode { STATS_FAST = 0, STATS_MEAN = 1, STATS_STD = 2 };
 
 struct AuxParams {
     int kind;

@@ -559,43 +559,165 @@ int build_convlv(Plan &pl, Builder &B, int dir)
     return B.rc;
 }
 
-// correl: dims = {n}.  io = data1, aux = data2 (read only), out = answers.
-int build_correl(Plan &pl, Builder &B)
+Step make_aux(int kind, int op, BufRef a, BufRef b, BufRef out, BufRef stats, u64 n, u64 m, u64 count, i64 a_stride,
+              i64 b_stride, i64 out_stride)
 {
-    const u64 n = pl.dims[0];
-    if (n <= 32) {   // Correlation.rs:19-21 direct branch (linear lags)
-        Step st;
-        st.is_aux = true;
-        memset(&st.ap, 0, sizeof(st.ap));
-        st.ap.kind = AUX_CORREL_DIRECT;
-        st.ap.n = n; st.ap.count = pl.batch;
-        st.ap.a_stride = st.ap.b_stride = st.ap.out_stride = (i64)n;   // in doubles
-        st.in = BufRef(BUF_IO, 0); st.b = BufRef(BUF_AUX, 0); st.out = BufRef(BUF_OUT, 0);
-        B.prog->steps.push_back(st);
-        return B.rc;
-    }
+    Step st;
+    st.is_aux = true;
+    memset(&st.ap, 0, sizeof(st.ap));
+    st.ap.kind = kind; st.ap.op = op;
+    st.ap.n = n; st.ap.m = m; st.ap.count = count;
+    st.ap.a_stride = a_stride; st.ap.b_stride = b_stride; st.ap.out_stride = out_stride;
+    st.in = a; st.b = b; st.out = out; st.speq = stats;
+    return st;
+}
+
+Step make_correl_direct(BufRef a, BufRef b, BufRef out, u64 n, u64 count)
+{
+    // Correlation.rs:19-21 direct branch (linear lags); strides in doubles
+    return make_aux(AUX_CORREL_DIRECT, 0, a, b, out, BufRef(), n, 0, count, (i64)n, (i64)n, (i64)n);
+}
+
+// FFT correlation (n > 32) of `cnt` signal pairs: a, b read only (b ignored for SPEC_AUTOCORREL), F2 and T scratch
+// of cnt * n/2 complex each.  Correlation.rs:23-33 with NR's correl for the placeholder (ledger D7).
+void emit_correl_group(Builder &B, BufRef a, BufRef b, BufRef out, BufRef F2, BufRef T, u64 cnt, u64 n, int op)
+{
     const u64 N = n / 2;
     const int p = ilog2((size_t)N);
+    const bool two = op != SPEC_AUTOCORREL;
+    if (real_needs_separate_untangle(p)) {
+        emit_axis(B, a, out, T, cnt, 0, cnt, p, 1, +1);
+        if (two) emit_axis(B, b, F2, T, cnt, 0, cnt, p, 1, +1);
+        B.prog->steps.push_back(make_spectral_z(op, out, two ? F2 : out, out, n, cnt, (i64)N, (i64)N, (i64)N));
+        emit_axis(B, out, out, T, cnt, 0, cnt, p, 1, -1);
+    } else {
+        emit_real(B, a, out, T, 0, cnt, p, +1, REAL_PACKED, BufRef());
+        if (two) emit_real(B, b, F2, T, 0, cnt, p, +1, REAL_PACKED, BufRef());
+        B.prog->steps.push_back(make_spectral(op, out, two ? F2 : out, out, n, cnt, (i64)N, (i64)N, (i64)N));
+        emit_real(B, out, out, T, 0, cnt, p, -1, REAL_PACKED, BufRef());
+    }
+}
+
+u64 correl_group_size(const Plan &pl, u64 n)
+{
     u64 gs = tunables().batch_group_bytes / (n * 8);
     if (gs < 1) gs = 1;
     if (gs > pl.batch) gs = pl.batch;
+    return gs;
+}
+
+// correl: dims = {n}.  io = data1, aux = data2 (read only), out = answers.
+// autocorrel_fast (Correlation.rs:286-323, ledger D10): the same with one forward transform and |F|^2.
+int build_correl(Plan &pl, Builder &B, int op)
+{
+    const u64 n = pl.dims[0];
+    const BufRef IO(BUF_IO, 0), AUXB(op == SPEC_AUTOCORREL ? BUF_IO : BUF_AUX, 0), OUT(BUF_OUT, 0);
+    if (n <= 32) {
+        B.prog->steps.push_back(make_correl_direct(IO, AUXB, OUT, n, pl.batch));
+        return B.rc;
+    }
+    const u64 N = n / 2, gs = correl_group_size(pl, n);
     const BufRef F2(BUF_WS, 0), T(BUF_WS, (i64)(gs * N));
     B.need_ws((size_t)(gs * N));
     for (u64 b0 = 0; b0 < pl.batch; b0 += gs) {
         const u64 b1 = (b0 + gs < pl.batch) ? b0 + gs : pl.batch;
-        const BufRef a(BUF_IO, (i64)(b0 * N)), b(BUF_AUX, (i64)(b0 * N)), out(BUF_OUT, (i64)(b0 * N));
-        if (real_needs_separate_untangle(p)) {
-            emit_axis(B, a, out, T, b1 - b0, 0, b1 - b0, p, 1, +1);
-            emit_axis(B, b, F2, T, b1 - b0, 0, b1 - b0, p, 1, +1);
-            B.prog->steps.push_back(make_spectral_z(SPEC_CORREL, out, F2, out, n, b1 - b0, (i64)N, (i64)N, (i64)N));
-            emit_axis(B, out, out, T, b1 - b0, 0, b1 - b0, p, 1, -1);
-        } else {
-            emit_real(B, a, out, T, 0, b1 - b0, p, +1, REAL_PACKED, BufRef());
-            emit_real(B, b, F2, T, 0, b1 - b0, p, +1, REAL_PACKED, BufRef());
-            B.prog->steps.push_back(make_spectral(SPEC_CORREL, out, F2, out, n, b1 - b0, (i64)N, (i64)N, (i64)N));
-            emit_real(B, out, out, T, 0, b1 - b0, p, -1, REAL_PACKED, BufRef());
-        }
+        emit_correl_group(B, IO + (i64)(b0 * N), AUXB + (i64)(b0 * N), OUT + (i64)(b0 * N), F2, T, b1 - b0, n, op);
     }
+    return B.rc;
+}
+
+// (mean, std) of S signals of n doubles (`a`: the first S/2 or all of them, `b`: the second half or none)
+// into stats[S] (double2), by deterministic strided partial sums in two or three levels.
+void emit_stats(Builder &B, BufRef a, BufRef b, BufRef stats, BufRef P0, BufRef P1, u64 S, u64 n, u64 C0, u64 C1, bool fast)
+{
+    auto level = [&](int red_op, int stats_op) {
+        B.prog->steps.push_back(make_aux(AUX_REDUCE, red_op, a, b, P0, stats, n, C0, S, (i64)n, (i64)n, 0));
+        if (C1) {
+            B.prog->steps.push_back(make_aux(AUX_REDUCE, RED_PARTIALS, P0, BufRef(), P1, BufRef(), C0, C1, S, 0, 0, 0));
+            B.prog->steps.push_back(make_aux(AUX_STATS_FINAL, stats_op, P1, BufRef(), stats, BufRef(), n, C1, S, 0, 0, 0));
+        } else {
+            B.prog->steps.push_back(make_aux(AUX_STATS_FINAL, stats_op, P0, BufRef(), stats, BufRef(), n, C0, S, 0, 0, 0));
+        }
+    };
+    if (fast) level(RED_SUM_SQ, STATS_FAST);                        // Correlation.rs:236-244 (single pass)
+    else { level(RED_SUM_SQ, STATS_MEAN); level(RED_CENTERED_SQ, STATS_STD); }   // Correlation.rs:199-212 (two passes)
+}
+
+// correl_normalized (Correlation.rs:189-223) / correl_normalized_fast (:226-270): dims = {n}.
+// io = data1, aux = data2 (read only); out = [2*batch] (mean, std) pairs -- data1's signals first, then data2's;
+// the host entry point turns a zero std into CorrelError::ZeroStdDev -- followed by batch x n answers.
+int build_correl_norm(Plan &pl, Builder &B, bool fast)
+{
+    const u64 n = pl.dims[0], S = 2 * pl.batch;
+    const BufRef IO(BUF_IO, 0), AUXB(BUF_AUX, 0), STATS(BUF_OUT, 0), ANS(BUF_OUT, (i64)S);
+    const u64 C0 = n <= 64 ? 1 : (n / 64 < 16384 ? n / 64 : 16384);
+    const u64 C1 = C0 > 256 ? 128 : 0;
+    i64 off = 0;
+    const BufRef P0(BUF_WS, off); off += (i64)(S * C0);
+    const BufRef P1(BUF_WS, off); off += (i64)(S * C1);
+    emit_stats(B, IO, AUXB, STATS, P0, P1, S, n, C0, C1, fast);
+    if (n <= 32) {
+        // normalise both inputs (strides in doubles), direct lags; the fast variant's own branch divides by n
+        const i64 half = (i64)((pl.batch * n + 1) / 2);
+        const BufRef NA(BUF_WS, off), NB = NA + half;
+        B.need_ws((size_t)(off + 2 * half));
+        B.prog->steps.push_back(make_aux(AUX_NORMALIZE, 0, IO, AUXB, NA, STATS, n, 0, S, (i64)n, (i64)n, (i64)n));
+        // the second half of the signals lands at NA + batch*n doubles: keep NB there (may be odd -> address in doubles)
+        Step cd = make_correl_direct(NA, NA, ANS, n, pl.batch);
+        cd.ap.m = pl.batch * n;     // b = a + m doubles (see aux_correl_direct)
+        B.prog->steps.push_back(cd);
+        if (fast) B.prog->steps.push_back(make_aux(AUX_SCALE, 0, BufRef(), BufRef(), ANS, BufRef(), pl.batch * n, n, 1, 0, 0, 0));
+        (void)NB;
+        return B.rc;
+    }
+    const u64 N = n / 2, gs = correl_group_size(pl, n);
+    const BufRef NA(BUF_WS, off); off += (i64)(gs * N);
+    const BufRef NB(BUF_WS, off); off += (i64)(gs * N);
+    const BufRef F2(BUF_WS, off); off += (i64)(gs * N);
+    const BufRef T(BUF_WS, off);
+    B.need_ws((size_t)off);
+    for (u64 b0 = 0; b0 < pl.batch; b0 += gs) {
+        const u64 b1 = (b0 + gs < pl.batch) ? b0 + gs : pl.batch, cnt = b1 - b0;
+        // two launches (one per input) so a group's signals and their stats are contiguous ranges
+        B.prog->steps.push_back(make_aux(AUX_NORMALIZE, 0, IO + (i64)(b0 * N), BufRef(), NA, STATS + (i64)b0, n, 0, cnt, (i64)n, 0, (i64)n));
+        B.prog->steps.push_back(make_aux(AUX_NORMALIZE, 0, AUXB + (i64)(b0 * N), BufRef(), NB, STATS + (i64)(pl.batch + b0), n, 0, cnt, (i64)n, 0, (i64)n));
+        emit_correl_group(B, NA, NB, ANS + (i64)(b0 * N), F2, T, cnt, n, SPEC_CORREL);
+    }
+    return B.rc;
+}
+
+// twofft (FFT_2.rs:3-17, ledger D9): dims = {n}.  io = data1, aux = data2 (n doubles each, read only);
+// out = fft1 [batch][n + 1] complex followed by fft2 [batch][n + 1] complex.
+int build_twofft(Plan &pl, Builder &B)
+{
+    const u64 n = pl.dims[0], per = n + 1;
+    const BufRef F1(BUF_OUT, 0), F2(BUF_OUT, (i64)(pl.batch * per));
+    const int p = ilog2((size_t)n);
+    // short lines: transform in place in fft1 (lines n + 1 complex apart); multi-step transforms need densely
+    // packed lines and go through the workspace
+    const bool dense = p > tunables().row_max_log2;
+    const BufRef D = dense ? BufRef(BUF_WS, 0) : F1, T(BUF_WS, (i64)(pl.batch * n));
+    const i64 ds = dense ? (i64)n : (i64)per;
+    if (dense) B.need_ws((size_t)(pl.batch * n));
+    B.prog->steps.push_back(make_aux(AUX_PACK2, 0, BufRef(BUF_IO, 0), BufRef(BUF_AUX, 0), D, BufRef(), n, 0, pl.batch, (i64)n, (i64)n, ds));
+    if (dense) {
+        emit_axis(B, D, D, T, pl.batch, 0, pl.batch, p, 1, +1);                  // FFT_2.rs:13 four1(fft1, n, 1)
+    } else if (p >= 1) {
+        AxisMap map;
+        map.on = true; map.s0 = (i64)per; map.es = 1; map.eshift = 30; map.es_hi = 0;
+        emit_axis(B, D, D, T, pl.batch, 0, pl.batch, p, 1, +1, &map, &map);
+    }
+    B.prog->steps.push_back(make_aux(AUX_TWOFFT_SPLIT, 0, D, BufRef(), F1, F2, n, 0, pl.batch, ds, 0, (i64)per));
+    return B.rc;
+}
+
+// power / magnitude spectrum (FFT_1.rs:206-228): dims = {npoints}; io = complex points, out = npoints doubles;
+// exec's `arg` = 1 takes the square root.
+int build_power(Plan &pl, Builder &B)
+{
+    Step st = make_aux(AUX_POWER, 0, BufRef(BUF_IO, 0), BufRef(), BufRef(BUF_OUT, 0), BufRef(), pl.dims[0] * pl.batch, 0, 1, 0, 0, 0);
+    st.patch_pad_mode = true;
+    B.prog->steps.push_back(st);
     return B.rc;
 }
 
@@ -638,6 +760,19 @@ int build_plan(Plan &pl, int kind, const size_t *dims, size_t ndim, size_t batch
         if (ndim != 1 || dims[0] == 0) { set_error("Input arrays cannot be empty"); return NRB_ERR_EMPTY_INPUT; }
         if (dims[0] > 32 && !is_pow2(dims[0])) { set_error("correl: n > 32 must be a power of two"); return NRB_ERR_NOT_POW2; }
         break;
+    case NRB_KIND_CORREL_NORM:
+    case NRB_KIND_CORREL_NORM_FAST:
+    case NRB_KIND_AUTOCORREL_FAST:
+        if (ndim != 1 || dims[0] == 0) { set_error("Input arrays cannot be empty"); return NRB_ERR_EMPTY_INPUT; }
+        if (dims[0] > 32 && !is_pow2(dims[0])) { set_error("correl: n > 32 must be a power of two"); return NRB_ERR_NOT_POW2; }
+        break;
+    case NRB_KIND_TWOFFT:
+        if (ndim != 1 || dims[0] == 0) { set_error("twofft: n must be >= 1"); return NRB_ERR_INVALID_DIMS; }
+        if ((rc = check_pow2_dims(dims, 1))) return rc;
+        break;
+    case NRB_KIND_POWER:
+        if (ndim != 1 || dims[0] == 0) { set_error("power spectrum: empty input"); return NRB_ERR_EMPTY_INPUT; }
+        break;
     default:
         set_error("unknown plan kind");
         return NRB_ERR_INVALID_DIMS;
@@ -653,7 +788,12 @@ int build_plan(Plan &pl, int kind, const size_t *dims, size_t ndim, size_t batch
         case NRB_KIND_REALFT: rc = build_realft(pl, B, dir); break;
         case NRB_KIND_RLFT3: rc = build_rlft3(pl, B, dir); break;
         case NRB_KIND_CONVLV: rc = build_convlv(pl, B, dir); break;
-        case NRB_KIND_CORREL: rc = build_correl(pl, B); break;
+        case NRB_KIND_CORREL: rc = build_correl(pl, B, SPEC_CORREL); break;
+        case NRB_KIND_AUTOCORREL_FAST: rc = build_correl(pl, B, SPEC_AUTOCORREL); break;
+        case NRB_KIND_CORREL_NORM: rc = build_correl_norm(pl, B, false); break;
+        case NRB_KIND_CORREL_NORM_FAST: rc = build_correl_norm(pl, B, true); break;
+        case NRB_KIND_TWOFFT: rc = build_twofft(pl, B); break;
+        case NRB_KIND_POWER: rc = build_power(pl, B); break;
         }
         if (rc != NRB_OK) { set_error("shape not supported by this build"); return rc; }
         for (const Step &st : pl.prog[s].steps) {
@@ -752,13 +892,22 @@ int describe_launch(const Plan &pl, int isign, int idx, char *name, size_t cap, 
         const double vol = (double)st.fs.units * (double)st.fs.ta * (double)(1 << tile_log2(st.key.log2n, st.key.layout));
         b = 2.0 * 16.0 * vol + 16.0 * (double)(st.key.layout == LAYOUT_ROW ? st.pp.q_end - st.pp.q_begin : st.pp2.q_end - st.pp2.q_begin);
     } else if (st.is_aux) {
-        static const char *names[] = {"untangle", "spectral", "pad_response", "correl_direct", "fill", "spectral_z"};
-        snprintf(buf, sizeof(buf), "aux_%s", names[st.ap.kind]);
+        static const char *names[AUX_KIND_COUNT] = {"untangle", "spectral", "pad_response", "correl_direct", "fill", "spectral_z",
+                                                    "signal", "wait", "reduce", "stats_final", "normalize", "power", "pack2",
+                                                    "twofft_split", "scale", "cosft", "scan"};
+        snprintf(buf, sizeof(buf), "aux_%s", st.ap.kind >= 0 && st.ap.kind < AUX_KIND_COUNT ? names[st.ap.kind] : "unknown");
         switch (st.ap.kind) {
         case AUX_UNTANGLE: b = 2.0 * 16.0 * (double)st.ap.count * (double)st.ap.n; break;
         case AUX_SPECTRAL: b = (double)st.ap.count * (double)st.ap.n * 8.0 * (st.ap.b_stride ? 3.0 : 2.0) + (st.ap.b_stride ? 0.0 : 8.0 * (double)st.ap.n); break;
         case AUX_PAD_RESPONSE: b = 8.0 * ((double)st.ap.n + (double)st.ap.m); break;
         case AUX_SPECTRAL_Z: b = (double)st.ap.count * (double)st.ap.n * 8.0 * (st.ap.b_stride ? 3.0 : 2.0) + (st.ap.b_stride ? 0.0 : 8.0 * (double)st.ap.n); break;
+        case AUX_REDUCE: b = (double)st.ap.count * ((st.ap.op == RED_PARTIALS ? 16.0 : 8.0) * (double)st.ap.n + 16.0 * (double)st.ap.m); break;
+        case AUX_STATS_FINAL: b = (double)st.ap.count * 16.0 * ((double)st.ap.m + 1.0); break;
+        case AUX_NORMALIZE: b = 2.0 * 8.0 * (double)st.ap.count * (double)st.ap.n; break;
+        case AUX_POWER: b = 24.0 * (double)st.ap.n; break;
+        case AUX_PACK2: b = 32.0 * (double)st.ap.count * (double)st.ap.n; break;
+        case AUX_TWOFFT_SPLIT: b = 48.0 * (double)st.ap.count * (double)st.ap.n; break;
+        case AUX_SCALE: b = 16.0 * (double)st.ap.n; break;
         default: b = 3.0 * 8.0 * (double)st.ap.count * (double)st.ap.n; break;
         }
     } else {

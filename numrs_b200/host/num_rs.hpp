@@ -83,7 +83,29 @@ inline std::vector<double> power_spectrum(const std::vector<double> &c)
     return p;
 }
 
+// device versions of the spectra: same result, computed by the CUDA library
+inline std::vector<double> power_spectrum_device(const std::vector<double> &c, bool take_sqrt = false)
+{
+    std::vector<double> p(c.size() / 2);
+    panic_on(nrb_power_spectrum(c.data(), p.size(), take_sqrt ? 1 : 0, p.data()));
+    return p;
+}
+
 } // namespace FFT_1
+
+// ------------------------------------------------------------------ FFT_2.rs
+namespace FFT_2 {
+// FFT_2.rs:3 twofft(data1, data2, fft1, fft2); asserts FFT_2.rs:5-7
+inline void twofft(const std::vector<double> &data1, const std::vector<double> &data2, std::vector<double> &fft1,
+                   std::vector<double> &fft2)
+{
+    const std::size_t n = data1.size();
+    if (data2.size() != n) throw Panic("data2 length must equal data1 length");
+    if (fft1.size() != 2 * n + 2) throw Panic("fft1 must have length 2*n + 2");
+    if (fft2.size() != 2 * n + 2) throw Panic("fft2 must have length 2*n + 2");
+    panic_on(nrb_twofft(data1.data(), data2.data(), n, fft1.data(), fft2.data()));
+}
+} // namespace FFT_2
 
 // ------------------------------------------------------------------ Fourn.rs / Real_FT3.rs:35
 namespace Fourn {
@@ -213,6 +235,7 @@ inline void raise(int rc)
     case NRB_OK: return;
     case NRB_ERR_EMPTY_INPUT: throw CorrelError(CorrelError::EmptyInput, "Input arrays cannot be empty");
     case NRB_ERR_LENGTH_MISMATCH: throw CorrelError(CorrelError::LengthMismatch, "Input arrays must have the same length");
+    case NRB_ERR_ZERO_STDDEV: throw CorrelError(CorrelError::ZeroStdDev, "Normalization error: standard deviation is zero");
     default: throw CorrelError(CorrelError::FftError, std::string("FFT computation error: ") + nrb_last_error());
     }
 }
@@ -233,6 +256,26 @@ inline std::vector<std::vector<double>> correl_batch(const std::vector<std::pair
     std::vector<std::vector<double>> out;
     for (const auto &p : pairs) out.push_back(correl(p.first, p.second));
     return out;
+}
+
+// Correlation.rs:189 / :226 / :286
+inline std::vector<double> correl_normalized(const std::vector<double> &a, const std::vector<double> &b)
+{
+    std::vector<double> ans(a.size());
+    raise(nrb_correl_normalized(a.data(), a.size(), b.data(), b.size(), 0, ans.data()));
+    return ans;
+}
+inline std::vector<double> correl_normalized_fast(const std::vector<double> &a, const std::vector<double> &b)
+{
+    std::vector<double> ans(a.size());
+    raise(nrb_correl_normalized(a.data(), a.size(), b.data(), b.size(), 1, ans.data()));
+    return ans;
+}
+inline std::vector<double> autocorrel_fast(const std::vector<double> &a)
+{
+    std::vector<double> ans(a.size());
+    raise(nrb_autocorrel_fast(a.data(), a.size(), ans.data()));
+    return ans;
 }
 
 } // namespace Correlation

@@ -562,3 +562,90 @@ int orc_num_threads(void)
     return 1;
 #endif
 }
+
+/* ==========================================================================================
+ * "Next" rows of SURVEY.md section 8(f): callers on either side of the hot path.
+ * ======================================================================================== */
+
+/* twofft -- FFT_2.rs:3-17: spectra of two real signals from one complex transform.
+ * NR intent (deviation D9): the reference applies NR's 1-based mirror `nn2 - j` (nn2 = 2n+2) to a
+ * 0-based array (FFT_2.rs:74,111,194), i.e. pairs bin k with bin n-k+1 (measured 84 % / 142 % error,
+ * SURVEY.md appendix A); the 0-based partner of bin k is n-k.  fft1 / fft2 receive the n complex
+ * bins F1[k], F2[k] = sum_j d{1,2}[j] exp(+2 pi i jk/n) in their first 2n doubles; the reference
+ * demands length 2n+2 (FFT_2.rs:6-7), the two extra doubles are set to 0. */
+void orc_twofft(const double *d1, const double *d2, size_t n, double *fft1, double *fft2)
+{
+    size_t j, k;
+    for (j = 0; j < n; ++j) { fft1[2 * j] = d1[j]; fft1[2 * j + 1] = d2[j]; }   /* FFT_2.rs:33-37 */
+    fft1[2 * n] = fft1[2 * n + 1] = 0.0;
+    fft2[2 * n] = fft2[2 * n + 1] = 0.0;
+    orc_four1(fft1, n, 1);                                                       /* FFT_2.rs:13 */
+    fft2[0] = fft1[1]; fft1[1] = 0.0; fft2[1] = 0.0;                             /* FFT_2.rs:60-62 */
+    for (k = 1; k <= n / 2; ++k) {
+        const size_t m = n - k;
+        const double rep = 0.5 * (fft1[2 * k] + fft1[2 * m]);                    /* FFT_2.rs:77-80 */
+        const double rem = 0.5 * (fft1[2 * k] - fft1[2 * m]);
+        const double aip = 0.5 * (fft1[2 * k + 1] + fft1[2 * m + 1]);
+        const double aim = 0.5 * (fft1[2 * k + 1] - fft1[2 * m + 1]);
+        fft1[2 * k] = rep; fft1[2 * k + 1] = aim;                                /* FFT_2.rs:82-90 */
+        fft1[2 * m] = rep; fft1[2 * m + 1] = -aim;
+        fft2[2 * k] = aip; fft2[2 * k + 1] = -rem;
+        fft2[2 * m] = aip; fft2[2 * m + 1] = rem;
+    }
+}
+
+/* power / magnitude spectrum -- FFT_1.rs:206-228 (literal) */
+void orc_power_spectrum(const double *c, size_t npoints, int take_sqrt, double *out)
+{
+    size_t i;
+    for (i = 0; i < npoints; ++i) {
+        const double p = c[2 * i] * c[2 * i] + c[2 * i + 1] * c[2 * i + 1];
+        out[i] = take_sqrt ? sqrt(p) : p;
+    }
+}
+
+/* correl_normalized -- Correlation.rs:189-223 (fast = 0) and correl_normalized_fast :226-270 (fast = 1).
+ * Literal: population statistics, -8 when a standard deviation is zero (CorrelError::ZeroStdDev), the
+ * signals are centred and scaled, then correl().  The fast variant computes std from the single-pass
+ * sums (Correlation.rs:236-244) and has its own n <= 32 branch with the extra 1/(s1 s2 n) factor
+ * (Correlation.rs:251-263); for n > 32 neither variant divides by n (literal). */
+int orc_correl_normalized(const double *d1, size_t n1, const double *d2, size_t n2, int fast, double *ans)
+{
+    const size_t n = n1;
+    size_t i, lag;
+    if (n == 0) return -1;
+    if (n2 != n) return -4;
+    double s1 = 0, s2 = 0, q1 = 0, q2 = 0;
+    for (i = 0; i < n; ++i) { s1 += d1[i]; s2 += d2[i]; }
+    const double m1 = s1 / (double)n, m2 = s2 / (double)n;
+    double sd1, sd2;
+    if (fast) {
+        for (i = 0; i < n; ++i) { q1 += d1[i] * d1[i]; q2 += d2[i] * d2[i]; }
+        sd1 = sqrt(q1 / (double)n - m1 * m1);
+        sd2 = sqrt(q2 / (double)n - m2 * m2);
+    } else {
+        for (i = 0; i < n; ++i) { q1 += (d1[i] - m1) * (d1[i] - m1); q2 += (d2[i] - m2) * (d2[i] - m2); }
+        sd1 = sqrt(q1 / (double)n);
+        sd2 = sqrt(q2 / (double)n);
+    }
+    if (sd1 == 0.0 || sd2 == 0.0) return -8;      /* Correlation.rs:214-216, :246-248 (a NaN std passes, literal) */
+    if (fast && n <= 32) {
+        const double f = 1.0 / (sd1 * sd2 * (double)n);
+        for (lag = 0; lag < n; ++lag) {
+            double sum = 0.0;
+            for (i = 0; i < n - lag; ++i) sum += (d1[i + lag] - m1) * (d2[i] - m2);
+            ans[lag] = sum * f;
+        }
+        return 0;
+    }
+    double *a = (double *)malloc(sizeof(double) * n), *b = (double *)malloc(sizeof(double) * n);
+    for (i = 0; i < n; ++i) { a[i] = (d1[i] - m1) / sd1; b[i] = (d2[i] - m2) / sd2; }
+    const int rc = orc_correl(a, n, b, n, ans);
+    free(a); free(b);
+    return rc;
+}
+
+/* autocorrel_fast -- Correlation.rs:286-323.  n <= 32: the direct loop (literal).  n > 32: NR intent
+ * (deviation D10): the literal code feeds |F|^2 to the placeholder inverse DFT in that placeholder's own
+ * layout and without the 1/no2 factor; the intent is the autocorrelation, i.e. correl(data, data). */
+int orc_autocorrel_fast(const double *d, size_t n, double *ans) { return orc_correl(d, n, d, n, ans); }

@@ -62,6 +62,14 @@ def lib():
         L.orc_correl_batch.argtypes = [ctypes.POINTER(_dp), ctypes.POINTER(_dp), _sz, _sz, ctypes.POINTER(_dp),
                                        ctypes.c_int]
         L.orc_correl_batch.restype = ctypes.c_int
+        L.orc_twofft.argtypes = [_dp, _dp, _sz, _dp, _dp]
+        L.orc_twofft.restype = None
+        L.orc_power_spectrum.argtypes = [_dp, _sz, ctypes.c_int, _dp]
+        L.orc_power_spectrum.restype = None
+        L.orc_correl_normalized.argtypes = [_dp, _sz, _dp, _sz, ctypes.c_int, _dp]
+        L.orc_correl_normalized.restype = ctypes.c_int
+        L.orc_autocorrel_fast.argtypes = [_dp, _sz, _dp]
+        L.orc_autocorrel_fast.restype = ctypes.c_int
         L.orc_num_threads.argtypes = []
         L.orc_num_threads.restype = ctypes.c_int
         _LIB = L
@@ -178,6 +186,39 @@ def correl_batch(a_list, b_list, mt=True):
     op = (_dp * cnt)(*[_p(o) for o in outs])
     rc = lib().orc_correl_batch(ap, bp, cnt, n, op, int(mt))
     return rc, outs
+
+
+def twofft(d1, d2):
+    """FFT_2.rs:3: returns (fft1, fft2), each 2n+2 doubles (n complex bins + 2 zero pad doubles)."""
+    d1 = np.ascontiguousarray(d1, dtype=np.float64)
+    d2 = np.ascontiguousarray(d2, dtype=np.float64)
+    assert d1.size == d2.size
+    f1 = np.zeros(2 * d1.size + 2)
+    f2 = np.zeros(2 * d1.size + 2)
+    lib().orc_twofft(_p(d1), _p(d2), d1.size, _p(f1), _p(f2))
+    return f1, f2
+
+
+def power_spectrum(c, take_sqrt=False):
+    c = np.ascontiguousarray(c, dtype=np.float64)
+    out = np.zeros(c.size // 2)
+    lib().orc_power_spectrum(_p(c), c.size // 2, int(take_sqrt), _p(out))
+    return out
+
+
+def correl_normalized(d1, d2, fast=False):
+    d1 = np.ascontiguousarray(d1, dtype=np.float64)
+    d2 = np.ascontiguousarray(d2, dtype=np.float64)
+    ans = np.zeros(max(1, d1.size))
+    rc = lib().orc_correl_normalized(_p(d1), d1.size, _p(d2), d2.size, int(fast), _p(ans))
+    return rc, ans[:d1.size]
+
+
+def autocorrel_fast(d):
+    d = np.ascontiguousarray(d, dtype=np.float64)
+    ans = np.zeros(max(1, d.size))
+    rc = lib().orc_autocorrel_fast(_p(d), d.size, _p(ans))
+    return rc, ans[:d.size]
 
 
 def num_threads():

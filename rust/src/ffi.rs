@@ -8,6 +8,7 @@ pub const NRB_ERR_RESPONSE_TOO_LONG: c_int = -2;
 pub const NRB_ERR_INVALID_ISIGN: c_int = -3;
 pub const NRB_ERR_LENGTH_MISMATCH: c_int = -4;
 pub const NRB_ERR_INVALID_DIMS: c_int = -5;
+pub const NRB_ERR_ZERO_STDDEV: c_int = -8;
 pub const NRB_PAD_LITERAL: c_int = 0;
 
 extern "C" {
@@ -25,6 +26,11 @@ extern "C" {
     pub fn nrb_correl(d1: *const c_double, n1: usize, d2: *const c_double, n2: usize, ans: *mut c_double) -> c_int;
     pub fn nrb_correl_batch(d1: *const *const c_double, d2: *const *const c_double, count: usize, n: usize,
                             ans: *const *mut c_double) -> c_int;
+    pub fn nrb_correl_normalized(d1: *const c_double, n1: usize, d2: *const c_double, n2: usize, fast: c_int,
+                                 ans: *mut c_double) -> c_int;
+    pub fn nrb_autocorrel_fast(data: *const c_double, n: usize, ans: *mut c_double) -> c_int;
+    pub fn nrb_twofft(d1: *const c_double, d2: *const c_double, n: usize, fft1: *mut c_double, fft2: *mut c_double) -> c_int;
+    pub fn nrb_power_spectrum(c: *const c_double, npoints: usize, take_sqrt: c_int, out: *mut c_double) -> c_int;
 }
 
 pub fn last_error() -> String {

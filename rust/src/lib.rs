@@ -234,6 +234,7 @@ pub mod Correlation {
             NRB_OK => Ok(()),
             NRB_ERR_EMPTY_INPUT => Err(CorrelError::EmptyInput),
             NRB_ERR_LENGTH_MISMATCH => Err(CorrelError::LengthMismatch),
+            NRB_ERR_ZERO_STDDEV => Err(CorrelError::ZeroStdDev),
             _ => Err(CorrelError::FftError(last_error())),
         }
     }
@@ -262,4 +263,32 @@ pub mod Correlation {
 
     /// reference: src/Correlation.rs:281
     pub fn autocorrel(data: &[f64]) -> Result<Array1<f64>, CorrelError> { correl(data, data) }
+
+    fn normalized(data1: &[f64], data2: &[f64], fast: i32) -> Result<Array1<f64>, CorrelError> {
+        let mut ans = vec![0.0f64; data1.len()];
+        map(unsafe { nrb_correl_normalized(data1.as_ptr(), data1.len(), data2.as_ptr(), data2.len(), fast, ans.as_mut_ptr()) })?;
+        Ok(Array1::from_vec(ans))
+    }
+    /// reference: src/Correlation.rs:189
+    pub fn correl_normalized(data1: &[f64], data2: &[f64]) -> Result<Array1<f64>, CorrelError> { normalized(data1, data2, 0) }
+    /// reference: src/Correlation.rs:226
+    pub fn correl_normalized_fast(data1: &[f64], data2: &[f64]) -> Result<Array1<f64>, CorrelError> { normalized(data1, data2, 1) }
+    /// reference: src/Correlation.rs:286
+    pub fn autocorrel_fast(data: &[f64]) -> Result<Array1<f64>, CorrelError> {
+        let mut ans = vec![0.0f64; data.len()];
+        map(unsafe { nrb_autocorrel_fast(data.as_ptr(), data.len(), ans.as_mut_ptr()) })?;
+        Ok(Array1::from_vec(ans))
+    }
+}
+
+pub mod FFT_2 {
+    use crate::ffi::*;
+    /// reference: src/FFT_2.rs:3 (asserts :5-7)
+    pub fn twofft(data1: &[f64], data2: &[f64], fft1: &mut [f64], fft2: &mut [f64]) {
+        let n = data1.len();
+        assert_eq!(data2.len(), n, "data2 length must equal data1 length");
+        assert_eq!(fft1.len(), 2 * n + 2, "fft1 must have length 2*n + 2");
+        assert_eq!(fft2.len(), 2 * n + 2, "fft2 must have length 2*n + 2");
+        panic_on(unsafe { nrb_twofft(data1.as_ptr(), data2.as_ptr(), n, fft1.as_mut_ptr(), fft2.as_mut_ptr()) });
+    }
 }

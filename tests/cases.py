@@ -123,3 +123,36 @@ def check_correl(L, n, seed=1004):
     assert rc == 0
     got = nb.correl(a, b, L)
     assert rel(got, ref) <= tol(n), (n, rel(got, ref))
+
+
+# ---------------------------------------------------------------- SURVEY.md 8f "next" rows
+def check_twofft(L, n, seed=1010):
+    a, b = gen(seed, n), gen(seed + 1, n)
+    r1, r2 = O.twofft(a, b)
+    f1, f2 = np.full(2 * n + 2, np.nan), np.full(2 * n + 2, np.nan)
+    nb.twofft(a, b, f1, f2, L)
+    assert rel(f1, r1) <= tol(n) and rel(f2, r2) <= tol(n), (n, rel(f1, r1), rel(f2, r2))
+    assert f1[1] == 0.0 and f2[1] == 0.0 and not f1[2 * n:].any() and not f2[2 * n:].any()   # FFT_2.rs:60-62, :6-7
+
+
+def check_correl_normalized(L, n, seed=1011, fast=False):
+    a = gen(seed, n) + 0.75
+    b = 2.0 * gen(seed + 1, n) - 0.25
+    rc, ref = O.correl_normalized(a, b, fast)
+    assert rc == 0
+    got = (nb.correl_normalized_fast if fast else nb.correl_normalized)(a, b, L)
+    assert rel(got, ref) <= tol(n), (n, fast, rel(got, ref))
+
+
+def check_autocorrel_fast(L, n, seed=1012):
+    a = gen(seed, n)
+    rc, ref = O.autocorrel_fast(a)
+    assert rc == 0
+    got = nb.autocorrel_fast(a, L)
+    assert rel(got, ref) <= tol(n), (n, rel(got, ref))
+
+
+def check_spectrum(L, npoints, seed=1013):
+    c = gen(seed, 2 * npoints)
+    assert rel(nb.power_spectrum(c, L), O.power_spectrum(c)) <= 1e-15
+    assert rel(nb.magnitude_spectrum(c, L), O.power_spectrum(c, True)) <= 1e-15

@@ -34,6 +34,7 @@ int main(int argc, char **argv)
     { std::vector<double> d(16); CHECK(throws<Fourn::InvalidInput>([&] { Fourn::fourn(d, {8}, 1, 0); })); }
     // Real_FT.rs:5-6, Real_FT3.rs:17-19
     { std::vector<double> d(6); CHECK(throws<Panic>([&] { Real_FT::realft(d, 5, 1); })); }
+    { std::vector<double> a(4), b(4), f(8), g(10); CHECK(throws<Panic>([&] { FFT_2::twofft(a, b, f, g); })); }   // FFT_2.rs:6
     { std::vector<double> d(64), s(32); CHECK(throws<Panic>([&] { Real_FT3::rlft3(d, s, 4, 4, 4, 0); })); }
     { std::vector<double> d(64), s(16); CHECK(throws<Panic>([&] { Real_FT3::rlft3(d, s, 4, 4, 4, 1); })); }
     if (gpu) {
@@ -54,6 +55,20 @@ int main(int argc, char **argv)
         CHECK(r[0] == 30.0 && r[0] > r[1]);
         auto r2 = Correlation::correl({1, 2}, {1, 2});
         CHECK(r2[0] == 5.0 && r2[1] == 2.0);
+        // Correlation.rs:505-512, ZeroStdDev :214-216; FFT_2.rs:406-428 (fft1[1] == 0, Hermitian symmetry)
+        CHECK(std::fabs(Correlation::correl_normalized_fast({1, 2, 3, 4}, {1, 2, 3, 4})[0] - 1.0) < 1e-10);
+        try { Correlation::correl_normalized({1, 1, 1, 1}, {1, 2, 3, 4}); CHECK(false); } catch (const Correlation::CorrelError &e) { CHECK(e.kind == Correlation::CorrelError::ZeroStdDev); }
+        CHECK(Correlation::autocorrel_fast({1, 2, 1, 2})[0] == 10.0);
+        {
+            const std::size_t m = 256;
+            std::vector<double> a(m), b(m), f1(2 * m + 2), f2(2 * m + 2);
+            for (std::size_t i = 0; i < m; ++i) { double t = (double)i / m; a[i] = std::sin(2 * M_PI * 5 * t); b[i] = std::cos(2 * M_PI * 10 * t); }
+            FFT_2::twofft(a, b, f1, f2);
+            CHECK(f1[1] == 0.0 && f2[1] == 0.0 && std::fabs(f2[20] - m / 2.0) < 1e-9);
+            for (std::size_t k = 1; k < m / 2; ++k) CHECK(std::fabs(f1[2 * k] - f1[2 * (m - k)]) < 1e-10 && std::fabs(f1[2 * k + 1] + f1[2 * (m - k) + 1]) < 1e-10);
+            auto pw = FFT_1::power_spectrum_device(f2), hp = FFT_1::power_spectrum(f2);
+            for (std::size_t k = 0; k < m; ++k) CHECK(pw[k] == hp[k]);
+        }
         // Real_FT3.rs:268-311 with the true factor N/2
         std::vector<double> d(512), s(128, 0.0), o(512);
         for (int i = 0; i < 8; ++i) for (int j = 0; j < 8; ++j) for (int k = 0; k < 8; ++k) o[(i * 8 + j) * 8 + k] = d[(i * 8 + j) * 8 + k] = i + j + k;

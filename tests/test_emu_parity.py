@@ -258,3 +258,110 @@ def test_device_fill_matches_generator(emu):
     out = np.zeros(5000)
     emu.fill_uniform_device(out.ctypes.data, 1006, 77, out.size)
     assert np.array_equal(out, O.fill_uniform(1006, 77, out.size))
+
+
+# ---------------------------------------------------------------- SURVEY.md 8f "next" rows (N2, N4)
+@pytest.mark.parametrize("n", [1, 2, 4, 16, 256, 4096, 8192, 1 << 14])
+def test_twofft(emu, n):
+    cases.check_twofft(emu, n)
+
+
+def test_twofft_multi_step_and_reference_properties(emu):
+    emu.set_option("row_max_log2", 3)       # dense workspace path
+    emu.set_option("col_max_log2", 3)
+    cases.check_twofft(emu, 256)
+    # FFT_2.rs:392-428 test_twofft_correctness (with the 0-based mirror n - k, ledger D9)
+    n = 256
+    t = np.arange(n) / n
+    f1, f2 = np.zeros(2 * n + 2), np.zeros(2 * n + 2)
+    nb.twofft(np.sin(2 * np.pi * 5 * t), np.cos(2 * np.pi * 10 * t), f1, f2, emu)
+    assert abs(f1[1]) < 1e-10 and abs(f2[1]) < 1e-10
+    for k in range(1, n // 2):
+        assert abs(f1[2 * k] - f1[2 * (n - k)]) < 1e-10 and abs(f1[2 * k + 1] + f1[2 * (n - k) + 1]) < 1e-10
+    # the spectra themselves: sin(2 pi 5 t) -> +-i n/2 at bins 5 / n-5; cos(2 pi 10 t) -> n/2 at bins 10 / n-10
+    assert abs(f1[2 * 5 + 1] - n / 2) < 1e-9 and abs(f2[2 * 10] - n / 2) < 1e-9
+    with pytest.raises(AssertionError):
+        nb.twofft(np.zeros(4), np.zeros(5), np.zeros(10), np.zeros(10), emu)      # FFT_2.rs:5
+    with pytest.raises(AssertionError):
+        nb.twofft(np.zeros(4), np.zeros(4), np.zeros(8), np.zeros(10), emu)       # FFT_2.rs:6
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 31, 32, 64, 128, 4096, 1 << 15])
+@pytest.mark.parametrize("fast", [False, True])
+def test_correl_normalized(emu, n, fast):
+    if n == 1:
+        with pytest.raises(nb.CorrelError) as ei:       # a single sample has zero std
+            (nb.correl_normalized_fast if fast else nb.correl_normalized)([1.0], [2.0], emu)
+        assert ei.value.kind == nb.CorrelError.ZeroStdDev
+        return
+    cases.check_correl_normalized(emu, n, fast=fast)
+
+
+def test_correl_normalized_long_line_path_and_errors(emu):
+    emu.set_option("row_max_log2", 2)
+    emu.set_option("col_max_log2", 3)
+    cases.check_correl_normalized(emu, 1024)
+    cases.check_correl_normalized(emu, 1024, fast=True)
+    cases.check_autocorrel_fast(emu, 1024)
+    # Correlation.rs:505-512 test_fast_normalized_correlation; :435-449 holds for the fast variant only (the plain
+    # variant's n <= 32 branch has no 1/n: literal result n at lag 0)
+    x = [1.0, 2.0, 3.0, 4.0]
+    assert abs(nb.correl_normalized_fast(x, x, emu)[0] - 1.0) < 1e-10
+    y = nb.correl_normalized_fast(x, x, emu)
+    assert np.all(y >= -1.0) and np.all(y <= 1.0)
+    assert abs(nb.correl_normalized(x, x, emu)[0] - 4.0) < 1e-10
+    for f in (nb.correl_normalized, nb.correl_normalized_fast):
+        with pytest.raises(nb.CorrelError) as ei:
+            f([], [1.0], emu)
+        assert ei.value.kind == nb.CorrelError.EmptyInput
+        with pytest.raises(nb.CorrelError) as ei:
+            f([1.0, 2.0], [1.0], emu)
+        assert ei.value.kind == nb.CorrelError.LengthMismatch
+        with pytest.raises(nb.CorrelError) as ei:
+            f(np.ones(64), np.arange(64.0), emu)
+        assert ei.value.kind == nb.CorrelError.ZeroStdDev
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 32, 64, 1024, 1 << 14, 1 << 15])
+def test_autocorrel_fast(emu, n):
+    cases.check_autocorrel_fast(emu, n)
+    if n == 2:
+        # Correlation.rs:481-491 expects 10 at lag 0 (pinned) and 8 at lag 2, but the n <= 32 branch is linear
+        # (Correlation.rs:294-303): lag 2 = 1*1 + 2*2 = 5 -- literal
+        assert list(nb.autocorrel_fast([1.0, 2.0, 1.0, 2.0], emu))[::2] == [10.0, 5.0]
+        with pytest.raises(nb.CorrelError):
+            nb.autocorrel_fast([], emu)
+
+
+@pytest.mark.parametrize("npoints", [1, 7, 1024, 5000])
+def test_spectrum_helpers(emu, npoints):
+    cases.check_spectrum(emu, npoints)
+    # FFT_1.rs:305-321: power = magnitude^2
+    c = O.fill_uniform(1, 0, 2 * npoints)
+    assert np.max(np.abs(nb.magnitude_spectrum(c, emu) ** 2 - nb.power_spectrum(c, emu))) < 1e-10
+
+
+def test_next_rows_plan_api_batched(emu):
+    """Device-resident plan API for the new kinds (batched)."""
+    n, cnt = 256, 3
+    a = O.fill_uniform(21, 0, n * cnt) + 0.5
+    b = O.fill_uniform(22, 0, n * cnt)
+    out = np.zeros(4 * cnt + n * cnt)
+    plan = emu.plan_create(nb.KIND_CORREL_NORM, [n], batch=cnt)
+    plan.exec(a.ctypes.data, b.ctypes.data, out.ctypes.data)
+    plan.destroy()
+    st = out[:4 * cnt].reshape(2 * cnt, 2)
+    for i in range(cnt):
+        x, y = a[i * n:(i + 1) * n], b[i * n:(i + 1) * n]
+        assert abs(st[i, 0] - x.mean()) < 1e-14 and abs(st[i, 1] - x.std()) < 1e-14
+        assert abs(st[cnt + i, 0] - y.mean()) < 1e-14 and abs(st[cnt + i, 1] - y.std()) < 1e-14
+        assert cases.rel(out[4 * cnt + i * n:4 * cnt + (i + 1) * n], O.correl_normalized(x, y)[1]) <= cases.tol(n)
+    f = np.zeros(2 * cnt * (2 * n + 2))
+    plan = emu.plan_create(nb.KIND_TWOFFT, [n], batch=cnt)
+    plan.exec(a.ctypes.data, b.ctypes.data, f.ctypes.data)
+    plan.destroy()
+    per = 2 * n + 2
+    for i in range(cnt):
+        r1, r2 = O.twofft(a[i * n:(i + 1) * n], b[i * n:(i + 1) * n])
+        assert cases.rel(f[i * per:(i + 1) * per], r1) <= cases.tol(n)
+        assert cases.rel(f[(cnt + i) * per:(cnt + i + 1) * per], r2) <= cases.tol(n)

@@ -138,6 +138,40 @@ def test_correl_reference_known_answers(gpu):
         assert ei.value.kind == case["err"]
 
 
+# ------------------------------------------------------------------ SURVEY.md 8f "next" rows (N2, N4)
+@pytest.mark.parametrize("n", [1, 2, 16, 256, 4096, 8192, 1 << 14, 1 << 20])
+def test_twofft(gpu, n):
+    cases.check_twofft(gpu, n)
+
+
+@pytest.mark.parametrize("n", [2, 5, 32, 64, 4096, 1 << 15, 1 << 20])
+@pytest.mark.parametrize("fast", [False, True])
+def test_correl_normalized(gpu, n, fast):
+    cases.check_correl_normalized(gpu, n, fast=fast)
+
+
+def test_correl_normalized_errors_and_known_answers(gpu):
+    x = [1.0, 2.0, 3.0, 4.0]
+    assert abs(nb.correl_normalized_fast(x, x)[0] - 1.0) < 1e-10          # Correlation.rs:505-512
+    assert abs(nb.correl_normalized(x, x)[0] - 4.0) < 1e-10               # literal: no 1/n in the plain variant
+    for f in (nb.correl_normalized, nb.correl_normalized_fast):
+        for args, kind in ((([], [1.0]), nb.CorrelError.EmptyInput), (([1.0, 2.0], [1.0]), nb.CorrelError.LengthMismatch),
+                           ((np.ones(64), np.arange(64.0)), nb.CorrelError.ZeroStdDev)):
+            with pytest.raises(nb.CorrelError) as ei:
+                f(*args)
+            assert ei.value.kind == kind
+
+
+@pytest.mark.parametrize("n", [1, 7, 32, 64, 1024, 1 << 15, 1 << 20])
+def test_autocorrel_fast(gpu, n):
+    cases.check_autocorrel_fast(gpu, n)
+
+
+@pytest.mark.parametrize("npoints", [1, 7, 5000, 1 << 20])
+def test_spectrum_helpers(gpu, npoints):
+    cases.check_spectrum(gpu, npoints)
+
+
 def test_golden_fixtures(gpu):
     for nn in (8, 64, 1024):
         for s, t in ((1, "p"), (-1, "m")):

@@ -175,3 +175,45 @@ def test_oracle_matches_golden_fixtures():
         assert np.array_equal(d, G[f"rlft3_{tag}_data"]) and np.array_equal(s, G[f"rlft3_{tag}_speq"])
     assert np.array_equal(O.convlv(G["convlv_128_9_in"], G["convlv_128_9_resp"], 1)[1], G["convlv_128_9_out"])
     assert np.array_equal(O.correl(G["correl_128_a"], G["correl_128_b"])[1], G["correl_128_out"])
+
+
+# ---------------------------------------------------------------- SURVEY.md 8f "next" rows (N2, N4)
+@pytest.mark.parametrize("n", [1, 2, 4, 16, 256, 4096])
+def test_twofft_vs_numpy(n):
+    """NR twofft (ledger D9): both spectra equal the e^{+} DFT of each real signal (numpy: n * ifft)."""
+    a, b = O.fill_uniform(1010, 0, n), O.fill_uniform(1011, 0, n)
+    f1, f2 = O.twofft(a, b)
+    assert rel(c(f1[:2 * n]), n * np.fft.ifft(a)) < 1e-13 * max(1, np.log2(max(n, 2)))
+    assert rel(c(f2[:2 * n]), n * np.fft.ifft(b)) < 1e-13 * max(1, np.log2(max(n, 2)))
+    assert not f1[2 * n:].any() and not f2[2 * n:].any() and f1[1] == 0.0 and f2[1] == 0.0
+
+
+@pytest.mark.parametrize("n", [2, 5, 32, 64, 1024])
+def test_correl_normalized_vs_numpy(n):
+    a = O.fill_uniform(1011, 0, n) + 0.75
+    b = 2.0 * O.fill_uniform(1012, 0, n) - 0.25
+    an, bn = (a - a.mean()) / a.std(), (b - b.mean()) / b.std()
+    for fast in (False, True):
+        rc, got = O.correl_normalized(a, b, fast)
+        assert rc == 0
+        if n <= 32:     # Correlation.rs:19-21 / :251-263 direct lags; only the fast variant divides by n
+            ref = np.array([np.dot(an[l:], bn[:n - l]) for l in range(n)]) * (1.0 / n if fast else 1.0)
+        else:
+            ref = np.fft.irfft(np.fft.rfft(an) * np.conj(np.fft.rfft(bn)), n)
+        assert rel(got, ref) < 1e-13 * max(1, np.log2(n))
+    assert O.correl_normalized(np.ones(8), np.arange(8.0))[0] == -8        # CorrelError::ZeroStdDev
+    assert O.correl_normalized([], [1.0])[0] == -1 and O.correl_normalized([1.0, 2.0], [1.0])[0] == -4
+    # Correlation.rs:505-512
+    assert abs(O.correl_normalized([1.0, 2.0, 3.0, 4.0], [1.0, 2.0, 3.0, 4.0], True)[1][0] - 1.0) < 1e-10
+
+
+@pytest.mark.parametrize("n", [3, 32, 64, 4096])
+def test_autocorrel_fast_and_spectra_vs_numpy(n):
+    a = O.fill_uniform(1012, 0, n)
+    rc, got = O.autocorrel_fast(a)
+    ref = (np.array([np.dot(a[l:], a[:n - l]) for l in range(n)]) if n <= 32
+           else np.fft.irfft(np.abs(np.fft.rfft(a)) ** 2, n))
+    assert rc == 0 and rel(got, ref) < 1e-13 * max(1, np.log2(n))
+    z = O.fill_uniform(1013, 0, 2 * n)
+    assert np.array_equal(O.power_spectrum(z), z[0::2] ** 2 + z[1::2] ** 2)
+    assert np.allclose(O.power_spectrum(z, True), np.abs(c(z)), rtol=1e-15, atol=0)
