@@ -67,7 +67,7 @@ int main(int argc, char **argv)
             CHECK(f1[1] == 0.0 && f2[1] == 0.0 && std::fabs(f2[20] - m / 2.0) < 1e-9);
             for (std::size_t k = 1; k < m / 2; ++k) CHECK(std::fabs(f1[2 * k] - f1[2 * (m - k)]) < 1e-10 && std::fabs(f1[2 * k + 1] + f1[2 * (m - k) + 1]) < 1e-10);
             auto pw = FFT_1::power_spectrum_device(f2), hp = FFT_1::power_spectrum(f2);
-            for (std::size_t k = 0; k < m; ++k) CHECK(pw[k] == hp[k]);
+            for (std::size_t k = 0; k < m; ++k) CHECK(std::fabs(pw[k] - hp[k]) <= 4e-16 * hp[k]);   // the device contracts x*x + y*y into an FMA
         }
         // Real_FT3.rs:268-311 with the true factor N/2
         std::vector<double> d(512), s(128, 0.0), o(512);

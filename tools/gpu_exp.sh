@@ -1,7 +1,9 @@
 #!/bin/bash
+# 2-GPU experiment: NVLink store patterns + the new rows' GPU parity
 cd "$(dirname "$0")/.."
-W="rlft3_512 fourn2d_8192 four1_20_64"
-echo "##### default"; timeout 300 python tools/kernel_table.py $W 2>&1 | grep -E "col|^=="
-for v in c16 c16m2; do
-echo "##### $v"; NUMRS_B200_LIB=$PWD/variants/lib_$v.so timeout 300 python tools/kernel_table.py $W 2>&1 | grep -E "col|^=="
-done
+mkdir -p gpurun_out
+nvidia-smi topo -m > gpurun_out/topo.txt 2>&1
+timeout 120 ./tools/p2p_store_bench > gpurun_out/p2p_store_bench.log 2>&1; echo "exit $?" >> gpurun_out/p2p_store_bench.log
+cat gpurun_out/p2p_store_bench.log
+timeout 900 python -m pytest tests -m gpu -x -q -k "twofft or correl_normalized or autocorrel_fast or spectrum or host_mirror" > gpurun_out/pytest_next.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_next.log
+tail -5 gpurun_out/pytest_next.log
