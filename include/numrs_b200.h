@@ -114,6 +114,16 @@ int nrb_twofft(const double *data1, const double *data2, size_t n, double *fft1,
 /* FFT_1.rs:218 power_spectrum (take_sqrt = 0) / :206 magnitude_spectrum (take_sqrt = 1) of npoints complex points */
 int nrb_power_spectrum(const double *complex_data, size_t npoints, int take_sqrt, double *out);
 
+/* N3: cosine / sine transforms around realft (NR semantics; the reference's bodies stop at `unimplemented!()`,
+ * Cos_FT.rs:70-74).  The reference's 1-based calling convention is kept: y[0] is unused.
+ * Cos_FT.rs:7   cosft1(y, n): y has n + 2 doubles, data y[1..=n+1];  F_k = f_0/2 + (-1)^k f_n/2 + sum f_j cos(pi j k / n)
+ * Cos_FT2.rs:7  cosft2(y, n, isign): y has n + 1 doubles, data y[1..=n]; isign = 1: F_k = sum f_j cos(pi k (j + 1/2) / n);
+ *               isign = -1: the inverse up to the factor 2/n; any other isign -> NRB_ERR_INVALID_ISIGN (Cos_FT2.rs:11 panics)
+ * README.md:72  sinft(y, n): y has n + 1 doubles, data y[1..=n]; y[1] is taken as 0; F_k = sum f_j sin(pi j k / n) */
+int nrb_cosft1(double *y, size_t n);
+int nrb_cosft2(double *y, size_t n, int isign);
+int nrb_sinft(double *y, size_t n);
+
 /* ---- device-resident plan API (what the benchmark times; pointers are DEVICE memory) ---- */
 typedef struct nrb_plan_s *nrb_plan_t;
 
@@ -133,6 +143,9 @@ typedef struct nrb_plan_s *nrb_plan_t;
 #define NRB_KIND_TWOFFT          10  /* dims = {n}; io = data1, aux = data2 (batch x n doubles); out = fft1
                                         [batch][n+1] complex followed by fft2 [batch][n+1] complex       */
 #define NRB_KIND_POWER           11  /* dims = {npoints}; io = complex points, out = doubles; arg = sqrt  */
+#define NRB_KIND_COSFT1          12  /* dims = {n}; io = batch x (n + 2) doubles (1-based lines), in place */
+#define NRB_KIND_COSFT2          13  /* dims = {n}; io = batch x (n + 1) doubles, in place; isign = +-1    */
+#define NRB_KIND_SINFT           14  /* dims = {n}; io = batch x (n + 1) doubles, in place                 */
 
 int    nrb_plan_create(int kind, const size_t *dims, size_t ndim, size_t batch, nrb_plan_t *plan);
 size_t nrb_plan_workspace_bytes(nrb_plan_t plan);

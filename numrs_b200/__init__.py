@@ -13,7 +13,7 @@ import numpy as np
 from . import _lib
 from ._lib import (NRB_PAD_LITERAL, NRB_PAD_NR, NrbError, KIND_FOUR1, KIND_FOURN, KIND_REALFT, KIND_RLFT3,
                    KIND_CONVLV, KIND_CORREL, KIND_CORREL_NORM, KIND_CORREL_NORM_FAST, KIND_AUTOCORREL_FAST,
-                   KIND_TWOFFT, KIND_POWER)
+                   KIND_TWOFFT, KIND_POWER, KIND_COSFT1, KIND_COSFT2, KIND_SINFT)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # NUMRS_B200_LIB may point at another build of the same CUDA library (tuning experiments)
@@ -142,6 +142,28 @@ def twofft(data1, data2, fft1, fft2, _L=None):
     assert fft2.size == 2 * n + 2, "fft2 must have length 2*n + 2"
     L = _L or lib()
     _panic(L, L.twofft(data1, data2, fft1, fft2))
+
+
+# ---------------------------------------------------------------- Cos_FT.rs / Cos_FT2.rs / sinft
+def cosft1(y, n, _L=None):
+    """Cos_FT.rs:7 `cosft1(y: &mut [f64], n)`: 1-based array, y[0] unused, data y[1..=n+1]; NR semantics."""
+    assert y.size >= n + 2, "y must hold n + 2 elements"        # Cos_FT.rs:17 reads y[n + 1]
+    L = _L or lib()
+    _panic(L, L.cosft1(y, n))
+
+
+def cosft2(y, n, isign, _L=None):
+    """Cos_FT2.rs:7 `cosft2(y, n, isign)`: 1-based array, data y[1..=n]; panics on isign not in {1, -1}."""
+    assert y.size >= n + 1, "y must hold n + 1 elements"
+    L = _L or lib()
+    _panic(L, L.cosft2(y, n, isign))
+
+
+def sinft(y, n, _L=None):
+    """NR sinft (README.md:72): 1-based array, data y[1..=n], y[1] is taken as 0."""
+    assert y.size >= n + 1, "y must hold n + 1 elements"
+    L = _L or lib()
+    _panic(L, L.sinft(y, n))
 
 
 # ---------------------------------------------------------------- Fourn.rs / Real_FT3.rs:35

@@ -31,6 +31,7 @@ NRB_PAD_NR = 1
 
 KIND_FOUR1, KIND_FOURN, KIND_REALFT, KIND_RLFT3, KIND_CONVLV, KIND_CORREL = 1, 2, 3, 4, 5, 6
 KIND_CORREL_NORM, KIND_CORREL_NORM_FAST, KIND_AUTOCORREL_FAST, KIND_TWOFFT, KIND_POWER = 7, 8, 9, 10, 11
+KIND_COSFT1, KIND_COSFT2, KIND_SINFT = 12, 13, 14
 
 # every symbol include/numrs_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
@@ -39,6 +40,7 @@ ABI_SYMBOLS = [
     "nrb_four1", "nrb_four1_batch", "nrb_fourn", "nrb_realft", "nrb_realft_batch", "nrb_rlft3",
     "nrb_convlv", "nrb_convlv_batch", "nrb_correl", "nrb_correl_batch",
     "nrb_correl_normalized", "nrb_autocorrel_fast", "nrb_twofft", "nrb_power_spectrum",
+    "nrb_cosft1", "nrb_cosft2", "nrb_sinft",
     "nrb_plan_create", "nrb_plan_workspace_bytes", "nrb_plan_num_launches", "nrb_plan_exec", "nrb_plan_destroy",
     "nrb_plan_profile", "nrb_plan_describe_launch", "nrb_fill_uniform_device",
     "nrb_slab_create", "nrb_slab_local_doubles", "nrb_slab_speq_doubles", "nrb_slab_xchg_doubles",
@@ -92,6 +94,9 @@ class Library:
         L.nrb_autocorrel_fast.argtypes = [_dp, _sz, _dp]
         L.nrb_twofft.argtypes = [_dp, _dp, _sz, _dp, _dp]
         L.nrb_power_spectrum.argtypes = [_dp, _sz, ctypes.c_int, _dp]
+        L.nrb_cosft1.argtypes = [_dp, _sz]
+        L.nrb_cosft2.argtypes = [_dp, _sz, ctypes.c_int]
+        L.nrb_sinft.argtypes = [_dp, _sz]
         L.nrb_plan_create.argtypes = [ctypes.c_int, ctypes.POINTER(_sz), _sz, _sz, ctypes.POINTER(_vp)]
         L.nrb_plan_workspace_bytes.argtypes = [_vp]
         L.nrb_plan_workspace_bytes.restype = _sz
@@ -246,6 +251,15 @@ class Library:
         rc = self.L.nrb_power_spectrum(_f64(c if c.size else np.zeros(2)), c.size // 2, int(take_sqrt),
                                        _f64(out if out.size else np.zeros(1)))
         return rc, out
+
+    def cosft1(self, y, n):
+        return self.L.nrb_cosft1(_f64(y), n)
+
+    def cosft2(self, y, n, isign):
+        return self.L.nrb_cosft2(_f64(y), n, isign)
+
+    def sinft(self, y, n):
+        return self.L.nrb_sinft(_f64(y), n)
 
     def fill_uniform_device(self, d_ptr, seed, offset, count, stream=0):
         self.check(self.L.nrb_fill_uniform_device(d_ptr, seed, offset, count, stream or None))

@@ -503,4 +503,21 @@ int nrb_power_spectrum(const double *complex_data, size_t npoints, int take_sqrt
     return run_segments(NRB_KIND_POWER, dims, 1, 1, {{complex_data, 0, 2 * npoints}}, {}, npoints, {{out, 0, npoints}}, 1, take_sqrt ? 1 : 0);
 }
 
+static int run_cosft(int kind, double *y, size_t n, size_t doubles, int isign)
+{
+    if (n < 2) return fail(NRB_ERR_INVALID_DIMS, "cosft/sinft: n must be >= 2");
+    if (!is_pow2(n)) return fail(NRB_ERR_NOT_POW2, "cosft/sinft: n must be a power of two");
+    if (!y) return fail(NRB_ERR_EMPTY_INPUT, "null data");
+    const size_t dims[1] = {n};
+    double *ptrs[1] = {y};
+    return run_inplace(kind, dims, 1, ptrs, 1, doubles, isign, nullptr, 0);
+}
+int nrb_cosft1(double *y, size_t n) { return run_cosft(NRB_KIND_COSFT1, y, n, n + 2, 1); }
+int nrb_cosft2(double *y, size_t n, int isign)
+{
+    if (isign != 1 && isign != -1) return fail(NRB_ERR_INVALID_ISIGN, "Invalid isign value. Must be 1 or -1");   // Cos_FT2.rs:11
+    return run_cosft(NRB_KIND_COSFT2, y, n, n + 1, isign);
+}
+int nrb_sinft(double *y, size_t n) { return run_cosft(NRB_KIND_SINFT, y, n, n + 1, 1); }
+
 } // extern "C"

@@ -253,6 +253,7 @@ NRB_DEV void aux_stats_final(const AuxParams &A, u64 gtid, u64 gthreads)
         double2 st = A.out[s];
         if (A.op == STATS_FAST) { st.x = sx / n; st.y = sqrt(sy / n - st.x * st.x); }   // Correlation.rs:241-244
         else if (A.op == STATS_MEAN) { st.x = sx / n; st.y = 0.0; }                     // Correlation.rs:200
+        else if (A.op == STATS_SUM) { st.x = sx; st.y = sy; }
         else st.y = sqrt(sx / n);                                                       // Correlation.rs:207
         A.out[s] = st;
     }
@@ -330,6 +331,130 @@ NRB_DEV void aux_scale(const AuxParams &A, u64 gtid, u64 gthreads)
     for (u64 i = gtid; i < A.n; i += gthreads) out[i] *= f;
 }
 
+// ------------------------------------------------------------------ cosft1 / cosft2 / sinft
+// The reference's routines work on 1-based arrays (y[0] unused): line l of the io buffer starts at
+// io + l*ld doubles and its data are f(i) = io[l*ld + 1 + i].  G is the realft work array (n/2 complex per line).
+// exp(-i pi m / n) from the two-level table of M = 2n; COS2 modes use M = 4n, i.e. exp(-i pi m / (2n)).
+
+// Pre-processing (and cosft2's inverse post-processing): m accumulators per line, accumulator c handles the
+// pairs j = c, c + m, ... (consecutive threads -> consecutive addresses) and, for cosft1, adds up its share
+// of sum = 0.5 (f_0 - f_n) + sum_j cos(j pi/n) (f_j - f_{n-j})  (Cos_FT.rs:17,36-55) into b[l*m + c].
+// a = io (doubles, stride a_stride = ld), out = G, except COS2I_POST: a = G, out = io (stride out_stride = ld).
+NRB_DEV void aux_cosft(const AuxParams &A, u64 gtid, u64 gthreads)
+{
+    const u64 n = A.n, N = n / 2, C = A.m, items = A.count * C;
+    const int mode = A.dir;
+    for (u64 it = gtid; it < items; it += gthreads) {
+        const u64 c = it % C, l = it / C;
+        double acc = 0.0;
+        if (mode == COS2I_POST) {                                          // Cos_FT2.rs:142-162
+            const double *g = reinterpret_cast<const double *>(A.a + (i64)(l * N));
+            double *f = reinterpret_cast<double *>(A.out) + (i64)l * A.out_stride + 1;
+            for (u64 i = c; i < N; i += C) {
+                const double2 t = two_level_tw(A.rtw_lo, A.rtw_hi, A.rtw_h, 2 * i + 1);   // sin((2i+1) pi/(2n)) = -t.y
+                const double gi = g[i], gm = g[n - 1 - i];
+                const double y1 = gi + gm, y2 = (0.5 / -t.y) * (gi - gm);
+                f[i] = 0.5 * (y1 + y2);
+                f[n - 1 - i] = 0.5 * (y1 - y2);
+            }
+            continue;
+        }
+        const double *f = reinterpret_cast<const double *>(A.a) + (i64)l * A.a_stride + 1;
+        double *g = reinterpret_cast<double *>(A.out + (i64)(l * N));
+        if (mode == COS1) {
+            for (u64 j = c; j <= N; j += C) {
+                if (j == 0) { g[0] = 0.5 * (f[0] + f[n]); acc += 0.5 * (f[0] - f[n]); }
+                else if (j == N) g[N] = f[N];
+                else {
+                    const double2 t = two_level_tw(A.rtw_lo, A.rtw_hi, A.rtw_h, j);      // (cos, -sin)(j pi/n)
+                    const double y1 = 0.5 * (f[j] + f[n - j]), y2 = f[j] - f[n - j];
+                    g[j] = y1 + t.y * y2;
+                    g[n - j] = y1 - t.y * y2;
+                    acc += t.x * y2;
+                }
+            }
+            if (A.b) const_cast<double2 *>(A.b)[it] = make_double2(acc, 0.0);
+        } else if (mode == COS2F) {                                        // Cos_FT2.rs:26-36
+            for (u64 i = c; i < N; i += C) {
+                const double2 t = two_level_tw(A.rtw_lo, A.rtw_hi, A.rtw_h, 2 * i + 1);
+                const double y1 = 0.5 * (f[i] + f[n - 1 - i]), y2 = -t.y * (f[i] - f[n - 1 - i]);
+                g[i] = y1 + y2;
+                g[n - 1 - i] = y1 - y2;
+            }
+        } else if (mode == SINFT) {                                        // NR sinft, first loop
+            for (u64 j = c; j <= N; j += C) {
+                if (j == 0) { g[0] = 0.0; continue; }
+                const double2 t = two_level_tw(A.rtw_lo, A.rtw_hi, A.rtw_h, j);
+                const double y1 = -t.y * (f[j] + f[n - j]), y2 = 0.5 * (f[j] - f[n - j]);
+                g[j] = y1 + y2;
+                if (j != N) g[n - j] = y1 - y2;
+            }
+        } else {                                                           // COS2I_PRE, Cos_FT2.rs:97-131
+            for (u64 k = c; k < N; k += C) {
+                if (k == 0) { g[0] = f[0]; g[1] = 2.0 * f[n - 1]; continue; }
+                const double2 t = two_level_tw(A.rtw_lo, A.rtw_hi, A.rtw_h, 2 * k);      // (cos, -sin)(k pi/n)
+                const double re = f[2 * k], im = f[2 * k - 1] - f[2 * k + 1];
+                g[2 * k] = re * t.x - im * t.y;
+                g[2 * k + 1] = im * t.x + re * t.y;
+            }
+        }
+    }
+}
+
+// The term of position pos (0 <= pos < N) in the running sum, and the packed-spectrum value that goes to the
+// even output: COS1 forward over Im F_k (Cos_FT.rs:64-67), SINFT forward over Re F_k (NR sinft, last loop),
+// COS2F backwards (pos = N-1-k) over Im(F_k e^{i k pi/n}) after the rotation (Cos_FT2.rs:54-85).
+NRB_DEV void scan_term(const AuxParams &A, const double2 *G, u64 pos, int mode, double &term, double &even, u64 &k)
+{
+    const u64 N = A.n / 2;
+    if (mode == COS1) { k = pos; const double2 z = G[k]; term = k ? z.y : 0.0; even = z.x; }
+    else if (mode == SINFT) { k = pos; const double2 z = G[k]; term = k ? z.x : 0.5 * z.x; even = k ? z.y : 0.0; }
+    else {
+        k = N - 1 - pos;
+        double2 z = G[k];
+        if (k) { const double2 t = two_level_tw(A.rtw_lo, A.rtw_hi, A.rtw_h, 2 * k); z = make_double2(z.x * t.x + z.y * t.y, z.y * t.x - z.x * t.y); }
+        term = z.y; even = z.x;
+    }
+}
+
+// Three-phase running sum, chunks of m positions: op 0 = chunk sums into b[l*nch + c]; op 1 = one thread per
+// line turns them into chunk prefixes (starting value: COS1 the sum of the pre-pass in speq[l].x, SINFT 0,
+// COS2F 0.5 F_{n/2}); op 2 = every chunk walks its positions again and writes the even and odd outputs.
+NRB_DEV void aux_scan(const AuxParams &A, u64 gtid, u64 gthreads)
+{
+    const u64 N = A.n / 2, K = A.m, nch = (N + K - 1) / K;
+    const int mode = A.dir;
+    double2 *P = const_cast<double2 *>(A.b);
+    if (A.op == 1) {
+        for (u64 l = gtid; l < A.count; l += gthreads) {
+            double run = mode == COS1 ? A.speq[l].x : mode == COS2F ? 0.5 * A.a[(i64)(l * N)].y : 0.0;
+            for (u64 c = 0; c < nch; ++c) { const double s = P[l * nch + c].x; P[l * nch + c].x = run; run += s; }
+        }
+        return;
+    }
+    const u64 items = A.count * nch;
+    for (u64 it = gtid; it < items; it += gthreads) {
+        const u64 c = it % nch, l = it / nch;
+        const double2 *G = A.a + (i64)(l * N);
+        const u64 p0 = c * K, p1 = p0 + K < N ? p0 + K : N;
+        if (A.op == 0) {
+            double s = 0.0;
+            for (u64 pos = p0; pos < p1; ++pos) { double term, even; u64 k; scan_term(A, G, pos, mode, term, even, k); s += term; }
+            P[it] = make_double2(s, 0.0);
+        } else {
+            double *f = reinterpret_cast<double *>(A.out) + (i64)l * A.out_stride + 1;
+            double run = P[it].x;
+            if (mode == COS1 && c == 0) f[A.n] = G[0].y;                  // Cos_FT.rs:61  y[n+1] = y[2]
+            for (u64 pos = p0; pos < p1; ++pos) {
+                double term, even; u64 k;
+                scan_term(A, G, pos, mode, term, even, k);
+                if (mode == COS2F) { f[2 * k] = even; f[2 * k + 1] = run; run += term; }   // exclusive, from the top
+                else { run += term; f[2 * k] = even; f[2 * k + 1] = run; }                 // inclusive
+            }
+        }
+    }
+}
+
 // Cross-GPU barrier of the fused slab exchange, without a collective: after its stage-0 kernels (whose
 // peer stores are complete when the kernel ends) every rank publishes the call's epoch into slot `rank`
 // of each peer's flag array; stage 1 starts after the local array shows the epoch in all slots.
@@ -381,6 +506,8 @@ NRB_DEV void aux_body(const AuxParams &A, u64 gtid, u64 gthreads)
     case AUX_PACK2: aux_pack2(A, gtid, gthreads); break;
     case AUX_TWOFFT_SPLIT: aux_twofft_split(A, gtid, gthreads); break;
     case AUX_SCALE: aux_scale(A, gtid, gthreads); break;
+    case AUX_COSFT: aux_cosft(A, gtid, gthreads); break;
+    case AUX_SCAN: aux_scan(A, gtid, gthreads); break;
     default: aux_correl_direct(A, gtid, gthreads); break;
     }
 }

@@ -240,7 +240,9 @@ enum AuxKind {
 };
 enum SpectralOp { SPEC_CONV_MUL = 0, SPEC_CONV_DIV = 1, SPEC_CORREL = 2, SPEC_AUTOCORREL = 3 };
 enum ReduceMode { RED_SUM_SQ = 0, RED_CENTERED_SQ = 1, RED_PARTIALS = 2 };
-enum StatsMode { STATS_FAST = 0, STATS_MEAN = 1, STATS_STD = 2 };
+enum StatsMode { STATS_FAST = 0, STATS_MEAN = 1, STATS_STD = 2, STATS_SUM = 3 };
+// AUX_COSFT / AUX_SCAN transform selector (AuxParams::dir)
+enum CosMode { COS1 = 0, COS2F = 1, SINFT = 2, COS2I_PRE = 3, COS2I_POST = 4 };
 
 struct AuxParams {
     int kind;

@@ -711,6 +711,55 @@ int build_twofft(Plan &pl, Builder &B)
     return B.rc;
 }
 
+// cosft1 (Cos_FT.rs:7), cosft2 (Cos_FT2.rs:7) and sinft (README.md:72) -- NR's O(n) pre/post-processing around
+// realft (ledger D11).  dims = {n}; io = batch lines of the reference's 1-based arrays (ld = n + 2 doubles for
+// cosft1, n + 1 otherwise; element 0 of a line is unused).  Workspace: G (realft work array, n/2 complex per
+// line), the pre-pass partial sums, the chunk sums of the running sum, one (sum, -) pair per line.
+int build_cosft(Plan &pl, Builder &B, int kind, int dir)
+{
+    const u64 n = pl.dims[0], N = n / 2, L = pl.batch;
+    const int p = ilog2((size_t)N);
+    const i64 ld = (i64)(kind == NRB_KIND_COSFT1 ? n + 2 : n + 1);
+    const int mode = kind == NRB_KIND_COSFT1 ? COS1 : kind == NRB_KIND_SINFT ? SINFT : COS2F;
+    const bool inverse = kind == NRB_KIND_COSFT2 && dir < 0;
+    const u64 C = N + 1 < 16384 ? N + 1 : 16384;        // pre-pass accumulators per line
+    const u64 C1 = C > 256 ? 128 : 0;
+    const u64 K = 128, nch = (N + K - 1) / K;           // running sum: positions per chunk
+    i64 off = 0;
+    const BufRef IO(BUF_IO, 0), G(BUF_WS, off); off += (i64)(L * N);
+    const BufRef T(BUF_WS, off); off += real_needs_separate_untangle(p) ? (i64)(L * N) : 0;
+    const BufRef P0(BUF_WS, off); off += (i64)(L * C);
+    const BufRef P1(BUF_WS, off); off += (i64)(L * C1);
+    const BufRef PC(BUF_WS, off); off += (i64)(L * nch);
+    const BufRef INIT(BUF_WS, off); off += (i64)L;
+    B.need_ws((size_t)off);
+    const FourStepTable tw = fourstep_table(ilog2((size_t)n) + (kind == NRB_KIND_COSFT2 ? 2 : 1));
+    auto with_tw = [&](Step st, int m) {
+        st.ap.dir = m;
+        st.ap.rtw_lo = tw.lo; st.ap.rtw_hi = tw.hi; st.ap.rtw_h = tw.h;
+        return st;
+    };
+    if (inverse) {
+        B.prog->steps.push_back(with_tw(make_aux(AUX_COSFT, 0, IO, BufRef(), G, BufRef(), n, C, L, ld, 0, 0), COS2I_PRE));
+        emit_real(B, G, G, T, 0, L, p, -1, REAL_PACKED, BufRef());
+        B.prog->steps.push_back(with_tw(make_aux(AUX_COSFT, 0, G, BufRef(), IO, BufRef(), n, C, L, 0, 0, ld), COS2I_POST));
+        return B.rc;
+    }
+    B.prog->steps.push_back(with_tw(make_aux(AUX_COSFT, 0, IO, mode == COS1 ? P0 : BufRef(), G, BufRef(), n, C, L, ld, 0, 0), mode));
+    if (mode == COS1) {
+        if (C1) {
+            B.prog->steps.push_back(make_aux(AUX_REDUCE, RED_PARTIALS, P0, BufRef(), P1, BufRef(), C, C1, L, 0, 0, 0));
+            B.prog->steps.push_back(make_aux(AUX_STATS_FINAL, STATS_SUM, P1, BufRef(), INIT, BufRef(), n, C1, L, 0, 0, 0));
+        } else {
+            B.prog->steps.push_back(make_aux(AUX_STATS_FINAL, STATS_SUM, P0, BufRef(), INIT, BufRef(), n, C, L, 0, 0, 0));
+        }
+    }
+    emit_real(B, G, G, T, 0, L, p, +1, REAL_PACKED, BufRef());
+    for (int phase = 0; phase < 3; ++phase)
+        B.prog->steps.push_back(with_tw(make_aux(AUX_SCAN, phase, G, PC, IO, INIT, n, K, L, 0, 0, ld), mode));
+    return B.rc;
+}
+
 // power / magnitude spectrum (FFT_1.rs:206-228): dims = {npoints}; io = complex points, out = npoints doubles;
 // exec's `arg` = 1 takes the square root.
 int build_power(Plan &pl, Builder &B)
@@ -773,6 +822,12 @@ int build_plan(Plan &pl, int kind, const size_t *dims, size_t ndim, size_t batch
     case NRB_KIND_POWER:
         if (ndim != 1 || dims[0] == 0) { set_error("power spectrum: empty input"); return NRB_ERR_EMPTY_INPUT; }
         break;
+    case NRB_KIND_COSFT1:
+    case NRB_KIND_COSFT2:
+    case NRB_KIND_SINFT:
+        if (ndim != 1 || dims[0] < 2) { set_error("cosft/sinft: n must be >= 2"); return NRB_ERR_INVALID_DIMS; }
+        if ((rc = check_pow2_dims(dims, 1))) return rc;
+        break;
     default:
         set_error("unknown plan kind");
         return NRB_ERR_INVALID_DIMS;
@@ -794,6 +849,7 @@ int build_plan(Plan &pl, int kind, const size_t *dims, size_t ndim, size_t batch
         case NRB_KIND_CORREL_NORM_FAST: rc = build_correl_norm(pl, B, true); break;
         case NRB_KIND_TWOFFT: rc = build_twofft(pl, B); break;
         case NRB_KIND_POWER: rc = build_power(pl, B); break;
+        case NRB_KIND_COSFT1: case NRB_KIND_COSFT2: case NRB_KIND_SINFT: rc = build_cosft(pl, B, kind, dir); break;
         }
         if (rc != NRB_OK) { set_error("shape not supported by this build"); return rc; }
         for (const Step &st : pl.prog[s].steps) {
@@ -908,6 +964,9 @@ int describe_launch(const Plan &pl, int isign, int idx, char *name, size_t cap, 
         case AUX_PACK2: b = 32.0 * (double)st.ap.count * (double)st.ap.n; break;
         case AUX_TWOFFT_SPLIT: b = 48.0 * (double)st.ap.count * (double)st.ap.n; break;
         case AUX_SCALE: b = 16.0 * (double)st.ap.n; break;
+        case AUX_COSFT: b = 16.0 * (double)st.ap.count * (double)st.ap.n; break;
+        case AUX_SCAN: b = st.ap.op == 1 ? 32.0 * (double)st.ap.count * (double)((st.ap.n / 2 + st.ap.m - 1) / st.ap.m)
+                                         : (st.ap.op == 0 ? 8.0 : 16.0) * (double)st.ap.count * (double)st.ap.n; break;
         default: b = 3.0 * 8.0 * (double)st.ap.count * (double)st.ap.n; break;
         }
     } else {

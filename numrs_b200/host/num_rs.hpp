@@ -107,6 +107,33 @@ inline void twofft(const std::vector<double> &data1, const std::vector<double> &
 }
 } // namespace FFT_2
 
+// ------------------------------------------------------------------ Cos_FT.rs / Cos_FT2.rs / sinft (README.md:72)
+namespace Cos_FT {
+// Cos_FT.rs:7 cosft1(y, n): 1-based array, y[0] unused, data y[1..=n+1] (an out-of-range index panics in Rust)
+inline void cosft1(std::vector<double> &y, std::size_t n)
+{
+    if (y.size() < n + 2) throw Panic("index out of bounds: y must hold n + 2 elements");
+    panic_on(nrb_cosft1(y.data(), n));
+}
+inline void cosft1_optimized(std::vector<double> &y, std::size_t n) { cosft1(y, n); }   // Cos_FT.rs:77
+} // namespace Cos_FT
+namespace Cos_FT2 {
+// Cos_FT2.rs:7 cosft2(y, n, isign): panics on isign outside {1, -1} (Cos_FT2.rs:11)
+inline void cosft2(std::vector<double> &y, std::size_t n, int isign)
+{
+    if (isign != 1 && isign != -1) throw Panic("Invalid isign value. Must be 1 or -1");
+    if (y.size() < n + 1) throw Panic("index out of bounds: y must hold n + 1 elements");
+    panic_on(nrb_cosft2(y.data(), n, isign));
+}
+} // namespace Cos_FT2
+namespace Sin_FT {
+inline void sinft(std::vector<double> &y, std::size_t n)
+{
+    if (y.size() < n + 1) throw Panic("index out of bounds: y must hold n + 1 elements");
+    panic_on(nrb_sinft(y.data(), n));
+}
+} // namespace Sin_FT
+
 // ------------------------------------------------------------------ Fourn.rs / Real_FT3.rs:35
 namespace Fourn {
 

@@ -649,3 +649,130 @@ int orc_correl_normalized(const double *d1, size_t n1, const double *d2, size_t 
  * (deviation D10): the literal code feeds |F|^2 to the placeholder inverse DFT in that placeholder's own
  * layout and without the 1/no2 factor; the intent is the autocorrelation, i.e. correl(data, data). */
 int orc_autocorrel_fast(const double *d, size_t n, double *ans) { return orc_correl(d, n, d, n, ans); }
+
+/* ==========================================================================================
+ * N3 of SURVEY.md 8f: cosft1 / cosft2 / sinft around realft.  The reference's bodies are NR
+ * transliterations that end in `unimplemented!()` (Cos_FT.rs:70-74, Cos_FT2.rs realft stub), so these are
+ * NR intent (deviation D11), with the reference's 1-based calling convention kept: y[0] is unused,
+ * the data are y[1..=n+1] (cosft1, Cos_FT.rs:7-67: `y[n + 1]` is read and written) resp. y[1..=n]
+ * (cosft2, Cos_FT2.rs:7-13; sinft, README.md:72 -- listed, no source file).  Twiddles by NR's recurrences, as
+ * the reference (Cos_FT.rs:9-12,27-34; Cos_FT2.rs:17-21,40-44).  Places where the reference departs from NR:
+ *   cosft1: `y[2] = sum` after `y[n+1] = y[2]` is missing (Cos_FT.rs:60-61);
+ *   cosft2: the first loop uses a constant wi1 (Cos_FT2.rs:26-36 updates it only afterwards, :39-44), the
+ *           second loop's scan adds wr1 / wi1 instead of the state (Cos_FT2.rs:58-59), the inverse rotation has
+ *           both outputs built from y[i+1]*wr (Cos_FT2.rs:125-126) and zero increments (:112-113).
+ * ======================================================================================== */
+void orc_cosft1(double *y, size_t n)
+{
+    const double theta = ORC_PI / (double)n;
+    double wtemp = sin(0.5 * theta);
+    const double wpr = -2.0 * wtemp * wtemp, wpi = sin(theta);
+    double wr = 1.0, wi = 0.0;
+    const size_t n2 = n + 2;
+    size_t j;
+    double sum = 0.5 * (y[1] - y[n + 1]);                        /* Cos_FT.rs:17-18 */
+    y[1] = 0.5 * (y[1] + y[n + 1]);
+    for (j = 2; j <= (n >> 1); ++j) {                            /* Cos_FT.rs:36-52 */
+        wtemp = wr;
+        wr = wr * wpr - wi * wpi + wr;
+        wi = wi * wpr + wtemp * wpi + wi;
+        const double y1 = 0.5 * (y[j] + y[n2 - j]);
+        const double y2 = y[j] - y[n2 - j];
+        y[j] = y1 - wi * y2;
+        y[n2 - j] = y1 + wi * y2;
+        sum += wr * y2;
+    }
+    orc_realft(y + 1, n, 1);                                     /* Cos_FT.rs:58 */
+    y[n + 1] = y[2];                                             /* Cos_FT.rs:61 */
+    y[2] = sum;                                                  /* NR; missing in the reference */
+    for (j = 4; j <= n; j += 2) { sum += y[j]; y[j] = sum; }     /* Cos_FT.rs:64-67 */
+}
+
+int orc_cosft2(double *y, size_t n, int isign)
+{
+    if (isign != 1 && isign != -1) return -3;                    /* Cos_FT2.rs:11 panics */
+    const double theta = 0.5 * ORC_PI / (double)n;
+    double wr1 = cos(theta), wi1 = sin(theta), wr = 1.0, wi = 0.0, wtemp;
+    const double wpr = -2.0 * wi1 * wi1, wpi = sin(2.0 * theta);
+    size_t i;
+    if (isign == 1) {
+        for (i = 1; i <= n / 2; ++i) {                           /* Cos_FT2.rs:26-36 (+ NR's update inside) */
+            const double y1 = 0.5 * (y[i] + y[n - i + 1]);
+            const double y2 = wi1 * (y[i] - y[n - i + 1]);
+            y[i] = y1 + y2;
+            y[n - i + 1] = y1 - y2;
+            wtemp = wr1;
+            wr1 = wr1 * wpr - wi1 * wpi + wr1;
+            wi1 = wi1 * wpr + wtemp * wpi + wi1;
+        }
+        orc_realft(y + 1, n, 1);                                 /* Cos_FT2.rs:48 */
+        for (i = 3; i <= n; i += 2) {                            /* Cos_FT2.rs:54-77 */
+            wtemp = wr;
+            wr = wr * wpr - wi * wpi + wr;
+            wi = wi * wpr + wtemp * wpi + wi;
+            const double y1 = y[i] * wr - y[i + 1] * wi;
+            const double y2 = y[i + 1] * wr + y[i] * wi;
+            y[i] = y1;
+            y[i + 1] = y2;
+        }
+        double sum = 0.5 * y[2];                                 /* Cos_FT2.rs:80-85 */
+        for (i = n; i >= 2; i -= 2) {
+            const double sum1 = sum;
+            sum += y[i];
+            y[i] = sum1;
+        }
+    } else {
+        const double ytemp = y[n];                               /* Cos_FT2.rs:97-101 */
+        for (i = n; i >= 4; i -= 2) y[i] = y[i - 2] - y[i];
+        y[2] = 2.0 * ytemp;
+        for (i = 3; i <= n; i += 2) {                            /* Cos_FT2.rs:108-131 (NR rotation) */
+            wtemp = wr;
+            wr = wr * wpr - wi * wpi + wr;
+            wi = wi * wpr + wtemp * wpi + wi;
+            const double y1 = y[i] * wr + y[i + 1] * wi;
+            const double y2 = y[i + 1] * wr - y[i] * wi;
+            y[i] = y1;
+            y[i + 1] = y2;
+        }
+        orc_realft(y + 1, n, -1);                                /* Cos_FT2.rs:134 */
+        for (i = 1; i <= n / 2; ++i) {                           /* Cos_FT2.rs:142-162 */
+            const double y1 = y[i] + y[n - i + 1];
+            const double y2 = (0.5 / wi1) * (y[i] - y[n - i + 1]);
+            y[i] = 0.5 * (y1 + y2);
+            y[n - i + 1] = 0.5 * (y1 - y2);
+            wtemp = wr1;
+            wr1 = wr1 * wpr - wi1 * wpi + wr1;
+            wi1 = wi1 * wpr + wtemp * wpi + wi1;
+        }
+    }
+    return 0;
+}
+
+/* NR sinft; the reference lists it (README.md:72) but has no source file for it */
+void orc_sinft(double *y, size_t n)
+{
+    const double theta = ORC_PI / (double)n;
+    double wtemp = sin(0.5 * theta);
+    const double wpr = -2.0 * wtemp * wtemp, wpi = sin(theta);
+    double wr = 1.0, wi = 0.0, sum;
+    const size_t n2 = n + 2;
+    size_t j;
+    y[1] = 0.0;
+    for (j = 2; j <= (n >> 1) + 1; ++j) {
+        wtemp = wr;
+        wr = wr * wpr - wi * wpi + wr;
+        wi = wi * wpr + wtemp * wpi + wi;
+        const double y1 = wi * (y[j] + y[n2 - j]);
+        const double y2 = 0.5 * (y[j] - y[n2 - j]);
+        y[j] = y1 + y2;
+        y[n2 - j] = y1 - y2;
+    }
+    orc_realft(y + 1, n, 1);
+    y[1] *= 0.5;
+    sum = y[2] = 0.0;
+    for (j = 1; j <= n - 1; j += 2) {
+        sum += y[j];
+        y[j] = y[j + 1];
+        y[j + 1] = sum;
+    }
+}

@@ -70,6 +70,12 @@ def lib():
         L.orc_correl_normalized.restype = ctypes.c_int
         L.orc_autocorrel_fast.argtypes = [_dp, _sz, _dp]
         L.orc_autocorrel_fast.restype = ctypes.c_int
+        L.orc_cosft1.argtypes = [_dp, _sz]
+        L.orc_cosft1.restype = None
+        L.orc_cosft2.argtypes = [_dp, _sz, ctypes.c_int]
+        L.orc_cosft2.restype = ctypes.c_int
+        L.orc_sinft.argtypes = [_dp, _sz]
+        L.orc_sinft.restype = None
         L.orc_num_threads.argtypes = []
         L.orc_num_threads.restype = ctypes.c_int
         _LIB = L
@@ -219,6 +225,27 @@ def autocorrel_fast(d):
     ans = np.zeros(max(1, d.size))
     rc = lib().orc_autocorrel_fast(_p(d), d.size, _p(ans))
     return rc, ans[:d.size]
+
+
+def cosft1(y, n):
+    """Cos_FT.rs:7: in place on the 1-based array y[0..n+2) (y[0] unused, data y[1..=n+1])."""
+    assert y.dtype == np.float64 and y.size >= n + 2
+    lib().orc_cosft1(_p(y), n)
+    return y
+
+
+def cosft2(y, n, isign):
+    """Cos_FT2.rs:7: in place on the 1-based array y[0..n+1) (y[0] unused, data y[1..=n])."""
+    assert y.dtype == np.float64 and y.size >= n + 1
+    rc = lib().orc_cosft2(_p(y), n, isign)
+    return rc, y
+
+
+def sinft(y, n):
+    """NR sinft (README.md:72): in place on the 1-based array y[0..n+1)."""
+    assert y.dtype == np.float64 and y.size >= n + 1
+    lib().orc_sinft(_p(y), n)
+    return y
 
 
 def num_threads():

@@ -30,6 +30,9 @@ extern "C" {
                                  ans: *mut c_double) -> c_int;
     pub fn nrb_autocorrel_fast(data: *const c_double, n: usize, ans: *mut c_double) -> c_int;
     pub fn nrb_twofft(d1: *const c_double, d2: *const c_double, n: usize, fft1: *mut c_double, fft2: *mut c_double) -> c_int;
+    pub fn nrb_cosft1(y: *mut c_double, n: usize) -> c_int;
+    pub fn nrb_cosft2(y: *mut c_double, n: usize, isign: c_int) -> c_int;
+    pub fn nrb_sinft(y: *mut c_double, n: usize) -> c_int;
     pub fn nrb_power_spectrum(c: *const c_double, npoints: usize, take_sqrt: c_int, out: *mut c_double) -> c_int;
 }
 

@@ -281,6 +281,36 @@ pub mod Correlation {
     }
 }
 
+pub mod Cos_FT {
+    use crate::ffi::*;
+    /// reference: src/Cos_FT.rs:7 (1-based array: y[0] unused, data y[1..=n+1])
+    pub fn cosft1(y: &mut [f64], n: usize) {
+        assert!(y.len() >= n + 2, "index out of bounds: y must hold n + 2 elements");
+        panic_on(unsafe { nrb_cosft1(y.as_mut_ptr(), n) });
+    }
+    /// reference: src/Cos_FT.rs:77
+    pub fn cosft1_optimized(y: &mut [f64], n: usize) { cosft1(y, n) }
+}
+
+pub mod Cos_FT2 {
+    use crate::ffi::*;
+    /// reference: src/Cos_FT2.rs:7
+    pub fn cosft2(y: &mut [f64], n: usize, isign: i32) {
+        if isign != 1 && isign != -1 { panic!("Invalid isign value: {}. Must be 1 or -1", isign); }
+        assert!(y.len() >= n + 1, "index out of bounds: y must hold n + 1 elements");
+        panic_on(unsafe { nrb_cosft2(y.as_mut_ptr(), n, isign) });
+    }
+}
+
+pub mod Sin_FT {
+    use crate::ffi::*;
+    /// README.md:72 lists sinft; the reference has no source file for it (NR semantics)
+    pub fn sinft(y: &mut [f64], n: usize) {
+        assert!(y.len() >= n + 1, "index out of bounds: y must hold n + 1 elements");
+        panic_on(unsafe { nrb_sinft(y.as_mut_ptr(), n) });
+    }
+}
+
 pub mod FFT_2 {
     use crate::ffi::*;
     /// reference: src/FFT_2.rs:3 (asserts :5-7)

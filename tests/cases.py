@@ -156,3 +156,36 @@ def check_spectrum(L, npoints, seed=1013):
     c = gen(seed, 2 * npoints)
     assert rel(nb.power_spectrum(c, L), O.power_spectrum(c)) <= 1e-15
     assert rel(nb.magnitude_spectrum(c, L), O.power_spectrum(c, True)) <= 1e-15
+
+
+def check_cosft1(L, n, seed=1014):
+    y = np.concatenate([[123.0], gen(seed, n + 1)])          # y[0] is unused and must stay untouched
+    ref = O.cosft1(y.copy(), n)
+    got = y.copy()
+    nb.cosft1(got, n, L)
+    assert got[0] == 123.0 and rel(got[1:], ref[1:]) <= tol(n), (n, rel(got[1:], ref[1:]))
+
+
+def check_cosft2(L, n, seed=1015):
+    y = np.concatenate([[123.0], gen(seed, n)])
+    for isign in (1, -1):
+        rc, ref = O.cosft2(y.copy(), n, isign)
+        got = y.copy()
+        nb.cosft2(got, n, isign, L)
+        assert rc == 0 and got[0] == 123.0 and rel(got[1:], ref[1:]) <= tol(n), (n, isign, rel(got[1:], ref[1:]))
+    # round trip = (n/2) x   (Cos_FT2.rs:248-264 with the true factor)
+    z = y.copy()
+    nb.cosft2(z, n, 1, L)
+    nb.cosft2(z, n, -1, L)
+    assert rel(z[1:] * (2.0 / n), y[1:]) <= tol(n)
+
+
+def check_sinft(L, n, seed=1016):
+    y = np.concatenate([[123.0], gen(seed, n)])
+    ref = O.sinft(y.copy(), n)
+    got = y.copy()
+    nb.sinft(got, n, L)
+    assert got[0] == 123.0 and rel(got[1:], ref[1:]) <= tol(n), (n, rel(got[1:], ref[1:]))
+    # the sine transform is its own inverse up to 2/n (y[1] is defined as 0)
+    nb.sinft(got, n, L)
+    assert rel(got[2:] * (2.0 / n), y[2:]) <= tol(n)

@@ -35,6 +35,7 @@ int main(int argc, char **argv)
     // Real_FT.rs:5-6, Real_FT3.rs:17-19
     { std::vector<double> d(6); CHECK(throws<Panic>([&] { Real_FT::realft(d, 5, 1); })); }
     { std::vector<double> a(4), b(4), f(8), g(10); CHECK(throws<Panic>([&] { FFT_2::twofft(a, b, f, g); })); }   // FFT_2.rs:6
+    { std::vector<double> y(9); CHECK(throws<Panic>([&] { Cos_FT2::cosft2(y, 8, 0); })); }                        // Cos_FT2.rs:266-272
     { std::vector<double> d(64), s(32); CHECK(throws<Panic>([&] { Real_FT3::rlft3(d, s, 4, 4, 4, 0); })); }
     { std::vector<double> d(64), s(16); CHECK(throws<Panic>([&] { Real_FT3::rlft3(d, s, 4, 4, 4, 1); })); }
     if (gpu) {
@@ -68,6 +69,19 @@ int main(int argc, char **argv)
             for (std::size_t k = 1; k < m / 2; ++k) CHECK(std::fabs(f1[2 * k] - f1[2 * (m - k)]) < 1e-10 && std::fabs(f1[2 * k + 1] + f1[2 * (m - k) + 1]) < 1e-10);
             auto pw = FFT_1::power_spectrum_device(f2), hp = FFT_1::power_spectrum(f2);
             for (std::size_t k = 0; k < m; ++k) CHECK(std::fabs(pw[k] - hp[k]) <= 4e-16 * hp[k]);   // the device contracts x*x + y*y into an FMA
+        }
+        // Cos_FT2.rs:248-264 round trip (true factor n/2); cosft1 of a constant: F_0 = n c, F_k = 0 for even k > 0
+        {
+            const std::size_t m = 16;
+            std::vector<double> y(m + 1), y0;
+            for (std::size_t i = 0; i <= m; ++i) y[i] = i == 0 ? 0.0 : std::sin((double)i);
+            y0 = y;
+            Cos_FT2::cosft2(y, m, 1);
+            Cos_FT2::cosft2(y, m, -1);
+            for (std::size_t i = 1; i <= m; ++i) CHECK(std::fabs(y[i] * 2.0 / m - y0[i]) < 1e-10);
+            std::vector<double> c(m + 2, 1.0);
+            Cos_FT::cosft1(c, m);
+            CHECK(std::fabs(c[1] - (double)m) < 1e-10 && std::fabs(c[3]) < 1e-10 && std::fabs(c[2]) < 1e-10);
         }
         // Real_FT3.rs:268-311 with the true factor N/2
         std::vector<double> d(512), s(128, 0.0), o(512);

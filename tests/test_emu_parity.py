@@ -365,3 +365,42 @@ def test_next_rows_plan_api_batched(emu):
         r1, r2 = O.twofft(a[i * n:(i + 1) * n], b[i * n:(i + 1) * n])
         assert cases.rel(f[i * per:(i + 1) * per], r1) <= cases.tol(n)
         assert cases.rel(f[(cnt + i) * per:(cnt + i + 1) * per], r2) <= cases.tol(n)
+
+
+# ---------------------------------------------------------------- cosft1 / cosft2 / sinft
+@pytest.mark.parametrize("n", [2, 4, 8, 64, 256, 1024, 4096, 1 << 15])
+def test_cosft_sinft(emu, n):
+    cases.check_cosft1(emu, n)
+    cases.check_cosft2(emu, n)
+    cases.check_sinft(emu, n)
+
+
+def test_cosft_long_line_path_batch_and_errors(emu):
+    emu.set_option("row_max_log2", 2)       # realft = c2c passes + standalone untangle
+    emu.set_option("col_max_log2", 3)
+    for n in (64, 2048):
+        cases.check_cosft1(emu, n)
+        cases.check_cosft2(emu, n)
+        cases.check_sinft(emu, n)
+    emu.set_option("row_max_log2", 13)
+    emu.set_option("col_max_log2", 10)
+    # Cos_FT2.rs:266-272: invalid isign panics
+    with pytest.raises(nb.NrbError):
+        nb.cosft2(np.zeros(9), 8, 0, emu)
+    assert emu.cosft1(np.zeros(8), 6) == nb._lib.NRB_ERR_NOT_POW2
+    # device-resident plan API, batched lines
+    n, cnt = 512, 5
+    y = O.fill_uniform(31, 0, cnt * (n + 2))
+    refs = [O.cosft1(y[i * (n + 2):(i + 1) * (n + 2)].copy(), n) for i in range(cnt)]
+    plan = emu.plan_create(nb.KIND_COSFT1, [n], batch=cnt)
+    plan.exec(y.ctypes.data)
+    plan.destroy()
+    for i in range(cnt):
+        assert cases.rel(y[i * (n + 2) + 1:(i + 1) * (n + 2)], refs[i][1:]) <= cases.tol(n)
+    y = O.fill_uniform(32, 0, cnt * (n + 1))
+    refs = [O.cosft2(y[i * (n + 1):(i + 1) * (n + 1)].copy(), n, 1)[1] for i in range(cnt)]
+    plan = emu.plan_create(nb.KIND_COSFT2, [n], batch=cnt)
+    plan.exec(y.ctypes.data, isign=1)
+    plan.destroy()
+    for i in range(cnt):
+        assert cases.rel(y[i * (n + 1) + 1:(i + 1) * (n + 1)], refs[i][1:]) <= cases.tol(n)

@@ -172,6 +172,13 @@ def test_spectrum_helpers(gpu, npoints):
     cases.check_spectrum(gpu, npoints)
 
 
+@pytest.mark.parametrize("n", [2, 8, 256, 4096, 1 << 15, 1 << 18, 1 << 22])
+def test_cosft_sinft(gpu, n):
+    cases.check_cosft1(gpu, n)
+    cases.check_cosft2(gpu, n)
+    cases.check_sinft(gpu, n)
+
+
 def test_golden_fixtures(gpu):
     for nn in (8, 64, 1024):
         for s, t in ((1, "p"), (-1, "m")):

@@ -217,3 +217,23 @@ def test_autocorrel_fast_and_spectra_vs_numpy(n):
     z = O.fill_uniform(1013, 0, 2 * n)
     assert np.array_equal(O.power_spectrum(z), z[0::2] ** 2 + z[1::2] ** 2)
     assert np.allclose(O.power_spectrum(z, True), np.abs(c(z)), rtol=1e-15, atol=0)
+
+
+@pytest.mark.parametrize("n", [2, 4, 8, 64, 1024, 1 << 14])
+def test_cosft_sinft_vs_scipy(n):
+    """N3 (ledger D11): NR cosft1 = DCT-I / 2, cosft2(+1) = DCT-II / 2, cosft2(-1) its inverse times n/2,
+    sinft = DST-I / 2 (scipy's unnormalised definitions carry a factor 2)."""
+    from scipy.fft import dct, dst
+    lim = 1e-12 * max(1, np.log2(n))
+    f = O.fill_uniform(1014, 0, n + 1)
+    y = np.concatenate([[7.0], f])
+    O.cosft1(y, n)
+    assert y[0] == 7.0 and rel(y[1:], dct(f, type=1) / 2) < lim
+    f = O.fill_uniform(1015, 0, n)
+    y = np.concatenate([[7.0], f])
+    assert O.cosft2(y, n, 1)[0] == 0 and rel(y[1:], dct(f, type=2) / 2) < lim
+    assert O.cosft2(y, n, -1)[0] == 0 and rel(y[1:] * (2.0 / n), f) < lim
+    assert O.cosft2(y, n, 0)[0] == -3                      # Cos_FT2.rs:11 / :266-272
+    y = np.concatenate([[7.0], f])
+    O.sinft(y, n)
+    assert y[1] == 0.0 and rel(y[2:], dst(f[1:], type=1) / 2) < lim
