@@ -232,10 +232,33 @@ NRB_DEV void aux_reduce(const AuxParams &A, u64 gtid, u64 gthreads)
             for (u64 i = c; i < A.n; i += C) { const double2 v = p[i]; sx += v.x; sy += v.y; }
         } else {
             const double *x = signal_src(A, s);
-            if (A.op == RED_SUM_SQ) {
+            const double mean = A.op == RED_CENTERED_SQ ? A.speq[s].x : 0.0;
+            // 16-byte loads when every signal starts on a 16-byte boundary (n even and aligned bases), four
+            // independent accumulator pairs for latency; same terms, fixed order -> deterministic
+            const bool vec = (A.n % 2 == 0) && (reinterpret_cast<size_t>(x) % 16 == 0);
+            if (vec) {
+                const double2 *x2 = reinterpret_cast<const double2 *>(x);
+                const u64 n2 = A.n / 2;
+                double ax[4] = {0.0, 0.0, 0.0, 0.0}, ay[4] = {0.0, 0.0, 0.0, 0.0};
+                u64 i = c;
+                for (; i + 3 * C < n2; i += 4 * C) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const double2 v = NRB_LDS(x2 + i + (u64)u * C);
+                        if (A.op == RED_SUM_SQ) { ax[u] += v.x + v.y; ay[u] += v.x * v.x + v.y * v.y; }
+                        else { const double a = v.x - mean, b = v.y - mean; ax[u] += a * a + b * b; }
+                    }
+                }
+                for (; i < n2; i += C) {
+                    const double2 v = NRB_LDS(x2 + i);
+                    if (A.op == RED_SUM_SQ) { ax[0] += v.x + v.y; ay[0] += v.x * v.x + v.y * v.y; }
+                    else { const double a = v.x - mean, b = v.y - mean; ax[0] += a * a + b * b; }
+                }
+                sx = (ax[0] + ax[1]) + (ax[2] + ax[3]);
+                sy = (ay[0] + ay[1]) + (ay[2] + ay[3]);
+            } else if (A.op == RED_SUM_SQ) {
                 for (u64 i = c; i < A.n; i += C) { const double v = x[i]; sx += v; sy += v * v; }
             } else {
-                const double mean = A.speq[s].x;
                 for (u64 i = c; i < A.n; i += C) { const double v = x[i] - mean; sx += v * v; }
             }
         }
@@ -259,10 +282,21 @@ NRB_DEV void aux_stats_final(const AuxParams &A, u64 gtid, u64 gthreads)
     }
 }
 
-// out[s][i] = (x[s][i] - mean_s) / std_s, stats in `speq`.  items: count * n.
+// out[s][i] = (x[s][i] - mean_s) / std_s, stats in `speq`.  items: count * n/2 pairs when n is even and the
+// lines are 16-byte aligned (op 1, chosen by the launcher), else count * n.
 NRB_DEV void aux_normalize(const AuxParams &A, u64 gtid, u64 gthreads)
 {
     double *out = reinterpret_cast<double *>(A.out);
+    if (A.op == 1) {
+        const u64 n2 = A.n / 2, items = A.count * n2;
+        for (u64 it = gtid; it < items; it += gthreads) {
+            const u64 i = it % n2, s = it / n2;
+            const double2 st = A.speq[s];
+            const double2 v = NRB_LDS(reinterpret_cast<const double2 *>(signal_src(A, s)) + i);
+            reinterpret_cast<double2 *>(out + (i64)s * A.out_stride)[i] = make_double2((v.x - st.x) / st.y, (v.y - st.x) / st.y);
+        }
+        return;
+    }
     const u64 items = A.count * A.n;
     for (u64 it = gtid; it < items; it += gthreads) {
         const u64 i = it % A.n, s = it / A.n;

@@ -102,7 +102,8 @@ int be_launch_aux(const AuxParams &a, void *stream)
     case AUX_SIGNAL: case AUX_WAIT: items = a.count; break;
     case AUX_REDUCE: items = a.count * a.m; break;
     case AUX_STATS_FINAL: items = a.count; break;
-    case AUX_NORMALIZE: case AUX_PACK2: items = a.count * a.n; break;
+    case AUX_NORMALIZE: items = a.count * (a.op == 1 ? a.n / 2 : a.n); break;
+    case AUX_PACK2: items = a.count * a.n; break;
     case AUX_POWER: case AUX_SCALE: items = a.n; break;
     case AUX_TWOFFT_SPLIT: items = a.count * (a.n / 2 + 1); break;
     case AUX_COSFT: items = a.count * a.m; break;

@@ -679,8 +679,8 @@ int build_correl_norm(Plan &pl, Builder &B, bool fast)
     for (u64 b0 = 0; b0 < pl.batch; b0 += gs) {
         const u64 b1 = (b0 + gs < pl.batch) ? b0 + gs : pl.batch, cnt = b1 - b0;
         // two launches (one per input) so a group's signals and their stats are contiguous ranges
-        B.prog->steps.push_back(make_aux(AUX_NORMALIZE, 0, IO + (i64)(b0 * N), BufRef(), NA, STATS + (i64)b0, n, 0, cnt, (i64)n, 0, (i64)n));
-        B.prog->steps.push_back(make_aux(AUX_NORMALIZE, 0, AUXB + (i64)(b0 * N), BufRef(), NB, STATS + (i64)(pl.batch + b0), n, 0, cnt, (i64)n, 0, (i64)n));
+        B.prog->steps.push_back(make_aux(AUX_NORMALIZE, 1, IO + (i64)(b0 * N), BufRef(), NA, STATS + (i64)b0, n, 0, cnt, (i64)n, 0, (i64)n));
+        B.prog->steps.push_back(make_aux(AUX_NORMALIZE, 1, AUXB + (i64)(b0 * N), BufRef(), NB, STATS + (i64)(pl.batch + b0), n, 0, cnt, (i64)n, 0, (i64)n));
         emit_correl_group(B, NA, NB, ANS + (i64)(b0 * N), F2, T, cnt, n, SPEC_CORREL);
     }
     return B.rc;
