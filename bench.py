@@ -366,7 +366,7 @@ def run_ours(args, rank, world, local_rank):
         else:
             from numrs_b200.dist_rlft3 import SlabRlft3
             G = world
-            slab = SlabRlft3(lib, n1, n2, n3, mode=args.exchange)
+            slab = SlabRlft3(lib, n1, n2, n3, mode=args.exchange, chunks=args.chunks)
             ld, sd, xd = slab.local_doubles, slab.speq_doubles, slab.xchg_doubles
             bufs = [torch.empty(ld, **f64) for _ in range(pool)]
             speq = torch.empty(sd, **f64)
@@ -646,6 +646,7 @@ def main():
     ap.add_argument("--workload", default="rlft3_512", choices=sorted(METRIC))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"], help="multi-GPU rlft3 exchange")
+    ap.add_argument("--chunks", type=int, default=1, help="multi-GPU rlft3, fused exchange: z-chunks of the pipelined exchange (1 = off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -64,6 +64,8 @@ int  nrb_shutdown(void);               /* frees cached plans / scratch of all th
  *   "fuse_zy"           rlft3: run the z and y passes of every x-plane in one persistent launch so the
  *                       y pass reads the z pass's output from L2 (default 0: measured 3-6 % slower on B200); "fuse_lag" = planes the y
  *                       tiles trail behind the z tiles (default 16)
+ *   "xchg_grid_cap"     pipelined slab exchange: CTAs of a peer-store pass (0 = one per tile); fewer CTAs leave SM
+ *                       slots to the local pass running beside it on the second stream
  * Environment overrides at load time: NRB_COL_MAX_LOG2, NRB_ROW_MAX_LOG2, NRB_L2_GROUP_MB,
  * NRB_BATCH_GROUP_MB. */
 int  nrb_set_option(const char *name, long value);
@@ -195,6 +197,16 @@ size_t nrb_slab_recv_bytes(nrb_slab_t plan);
  * `epoch` into this rank's slot of every peer's flag array; phase 1 (before stage 1) spins on the
  * device until all ranks have published `epoch` locally.  Epochs must increase per receive buffer. */
 int    nrb_slab_barrier(nrb_slab_t plan, int phase, unsigned long long epoch, void *stream);
+/* Pipelined exchange (fused mode only): cut the volume into `chunks` z-ranges (a power of two, at most 16;
+ * 1 = off) so that stage 1 of chunk c can run -- on a second stream -- under the NVLink-bound stores of chunk
+ * c + 1.  nrb_slab_stage_part runs one piece: part = -1 is the work before the chunks (forward: the z pass),
+ * part = chunks the work after them (inverse: the z pass), otherwise stage `stage` (0 or 1) of chunk `part`.
+ * Order per direction:  part -1;  for every c: [stage 0 of c, barrier_chunk(0, c)] on the main stream and
+ * [barrier_chunk(1, c), stage 1 of c] on the side stream;  join the streams;  part `chunks`.
+ * Stage 1 no longer runs in place behind stage 0, so the plan owns one extra slab of workspace. */
+int    nrb_slab_set_chunks(nrb_slab_t plan, int chunks);
+int    nrb_slab_stage_part(nrb_slab_t plan, int stage, int part, int isign, double *d_slab, double *d_speq, void *stream);
+int    nrb_slab_barrier_chunk(nrb_slab_t plan, int phase, int chunk, unsigned long long epoch, void *stream);
 int    nrb_slab_destroy(nrb_slab_t plan);
 /* raw (zero-initialised) device memory + CUDA IPC plumbing for the above */
 int    nrb_device_alloc(size_t bytes, void **dptr);

@@ -45,6 +45,7 @@ ABI_SYMBOLS = [
     "nrb_plan_profile", "nrb_plan_describe_launch", "nrb_fill_uniform_device",
     "nrb_slab_create", "nrb_slab_local_doubles", "nrb_slab_speq_doubles", "nrb_slab_xchg_doubles",
     "nrb_slab_stage", "nrb_slab_destroy", "nrb_slab_set_peers", "nrb_slab_recv_bytes", "nrb_slab_barrier",
+    "nrb_slab_set_chunks", "nrb_slab_stage_part", "nrb_slab_barrier_chunk",
     "nrb_device_alloc", "nrb_device_free", "nrb_ipc_export", "nrb_ipc_import", "nrb_ipc_release",
 ]
 
@@ -117,6 +118,9 @@ class Library:
         L.nrb_slab_recv_bytes.argtypes = [_vp]
         L.nrb_slab_recv_bytes.restype = _sz
         L.nrb_slab_barrier.argtypes = [_vp, ctypes.c_int, ctypes.c_ulonglong, _vp]
+        L.nrb_slab_set_chunks.argtypes = [_vp, ctypes.c_int]
+        L.nrb_slab_stage_part.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]
+        L.nrb_slab_barrier_chunk.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_ulonglong, _vp]
         L.nrb_device_alloc.argtypes = [_sz, ctypes.POINTER(_vp)]
         L.nrb_device_free.argtypes = [_vp]
         L.nrb_ipc_export.argtypes = [_vp, ctypes.c_char_p]
@@ -361,6 +365,15 @@ class SlabPlan:
 
     def barrier(self, phase, epoch, stream=0):
         self.lib.check(self.lib.L.nrb_slab_barrier(self.h, phase, epoch, stream or None))
+
+    def set_chunks(self, chunks):
+        self.lib.check(self.lib.L.nrb_slab_set_chunks(self.h, chunks))
+
+    def stage_part(self, stage, part, isign, d_slab, d_speq, stream=0):
+        self.lib.check(self.lib.L.nrb_slab_stage_part(self.h, stage, part, isign, d_slab, d_speq, stream or None))
+
+    def barrier_chunk(self, phase, chunk, epoch, stream=0):
+        self.lib.check(self.lib.L.nrb_slab_barrier_chunk(self.h, phase, chunk, epoch, stream or None))
 
     def stage(self, stage, isign, d_slab, d_speq, d_send, d_recv, stream=0):
         self.lib.check(self.lib.L.nrb_slab_stage(self.h, stage, isign, d_slab, d_speq, d_send or None,

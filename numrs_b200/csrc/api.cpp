@@ -309,7 +309,23 @@ int nrb_slab_barrier(nrb_slab_t p, int phase, unsigned long long epoch, void *st
     if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
     return slab_barrier(p->plan, phase, epoch, stream);
 }
-size_t nrb_slab_recv_bytes(nrb_slab_t p) { return p ? nrb_slab_xchg_doubles(p) * sizeof(double) + 256 : 0; }
+size_t nrb_slab_recv_bytes(nrb_slab_t p) { return p ? nrb_slab_xchg_doubles(p) * sizeof(double) + 8 * 8 * kSlabMaxChunks : 0; }
+int nrb_slab_set_chunks(nrb_slab_t p, int chunks)
+{
+    if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
+    if (chunks > kSlabMaxChunks) return fail(NRB_ERR_INVALID_DIMS, "slab: at most 16 chunks");
+    return slab_set_chunks(p->plan, chunks);
+}
+int nrb_slab_stage_part(nrb_slab_t p, int stage, int part, int isign, double *d_slab, double *d_speq, void *stream)
+{
+    if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
+    return exec_slab_part(p->plan, stage, part, isign, d_slab, d_speq, stream);
+}
+int nrb_slab_barrier_chunk(nrb_slab_t p, int phase, int chunk, unsigned long long epoch, void *stream)
+{
+    if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
+    return slab_barrier_chunk(p->plan, phase, chunk, epoch, stream);
+}
 int nrb_device_alloc(size_t bytes, void **dptr)
 {
     if (!dptr) return fail(NRB_ERR_INVALID_DIMS, "null pointer");

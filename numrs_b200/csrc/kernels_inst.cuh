@@ -71,6 +71,7 @@ int launch_pass_t(const PassParams &p, u64 ntiles, cudaStream_t s)
     if (ntiles == 0) return 0;
     u64 grid = ntiles;
     if (NRB_PERSISTENT && grid > (u64)resident[dev & 63]) grid = (u64)resident[dev & 63];
+    if (p.grid_cap > 0 && grid > (u64)p.grid_cap) grid = (u64)p.grid_cap;
     fft_pass_kernel<LOG2N, LAYOUT, DIR, VARIANT><<<(unsigned)grid, NT, smem, s>>>(p, (unsigned)ntiles);
     return (int)cudaGetLastError();
 }

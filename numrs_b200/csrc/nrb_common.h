@@ -61,6 +61,7 @@ enum Variant { VAR_PLAIN = 0, VAR_REAL = 1, VAR_XPOSE = 2 };
 
 enum RealMode { REAL_NONE = 0, REAL_PACKED = 1, REAL_SPEQ = 2 };
 
+constexpr int kSlabMaxChunks = 16;  // z-chunks of the pipelined slab exchange (flag slots per receive buffer)
 constexpr int kMaxLog2N = 13;       // longest line one CTA transforms in shared memory
 // points each thread owns per stage (compile-time): 16 -> TILE/16 threads and two radix-8 butterflies
 // per thread (128 registers, 2 CTAs/SM), 8 -> TILE/8 threads and one (64 registers, 2 CTAs/SM, twice
@@ -77,9 +78,15 @@ constexpr int kMaxLog2N = 13;       // longest line one CTA transforms in shared
 #ifndef NRB_PPT_COL
 #define NRB_PPT_COL 8
 #endif
+// COL line lengths (bit log2n) that run 16 points/thread instead (256 threads, 128 registers, 2 CTAs/SM): measured
+// +2.5 % at N = 512 and +2 % at N = 64, -3 % at N = 128 and N = 1024 (profiles/r01_tuning.md #23)
+#ifndef NRB_PPT_COL16_MASK
+#define NRB_PPT_COL16_MASK ((1 << 9) | (1 << 6))
+#endif
 NRB_HD constexpr int points_per_thread(int layout, int log2n)
 {
-    return layout == 0 /* LAYOUT_ROW */ ? (log2n <= NRB_PPT_ROW_SPLIT ? NRB_PPT_ROW_SMALL : NRB_PPT_ROW_LARGE) : NRB_PPT_COL;
+    return layout == 0 /* LAYOUT_ROW */ ? (log2n <= NRB_PPT_ROW_SPLIT ? NRB_PPT_ROW_SMALL : NRB_PPT_ROW_LARGE)
+                                        : (((NRB_PPT_COL16_MASK >> log2n) & 1) ? 16 : NRB_PPT_COL);
 }
 
 // ---- radix plan per log2(N): stage radices, first stage first ----
@@ -196,6 +203,8 @@ struct PassParams {
     double2 *out_peer[8];
     i64 out_peer_off;
     int out_peer_on;
+    int grid_cap;           // > 0: launch at most this many CTAs (they loop over the tiles); used to leave SM slots
+                            // to the local pass that runs beside an NVLink-bound exchange pass
     u64 q_begin, q_end;
     int logA, logB;
     int tw_on;              // multiply output k of line q by exp(-/+ 2 pi i q1 k / M)

@@ -48,6 +48,7 @@ static Tunables &tunables_mut()
         x.batch_group_bytes = (u64)env_int("NRB_BATCH_GROUP_MB", 512) << 20;
         x.fuse_zy = env_int("NRB_FUSE_ZY", 0);
         x.fuse_lag = env_int("NRB_FUSE_LAG", 16);
+        x.xchg_grid_cap = env_int("NRB_XCHG_GRID_CAP", 0);
         return x;
     }();
     if (t.col_max_log2 < 1) t.col_max_log2 = 1;
@@ -71,6 +72,7 @@ int set_tunable(const char *name, long value)
     else if (n == "batch_group_bytes") t.batch_group_bytes = (u64)value;
     else if (n == "fuse_zy") t.fuse_zy = (int)value;
     else if (n == "fuse_lag") t.fuse_lag = (int)value;
+    else if (n == "xchg_grid_cap") t.xchg_grid_cap = (int)value;
     else return -1;
     tunables_mut();   // re-clamp
     return 0;
@@ -1064,6 +1066,114 @@ int build_slab_plan(SlabPlan &sp, size_t nn1, size_t nn2, size_t nn3, int nranks
     return NRB_OK;
 }
 
+// ---- pipelined exchange -------------------------------------------------------------------------------
+// Lines of the x and y passes are (y or x_local, z).  Ordering them (z-chunk, y or x_local, z within chunk)
+// makes a z-chunk a contiguous line range, so stage 0 can publish chunk c (all ranks' stores for that
+// z-range have landed) while it works on chunk c+1, and stage 1 of chunk c runs on a second stream under the
+// NVLink-bound stores of chunk c+1.  Because stage 1 then overlaps stage 0, the two must not share a buffer:
+// forward  z pass: slab -> work;  x pass (c): work -> peers;  y pass (c): recv -> slab
+// inverse  y pass (c): slab -> peers;  x pass (c): recv -> work;  z pass: work -> slab
+// The speq planes travel with chunk 0.  `work` sits in the plan's workspace after the [nn1][Y] speq scratch.
+namespace {
+void chunk_lines(Step &st, u64 mid, i64 mid_stride_in, i64 mid_stride_out, u64 N3, u64 Zc, int c)
+{
+    PassParams &pp = st.pp;
+    pp.logB = ilog2((size_t)Zc);
+    pp.logA = ilog2((size_t)mid);
+    pp.in_s0 = (i64)Zc; pp.in_s1 = mid_stride_in; pp.in_s2 = 1;
+    pp.out_s0 = (i64)Zc; pp.out_s1 = mid_stride_out; pp.out_s2 = 1;
+    pp.q_begin = (u64)c * mid * Zc;
+    pp.q_end = (u64)(c + 1) * mid * Zc;
+    st.ntiles = tiles_for(st.key.log2n, st.key.layout, pp.q_end - pp.q_begin);
+    (void)N3;
+}
+} // namespace
+
+int slab_set_chunks(SlabPlan &sp, int chunks)
+{
+    const u64 G = (u64)sp.nranks, X = sp.nn1 / G, Y = sp.nn2 / G, N3 = sp.nn3 / 2;
+    const int p1 = ilog2(sp.nn1), p2 = ilog2(sp.nn2), p3 = ilog2((size_t)N3);
+    if (chunks < 1 || !is_pow2((size_t)chunks)) { set_error("slab: chunks must be a power of two"); return NRB_ERR_INVALID_DIMS; }
+    for (int s = 0; s < 2; ++s) sp.part[s].clear();
+    sp.chunks = 1;
+    if (chunks == 1) return NRB_OK;
+    const u64 Zc = N3 / (u64)chunks;
+    // (a chunk narrower than a COL tile's line count still works -- every thread addresses its own line -- but
+    // shortens the contiguous runs; at 512^3 a tile has 8 lines and a chunk 32 or more)
+    if (Zc < 1 || Zc * (u64)chunks != N3) { set_error("slab: too many chunks for this nn3"); return NRB_ERR_INVALID_DIMS; }
+    const i64 BLK = (i64)(X * Y * (N3 + 1)), SPQ = (i64)(X * Y * N3);
+    const size_t speq_ws = (size_t)(sp.nn1 * Y), work_elems = (size_t)(sp.nn1 * Y * N3);
+    if (sp.ws_elems < speq_ws + work_elems) {
+        void *nw = nullptr;
+        if (be_malloc(&nw, (speq_ws + work_elems) * sizeof(double2)) != 0) { set_error("slab: work buffer allocation failed"); return NRB_ERR_OOM; }
+        if (sp.ws) be_free(sp.ws);
+        sp.ws = nw;
+        sp.ws_elems = speq_ws + work_elems;
+    }
+    const BufRef SLAB(BUF_IO, 0), SPEQ(BUF_AUX, 0), XCH(BUF_OUT, 0), WSPEQ(BUF_WS, 0), WORK(BUF_WS, (i64)speq_ws);
+    AxisMap x_blocks;
+    x_blocks.on = true; x_blocks.s0 = 0; x_blocks.es = (i64)(Y * N3); x_blocks.eshift = ilog2((size_t)X); x_blocks.es_hi = BLK;
+    AxisMap x_blocks_speq = x_blocks;
+    x_blocks_speq.es = (i64)Y;
+    AxisMap y_blocks;
+    y_blocks.on = true; y_blocks.s0 = (i64)(Y * N3); y_blocks.es = (i64)N3; y_blocks.eshift = ilog2((size_t)Y); y_blocks.es_hi = BLK;
+    AxisMap y_blocks_speq;
+    y_blocks_speq.on = true; y_blocks_speq.s0 = (i64)Y; y_blocks_speq.es = 1; y_blocks_speq.eshift = ilog2((size_t)Y); y_blocks_speq.es_hi = BLK;
+    int rc = NRB_OK;
+    for (int s = 0; s < 2; ++s) {
+        const int dir = s == 0 ? +1 : -1;
+        sp.part[s].resize((size_t)(2 * chunks + 2));
+        {   // before the chunks
+            Builder B(&sp.part[s][0]);
+            if (dir > 0) emit_real(B, SLAB, WORK, BufRef(), 0, sp.nn1 * Y, p3, +1, REAL_SPEQ, WSPEQ);
+            rc = B.rc ? B.rc : rc;
+        }
+        for (int c = 0; c < chunks; ++c) {
+            Builder B0(&sp.part[s][(size_t)(1 + 2 * c)]), B1(&sp.part[s][(size_t)(2 + 2 * c)]);
+            if (dir > 0) {
+                emit_axis(B0, WORK, XCH, BufRef(), 1, 0, 1, p1, Y * N3, +1, nullptr, &x_blocks);
+                chunk_lines(B0.prog->steps.back(), Y, (i64)N3, (i64)N3, N3, Zc, c);
+                if (c == 0) emit_axis(B0, WSPEQ, XCH + SPQ, BufRef(), 1, 0, 1, p1, Y, +1, nullptr, &x_blocks_speq);
+                emit_axis(B1, XCH, SLAB, BufRef(), X, 0, X, p2, N3, +1, &y_blocks, nullptr);
+                chunk_lines(B1.prog->steps.back(), X, (i64)(Y * N3), (i64)(sp.nn2 * N3), N3, Zc, c);
+                if (c == 0) emit_axis(B1, XCH + SPQ, SPEQ, BufRef(), X, 0, X, p2, 1, +1, &y_blocks_speq, nullptr);
+            } else {
+                emit_axis(B0, SLAB, XCH, BufRef(), X, 0, X, p2, N3, -1, nullptr, &y_blocks);
+                chunk_lines(B0.prog->steps.back(), X, (i64)(sp.nn2 * N3), (i64)(Y * N3), N3, Zc, c);
+                if (c == 0) emit_axis(B0, SPEQ, XCH + SPQ, BufRef(), X, 0, X, p2, 1, -1, nullptr, &y_blocks_speq);
+                if (c == 0) emit_axis(B1, XCH + SPQ, WSPEQ, BufRef(), 1, 0, 1, p1, Y, -1, &x_blocks_speq, nullptr);
+                emit_axis(B1, XCH, WORK, BufRef(), 1, 0, 1, p1, Y * N3, -1, &x_blocks, nullptr);
+                chunk_lines(B1.prog->steps.back(), Y, (i64)N3, (i64)N3, N3, Zc, c);
+            }
+            rc = B0.rc ? B0.rc : (B1.rc ? B1.rc : rc);
+        }
+        {   // after the chunks
+            Builder B(&sp.part[s][(size_t)(2 * chunks + 1)]);
+            if (dir < 0) emit_real(B, WORK, SLAB, BufRef(), 0, sp.nn1 * Y, p3, -1, REAL_SPEQ, WSPEQ);
+            rc = B.rc ? B.rc : rc;
+        }
+    }
+    if (rc != NRB_OK) { for (int s = 0; s < 2; ++s) sp.part[s].clear(); set_error("slab: shape not supported"); return rc; }
+    sp.chunks = chunks;
+    return NRB_OK;
+}
+
+int exec_slab_part(SlabPlan &sp, int stage, int part, int isign, double *d_slab, double *d_speq, void *stream)
+{
+    if (isign != 1 && isign != -1) { set_error("isign must be 1 or -1"); return NRB_ERR_INVALID_ISIGN; }
+    if (!sp.fused || sp.chunks <= 1) { set_error("slab: the pipelined exchange needs nrb_slab_set_peers and nrb_slab_set_chunks"); return NRB_ERR_INVALID_DIMS; }
+    if (part < -1 || part > sp.chunks || ((part >= 0 && part < sp.chunks) && stage != 0 && stage != 1)) { set_error("slab: bad part"); return NRB_ERR_INVALID_DIMS; }
+    const size_t idx = part < 0 ? 0 : part == sp.chunks ? (size_t)(2 * sp.chunks + 1) : (size_t)(1 + 2 * part + stage);
+    const u64 G = (u64)sp.nranks;
+    const i64 BLK = (i64)((sp.nn1 / G) * (sp.nn2 / G) * (sp.nn3 / 2 + 1));
+    double2 *const base[4] = {(double2 *)d_slab, (double2 *)d_speq, sp.peers[sp.rank], (double2 *)sp.ws};
+    PeerExchange px{sp.peers, (i64)sp.rank * BLK};
+    const bool sends = part >= 0 && part < sp.chunks && stage == 0;
+    Program &prog = sp.part[isign == 1 ? 0 : 1][idx];
+    for (Step &st : prog.steps) if (!st.is_aux) st.pp.grid_cap = sends ? tunables().xchg_grid_cap : 0;
+    return run_program(prog, base, 0, stream, nullptr, sends ? &px : nullptr);
+}
+
 int slab_set_peers(SlabPlan &sp, void *const *peer_recv, int count)
 {
     if (!peer_recv) { sp.fused = false; return NRB_OK; }
@@ -1076,6 +1186,12 @@ int slab_set_peers(SlabPlan &sp, void *const *peer_recv, int count)
 
 int slab_barrier(SlabPlan &sp, int phase, unsigned long long epoch, void *stream)
 {
+    return slab_barrier_chunk(sp, phase, 0, epoch, stream);
+}
+
+int slab_barrier_chunk(SlabPlan &sp, int phase, int chunk, unsigned long long epoch, void *stream)
+{
+    if (chunk < 0 || chunk >= kSlabMaxChunks) { set_error("slab: bad chunk"); return NRB_ERR_INVALID_DIMS; }
     if (!sp.fused) { set_error("slab: the flag barrier needs the fused exchange (nrb_slab_set_peers)"); return NRB_ERR_INVALID_DIMS; }
     const u64 G = (u64)sp.nranks;
     const size_t xchg = (size_t)(G * (sp.nn1 / G) * (sp.nn2 / G) * (sp.nn3 / 2 + 1));   // complex elements
@@ -1083,10 +1199,10 @@ int slab_barrier(SlabPlan &sp, int phase, unsigned long long epoch, void *stream
     memset(&ap, 0, sizeof(ap));
     ap.kind = phase == 0 ? AUX_SIGNAL : AUX_WAIT;
     ap.m = epoch;
-    ap.n = (u64)sp.rank;
+    ap.n = (u64)sp.rank + (u64)chunk * G;       // one flag slot per (chunk, rank)
     ap.count = G;
     for (int i = 0; i < sp.nranks; ++i) ap.peer_flags[i] = (unsigned long long *)(sp.peers[i] + xchg);
-    if (phase != 0) ap.peer_flags[0] = (unsigned long long *)(sp.peers[sp.rank] + xchg);
+    if (phase != 0) ap.peer_flags[0] = (unsigned long long *)(sp.peers[sp.rank] + xchg) + (u64)chunk * G;
     if (be_launch_aux(ap, stream) != 0) { set_error(std::string("kernel launch failed: ") + be_last_error()); return NRB_ERR_CUDA; }
     return NRB_OK;
 }

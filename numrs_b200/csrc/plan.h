@@ -92,6 +92,7 @@ struct Tunables {
     int fuse_zy;           // rlft3: fuse the z and y passes of each x-plane through L2 (NRB_FUSE_ZY, default 0: measured slower)
     int fuse_lag;          // planes pass B runs behind pass A (NRB_FUSE_LAG, default 16)
     u64 batch_group_bytes; // convlv/correl: bytes of signals handled per launch group (NRB_BATCH_GROUP_MB, default 512)
+    int xchg_grid_cap;     // pipelined slab exchange: CTAs of an exchange (peer-store) pass, 0 = one per tile (NRB_XCHG_GRID_CAP)
 };
 const Tunables &tunables();
 int set_tunable(const char *name, long value);   // returns 0 if the name is known
@@ -124,13 +125,23 @@ struct SlabPlan {
     size_t nn1, nn2, nn3;
     int nranks, rank;
     Program prog[2][2];    // [isign index][stage]
+    // pipelined exchange: the volume is cut into `chunks` z-ranges; part[isign][0] = work that precedes the
+    // chunks (forward: z pass), part[isign][1 + 2c] / [2 + 2c] = stage 0 / stage 1 of chunk c,
+    // part[isign][1 + 2*chunks] = work that follows them (inverse: z pass)
+    int chunks;
+    std::vector<Program> part[2];
     size_t ws_elems;
     void *ws;
     double2 *peers[8];     // peer receive buffers (fused exchange); peers[rank] is the local one
     bool fused;
-    SlabPlan() : nn1(0), nn2(0), nn3(0), nranks(1), rank(0), ws_elems(0), ws(nullptr), peers{}, fused(false) {}
+    SlabPlan() : nn1(0), nn2(0), nn3(0), nranks(1), rank(0), chunks(1), ws_elems(0), ws(nullptr), peers{}, fused(false) {}
 };
 int build_slab_plan(SlabPlan &sp, size_t nn1, size_t nn2, size_t nn3, int nranks, int rank);
+// cut the exchange into `chunks` z-ranges (1 = off); allocates the out-of-place work slab
+int slab_set_chunks(SlabPlan &sp, int chunks);
+// part: -1 = before the chunks, chunks = after them, else stage `stage` of chunk `part` (fused exchange only)
+int exec_slab_part(SlabPlan &sp, int stage, int part, int isign, double *d_slab, double *d_speq, void *stream);
+int slab_barrier_chunk(SlabPlan &sp, int phase, int chunk, unsigned long long epoch, void *stream);
 int slab_set_peers(SlabPlan &sp, void *const *peer_recv, int count);
 // flag barrier of the fused exchange (flags live right after the exchange area of each receive buffer)
 int slab_barrier(SlabPlan &sp, int phase /*0 = signal, 1 = wait*/, unsigned long long epoch, void *stream);

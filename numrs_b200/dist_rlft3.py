@@ -11,6 +11,9 @@ Inverse (isign=-1) is the mirror image.  Exactly one exchange per direction:
       is a pair of one-warp kernels exchanging epoch flags through the same peer mappings
       (`barrier="flags"`, default: no collective at all on the data path) or a stream-ordered
       1-element NCCL all-reduce (`barrier="nccl"`).
+      `chunks` > 1 pipelines the exchange: the volume is cut into z-ranges, stage 1 of chunk c (HBM-bound, local)
+      runs on a second stream under the NVLink-bound stage-0 stores of chunk c + 1; every chunk has its own
+      epoch flags.
   mode "nccl": stage 0 writes a send buffer, torch.distributed.all_to_all_single moves the blocks.
 """
 import torch
@@ -18,7 +21,7 @@ import torch.distributed as dist
 
 
 class SlabRlft3:
-    def __init__(self, lib, nn1, nn2, nn3, mode="fused", barrier="flags"):
+    def __init__(self, lib, nn1, nn2, nn3, mode="fused", barrier="flags", chunks=1):
         self.lib = lib
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.dims = (nn1, nn2, nn3)
@@ -30,6 +33,11 @@ class SlabRlft3:
         self.barrier = barrier
         self._flag = torch.zeros(1, dtype=torch.int32, device="cuda")
         self._call = 0
+        self.chunks = chunks if (mode == "fused" and barrier == "flags" and self.world > 1) else 1
+        if self.chunks > 1:
+            self.plan.set_chunks(self.chunks)
+            self._side = torch.cuda.Stream(priority=-1)       # stage 1 pieces: short, HBM-bound -> scheduled first
+            self._ev_go, self._ev_done = torch.cuda.Event(), torch.cuda.Event()
         if mode == "fused":
             # two receive buffers, alternated per call, so a peer still reading call k's data in its
             # stage 1 is never overwritten by call k+1's stage 0 (ordered by call k+1's barrier)
@@ -60,6 +68,9 @@ class SlabRlft3:
             peers = self._peers[self._call & 1]
             self._call += 1
             self.plan.set_peers(peers)
+            if self.chunks > 1:
+                self._pipelined(slab, speq, isign, (self._call + 1) // 2)
+                return
             self.plan.stage(0, isign, slab.data_ptr(), speq.data_ptr(), 0, 0, st)
             if self.barrier == "flags":
                 epoch = (self._call + 1) // 2            # per receive buffer: 1, 2, 3, ...
@@ -72,6 +83,22 @@ class SlabRlft3:
             self.plan.stage(0, isign, slab.data_ptr(), speq.data_ptr(), self.send.data_ptr(), 0, st)
             dist.all_to_all_single(self.recv, self.send)
             self.plan.stage(1, isign, slab.data_ptr(), speq.data_ptr(), 0, self.recv.data_ptr(), st)
+
+    def _pipelined(self, slab, speq, isign, epoch):
+        main = torch.cuda.current_stream()
+        st, sd = main.cuda_stream, self._side.cuda_stream
+        d, q, C = slab.data_ptr(), speq.data_ptr(), self.chunks
+        self.plan.stage_part(0, -1, isign, d, q, st)              # forward: z pass (slab -> work)
+        self._ev_go.record(main)
+        self._side.wait_event(self._ev_go)
+        for c in range(C):
+            self.plan.stage_part(0, c, isign, d, q, st)           # x (or y) pass of chunk c, stores go to the peers
+            self.plan.barrier_chunk(0, c, epoch, st)              # chunk c of this rank has landed everywhere
+            self.plan.barrier_chunk(1, c, epoch, sd)              # side stream: chunk c of every rank has landed here
+            self.plan.stage_part(1, c, isign, d, q, sd)
+        self._ev_done.record(self._side)
+        main.wait_event(self._ev_done)
+        self.plan.stage_part(0, C, isign, d, q, st)               # inverse: z pass (work -> slab)
 
     def close(self):
         torch.cuda.synchronize()

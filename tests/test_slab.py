@@ -74,6 +74,68 @@ def test_slab_simulated_ranks(emu, shape, G, fused):
         assert cases.rel(back[r] * (2.0 / x.size), slab_of(x, r, G)) <= cases.tol(x.size), (r, "round trip")
 
 
+def run_simulated_pipelined(L, x, G, isign, chunks, speq_in=None):
+    """Pipelined (z-chunked) fused exchange with all G ranks in one process.  The emulated flag wait does not
+    block, so the test orders the pieces itself: stage 0 of chunk c on every rank, then stage 1 of chunk c."""
+    nn1, nn2, nn3 = x.shape
+    X = nn1 // G
+    plans = [L.slab_create(nn1, nn2, nn3, G, r) for r in range(G)]
+    xd = plans[0].xchg_doubles()
+    if isign == 1:
+        slabs = [slab_of(x, r, G).ravel().copy() for r in range(G)]
+        speqs = [np.zeros(plans[r].speq_doubles()) for r in range(G)]
+    else:
+        slabs = [np.ascontiguousarray(x[r * X:(r + 1) * X]).ravel().copy() for r in range(G)]
+        speqs = [np.ascontiguousarray(speq_in[r * X:(r + 1) * X]).ravel().copy() for r in range(G)]
+    recvs = [np.zeros(plans[0].recv_bytes() // 8) for _ in range(G)]
+    for r in range(G):
+        plans[r].set_peers([rv.ctypes.data for rv in recvs])
+        plans[r].set_chunks(chunks)
+        plans[r].stage_part(0, -1, isign, slabs[r].ctypes.data, speqs[r].ctypes.data)
+    for c in range(chunks):
+        for r in range(G):
+            plans[r].stage_part(0, c, isign, slabs[r].ctypes.data, speqs[r].ctypes.data)
+            plans[r].barrier_chunk(0, c, 1)
+        for r in range(G):
+            plans[r].barrier_chunk(1, c, 1)
+            assert list(recvs[r][xd + c * G:xd + (c + 1) * G].view(np.uint64)) == [1] * G
+            plans[r].stage_part(1, c, isign, slabs[r].ctypes.data, speqs[r].ctypes.data)
+    for r in range(G):
+        plans[r].stage_part(0, chunks, isign, slabs[r].ctypes.data, speqs[r].ctypes.data)
+    for p in plans:
+        p.destroy()
+    return slabs, speqs
+
+
+@pytest.mark.parametrize("shape,G,chunks", [((8, 8, 32), 2, 2), ((16, 16, 64), 4, 4), ((8, 16, 64), 8, 2), ((16, 8, 16), 2, 1)])
+def test_slab_pipelined_exchange(emu, shape, G, chunks):
+    nn1, nn2, nn3 = shape
+    X = nn1 // G
+    x = O.fill_uniform(1006, 0, nn1 * nn2 * nn3).reshape(shape)
+    rd, rs = O.rlft3(x.copy(), np.zeros((nn1, 2 * nn2)), 1)
+    if chunks == 1:     # chunks = 1 switches the pipeline off again
+        plan = emu.slab_create(nn1, nn2, nn3, G, 0)
+        plan.set_chunks(1)
+        with pytest.raises(Exception):
+            plan.stage_part(0, 0, 1, 0, 0)
+        plan.destroy()
+        return
+    slabs, speqs = run_simulated_pipelined(emu, x, G, 1, chunks)
+    for r in range(G):
+        assert cases.rel(slabs[r], rd[r * X:(r + 1) * X]) <= cases.tol(x.size), (r, "data")
+        assert cases.rel(speqs[r], rs[r * X:(r + 1) * X]) <= cases.tol(x.size), (r, "speq")
+    back, _ = run_simulated_pipelined(emu, rd, G, -1, chunks, rs)
+    for r in range(G):
+        assert cases.rel(back[r] * (2.0 / x.size), slab_of(x, r, G)) <= cases.tol(x.size), (r, "round trip")
+    # more chunks than complex z values, or not a power of two
+    plan = emu.slab_create(nn1, nn2, nn3, G, 0)
+    import numrs_b200 as nb
+    for bad in (nn3, 3):
+        with pytest.raises(nb.NrbError):
+            plan.set_chunks(bad)
+    plan.destroy()
+
+
 def test_slab_rejects_bad_rank_counts(emu):
     import numrs_b200 as nb
     for args in ((8, 8, 8, 3, 0), (8, 8, 8, 16, 0), (8, 8, 8, 2, 2), (8, 6, 8, 2, 0)):
