@@ -169,6 +169,17 @@ int    nrb_plan_describe_launch(nrb_plan_t plan, int isign, int idx, char *name,
 int    nrb_fill_uniform_device(double *d_out, unsigned long long seed, unsigned long long offset,
                                size_t count, void *stream);
 
+/* ---- device-resident buffers: chains such as rlft3 -> pointwise product -> rlft3^-1 stay in HBM.
+ * Buffers come from nrb_device_alloc / nrb_device_free (below); copies are asynchronous on `stream` (NULL = the
+ * default stream) and full speed only from / to pinned host memory (nrb_host_alloc); nrb_stream_synchronize blocks
+ * until everything enqueued on `stream` is done.  nrb_complex_multiply_device: a[i] = a[i] * b[i] * scale, or
+ * a[i] * conj(b[i]) * scale when conj_b != 0, over ncomplex interleaved complex elements (what NR's 3-D convolution
+ * example does between rlft3 and its inverse, applied to `data` and to `speq`). */
+int    nrb_upload(void *d_dst, const void *h_src, size_t bytes, void *stream);
+int    nrb_download(void *h_dst, const void *d_src, size_t bytes, void *stream);
+int    nrb_stream_synchronize(void *stream);
+int    nrb_complex_multiply_device(double *d_a, const double *d_b, size_t ncomplex, int conj_b, double scale, void *stream);
+
 /* ---- slab-decomposed rlft3 across the GPUs of one box (one process per GPU) ----
  * Forward: rank r holds the nn2-slab data[:, r*nn2/G:(r+1)*nn2/G, :] as a contiguous
  * [nn1][nn2/G][nn3] array.  stage 0 = z real transform + x transform on the slab (output

@@ -46,6 +46,7 @@ ABI_SYMBOLS = [
     "nrb_slab_create", "nrb_slab_local_doubles", "nrb_slab_speq_doubles", "nrb_slab_xchg_doubles",
     "nrb_slab_stage", "nrb_slab_destroy", "nrb_slab_set_peers", "nrb_slab_recv_bytes", "nrb_slab_barrier",
     "nrb_slab_set_chunks", "nrb_slab_stage_part", "nrb_slab_barrier_chunk",
+    "nrb_upload", "nrb_download", "nrb_stream_synchronize", "nrb_complex_multiply_device",
     "nrb_device_alloc", "nrb_device_free", "nrb_ipc_export", "nrb_ipc_import", "nrb_ipc_release",
 ]
 
@@ -121,6 +122,10 @@ class Library:
         L.nrb_slab_set_chunks.argtypes = [_vp, ctypes.c_int]
         L.nrb_slab_stage_part.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]
         L.nrb_slab_barrier_chunk.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_ulonglong, _vp]
+        L.nrb_upload.argtypes = [_vp, _vp, _sz, _vp]
+        L.nrb_download.argtypes = [_vp, _vp, _sz, _vp]
+        L.nrb_stream_synchronize.argtypes = [_vp]
+        L.nrb_complex_multiply_device.argtypes = [_vp, _vp, _sz, ctypes.c_int, ctypes.c_double, _vp]
         L.nrb_device_alloc.argtypes = [_sz, ctypes.POINTER(_vp)]
         L.nrb_device_free.argtypes = [_vp]
         L.nrb_ipc_export.argtypes = [_vp, ctypes.c_char_p]
@@ -275,6 +280,20 @@ class Library:
 
     def device_free(self, ptr):
         self.L.nrb_device_free(ptr)
+
+    def upload(self, d_ptr, host, stream=0):
+        host = np.ascontiguousarray(host, dtype=np.float64)
+        self.check(self.L.nrb_upload(d_ptr, host.ctypes.data, host.nbytes, stream or None))
+
+    def download(self, host, d_ptr, stream=0):
+        assert host.dtype == np.float64 and host.flags["C_CONTIGUOUS"]
+        self.check(self.L.nrb_download(host.ctypes.data, d_ptr, host.nbytes, stream or None))
+
+    def stream_synchronize(self, stream=0):
+        self.check(self.L.nrb_stream_synchronize(stream or None))
+
+    def complex_multiply_device(self, d_a, d_b, ncomplex, conj_b=False, scale=1.0, stream=0):
+        self.check(self.L.nrb_complex_multiply_device(d_a, d_b, ncomplex, int(conj_b), float(scale), stream or None))
 
     def ipc_export(self, ptr):
         buf = ctypes.create_string_buffer(64)

@@ -267,6 +267,33 @@ int nrb_fill_uniform_device(double *d_out, unsigned long long seed, unsigned lon
     if (be_device_count() <= 0) return fail(NRB_ERR_CUDA, "no CUDA device available (numrs_b200 has no CPU fallback)");
     return fill_uniform_device(d_out, seed, offset, count, stream);
 }
+int nrb_upload(void *d_dst, const void *h_src, size_t bytes, void *stream)
+{
+    if (be_device_count() <= 0) return fail(NRB_ERR_CUDA, "no CUDA device available (numrs_b200 has no CPU fallback)");
+    if (bytes && (!d_dst || !h_src)) return fail(NRB_ERR_EMPTY_INPUT, "null pointer");
+    if (bytes && be_h2d(d_dst, h_src, bytes, stream) != 0) return copy_fail("host-to-device copy");
+    return NRB_OK;
+}
+int nrb_download(void *h_dst, const void *d_src, size_t bytes, void *stream)
+{
+    if (be_device_count() <= 0) return fail(NRB_ERR_CUDA, "no CUDA device available (numrs_b200 has no CPU fallback)");
+    if (bytes && (!h_dst || !d_src)) return fail(NRB_ERR_EMPTY_INPUT, "null pointer");
+    if (bytes && be_d2h(h_dst, d_src, bytes, stream) != 0) return copy_fail("device-to-host copy");
+    return NRB_OK;
+}
+int nrb_stream_synchronize(void *stream)
+{
+    if (be_device_count() <= 0) return fail(NRB_ERR_CUDA, "no CUDA device available (numrs_b200 has no CPU fallback)");
+    if (be_sync(stream) != 0) return copy_fail("stream synchronisation");
+    return NRB_OK;
+}
+int nrb_complex_multiply_device(double *d_a, const double *d_b, size_t ncomplex, int conj_b, double scale, void *stream)
+{
+    if (be_device_count() <= 0) return fail(NRB_ERR_CUDA, "no CUDA device available (numrs_b200 has no CPU fallback)");
+    if (ncomplex == 0) return NRB_OK;
+    if (!d_a || !d_b) return fail(NRB_ERR_EMPTY_INPUT, "null pointer");
+    return complex_multiply_device(d_a, d_b, ncomplex, conj_b, scale, stream);
+}
 int nrb_plan_destroy(nrb_plan_t plan)
 {
     delete plan;

@@ -489,6 +489,20 @@ NRB_DEV void aux_scan(const AuxParams &A, u64 gtid, u64 gthreads)
     }
 }
 
+// Pointwise product of two device-resident complex arrays (rlft3 -> multiply -> rlft3^-1 chains
+// without PCIe): out[i] = a[i] * b[i] * scale (op 0) or a[i] * conj(b[i]) * scale (op 1).  items: n.
+NRB_DEV void aux_cmul(const AuxParams &A, u64 gtid, u64 gthreads)
+{
+    union { u64 u; double d; } sc;
+    sc.u = A.m;
+    for (u64 i = gtid; i < A.n; i += gthreads) {
+        const double2 a = NRB_LDS(A.a + i), b = NRB_LDS(A.b + i);
+        const double2 p = A.op ? make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y)
+                               : make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+        A.out[i] = make_double2(p.x * sc.d, p.y * sc.d);
+    }
+}
+
 // Cross-GPU barrier of the fused slab exchange, without a collective: after its stage-0 kernels (whose
 // peer stores are complete when the kernel ends) every rank publishes the call's epoch into slot `rank`
 // of each peer's flag array; stage 1 starts after the local array shows the epoch in all slots.
@@ -542,6 +556,7 @@ NRB_DEV void aux_body(const AuxParams &A, u64 gtid, u64 gthreads)
     case AUX_SCALE: aux_scale(A, gtid, gthreads); break;
     case AUX_COSFT: aux_cosft(A, gtid, gthreads); break;
     case AUX_SCAN: aux_scan(A, gtid, gthreads); break;
+    case AUX_CMUL: aux_cmul(A, gtid, gthreads); break;
     default: aux_correl_direct(A, gtid, gthreads); break;
     }
 }

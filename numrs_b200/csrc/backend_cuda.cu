@@ -104,7 +104,7 @@ int be_launch_aux(const AuxParams &a, void *stream)
     case AUX_STATS_FINAL: items = a.count; break;
     case AUX_NORMALIZE: items = a.count * (a.op == 1 ? a.n / 2 : a.n); break;
     case AUX_PACK2: items = a.count * a.n; break;
-    case AUX_POWER: case AUX_SCALE: items = a.n; break;
+    case AUX_POWER: case AUX_SCALE: case AUX_CMUL: items = a.n; break;
     case AUX_TWOFFT_SPLIT: items = a.count * (a.n / 2 + 1); break;
     case AUX_COSFT: items = a.count * a.m; break;
     case AUX_SCAN: items = a.op == 1 ? a.count : a.count * ((a.n / 2 + a.m - 1) / a.m); break;

@@ -952,7 +952,7 @@ int describe_launch(const Plan &pl, int isign, int idx, char *name, size_t cap, 
     } else if (st.is_aux) {
         static const char *names[AUX_KIND_COUNT] = {"untangle", "spectral", "pad_response", "correl_direct", "fill", "spectral_z",
                                                     "signal", "wait", "reduce", "stats_final", "normalize", "power", "pack2",
-                                                    "twofft_split", "scale", "cosft", "scan"};
+                                                    "twofft_split", "scale", "cosft", "scan", "cmul"};
         snprintf(buf, sizeof(buf), "aux_%s", st.ap.kind >= 0 && st.ap.kind < AUX_KIND_COUNT ? names[st.ap.kind] : "unknown");
         switch (st.ap.kind) {
         case AUX_UNTANGLE: b = 2.0 * 16.0 * (double)st.ap.count * (double)st.ap.n; break;
@@ -981,6 +981,19 @@ int describe_launch(const Plan &pl, int isign, int idx, char *name, size_t cap, 
     }
     if (name && cap) { strncpy(name, buf, cap - 1); name[cap - 1] = 0; }
     if (bytes) *bytes = b;
+    return NRB_OK;
+}
+
+int complex_multiply_device(double *d_a, const double *d_b, u64 ncomplex, int conj_b, double scale, void *stream)
+{
+    AuxParams ap;
+    memset(&ap, 0, sizeof(ap));
+    ap.kind = AUX_CMUL;
+    ap.op = conj_b ? 1 : 0;
+    ap.a = (const double2 *)d_a; ap.b = (const double2 *)d_b; ap.out = (double2 *)d_a;
+    ap.n = ncomplex;
+    memcpy(&ap.m, &scale, sizeof(double));
+    if (be_launch_aux(ap, stream) != 0) { set_error(std::string("kernel launch failed: ") + be_last_error()); return NRB_ERR_CUDA; }
     return NRB_OK;
 }
 

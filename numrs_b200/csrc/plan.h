@@ -119,6 +119,7 @@ int profile_plan(Plan &pl, double *d_io, double *d_aux, double *d_out, int isign
 // description of launch i: kernel name and the bytes it must read + write (algorithmic)
 int describe_launch(const Plan &pl, int isign, int idx, char *name, size_t cap, double *bytes);
 int fill_uniform_device(double *d_out, u64 seed, u64 offset, u64 count, void *stream);
+int complex_multiply_device(double *d_a, const double *d_b, u64 ncomplex, int conj_b, double scale, void *stream);
 
 // slab-decomposed rlft3 (one rank's share)
 struct SlabPlan {

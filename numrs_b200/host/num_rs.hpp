@@ -307,4 +307,34 @@ inline std::vector<double> autocorrel_fast(const std::vector<double> &a)
 
 } // namespace Correlation
 
+// ------------------------------------------------------------------ device-resident buffers
+// RAII owner of device memory; upload / download are synchronous here (NULL stream + synchronise).
+class DeviceBuffer {
+  public:
+    explicit DeviceBuffer(std::size_t doubles) : n_(doubles), p_(nullptr) { panic_on(nrb_device_alloc(8 * (doubles ? doubles : 1), &p_)); }
+    explicit DeviceBuffer(const std::vector<double> &host) : DeviceBuffer(host.size()) { upload(host); }
+    ~DeviceBuffer() { if (p_) nrb_device_free(p_); }
+    DeviceBuffer(const DeviceBuffer &) = delete;
+    DeviceBuffer &operator=(const DeviceBuffer &) = delete;
+    void upload(const std::vector<double> &host)
+    {
+        if (host.size() > n_) throw Panic("DeviceBuffer::upload: source larger than the buffer");
+        panic_on(nrb_upload(p_, host.data(), 8 * host.size(), nullptr));
+        panic_on(nrb_stream_synchronize(nullptr));
+    }
+    std::vector<double> download() const
+    {
+        std::vector<double> host(n_);
+        panic_on(nrb_download(host.data(), p_, 8 * n_, nullptr));
+        panic_on(nrb_stream_synchronize(nullptr));
+        return host;
+    }
+    double *data() const { return static_cast<double *>(p_); }
+    std::size_t size() const { return n_; }
+
+  private:
+    std::size_t n_;
+    void *p_;
+};
+
 } // namespace num_rs

@@ -33,6 +33,15 @@ extern "C" {
     pub fn nrb_cosft1(y: *mut c_double, n: usize) -> c_int;
     pub fn nrb_cosft2(y: *mut c_double, n: usize, isign: c_int) -> c_int;
     pub fn nrb_sinft(y: *mut c_double, n: usize) -> c_int;
+    pub fn nrb_device_alloc(bytes: usize, dptr: *mut *mut std::os::raw::c_void) -> c_int;
+    pub fn nrb_device_free(dptr: *mut std::os::raw::c_void) -> c_int;
+    pub fn nrb_upload(d_dst: *mut std::os::raw::c_void, h_src: *const std::os::raw::c_void, bytes: usize,
+                      stream: *mut std::os::raw::c_void) -> c_int;
+    pub fn nrb_download(h_dst: *mut std::os::raw::c_void, d_src: *const std::os::raw::c_void, bytes: usize,
+                        stream: *mut std::os::raw::c_void) -> c_int;
+    pub fn nrb_stream_synchronize(stream: *mut std::os::raw::c_void) -> c_int;
+    pub fn nrb_complex_multiply_device(d_a: *mut c_double, d_b: *const c_double, ncomplex: usize, conj_b: c_int,
+                                       scale: c_double, stream: *mut std::os::raw::c_void) -> c_int;
     pub fn nrb_power_spectrum(c: *const c_double, npoints: usize, take_sqrt: c_int, out: *mut c_double) -> c_int;
 }
 

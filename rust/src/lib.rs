@@ -311,6 +311,35 @@ pub mod Sin_FT {
     }
 }
 
+/// Device-resident buffers (not in the reference: SURVEY.md 8f N1) so chains of transforms stay in HBM.
+pub mod device {
+    use crate::ffi::*;
+    use std::os::raw::c_void;
+    pub struct DeviceBuffer { ptr: *mut c_void, len: usize }
+    impl DeviceBuffer {
+        pub fn new(len: usize) -> Self {
+            let mut ptr: *mut c_void = std::ptr::null_mut();
+            panic_on(unsafe { nrb_device_alloc(8 * len.max(1), &mut ptr) });
+            Self { ptr, len }
+        }
+        pub fn from_slice(host: &[f64]) -> Self { let b = Self::new(host.len()); b.upload(host); b }
+        pub fn upload(&self, host: &[f64]) {
+            assert!(host.len() <= self.len);
+            panic_on(unsafe { nrb_upload(self.ptr, host.as_ptr() as *const c_void, 8 * host.len(), std::ptr::null_mut()) });
+            panic_on(unsafe { nrb_stream_synchronize(std::ptr::null_mut()) });
+        }
+        pub fn download(&self) -> Vec<f64> {
+            let mut host = vec![0.0f64; self.len];
+            panic_on(unsafe { nrb_download(host.as_mut_ptr() as *mut c_void, self.ptr, 8 * self.len, std::ptr::null_mut()) });
+            panic_on(unsafe { nrb_stream_synchronize(std::ptr::null_mut()) });
+            host
+        }
+        pub fn as_mut_ptr(&self) -> *mut f64 { self.ptr as *mut f64 }
+        pub fn len(&self) -> usize { self.len }
+    }
+    impl Drop for DeviceBuffer { fn drop(&mut self) { unsafe { nrb_device_free(self.ptr); } } }
+}
+
 pub mod FFT_2 {
     use crate::ffi::*;
     /// reference: src/FFT_2.rs:3 (asserts :5-7)

@@ -189,3 +189,32 @@ def check_sinft(L, n, seed=1016):
     # the sine transform is its own inverse up to 2/n (y[1] is defined as 0)
     nb.sinft(got, n, L)
     assert rel(got[2:] * (2.0 / n), y[2:]) <= tol(n)
+
+
+def check_device_resident_chain(L, shape=(8, 16, 8), seed=1017):
+    """N1: upload once, rlft3 -> spectrum product -> rlft3^-1 on the device (repeated), download once."""
+    from numrs_b200.device import DeviceArray, Rlft3Convolver
+    n = int(np.prod(shape))
+    x = gen(seed, n).reshape(shape)
+    k = gen(seed + 1, n).reshape(shape) / 8.0
+    conv = Rlft3Convolver(L, k)
+    with DeviceArray.from_host(L, x) as xd:
+        conv.apply(xd)
+        conv.apply(xd)                      # a second pass without leaving the device
+        got = xd.to_host().reshape(shape)
+    conv.close()
+    fk = np.fft.rfftn(k)
+    ref = np.fft.irfftn(np.fft.rfftn(x) * fk * fk, shape, axes=(0, 1, 2))
+    assert rel(got, ref) <= tol(n), rel(got, ref)
+    # against the oracle's rlft3 as well (same chain on the CPU)
+    d, s = x.copy(), np.zeros((shape[0], 2 * shape[1]))
+    kd, ks = k.copy(), np.zeros((shape[0], 2 * shape[1]))
+    O.rlft3(kd, ks, 1)
+    for _ in range(2):
+        O.rlft3(d, s, 1)
+        dz = (d.reshape(-1)[0::2] + 1j * d.reshape(-1)[1::2]) * (kd.reshape(-1)[0::2] + 1j * kd.reshape(-1)[1::2]) * (2.0 / n)
+        sz = (s.reshape(-1)[0::2] + 1j * s.reshape(-1)[1::2]) * (ks.reshape(-1)[0::2] + 1j * ks.reshape(-1)[1::2]) * (2.0 / n)
+        d.reshape(-1)[0::2], d.reshape(-1)[1::2] = dz.real, dz.imag
+        s.reshape(-1)[0::2], s.reshape(-1)[1::2] = sz.real, sz.imag
+        O.rlft3(d, s, -1)
+    assert rel(got, d) <= tol(n), rel(got, d)

@@ -83,6 +83,24 @@ int main(int argc, char **argv)
             Cos_FT::cosft1(c, m);
             CHECK(std::fabs(c[1] - (double)m) < 1e-10 && std::fabs(c[3]) < 1e-10 && std::fabs(c[2]) < 1e-10);
         }
+        // N1: device-resident chain rlft3 -> identity-kernel product -> rlft3^-1 (kernel = unit impulse)
+        {
+            const std::size_t dims[3] = {8, 8, 8};
+            nrb_plan_t plan = nullptr;
+            CHECK(nrb_plan_create(NRB_KIND_RLFT3, dims, 3, 1, &plan) == NRB_OK);
+            std::vector<double> v(512), imp(512, 0.0);
+            for (int i = 0; i < 512; ++i) v[i] = std::cos(0.37 * i);
+            imp[0] = 1.0;
+            DeviceBuffer dv(v), dk(imp), sv(128), sk(128);
+            CHECK(nrb_plan_exec(plan, dk.data(), sk.data(), nullptr, 1, 0, nullptr) == NRB_OK);
+            CHECK(nrb_plan_exec(plan, dv.data(), sv.data(), nullptr, 1, 0, nullptr) == NRB_OK);
+            CHECK(nrb_complex_multiply_device(dv.data(), dk.data(), 256, 0, 2.0 / 512, nullptr) == NRB_OK);
+            CHECK(nrb_complex_multiply_device(sv.data(), sk.data(), 64, 0, 2.0 / 512, nullptr) == NRB_OK);
+            CHECK(nrb_plan_exec(plan, dv.data(), sv.data(), nullptr, -1, 0, nullptr) == NRB_OK);
+            auto back = dv.download();
+            for (int i = 0; i < 512; ++i) CHECK(std::fabs(back[i] - v[i]) < 1e-12);
+            nrb_plan_destroy(plan);
+        }
         // Real_FT3.rs:268-311 with the true factor N/2
         std::vector<double> d(512), s(128, 0.0), o(512);
         for (int i = 0; i < 8; ++i) for (int j = 0; j < 8; ++j) for (int k = 0; k < 8; ++k) o[(i * 8 + j) * 8 + k] = d[(i * 8 + j) * 8 + k] = i + j + k;

@@ -404,3 +404,22 @@ def test_cosft_long_line_path_batch_and_errors(emu):
     plan.destroy()
     for i in range(cnt):
         assert cases.rel(y[i * (n + 1) + 1:(i + 1) * (n + 1)], refs[i][1:]) <= cases.tol(n)
+
+
+def test_device_resident_chain(emu):
+    """SURVEY.md 8f N1 (under emulation 'device' memory is host memory)."""
+    cases.check_device_resident_chain(emu)
+    cases.check_device_resident_chain(emu, (4, 4, 32))
+    a = O.fill_uniform(1, 0, 64)
+    b = O.fill_uniform(2, 0, 64)
+    pa, pb = emu.device_alloc(512), emu.device_alloc(512)
+    emu.upload(pa, a)
+    emu.upload(pb, b)
+    emu.complex_multiply_device(pa, pb, 32, True, 0.5)
+    out = np.empty(64)
+    emu.download(out, pa)
+    emu.stream_synchronize()
+    za, zb = a[0::2] + 1j * a[1::2], b[0::2] + 1j * b[1::2]
+    assert np.allclose(out[0::2] + 1j * out[1::2], za * np.conj(zb) * 0.5, rtol=1e-15, atol=0)
+    emu.device_free(pa)
+    emu.device_free(pb)

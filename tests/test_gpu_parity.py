@@ -179,6 +179,12 @@ def test_cosft_sinft(gpu, n):
     cases.check_sinft(gpu, n)
 
 
+def test_device_resident_chain(gpu):
+    """rlft3 -> spectrum product -> rlft3^-1 without leaving HBM, C ABI only (no torch)."""
+    cases.check_device_resident_chain(gpu)
+    cases.check_device_resident_chain(gpu, (64, 64, 64))
+
+
 def test_golden_fixtures(gpu):
     for nn in (8, 64, 1024):
         for s, t in ((1, "p"), (-1, "m")):
