@@ -486,6 +486,31 @@ NRB_DEV double2 dc_inverse_speq(double2 g0, double2 gn)
     return make_double2(0.5 * ((g0.x - g0.y) + (gn.x - gn.y)), 0.5 * ((g0.x + g0.y) - (gn.x + gn.y)));
 }
 
+// ------------------------------------------------------------------ L2 prefetch of a later tile
+// One prefetch per 128-byte piece of the tile's input footprint (exact addresses of lines that exist).
+template <int LOG2N, int LAYOUT, int VARIANT>
+NRB_DEV void prefetch_tile(const PassParams &P, unsigned tile, int tid)
+{
+    typedef Geo<LOG2N, LAYOUT, VARIANT> G;
+    const u64 q0 = P.q_begin + (u64)tile * G::L;
+    if (LAYOUT == LAYOUT_COL) {
+        constexpr int CPR = (G::L + 7) / 8;                 // 128-byte pieces per row (L lines of 16 bytes)
+        for (int u = tid; u < G::N * CPR; u += G::NT) {
+            const int r = u / CPR, c = u % CPR;
+            const u64 q = q0 + (u64)c * 8;
+            if (q < P.q_end)
+                NRB_PREFETCH_L2(P.in + line_base(q, P.in_s0, P.in_s1, P.in_s2, P.logA, P.logB) + elem_off(r, P.in_es, P.in_eshift, P.in_es_hi));
+        }
+    } else {
+        for (int u = tid; u < G::TILE / 8; u += G::NT) {
+            const int e = u * 8, l = e >> LOG2N, n = e & (G::N - 1);
+            const u64 q = q0 + (u64)l;
+            if (q < P.q_end && G::N >= 8)
+                NRB_PREFETCH_L2(P.in + line_base(q, P.in_s0, P.in_s1, P.in_s2, P.logA, P.logB) + elem_off(n, P.in_es, P.in_eshift, P.in_es_hi));
+        }
+    }
+}
+
 // ------------------------------------------------------------------ the pass body
 template <int LOG2N, int LAYOUT, int DIR, int VARIANT>
 NRB_DEV void fft_pass_body(const PassParams &P, double2 *sm, unsigned tile, int tid)

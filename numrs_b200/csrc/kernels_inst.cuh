@@ -45,6 +45,8 @@ fft_pass_kernel(const __grid_constant__ PassParams P, const unsigned ntiles)
 {
     extern __shared__ double2 nrb_smem[];
     for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (P.prefetch_dist > 0 && tile + (unsigned)P.prefetch_dist < ntiles)
+            prefetch_tile<LOG2N, LAYOUT, VARIANT>(P, tile + (unsigned)P.prefetch_dist, (int)threadIdx.x);
         fft_pass_body<LOG2N, LAYOUT, DIR, VARIANT>(P, nrb_smem, tile, (int)threadIdx.x);
         __syncthreads();   // shared memory is reused by the next tile
     }

@@ -23,6 +23,7 @@ namespace nrb_emu { void barrier(); }
 #define NRB_STS(p, v) (*(p) = (v))
 namespace nrb_emu { double shfl(double v, int src_lane); }
 #define NRB_SHFL(v, lane) nrb_emu::shfl((v), (lane))
+#define NRB_PREFETCH_L2(p) ((void)(p))
 #else
 #include <cuda_runtime.h>
 #define NRB_DEV __device__ __forceinline__
@@ -39,6 +40,7 @@ namespace nrb_emu { double shfl(double v, int src_lane); }
 #define NRB_LDS(p) (*(p))
 #endif
 #define NRB_SHFL(v, lane) __shfl_sync(0xffffffffu, (v), (lane))
+#define NRB_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #ifdef NRB_STREAM_ST
 #define NRB_STS(p, v) __stcg((p), (v))
 #else
@@ -203,6 +205,8 @@ struct PassParams {
     double2 *out_peer[8];
     i64 out_peer_off;
     int out_peer_on;
+    int prefetch_dist;      // > 0: every CTA first asks L2 for the input of tile (own + prefetch_dist), so DRAM keeps
+                            // streaming while the CTAs of an SM are in their shared-memory stages
     int grid_cap;           // > 0: launch at most this many CTAs (they loop over the tiles); used to leave SM slots
                             // to the local pass that runs beside an NVLink-bound exchange pass
     u64 q_begin, q_end;

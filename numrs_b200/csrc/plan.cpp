@@ -49,6 +49,7 @@ static Tunables &tunables_mut()
         x.fuse_zy = env_int("NRB_FUSE_ZY", 0);
         x.fuse_lag = env_int("NRB_FUSE_LAG", 16);
         x.xchg_grid_cap = env_int("NRB_XCHG_GRID_CAP", 0);
+        x.prefetch_dist = env_int("NRB_PREFETCH_DIST", -1);
         return x;
     }();
     if (t.col_max_log2 < 1) t.col_max_log2 = 1;
@@ -73,6 +74,7 @@ int set_tunable(const char *name, long value)
     else if (n == "fuse_zy") t.fuse_zy = (int)value;
     else if (n == "fuse_lag") t.fuse_lag = (int)value;
     else if (n == "xchg_grid_cap") t.xchg_grid_cap = (int)value;
+    else if (n == "prefetch_dist") t.prefetch_dist = (int)value;
     else return -1;
     tunables_mut();   // re-clamp
     return 0;
@@ -901,6 +903,11 @@ static int run_program(Program &prog, double2 *const base[4], int arg, void *str
             PassParams pp = st.pp;
             pp.in = base[st.in.id] + st.in.off;
             pp.out = base[st.out.id] + st.out.off;
+            // L2 prefetch of the tile one wave ahead: pays where an SM holds too few CTAs to overlap its own loads
+            // with another CTA's shared-memory stages (ROW lines >= 4096: +3 ... +7 %) and for COL N = 128 (+3 %);
+            // it costs 3 - 6 % on the other COL kernels (profiles/r01_tuning.md #26).  -1 = this policy.
+            pp.prefetch_dist = tunables().prefetch_dist >= 0 ? tunables().prefetch_dist
+                             : ((st.key.layout == LAYOUT_ROW && st.key.log2n >= 12) || (st.key.layout == LAYOUT_COL && st.key.log2n == 7 && st.key.variant == VAR_PLAIN)) ? 148 : 0;
             pp.speq = st.speq.id == BUF_NONE ? nullptr : base[st.speq.id] + st.speq.off;
             if (px && st.out.id == BUF_OUT) {   // exchange output: write into the peers' receive buffers
                 pp.out_peer_on = 1;
