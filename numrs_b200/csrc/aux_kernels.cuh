@@ -451,40 +451,88 @@ NRB_DEV void scan_term(const AuxParams &A, const double2 *G, u64 pos, int mode, 
     }
 }
 
-// Three-phase running sum, chunks of m positions: op 0 = chunk sums into b[l*nch + c]; op 1 = one thread per
-// line turns them into chunk prefixes (starting value: COS1 the sum of the pre-pass in speq[l].x, SINFT 0,
-// COS2F 0.5 F_{n/2}); op 2 = every chunk walks its positions again and writes the even and odd outputs.
+// Three-phase running sum over chunks of kScanChunk positions.  Phases 0 and 2 are block-cooperative (one CTA of
+// kScanThreads threads per chunk, all global accesses coalesced, aux_scan_cta); phase 1 is one thread per line
+// (aux_scan, op 1).  op 0 = chunk sums into b[l*nch + c]; op 1 = chunk sums -> chunk prefixes (starting value:
+// COS1 the sum of the pre-pass in speq[l].x, SINFT 0, COS2F 0.5 F_{n/2}); op 2 = every chunk turns its terms into
+// running sums and writes the even and odd outputs.
+
 NRB_DEV void aux_scan(const AuxParams &A, u64 gtid, u64 gthreads)
 {
-    const u64 N = A.n / 2, K = A.m, nch = (N + K - 1) / K;
+    const u64 N = A.n / 2, nch = (N + kScanChunk - 1) / kScanChunk;
     const int mode = A.dir;
     double2 *P = const_cast<double2 *>(A.b);
-    if (A.op == 1) {
-        for (u64 l = gtid; l < A.count; l += gthreads) {
-            double run = mode == COS1 ? A.speq[l].x : mode == COS2F ? 0.5 * A.a[(i64)(l * N)].y : 0.0;
-            for (u64 c = 0; c < nch; ++c) { const double s = P[l * nch + c].x; P[l * nch + c].x = run; run += s; }
+    for (u64 l = gtid; l < A.count; l += gthreads) {
+        double run = mode == COS1 ? A.speq[l].x : mode == COS2F ? 0.5 * A.a[(i64)(l * N)].y : 0.0;
+        for (u64 c = 0; c < nch; ++c) { const double s = P[l * nch + c].x; P[l * nch + c].x = run; run += s; }
+    }
+}
+
+// block = l * nch + c; sm holds kScanSmem double2
+NRB_DEV void aux_scan_cta(const AuxParams &A, double2 *sm, unsigned block, int tid)
+{
+    const u64 N = A.n / 2, nch = (N + kScanChunk - 1) / kScanChunk;
+    const int mode = A.dir;
+    const u64 c = block % nch, l = block / nch;
+    const double2 *G = A.a + (i64)(l * N);
+    double2 *P = const_cast<double2 *>(A.b);
+    const u64 p0 = c * kScanChunk;
+    double2 *ts = sm + kScanChunk + kScanChunk / 8;          // per-thread sums
+    // coalesced pass over the chunk: (term, even) of position p0 + i*T + tid
+    double part = 0.0;
+#pragma unroll
+    for (int i = 0; i < kScanPer; ++i) {
+        const int j = i * kScanThreads + tid;
+        const u64 pos = p0 + (u64)j;
+        double term = 0.0, even = 0.0;
+        u64 k = 0;
+        if (pos < N) scan_term(A, G, pos, mode, term, even, k);
+        part += term;
+        if (A.op == 2) sm[j + (j >> 3)] = make_double2(term, even);
+    }
+    if (A.op == 0) {
+        ts[tid] = make_double2(part, 0.0);
+        NRB_SYNC();
+        for (int s = kScanThreads / 2; s > 0; s >>= 1) {
+            if (tid < s) ts[tid].x += ts[tid + s].x;
+            NRB_SYNC();
         }
+        if (tid == 0) P[block] = make_double2(ts[0].x, 0.0);
         return;
     }
-    const u64 items = A.count * nch;
-    for (u64 it = gtid; it < items; it += gthreads) {
-        const u64 c = it % nch, l = it / nch;
-        const double2 *G = A.a + (i64)(l * N);
-        const u64 p0 = c * K, p1 = p0 + K < N ? p0 + K : N;
-        if (A.op == 0) {
-            double s = 0.0;
-            for (u64 pos = p0; pos < p1; ++pos) { double term, even; u64 k; scan_term(A, G, pos, mode, term, even, k); s += term; }
-            P[it] = make_double2(s, 0.0);
-        } else {
-            double *f = reinterpret_cast<double *>(A.out) + (i64)l * A.out_stride + 1;
-            double run = P[it].x;
-            if (mode == COS1 && c == 0) f[A.n] = G[0].y;                  // Cos_FT.rs:61  y[n+1] = y[2]
-            for (u64 pos = p0; pos < p1; ++pos) {
-                double term, even; u64 k;
-                scan_term(A, G, pos, mode, term, even, k);
-                if (mode == COS2F) { f[2 * k] = even; f[2 * k + 1] = run; run += term; }   // exclusive, from the top
-                else { run += term; f[2 * k] = even; f[2 * k + 1] = run; }                 // inclusive
-            }
+    NRB_SYNC();
+    // thread tid owns positions [tid*PER, tid*PER + PER): local sum, block-wide exclusive scan of the sums
+    double loc = 0.0;
+#pragma unroll
+    for (int i = 0; i < kScanPer; ++i) { const int j = tid * kScanPer + i; loc += sm[j + (j >> 3)].x; }
+    ts[tid] = make_double2(loc, 0.0);
+    NRB_SYNC();
+    for (int s = 1; s < kScanThreads; s <<= 1) {             // Hillis-Steele inclusive scan
+        const double add = tid >= s ? ts[tid - s].x : 0.0;
+        NRB_SYNC();
+        ts[tid].x += add;
+        NRB_SYNC();
+    }
+    double run = P[block].x + (ts[tid].x - loc);
+#pragma unroll
+    for (int i = 0; i < kScanPer; ++i) {                    // (term, even) -> (odd output, even output)
+        const int j = tid * kScanPer + i;
+        const double2 te = sm[j + (j >> 3)];
+        if (mode == COS2F) { sm[j + (j >> 3)] = make_double2(run, te.y); run += te.x; }   // exclusive, from the top
+        else { run += te.x; sm[j + (j >> 3)] = make_double2(run, te.y); }                 // inclusive
+    }
+    NRB_SYNC();
+    double *f = reinterpret_cast<double *>(A.out) + (i64)l * A.out_stride + 1;
+    if (mode == COS1 && c == 0 && tid == 0) f[A.n] = G[0].y;                              // Cos_FT.rs:61  y[n+1] = y[2]
+#pragma unroll
+    for (int i = 0; i < kScanPer; ++i) {
+        const int j = i * kScanThreads + tid;
+        const u64 pos = p0 + (u64)j;
+        if (pos < N) {
+            const u64 k = mode == COS2F ? N - 1 - pos : pos;
+            const double2 oe = sm[j + (j >> 3)];
+            f[2 * k] = oe.y;
+            f[2 * k + 1] = oe.x;
         }
     }
 }

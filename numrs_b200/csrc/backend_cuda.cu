@@ -90,8 +90,22 @@ __global__ void __launch_bounds__(256) aux_kernel(const __grid_constant__ AuxPar
     aux_body(A, (u64)blockIdx.x * blockDim.x + threadIdx.x, (u64)gridDim.x * blockDim.x);
 }
 
+__global__ void __launch_bounds__(kScanThreads) aux_scan_kernel(const __grid_constant__ AuxParams A)
+{
+    __shared__ double2 sm[kScanSmem];
+    aux_scan_cta(A, sm, blockIdx.x, (int)threadIdx.x);
+}
+
 int be_launch_aux(const AuxParams &a, void *stream)
 {
+    if (a.kind == AUX_SCAN && a.op != 1) {      // block-cooperative phases of the running sum
+        const u64 blocks = a.count * ((a.n / 2 + kScanChunk - 1) / kScanChunk);
+        if (blocks == 0) return 0;
+        if (blocks > 0x7fffffffull) { g_be_err = "grid too large"; return -1; }
+        aux_scan_kernel<<<(unsigned)blocks, kScanThreads, 0, (cudaStream_t)stream>>>(a);
+        cudaError_t e = cudaGetLastError();
+        return e == cudaSuccess ? 0 : fail(e);
+    }
     u64 items = 0;
     switch (a.kind) {
     case AUX_UNTANGLE: items = a.count * (a.n >= 2 ? a.n / 2 : 1); break;
@@ -107,7 +121,7 @@ int be_launch_aux(const AuxParams &a, void *stream)
     case AUX_POWER: case AUX_SCALE: case AUX_CMUL: items = a.n; break;
     case AUX_TWOFFT_SPLIT: items = a.count * (a.n / 2 + 1); break;
     case AUX_COSFT: items = a.count * a.m; break;
-    case AUX_SCAN: items = a.op == 1 ? a.count : a.count * ((a.n / 2 + a.m - 1) / a.m); break;
+    case AUX_SCAN: items = a.count; break;
     default: items = a.count * a.n; break;
     }
     if (items == 0) return 0;

@@ -63,6 +63,11 @@ enum Variant { VAR_PLAIN = 0, VAR_REAL = 1, VAR_XPOSE = 2 };
 
 enum RealMode { REAL_NONE = 0, REAL_PACKED = 1, REAL_SPEQ = 2 };
 
+// geometry of the block-cooperative running sum (aux_scan_cta)
+constexpr int kScanThreads = 256;
+constexpr int kScanPer = 8;                                  // consecutive positions per thread in phase 2
+constexpr int kScanChunk = kScanThreads * kScanPer;          // positions per CTA
+constexpr int kScanSmem = kScanChunk + kScanChunk / 8 + kScanThreads;   // double2 elements (padded tile + thread sums)
 constexpr int kSlabMaxChunks = 16;  // z-chunks of the pipelined slab exchange (flag slots per receive buffer)
 constexpr int kMaxLog2N = 13;       // longest line one CTA transforms in shared memory
 // points each thread owns per stage (compile-time): 16 -> TILE/16 threads and two radix-8 butterflies

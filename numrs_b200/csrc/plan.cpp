@@ -728,7 +728,7 @@ int build_cosft(Plan &pl, Builder &B, int kind, int dir)
     const bool inverse = kind == NRB_KIND_COSFT2 && dir < 0;
     const u64 C = N + 1 < 16384 ? N + 1 : 16384;        // pre-pass accumulators per line
     const u64 C1 = C > 256 ? 128 : 0;
-    const u64 K = 128, nch = (N + K - 1) / K;           // running sum: positions per chunk
+    const u64 K = (u64)kScanChunk, nch = (N + K - 1) / K;   // running sum: positions per chunk (one CTA each)
     i64 off = 0;
     const BufRef IO(BUF_IO, 0), G(BUF_WS, off); off += (i64)(L * N);
     const BufRef T(BUF_WS, off); off += real_needs_separate_untangle(p) ? (i64)(L * N) : 0;
@@ -974,7 +974,7 @@ int describe_launch(const Plan &pl, int isign, int idx, char *name, size_t cap, 
         case AUX_TWOFFT_SPLIT: b = 48.0 * (double)st.ap.count * (double)st.ap.n; break;
         case AUX_SCALE: b = 16.0 * (double)st.ap.n; break;
         case AUX_COSFT: b = 16.0 * (double)st.ap.count * (double)st.ap.n; break;
-        case AUX_SCAN: b = st.ap.op == 1 ? 32.0 * (double)st.ap.count * (double)((st.ap.n / 2 + st.ap.m - 1) / st.ap.m)
+        case AUX_SCAN: b = st.ap.op == 1 ? 32.0 * (double)st.ap.count * (double)((st.ap.n / 2 + kScanChunk - 1) / kScanChunk)
                                          : (st.ap.op == 0 ? 8.0 : 16.0) * (double)st.ap.count * (double)st.ap.n; break;
         default: b = 3.0 * 8.0 * (double)st.ap.count * (double)st.ap.n; break;
         }

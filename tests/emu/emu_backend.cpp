@@ -183,9 +183,29 @@ int be_launch_fused(const KernelKey &ka, const PassParams &pa, const KernelKey &
     return rc;
 }
 
+static void scan_cta_body(const void *p, double2 *sm, unsigned block, int tid)
+{
+    aux_scan_cta(*(const AuxParams *)p, sm, block, tid);
+}
+
 int be_launch_aux(const AuxParams &a, void *)
 {
     ++g_aux_launches;
+    if (a.kind == AUX_SCAN && a.op != 1) {      // block-cooperative kernel: one emulated CTA per chunk
+        const u64 blocks = a.count * ((a.n / 2 + kScanChunk - 1) / kScanChunk);
+        nrb_emu::Cta c;
+        c.fibers.resize(kScanThreads);
+        c.stacks.resize((size_t)kScanThreads * nrb_emu::kStack);
+        c.done.resize(kScanThreads);
+        c.body = scan_cta_body;
+        c.params = &a;
+        for (u64 b = 0; b < blocks; ++b) {
+            c.tile = (unsigned)b;
+            c.smem.assign(kScanSmem, make_double2(__builtin_nan(""), __builtin_nan("")));
+            nrb_emu::run_cta(c, kScanThreads);
+        }
+        return 0;
+    }
     const u64 nthreads = 977;   // deliberately odd: exercises the grid-stride loops
     for (u64 t = 0; t < nthreads; ++t) aux_body(a, t, nthreads);
     return 0;

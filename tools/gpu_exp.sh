@@ -1,7 +1,6 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-W="rlft3_512 four1_12_4096 four1_20_64 fourn2d_8192"
-for d in 0 148 296 592 1184; do
-echo "##### prefetch_dist $d"; NRB_PREFETCH_DIST=$d timeout 300 python tools/kernel_table.py $W 2>&1 | grep -E "^==|_L131072|_L262144|L4096|L65536|L8192|L524288|L1048576"
-done
+timeout 120 ./tools/cluster_exchange_bench 2>&1 | tee gpurun_out/cluster_exchange_bench.log
+timeout 600 python -m pytest tests -m gpu -x -q -k "cosft or correl_normalized or device_resident or host_mirror" 2>&1 | tail -3
+timeout 300 python tools/kernel_table.py cosft1_22_16 cosft1_12_4096 cosft2_22_16 cosft2_12_4096 sinft_12_4096 correlnorm_22_16 correlnormfast_22_16 fourn2d_8192 2>&1 | tee gpurun_out/r01_kernel_table_next2.txt
