@@ -19,6 +19,13 @@
  *   realft, fourn, rlft3, large-n convlv/correl: "parity unpinned" by the reference's own tests
  *                         (none of them can run); pinned here against numpy (pocketfft) and an
  *                         mpmath 50-digit DFT in tests/test_oracle.py.
+ *   next rows, at the end of this file, ledger D9..D11:
+ *     correl_normalized_fast, autocorrel (small n), power/magnitude spectrum: pinned by Correlation.rs:505-512,
+ *                         :481-491 (lag 0) and FFT_1.rs:305-321
+ *     twofft, correl_normalized, autocorrel_fast (n > 32), cosft1, cosft2, sinft: "parity unpinned" by the
+ *                         reference (twofft's mirror is off by one, FFT_2.rs:74; the cosine transforms stop at
+ *                         `unimplemented!()`, Cos_FT.rs:70-74; sinft has no source); pinned here against numpy
+ *                         and scipy.fft dct / dst in tests/test_oracle.py.
  *
  * All file:line citations are relative to /root/reference/src.
  */
