@@ -64,6 +64,8 @@ int  nrb_shutdown(void);               /* frees cached plans / scratch of all th
  *   "fuse_zy"           rlft3: run the z and y passes of every x-plane in one persistent launch so the
  *                       y pass reads the z pass's output from L2 (default 0: measured 3-6 % slower on B200); "fuse_lag" = planes the y
  *                       tiles trail behind the z tiles (default 16)
+ *   "conv_transposed"   convlv/correl with lines longer than a tile: two passes per transform, spectrum kept in transposed
+ *                       order (default 1); 0 = three natural-order passes per transform
  *   "prefetch_dist"     tiles ahead whose input every CTA prefetches into L2 (-1 = per-kernel policy, 0 = off)
  *   "xchg_grid_cap"     pipelined slab exchange: CTAs of a peer-store pass (0 = one per tile); fewer CTAs leave SM
  *                       slots to the local pass running beside it on the second stream

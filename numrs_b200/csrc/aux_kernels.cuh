@@ -153,6 +153,67 @@ NRB_DEV void aux_spectral_z(const AuxParams &A, u64 gtid, u64 gthreads)
     }
 }
 
+// The same fused step for spectra left in the TRANSPOSED order of a two-pass transform without transposition:
+// N = F * REST complex points (F = 2^m), bin k = kf + F*kr sits at position kf*REST + kr (what "strided F-point
+// pass + twiddle, then contiguous REST-point pass" produces from natural-order input, and what the mirrored
+// inverse consumes).  A spectrum that is only an intermediate -- convlv / correl -- never needs natural order,
+// which saves one HBM pass per transform over the three-factor natural-order plan.
+// Partner of (kf, kr): (F - kf, REST - 1 - kr) for kf != 0, (0, (REST - kr) mod REST) for kf = 0; an item owns one
+// pair.  Items are enumerated row by row, (kf in [0, F/2], kr in [0, REST)), so that a warp reads row kf forwards
+// and row F - kf backwards: count * (F/2 + 1) * REST items, the surplus ones of rows 0 and F/2 are skipped.
+// b: the raw transposed c2c output of the second operand -- per signal (b_stride != 0, correl) or one shared by all
+// signals (b_stride == 0 and dir == 1: the response of convlv, kept raw so that its reads are coalesced like a's);
+// b_stride == 0 and dir == 0: a packed, untangled spectrum in NATURAL order; SPEC_AUTOCORREL: the first operand.
+NRB_DEV void aux_spectral_zt(const AuxParams &A, u64 gtid, u64 gthreads)
+{
+    const u64 N = A.n / 2;
+    const int f = (int)A.m;
+    const u64 F = 1ull << f, REST = N >> f;
+    const u64 rows = F / 2 + 1, per = rows * REST, items = A.count * per;
+    const double inv = 1.0 / (double)N;
+    const bool self = A.op == SPEC_AUTOCORREL;
+    const bool b_raw = (A.b_stride != 0 || A.dir == 1) && !self;
+    const int op = self ? SPEC_CORREL : A.op;
+    for (u64 it = gtid; it < items; it += gthreads) {
+        const u64 sig = it / per, w = it % per, kf = w / REST, kr = w % REST;
+        const double2 *za = A.a + (i64)sig * A.a_stride;
+        const double2 *zb = self ? za : A.b + (i64)sig * A.b_stride;
+        double2 *out = A.out + (i64)sig * A.out_stride;
+        if (kf == 0 && kr == 0) {                           // k = 0: DC and Nyquist share the element
+            const double2 a0 = NRB_LDS(za);
+            double2 r0 = self ? a0 : (b_raw ? NRB_LDS(zb) : NRB_LDG(zb));
+            if (b_raw || self) r0 = make_double2(r0.x + r0.y, r0.x - r0.y);
+            const double g0 = spectral_op_real(op, a0.x + a0.y, r0.x, inv);
+            const double gn = spectral_op_real(op, a0.x - a0.y, r0.y, inv);
+            out[0] = make_double2(0.5 * (g0 + gn), 0.5 * (g0 - gn));
+            continue;
+        }
+        if (kf == 0 && kr == REST / 2) {                    // k = N/2: untangling is the identity
+            const double2 am = NRB_LDS(za + kr);
+            const double2 rm = self ? am : (b_raw ? NRB_LDS(zb + kr) : NRB_LDG(zb + N / 2));
+            out[kr] = spectral_op(op, am, rm, inv);
+            continue;
+        }
+        u64 pkf, pkr;                                       // partner
+        if (kf == 0) { if (kr > REST / 2) continue; pkf = 0; pkr = REST - kr; }
+        else if (2 * kf == F) { if (kr >= REST / 2) continue; pkf = kf; pkr = REST - 1 - kr; }
+        else { pkf = F - kf; pkr = REST - 1 - kr; }
+        const u64 k = kf + F * kr;                          // any 1 <= k <= N-1 works in the pair formula
+        const u64 pa = kf * REST + kr, pm = pkf * REST + pkr;
+        const double2 t = two_level_tw(A.rtw_lo, A.rtw_hi, A.rtw_h, k);
+        double2 fa, fm, ra, rm;
+        untangle_pair<1>(NRB_LDS(za + pa), NRB_LDS(za + pm), t, fa, fm);
+        if (self) { ra = fa; rm = fm; }
+        else if (b_raw) untangle_pair<1>(NRB_LDS(zb + pa), NRB_LDS(zb + pm), t, ra, rm);
+        else { ra = NRB_LDG(zb + k); rm = NRB_LDG(zb + (N - k)); }
+        const double2 ga = spectral_op(op, fa, ra, inv), gm = spectral_op(op, fm, rm, inv);
+        double2 oa, ob;
+        untangle_pair<-1>(ga, gm, t, oa, ob);
+        out[pa] = oa;
+        out[pm] = ob;
+    }
+}
+
 // a = response taps (m doubles), out = padded response (n doubles).  items: n.
 NRB_DEV void aux_pad_response(const AuxParams &A, u64 gtid, u64 gthreads)
 {
@@ -605,6 +666,7 @@ NRB_DEV void aux_body(const AuxParams &A, u64 gtid, u64 gthreads)
     case AUX_COSFT: aux_cosft(A, gtid, gthreads); break;
     case AUX_SCAN: aux_scan(A, gtid, gthreads); break;
     case AUX_CMUL: aux_cmul(A, gtid, gthreads); break;
+    case AUX_SPECTRAL_ZT: aux_spectral_zt(A, gtid, gthreads); break;
     default: aux_correl_direct(A, gtid, gthreads); break;
     }
 }

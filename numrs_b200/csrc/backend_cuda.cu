@@ -113,6 +113,7 @@ int be_launch_aux(const AuxParams &a, void *stream)
     case AUX_PAD_RESPONSE: items = a.n; break;
     case AUX_FILL: items = a.n; break;
     case AUX_SPECTRAL_Z: items = a.count * (a.n >= 8 ? a.n / 4 : 1); break;
+    case AUX_SPECTRAL_ZT: items = a.count * (((1ull << a.m) / 2 + 1) * ((a.n / 2) >> a.m)); break;
     case AUX_SIGNAL: case AUX_WAIT: items = a.count; break;
     case AUX_REDUCE: items = a.count * a.m; break;
     case AUX_STATS_FINAL: items = a.count; break;

@@ -255,7 +255,8 @@ enum AuxKind {
     AUX_COSFT = 15,       // cosft1 / cosft2 / sinft pre- and post-processing around realft (Cos_FT.rs, Cos_FT2.rs)
     AUX_SCAN = 16,        // running sums of the odd (cosft1) / even-from-the-top (cosft2) outputs, three-phase
     AUX_CMUL = 17,        // a[i] = a[i] * b[i] (op 0) or a[i] * conj(b[i]) (op 1), times a real scale (bits in m)
-    AUX_KIND_COUNT = 18
+    AUX_SPECTRAL_ZT = 18, // AUX_SPECTRAL_Z on spectra kept in the transposed order of a two-pass transform (see aux_spectral_zt)
+    AUX_KIND_COUNT = 19
 };
 enum SpectralOp { SPEC_CONV_MUL = 0, SPEC_CONV_DIV = 1, SPEC_CORREL = 2, SPEC_AUTOCORREL = 3 };
 enum ReduceMode { RED_SUM_SQ = 0, RED_CENTERED_SQ = 1, RED_PARTIALS = 2 };

@@ -50,6 +50,7 @@ static Tunables &tunables_mut()
         x.fuse_lag = env_int("NRB_FUSE_LAG", 16);
         x.xchg_grid_cap = env_int("NRB_XCHG_GRID_CAP", 0);
         x.prefetch_dist = env_int("NRB_PREFETCH_DIST", -1);
+        x.conv_transposed = env_int("NRB_CONV_TRANSPOSED", 1);
         return x;
     }();
     if (t.col_max_log2 < 1) t.col_max_log2 = 1;
@@ -75,6 +76,7 @@ int set_tunable(const char *name, long value)
     else if (n == "fuse_lag") t.fuse_lag = (int)value;
     else if (n == "xchg_grid_cap") t.xchg_grid_cap = (int)value;
     else if (n == "prefetch_dist") t.prefetch_dist = (int)value;
+    else if (n == "conv_transposed") t.conv_transposed = (int)value;
     else return -1;
     tunables_mut();   // re-clamp
     return 0;
@@ -398,6 +400,76 @@ Step make_spectral_z(int op, BufRef a, BufRef b, BufRef out, u64 n, u64 count, i
     return st;
 }
 
+// ---- two-pass transforms with the spectrum left in transposed order (convlv / correl intermediates) ----
+// N = 2^p = F * REST, F = 2^f.  Forward: strided F-point pass over n = j*REST + r for every r (COL, lines adjacent),
+// output kf multiplied by exp(-+2 pi i r kf / N), stored in place; then contiguous REST-point pass per kf (ROW).
+// Bin kf + F*kr ends at position kf*REST + kr.  Inverse: ROW pass per kf with the twiddle on its output, then the
+// COL pass; the result is in natural order again.  No scratch, no transposing stores.
+int conv_split(int p)
+{
+    const Tunables &T = tunables();
+    if (!T.conv_transposed || p < 2) return -1;
+    int rest = p - 1 < 12 ? p - 1 : 12;                 // contiguous pass: 4096 points at most (the fast ROW kernels)
+    if (rest > T.row_max_log2) rest = T.row_max_log2;
+    int f = p - rest;
+    if (f > T.col_max_log2) { f = T.col_max_log2; rest = p - f; }
+    if (f < 1 || rest < 1 || rest > T.row_max_log2) return -1;
+    return f;
+}
+
+void emit_conv_forward(Builder &B, BufRef src, BufRef dst, u64 cnt, int p, int f)
+{
+    const u64 N = 1ull << p, F = 1ull << f, REST = N >> f;
+    {
+        Step st;
+        init_pass(st.pp);
+        PassParams &pp = st.pp;
+        st.key = KernelKey{f, LAYOUT_COL, +1, VAR_PLAIN};
+        pp.logB = 0; pp.logA = p - f;                   // line q = b*REST + r: q1 = r, q0 = b
+        pp.q_begin = 0; pp.q_end = cnt * REST;
+        pp.in_s0 = (i64)N; pp.in_s1 = 1; pp.in_s2 = 0; pp.in_es = (i64)REST;
+        pp.out_s0 = (i64)N; pp.out_s1 = 1; pp.out_s2 = 0; pp.out_es = (i64)REST;
+        const FourStepTable fs = fourstep_table(p);
+        pp.tw_on = 1; pp.tw_lo = fs.lo; pp.tw_hi = fs.hi; pp.tw_h = fs.h;
+        pp.tw = stage_twiddles(f);
+        st.in = src; st.out = dst;
+        st.ntiles = tiles_for(f, LAYOUT_COL, pp.q_end);
+        B.prog->steps.push_back(st);
+    }
+    emit_axis(B, dst, dst, BufRef(), cnt * F, 0, cnt * F, p - f, 1, +1);
+}
+
+void emit_conv_inverse(Builder &B, BufRef buf, u64 cnt, int p, int f)
+{
+    const u64 N = 1ull << p, F = 1ull << f, REST = N >> f;
+    {
+        Step st;
+        init_pass(st.pp);
+        PassParams &pp = st.pp;
+        st.key = KernelKey{p - f, LAYOUT_ROW, -1, VAR_PLAIN};
+        pp.logB = 0; pp.logA = f;                       // line q = b*F + kf: q1 = kf, q0 = b
+        pp.q_begin = 0; pp.q_end = cnt * F;
+        pp.in_s0 = (i64)N; pp.in_s1 = (i64)REST; pp.in_s2 = 0; pp.in_es = 1;
+        pp.out_s0 = (i64)N; pp.out_s1 = (i64)REST; pp.out_s2 = 0; pp.out_es = 1;
+        const FourStepTable fs = fourstep_table(p);
+        pp.tw_on = 1; pp.tw_lo = fs.lo; pp.tw_hi = fs.hi; pp.tw_h = fs.h;
+        pp.tw = stage_twiddles(p - f);
+        st.in = buf; st.out = buf;
+        st.ntiles = tiles_for(p - f, LAYOUT_ROW, pp.q_end);
+        B.prog->steps.push_back(st);
+    }
+    // COL pass over kf for every r: view [cnt][F][REST]
+    emit_axis(B, buf, buf, BufRef(), cnt, 0, cnt, f, REST, -1);
+}
+
+Step make_spectral_zt(int op, BufRef a, BufRef b, BufRef out, u64 n, int f, u64 count, i64 a_stride, i64 b_stride, i64 out_stride)
+{
+    Step st = make_spectral_z(op, a, b, out, n, count, a_stride, b_stride, out_stride);
+    st.ap.kind = AUX_SPECTRAL_ZT;
+    st.ap.m = (u64)f;
+    return st;
+}
+
 Step make_spectral(int op, BufRef a, BufRef b, BufRef out, u64 n, u64 count, i64 a_stride, i64 b_stride,
                    i64 out_stride)
 {
@@ -539,7 +611,10 @@ int build_convlv(Plan &pl, Builder &B, int dir)
         st.patch_pad_mode = true;
         B.prog->steps.push_back(st);
     }
-    emit_real(B, R, R, T, 0, 1, p, +1, REAL_PACKED, BufRef());
+    const int fsplit = real_needs_separate_untangle(p) ? conv_split(p) : -1;
+    // (two-pass plan: the response spectrum stays raw and transposed like the signals', untangled on the fly)
+    if (fsplit > 0) emit_conv_forward(B, R, R, 1, p, fsplit);
+    else emit_real(B, R, R, T, 0, 1, p, +1, REAL_PACKED, BufRef());
     // signals in L2-sized groups: forward, spectral op, inverse
     u64 gs = tunables().batch_group_bytes / (n * 8);
     if (gs < 1) gs = 1;
@@ -547,7 +622,14 @@ int build_convlv(Plan &pl, Builder &B, int dir)
     for (u64 b0 = 0; b0 < pl.batch; b0 += gs) {
         const u64 b1 = (b0 + gs < pl.batch) ? b0 + gs : pl.batch;
         const BufRef in(BUF_IO, (i64)(b0 * N)), out(BUF_OUT, (i64)(b0 * N));
-        if (real_needs_separate_untangle(p)) {
+        if (fsplit > 0) {
+            // two passes, spectrum in transposed order, [untangle + multiply + inverse untangle], two passes back
+            emit_conv_forward(B, in, out, b1 - b0, p, fsplit);
+            Step sp = make_spectral_zt(dir > 0 ? SPEC_CONV_MUL : SPEC_CONV_DIV, out, R, out, n, fsplit, b1 - b0, (i64)N, 0, (i64)N);
+            sp.ap.dir = 1;      // b = raw transposed response
+            B.prog->steps.push_back(sp);
+            emit_conv_inverse(B, out, b1 - b0, p, fsplit);
+        } else if (real_needs_separate_untangle(p)) {
             // c2c -> [untangle + multiply + inverse untangle in one pass] -> inverse c2c
             emit_axis(B, in, out, T, b1 - b0, 0, b1 - b0, p, 1, +1);
             B.prog->steps.push_back(make_spectral_z(dir > 0 ? SPEC_CONV_MUL : SPEC_CONV_DIV, out, R, out, n, b1 - b0,
@@ -589,7 +671,13 @@ void emit_correl_group(Builder &B, BufRef a, BufRef b, BufRef out, BufRef F2, Bu
     const u64 N = n / 2;
     const int p = ilog2((size_t)N);
     const bool two = op != SPEC_AUTOCORREL;
-    if (real_needs_separate_untangle(p)) {
+    const int fsplit = real_needs_separate_untangle(p) ? conv_split(p) : -1;
+    if (fsplit > 0) {
+        emit_conv_forward(B, a, out, cnt, p, fsplit);
+        if (two) emit_conv_forward(B, b, F2, cnt, p, fsplit);
+        B.prog->steps.push_back(make_spectral_zt(op, out, two ? F2 : out, out, n, fsplit, cnt, (i64)N, (i64)N, (i64)N));
+        emit_conv_inverse(B, out, cnt, p, fsplit);
+    } else if (real_needs_separate_untangle(p)) {
         emit_axis(B, a, out, T, cnt, 0, cnt, p, 1, +1);
         if (two) emit_axis(B, b, F2, T, cnt, 0, cnt, p, 1, +1);
         B.prog->steps.push_back(make_spectral_z(op, out, two ? F2 : out, out, n, cnt, (i64)N, (i64)N, (i64)N));
@@ -959,12 +1047,13 @@ int describe_launch(const Plan &pl, int isign, int idx, char *name, size_t cap, 
     } else if (st.is_aux) {
         static const char *names[AUX_KIND_COUNT] = {"untangle", "spectral", "pad_response", "correl_direct", "fill", "spectral_z",
                                                     "signal", "wait", "reduce", "stats_final", "normalize", "power", "pack2",
-                                                    "twofft_split", "scale", "cosft", "scan", "cmul"};
+                                                    "twofft_split", "scale", "cosft", "scan", "cmul", "spectral_zt"};
         snprintf(buf, sizeof(buf), "aux_%s", st.ap.kind >= 0 && st.ap.kind < AUX_KIND_COUNT ? names[st.ap.kind] : "unknown");
         switch (st.ap.kind) {
         case AUX_UNTANGLE: b = 2.0 * 16.0 * (double)st.ap.count * (double)st.ap.n; break;
         case AUX_SPECTRAL: b = (double)st.ap.count * (double)st.ap.n * 8.0 * (st.ap.b_stride ? 3.0 : 2.0) + (st.ap.b_stride ? 0.0 : 8.0 * (double)st.ap.n); break;
         case AUX_PAD_RESPONSE: b = 8.0 * ((double)st.ap.n + (double)st.ap.m); break;
+        case AUX_SPECTRAL_ZT:
         case AUX_SPECTRAL_Z: b = (double)st.ap.count * (double)st.ap.n * 8.0 * (st.ap.b_stride ? 3.0 : 2.0) + (st.ap.b_stride ? 0.0 : 8.0 * (double)st.ap.n); break;
         case AUX_REDUCE: b = (double)st.ap.count * ((st.ap.op == RED_PARTIALS ? 16.0 : 8.0) * (double)st.ap.n + 16.0 * (double)st.ap.m); break;
         case AUX_STATS_FINAL: b = (double)st.ap.count * 16.0 * ((double)st.ap.m + 1.0); break;

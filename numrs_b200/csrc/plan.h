@@ -92,6 +92,8 @@ struct Tunables {
     int fuse_zy;           // rlft3: fuse the z and y passes of each x-plane through L2 (NRB_FUSE_ZY, default 0: measured slower)
     int fuse_lag;          // planes pass B runs behind pass A (NRB_FUSE_LAG, default 16)
     u64 batch_group_bytes; // convlv/correl: bytes of signals handled per launch group (NRB_BATCH_GROUP_MB, default 512)
+    int conv_transposed;   // convlv/correl with lines longer than a tile: two passes per transform and the spectrum in
+                           // transposed order instead of three natural-order passes (NRB_CONV_TRANSPOSED, default 1)
     int prefetch_dist;     // tiles ahead whose input every CTA prefetches into L2 (NRB_PREFETCH_DIST; 0 = off, -1 = per-kernel policy, default)
     int xchg_grid_cap;     // pipelined slab exchange: CTAs of an exchange (peer-store) pass, 0 = one per tile (NRB_XCHG_GRID_CAP)
 };

@@ -45,4 +45,5 @@ def _reset_options(request):
             L.set_option("fuse_zy", 0)
             L.set_option("fuse_lag", 16)
             L.set_option("prefetch_dist", -1)
+            L.set_option("conv_transposed", 1)
             L.set_option("xchg_grid_cap", 0)

@@ -423,3 +423,33 @@ def test_device_resident_chain(emu):
     assert np.allclose(out[0::2] + 1j * out[1::2], za * np.conj(zb) * 0.5, rtol=1e-15, atol=0)
     emu.device_free(pa)
     emu.device_free(pb)
+
+
+@pytest.mark.parametrize("n", [128, 256, 512, 1024])
+def test_convlv_correl_transposed_spectrum_path(emu, n):
+    """Lines longer than a tile: two passes per transform with the spectrum left in transposed order
+    (AUX_SPECTRAL_ZT), against the oracle, and the same answers as the three-factor natural-order plan."""
+    emu.set_option("row_max_log2", 5)
+    emu.set_option("col_max_log2", 4)
+    for flag in (1, 0):
+        emu.set_option("conv_transposed", flag)
+        cases.check_convlv(emu, n, 9)
+        cases.check_correl(emu, n)
+        cases.check_autocorrel_fast(emu, n)
+        cases.check_correl_normalized(emu, n)
+    emu.set_option("conv_transposed", 1)
+    plan = emu.plan_create(nb.KIND_CONVLV, [n, 9], batch=3)
+    sig, taps, ans = O.fill_uniform(1, 0, 3 * n), np.ones(9), np.zeros(3 * n)
+    names = [nm for nm, _, _ in plan.profile(sig.ctypes.data, taps.ctypes.data, ans.ctypes.data)]
+    plan.destroy()
+    assert sum(nm.startswith("fft_") for nm in names[-5:]) == 4 and "aux_spectral_zt" in names, names
+
+
+def test_convlv_default_plan_uses_two_passes_per_transform(emu):
+    plan = emu.plan_create(nb.KIND_CORREL, [1 << 15], batch=1)
+    assert plan.num_launches(1) == 7          # 2 + 2 forward, spectral, 2 inverse
+    plan.destroy()
+    emu.set_option("conv_transposed", 0)
+    plan = emu.plan_create(nb.KIND_CORREL, [1 << 15], batch=1)
+    assert plan.num_launches(1) == 7          # 2^14 complex = 2 natural-order passes as well
+    plan.destroy()
