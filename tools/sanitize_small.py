@@ -36,4 +36,27 @@ for n, m in ((4, 2), (64, 5), (1024, 33)):
     cases.check_convlv(L, n, m)
 for n in (3, 32, 64, 1024):
     cases.check_correl(L, n)
+# next rows and the transposed-spectrum convolution path
+for n in (1, 16, 4096, 1 << 14):
+    cases.check_twofft(L, n)
+for n in (5, 32, 64, 4096):
+    cases.check_correl_normalized(L, n)
+    cases.check_correl_normalized(L, n, fast=True)
+    cases.check_autocorrel_fast(L, n)
+for n in (2, 8, 256, 4096, 1 << 15):
+    cases.check_cosft1(L, n)
+    cases.check_cosft2(L, n)
+    cases.check_sinft(L, n)
+cases.check_spectrum(L, 5000)
+cases.check_device_resident_chain(L)
+for flag in (1, 0):
+    L.set_option("conv_transposed", flag)
+    cases.check_convlv(L, 1 << 15, 100)
+    cases.check_correl(L, 1 << 15)
+    cases.check_autocorrel_fast(L, 1 << 15)
+L.set_option("conv_transposed", 1)
+L.set_option("prefetch_dist", 3)
+cases.check_rlft3(L, (16, 8, 32))
+cases.check_four1(L, 4096)
+L.set_option("prefetch_dist", -1)
 print("sanitize_small: all parity checks passed")
