@@ -374,8 +374,10 @@ def run_ours(args, rank, world, local_rank):
                 lib.fill_uniform_device(b.data_ptr(), 1006, rank * ld, ld, st())
             launches_step = 0
             extra["a2a_bytes_per_gpu_per_direction"] = slab.a2a_bytes_per_gpu()
-            extra["exchange"] = ("fused: stage-0 kernels store into peer receive buffers over NVLink (CUDA IPC), 1-element NCCL all-reduce as barrier"
-                                 if args.exchange == "fused" else "NCCL all_to_all_single")
+            extra["exchange"] = {"fused": "fused: stage-0 kernels store into peer receive buffers over NVLink (CUDA IPC), epoch-flag barrier",
+                                 "dma": f"dma: stage 0 writes a chunk-major send buffer, copy engines push the pieces into the peers' receive "
+                                        f"buffers over NVLink ({slab.chunks} z-chunk(s), per-chunk epoch flags), stage 1 on a side stream",
+                                 "nccl": "NCCL all_to_all_single"}[args.exchange]
 
             def one_direction(b, isign):
                 slab.transform(b, speq, isign)
@@ -645,7 +647,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="rlft3_512", choices=sorted(METRIC))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"], help="multi-GPU rlft3 exchange")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "dma", "nccl"], help="multi-GPU rlft3 exchange")
     ap.add_argument("--chunks", type=int, default=1, help="multi-GPU rlft3, fused exchange: z-chunks of the pipelined exchange (1 = off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

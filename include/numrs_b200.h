@@ -221,6 +221,20 @@ int    nrb_slab_barrier(nrb_slab_t plan, int phase, unsigned long long epoch, vo
 int    nrb_slab_set_chunks(nrb_slab_t plan, int chunks);
 int    nrb_slab_stage_part(nrb_slab_t plan, int stage, int part, int isign, double *d_slab, double *d_speq, void *stream);
 int    nrb_slab_barrier_chunk(nrb_slab_t plan, int phase, int chunk, unsigned long long epoch, void *stream);
+/* DMA-pipelined exchange: stage 0 writes a plan-owned send buffer whose blocks are laid out chunk-major
+ * ([chunk][nn1/G][nn2/G][nn3/2/chunks]), so the piece (peer, chunk) is contiguous; copy engines -- not SMs -- push
+ * the pieces into the peers' receive buffers (nrb_slab_set_peers) and a one-warp kernel then publishes the chunk's
+ * epoch flag; stage 1 of the chunk runs on the plan's high-priority side stream as soon as every rank's flag is in.
+ * nrb_slab_exec_dma enqueues one whole direction (work before the chunks, all chunks, work after them) and makes
+ * `stream` wait for the plan's internal streams at the end.  `chunks` is a power of two, 1 ... 16.
+ * nrb_slab_stage_part_xchg is the step-wise form (tests): stage 0 of a chunk writes d_xchg, stage 1 reads it. */
+int    nrb_slab_set_dma(nrb_slab_t plan, int chunks);
+int    nrb_slab_exec_dma(nrb_slab_t plan, int isign, double *d_slab, double *d_speq, unsigned long long epoch, void *stream);
+int    nrb_slab_stage_part_xchg(nrb_slab_t plan, int stage, int part, int isign, double *d_slab, double *d_speq, double *d_xchg,
+                                void *stream);
+/* diagnostics: (after a synchronise) writes "piece=ms since the start" for every piece of the last nrb_slab_exec_dma
+ * into `text`, then switches the recording of those timing events on or off for the next calls */
+int    nrb_slab_dma_timeline(nrb_slab_t plan, int enable, char *text, size_t cap);
 int    nrb_slab_destroy(nrb_slab_t plan);
 /* raw (zero-initialised) device memory + CUDA IPC plumbing for the above */
 int    nrb_device_alloc(size_t bytes, void **dptr);

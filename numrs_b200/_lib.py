@@ -46,6 +46,7 @@ ABI_SYMBOLS = [
     "nrb_slab_create", "nrb_slab_local_doubles", "nrb_slab_speq_doubles", "nrb_slab_xchg_doubles",
     "nrb_slab_stage", "nrb_slab_destroy", "nrb_slab_set_peers", "nrb_slab_recv_bytes", "nrb_slab_barrier",
     "nrb_slab_set_chunks", "nrb_slab_stage_part", "nrb_slab_barrier_chunk",
+    "nrb_slab_set_dma", "nrb_slab_exec_dma", "nrb_slab_stage_part_xchg", "nrb_slab_dma_timeline",
     "nrb_upload", "nrb_download", "nrb_stream_synchronize", "nrb_complex_multiply_device",
     "nrb_device_alloc", "nrb_device_free", "nrb_ipc_export", "nrb_ipc_import", "nrb_ipc_release",
 ]
@@ -126,6 +127,10 @@ class Library:
         L.nrb_download.argtypes = [_vp, _vp, _sz, _vp]
         L.nrb_stream_synchronize.argtypes = [_vp]
         L.nrb_complex_multiply_device.argtypes = [_vp, _vp, _sz, ctypes.c_int, ctypes.c_double, _vp]
+        L.nrb_slab_set_dma.argtypes = [_vp, ctypes.c_int]
+        L.nrb_slab_exec_dma.argtypes = [_vp, ctypes.c_int, _vp, _vp, ctypes.c_ulonglong, _vp]
+        L.nrb_slab_stage_part_xchg.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp]
+        L.nrb_slab_dma_timeline.argtypes = [_vp, ctypes.c_int, ctypes.c_char_p, _sz]
         L.nrb_device_alloc.argtypes = [_sz, ctypes.POINTER(_vp)]
         L.nrb_device_free.argtypes = [_vp]
         L.nrb_ipc_export.argtypes = [_vp, ctypes.c_char_p]
@@ -390,6 +395,21 @@ class SlabPlan:
 
     def stage_part(self, stage, part, isign, d_slab, d_speq, stream=0):
         self.lib.check(self.lib.L.nrb_slab_stage_part(self.h, stage, part, isign, d_slab, d_speq, stream or None))
+
+    def set_dma(self, chunks):
+        self.lib.check(self.lib.L.nrb_slab_set_dma(self.h, chunks))
+
+    def exec_dma(self, isign, d_slab, d_speq, epoch, stream=0):
+        self.lib.check(self.lib.L.nrb_slab_exec_dma(self.h, isign, d_slab, d_speq, epoch, stream or None))
+
+    def stage_part_xchg(self, stage, part, isign, d_slab, d_speq, d_xchg, stream=0):
+        self.lib.check(self.lib.L.nrb_slab_stage_part_xchg(self.h, stage, part, isign, d_slab, d_speq, d_xchg or None,
+                                                           stream or None))
+
+    def dma_timeline(self, enable):
+        buf = ctypes.create_string_buffer(4096)
+        self.lib.check(self.lib.L.nrb_slab_dma_timeline(self.h, int(enable), buf, 4096))
+        return buf.value.decode()
 
     def barrier_chunk(self, phase, chunk, epoch, stream=0):
         self.lib.check(self.lib.L.nrb_slab_barrier_chunk(self.h, phase, chunk, epoch, stream or None))

@@ -26,7 +26,7 @@ struct nrb_plan_s {
 };
 struct nrb_slab_s {
     SlabPlan plan;
-    ~nrb_slab_s() { if (plan.ws) be_free(plan.ws); }
+    ~nrb_slab_s() { slab_release(plan); }
 };
 
 namespace {
@@ -347,6 +347,32 @@ int nrb_slab_stage_part(nrb_slab_t p, int stage, int part, int isign, double *d_
 {
     if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
     return exec_slab_part(p->plan, stage, part, isign, d_slab, d_speq, stream);
+}
+int nrb_slab_set_dma(nrb_slab_t p, int chunks)
+{
+    if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
+    return slab_set_dma(p->plan, chunks);
+}
+int nrb_slab_stage_part_xchg(nrb_slab_t p, int stage, int part, int isign, double *d_slab, double *d_speq, double *d_xchg, void *stream)
+{
+    if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
+    return exec_slab_part(p->plan, stage, part, isign, d_slab, d_speq, stream, d_xchg);
+}
+int nrb_slab_exec_dma(nrb_slab_t p, int isign, double *d_slab, double *d_speq, unsigned long long epoch, void *stream)
+{
+    if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
+    return exec_slab_dma(p->plan, isign, d_slab, d_speq, epoch, stream);
+}
+int nrb_slab_dma_timeline(nrb_slab_t p, int enable, char *text, size_t cap)
+{
+    if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
+    if (text && cap) {
+        const std::string t = slab_dma_timeline(p->plan);
+        strncpy(text, t.c_str(), cap - 1);
+        text[cap - 1] = 0;
+    }
+    p->plan.timeline = enable != 0;
+    return NRB_OK;
 }
 int nrb_slab_barrier_chunk(nrb_slab_t p, int phase, int chunk, unsigned long long epoch, void *stream)
 {

@@ -204,6 +204,32 @@ void *be_event_record(void *stream)
     cudaEventRecord(e, (cudaStream_t)stream);
     return (void *)e;
 }
+void *be_event_create()
+{
+    cudaEvent_t e;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    return (void *)e;
+}
+int be_event_record_on(void *event, void *stream)
+{
+    cudaError_t e = cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail(e);
+}
+int be_stream_wait(void *stream, void *event)
+{
+    cudaError_t e = cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0);
+    return e == cudaSuccess ? 0 : fail(e);
+}
+int be_stream_create_prio(void **stream, int high_priority)
+{
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    cudaStream_t s;
+    cudaError_t e = cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high_priority ? hi : lo);
+    if (e != cudaSuccess) return fail(e);
+    *stream = (void *)s;
+    return 0;
+}
 float be_event_elapsed_ms(void *a, void *b)
 {
     float ms = 0.f;

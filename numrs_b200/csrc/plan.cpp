@@ -1010,6 +1010,26 @@ static int run_program(Program &prog, double2 *const base[4], int arg, void *str
     return NRB_OK;
 }
 
+// stage 0 of the DMA exchange: like run_program, but block p of the exchange output lives at table[p] + p*BLK
+static int run_program_dma(Program &prog, double2 *const base[4], void *stream, double2 *const table[8], i64 BLK)
+{
+    for (Step &st : prog.steps) {
+        if (st.is_aux || st.is_fused) { set_error("slab: unexpected step in an exchange program"); return NRB_ERR_UNSUPPORTED; }
+        PassParams pp = st.pp;
+        pp.in = base[st.in.id] + st.in.off;
+        pp.out = base[st.out.id] + st.out.off;
+        pp.speq = st.speq.id == BUF_NONE ? nullptr : base[st.speq.id] + st.speq.off;
+        pp.prefetch_dist = 0;
+        if (st.out.id == BUF_OUT) {
+            pp.out_peer_on = 1;
+            pp.out_peer_off = 0;
+            for (int i = 0; i < 8; ++i) pp.out_peer[i] = table[i] ? table[i] + (i64)i * BLK + st.out.off : nullptr;
+        }
+        if (be_launch_pass(st.key, pp, st.ntiles, stream) != 0) { set_error(std::string("kernel launch failed: ") + be_last_error()); return NRB_ERR_CUDA; }
+    }
+    return NRB_OK;
+}
+
 int exec_plan(Plan &pl, double *d_io, double *d_aux, double *d_out, int isign, int arg, void *stream)
 {
     if (isign != 1 && isign != -1) { set_error("isign must be 1 or -1"); return NRB_ERR_INVALID_ISIGN; }
@@ -1184,33 +1204,28 @@ int build_slab_plan(SlabPlan &sp, size_t nn1, size_t nn2, size_t nn3, int nranks
 // inverse  y pass (c): slab -> peers;  x pass (c): recv -> work;  z pass: work -> slab
 // The speq planes travel with chunk 0.  `work` sits in the plan's workspace after the [nn1][Y] speq scratch.
 namespace {
-void chunk_lines(Step &st, u64 mid, i64 mid_stride_in, i64 mid_stride_out, u64 N3, u64 Zc, int c)
+struct LineMap { i64 s0, s1; };     // strides of (z-chunk, middle index); the z index inside a chunk has stride 1
+void chunk_lines(Step &st, u64 mid, LineMap in, LineMap out, u64 Zc, int c)
 {
     PassParams &pp = st.pp;
     pp.logB = ilog2((size_t)Zc);
     pp.logA = ilog2((size_t)mid);
-    pp.in_s0 = (i64)Zc; pp.in_s1 = mid_stride_in; pp.in_s2 = 1;
-    pp.out_s0 = (i64)Zc; pp.out_s1 = mid_stride_out; pp.out_s2 = 1;
+    pp.in_s0 = in.s0; pp.in_s1 = in.s1; pp.in_s2 = 1;
+    pp.out_s0 = out.s0; pp.out_s1 = out.s1; pp.out_s2 = 1;
     pp.q_begin = (u64)c * mid * Zc;
     pp.q_end = (u64)(c + 1) * mid * Zc;
     st.ntiles = tiles_for(st.key.log2n, st.key.layout, pp.q_end - pp.q_begin);
-    (void)N3;
 }
-} // namespace
 
-int slab_set_chunks(SlabPlan &sp, int chunks)
+// dma = false: blocks [X][Y][N3] (peer stores from the FFT epilogue); dma = true: blocks [chunk][X][Y][Zc], so the
+// piece (peer, chunk) is one contiguous range for a copy engine
+int build_chunk_programs(SlabPlan &sp, int chunks, bool dma)
 {
     const u64 G = (u64)sp.nranks, X = sp.nn1 / G, Y = sp.nn2 / G, N3 = sp.nn3 / 2;
     const int p1 = ilog2(sp.nn1), p2 = ilog2(sp.nn2), p3 = ilog2((size_t)N3);
-    if (chunks < 1 || !is_pow2((size_t)chunks)) { set_error("slab: chunks must be a power of two"); return NRB_ERR_INVALID_DIMS; }
-    for (int s = 0; s < 2; ++s) sp.part[s].clear();
-    sp.chunks = 1;
-    if (chunks == 1) return NRB_OK;
     const u64 Zc = N3 / (u64)chunks;
-    // (a chunk narrower than a COL tile's line count still works -- every thread addresses its own line -- but
-    // shortens the contiguous runs; at 512^3 a tile has 8 lines and a chunk 32 or more)
     if (Zc < 1 || Zc * (u64)chunks != N3) { set_error("slab: too many chunks for this nn3"); return NRB_ERR_INVALID_DIMS; }
-    const i64 BLK = (i64)(X * Y * (N3 + 1)), SPQ = (i64)(X * Y * N3);
+    const i64 BLK = (i64)(X * Y * (N3 + 1)), SPQ = (i64)(X * Y * N3), PIECE = (i64)(X * Y * Zc);
     const size_t speq_ws = (size_t)(sp.nn1 * Y), work_elems = (size_t)(sp.nn1 * Y * N3);
     if (sp.ws_elems < speq_ws + work_elems) {
         void *nw = nullptr;
@@ -1220,17 +1235,24 @@ int slab_set_chunks(SlabPlan &sp, int chunks)
         sp.ws_elems = speq_ws + work_elems;
     }
     const BufRef SLAB(BUF_IO, 0), SPEQ(BUF_AUX, 0), XCH(BUF_OUT, 0), WSPEQ(BUF_WS, 0), WORK(BUF_WS, (i64)speq_ws);
+    // strides inside an exchange block
+    const i64 xl_stride = dma ? (i64)(Y * Zc) : (i64)(Y * N3), yl_stride = dma ? (i64)Zc : (i64)N3, zc_stride = dma ? PIECE : (i64)Zc;
     AxisMap x_blocks;
-    x_blocks.on = true; x_blocks.s0 = 0; x_blocks.es = (i64)(Y * N3); x_blocks.eshift = ilog2((size_t)X); x_blocks.es_hi = BLK;
+    x_blocks.on = true; x_blocks.s0 = 0; x_blocks.es = xl_stride; x_blocks.eshift = ilog2((size_t)X); x_blocks.es_hi = BLK;
     AxisMap x_blocks_speq = x_blocks;
     x_blocks_speq.es = (i64)Y;
     AxisMap y_blocks;
-    y_blocks.on = true; y_blocks.s0 = (i64)(Y * N3); y_blocks.es = (i64)N3; y_blocks.eshift = ilog2((size_t)Y); y_blocks.es_hi = BLK;
+    y_blocks.on = true; y_blocks.s0 = xl_stride; y_blocks.es = yl_stride; y_blocks.eshift = ilog2((size_t)Y); y_blocks.es_hi = BLK;
     AxisMap y_blocks_speq;
     y_blocks_speq.on = true; y_blocks_speq.s0 = (i64)Y; y_blocks_speq.es = 1; y_blocks_speq.eshift = ilog2((size_t)Y); y_blocks_speq.es_hi = BLK;
+    const LineMap work_lines{(i64)Zc, (i64)N3};                      // [nn1][Y][N3]: lines (zc, y, zl)
+    const LineMap slab_lines{(i64)Zc, (i64)(sp.nn2 * N3)};           // [X][nn2][N3]: lines (zc, xl, zl)
+    const LineMap xch_x_lines{zc_stride, yl_stride};                 // exchange block, lines (zc, y_local, zl)
+    const LineMap xch_y_lines{zc_stride, xl_stride};                 // exchange block, lines (zc, x_local, zl)
     int rc = NRB_OK;
     for (int s = 0; s < 2; ++s) {
         const int dir = s == 0 ? +1 : -1;
+        sp.part[s].clear();
         sp.part[s].resize((size_t)(2 * chunks + 2));
         {   // before the chunks
             Builder B(&sp.part[s][0]);
@@ -1241,18 +1263,18 @@ int slab_set_chunks(SlabPlan &sp, int chunks)
             Builder B0(&sp.part[s][(size_t)(1 + 2 * c)]), B1(&sp.part[s][(size_t)(2 + 2 * c)]);
             if (dir > 0) {
                 emit_axis(B0, WORK, XCH, BufRef(), 1, 0, 1, p1, Y * N3, +1, nullptr, &x_blocks);
-                chunk_lines(B0.prog->steps.back(), Y, (i64)N3, (i64)N3, N3, Zc, c);
+                chunk_lines(B0.prog->steps.back(), Y, work_lines, xch_x_lines, Zc, c);
                 if (c == 0) emit_axis(B0, WSPEQ, XCH + SPQ, BufRef(), 1, 0, 1, p1, Y, +1, nullptr, &x_blocks_speq);
                 emit_axis(B1, XCH, SLAB, BufRef(), X, 0, X, p2, N3, +1, &y_blocks, nullptr);
-                chunk_lines(B1.prog->steps.back(), X, (i64)(Y * N3), (i64)(sp.nn2 * N3), N3, Zc, c);
+                chunk_lines(B1.prog->steps.back(), X, xch_y_lines, slab_lines, Zc, c);
                 if (c == 0) emit_axis(B1, XCH + SPQ, SPEQ, BufRef(), X, 0, X, p2, 1, +1, &y_blocks_speq, nullptr);
             } else {
                 emit_axis(B0, SLAB, XCH, BufRef(), X, 0, X, p2, N3, -1, nullptr, &y_blocks);
-                chunk_lines(B0.prog->steps.back(), X, (i64)(sp.nn2 * N3), (i64)(Y * N3), N3, Zc, c);
+                chunk_lines(B0.prog->steps.back(), X, slab_lines, xch_y_lines, Zc, c);
                 if (c == 0) emit_axis(B0, SPEQ, XCH + SPQ, BufRef(), X, 0, X, p2, 1, -1, nullptr, &y_blocks_speq);
                 if (c == 0) emit_axis(B1, XCH + SPQ, WSPEQ, BufRef(), 1, 0, 1, p1, Y, -1, &x_blocks_speq, nullptr);
                 emit_axis(B1, XCH, WORK, BufRef(), 1, 0, 1, p1, Y * N3, -1, &x_blocks, nullptr);
-                chunk_lines(B1.prog->steps.back(), Y, (i64)N3, (i64)N3, N3, Zc, c);
+                chunk_lines(B1.prog->steps.back(), Y, xch_x_lines, work_lines, Zc, c);
             }
             rc = B0.rc ? B0.rc : (B1.rc ? B1.rc : rc);
         }
@@ -1263,24 +1285,144 @@ int slab_set_chunks(SlabPlan &sp, int chunks)
         }
     }
     if (rc != NRB_OK) { for (int s = 0; s < 2; ++s) sp.part[s].clear(); set_error("slab: shape not supported"); return rc; }
+    return NRB_OK;
+}
+} // namespace
+
+int slab_set_chunks(SlabPlan &sp, int chunks)
+{
+    if (chunks < 1 || !is_pow2((size_t)chunks)) { set_error("slab: chunks must be a power of two"); return NRB_ERR_INVALID_DIMS; }
+    for (int s = 0; s < 2; ++s) sp.part[s].clear();
+    sp.chunks = 1;
+    sp.dma = false;
+    if (chunks == 1) return NRB_OK;
+    const int rc = build_chunk_programs(sp, chunks, false);
+    if (rc == NRB_OK) sp.chunks = chunks;
+    return rc;
+}
+
+int slab_set_dma(SlabPlan &sp, int chunks)
+{
+    if (chunks < 1 || chunks > kSlabMaxChunks || !is_pow2((size_t)chunks)) { set_error("slab: chunks must be a power of two <= 16"); return NRB_ERR_INVALID_DIMS; }
+    for (int s = 0; s < 2; ++s) sp.part[s].clear();
+    sp.chunks = 1;
+    sp.dma = false;
+    const int rc = build_chunk_programs(sp, chunks, true);
+    if (rc != NRB_OK) return rc;
+    const u64 G = (u64)sp.nranks;
+    const size_t xchg = (size_t)(G * (sp.nn1 / G) * (sp.nn2 / G) * (sp.nn3 / 2 + 1));
+    if (!sp.send && be_malloc(&sp.send, xchg * sizeof(double2)) != 0) { set_error("slab: send buffer allocation failed"); return NRB_ERR_OOM; }
+    if (!sp.copy_stream) {
+        if (be_stream_create_prio(&sp.copy_stream, 0) != 0 || be_stream_create_prio(&sp.side_stream, 1) != 0) { set_error("slab: stream creation failed"); return NRB_ERR_CUDA; }
+        sp.ev_go = be_event_create(); sp.ev_side = be_event_create(); sp.ev_copy = be_event_create();
+        for (int c = 0; c < kSlabMaxChunks; ++c) sp.ev_s0[c] = be_event_create();
+    }
     sp.chunks = chunks;
+    sp.dma = true;
     return NRB_OK;
 }
 
-int exec_slab_part(SlabPlan &sp, int stage, int part, int isign, double *d_slab, double *d_speq, void *stream)
+void slab_release(SlabPlan &sp)
+{
+    if (sp.ws) be_free(sp.ws);
+    if (sp.send) be_free(sp.send);
+    if (sp.copy_stream) be_stream_destroy(sp.copy_stream);
+    if (sp.side_stream) be_stream_destroy(sp.side_stream);
+    for (void *e : {sp.ev_go, sp.ev_side, sp.ev_copy}) if (e) be_event_destroy(e);
+    for (int c = 0; c < kSlabMaxChunks; ++c) if (sp.ev_s0[c]) be_event_destroy(sp.ev_s0[c]);
+    sp.ws = sp.send = sp.copy_stream = sp.side_stream = sp.ev_go = sp.ev_side = sp.ev_copy = nullptr;
+    for (int c = 0; c < kSlabMaxChunks; ++c) sp.ev_s0[c] = nullptr;
+}
+
+int exec_slab_part(SlabPlan &sp, int stage, int part, int isign, double *d_slab, double *d_speq, void *stream, double *d_xchg)
 {
     if (isign != 1 && isign != -1) { set_error("isign must be 1 or -1"); return NRB_ERR_INVALID_ISIGN; }
-    if (!sp.fused || sp.chunks <= 1) { set_error("slab: the pipelined exchange needs nrb_slab_set_peers and nrb_slab_set_chunks"); return NRB_ERR_INVALID_DIMS; }
+    if (sp.part[0].empty() || (!sp.dma && !sp.fused)) { set_error("slab: the pipelined exchange needs nrb_slab_set_peers and nrb_slab_set_chunks / nrb_slab_set_dma"); return NRB_ERR_INVALID_DIMS; }
     if (part < -1 || part > sp.chunks || ((part >= 0 && part < sp.chunks) && stage != 0 && stage != 1)) { set_error("slab: bad part"); return NRB_ERR_INVALID_DIMS; }
     const size_t idx = part < 0 ? 0 : part == sp.chunks ? (size_t)(2 * sp.chunks + 1) : (size_t)(1 + 2 * part + stage);
     const u64 G = (u64)sp.nranks;
     const i64 BLK = (i64)((sp.nn1 / G) * (sp.nn2 / G) * (sp.nn3 / 2 + 1));
+    const bool chunk_part = part >= 0 && part < sp.chunks;
+    Program &prog = sp.part[isign == 1 ? 0 : 1][idx];
+    if (sp.dma) {
+        // stage 0 writes the caller's send buffer, stage 1 reads the caller's receive buffer
+        if (chunk_part && !d_xchg) { set_error("slab: DMA exchange needs the send / receive buffer"); return NRB_ERR_INVALID_DIMS; }
+        double2 *const base[4] = {(double2 *)d_slab, (double2 *)d_speq, (double2 *)d_xchg, (double2 *)sp.ws};
+        for (Step &st : prog.steps) if (!st.is_aux) st.pp.grid_cap = 0;
+        if (chunk_part && stage == 0 && sp.fused) {
+            // blocks for the peers go to the send buffer; the own block goes straight to block `rank` of the own
+            // receive buffer (no copy for it).  The pointer table is what the fused exchange uses for peer stores.
+            double2 *table[8];
+            for (int i = 0; i < 8; ++i) table[i] = i >= sp.nranks ? nullptr : i == sp.rank ? sp.peers[sp.rank] : (double2 *)d_xchg;
+            return run_program_dma(prog, base, stream, table, BLK);
+        }
+        return run_program(prog, base, 0, stream);
+    }
     double2 *const base[4] = {(double2 *)d_slab, (double2 *)d_speq, sp.peers[sp.rank], (double2 *)sp.ws};
     PeerExchange px{sp.peers, (i64)sp.rank * BLK};
-    const bool sends = part >= 0 && part < sp.chunks && stage == 0;
-    Program &prog = sp.part[isign == 1 ? 0 : 1][idx];
+    const bool sends = chunk_part && stage == 0;
     for (Step &st : prog.steps) if (!st.is_aux) st.pp.grid_cap = sends ? tunables().xchg_grid_cap : 0;
     return run_program(prog, base, 0, stream, nullptr, sends ? &px : nullptr);
+}
+
+// One direction with the DMA-pipelined exchange.  Streams: `stream` runs the work before the chunks, every chunk's
+// stage 0 and the work after the chunks; the copy stream pushes chunk c's pieces to the peers (copy engines, no SMs)
+// and then publishes chunk c's epoch flag; the side stream waits for chunk c's flags of all ranks and runs stage 1.
+int exec_slab_dma(SlabPlan &sp, int isign, double *d_slab, double *d_speq, unsigned long long epoch, void *stream)
+{
+    if (!sp.dma || !sp.fused) { set_error("slab: nrb_slab_set_dma and nrb_slab_set_peers first"); return NRB_ERR_INVALID_DIMS; }
+    const u64 G = (u64)sp.nranks, X = sp.nn1 / G, Y = sp.nn2 / G, N3 = sp.nn3 / 2;
+    const i64 BLK = (i64)(X * Y * (N3 + 1)), SPQ = (i64)(X * Y * N3), PIECE = (i64)(X * Y * (N3 / (u64)sp.chunks));
+    double2 *send = (double2 *)sp.send, *recv = sp.peers[sp.rank];
+    if (sp.timeline) { for (void *e : sp.tl_events) be_event_destroy(e); sp.tl_events.clear(); sp.tl_names.clear(); }
+    auto mark = [&](const char *what, int c, void *s) {
+        if (!sp.timeline) return;
+        sp.tl_events.push_back(be_event_record(s));
+        sp.tl_names.push_back(c >= 0 ? std::string(what) + "[" + std::to_string(c) + "]" : std::string(what));
+    };
+    mark("start", -1, stream);
+    int rc = exec_slab_part(sp, 0, -1, isign, d_slab, d_speq, stream);
+    if (rc) return rc;
+    mark("pre", -1, stream);
+    if (be_event_record_on(sp.ev_go, stream) || be_stream_wait(sp.copy_stream, sp.ev_go) || be_stream_wait(sp.side_stream, sp.ev_go)) {
+        set_error(std::string("stream ordering failed: ") + be_last_error());
+        return NRB_ERR_CUDA;
+    }
+    for (int c = 0; c < sp.chunks; ++c) {
+        if ((rc = exec_slab_part(sp, 0, c, isign, d_slab, d_speq, stream, (double *)send))) return rc;
+        mark("s0", c, stream);
+        if (be_event_record_on(sp.ev_s0[c], stream) || be_stream_wait(sp.copy_stream, sp.ev_s0[c])) { set_error("stream ordering failed"); return NRB_ERR_CUDA; }
+        for (u64 i = 1; i < G; ++i) {                     // rotated so that every rank targets a different peer at a time;
+            const u64 p = ((u64)sp.rank + i) % G;         // the own block went straight into the own receive buffer
+            if (be_d2d(sp.peers[p] + (i64)sp.rank * BLK + (i64)c * PIECE, send + (i64)p * BLK + (i64)c * PIECE, (size_t)PIECE * sizeof(double2), sp.copy_stream) != 0 ||
+                (c == 0 && be_d2d(sp.peers[p] + (i64)sp.rank * BLK + SPQ, send + (i64)p * BLK + SPQ, (size_t)(X * Y) * sizeof(double2), sp.copy_stream) != 0)) {
+                set_error(std::string("peer copy failed: ") + be_last_error());
+                return NRB_ERR_CUDA;
+            }
+        }
+        mark("copy", c, sp.copy_stream);
+        if ((rc = slab_barrier_chunk(sp, 0, c, epoch, sp.copy_stream))) return rc;     // chunk c of this rank has landed everywhere
+        if ((rc = slab_barrier_chunk(sp, 1, c, epoch, sp.side_stream))) return rc;     // chunk c of every rank has landed here
+        mark("wait", c, sp.side_stream);
+        if ((rc = exec_slab_part(sp, 1, c, isign, d_slab, d_speq, sp.side_stream, (double *)recv))) return rc;
+        mark("s1", c, sp.side_stream);
+    }
+    if (be_event_record_on(sp.ev_side, sp.side_stream) || be_stream_wait(stream, sp.ev_side) ||
+        be_event_record_on(sp.ev_copy, sp.copy_stream) || be_stream_wait(stream, sp.ev_copy)) { set_error("stream ordering failed"); return NRB_ERR_CUDA; }
+    rc = exec_slab_part(sp, 0, sp.chunks, isign, d_slab, d_speq, stream);
+    mark("end", -1, stream);
+    return rc;
+}
+
+std::string slab_dma_timeline(SlabPlan &sp)
+{
+    std::string out;
+    char buf[64];
+    for (size_t i = 0; i < sp.tl_events.size(); ++i) {
+        snprintf(buf, sizeof(buf), "%s=%.3f ", sp.tl_names[i].c_str(), i ? be_event_elapsed_ms(sp.tl_events[0], sp.tl_events[i]) : 0.0f);
+        out += buf;
+    }
+    return out;
 }
 
 int slab_set_peers(SlabPlan &sp, void *const *peer_recv, int count)

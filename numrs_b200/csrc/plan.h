@@ -36,6 +36,10 @@ int be_stream_destroy(void *stream);
 void *be_host_alloc(size_t bytes);
 void be_host_free(void *p);
 void *be_event_record(void *stream);
+void *be_event_create();                          // reusable, no timing
+int be_event_record_on(void *event, void *stream);
+int be_stream_wait(void *stream, void *event);
+int be_stream_create_prio(void **stream, int high_priority);
 float be_event_elapsed_ms(void *a, void *b);
 void be_event_destroy(void *e);
 const char *be_last_error();
@@ -134,17 +138,34 @@ struct SlabPlan {
     // part[isign][1 + 2*chunks] = work that follows them (inverse: z pass)
     int chunks;
     std::vector<Program> part[2];
+    // DMA exchange (slab_set_dma): stage 0 writes a local send buffer whose blocks are laid out chunk-major, so the
+    // piece (peer, chunk) is contiguous and copy engines push it into the peer's receive buffer; per-chunk flags
+    bool dma;
+    void *send;                  // owned, xchg size
+    void *copy_stream, *side_stream, *ev_go, *ev_side, *ev_copy, *ev_s0[16];
+    bool timeline;               // diagnostics: timing events around every piece of the last exec_slab_dma
+    std::vector<void *> tl_events;
+    std::vector<std::string> tl_names;
     size_t ws_elems;
     void *ws;
     double2 *peers[8];     // peer receive buffers (fused exchange); peers[rank] is the local one
     bool fused;
-    SlabPlan() : nn1(0), nn2(0), nn3(0), nranks(1), rank(0), chunks(1), ws_elems(0), ws(nullptr), peers{}, fused(false) {}
+    SlabPlan() : nn1(0), nn2(0), nn3(0), nranks(1), rank(0), chunks(1), dma(false), send(nullptr), copy_stream(nullptr), side_stream(nullptr),
+                 ev_go(nullptr), ev_side(nullptr), ev_copy(nullptr), ev_s0{}, timeline(false), ws_elems(0), ws(nullptr), peers{}, fused(false) {}
 };
 int build_slab_plan(SlabPlan &sp, size_t nn1, size_t nn2, size_t nn3, int nranks, int rank);
 // cut the exchange into `chunks` z-ranges (1 = off); allocates the out-of-place work slab
 int slab_set_chunks(SlabPlan &sp, int chunks);
 // part: -1 = before the chunks, chunks = after them, else stage `stage` of chunk `part` (fused exchange only)
-int exec_slab_part(SlabPlan &sp, int stage, int part, int isign, double *d_slab, double *d_speq, void *stream);
+int exec_slab_part(SlabPlan &sp, int stage, int part, int isign, double *d_slab, double *d_speq, void *stream,
+                   double *d_xchg = nullptr);
+// DMA exchange: chunk-major block layout + plan-owned send buffer, streams and events (chunks >= 1)
+int slab_set_dma(SlabPlan &sp, int chunks);
+// one direction of the DMA-pipelined transform, enqueued on `stream` (plus the plan's copy and side streams)
+int exec_slab_dma(SlabPlan &sp, int isign, double *d_slab, double *d_speq, unsigned long long epoch, void *stream);
+void slab_release(SlabPlan &sp);
+// diagnostics: after a synchronise, "name=ms since the start" of every piece of the last exec_slab_dma
+std::string slab_dma_timeline(SlabPlan &sp);
 int slab_barrier_chunk(SlabPlan &sp, int phase, int chunk, unsigned long long epoch, void *stream);
 int slab_set_peers(SlabPlan &sp, void *const *peer_recv, int count);
 // flag barrier of the fused exchange (flags live right after the exchange area of each receive buffer)

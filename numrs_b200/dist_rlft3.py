@@ -14,6 +14,10 @@ Inverse (isign=-1) is the mirror image.  Exactly one exchange per direction:
       `chunks` > 1 pipelines the exchange: the volume is cut into z-ranges, stage 1 of chunk c (HBM-bound, local)
       runs on a second stream under the NVLink-bound stage-0 stores of chunk c + 1; every chunk has its own
       epoch flags.
+  mode "dma": stage 0 writes a chunk-major send buffer, copy engines (not SMs) push every (peer, chunk) piece into
+      the peer's receive buffer over NVLink, a flag per chunk follows the copies, and stage 1 of the chunk runs on
+      a high-priority side stream -- the local passes overlap the transfer (nrb_slab_exec_dma does the whole
+      direction in one C call to keep the launch overhead down).
   mode "nccl": stage 0 writes a send buffer, torch.distributed.all_to_all_single moves the blocks.
 """
 import torch
@@ -33,12 +37,14 @@ class SlabRlft3:
         self.barrier = barrier
         self._flag = torch.zeros(1, dtype=torch.int32, device="cuda")
         self._call = 0
-        self.chunks = chunks if (mode == "fused" and barrier == "flags" and self.world > 1) else 1
-        if self.chunks > 1:
+        self.chunks = chunks if (mode in ("fused", "dma") and barrier == "flags" and self.world > 1) else 1
+        if mode == "dma":
+            self.plan.set_dma(self.chunks)
+        elif self.chunks > 1:
             self.plan.set_chunks(self.chunks)
             self._side = torch.cuda.Stream(priority=-1)       # stage 1 pieces: short, HBM-bound -> scheduled first
             self._ev_go, self._ev_done = torch.cuda.Event(), torch.cuda.Event()
-        if mode == "fused":
+        if mode in ("fused", "dma"):
             # two receive buffers, alternated per call, so a peer still reading call k's data in its
             # stage 1 is never overwritten by call k+1's stage 0 (ordered by call k+1's barrier)
             self._own, self._peers = [], []
@@ -64,7 +70,11 @@ class SlabRlft3:
         """slab, speq: torch float64 CUDA tensors (local_doubles / speq_doubles); in place; enqueues on
         the current stream."""
         st = torch.cuda.current_stream().cuda_stream
-        if self.mode == "fused":
+        if self.mode == "dma":
+            self.plan.set_peers(self._peers[self._call & 1])
+            self._call += 1
+            self.plan.exec_dma(isign, slab.data_ptr(), speq.data_ptr(), (self._call + 1) // 2, st)
+        elif self.mode == "fused":
             peers = self._peers[self._call & 1]
             self._call += 1
             self.plan.set_peers(peers)
@@ -103,7 +113,7 @@ class SlabRlft3:
     def close(self):
         torch.cuda.synchronize()
         dist.barrier()
-        if self.mode == "fused":
+        if self.mode in ("fused", "dma"):
             for own, peers in zip(self._own, self._peers):
                 for r, p in enumerate(peers):
                     if r != self.rank:

@@ -217,6 +217,10 @@ void *be_event_record(void *)
     clock_gettime(CLOCK_MONOTONIC, ts);
     return ts;
 }
+void *be_event_create() { return new timespec; }
+int be_event_record_on(void *, void *) { return 0; }
+int be_stream_wait(void *, void *) { return 0; }
+int be_stream_create_prio(void **s, int) { *s = (void *)1; return 0; }
 float be_event_elapsed_ms(void *a, void *b)
 {
     const timespec *x = (const timespec *)a, *y = (const timespec *)b;

@@ -136,6 +136,77 @@ def test_slab_pipelined_exchange(emu, shape, G, chunks):
     plan.destroy()
 
 
+def run_simulated_dma(L, x, G, isign, chunks, speq_in=None):
+    """DMA exchange, step-wise, all G ranks in one process: stage 0 of chunk c writes each rank's send buffer
+    (chunk-major blocks), the test plays the copy engines (piece (peer, chunk) -> block `rank` of the peer's
+    receive buffer), then stage 1 of chunk c."""
+    nn1, nn2, nn3 = x.shape
+    X, Y, N3 = nn1 // G, nn2 // G, nn3 // 2
+    plans = [L.slab_create(nn1, nn2, nn3, G, r) for r in range(G)]
+    xd = plans[0].xchg_doubles()
+    blk, spq, piece = 2 * X * Y * (N3 + 1), 2 * X * Y * N3, 2 * X * Y * (N3 // chunks)      # in doubles
+    if isign == 1:
+        slabs = [slab_of(x, r, G).ravel().copy() for r in range(G)]
+        speqs = [np.zeros(plans[r].speq_doubles()) for r in range(G)]
+    else:
+        slabs = [np.ascontiguousarray(x[r * X:(r + 1) * X]).ravel().copy() for r in range(G)]
+        speqs = [np.ascontiguousarray(speq_in[r * X:(r + 1) * X]).ravel().copy() for r in range(G)]
+    sends = [np.full(xd, np.nan) for _ in range(G)]
+    recvs = [np.full(xd, np.nan) for _ in range(G)]
+    for r in range(G):
+        plans[r].set_dma(chunks)
+        plans[r].stage_part_xchg(0, -1, isign, slabs[r].ctypes.data, speqs[r].ctypes.data, 0)
+    for c in range(chunks):
+        for r in range(G):
+            plans[r].stage_part_xchg(0, c, isign, slabs[r].ctypes.data, speqs[r].ctypes.data, sends[r].ctypes.data)
+        for r in range(G):
+            for p in range(G):
+                recvs[p][r * blk + c * piece:r * blk + (c + 1) * piece] = sends[r][p * blk + c * piece:p * blk + (c + 1) * piece]
+                if c == 0:
+                    recvs[p][r * blk + spq:(r + 1) * blk] = sends[r][p * blk + spq:(p + 1) * blk]
+        for r in range(G):
+            plans[r].stage_part_xchg(1, c, isign, slabs[r].ctypes.data, speqs[r].ctypes.data, recvs[r].ctypes.data)
+    for r in range(G):
+        plans[r].stage_part_xchg(0, chunks, isign, slabs[r].ctypes.data, speqs[r].ctypes.data, 0)
+    for p in plans:
+        p.destroy()
+    return slabs, speqs
+
+
+@pytest.mark.parametrize("shape,G,chunks", [((8, 8, 32), 2, 2), ((16, 16, 64), 4, 4), ((8, 16, 64), 8, 1), ((16, 8, 16), 2, 8)])
+def test_slab_dma_exchange(emu, shape, G, chunks):
+    nn1, nn2, nn3 = shape
+    X = nn1 // G
+    x = O.fill_uniform(1006, 0, nn1 * nn2 * nn3).reshape(shape)
+    rd, rs = O.rlft3(x.copy(), np.zeros((nn1, 2 * nn2)), 1)
+    slabs, speqs = run_simulated_dma(emu, x, G, 1, chunks)
+    for r in range(G):
+        assert cases.rel(slabs[r], rd[r * X:(r + 1) * X]) <= cases.tol(x.size), (r, "data")
+        assert cases.rel(speqs[r], rs[r * X:(r + 1) * X]) <= cases.tol(x.size), (r, "speq")
+    back, _ = run_simulated_dma(emu, rd, G, -1, chunks, rs)
+    for r in range(G):
+        assert cases.rel(back[r] * (2.0 / x.size), slab_of(x, r, G)) <= cases.tol(x.size), (r, "round trip")
+
+
+def test_slab_dma_one_call_single_rank(emu):
+    """nrb_slab_exec_dma (streams, events, copies, per-chunk flags in one call) with world size 1, where the
+    emulated in-order execution is a valid schedule."""
+    shape = (8, 16, 32)
+    nn1, nn2, nn3 = shape
+    x = O.fill_uniform(1006, 0, nn1 * nn2 * nn3).reshape(shape)
+    rd, rs = O.rlft3(x.copy(), np.zeros((nn1, 2 * nn2)), 1)
+    plan = emu.slab_create(nn1, nn2, nn3, 1, 0)
+    recv = np.zeros(plan.recv_bytes() // 8)
+    plan.set_peers([recv.ctypes.data])
+    plan.set_dma(4)
+    slab, speq = x.ravel().copy(), np.zeros(plan.speq_doubles())
+    plan.exec_dma(1, slab.ctypes.data, speq.ctypes.data, 1)
+    assert cases.rel(slab, rd) <= cases.tol(x.size) and cases.rel(speq, rs) <= cases.tol(x.size)
+    plan.exec_dma(-1, slab.ctypes.data, speq.ctypes.data, 2)
+    assert cases.rel(slab * (2.0 / x.size), x) <= cases.tol(x.size)
+    plan.destroy()
+
+
 def test_slab_rejects_bad_rank_counts(emu):
     import numrs_b200 as nb
     for args in ((8, 8, 8, 3, 0), (8, 8, 8, 16, 0), (8, 8, 8, 2, 2), (8, 6, 8, 2, 0)):

@@ -1,13 +1,12 @@
 #!/bin/bash
-# sanitizer evidence for the kernels added after the first sanitizer run + C4 bench refresh
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 3 python tools/sanitize_small.py > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck exit $?" >> gpurun_out/sanitizer_memcheck.log
-tail -4 gpurun_out/sanitizer_memcheck.log
-timeout 1200 compute-sanitizer --tool racecheck --error-exitcode 3 python tools/sanitize_small.py > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck exit $?" >> gpurun_out/sanitizer_racecheck.log
-tail -4 gpurun_out/sanitizer_racecheck.log
-for w in convlv correl; do
-  timeout 300 python bench.py --steps 10 --warmup 3 --workload $w > gpurun_out/r01_bench_$w.json 2> gpurun_out/bench_$w.err
+N=${1:-2}
+for c in 1 4; do
+  timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2975$c tools/slab_dma_timeline.py 512 $c 2>&1 | grep -E "==|Error|error" | head
 done
-timeout 300 python tools/kernel_table.py convlv_22_16 correl_22_16 autocorrel_22_16 correlnorm_22_16 correlnormfast_22_16 > gpurun_out/r01_kernel_table_c4.txt 2>&1
-grep "^==" gpurun_out/r01_kernel_table_c4.txt; grep spectral gpurun_out/r01_kernel_table_c4.txt
+for cfg in "dma 1" "dma 4"; do
+  set -- $cfg; x=$1; c=$2
+  timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2976$c bench.py --gpus $N --steps 20 --warmup 3 --no-cpu --exchange $x --chunks $c > gpurun_out/bench_tmp.json 2> gpurun_out/bench_tmp.err
+  python -c "import json; d=json.loads(open('gpurun_out/bench_tmp.json').read()); print('  n=%d exchange=$x chunks=$c value %.0f GB/s  ms/step %.3f  roundtrip err %.2e' % (d['n_gpus'], d['value'], d['ms_per_step'], d['roundtrip_rel_l2']))" || tail -5 gpurun_out/bench_tmp.err
+done
