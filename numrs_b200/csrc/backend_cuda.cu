@@ -27,6 +27,18 @@ PassTable &pass_table()
     return t;
 }
 
+void register_big(PassTable &);
+PassTable &pass2_table()
+{
+    static PassTable t;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        memset(&t, 0, sizeof(t));
+        register_big(t);
+    });
+    return t;
+}
+
 void register_fused_a();
 void register_fused_b();
 void register_fused_c();
@@ -61,9 +73,15 @@ int be_launch_pass(const KernelKey &key, const PassParams &p, u64 ntiles, void *
         return -1;
     }
     PassLaunchFn fn = pass_table().fn[key.log2n][key.layout][key.dir > 0 ? 1 : 0][key.variant];
+    if (use_big_tiles(key, p)) {
+        PassLaunchFn big = pass2_table().fn[key.log2n][key.layout][key.dir > 0 ? 1 : 0][key.variant];
+        if (big) fn = big;
+    }
     if (!fn) { g_be_err = "kernel variant not built"; return -1; }
     if (ntiles > 0x7fffffffull) { g_be_err = "grid too large"; return -1; }
-    const int rc = fn(p, ntiles, (cudaStream_t)stream);
+    PassParams pp = p;
+    pp.simple = pass_is_simple(key, p) ? 1 : 0;
+    const int rc = fn(pp, ntiles, (cudaStream_t)stream);
     if (rc != 0) return fail((cudaError_t)rc);
     return 0;
 }

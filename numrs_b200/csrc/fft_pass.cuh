@@ -253,7 +253,18 @@ template <int LOG2N, int LAYOUT> NRB_DEV void stage_sync()
 
 // ------------------------------------------------------------------ one Stockham stage
 // SRC_G: inputs come from global memory (else shared); DST_G: outputs go to global memory.
-template <int LOG2N, int LAYOUT, int DIR, int VARIANT, int S, bool SRC_G, bool DST_G>
+// SIMPLE (compile-time copy of PassParams::simple, see simple_ok / pass_is_simple): the element index is not split
+// (offset = n * es, with es = 1 for ROW) -- then a thread's global addresses are one base pointer plus multiples of a
+// fixed step (immediate offsets for ROW), instead of ~13 integer instructions per element for the general form.
+// ncu on the N = 8192 pass: 45 % of all executed instructions were address arithmetic (profiles/r01_tuning.md #36).
+template <int LOG2N, int LAYOUT> NRB_HD constexpr bool simple_ok()
+{
+    // every butterfly of a thread must belong to the same line
+    return LAYOUT == LAYOUT_ROW ? line_owned<LOG2N, LAYOUT>()
+                                : (cta_threads(LOG2N, LAYOUT) % lines_per_tile(LOG2N, LAYOUT)) == 0;
+}
+
+template <int LOG2N, int LAYOUT, int DIR, int VARIANT, int S, bool SRC_G, bool DST_G, bool SIMPLE = false>
 NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
 {
     typedef Geo<LOG2N, LAYOUT, VARIANT> G;
@@ -262,6 +273,12 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
     constexpr int NB = G::N / R;           // butterflies per line
     constexpr int BPT = G::PPT / R;        // butterflies per thread
     static_assert(BPT >= 1, "radix larger than points per thread");
+    constexpr bool FAST = SIMPLE && simple_ok<LOG2N, LAYOUT>() && VARIANT == VAR_PLAIN;
+    // ROW shared-memory index n + (n >> 3): for the strides of a butterfly's legs the pad term is a compile-time
+    // constant -- phys(l, a + r*D) = phys(l, a) + r*D + (r*D >> 3) whenever D is a multiple of 8 or (writes) a + r*D
+    // stays inside the 8-block of a (checked exhaustively for every radix plan) -- so the legs are immediate offsets
+    constexpr bool ROW_RD_CONST = LAYOUT == LAYOUT_ROW && (NB % 8) == 0;
+    constexpr bool ROW_WR_CONST = LAYOUT == LAYOUT_ROW && (S == 0 || R == 8);
 
     double2 v[BPT][R];
     int ln[BPT], jj[BPT];
@@ -318,7 +335,7 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
                         }
                     }
                 }
-            } else {
+            } else if (!FAST) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     double2 x = make_double2(0.0, 0.0);
@@ -326,9 +343,44 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
                     v[i][r] = io_swap<DIR>(x);
                 }
             }
+        } else if (ROW_RD_CONST) {
+            const double2 *sp = sm + G::phys(ln[i], jj[i]);
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[i][r] = sp[r * NB + ((r * NB) >> 3)];
         } else {
 #pragma unroll
             for (int r = 0; r < R; ++r) v[i][r] = sm[G::phys(ln[i], jj[i] + r * NB)];
+        }
+    }
+    if (SRC_G && FAST) {
+        // one line per thread: base pointer once, then fixed steps (jj[i] = jj[0] + i * JSTEP)
+        constexpr int JSTEP = LAYOUT == LAYOUT_ROW ? (G::N / G::PPT) : (G::NT / G::L);
+        const u64 q = P.q_begin + (u64)tile * G::L + (u64)ln[0];
+        const bool ok = q < P.q_end;
+        const double2 *src = P.in + line_base(q, P.in_s0, P.in_s1, P.in_s2, P.logA, P.logB);
+        if (LAYOUT == LAYOUT_ROW) {
+            src += jj[0];
+#pragma unroll
+            for (int i = 0; i < BPT; ++i) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    double2 x = make_double2(0.0, 0.0);
+                    if (ok) x = NRB_LDS(src + (i * JSTEP + r * NB));
+                    v[i][r] = io_swap<DIR>(x);
+                }
+            }
+        } else {
+            const i64 es = P.in_es;
+            src += (i64)jj[0] * es;
+#pragma unroll
+            for (int i = 0; i < BPT; ++i) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    double2 x = make_double2(0.0, 0.0);
+                    if (ok) x = NRB_LDS(src + (i64)(i * JSTEP + r * NB) * es);
+                    v[i][r] = io_swap<DIR>(x);
+                }
+            }
         }
     }
 
@@ -406,6 +458,26 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
                     if (ok) NRB_STS(dst + (i64)k * P.out_es, f);
                 }
             }
+        } else if (DST_G && FAST && !P.out_peer_on) {
+            const u64 q = P.q_begin + (u64)tile * G::L + (u64)ln[0];
+            if (q < P.q_end) {
+                double2 *dst = P.out + line_base(q, P.out_s0, P.out_s1, P.out_s2, P.logA, P.logB);
+                double2 tw = make_double2(1.0, 0.0), tw_step = make_double2(1.0, 0.0);
+                if (P.tw_on) {
+                    const unsigned q1 = line_q1(P, q);
+                    tw = fourstep_tw_m(P, q1 * (unsigned)kb);
+                    tw_step = fourstep_tw_m(P, q1 * (unsigned)NS);
+                }
+                const i64 es = LAYOUT == LAYOUT_ROW ? (i64)1 : P.out_es;
+                dst += (i64)kb * es;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    double2 y = v[i][r];
+                    if (P.tw_on) { y = cmul(y, tw); tw = cmul(tw, tw_step); }
+                    if (LAYOUT == LAYOUT_ROW) NRB_STS(dst + r * NS, io_swap<DIR>(y));
+                    else NRB_STS(dst + (i64)(r * NS) * es, io_swap<DIR>(y));
+                }
+            }
         } else if (DST_G) {
             const u64 q = P.q_begin + (u64)tile * G::L + (u64)ln[i];
             if (q < P.q_end) {
@@ -433,6 +505,10 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
                     }
                 }
             }
+        } else if (ROW_WR_CONST) {
+            double2 *sp = sm + G::phys(ln[i], kb);
+#pragma unroll
+            for (int r = 0; r < R; ++r) sp[r * NS + ((r * NS) >> 3)] = v[i][r];
         } else {
 #pragma unroll
             for (int r = 0; r < R; ++r) sm[G::phys(ln[i], kb + r * NS)] = v[i][r];
@@ -442,7 +518,7 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
 
 // run stages FIRST..NST-1; stage FIRST reads global iff SRC_G0, the last stage writes global
 // iff DST_GL.  Barriers: after every stage that wrote shared memory.
-template <int LOG2N, int LAYOUT, int DIR, int VARIANT, int S, bool SRC_G0, bool DST_GL>
+template <int LOG2N, int LAYOUT, int DIR, int VARIANT, int S, bool SRC_G0, bool DST_GL, bool SIMPLE = false>
 struct StageRunner {
     NRB_DEVM static void run(const PassParams &P, double2 *sm, unsigned tile, int tid)
     {
@@ -450,13 +526,13 @@ struct StageRunner {
         constexpr bool last = (S == NST - 1);
         constexpr bool src_g = (S == 0) && SRC_G0;
         constexpr bool dst_g = last && DST_GL;
-        fft_stage<LOG2N, LAYOUT, DIR, VARIANT, S, src_g, dst_g>(P, sm, tile, tid);
+        fft_stage<LOG2N, LAYOUT, DIR, VARIANT, S, src_g, dst_g, SIMPLE>(P, sm, tile, tid);
         if (!dst_g) stage_sync<LOG2N, LAYOUT>();
-        StageRunner<LOG2N, LAYOUT, DIR, VARIANT, last ? -1 : S + 1, SRC_G0, DST_GL>::run(P, sm, tile, tid);
+        StageRunner<LOG2N, LAYOUT, DIR, VARIANT, last ? -1 : S + 1, SRC_G0, DST_GL, SIMPLE>::run(P, sm, tile, tid);
     }
 };
-template <int LOG2N, int LAYOUT, int DIR, int VARIANT, bool SRC_G0, bool DST_GL>
-struct StageRunner<LOG2N, LAYOUT, DIR, VARIANT, -1, SRC_G0, DST_GL> {
+template <int LOG2N, int LAYOUT, int DIR, int VARIANT, bool SRC_G0, bool DST_GL, bool SIMPLE>
+struct StageRunner<LOG2N, LAYOUT, DIR, VARIANT, -1, SRC_G0, DST_GL, SIMPLE> {
     NRB_DEVM static void run(const PassParams &, double2 *, unsigned, int) {}
 };
 
@@ -512,13 +588,13 @@ NRB_DEV void prefetch_tile(const PassParams &P, unsigned tile, int tid)
 }
 
 // ------------------------------------------------------------------ the pass body
-template <int LOG2N, int LAYOUT, int DIR, int VARIANT>
+template <int LOG2N, int LAYOUT, int DIR, int VARIANT, bool SIMPLE = false>
 NRB_DEV void fft_pass_body(const PassParams &P, double2 *sm, unsigned tile, int tid)
 {
     typedef Geo<LOG2N, LAYOUT, VARIANT> G;
 
     if (VARIANT == VAR_PLAIN) {
-        StageRunner<LOG2N, LAYOUT, DIR, VARIANT, 0, true, true>::run(P, sm, tile, tid);
+        StageRunner<LOG2N, LAYOUT, DIR, VARIANT, 0, true, true, SIMPLE>::run(P, sm, tile, tid);
         return;
     }
 

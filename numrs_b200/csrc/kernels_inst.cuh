@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include "aux_kernels.cuh"
+#include "fft_pass2.cuh"
 #include "plan.h"
 
 // resident CTAs per SM the register allocator targets for the 4096-point tiles
@@ -47,7 +48,12 @@ fft_pass_kernel(const __grid_constant__ PassParams P, const unsigned ntiles)
     for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         if (P.prefetch_dist > 0 && tile + (unsigned)P.prefetch_dist < ntiles)
             prefetch_tile<LOG2N, LAYOUT, VARIANT>(P, tile + (unsigned)P.prefetch_dist, (int)threadIdx.x);
-        fft_pass_body<LOG2N, LAYOUT, DIR, VARIANT>(P, nrb_smem, tile, (int)threadIdx.x);
+        if constexpr (VARIANT == VAR_PLAIN && simple_built(LOG2N, LAYOUT)) {
+            if (P.simple) fft_pass_body<LOG2N, LAYOUT, DIR, VARIANT, true>(P, nrb_smem, tile, (int)threadIdx.x);
+            else fft_pass_body<LOG2N, LAYOUT, DIR, VARIANT, false>(P, nrb_smem, tile, (int)threadIdx.x);
+        } else {
+            fft_pass_body<LOG2N, LAYOUT, DIR, VARIANT, false>(P, nrb_smem, tile, (int)threadIdx.x);
+        }
         __syncthreads();   // shared memory is reused by the next tile
     }
 }
@@ -192,6 +198,58 @@ template <int LOG2N, int LAYOUT> void register_size(PassTable &t)
         t.fn[LOG2N][LAYOUT_COL][0][VAR_PLAIN] = launch_pass_t<LOG2N, LAYOUT_COL, -1, VAR_PLAIN>;
         t.fn[LOG2N][LAYOUT_COL][1][VAR_XPOSE] = launch_pass_t<LOG2N, LAYOUT_COL, +1, VAR_XPOSE>;
         t.fn[LOG2N][LAYOUT_COL][0][VAR_XPOSE] = launch_pass_t<LOG2N, LAYOUT_COL, -1, VAR_XPOSE>;
+    }
+}
+
+// ---- big-tile passes (fft_pass2.cuh): persistent CTAs, one per resident slot ----
+PassTable &pass2_table();
+
+template <int LOG2N, int LAYOUT, int DIR, int VARIANT>
+__global__ void __launch_bounds__(Geo2<LOG2N, LAYOUT, VARIANT>::NT, (Geo2<LOG2N, LAYOUT, VARIANT>::TL > 12 ? 1 : 2))
+fft_pass2_kernel(const __grid_constant__ PassParams P, const unsigned ntiles)
+{
+    extern __shared__ double2 nrb_smem[];
+    fft_pass2_cta<LOG2N, LAYOUT, DIR, VARIANT>(P, nrb_smem, blockIdx.x, gridDim.x, ntiles, (int)threadIdx.x);
+}
+
+// `ntiles_v1` is ignored: the tile count follows from the lines of the pass and this kernel's own geometry
+template <int LOG2N, int LAYOUT, int DIR, int VARIANT>
+int launch_pass2_t(const PassParams &p, u64, cudaStream_t s)
+{
+    typedef Geo2<LOG2N, LAYOUT, VARIANT> G;
+    constexpr size_t smem = G::SMEM_BYTES;
+    auto kern = fft_pass2_kernel<LOG2N, LAYOUT, DIR, VARIANT>;
+    static int resident[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!resident[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        int per_sm = 0, sms = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, G::NT, smem);
+        if (e != cudaSuccess) return (int)e;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        resident[dev & 63] = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
+    }
+    const u64 lines = p.q_end - p.q_begin;
+    const u64 ntiles = (lines + G::L - 1) / G::L;
+    if (ntiles == 0) return 0;
+    if (ntiles > 0x7fffffffull) return (int)cudaErrorInvalidConfiguration;
+    const u64 grid = (NRB_V2_DIRECT || ntiles < (u64)resident[dev & 63]) ? ntiles : (u64)resident[dev & 63];
+    kern<<<(unsigned)grid, G::NT, smem, s>>>(p, (unsigned)ntiles);
+    return (int)cudaGetLastError();
+}
+
+template <int LOG2N, int LAYOUT> void register_size2(PassTable &t)
+{
+    if constexpr (LAYOUT == LAYOUT_ROW) {
+        t.fn[LOG2N][LAYOUT_ROW][1][VAR_PLAIN] = launch_pass2_t<LOG2N, LAYOUT_ROW, +1, VAR_PLAIN>;
+        t.fn[LOG2N][LAYOUT_ROW][0][VAR_PLAIN] = launch_pass2_t<LOG2N, LAYOUT_ROW, -1, VAR_PLAIN>;
+    } else {
+        t.fn[LOG2N][LAYOUT_COL][1][VAR_PLAIN] = launch_pass2_t<LOG2N, LAYOUT_COL, +1, VAR_PLAIN>;
+        t.fn[LOG2N][LAYOUT_COL][0][VAR_PLAIN] = launch_pass2_t<LOG2N, LAYOUT_COL, -1, VAR_PLAIN>;
+        t.fn[LOG2N][LAYOUT_COL][1][VAR_XPOSE] = launch_pass2_t<LOG2N, LAYOUT_COL, +1, VAR_XPOSE>;
+        t.fn[LOG2N][LAYOUT_COL][0][VAR_XPOSE] = launch_pass2_t<LOG2N, LAYOUT_COL, -1, VAR_XPOSE>;
     }
 }
 

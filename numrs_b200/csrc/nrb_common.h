@@ -96,6 +96,21 @@ NRB_HD constexpr int points_per_thread(int layout, int log2n)
                                         : (((NRB_PPT_COL16_MASK >> log2n) & 1) ? 16 : NRB_PPT_COL);
 }
 
+// line lengths (bit log2n) whose PLAIN pass is also built with the cheap addressing path (fft_stage, SIMPLE) and takes
+// it whenever the pass's element index is not split.  Measured on B200 (profiles/r01_simple_addr_ab.txt): +6 % on
+// contiguous lines of 8192, +2.4 ... +6.6 % on strided lines of 512, +3 % on 1024; neutral on contiguous 4096;
+// -3 % on strided lines of 64 / 128 (so those are left out).
+#ifndef NRB_SIMPLE_ROW_MASK
+#define NRB_SIMPLE_ROW_MASK (1 << 13)
+#endif
+#ifndef NRB_SIMPLE_COL_MASK
+#define NRB_SIMPLE_COL_MASK ((1 << 9) | (1 << 10))
+#endif
+NRB_HD constexpr bool simple_built(int log2n, int layout)
+{
+    return (((layout == 0 /* LAYOUT_ROW */ ? NRB_SIMPLE_ROW_MASK : NRB_SIMPLE_COL_MASK) >> log2n) & 1) != 0;
+}
+
 // ---- radix plan per log2(N): stage radices, first stage first ----
 constexpr int kMaxStages = 5;
 struct RadixPlan { int nst; int r[kMaxStages]; };
@@ -219,6 +234,8 @@ struct PassParams {
     int tw_on;              // multiply output k of line q by exp(-/+ 2 pi i q1 k / M)
     int tw_h;               // m = (hi << tw_h) | lo
     int real_mode;
+    int simple;             // set by the backend (pass_is_simple): no split element index, ROW element stride 1 -> the kernel
+                            // takes the cheap addressing path (fft_stage, SIMPLE)
 };
 
 // ---- two dependent passes fused into one persistent launch (rlft3 z + y through L2) ----

@@ -51,6 +51,9 @@ static Tunables &tunables_mut()
         x.xchg_grid_cap = env_int("NRB_XCHG_GRID_CAP", 0);
         x.prefetch_dist = env_int("NRB_PREFETCH_DIST", -1);
         x.conv_transposed = env_int("NRB_CONV_TRANSPOSED", 1);
+        x.simple_addr = env_int("NRB_SIMPLE_ADDR", 1);
+        x.big_row_mask = env_int("NRB_BIG_ROW_MASK", 0);
+        x.big_col_mask = env_int("NRB_BIG_COL_MASK", 0);
         return x;
     }();
     if (t.col_max_log2 < 1) t.col_max_log2 = 1;
@@ -77,6 +80,9 @@ int set_tunable(const char *name, long value)
     else if (n == "xchg_grid_cap") t.xchg_grid_cap = (int)value;
     else if (n == "prefetch_dist") t.prefetch_dist = (int)value;
     else if (n == "conv_transposed") t.conv_transposed = (int)value;
+    else if (n == "simple_addr") t.simple_addr = (int)value;
+    else if (n == "big_row_mask") t.big_row_mask = (int)value;
+    else if (n == "big_col_mask") t.big_col_mask = (int)value;
     else return -1;
     tunables_mut();   // re-clamp
     return 0;

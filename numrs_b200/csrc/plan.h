@@ -99,10 +99,28 @@ struct Tunables {
     int conv_transposed;   // convlv/correl with lines longer than a tile: two passes per transform and the spectrum in
                            // transposed order instead of three natural-order passes (NRB_CONV_TRANSPOSED, default 1)
     int prefetch_dist;     // tiles ahead whose input every CTA prefetches into L2 (NRB_PREFETCH_DIST; 0 = off, -1 = per-kernel policy, default)
+    int simple_addr;       // 1: passes whose element index is not split use the cheap addressing path (NRB_SIMPLE_ADDR, default 1)
+    int big_row_mask;      // bit log2n set: contiguous lines of 2^log2n points use the big-tile pass of fft_pass2.cuh (NRB_BIG_ROW_MASK)
+    int big_col_mask;      // the same for strided lines (NRB_BIG_COL_MASK)
     int xchg_grid_cap;     // pipelined slab exchange: CTAs of an exchange (peer-store) pass, 0 = one per tile (NRB_XCHG_GRID_CAP)
 };
 const Tunables &tunables();
 int set_tunable(const char *name, long value);   // returns 0 if the name is known
+// can the pass use the cheap addressing path of fft_stage (element offset = n * es, es = 1 for contiguous lines)?
+inline bool pass_is_simple(const KernelKey &key, const PassParams &p)
+{
+    if (!tunables().simple_addr || key.variant != VAR_PLAIN || p.out_peer_on || !simple_built(key.log2n, key.layout)) return false;
+    if (p.in_eshift <= kMaxLog2N || p.out_eshift <= kMaxLog2N) return false;   // the element index is split
+    if (key.layout == LAYOUT_ROW) return p.in_es == 1 && p.out_es == 1;
+    return true;
+}
+// does this launch go to the big-tile kernel (if the backend has one for the key)?
+inline bool use_big_tiles(const KernelKey &key, const PassParams &p)
+{
+    if (key.variant == VAR_REAL || p.out_peer_on || p.grid_cap > 0) return false;
+    const int mask = key.layout == LAYOUT_ROW ? tunables().big_row_mask : tunables().big_col_mask;
+    return ((mask >> key.log2n) & 1) != 0;
+}
 
 struct Plan {
     int kind;

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../numrs_b200/csrc/aux_kernels.cuh"
+#include "../../numrs_b200/csrc/fft_pass2.cuh"
 #include "../../numrs_b200/csrc/plan.h"
 
 namespace nrb_emu {
@@ -91,7 +92,11 @@ static void run_cta(Cta &c, int nthreads)
 template <int LOG2N, int LAYOUT, int DIR, int VARIANT>
 static void body_tpl(const void *p, double2 *sm, unsigned tile, int tid)
 {
-    nrb::fft_pass_body<LOG2N, LAYOUT, DIR, VARIANT>(*(const nrb::PassParams *)p, sm, tile, tid);
+    const nrb::PassParams &P = *(const nrb::PassParams *)p;
+    if constexpr (VARIANT == nrb::VAR_PLAIN && nrb::simple_built(LOG2N, LAYOUT)) {
+        if (P.simple) { nrb::fft_pass_body<LOG2N, LAYOUT, DIR, VARIANT, true>(P, sm, tile, tid); return; }
+    }
+    nrb::fft_pass_body<LOG2N, LAYOUT, DIR, VARIANT, false>(P, sm, tile, tid);
 }
 
 typedef void (*BodyFn)(const void *, double2 *, unsigned, int);
@@ -115,6 +120,24 @@ template <int LOG2N, int LAYOUT> static void reg()
     }
 }
 
+// big-tile passes (fft_pass2.cuh): one emulated CTA runs the whole persistent loop first, first + stride, ...
+struct BigParams { nrb::PassParams p; unsigned stride, ntiles; };
+template <int LOG2N, int LAYOUT, int DIR, int VARIANT>
+static void body2_tpl(const void *p, double2 *sm, unsigned first, int tid)
+{
+    const BigParams *b = (const BigParams *)p;
+    nrb::fft_pass2_cta<LOG2N, LAYOUT, DIR, VARIANT>(b->p, sm, first, b->stride, b->ntiles, tid);
+}
+struct Entry2 { BodyFn fn; int nthreads; size_t smem; int lines; };
+static Entry2 g_table2[nrb::kMaxLog2N + 1][2][2][3];
+template <int LOG2N, int LAYOUT, int VARIANT> static void reg2()
+{
+    typedef nrb::Geo2<LOG2N, LAYOUT, VARIANT> G;
+    const size_t smem = (G::SMEM_BYTES + 15) / 16;
+    g_table2[LOG2N][LAYOUT][1][VARIANT] = Entry2{body2_tpl<LOG2N, LAYOUT, 1, VARIANT>, G::NT, smem, G::L};
+    g_table2[LOG2N][LAYOUT][0][VARIANT] = Entry2{body2_tpl<LOG2N, LAYOUT, -1, VARIANT>, G::NT, smem, G::L};
+}
+
 static void init_table()
 {
     static bool done = false;
@@ -125,6 +148,9 @@ static void init_table()
     reg<8, 0>(); reg<9, 0>(); reg<10, 0>(); reg<11, 0>(); reg<12, 0>(); reg<13, 0>();
     reg<1, 1>(); reg<2, 1>(); reg<3, 1>(); reg<4, 1>(); reg<5, 1>(); reg<6, 1>(); reg<7, 1>();
     reg<8, 1>(); reg<9, 1>(); reg<10, 1>(); reg<11, 1>(); reg<12, 1>();
+    // same set as the CUDA build (k_big.cu)
+    reg2<11, 0, VAR_PLAIN>(); reg2<12, 0, VAR_PLAIN>(); reg2<13, 0, VAR_PLAIN>();
+    reg2<9, 1, VAR_PLAIN>(); reg2<10, 1, VAR_PLAIN>(); reg2<9, 1, VAR_XPOSE>(); reg2<10, 1, VAR_XPOSE>();
 }
 
 } // namespace nrb_emu
@@ -134,13 +160,42 @@ namespace nrb {
 static thread_local std::string g_emu_err;
 const char *be_last_error() { return g_emu_err.c_str(); }
 
-static long g_pass_launches = 0, g_aux_launches = 0;
+static long g_pass_launches = 0, g_aux_launches = 0, g_big_launches = 0;
 
-int be_launch_pass(const KernelKey &key, const PassParams &p, u64 ntiles, void *)
+static long g_simple_launches = 0;
+int be_launch_pass(const KernelKey &key, const PassParams &p_in, u64 ntiles, void *)
 {
+    PassParams p = p_in;
+    p.simple = pass_is_simple(key, p_in) ? 1 : 0;
+    if (p.simple) ++g_simple_launches;
     nrb_emu::init_table();
     if (key.log2n < 1 || key.log2n > kMaxLog2N) { g_emu_err = "no such kernel"; return -1; }
     const nrb_emu::Entry e = nrb_emu::g_table[key.log2n][key.layout][key.dir > 0 ? 1 : 0][key.variant];
+    if (use_big_tiles(key, p) && nrb_emu::g_table2[key.log2n][key.layout][key.dir > 0 ? 1 : 0][key.variant].fn) {
+        const nrb_emu::Entry2 e2 = nrb_emu::g_table2[key.log2n][key.layout][key.dir > 0 ? 1 : 0][key.variant];
+        const u64 lines = p.q_end - p.q_begin;
+        nrb_emu::BigParams bp;
+        bp.p = p;
+        bp.ntiles = (unsigned)((lines + e2.lines - 1) / e2.lines);
+        bp.stride = 3;      // a "grid" of 3 persistent CTAs: every CTA walks several tiles when there are more than 3
+        ++g_pass_launches;
+        ++g_big_launches;
+#pragma omp parallel for schedule(dynamic)
+        for (int first = 0; first < (int)bp.stride; ++first) {
+            nrb_emu::Cta c;
+            c.fibers.resize(e2.nthreads);
+            c.stacks.resize((size_t)e2.nthreads * nrb_emu::kStack);
+            c.done.resize(e2.nthreads);
+            c.smem.assign(e2.smem, make_double2(__builtin_nan(""), __builtin_nan("")));
+            std::vector<double> shfl_buf(e2.nthreads + 32, 0.0);
+            nrb_emu::t_shfl = &shfl_buf;
+            c.body = e2.fn;
+            c.params = &bp;
+            c.tile = (unsigned)first;
+            nrb_emu::run_cta(c, e2.nthreads);
+        }
+        return 0;
+    }
     if (!e.fn) { g_emu_err = "kernel variant not built"; return -1; }
     ++g_pass_launches;
 #pragma omp parallel
@@ -247,4 +302,4 @@ void be_host_free(void *p) { free(p); }
 
 } // namespace nrb
 
-extern "C" long nrb_emu_launch_count(int aux) { return aux ? nrb::g_aux_launches : nrb::g_pass_launches; }
+extern "C" long nrb_emu_launch_count(int aux) { return aux == 3 ? nrb::g_simple_launches : aux == 2 ? nrb::g_big_launches : aux ? nrb::g_aux_launches : nrb::g_pass_launches; }

@@ -453,3 +453,77 @@ def test_convlv_default_plan_uses_two_passes_per_transform(emu):
     plan = emu.plan_create(nb.KIND_CORREL, [1 << 15], batch=1)
     assert plan.num_launches(1) == 7          # 2^14 complex = 2 natural-order passes as well
     plan.destroy()
+
+
+# ---- addressing fast path (fft_stage SIMPLE) and the big-tile pass (fft_pass2.cuh) ----
+def _emu_count(emu, which):
+    import ctypes
+    emu.L.nrb_emu_launch_count.restype = ctypes.c_long
+    return emu.L.nrb_emu_launch_count(which)
+
+
+def _ab_equal(emu, run, option, a, b):
+    """The same call under two settings of an option must give bit-identical results (same arithmetic, other addressing)."""
+    emu.set_option(option, a)
+    ra = run()
+    emu.set_option(option, b)
+    rb = run()
+    assert np.array_equal(ra, rb)
+
+
+@pytest.mark.parametrize("shape", [(8192,), (4, 8192), (512, 8), (1024, 32), (2, 512, 16), (1024, 8, 2)])
+def test_simple_addressing_path_is_taken_and_bit_identical(emu, shape):
+    n = int(np.prod(shape))
+    x = cases.gen(77, 2 * n)
+
+    def run():
+        y = x.copy()
+        nb.fourn(y, list(shape), len(shape), 1, emu)
+        return y
+
+    before = _emu_count(emu, 3)
+    _ab_equal(emu, run, "simple_addr", 1, 0)
+    assert _emu_count(emu, 3) > before          # the lengths built with the fast path (8192 contiguous, 512 / 1024 strided)
+    cases.check_fourn(emu, shape)
+
+
+def test_simple_addressing_with_four_step_twiddle_and_ragged_tiles(emu):
+    # strided 2^18-point axis = 512 x 512: the first pass is a PLAIN strided pass with the four-step twiddle and a
+    # transposed store (tw_on), 4 lines -> a ragged tile (4 of 8 lines exist)
+    emu.set_option("col_max_log2", 9)
+    before = _emu_count(emu, 3)
+    cases.check_fourn(emu, (1 << 18, 4))
+    assert _emu_count(emu, 3) > before
+    x = cases.gen(78, 2 * (1 << 18) * 4)
+
+    def run():
+        y = x.copy()
+        nb.fourn(y, [1 << 18, 4], 2, -1, emu)
+        return y
+
+    _ab_equal(emu, run, "simple_addr", 1, 0)
+
+
+@pytest.mark.parametrize("nn,count", [(8192, 7), (4096, 9), (2048, 11)])
+def test_big_tile_pass_contiguous_lines(emu, nn, count):
+    emu.set_option("big_row_mask", (1 << 11) | (1 << 12) | (1 << 13))
+    before = _emu_count(emu, 2)
+    cases.check_four1_batch(emu, nn, count)          # more tiles than emulated persistent CTAs, ragged last tile
+    cases.check_four1(emu, nn)
+    assert _emu_count(emu, 2) > before
+
+
+@pytest.mark.parametrize("shape", [(512, 16), (1024, 8), (2, 512, 8), (1024, 64)])
+def test_big_tile_pass_strided_lines(emu, shape):
+    emu.set_option("big_col_mask", (1 << 9) | (1 << 10))
+    before = _emu_count(emu, 2)
+    cases.check_fourn(emu, shape)
+    assert _emu_count(emu, 2) > before
+
+
+def test_big_tile_pass_transposing_four_step(emu):
+    emu.set_option("big_col_mask", (1 << 9) | (1 << 10))
+    before = _emu_count(emu, 2)
+    cases.check_four1(emu, 1 << 20)                  # XPOSE 1024 + strided 1024
+    cases.check_four1(emu, 1 << 19)                  # XPOSE 1024 + strided 512
+    assert _emu_count(emu, 2) - before >= 16

@@ -350,3 +350,33 @@ def test_host_calls_are_thread_safe(gpu):
     for t in ts:
         t.join()
     assert not errs, errs
+
+
+# ---- addressing fast path (on by default for contiguous 8192 / strided 512, 1024) and the big-tile pass (option) ----
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(4, 8192), (512, 32), (1024, 8, 2), (8192, 512)])
+def test_simple_addressing_bit_identical_to_general_path(gpu, shape):
+    n = int(np.prod(shape))
+    x = cases.gen(77, 2 * n)
+    out = []
+    for flag in (1, 0):
+        gpu.set_option("simple_addr", flag)
+        y = x.copy()
+        nb.fourn(y, list(shape), len(shape), 1, gpu)
+        out.append(y)
+    assert np.array_equal(out[0], out[1])
+    gpu.set_option("simple_addr", 1)
+    if n <= (1 << 18):
+        cases.check_fourn(gpu, shape)
+
+
+@pytest.mark.gpu
+def test_big_tile_passes(gpu):
+    gpu.set_option("big_row_mask", (1 << 11) | (1 << 12) | (1 << 13))
+    gpu.set_option("big_col_mask", (1 << 9) | (1 << 10))
+    cases.check_four1_batch(gpu, 8192, 301)          # more tiles than persistent CTAs (148), ragged
+    cases.check_four1_batch(gpu, 4096, 700)
+    cases.check_four1_batch(gpu, 2048, 1500)
+    cases.check_fourn(gpu, (1024, 64))
+    cases.check_fourn(gpu, (2, 512, 8))
+    cases.check_four1(gpu, 1 << 20)
