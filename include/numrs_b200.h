@@ -116,6 +116,10 @@ int nrb_autocorrel_fast(const double *data, size_t n, double *ans);
 /* FFT_2.rs:3 twofft(data1, data2, fft1, fft2): spectra of two real signals from one complex four1(+1);
  * fft1 / fft2 have 2n + 2 doubles (FFT_2.rs:6-7): n complex bins followed by two zero doubles. */
 int nrb_twofft(const double *data1, const double *data2, size_t n, double *fft1, double *fft2);
+/* FFT_2.rs:258 TwoFFTProcessor::process_batch: `count` independent signal pairs of the same length n in one batched
+ * plan (the reference loops over the tuples and calls twofft on each); fft1[b] / fft2[b] have 2n + 2 doubles. */
+int nrb_twofft_batch(const double *const *data1, const double *const *data2, size_t count, size_t n,
+                     double *const *fft1, double *const *fft2);
 /* FFT_1.rs:218 power_spectrum (take_sqrt = 0) / :206 magnitude_spectrum (take_sqrt = 1) of npoints complex points */
 int nrb_power_spectrum(const double *complex_data, size_t npoints, int take_sqrt, double *out);
 

@@ -144,6 +144,62 @@ def twofft(data1, data2, fft1, fft2, _L=None):
     _panic(L, L.twofft(data1, data2, fft1, fft2))
 
 
+def twofft_optimized(data1, data2, fft1, fft2, _L=None):
+    """FFT_2.rs:135: same contract as `twofft`."""
+    twofft(data1, data2, fft1, fft2, _L)
+
+
+class TwoFFTProcessor:
+    """FFT_2.rs:222-265.  `use_optimized` / `parallel_threshold` select between CPU code paths in the reference;
+    they are kept and ignored (one device path)."""
+
+    def __init__(self, _L=None):
+        self.use_optimized = True          # FFT_2.rs:230
+        self.parallel_threshold = 1024     # FFT_2.rs:231
+        self._L = _L
+
+    def with_optimized(self, use_optimized):
+        self.use_optimized = bool(use_optimized)
+        return self
+
+    def with_threshold(self, threshold):
+        self.parallel_threshold = int(threshold)
+        return self
+
+    def process(self, data1, data2, fft1, fft2):
+        twofft(data1, data2, fft1, fft2, self._L)
+
+    def process_batch(self, batches):
+        """FFT_2.rs:258 `process_batch(&[(data1, data2, fft1, fft2)])`: tuples of equal length share one batched
+        device plan (the reference loops over them)."""
+        L = self._L or lib()
+        groups = {}
+        for d1, d2, f1, f2 in batches:
+            n = d1.size
+            assert d2.size == n, "data2 length must equal data1 length"             # FFT_2.rs:5
+            assert f1.size == 2 * n + 2, "fft1 must have length 2*n + 2"            # FFT_2.rs:6
+            assert f2.size == 2 * n + 2, "fft2 must have length 2*n + 2"            # FFT_2.rs:7
+            groups.setdefault(n, []).append((d1, d2, f1, f2))
+        for n, items in groups.items():
+            _panic(L, L.twofft_batch([i[0] for i in items], [i[1] for i in items], [i[2] for i in items], [i[3] for i in items]))
+
+
+def extract_real_imag(fft):                 # FFT_2.rs:361-372
+    fft = np.asarray(fft, dtype=np.float64)
+    n = fft.size // 2
+    return fft[0:2 * n:2].copy(), fft[1:2 * n:2].copy()
+
+
+def combine_real_imag(real, imag):          # FFT_2.rs:375-385
+    real = np.asarray(real, dtype=np.float64)
+    imag = np.asarray(imag, dtype=np.float64)
+    assert real.size == imag.size, "Real and imaginary parts must have same length"
+    out = np.empty(2 * real.size, dtype=np.float64)
+    out[0::2] = real
+    out[1::2] = imag
+    return out
+
+
 # ---------------------------------------------------------------- Cos_FT.rs / Cos_FT2.rs / sinft
 def cosft1(y, n, _L=None):
     """Cos_FT.rs:7 `cosft1(y: &mut [f64], n)`: 1-based array, y[0] unused, data y[1..=n+1]; NR semantics."""
@@ -152,11 +208,21 @@ def cosft1(y, n, _L=None):
     _panic(L, L.cosft1(y, n))
 
 
+def cosft1_optimized(y, n, _L=None):
+    """Cos_FT.rs:78: same contract as `cosft1`."""
+    cosft1(y, n, _L)
+
+
 def cosft2(y, n, isign, _L=None):
     """Cos_FT2.rs:7 `cosft2(y, n, isign)`: 1-based array, data y[1..=n]; panics on isign not in {1, -1}."""
     assert y.size >= n + 1, "y must hold n + 1 elements"
     L = _L or lib()
     _panic(L, L.cosft2(y, n, isign))
+
+
+def cosft2_simd(y, n, isign, _L=None):
+    """Cos_FT2.rs:202: same contract as `cosft2`."""
+    cosft2(y, n, isign, _L)
 
 
 def sinft(y, n, _L=None):

@@ -39,7 +39,7 @@ ABI_SYMBOLS = [
     "nrb_set_option", "nrb_host_alloc", "nrb_host_free",
     "nrb_four1", "nrb_four1_batch", "nrb_fourn", "nrb_realft", "nrb_realft_batch", "nrb_rlft3",
     "nrb_convlv", "nrb_convlv_batch", "nrb_correl", "nrb_correl_batch",
-    "nrb_correl_normalized", "nrb_autocorrel_fast", "nrb_twofft", "nrb_power_spectrum",
+    "nrb_correl_normalized", "nrb_autocorrel_fast", "nrb_twofft", "nrb_twofft_batch", "nrb_power_spectrum",
     "nrb_cosft1", "nrb_cosft2", "nrb_sinft",
     "nrb_plan_create", "nrb_plan_workspace_bytes", "nrb_plan_num_launches", "nrb_plan_exec", "nrb_plan_destroy",
     "nrb_plan_profile", "nrb_plan_describe_launch", "nrb_fill_uniform_device",
@@ -96,6 +96,7 @@ class Library:
         L.nrb_correl_normalized.argtypes = [_dp, _sz, _dp, _sz, ctypes.c_int, _dp]
         L.nrb_autocorrel_fast.argtypes = [_dp, _sz, _dp]
         L.nrb_twofft.argtypes = [_dp, _dp, _sz, _dp, _dp]
+        L.nrb_twofft_batch.argtypes = [ctypes.POINTER(_dp), ctypes.POINTER(_dp), _sz, _sz, ctypes.POINTER(_dp), ctypes.POINTER(_dp)]
         L.nrb_power_spectrum.argtypes = [_dp, _sz, ctypes.c_int, _dp]
         L.nrb_cosft1.argtypes = [_dp, _sz]
         L.nrb_cosft2.argtypes = [_dp, _sz, ctypes.c_int]
@@ -258,6 +259,12 @@ class Library:
 
     def twofft(self, d1, d2, fft1, fft2):
         return self.L.nrb_twofft(_f64(d1), _f64(d2), d1.size, _f64(fft1), _f64(fft2))
+
+    def twofft_batch(self, d1_list, d2_list, fft1_list, fft2_list):
+        cnt = len(d1_list)
+        n = d1_list[0].size if cnt else 1
+        arr = lambda xs: (_dp * max(cnt, 1))(*[_f64(x) for x in xs])   # noqa: E731
+        return self.L.nrb_twofft_batch(arr(d1_list), arr(d2_list), cnt, n, arr(fft1_list), arr(fft2_list))
 
     def power_spectrum(self, c, take_sqrt=False):
         c = np.ascontiguousarray(c, dtype=np.float64)

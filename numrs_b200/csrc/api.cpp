@@ -5,6 +5,9 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <new>
+#include <set>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -48,12 +51,33 @@ struct DevBuf {
     void release() { if (p) be_free(p); p = nullptr; cap = 0; }
 };
 
+// Every thread that makes host-slice calls owns a stream and three staging buffers.  The contexts are registered so
+// that nrb_shutdown can release the device memory of ALL threads, and a thread that exits releases its own.
+struct ThreadCtx;
+std::mutex g_ctx_mu;
+std::set<ThreadCtx *> g_ctxs;
+
 struct ThreadCtx {
     void *stream;
     int device;
     DevBuf io, aux, out;
-    ThreadCtx() : stream(nullptr), device(-1) {}
-    ~ThreadCtx() {}   // device memory is reclaimed by nrb_shutdown / process exit
+    ThreadCtx() : stream(nullptr), device(-1)
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        g_ctxs.insert(this);
+    }
+    void release()
+    {
+        io.release(); aux.release(); out.release();
+        if (stream) { be_stream_destroy(stream); stream = nullptr; }
+        device = -1;
+    }
+    ~ThreadCtx()
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        release();
+        g_ctxs.erase(this);
+    }
 };
 thread_local ThreadCtx t_ctx;
 
@@ -62,16 +86,30 @@ std::map<std::string, std::shared_ptr<nrb_plan_s>> g_plan_cache;
 
 int fail(int code, const std::string &msg) { set_error(msg); return code; }
 
+// No C++ exception may cross the C ABI (the callers are Rust / C / ctypes): every entry point that can allocate is a
+// function-try-block ending in this handler.
+int on_exception() noexcept
+{
+    try { throw; }
+    catch (const std::bad_alloc &) {
+        try { set_error("out of host memory"); } catch (...) {}
+        return NRB_ERR_OOM;
+    }
+    catch (const std::exception &e) {
+        try { set_error(std::string("internal error: ") + e.what()); } catch (...) {}
+        return NRB_ERR_CUDA;
+    }
+    catch (...) {
+        return NRB_ERR_CUDA;
+    }
+}
+
 int ensure_ctx()
 {
     if (be_device_count() <= 0) return fail(NRB_ERR_CUDA, "no CUDA device available (numrs_b200 has no CPU fallback)");
     const int dev = be_current_device();
     if (dev < 0) return fail(NRB_ERR_CUDA, std::string("cannot query CUDA device: ") + be_last_error());
-    if (t_ctx.stream && t_ctx.device != dev) {   // thread moved to another device
-        be_stream_destroy(t_ctx.stream);
-        t_ctx.stream = nullptr;
-        t_ctx.io.release(); t_ctx.aux.release(); t_ctx.out.release();
-    }
+    if (t_ctx.stream && t_ctx.device != dev) t_ctx.release();   // thread moved to another device
     if (!t_ctx.stream) {
         if (be_stream_create(&t_ctx.stream) != 0) return fail(NRB_ERR_CUDA, std::string("stream creation failed: ") + be_last_error());
         t_ctx.device = dev;
@@ -206,46 +244,52 @@ const char *nrb_version(void) { return "numrs_b200 0.1.0 (sm_100a)"; }
 const char *nrb_last_error(void) { return get_error().c_str(); }
 int nrb_device_count(void) { return be_device_count(); }
 int nrb_set_device(int device)
-{
+try {
     if (be_set_device(device) != 0) return fail(NRB_ERR_CUDA, std::string("cudaSetDevice failed: ") + be_last_error());
     return NRB_OK;
-}
+} catch (...) { return on_exception(); }
 int nrb_shutdown(void)
 {
-    std::lock_guard<std::mutex> lk(g_cache_mu);
-    g_plan_cache.clear();
-    t_ctx.io.release(); t_ctx.aux.release(); t_ctx.out.release();
-    if (t_ctx.stream) { be_stream_destroy(t_ctx.stream); t_ctx.stream = nullptr; }
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        g_plan_cache.clear();
+    }
+    {
+        // staging buffers and streams of every thread that ever made a host-slice call (the caller guarantees that no
+        // other nrb_* call is in flight, as for any shutdown function)
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        for (ThreadCtx *c : g_ctxs) c->release();
+    }
     release_tables();
     return NRB_OK;
 }
 int nrb_set_option(const char *name, long value)
-{
+try {
     if (set_tunable(name, value) != 0) return fail(NRB_ERR_INVALID_DIMS, "unknown option");
     std::lock_guard<std::mutex> lk(g_cache_mu);
     g_plan_cache.clear();
     return NRB_OK;
-}
+} catch (...) { return on_exception(); }
 void *nrb_host_alloc(size_t bytes) { return be_host_alloc(bytes); }
 void nrb_host_free(void *p) { if (p) be_host_free(p); }
 
 // ------------------------------------------------------------------ plan API
 int nrb_plan_create(int kind, const size_t *dims, size_t ndim, size_t batch, nrb_plan_t *plan)
-{
+try {
     if (!plan) return fail(NRB_ERR_INVALID_DIMS, "plan pointer is NULL");
     *plan = nullptr;
     if (be_device_count() <= 0) return fail(NRB_ERR_CUDA, "no CUDA device available (numrs_b200 has no CPU fallback)");
-    nrb_plan_s *h = new nrb_plan_s();
+    std::unique_ptr<nrb_plan_s> h(new nrb_plan_s());
     const int rc = build_plan(h->plan, kind, dims, ndim, batch);
-    if (rc != NRB_OK) { delete h; return rc; }
-    *plan = h;
+    if (rc != NRB_OK) return rc;
+    *plan = h.release();
     return NRB_OK;
-}
+} catch (...) { return on_exception(); }
 size_t nrb_plan_workspace_bytes(nrb_plan_t plan) { return plan ? plan->plan.ws_elems * sizeof(double2) : 0; }
 int nrb_plan_num_launches(nrb_plan_t plan, int isign)
-{
+try {
     return plan ? (int)plan->plan.prog[isign == 1 ? 0 : 1].steps.size() : 0;
-}
+} catch (...) { return on_exception(); }
 int nrb_plan_exec(nrb_plan_t plan, double *d_io, double *d_aux, double *d_out, int isign, int arg, void *stream)
 {
     if (!plan) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
@@ -253,20 +297,20 @@ int nrb_plan_exec(nrb_plan_t plan, double *d_io, double *d_aux, double *d_out, i
 }
 int nrb_plan_profile(nrb_plan_t plan, double *d_io, double *d_aux, double *d_out, int isign, int arg, void *stream,
                      float *ms, int cap)
-{
+try {
     if (!plan || !ms) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
     return profile_plan(plan->plan, d_io, d_aux, d_out, isign, arg, stream, ms, cap);
-}
+} catch (...) { return on_exception(); }
 int nrb_plan_describe_launch(nrb_plan_t plan, int isign, int idx, char *name, size_t cap, double *bytes)
 {
     if (!plan) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
     return describe_launch(plan->plan, isign, idx, name, cap, bytes);
 }
 int nrb_fill_uniform_device(double *d_out, unsigned long long seed, unsigned long long offset, size_t count, void *stream)
-{
+try {
     if (be_device_count() <= 0) return fail(NRB_ERR_CUDA, "no CUDA device available (numrs_b200 has no CPU fallback)");
     return fill_uniform_device(d_out, seed, offset, count, stream);
-}
+} catch (...) { return on_exception(); }
 int nrb_upload(void *d_dst, const void *h_src, size_t bytes, void *stream)
 {
     if (be_device_count() <= 0) return fail(NRB_ERR_CUDA, "no CUDA device available (numrs_b200 has no CPU fallback)");
@@ -275,12 +319,12 @@ int nrb_upload(void *d_dst, const void *h_src, size_t bytes, void *stream)
     return NRB_OK;
 }
 int nrb_download(void *h_dst, const void *d_src, size_t bytes, void *stream)
-{
+try {
     if (be_device_count() <= 0) return fail(NRB_ERR_CUDA, "no CUDA device available (numrs_b200 has no CPU fallback)");
     if (bytes && (!h_dst || !d_src)) return fail(NRB_ERR_EMPTY_INPUT, "null pointer");
     if (bytes && be_d2h(h_dst, d_src, bytes, stream) != 0) return copy_fail("device-to-host copy");
     return NRB_OK;
-}
+} catch (...) { return on_exception(); }
 int nrb_stream_synchronize(void *stream)
 {
     if (be_device_count() <= 0) return fail(NRB_ERR_CUDA, "no CUDA device available (numrs_b200 has no CPU fallback)");
@@ -288,12 +332,12 @@ int nrb_stream_synchronize(void *stream)
     return NRB_OK;
 }
 int nrb_complex_multiply_device(double *d_a, const double *d_b, size_t ncomplex, int conj_b, double scale, void *stream)
-{
+try {
     if (be_device_count() <= 0) return fail(NRB_ERR_CUDA, "no CUDA device available (numrs_b200 has no CPU fallback)");
     if (ncomplex == 0) return NRB_OK;
     if (!d_a || !d_b) return fail(NRB_ERR_EMPTY_INPUT, "null pointer");
     return complex_multiply_device(d_a, d_b, ncomplex, conj_b, scale, stream);
-}
+} catch (...) { return on_exception(); }
 int nrb_plan_destroy(nrb_plan_t plan)
 {
     delete plan;
@@ -302,16 +346,16 @@ int nrb_plan_destroy(nrb_plan_t plan)
 
 // ------------------------------------------------------------------ slab API
 int nrb_slab_create(size_t nn1, size_t nn2, size_t nn3, int nranks, int rank, nrb_slab_t *plan)
-{
+try {
     if (!plan) return fail(NRB_ERR_INVALID_DIMS, "plan pointer is NULL");
     *plan = nullptr;
     if (be_device_count() <= 0) return fail(NRB_ERR_CUDA, "no CUDA device available (numrs_b200 has no CPU fallback)");
-    nrb_slab_s *h = new nrb_slab_s();
+    std::unique_ptr<nrb_slab_s> h(new nrb_slab_s());
     const int rc = build_slab_plan(h->plan, nn1, nn2, nn3, nranks, rank);
-    if (rc != NRB_OK) { delete h; return rc; }
-    *plan = h;
+    if (rc != NRB_OK) return rc;
+    *plan = h.release();
     return NRB_OK;
-}
+} catch (...) { return on_exception(); }
 size_t nrb_slab_local_doubles(nrb_slab_t p) { return p ? p->plan.nn1 * p->plan.nn2 * p->plan.nn3 / (size_t)p->plan.nranks : 0; }
 size_t nrb_slab_speq_doubles(nrb_slab_t p) { return p ? 2 * p->plan.nn1 * p->plan.nn2 / (size_t)p->plan.nranks : 0; }
 size_t nrb_slab_xchg_doubles(nrb_slab_t p)
@@ -322,47 +366,47 @@ size_t nrb_slab_xchg_doubles(nrb_slab_t p)
 }
 int nrb_slab_stage(nrb_slab_t p, int stage, int isign, double *d_slab, double *d_speq, double *d_send, double *d_recv,
                    void *stream)
-{
+try {
     if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
     return exec_slab_stage(p->plan, stage, isign, d_slab, d_speq, d_send, d_recv, stream);
-}
+} catch (...) { return on_exception(); }
 int nrb_slab_set_peers(nrb_slab_t p, void *const *peer_recv, int count)
 {
     if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
     return slab_set_peers(p->plan, peer_recv, count);
 }
 int nrb_slab_barrier(nrb_slab_t p, int phase, unsigned long long epoch, void *stream)
-{
+try {
     if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
     return slab_barrier(p->plan, phase, epoch, stream);
-}
+} catch (...) { return on_exception(); }
 size_t nrb_slab_recv_bytes(nrb_slab_t p) { return p ? nrb_slab_xchg_doubles(p) * sizeof(double) + 8 * 8 * kSlabMaxChunks : 0; }
 int nrb_slab_set_chunks(nrb_slab_t p, int chunks)
-{
+try {
     if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
     if (chunks > kSlabMaxChunks) return fail(NRB_ERR_INVALID_DIMS, "slab: at most 16 chunks");
     return slab_set_chunks(p->plan, chunks);
-}
+} catch (...) { return on_exception(); }
 int nrb_slab_stage_part(nrb_slab_t p, int stage, int part, int isign, double *d_slab, double *d_speq, void *stream)
 {
     if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
     return exec_slab_part(p->plan, stage, part, isign, d_slab, d_speq, stream);
 }
 int nrb_slab_set_dma(nrb_slab_t p, int chunks)
-{
+try {
     if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
     return slab_set_dma(p->plan, chunks);
-}
+} catch (...) { return on_exception(); }
 int nrb_slab_stage_part_xchg(nrb_slab_t p, int stage, int part, int isign, double *d_slab, double *d_speq, double *d_xchg, void *stream)
 {
     if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
     return exec_slab_part(p->plan, stage, part, isign, d_slab, d_speq, stream, d_xchg);
 }
 int nrb_slab_exec_dma(nrb_slab_t p, int isign, double *d_slab, double *d_speq, unsigned long long epoch, void *stream)
-{
+try {
     if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
     return exec_slab_dma(p->plan, isign, d_slab, d_speq, epoch, stream);
-}
+} catch (...) { return on_exception(); }
 int nrb_slab_dma_timeline(nrb_slab_t p, int enable, char *text, size_t cap)
 {
     if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
@@ -375,10 +419,10 @@ int nrb_slab_dma_timeline(nrb_slab_t p, int enable, char *text, size_t cap)
     return NRB_OK;
 }
 int nrb_slab_barrier_chunk(nrb_slab_t p, int phase, int chunk, unsigned long long epoch, void *stream)
-{
+try {
     if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
     return slab_barrier_chunk(p->plan, phase, chunk, epoch, stream);
-}
+} catch (...) { return on_exception(); }
 int nrb_device_alloc(size_t bytes, void **dptr)
 {
     if (!dptr) return fail(NRB_ERR_INVALID_DIMS, "null pointer");
@@ -389,20 +433,20 @@ int nrb_device_alloc(size_t bytes, void **dptr)
 }
 int nrb_device_free(void *dptr) { if (dptr) be_free(dptr); return NRB_OK; }
 int nrb_ipc_export(void *dptr, unsigned char handle[64])
-{
+try {
     if (be_ipc_export(dptr, handle) != 0) return fail(NRB_ERR_CUDA, std::string("cudaIpcGetMemHandle failed: ") + be_last_error());
     return NRB_OK;
-}
+} catch (...) { return on_exception(); }
 int nrb_ipc_import(const unsigned char handle[64], void **dptr)
 {
     if (be_ipc_import(handle, dptr) != 0) return fail(NRB_ERR_CUDA, std::string("cudaIpcOpenMemHandle failed: ") + be_last_error());
     return NRB_OK;
 }
 int nrb_ipc_release(void *dptr)
-{
+try {
     if (be_ipc_release(dptr) != 0) return fail(NRB_ERR_CUDA, std::string("cudaIpcCloseMemHandle failed: ") + be_last_error());
     return NRB_OK;
-}
+} catch (...) { return on_exception(); }
 int nrb_slab_destroy(nrb_slab_t p)
 {
     delete p;
@@ -411,14 +455,14 @@ int nrb_slab_destroy(nrb_slab_t p)
 
 // ------------------------------------------------------------------ host-slice entry points
 int nrb_four1(double *data, size_t nn, int isign)
-{
+try {
     double *ptrs[1] = {data};
     size_t sizes[1] = {nn};
     return nrb_four1_batch(ptrs, sizes, 1, isign);
-}
+} catch (...) { return on_exception(); }
 
 int nrb_four1_batch(double *const *ptrs, const size_t *nn, size_t count, int isign)
-{
+try {
     if (isign != 1 && isign != -1) return fail(NRB_ERR_INVALID_ISIGN, "isign must be 1 or -1");
     if (count == 0) return NRB_OK;
     if (!ptrs || !nn) return fail(NRB_ERR_EMPTY_INPUT, "null batch");
@@ -437,10 +481,10 @@ int nrb_four1_batch(double *const *ptrs, const size_t *nn, size_t count, int isi
         if (rc) return rc;
     }
     return NRB_OK;
-}
+} catch (...) { return on_exception(); }
 
 int nrb_fourn(double *data, const size_t *nn, size_t ndim, int isign)
-{
+try {
     // Fourn.rs:367-378 validation order
     if (ndim == 0 || !nn) return fail(NRB_ERR_INVALID_DIMS, "Invalid dimensions");
     if (isign != 1 && isign != -1) return fail(NRB_ERR_INVALID_ISIGN, "isign must be 1 or -1");
@@ -452,16 +496,16 @@ int nrb_fourn(double *data, const size_t *nn, size_t ndim, int isign)
     if (!data) return fail(NRB_ERR_EMPTY_INPUT, "null data");
     double *ptrs[1] = {data};
     return run_inplace(NRB_KIND_FOURN, nn, ndim, ptrs, 1, 2 * total, isign, nullptr, 0);
-}
+} catch (...) { return on_exception(); }
 
 int nrb_realft(double *data, size_t n, int isign)
-{
+try {
     double *ptrs[1] = {data};
     return nrb_realft_batch(ptrs, n, 1, isign);
-}
+} catch (...) { return on_exception(); }
 
 int nrb_realft_batch(double *const *ptrs, size_t n, size_t count, int isign)
-{
+try {
     if (n % 2 != 0) return fail(NRB_ERR_INVALID_DIMS, "n must be even");          // Real_FT.rs:5
     if (n == 0) return fail(NRB_ERR_EMPTY_INPUT, "data length must be at least n"); // Real_FT.rs:6 / :43
     if (!is_pow2(n)) return fail(NRB_ERR_NOT_POW2, "realft: n must be a power of two");
@@ -470,28 +514,28 @@ int nrb_realft_batch(double *const *ptrs, size_t n, size_t count, int isign)
     const size_t dims[1] = {n};
     // Real_FT.rs:10,15: isign == 1 is forward, anything else inverse
     return run_inplace(NRB_KIND_REALFT, dims, 1, ptrs, count, n, isign == 1 ? 1 : -1, nullptr, 0);
-}
+} catch (...) { return on_exception(); }
 
 int nrb_rlft3(double *data, double *speq, size_t nn1, size_t nn2, size_t nn3, int isign)
-{
+try {
     if (isign != 1 && isign != -1) return fail(NRB_ERR_INVALID_ISIGN, "isign must be 1 or -1");   // Real_FT3.rs:17
     if (nn1 == 0 || nn2 == 0 || nn3 < 2) return fail(NRB_ERR_INVALID_DIMS, "data dimensions mismatch");
     if (!data || !speq) return fail(NRB_ERR_EMPTY_INPUT, "null data");
     const size_t dims[3] = {nn1, nn2, nn3};
     double *ptrs[1] = {data};
     return run_inplace(NRB_KIND_RLFT3, dims, 3, ptrs, 1, nn1 * nn2 * nn3, isign, speq, 2 * nn1 * nn2);
-}
+} catch (...) { return on_exception(); }
 
 int nrb_convlv(const double *data, size_t n, const double *respns, size_t m, int isign, int pad_mode, double *ans)
-{
+try {
     const double *in[1] = {data};
     double *out[1] = {ans};
     return nrb_convlv_batch(in, 1, n, respns, m, isign, pad_mode, out);
-}
+} catch (...) { return on_exception(); }
 
 int nrb_convlv_batch(const double *const *data, size_t count, size_t n, const double *respns, size_t m, int isign,
                      int pad_mode, double *const *ans)
-{
+try {
     // Convolve.rs:13-21 check order
     if (n == 0 || m == 0) return fail(NRB_ERR_EMPTY_INPUT, "Input arrays cannot be empty");
     if (m > n) return fail(NRB_ERR_RESPONSE_TOO_LONG, "Response function longer than data");
@@ -503,31 +547,31 @@ int nrb_convlv_batch(const double *const *data, size_t count, size_t n, const do
     const size_t dims[2] = {n, m};
     const double *aux[1] = {respns};
     return run_outofplace(NRB_KIND_CONVLV, dims, 2, data, aux, 1, m, ans, count, n, isign, pad_mode);
-}
+} catch (...) { return on_exception(); }
 
 int nrb_correl(const double *data1, size_t n1, const double *data2, size_t n2, double *ans)
-{
+try {
     // Correlation.rs:11-16 check order
     if (n1 == 0) return fail(NRB_ERR_EMPTY_INPUT, "Input arrays cannot be empty");
     if (n2 != n1) return fail(NRB_ERR_LENGTH_MISMATCH, "Input arrays must have the same length");
     const double *a[1] = {data1}, *b[1] = {data2};
     double *o[1] = {ans};
     return nrb_correl_batch(a, b, 1, n1, o);
-}
+} catch (...) { return on_exception(); }
 
 int nrb_correl_batch(const double *const *data1, const double *const *data2, size_t count, size_t n, double *const *ans)
-{
+try {
     if (n == 0) return fail(NRB_ERR_EMPTY_INPUT, "Input arrays cannot be empty");
     if (n > 32 && !is_pow2(n)) return fail(NRB_ERR_NOT_POW2, "correl: n > 32 must be a power of two");
     if (count == 0) return NRB_OK;
     if (!data1 || !data2 || !ans) return fail(NRB_ERR_EMPTY_INPUT, "null pointer");
     const size_t dims[1] = {n};
     return run_outofplace(NRB_KIND_CORREL, dims, 1, data1, data2, count, n, ans, count, n, 1, 0);
-}
+} catch (...) { return on_exception(); }
 
 // ------------------------------------------------------------------ "next" rows
 int nrb_correl_normalized(const double *data1, size_t n1, const double *data2, size_t n2, int fast, double *ans)
-{
+try {
     // Correlation.rs:190-196 / :227-233 check order
     if (n1 == 0) return fail(NRB_ERR_EMPTY_INPUT, "Input arrays cannot be empty");
     if (n2 != n1) return fail(NRB_ERR_LENGTH_MISMATCH, "Input arrays must have the same length");
@@ -543,50 +587,67 @@ int nrb_correl_normalized(const double *data1, size_t n1, const double *data2, s
     if (be_d2h(ans, (double *)t_ctx.out.p + 4, n1 * sizeof(double), t_ctx.stream) != 0 || be_sync(t_ctx.stream) != 0)
         return copy_fail("device-to-host copy");
     return NRB_OK;
-}
+} catch (...) { return on_exception(); }
 
 int nrb_autocorrel_fast(const double *data, size_t n, double *ans)
-{
+try {
     if (n == 0) return fail(NRB_ERR_EMPTY_INPUT, "Input arrays cannot be empty");                 // Correlation.rs:288-290
     if (n > 32 && !is_pow2(n)) return fail(NRB_ERR_NOT_POW2, "correl: n > 32 must be a power of two");
     if (!data || !ans) return fail(NRB_ERR_EMPTY_INPUT, "null pointer");
     const size_t dims[1] = {n};
     return run_segments(NRB_KIND_AUTOCORREL_FAST, dims, 1, 1, {{data, 0, n}}, {}, n, {{ans, 0, n}}, 1, 0);
-}
+} catch (...) { return on_exception(); }
 
 int nrb_twofft(const double *data1, const double *data2, size_t n, double *fft1, double *fft2)
 {
+    const double *a[1] = {data1}, *b[1] = {data2};
+    double *f1[1] = {fft1}, *f2[1] = {fft2};
+    return nrb_twofft_batch(a, b, 1, n, f1, f2);
+}
+
+int nrb_twofft_batch(const double *const *data1, const double *const *data2, size_t count, size_t n, double *const *fft1,
+                     double *const *fft2)
+try {
     if (n == 0) return fail(NRB_ERR_EMPTY_INPUT, "twofft: empty input");
     if (!is_pow2(n)) return fail(NRB_ERR_NOT_POW2, "twofft: n must be a power of two");
+    if (count == 0) return NRB_OK;
     if (!data1 || !data2 || !fft1 || !fft2) return fail(NRB_ERR_EMPTY_INPUT, "null pointer");
     const size_t dims[1] = {n};
     const size_t per = 2 * n + 2;   // FFT_2.rs:6-7
-    return run_segments(NRB_KIND_TWOFFT, dims, 1, 1, {{data1, 0, n}}, {{data2, 0, n}}, 2 * per, {{fft1, 0, per}, {fft2, per, per}}, 1, 0);
-}
+    std::vector<Seg> io, aux, outs;
+    for (size_t b = 0; b < count; ++b) {
+        if (!data1[b] || !data2[b] || !fft1[b] || !fft2[b]) return fail(NRB_ERR_EMPTY_INPUT, "null pointer");
+        io.push_back(Seg{data1[b], b * n, n});
+        aux.push_back(Seg{data2[b], b * n, n});
+        outs.push_back(Seg{fft1[b], b * per, per});
+        outs.push_back(Seg{fft2[b], (count + b) * per, per});
+    }
+    return run_segments(NRB_KIND_TWOFFT, dims, 1, count, io, aux, 2 * count * per, outs, 1, 0);
+} catch (...) { return on_exception(); }
 
 int nrb_power_spectrum(const double *complex_data, size_t npoints, int take_sqrt, double *out)
-{
+try {
     if (npoints == 0) return NRB_OK;                           // FFT_1.rs:206-228: empty in, empty out
     if (!complex_data || !out) return fail(NRB_ERR_EMPTY_INPUT, "null pointer");
     const size_t dims[1] = {npoints};
     return run_segments(NRB_KIND_POWER, dims, 1, 1, {{complex_data, 0, 2 * npoints}}, {}, npoints, {{out, 0, npoints}}, 1, take_sqrt ? 1 : 0);
-}
+} catch (...) { return on_exception(); }
 
 static int run_cosft(int kind, double *y, size_t n, size_t doubles, int isign)
-{
+try {
     if (n < 2) return fail(NRB_ERR_INVALID_DIMS, "cosft/sinft: n must be >= 2");
     if (!is_pow2(n)) return fail(NRB_ERR_NOT_POW2, "cosft/sinft: n must be a power of two");
     if (!y) return fail(NRB_ERR_EMPTY_INPUT, "null data");
     const size_t dims[1] = {n};
     double *ptrs[1] = {y};
     return run_inplace(kind, dims, 1, ptrs, 1, doubles, isign, nullptr, 0);
-}
+} catch (...) { return on_exception(); }
 int nrb_cosft1(double *y, size_t n) { return run_cosft(NRB_KIND_COSFT1, y, n, n + 2, 1); }
 int nrb_cosft2(double *y, size_t n, int isign)
-{
+try {
     if (isign != 1 && isign != -1) return fail(NRB_ERR_INVALID_ISIGN, "Invalid isign value. Must be 1 or -1");   // Cos_FT2.rs:11
     return run_cosft(NRB_KIND_COSFT2, y, n, n + 1, isign);
-}
+} catch (...) { return on_exception(); }
 int nrb_sinft(double *y, size_t n) { return run_cosft(NRB_KIND_SINFT, y, n, n + 1, 1); }
 
 } // extern "C"

@@ -105,6 +105,59 @@ inline void twofft(const std::vector<double> &data1, const std::vector<double> &
     if (fft2.size() != 2 * n + 2) throw Panic("fft2 must have length 2*n + 2");
     panic_on(nrb_twofft(data1.data(), data2.data(), n, fft1.data(), fft2.data()));
 }
+inline void twofft_optimized(const std::vector<double> &data1, const std::vector<double> &data2, std::vector<double> &fft1,
+                             std::vector<double> &fft2) { twofft(data1, data2, fft1, fft2); }   // FFT_2.rs:135
+
+// FFT_2.rs:222-265.  The builder flags select CPU code paths in the reference; kept and ignored (one device path).
+class TwoFFTProcessor {
+public:
+    struct Item { const std::vector<double> *data1, *data2; std::vector<double> *fft1, *fft2; };
+    TwoFFTProcessor() : use_optimized_(true), parallel_threshold_(1024) {}
+    TwoFFTProcessor &with_optimized(bool v) { use_optimized_ = v; return *this; }
+    TwoFFTProcessor &with_threshold(std::size_t t) { parallel_threshold_ = t; return *this; }
+    void process(const std::vector<double> &data1, const std::vector<double> &data2, std::vector<double> &fft1,
+                 std::vector<double> &fft2) const { twofft(data1, data2, fft1, fft2); }
+    // FFT_2.rs:258 process_batch: runs of tuples with equal length go to the device as one batched plan
+    void process_batch(const std::vector<Item> &batches) const
+    {
+        std::size_t i = 0;
+        while (i < batches.size()) {
+            const std::size_t n = batches[i].data1->size();
+            std::vector<const double *> a, b;
+            std::vector<double *> f1, f2;
+            std::size_t j = i;
+            for (; j < batches.size() && batches[j].data1->size() == n; ++j) {
+                const Item &it = batches[j];
+                if (it.data2->size() != n) throw Panic("data2 length must equal data1 length");
+                if (it.fft1->size() != 2 * n + 2) throw Panic("fft1 must have length 2*n + 2");
+                if (it.fft2->size() != 2 * n + 2) throw Panic("fft2 must have length 2*n + 2");
+                a.push_back(it.data1->data()); b.push_back(it.data2->data());
+                f1.push_back(it.fft1->data()); f2.push_back(it.fft2->data());
+            }
+            panic_on(nrb_twofft_batch(a.data(), b.data(), a.size(), n, f1.data(), f2.data()));
+            i = j;
+        }
+    }
+private:
+    bool use_optimized_;
+    std::size_t parallel_threshold_;
+};
+
+// FFT_2.rs:361 / :375
+inline std::pair<std::vector<double>, std::vector<double>> extract_real_imag(const std::vector<double> &fft)
+{
+    const std::size_t n = fft.size() / 2;
+    std::vector<double> re(n), im(n);
+    for (std::size_t i = 0; i < n; ++i) { re[i] = fft[2 * i]; im[i] = fft[2 * i + 1]; }
+    return {re, im};
+}
+inline std::vector<double> combine_real_imag(const std::vector<double> &re, const std::vector<double> &im)
+{
+    if (re.size() != im.size()) throw Panic("Real and imaginary parts must have same length");
+    std::vector<double> c(2 * re.size());
+    for (std::size_t i = 0; i < re.size(); ++i) { c[2 * i] = re[i]; c[2 * i + 1] = im[i]; }
+    return c;
+}
 } // namespace FFT_2
 
 // ------------------------------------------------------------------ Cos_FT.rs / Cos_FT2.rs / sinft (README.md:72)
@@ -125,6 +178,7 @@ inline void cosft2(std::vector<double> &y, std::size_t n, int isign)
     if (y.size() < n + 1) throw Panic("index out of bounds: y must hold n + 1 elements");
     panic_on(nrb_cosft2(y.data(), n, isign));
 }
+inline void cosft2_simd(std::vector<double> &y, std::size_t n, int isign) { cosft2(y, n, isign); }   // Cos_FT2.rs:202
 } // namespace Cos_FT2
 namespace Sin_FT {
 inline void sinft(std::vector<double> &y, std::size_t n)
@@ -167,6 +221,37 @@ inline void realft(std::vector<double> &data, std::size_t n, int isign)
 }
 inline void realft_optimized(std::vector<double> &data, std::size_t n, int isign) { realft(data, n, isign); }
 
+// Real_FT.rs:332-370 (builder flags kept and ignored: one device path)
+class RealFTProcessor {
+public:
+    struct Item { std::vector<double> *data; std::size_t n; int isign; };
+    RealFTProcessor() : use_optimized_(true), parallel_threshold_(1024) {}
+    RealFTProcessor &with_optimized(bool v) { use_optimized_ = v; return *this; }
+    RealFTProcessor &with_threshold(std::size_t t) { parallel_threshold_ = t; return *this; }
+    void process(std::vector<double> &data, std::size_t n, int isign) const { realft(data, n, isign); }
+    // Real_FT.rs:365 process_batch: runs of equal (n, direction) go to the device as one batch
+    void process_batch(const std::vector<Item> &batches) const
+    {
+        std::size_t i = 0;
+        while (i < batches.size()) {
+            const std::size_t n = batches[i].n;
+            const int dir = batches[i].isign == 1 ? 1 : -1;      // Real_FT.rs:10,15: anything but 1 is the inverse
+            std::vector<double *> ptrs;
+            std::size_t j = i;
+            for (; j < batches.size() && batches[j].n == n && (batches[j].isign == 1 ? 1 : -1) == dir; ++j) {
+                if (n % 2 != 0) throw Panic("n must be even");
+                if (batches[j].data->size() < n) throw Panic("data length must be at least n");
+                ptrs.push_back(batches[j].data->data());
+            }
+            panic_on(nrb_realft_batch(ptrs.data(), n, ptrs.size(), dir));
+            i = j;
+        }
+    }
+private:
+    bool use_optimized_;
+    std::size_t parallel_threshold_;
+};
+
 } // namespace Real_FT
 
 // ------------------------------------------------------------------ Real_FT3.rs
@@ -181,6 +266,9 @@ inline void rlft3(std::vector<double> &data, std::vector<double> &speq, std::siz
     if (speq.size() != nn1 * 2 * nn2) throw Panic("speq dimensions mismatch");
     panic_on(nrb_rlft3(data.data(), speq.data(), nn1, nn2, nn3, isign));
 }
+// Real_FT3.rs:145 rlft3_optimized: flat slices, same transform
+inline void rlft3_optimized(std::vector<double> &data, std::vector<double> &speq, std::size_t nn1, std::size_t nn2,
+                            std::size_t nn3, int isign) { rlft3(data, speq, nn1, nn2, nn3, isign); }
 
 } // namespace Real_FT3
 

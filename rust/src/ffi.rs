@@ -30,6 +30,8 @@ extern "C" {
                                  ans: *mut c_double) -> c_int;
     pub fn nrb_autocorrel_fast(data: *const c_double, n: usize, ans: *mut c_double) -> c_int;
     pub fn nrb_twofft(d1: *const c_double, d2: *const c_double, n: usize, fft1: *mut c_double, fft2: *mut c_double) -> c_int;
+    pub fn nrb_twofft_batch(d1: *const *const c_double, d2: *const *const c_double, count: usize, n: usize,
+                            fft1: *const *mut c_double, fft2: *const *mut c_double) -> c_int;
     pub fn nrb_cosft1(y: *mut c_double, n: usize) -> c_int;
     pub fn nrb_cosft2(y: *mut c_double, n: usize, isign: c_int) -> c_int;
     pub fn nrb_sinft(y: *mut c_double, n: usize) -> c_int;

@@ -300,6 +300,8 @@ pub mod Cos_FT2 {
         assert!(y.len() >= n + 1, "index out of bounds: y must hold n + 1 elements");
         panic_on(unsafe { nrb_cosft2(y.as_mut_ptr(), n, isign) });
     }
+    /// reference: src/Cos_FT2.rs:202 (same contract)
+    pub fn cosft2_simd(y: &mut [f64], n: usize, isign: i32) { cosft2(y, n, isign) }
 }
 
 pub mod Sin_FT {
@@ -349,5 +351,47 @@ pub mod FFT_2 {
         assert_eq!(fft1.len(), 2 * n + 2, "fft1 must have length 2*n + 2");
         assert_eq!(fft2.len(), 2 * n + 2, "fft2 must have length 2*n + 2");
         panic_on(unsafe { nrb_twofft(data1.as_ptr(), data2.as_ptr(), n, fft1.as_mut_ptr(), fft2.as_mut_ptr()) });
+    }
+    /// reference: src/FFT_2.rs:135
+    pub fn twofft_optimized(data1: &[f64], data2: &[f64], fft1: &mut [f64], fft2: &mut [f64]) { twofft(data1, data2, fft1, fft2) }
+
+    /// reference: src/FFT_2.rs:222-265 (builder flags kept and ignored: one device path)
+    pub struct TwoFFTProcessor { use_optimized: bool, parallel_threshold: usize }
+    impl TwoFFTProcessor {
+        pub fn new() -> Self { Self { use_optimized: true, parallel_threshold: 1024 } }
+        pub fn with_optimized(mut self, v: bool) -> Self { self.use_optimized = v; self }
+        pub fn with_threshold(mut self, t: usize) -> Self { self.parallel_threshold = t; self }
+        pub fn process(&self, data1: &[f64], data2: &[f64], fft1: &mut [f64], fft2: &mut [f64]) { twofft(data1, data2, fft1, fft2) }
+        /// reference: src/FFT_2.rs:258 (which cannot mutate through its `&[(.., &mut [f64], &mut [f64])]` argument and
+        /// does not compile, err.log; the slice of tuples is taken mutably here).  Runs of equal length = one batch.
+        pub fn process_batch(&self, batches: &mut [(&[f64], &[f64], &mut [f64], &mut [f64])]) {
+            let mut i = 0;
+            while i < batches.len() {
+                let n = batches[i].0.len();
+                let (mut a, mut b, mut f1, mut f2) = (Vec::new(), Vec::new(), Vec::new(), Vec::new());
+                let mut j = i;
+                while j < batches.len() && batches[j].0.len() == n {
+                    assert_eq!(batches[j].1.len(), n, "data2 length must equal data1 length");
+                    assert_eq!(batches[j].2.len(), 2 * n + 2, "fft1 must have length 2*n + 2");
+                    assert_eq!(batches[j].3.len(), 2 * n + 2, "fft2 must have length 2*n + 2");
+                    a.push(batches[j].0.as_ptr()); b.push(batches[j].1.as_ptr());
+                    f1.push(batches[j].2.as_mut_ptr()); f2.push(batches[j].3.as_mut_ptr());
+                    j += 1;
+                }
+                panic_on(unsafe { nrb_twofft_batch(a.as_ptr(), b.as_ptr(), a.len(), n, f1.as_ptr(), f2.as_ptr()) });
+                i = j;
+            }
+        }
+    }
+
+    /// reference: src/FFT_2.rs:361
+    pub fn extract_real_imag(fft: &[f64]) -> (Vec<f64>, Vec<f64>) {
+        let n = fft.len() / 2;
+        ((0..n).map(|i| fft[2 * i]).collect(), (0..n).map(|i| fft[2 * i + 1]).collect())
+    }
+    /// reference: src/FFT_2.rs:375
+    pub fn combine_real_imag(real: &[f64], imag: &[f64]) -> Vec<f64> {
+        assert_eq!(real.len(), imag.len(), "Real and imaginary parts must have same length");
+        real.iter().zip(imag.iter()).flat_map(|(r, i)| [*r, *i]).collect()
     }
 }

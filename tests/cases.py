@@ -135,6 +135,25 @@ def check_twofft(L, n, seed=1010):
     assert f1[1] == 0.0 and f2[1] == 0.0 and not f1[2 * n:].any() and not f2[2 * n:].any()   # FFT_2.rs:60-62, :6-7
 
 
+def check_twofft_batch(L, lengths, seed=1030):
+    """FFT_2.rs:258 TwoFFTProcessor::process_batch: mixed lengths in one call, each result = twofft of that pair."""
+    items, refs = [], []
+    for i, n in enumerate(lengths):
+        a, b = gen(seed + 2 * i, n), gen(seed + 2 * i + 1, n)
+        items.append((a, b, np.full(2 * n + 2, np.nan), np.full(2 * n + 2, np.nan)))
+        refs.append(O.twofft(a, b))
+    nb.TwoFFTProcessor(L).with_optimized(False).with_threshold(16).process_batch(items)
+    for (a, b, f1, f2), (r1, r2) in zip(items, refs):
+        assert rel(f1, r1) <= tol(a.size) and rel(f2, r2) <= tol(a.size), (a.size, rel(f1, r1), rel(f2, r2))
+    # the single-pair entry point gives the same bits as the batched one
+    a, b, f1, f2 = items[0]
+    g1, g2 = np.empty_like(f1), np.empty_like(f2)
+    nb.TwoFFTProcessor(L).process(a, b, g1, g2)
+    assert np.array_equal(f1, g1) and np.array_equal(f2, g2)
+    re, im = nb.extract_real_imag(f1)
+    assert np.array_equal(nb.combine_real_imag(re, im), f1)
+
+
 def check_correl_normalized(L, n, seed=1011, fast=False):
     a = gen(seed, n) + 0.75
     b = 2.0 * gen(seed + 1, n) - 0.25

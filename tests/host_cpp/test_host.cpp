@@ -70,6 +70,23 @@ int main(int argc, char **argv)
             auto pw = FFT_1::power_spectrum_device(f2), hp = FFT_1::power_spectrum(f2);
             for (std::size_t k = 0; k < m; ++k) CHECK(std::fabs(pw[k] - hp[k]) <= 4e-16 * hp[k]);   // the device contracts x*x + y*y into an FMA
         }
+        {   // FFT_2.rs:258 process_batch = twofft on every tuple; Real_FT.rs:365 process_batch = realft on every item
+            std::vector<double> a1(64), b1(64), a2(256), b2(256), f1(130), g1(130), f2(514), g2(514), r1(130), s1(130);
+            for (std::size_t i = 0; i < 256; ++i) { a2[i] = std::sin(0.1 * i); b2[i] = std::cos(0.3 * i); if (i < 64) { a1[i] = a2[i] * 2; b1[i] = b2[i] - 1; } }
+            FFT_2::TwoFFTProcessor().with_optimized(false).with_threshold(8).process_batch({{&a1, &b1, &f1, &g1}, {&a2, &b2, &f2, &g2}});
+            FFT_2::twofft_optimized(a1, b1, r1, s1);
+            CHECK(r1 == f1 && s1 == g1);
+            auto ri = FFT_2::extract_real_imag(f2);
+            CHECK(FFT_2::combine_real_imag(ri.first, ri.second) == f2);
+            std::vector<double> x(64), y(64), x0, y0;
+            for (std::size_t i = 0; i < 64; ++i) { x[i] = std::sin(0.2 * i); y[i] = 1.0 / (1 + i); }
+            x0 = x; y0 = y;
+            Real_FT::RealFTProcessor().process_batch({{&x, 64, 1}, {&y, 64, 1}});
+            Real_FT::realft_optimized(x0, 64, 1);
+            CHECK(x == x0);
+            Real_FT::RealFTProcessor().process_batch({{&x, 64, -1}, {&y, 64, 7}});      // anything but 1 is the inverse (Real_FT.rs:15)
+            for (std::size_t i = 0; i < 64; ++i) CHECK(std::fabs(y[i] / 32.0 - y0[i]) < 1e-12);
+        }
         // Cos_FT2.rs:248-264 round trip (true factor n/2); cosft1 of a constant: F_0 = n c, F_k = 0 for even k > 0
         {
             const std::size_t m = 16;

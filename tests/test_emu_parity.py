@@ -527,3 +527,12 @@ def test_big_tile_pass_transposing_four_step(emu):
     cases.check_four1(emu, 1 << 20)                  # XPOSE 1024 + strided 1024
     cases.check_four1(emu, 1 << 19)                  # XPOSE 1024 + strided 512
     assert _emu_count(emu, 2) - before >= 16
+
+
+def test_twofft_processor_batch_and_helpers(emu):
+    cases.check_twofft_batch(emu, [64, 64, 256, 64, 1024, 8])
+    with pytest.raises(AssertionError):                         # FFT_2.rs:6
+        nb.TwoFFTProcessor(emu).process_batch([(np.zeros(8), np.zeros(8), np.zeros(17), np.zeros(18))])
+    with pytest.raises(AssertionError):                         # FFT_2.rs:377
+        nb.combine_real_imag(np.zeros(3), np.zeros(4))
+    assert emu.twofft_batch([], [], [], []) == 0                # empty batch: nothing to do

@@ -380,3 +380,8 @@ def test_big_tile_passes(gpu):
     cases.check_fourn(gpu, (1024, 64))
     cases.check_fourn(gpu, (2, 512, 8))
     cases.check_four1(gpu, 1 << 20)
+
+
+@pytest.mark.gpu
+def test_twofft_processor_batch(gpu):
+    cases.check_twofft_batch(gpu, [64, 4096, 64, 1 << 15, 4096, 2, 1 << 15])
