@@ -25,6 +25,7 @@ struct nrb_plan_s {
     {
         if (plan.ws) be_free(plan.ws);
         if (plan.sched) be_free(plan.sched);
+        release_side_lane(plan.side);
     }
 };
 struct nrb_slab_s {

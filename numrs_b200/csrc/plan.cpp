@@ -52,6 +52,7 @@ static Tunables &tunables_mut()
         x.prefetch_dist = env_int("NRB_PREFETCH_DIST", -1);
         x.conv_transposed = env_int("NRB_CONV_TRANSPOSED", 1);
         x.simple_addr = env_int("NRB_SIMPLE_ADDR", 1);
+        x.speq_side = env_int("NRB_SPEQ_SIDE", 0);
         x.big_row_mask = env_int("NRB_BIG_ROW_MASK", 0);
         x.big_col_mask = env_int("NRB_BIG_COL_MASK", 0);
         return x;
@@ -81,6 +82,7 @@ int set_tunable(const char *name, long value)
     else if (n == "prefetch_dist") t.prefetch_dist = (int)value;
     else if (n == "conv_transposed") t.conv_transposed = (int)value;
     else if (n == "simple_addr") t.simple_addr = (int)value;
+    else if (n == "speq_side") t.speq_side = (int)value;
     else if (n == "big_row_mask") t.big_row_mask = (int)value;
     else if (n == "big_col_mask") t.big_col_mask = (int)value;
     else return -1;
@@ -571,7 +573,22 @@ int build_rlft3(Plan &pl, Builder &B, int dir)
         B.prog->steps.push_back(st);
         return true;
     };
-    if (dir > 0) {
+    // speq-plane passes: single-pass axes only touch the speq buffer, so they may run beside the data passes (lane 1)
+    const bool side = tunables().speq_side && g == nn1 && !fusable && p1 <= tunables().col_max_log2 && p2 <= tunables().row_max_log2;
+    auto emit_speq = [&](int axis, int d) {
+        const size_t first = B.prog->steps.size();
+        if (axis == 2) emit_axis(B, S, S, W, nn1, 0, nn1, p2, 1, d);
+        else emit_axis(B, S, S, W, 1, 0, 1, p1, nn2, d);
+        if (side) for (size_t i = first; i < B.prog->steps.size(); ++i) B.prog->steps[i].lane = 1;
+    };
+    if (dir > 0 && side) {
+        // z pass (writes data and speq), then the two speq passes on the side lane beside the y and x passes
+        emit_real(B, D, D, W, 0, nn1 * nn2, p3, +1, REAL_SPEQ, S);
+        emit_speq(2, +1);
+        emit_speq(1, +1);
+        emit_axis(B, D, D, W, nn1, 0, nn1, p2, N3, +1);
+        emit_axis(B, D, D, W, 1, 0, 1, p1, nn2 * N3, +1);
+    } else if (dir > 0) {
         if (!emit_fused(+1)) {
             for (u64 x0 = 0; x0 < nn1; x0 += g) {
                 const u64 x1 = (x0 + g < nn1) ? x0 + g : nn1;
@@ -579,13 +596,19 @@ int build_rlft3(Plan &pl, Builder &B, int dir)
                 emit_axis(B, D, D, W, nn1, x0, x1, p2, N3, +1);
             }
         }
-        emit_axis(B, S, S, W, nn1, 0, nn1, p2, 1, +1);
+        emit_speq(2, +1);
         emit_axis(B, D, D, W, 1, 0, 1, p1, nn2 * N3, +1);
-        emit_axis(B, S, S, W, 1, 0, 1, p1, nn2, +1);
-    } else {
-        emit_axis(B, S, S, W, 1, 0, 1, p1, nn2, -1);
+        emit_speq(1, +1);
+    } else if (side) {
+        emit_speq(1, -1);
+        emit_speq(2, -1);
         emit_axis(B, D, D, W, 1, 0, 1, p1, nn2 * N3, -1);
-        emit_axis(B, S, S, W, nn1, 0, nn1, p2, 1, -1);
+        emit_axis(B, D, D, W, nn1, 0, nn1, p2, N3, -1);
+        emit_real(B, D, D, W, 0, nn1 * nn2, p3, -1, REAL_SPEQ, S);   // reads speq: joins the side lane first
+    } else {
+        emit_speq(1, -1);
+        emit_axis(B, D, D, W, 1, 0, 1, p1, nn2 * N3, -1);
+        emit_speq(2, -1);
         if (!emit_fused(-1)) {
             for (u64 x0 = 0; x0 < nn1; x0 += g) {
                 const u64 x1 = (x0 + g < nn1) ? x0 + g : nn1;
@@ -969,12 +992,56 @@ int build_plan(Plan &pl, int kind, const size_t *dims, size_t ndim, size_t batch
 
 struct PeerExchange { double2 *const *peers; i64 off; };
 
-static int run_program(Program &prog, double2 *const base[4], int arg, void *stream, std::vector<void *> *events = nullptr,
-                       const PeerExchange *px = nullptr, void *sched = nullptr)
+void release_side_lane(SideLane &sl)
 {
+    if (sl.ev_fork) be_event_destroy(sl.ev_fork);
+    if (sl.ev_join) be_event_destroy(sl.ev_join);
+    if (sl.stream) be_stream_destroy(sl.stream);
+    sl = SideLane();
+}
+
+static bool open_side_lane(SideLane &sl)
+{
+    if (sl.stream) return true;
+    if (be_stream_create_prio(&sl.stream, 0) != 0) { sl.stream = nullptr; return false; }
+    sl.ev_fork = be_event_create();
+    sl.ev_join = be_event_create();
+    if (!sl.ev_fork || !sl.ev_join) { release_side_lane(sl); return false; }
+    return true;
+}
+
+static int run_program(Program &prog, double2 *const base[4], int arg, void *main_stream, std::vector<void *> *events = nullptr,
+                       const PeerExchange *px = nullptr, void *sched = nullptr, SideLane *side = nullptr)
+{
+    void *stream = main_stream;
     if (events) events->push_back(be_event_record(stream));
+    bool forked = false;
+    // lanes are only honoured for plain executions (profiling times one launch after the other on one stream)
+    const bool lanes = side && !events;
     for (Step &st : prog.steps) {
         int rc;
+        if (lanes) {
+            const bool touches_speq = st.speq.id != BUF_NONE || (st.is_fused && st.speq2.id != BUF_NONE);
+            if (st.lane == 1 && (forked || open_side_lane(*side))) {
+                if (!forked) {   // fork: everything enqueued so far precedes the side work
+                    if (be_event_record_on(side->ev_fork, main_stream) != 0 || be_stream_wait(side->stream, side->ev_fork) != 0) {
+                        set_error(std::string("side lane fork failed: ") + be_last_error());
+                        return NRB_ERR_CUDA;
+                    }
+                    forked = true;
+                }
+                stream = side->stream;
+            } else {
+                if (forked && touches_speq) {   // join before the speq plane is used on the main lane again
+                    if (be_event_record_on(side->ev_join, side->stream) != 0 || be_stream_wait(main_stream, side->ev_join) != 0) {
+                        set_error(std::string("side lane join failed: ") + be_last_error());
+                        return NRB_ERR_CUDA;
+                    }
+                    forked = false;
+                }
+                stream = main_stream;
+            }
+        }
         if (st.is_fused) {
             PassParams pa = st.pp, pb = st.pp2;
             pa.in = base[st.in.id] + st.in.off; pa.out = base[st.out.id] + st.out.off;
@@ -1013,6 +1080,12 @@ static int run_program(Program &prog, double2 *const base[4], int arg, void *str
         if (rc != 0) { set_error(std::string("kernel launch failed: ") + be_last_error()); return NRB_ERR_CUDA; }
         if (events) events->push_back(be_event_record(stream));
     }
+    if (forked) {   // the program ends with side work in flight: later work on the caller's stream must see it
+        if (be_event_record_on(side->ev_join, side->stream) != 0 || be_stream_wait(main_stream, side->ev_join) != 0) {
+            set_error(std::string("side lane join failed: ") + be_last_error());
+            return NRB_ERR_CUDA;
+        }
+    }
     return NRB_OK;
 }
 
@@ -1040,7 +1113,10 @@ int exec_plan(Plan &pl, double *d_io, double *d_aux, double *d_out, int isign, i
 {
     if (isign != 1 && isign != -1) { set_error("isign must be 1 or -1"); return NRB_ERR_INVALID_ISIGN; }
     double2 *const base[4] = {(double2 *)d_io, (double2 *)d_aux, (double2 *)d_out, (double2 *)pl.ws};
-    return run_program(pl.prog[isign == 1 ? 0 : 1], base, arg, stream, nullptr, nullptr, pl.sched);
+    Program &prog = pl.prog[isign == 1 ? 0 : 1];
+    bool any_side = false;
+    for (const Step &st : prog.steps) any_side = any_side || st.lane != 0;
+    return run_program(prog, base, arg, stream, nullptr, nullptr, pl.sched, any_side ? &pl.side : nullptr);
 }
 
 int profile_plan(Plan &pl, double *d_io, double *d_aux, double *d_out, int isign, int arg, void *stream, float *ms,

@@ -66,6 +66,7 @@ struct Step {
     u64 ntiles;
     BufRef in, out, speq, b;
     bool patch_pad_mode;   // AUX_PAD_RESPONSE: op comes from exec's `arg`
+    int lane;              // 0 = the caller's stream; 1 = the plan's side stream (small independent work, see SideLane)
     // fused pair: (key, pp, in/out/speq) is pass A, the *2 members are pass B
     bool is_fused;
     KernelKey key2;
@@ -73,7 +74,7 @@ struct Step {
     BufRef in2, out2, speq2;
     FuseSched fs;          // counters live in the plan's scheduler scratch (sched_off = element offset)
     size_t sched_off;
-    Step() : is_aux(false), key{0, 0, 0, 0}, pp(), ap(), ntiles(0), patch_pad_mode(false), is_fused(false),
+    Step() : is_aux(false), key{0, 0, 0, 0}, pp(), ap(), ntiles(0), patch_pad_mode(false), lane(0), is_fused(false),
              key2{0, 0, 0, 0}, pp2(), fs{nullptr, nullptr, 0, 0, 0, 0}, sched_off(0) {}
 };
 
@@ -99,6 +100,7 @@ struct Tunables {
     int conv_transposed;   // convlv/correl with lines longer than a tile: two passes per transform and the spectrum in
                            // transposed order instead of three natural-order passes (NRB_CONV_TRANSPOSED, default 1)
     int prefetch_dist;     // tiles ahead whose input every CTA prefetches into L2 (NRB_PREFETCH_DIST; 0 = off, -1 = per-kernel policy, default)
+    int speq_side;         // rlft3: run the speq-plane passes on the plan's side stream (NRB_SPEQ_SIDE, default 0: not measured yet)
     int simple_addr;       // 1: passes whose element index is not split use the cheap addressing path (NRB_SIMPLE_ADDR, default 1)
     int big_row_mask;      // bit log2n set: contiguous lines of 2^log2n points use the big-tile pass of fft_pass2.cuh (NRB_BIG_ROW_MASK)
     int big_col_mask;      // the same for strided lines (NRB_BIG_COL_MASK)
@@ -122,6 +124,14 @@ inline bool use_big_tiles(const KernelKey &key, const PassParams &p)
     return ((mask >> key.log2n) & 1) != 0;
 }
 
+// Side lane of a plan: steps tagged lane 1 (the speq-plane passes of rlft3: 4 launches of ~10 us that depend only on
+// the z pass) run on a second stream, forked from the caller's stream at the first of them and joined before the first
+// lane-0 step that touches the speq plane again, or at the end of the program.  Created on first use.
+struct SideLane {
+    void *stream, *ev_fork, *ev_join;
+    SideLane() : stream(nullptr), ev_fork(nullptr), ev_join(nullptr) {}
+};
+
 struct Plan {
     int kind;
     std::vector<size_t> dims;
@@ -132,8 +142,10 @@ struct Plan {
     void *sched;           // device scratch for fused-launch counters (owned)
     size_t sched_bytes;
     int device;
+    SideLane side;
     Plan() : kind(0), batch(1), ws_elems(0), ws(nullptr), sched(nullptr), sched_bytes(0), device(0) {}
 };
+void release_side_lane(SideLane &sl);
 
 // builders; return NRB_* codes
 int build_plan(Plan &pl, int kind, const size_t *dims, size_t ndim, size_t batch);

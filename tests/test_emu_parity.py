@@ -536,3 +536,13 @@ def test_twofft_processor_batch_and_helpers(emu):
     with pytest.raises(AssertionError):                         # FFT_2.rs:377
         nb.combine_real_imag(np.zeros(3), np.zeros(4))
     assert emu.twofft_batch([], [], [], []) == 0                # empty batch: nothing to do
+
+
+@pytest.mark.parametrize("shp", [(8, 8, 8), (4, 16, 8), (16, 8, 32), (2, 2, 2), (32, 64, 16)])
+def test_rlft3_speq_passes_on_the_side_lane(emu, shp):
+    """speq_side = 1 reorders the program (z, speq passes on lane 1, y, x); same results, and the option is a no-op
+    for the lane-less executions of the profiler."""
+    emu.set_option("speq_side", 1)
+    cases.check_rlft3(emu, shp)
+    plan = emu.plan_create(nb.KIND_RLFT3, list(shp))
+    assert plan.num_launches(1) == plan.num_launches(-1)

@@ -385,3 +385,42 @@ def test_big_tile_passes(gpu):
 @pytest.mark.gpu
 def test_twofft_processor_batch(gpu):
     cases.check_twofft_batch(gpu, [64, 4096, 64, 1 << 15, 4096, 2, 1 << 15])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shp", [(8, 8, 8), (16, 8, 32), (64, 128, 256), (256, 256, 256)])
+def test_rlft3_speq_passes_on_the_side_lane(gpu, shp):
+    """The speq-plane passes on the plan's side stream (fork after the z pass, join before speq is used again): same
+    results as the single-stream program, also when calls follow each other without a synchronise in between."""
+    gpu.set_option("speq_side", 1)
+    cases.check_rlft3(gpu, shp)
+    n = int(np.prod(shp))
+    x = cases.gen(91, n).reshape(shp)
+    d, s = x.copy(), np.zeros((shp[0], 2 * shp[1]))
+    for _ in range(3):                          # forward / inverse chains on the same buffers
+        nb.rlft3(d, s, *shp, 1, gpu)
+        nb.rlft3(d, s, *shp, -1, gpu)
+        d *= 2.0 / n
+    assert cases.rel(d, x) <= 3 * cases.tol(n)
+
+
+@pytest.mark.gpu
+def test_rlft3_side_lane_device_resident_back_to_back(gpu):
+    """Device-resident executions enqueued back to back on one stream with the speq passes on the side lane: the
+    fork / join events must order every use of the speq plane (forward writes it, inverse reads it)."""
+    import torch
+    shp = (128, 128, 128)
+    n = int(np.prod(shp))
+    st = torch.cuda.current_stream().cuda_stream
+    x = torch.from_numpy(cases.gen(92, n)).cuda()
+    ref = x.clone()
+    sp = torch.zeros(2 * shp[0] * shp[1], dtype=torch.float64, device="cuda")
+    gpu.set_option("speq_side", 1)
+    plan = gpu.plan_create(nb.KIND_RLFT3, list(shp))
+    for _ in range(20):
+        plan.exec(x.data_ptr(), sp.data_ptr(), isign=1, stream=st)
+        plan.exec(x.data_ptr(), sp.data_ptr(), isign=-1, stream=st)
+        x.mul_(2.0 / n)
+    torch.cuda.synchronize()
+    assert float(torch.linalg.norm(x - ref) / torch.linalg.norm(ref)) <= 20 * cases.tol(n)
+    plan.destroy()
