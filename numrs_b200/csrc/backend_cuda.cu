@@ -86,6 +86,16 @@ int be_launch_pass(const KernelKey &key, const PassParams &p, u64 ntiles, void *
     return 0;
 }
 
+int launch_conv_mid(int log2rest, const ConvMidParams &m, u64 ntiles, cudaStream_t s);   // k_mid.cu
+bool be_conv_mid_available(int log2rest) { return log2rest == 4 || log2rest == 6 || log2rest == 12; }
+int be_launch_conv_mid(int log2rest, const ConvMidParams &m, u64 ntiles, void *stream)
+{
+    if (!be_conv_mid_available(log2rest)) { g_be_err = "conv_mid kernel not built for this row length"; return -1; }
+    const int rc = launch_conv_mid(log2rest, m, ntiles, (cudaStream_t)stream);
+    if (rc != 0) return fail((cudaError_t)rc);
+    return 0;
+}
+
 bool be_fused_available(const KernelKey &a, const KernelKey &b)
 {
     init_fused();

@@ -159,8 +159,8 @@ NRB_DEV void v2_load_direct(const PassParams &P, unsigned tile, int tid, double2
 }
 
 // ---- twiddle + butterfly of stage S on the thread's registers (same arithmetic as fft_stage) ----
-template <class G, int S>
-NRB_DEV void v2_compute(const PassParams &P, int tid, double2 *v)
+template <class G, int S, class PP>
+NRB_DEV void v2_compute(const PP &P, int tid, double2 *v)
 {
     typedef Stage2<G, S> T;
     constexpr int R = T::R;

@@ -299,4 +299,19 @@ struct AuxParams {
     unsigned long long *peer_flags[8];  // AUX_SIGNAL: every rank's flag array (IPC-mapped); AUX_WAIT: [0] = local
 };
 
+// ---- fused middle of the long-line convlv / correl pipeline (conv_mid.cuh) ----
+struct ConvMidParams {
+    double2 *data;               // [count][F][REST] the strided pass's output (twiddled), transformed in place
+    const double2 *b;            // second operand: finished transposed spectrum (unused for SPEC_AUTOCORREL)
+    i64 data_stride, b_stride;   // per signal, in complex elements; b_stride = 0: one spectrum for the whole batch
+    u64 count;
+    int f;                       // log2 F
+    int op;                      // SpectralOp
+    const double2 *tw;           // stage twiddles of the REST-point transform
+    const double2 *fs_lo, *fs_hi;   // four-step twiddle exp(-2 pi i m / N), two-level
+    int fs_h;
+    const double2 *rtw_lo, *rtw_hi; // untangle twiddle exp(-i pi k / N), two-level
+    int rtw_h;
+};
+
 } // namespace nrb

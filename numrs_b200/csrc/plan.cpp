@@ -53,6 +53,7 @@ static Tunables &tunables_mut()
         x.conv_transposed = env_int("NRB_CONV_TRANSPOSED", 1);
         x.simple_addr = env_int("NRB_SIMPLE_ADDR", 1);
         x.speq_side = env_int("NRB_SPEQ_SIDE", 0);
+        x.conv_fused_mid = env_int("NRB_CONV_FUSED_MID", 0);
         x.big_row_mask = env_int("NRB_BIG_ROW_MASK", 0);
         x.big_col_mask = env_int("NRB_BIG_COL_MASK", 0);
         return x;
@@ -83,6 +84,7 @@ int set_tunable(const char *name, long value)
     else if (n == "conv_transposed") t.conv_transposed = (int)value;
     else if (n == "simple_addr") t.simple_addr = (int)value;
     else if (n == "speq_side") t.speq_side = (int)value;
+    else if (n == "conv_fused_mid") t.conv_fused_mid = (int)value;
     else if (n == "big_row_mask") t.big_row_mask = (int)value;
     else if (n == "big_col_mask") t.big_col_mask = (int)value;
     else return -1;
@@ -425,7 +427,7 @@ int conv_split(int p)
     return f;
 }
 
-void emit_conv_forward(Builder &B, BufRef src, BufRef dst, u64 cnt, int p, int f)
+void emit_conv_forward(Builder &B, BufRef src, BufRef dst, u64 cnt, int p, int f, bool with_row = true)
 {
     const u64 N = 1ull << p, F = 1ull << f, REST = N >> f;
     {
@@ -444,13 +446,13 @@ void emit_conv_forward(Builder &B, BufRef src, BufRef dst, u64 cnt, int p, int f
         st.ntiles = tiles_for(f, LAYOUT_COL, pp.q_end);
         B.prog->steps.push_back(st);
     }
-    emit_axis(B, dst, dst, BufRef(), cnt * F, 0, cnt * F, p - f, 1, +1);
+    if (with_row) emit_axis(B, dst, dst, BufRef(), cnt * F, 0, cnt * F, p - f, 1, +1);
 }
 
-void emit_conv_inverse(Builder &B, BufRef buf, u64 cnt, int p, int f)
+void emit_conv_inverse(Builder &B, BufRef buf, u64 cnt, int p, int f, bool with_row = true)
 {
     const u64 N = 1ull << p, F = 1ull << f, REST = N >> f;
-    {
+    if (with_row) {
         Step st;
         init_pass(st.pp);
         PassParams &pp = st.pp;
@@ -468,6 +470,29 @@ void emit_conv_inverse(Builder &B, BufRef buf, u64 cnt, int p, int f)
     }
     // COL pass over kf for every r: view [cnt][F][REST]
     emit_axis(B, buf, buf, BufRef(), cnt, 0, cnt, f, REST, -1);
+}
+
+// fused middle (conv_mid.cuh): rows of REST = 2^(p-f) points, `cnt` signals in `data` (in place), second operand `b`
+bool conv_mid_usable(int p, int f)
+{
+    return tunables().conv_fused_mid && f >= 1 && be_conv_mid_available(p - f);
+}
+Step make_conv_mid(int op, BufRef data, BufRef b, u64 cnt, int p, int f, i64 b_stride)
+{
+    Step st;
+    st.is_mid = true;
+    memset(&st.mp, 0, sizeof(st.mp));
+    st.key = KernelKey{p - f, LAYOUT_ROW, 0, VAR_PLAIN};
+    st.mp.data_stride = (i64)1 << p; st.mp.b_stride = b_stride;
+    st.mp.count = cnt; st.mp.f = f; st.mp.op = op;
+    st.mp.tw = stage_twiddles(p - f);
+    const FourStepTable fs = fourstep_table(p);
+    st.mp.fs_lo = fs.lo; st.mp.fs_hi = fs.hi; st.mp.fs_h = fs.h;
+    const FourStepTable rt = fourstep_table(p + 1);          // exp(-2 pi i k / n) = exp(-i pi k / N)
+    st.mp.rtw_lo = rt.lo; st.mp.rtw_hi = rt.hi; st.mp.rtw_h = rt.h;
+    st.in = data; st.out = data; st.b = b;
+    st.ntiles = cnt * ((1ull << f) / 2);
+    return st;
 }
 
 Step make_spectral_zt(int op, BufRef a, BufRef b, BufRef out, u64 n, int f, u64 count, i64 a_stride, i64 b_stride, i64 out_stride)
@@ -653,6 +678,13 @@ int build_convlv(Plan &pl, Builder &B, int dir)
         const BufRef in(BUF_IO, (i64)(b0 * N)), out(BUF_OUT, (i64)(b0 * N));
         if (fsplit > 0) {
             // two passes, spectrum in transposed order, [untangle + multiply + inverse untangle], two passes back
+            if (conv_mid_usable(p, fsplit)) {
+                // strided pass | contiguous forward pass + spectral step + contiguous inverse pass in one kernel | strided pass
+                emit_conv_forward(B, in, out, b1 - b0, p, fsplit, false);
+                B.prog->steps.push_back(make_conv_mid(dir > 0 ? SPEC_CONV_MUL : SPEC_CONV_DIV, out, R, b1 - b0, p, fsplit, 0));
+                emit_conv_inverse(B, out, b1 - b0, p, fsplit, false);
+                continue;
+            }
             emit_conv_forward(B, in, out, b1 - b0, p, fsplit);
             Step sp = make_spectral_zt(dir > 0 ? SPEC_CONV_MUL : SPEC_CONV_DIV, out, R, out, n, fsplit, b1 - b0, (i64)N, 0, (i64)N);
             sp.ap.dir = 1;      // b = raw transposed response
@@ -701,7 +733,12 @@ void emit_correl_group(Builder &B, BufRef a, BufRef b, BufRef out, BufRef F2, Bu
     const int p = ilog2((size_t)N);
     const bool two = op != SPEC_AUTOCORREL;
     const int fsplit = real_needs_separate_untangle(p) ? conv_split(p) : -1;
-    if (fsplit > 0) {
+    if (fsplit > 0 && conv_mid_usable(p, fsplit)) {
+        if (two) emit_conv_forward(B, b, F2, cnt, p, fsplit);          // the second operand's finished spectrum
+        emit_conv_forward(B, a, out, cnt, p, fsplit, false);
+        B.prog->steps.push_back(make_conv_mid(op, out, two ? F2 : out, cnt, p, fsplit, (i64)N));
+        emit_conv_inverse(B, out, cnt, p, fsplit, false);
+    } else if (fsplit > 0) {
         emit_conv_forward(B, a, out, cnt, p, fsplit);
         if (two) emit_conv_forward(B, b, F2, cnt, p, fsplit);
         B.prog->steps.push_back(make_spectral_zt(op, out, two ? F2 : out, out, n, fsplit, cnt, (i64)N, (i64)N, (i64)N));
@@ -974,7 +1011,7 @@ int build_plan(Plan &pl, int kind, const size_t *dims, size_t ndim, size_t batch
         }
         if (rc != NRB_OK) { set_error("shape not supported by this build"); return rc; }
         for (const Step &st : pl.prog[s].steps) {
-            if (!st.is_aux && (!st.pp.tw && radix_plan(st.key.log2n).nst > 1)) { set_error(be_last_error()); return NRB_ERR_CUDA; }
+            if (!st.is_aux && (!(st.is_mid ? st.mp.tw : st.pp.tw) && radix_plan(st.key.log2n).nst > 1)) { set_error(std::string("twiddle table allocation failed: ") + be_last_error()); return NRB_ERR_CUDA; }
         }
         if (B.ws_used > ws) ws = B.ws_used;
         if (B.sched_used > pl.sched_bytes) pl.sched_bytes = B.sched_used;
@@ -1052,6 +1089,11 @@ static int run_program(Program &prog, double2 *const base[4], int arg, void *mai
             fs.ticket = (unsigned long long *)((char *)sched + st.sched_off);
             fs.done = (unsigned *)((char *)sched + st.sched_off + 16);
             rc = be_launch_fused(st.key, pa, st.key2, pb, fs, stream);
+        } else if (st.is_mid) {
+            ConvMidParams mp = st.mp;
+            mp.data = base[st.in.id] + st.in.off;
+            mp.b = st.b.id == BUF_NONE ? nullptr : base[st.b.id] + st.b.off;
+            rc = be_launch_conv_mid(st.key.log2n, mp, st.ntiles, stream);
         } else if (st.is_aux) {
             AuxParams ap = st.ap;
             ap.a = st.in.id == BUF_NONE ? nullptr : base[st.in.id] + st.in.off;
@@ -1146,6 +1188,12 @@ int describe_launch(const Plan &pl, int isign, int idx, char *name, size_t cap, 
         // the pair reads the volume once and writes it once (the intermediate stays in L2)
         const double vol = (double)st.fs.units * (double)st.fs.ta * (double)(1 << tile_log2(st.key.log2n, st.key.layout));
         b = 2.0 * 16.0 * vol + 16.0 * (double)(st.key.layout == LAYOUT_ROW ? st.pp.q_end - st.pp.q_begin : st.pp2.q_end - st.pp2.q_begin);
+    } else if (st.is_mid) {
+        snprintf(buf, sizeof(buf), "conv_mid_n%d_f%d_op%d", 1 << st.key.log2n, st.mp.f, st.mp.op);
+        const double pts = (double)st.mp.count * (double)((u64)1 << (st.key.log2n + st.mp.f));
+        // the signals' intermediate is read and written once; the second operand is read once (per signal, or once
+        // for the whole batch when it is shared)
+        b = 2.0 * 16.0 * pts + (st.mp.op == SPEC_AUTOCORREL ? 0.0 : 16.0 * (st.mp.b_stride ? pts : pts / (double)st.mp.count));
     } else if (st.is_aux) {
         static const char *names[AUX_KIND_COUNT] = {"untangle", "spectral", "pad_response", "correl_direct", "fill", "spectral_z",
                                                     "signal", "wait", "reduce", "stats_final", "normalize", "power", "pack2",

@@ -18,6 +18,9 @@ int be_launch_aux(const AuxParams &a, void *stream);
 bool be_fused_available(const KernelKey &a, const KernelKey &b);
 int be_launch_fused(const KernelKey &ka, const PassParams &pa, const KernelKey &kb, const PassParams &pb, const FuseSched &fs,
                     void *stream);
+// fused middle of the long-line convlv / correl pipeline (rows of 2^log2rest points); available for the built lengths
+bool be_conv_mid_available(int log2rest);
+int be_launch_conv_mid(int log2rest, const ConvMidParams &m, u64 ntiles, void *stream);
 int be_malloc(void **p, size_t bytes);
 int be_free(void *p);
 int be_memset(void *p, int value, size_t bytes, void *stream);
@@ -66,6 +69,8 @@ struct Step {
     u64 ntiles;
     BufRef in, out, speq, b;
     bool patch_pad_mode;   // AUX_PAD_RESPONSE: op comes from exec's `arg`
+    bool is_mid;           // fused conv middle: mp, in = data (in place), b = second operand; key.log2n = log2 REST
+    ConvMidParams mp;
     int lane;              // 0 = the caller's stream; 1 = the plan's side stream (small independent work, see SideLane)
     // fused pair: (key, pp, in/out/speq) is pass A, the *2 members are pass B
     bool is_fused;
@@ -74,7 +79,7 @@ struct Step {
     BufRef in2, out2, speq2;
     FuseSched fs;          // counters live in the plan's scheduler scratch (sched_off = element offset)
     size_t sched_off;
-    Step() : is_aux(false), key{0, 0, 0, 0}, pp(), ap(), ntiles(0), patch_pad_mode(false), lane(0), is_fused(false),
+    Step() : is_aux(false), key{0, 0, 0, 0}, pp(), ap(), ntiles(0), patch_pad_mode(false), is_mid(false), mp(), lane(0), is_fused(false),
              key2{0, 0, 0, 0}, pp2(), fs{nullptr, nullptr, 0, 0, 0, 0}, sched_off(0) {}
 };
 
@@ -100,6 +105,8 @@ struct Tunables {
     int conv_transposed;   // convlv/correl with lines longer than a tile: two passes per transform and the spectrum in
                            // transposed order instead of three natural-order passes (NRB_CONV_TRANSPOSED, default 1)
     int prefetch_dist;     // tiles ahead whose input every CTA prefetches into L2 (NRB_PREFETCH_DIST; 0 = off, -1 = per-kernel policy, default)
+    int conv_fused_mid;    // long-line convlv / correl: contiguous forward pass + spectral step + contiguous inverse pass in one kernel
+                           // (NRB_CONV_FUSED_MID, default 0: not measured yet)
     int speq_side;         // rlft3: run the speq-plane passes on the plan's side stream (NRB_SPEQ_SIDE, default 0: not measured yet)
     int simple_addr;       // 1: passes whose element index is not split use the cheap addressing path (NRB_SIMPLE_ADDR, default 1)
     int big_row_mask;      // bit log2n set: contiguous lines of 2^log2n points use the big-tile pass of fft_pass2.cuh (NRB_BIG_ROW_MASK)

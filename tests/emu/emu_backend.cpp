@@ -17,6 +17,7 @@
 
 #include "../../numrs_b200/csrc/aux_kernels.cuh"
 #include "../../numrs_b200/csrc/fft_pass2.cuh"
+#include "../../numrs_b200/csrc/conv_mid.cuh"
 #include "../../numrs_b200/csrc/plan.h"
 
 namespace nrb_emu {
@@ -220,6 +221,44 @@ int be_launch_pass(const KernelKey &key, const PassParams &p_in, u64 ntiles, voi
     return 0;
 }
 
+template <int LOG2R> static void mid_body(const void *p, double2 *sm, unsigned tile, int tid)
+{
+    conv_mid_cta<LOG2R>(*(const ConvMidParams *)p, sm, tile, tid);
+}
+bool be_conv_mid_available(int log2rest) { return log2rest == 4 || log2rest == 6 || log2rest == 12; }   // as k_mid.cu
+static long g_mid_launches = 0;
+int be_launch_conv_mid(int log2rest, const ConvMidParams &m, u64 ntiles, void *)
+{
+    nrb_emu::BodyFn fn = nullptr;
+    int nt = 0;
+    size_t smem = 0;
+    switch (log2rest) {
+    case 4: fn = mid_body<4>; nt = GeoM<4>::NT; smem = GeoM<4>::SMEM_BYTES / 16; break;
+    case 6: fn = mid_body<6>; nt = GeoM<6>::NT; smem = GeoM<6>::SMEM_BYTES / 16; break;
+    case 12: fn = mid_body<12>; nt = GeoM<12>::NT; smem = GeoM<12>::SMEM_BYTES / 16; break;
+    default: g_emu_err = "conv_mid kernel not built for this row length"; return -1;
+    }
+    ++g_mid_launches;
+#pragma omp parallel
+    {
+        nrb_emu::Cta c;
+        c.fibers.resize(nt);
+        c.stacks.resize((size_t)nt * nrb_emu::kStack);
+        c.done.resize(nt);
+        std::vector<double> shfl_buf(nt + 32, 0.0);
+        nrb_emu::t_shfl = &shfl_buf;
+        c.body = fn;
+        c.params = &m;
+#pragma omp for schedule(dynamic)
+        for (long long t = 0; t < (long long)ntiles; ++t) {
+            c.tile = (unsigned)t;
+            c.smem.assign(smem, make_double2(__builtin_nan(""), __builtin_nan("")));
+            nrb_emu::run_cta(c, nt);
+        }
+    }
+    return 0;
+}
+
 bool be_fused_available(const KernelKey &a, const KernelKey &b)
 {
     // same set as the CUDA build (k_fused_*.cu): z in {128,256,512} (ROW REAL), y in {256,512,1024} (COL PLAIN)
@@ -302,4 +341,4 @@ void be_host_free(void *p) { free(p); }
 
 } // namespace nrb
 
-extern "C" long nrb_emu_launch_count(int aux) { return aux == 3 ? nrb::g_simple_launches : aux == 2 ? nrb::g_big_launches : aux ? nrb::g_aux_launches : nrb::g_pass_launches; }
+extern "C" long nrb_emu_launch_count(int aux) { return aux == 4 ? nrb::g_mid_launches : aux == 3 ? nrb::g_simple_launches : aux == 2 ? nrb::g_big_launches : aux ? nrb::g_aux_launches : nrb::g_pass_launches; }

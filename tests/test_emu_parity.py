@@ -546,3 +546,32 @@ def test_rlft3_speq_passes_on_the_side_lane(emu, shp):
     cases.check_rlft3(emu, shp)
     plan = emu.plan_create(nb.KIND_RLFT3, list(shp))
     assert plan.num_launches(1) == plan.num_launches(-1)
+
+
+@pytest.mark.parametrize("row_max,n", [(4, 64), (4, 1024), (6, 256), (6, 4096), (12, 1 << 14), (12, 1 << 15)])
+def test_conv_fused_middle_kernel(emu, row_max, n):
+    """conv_mid.cuh: contiguous forward pass + spectral step + contiguous inverse pass of a row pair in one kernel.
+    Rows of 16 / 64 / 4096 points (the built lengths), F = 2 (only the self-paired rows) and larger."""
+    emu.set_option("row_max_log2", row_max)
+    emu.set_option("conv_fused_mid", 1)
+    before = _emu_count(emu, 4)
+    cases.check_convlv(emu, n, min(n, 33))            # multiply (both paddings) and divide
+    cases.check_correl(emu, n)
+    cases.check_autocorrel_fast(emu, n)
+    sigs = [cases.gen(50 + b, n) for b in range(3)]
+    r = cases.gen(60, 7) / 8
+    for g, a in zip(nb.convlv_batch(sigs, r, 1, 0, emu), sigs):
+        assert cases.rel(g, O.convlv(a, r, 1, 0)[1]) <= cases.tol(n)
+    pairs = [(cases.gen(70 + b, n), cases.gen(80 + b, n)) for b in range(3)]
+    for g, (a, b) in zip(nb.correl_batch(pairs, emu), pairs):
+        assert cases.rel(g, O.correl(a, b)[1]) <= cases.tol(n)
+    assert _emu_count(emu, 4) - before == 7           # every long-line program went through the fused kernel
+
+
+def test_conv_fused_middle_falls_back_when_not_built(emu):
+    emu.set_option("row_max_log2", 5)                 # rows of 32 points: no fused kernel for that length
+    emu.set_option("conv_fused_mid", 1)
+    before = _emu_count(emu, 4)
+    cases.check_convlv(emu, 1024, 9)
+    cases.check_correl(emu, 1024)
+    assert _emu_count(emu, 4) == before

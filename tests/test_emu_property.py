@@ -86,9 +86,10 @@ def test_rlft3_any_shape(emu, l1, l2, l3, isign, side, col_max):
 
 @SET
 @given(lg=st.integers(1, 13), m_frac=st.floats(0.0, 1.0), isign=st.sampled_from([1, -1]), pad=st.sampled_from([0, 1]),
-       count=st.integers(1, 3), transposed=st.integers(0, 1), row_max=st.integers(4, 13))
-def test_convlv_any_response_length(emu, lg, m_frac, isign, pad, count, transposed, row_max):
+       count=st.integers(1, 3), transposed=st.integers(0, 1), row_max=st.integers(4, 13), fused=st.integers(0, 1))
+def test_convlv_any_response_length(emu, lg, m_frac, isign, pad, count, transposed, row_max, fused):
     emu.set_option("conv_transposed", transposed)
+    emu.set_option("conv_fused_mid", fused)
     emu.set_option("row_max_log2", row_max)
     n = 1 << lg
     m = max(1, min(n, int(round(m_frac * n))))
@@ -102,8 +103,11 @@ def test_convlv_any_response_length(emu, lg, m_frac, isign, pad, count, transpos
 
 
 @SET
-@given(n=st.one_of(st.integers(1, 40), st.sampled_from([64, 256, 1024, 4096])), count=st.integers(1, 3))
-def test_correl_direct_and_fft_branches(emu, n, count):
+@given(n=st.one_of(st.integers(1, 40), st.sampled_from([64, 256, 1024, 4096])), count=st.integers(1, 3),
+       row_max=st.sampled_from([4, 6, 13]), fused=st.integers(0, 1))
+def test_correl_direct_and_fft_branches(emu, n, count, row_max, fused):
+    emu.set_option("row_max_log2", row_max)
+    emu.set_option("conv_fused_mid", fused)
     if n > 32 and n & (n - 1):
         with pytest.raises(nb.CorrelError):
             nb.correl(np.ones(n), np.ones(n), emu)          # n > 32 must be a power of two (documented restriction)

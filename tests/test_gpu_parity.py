@@ -433,3 +433,27 @@ def test_rlft3_side_lane_device_resident_back_to_back(gpu):
     torch.cuda.synchronize()
     assert float(torch.linalg.norm(x - ref) / torch.linalg.norm(ref)) <= 20 * cases.tol(n)
     plan.destroy()
+
+
+@pytest.mark.gpu
+@experimental
+@pytest.mark.parametrize("n", [1 << 15, 1 << 16, 1 << 20])
+def test_conv_fused_middle_kernel(gpu, n):
+    gpu.set_option("conv_fused_mid", 1)
+    cases.check_convlv(gpu, n, 4096)
+    cases.check_correl(gpu, n)
+    cases.check_autocorrel_fast(gpu, n)
+
+
+@pytest.mark.gpu
+@experimental
+def test_conv_fused_middle_matches_three_launch_pipeline_at_full_size(gpu):
+    n, m = 1 << 22, 4096
+    sigs = [cases.gen(1004, n, b * n) for b in range(2)]
+    r = cases.gen(1005, m) / 64
+    out = []
+    for flag in (0, 1):
+        gpu.set_option("conv_fused_mid", flag)
+        out.append((nb.convlv_batch(sigs, r, 1, 0, gpu), nb.correl_batch([(sigs[0], sigs[1])], gpu)))
+    for a, b in zip(out[0][0] + out[0][1], out[1][0] + out[1][1]):
+        assert cases.rel(b, a) <= 1e-13
