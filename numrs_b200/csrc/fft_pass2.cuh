@@ -1,15 +1,21 @@
 // fft_pass2.cuh -- the "big tile" FFT pass: persistent CTAs, asynchronous prefetch of the next tile into a
 // thread-private shared-memory landing zone, and a shared-memory exchange that moves re and im parts separately.
+// AN EXPERIMENT, OFF BY DEFAULT (big_row_mask / big_col_mask): measured no faster than fft_pass.cuh, see below.
 //
-// Why (profiles/r01_prefetch_row_bench.txt, profiles/r01_tuning.md #33): a tile of 8192 points fills the register
+// Idea (profiles/r01_prefetch_row_bench.txt, profiles/r01_tuning.md #34): a tile of 8192 points fills the register
 // file of an SM (512 threads x 16 points), so only ONE CTA is resident and nothing overlaps its global loads with
-// its shared-memory stages: the plain pass (fft_pass.cuh) runs N = 8192 lines at 3.4-3.6 TB/s, exactly what its
-// memory skeleton does (3.8 TB/s).  Here every thread issues cp.async copies of the 16 elements IT will need for
-// the NEXT tile into 16 private slots while the current tile is in its exchange rounds; it later waits for its
-// own copies only (no barrier, no mbarrier: nobody else touches those slots).  The landing zone costs TILE x 16
-// bytes, which is paid for by exchanging the re and im parts one after the other through a buffer of half the
-// size (8-byte accesses, same padding rule): 128 KiB + 72 KiB = 200 KiB for an 8192-point tile.
-// Skeleton: 3.79 -> 5.33 TB/s.
+// its shared-memory stages.  Here every thread issues cp.async copies of the 16 elements IT will need for the NEXT
+// tile into 16 private slots while the current tile is in its exchange rounds; it later waits for its own copies
+// only (no barrier, no mbarrier: nobody else touches those slots).  The landing zone costs TILE x 16 bytes, which is
+// paid for by exchanging the re and im parts one after the other through a buffer of half the size (8-byte
+// accesses; a per-exchange XOR swizzle keeps the 16-lane phases conflict-free): 128 KiB + 64 KiB for an 8192-point
+// tile.  The memory skeleton of this structure runs at 5.33 TB/s against 3.79 TB/s for the plain pass's skeleton.
+//
+// Result (profiles/r01_tuning.md #35, profiles/r01_big_tile_ab_{1,2,3}.txt): with the math back the kernel does
+// 3.53 TB/s on N = 8192 against 3.56 TB/s for fft_pass.cuh, and is slower on every other length: those passes are
+// bound by instruction issue and latency at 16 warps per SM, not by exposed load latency, and the split exchange
+// doubles the shared-memory instructions.  Kept, with its tests, as the record of that experiment and because its
+// stage helpers (Stage2, v2_compute) carry the fused convolution middle (conv_mid.cuh).
 //
 // Same mathematics, addressing (PassParams) and twiddle tables as fft_pass.cuh: Stockham autosort, radix plan of
 // nrb_common.h, first stage fed from the landing zone, last stage stores to global memory.
