@@ -575,3 +575,27 @@ def test_conv_fused_middle_falls_back_when_not_built(emu):
     cases.check_convlv(emu, 1024, 9)
     cases.check_correl(emu, 1024)
     assert _emu_count(emu, 4) == before
+
+
+def test_thread_contexts_are_released_at_thread_exit_and_by_shutdown(emu):
+    """Every calling thread owns a stream and staging buffers (api.cpp ThreadCtx): short-lived threads must be able to
+    come and go, nrb_shutdown releases what is left, and the library stays usable afterwards."""
+    import threading
+    errs = []
+
+    def work(i):
+        try:
+            x = cases.gen(i, 2 * 256)
+            ref = O.four1(x.copy(), 256, 1)
+            nb.four1(x, 256, 1, emu)
+            assert cases.rel(x, ref) <= cases.tol(256)
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+
+    for _ in range(4):
+        ts = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+    assert not errs
+    emu.shutdown()
+    cases.check_four1(emu, 64)
