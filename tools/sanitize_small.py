@@ -59,4 +59,29 @@ L.set_option("prefetch_dist", 3)
 cases.check_rlft3(L, (16, 8, 32))
 cases.check_four1(L, 4096)
 L.set_option("prefetch_dist", -1)
+# kernels added after the first sanitizer run: cheap addressing path, big-tile pass, fused convolution middle, side lane,
+# batched twofft
+for flag in (0, 1):
+    L.set_option("simple_addr", flag)
+    for shape in ((4, 8192), (512, 32), (1024, 8, 2)):
+        cases.check_fourn(L, shape)
+L.set_option("big_row_mask", (1 << 11) | (1 << 12) | (1 << 13))
+L.set_option("big_col_mask", (1 << 9) | (1 << 10))
+cases.check_four1_batch(L, 8192, 151)
+cases.check_four1_batch(L, 2048, 301)
+cases.check_fourn(L, (1024, 64))
+cases.check_four1(L, 1 << 19)
+L.set_option("big_row_mask", 0)
+L.set_option("big_col_mask", 0)
+L.set_option("conv_fused_mid", 1)
+for n in (1 << 15, 1 << 16):
+    cases.check_convlv(L, n, 100)
+    cases.check_correl(L, n)
+    cases.check_autocorrel_fast(L, n)
+L.set_option("conv_fused_mid", 0)
+L.set_option("speq_side", 1)
+cases.check_rlft3(L, (16, 8, 32))
+cases.check_rlft3(L, (64, 64, 64))
+L.set_option("speq_side", 0)
+cases.check_twofft_batch(L, [64, 4096, 64, 2])
 print("sanitize_small: all parity checks passed")
