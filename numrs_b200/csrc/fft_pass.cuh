@@ -36,6 +36,12 @@
 #ifndef NRB_TW_POWERS_COL
 #define NRB_TW_POWERS_COL 1
 #endif
+// radix-8 twiddle powers: 1 = all built from one table load (6 complex products), 3 = w, w^2 and w^4 loaded, the other
+// four built from them (4 complex products, 8 fewer FP64 instructions per butterfly, 2 more L1 hits).  Not measured yet:
+// build a variant with -DNRB_TW_LOADS=3 and compare (the passes are issue / latency bound, FP64 is ~40 % of their mix).
+#ifndef NRB_TW_LOADS
+#define NRB_TW_LOADS 1
+#endif
 #ifndef NRB_PRE_OWN
 #define NRB_PRE_OWN 0
 #endif
@@ -396,6 +402,14 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
                 // the other powers with complex multiplies on the half-idle FP64 pipe (<= 3 products deep)
                 double2 w[R];
                 w[1] = NRB_LDG(tp);
+                if (NRB_TW_LOADS == 3 && R == 8) {
+                    w[2] = NRB_LDG(tp + 1);
+                    w[4] = NRB_LDG(tp + 3);
+                    w[3] = cmul(w[2], w[1]);
+                    w[5] = cmul(w[4], w[1]);
+                    w[6] = cmul(w[4], w[2]);
+                    w[7] = cmul(w[4], w[3]);
+                } else {
                 w[2] = cmul(w[1], w[1]);
                 w[3] = cmul(w[2], w[1]);
                 if (R >= 8) {
@@ -403,6 +417,7 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
                     w[5] = cmul(w[4], w[1]);
                     w[6] = cmul(w[3], w[3]);
                     w[7] = cmul(w[4], w[3]);
+                }
                 }
                 if (R >= 16) {
 #pragma unroll
