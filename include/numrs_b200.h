@@ -55,7 +55,8 @@ const char *nrb_version(void);
 const char *nrb_last_error(void);      /* thread-local, never NULL */
 int  nrb_device_count(void);           /* number of CUDA devices, 0 if none */
 int  nrb_set_device(int device);       /* device used by the calling thread */
-int  nrb_shutdown(void);               /* frees cached plans / scratch of all threads */
+int  nrb_shutdown(void);               /* frees cached plans, twiddle tables and the staging buffers / streams of every
+                                          thread that made host-slice calls; no other nrb_* call may be in flight */
 /* Planner tunables (affect plans created afterwards; cached host-call plans are dropped):
  *   "col_max_log2"   longest strided-axis FFT done in one pass          (default 10)
  *   "row_max_log2"   longest contiguous FFT done in one pass            (default 13)
@@ -69,8 +70,16 @@ int  nrb_shutdown(void);               /* frees cached plans / scratch of all th
  *   "prefetch_dist"     tiles ahead whose input every CTA prefetches into L2 (-1 = per-kernel policy, 0 = off)
  *   "xchg_grid_cap"     pipelined slab exchange: CTAs of a peer-store pass (0 = one per tile); fewer CTAs leave SM
  *                       slots to the local pass running beside it on the second stream
- * Environment overrides at load time: NRB_COL_MAX_LOG2, NRB_ROW_MAX_LOG2, NRB_L2_GROUP_MB,
- * NRB_BATCH_GROUP_MB. */
+ *   "simple_addr"       1 (default): passes whose element index is not split take the cheap addressing code path where it
+ *                       is built (contiguous 8192-point lines, strided 512 / 1024-point lines); 0 = general path (A/B)
+ *   "conv_fused_mid"    long-line convlv / correl / autocorrel_fast: contiguous forward pass + spectral step + contiguous
+ *                       inverse pass of a row pair in ONE kernel, 5 -> 3 passes per signal (default 0: not measured yet)
+ *   "speq_side"         rlft3: the four small speq-plane launches run on a second stream beside the data passes
+ *                       (default 0: not measured yet)
+ *   "big_row_mask" / "big_col_mask"  bit log2(n) set: lines of n points use the big-tile prefetching pass (default 0:
+ *                       measured no faster, kept as an experiment)
+ * Environment overrides at load time: NRB_COL_MAX_LOG2, NRB_ROW_MAX_LOG2, NRB_L2_GROUP_MB, NRB_BATCH_GROUP_MB,
+ * NRB_SIMPLE_ADDR, NRB_CONV_FUSED_MID, NRB_SPEQ_SIDE, NRB_BIG_ROW_MASK, NRB_BIG_COL_MASK. */
 int  nrb_set_option(const char *name, long value);
 /* pinned host memory, so host-slice calls copy at full PCIe rate (optional) */
 void *nrb_host_alloc(size_t bytes);
