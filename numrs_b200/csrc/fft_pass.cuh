@@ -279,7 +279,7 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
     constexpr int NB = G::N / R;           // butterflies per line
     constexpr int BPT = G::PPT / R;        // butterflies per thread
     static_assert(BPT >= 1, "radix larger than points per thread");
-    constexpr bool FAST = SIMPLE && simple_ok<LOG2N, LAYOUT>() && VARIANT == VAR_PLAIN;
+    constexpr bool FAST = SIMPLE && simple_ok<LOG2N, LAYOUT>() && (VARIANT == VAR_PLAIN || VARIANT == VAR_XPOSE);
     // ROW shared-memory index n + (n >> 3): for the strides of a butterfly's legs the pad term is a compile-time
     // constant -- phys(l, a + r*D) = phys(l, a) + r*D + (r*D >> 3) whenever D is a multiple of 8 or (writes) a + r*D
     // stays inside the 8-block of a (checked exhaustively for every radix plan) -- so the legs are immediate offsets
@@ -341,7 +341,7 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
                         }
                     }
                 }
-            } else if (!FAST) {
+            } else if (!(FAST && SRC_G)) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     double2 x = make_double2(0.0, 0.0);
@@ -617,12 +617,13 @@ NRB_DEV void fft_pass_body(const PassParams &P, double2 *sm, unsigned tile, int 
         // COL layout; last stage to shared memory, then row-like (line-contiguous) store with the
         // four-step twiddle W^(q1(l)*k).  A thread's elements share k (C distinct values when N > NT)
         // and walk the lines with a fixed step D, so the twiddle is a geometric sequence per k.
-        StageRunner<LOG2N, LAYOUT, DIR, VARIANT, 0, true, false>::run(P, sm, tile, tid);
+        StageRunner<LOG2N, LAYOUT, DIR, VARIANT, 0, true, false, SIMPLE>::run(P, sm, tile, tid);
         constexpr int C = (G::N > G::NT) ? G::N / G::NT : 1;
         constexpr int D = (G::NT >= G::N) ? G::NT / G::N : 1;
         constexpr int E = G::PPT / C;
         const u64 q_tile = P.q_begin + (u64)tile * G::L;
-        const bool geometric = P.tw_on && P.logB == 0 && ((1ull << P.logA) >= (u64)G::L);   // no wrap of q1 inside the tile
+        const bool linear = P.logB == 0 && ((1ull << P.logA) >= (u64)G::L);   // no wrap of q1 inside the tile
+        const bool geometric = P.tw_on && linear;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const int idx0 = tid + c * G::NT;
@@ -631,6 +632,22 @@ NRB_DEV void fft_pass_body(const PassParams &P, double2 *sm, unsigned tile, int 
             if (geometric) {
                 tw = fourstep_tw_m(P, line_q1(P, q_tile + (u64)l0) * (unsigned)k);
                 tw_step = fourstep_tw_m(P, (unsigned)(D * k));
+            }
+            if (SIMPLE && linear) {
+                // the lines of a tile advance q1 only: one line base, then a fixed step per line (SIMPLE, fft_stage)
+                double2 *dst = P.out + line_base(q_tile + (u64)l0, P.out_s0, P.out_s1, P.out_s2, P.logA, P.logB) + (i64)k * P.out_es;
+                const i64 step = (i64)D * P.out_s1;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int l = l0 + e * D;
+                    if (q_tile + (u64)l < P.q_end) {
+                        double2 y = sm[G::phys(l, k)];
+                        if (geometric) y = cmul(y, tw);
+                        NRB_STS(dst + (i64)e * step, io_swap<DIR>(y));
+                    }
+                    tw = cmul(tw, tw_step);
+                }
+                continue;
             }
 #pragma unroll
             for (int e = 0; e < E; ++e) {

@@ -48,7 +48,7 @@ fft_pass_kernel(const __grid_constant__ PassParams P, const unsigned ntiles)
     for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         if (P.prefetch_dist > 0 && tile + (unsigned)P.prefetch_dist < ntiles)
             prefetch_tile<LOG2N, LAYOUT, VARIANT>(P, tile + (unsigned)P.prefetch_dist, (int)threadIdx.x);
-        if constexpr (VARIANT == VAR_PLAIN && simple_built(LOG2N, LAYOUT)) {
+        if constexpr (simple_built(LOG2N, LAYOUT, VARIANT)) {
             if (P.simple) fft_pass_body<LOG2N, LAYOUT, DIR, VARIANT, true>(P, nrb_smem, tile, (int)threadIdx.x);
             else fft_pass_body<LOG2N, LAYOUT, DIR, VARIANT, false>(P, nrb_smem, tile, (int)threadIdx.x);
         } else {

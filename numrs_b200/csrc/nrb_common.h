@@ -106,9 +106,16 @@ NRB_HD constexpr int points_per_thread(int layout, int log2n)
 #ifndef NRB_SIMPLE_COL_MASK
 #define NRB_SIMPLE_COL_MASK ((1 << 9) | (1 << 10))
 #endif
-NRB_HD constexpr bool simple_built(int log2n, int layout)
+// the transposing (XPOSE) passes: cheap addressing for the strided loads and the line-contiguous store; not measured
+// yet, so no length is built by default (next A/B: -DNRB_SIMPLE_XPOSE_MASK=1024 for the first pass of a 2^20 transform)
+#ifndef NRB_SIMPLE_XPOSE_MASK
+#define NRB_SIMPLE_XPOSE_MASK 0
+#endif
+NRB_HD constexpr bool simple_built(int log2n, int layout, int variant = 0 /* VAR_PLAIN */)
 {
-    return (((layout == 0 /* LAYOUT_ROW */ ? NRB_SIMPLE_ROW_MASK : NRB_SIMPLE_COL_MASK) >> log2n) & 1) != 0;
+    return variant == 2 /* VAR_XPOSE */ ? ((NRB_SIMPLE_XPOSE_MASK >> log2n) & 1) != 0
+         : variant == 0 ? (((layout == 0 /* LAYOUT_ROW */ ? NRB_SIMPLE_ROW_MASK : NRB_SIMPLE_COL_MASK) >> log2n) & 1) != 0
+                        : false;
 }
 
 // ---- radix plan per log2(N): stage radices, first stage first ----

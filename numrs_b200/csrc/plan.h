@@ -118,7 +118,7 @@ int set_tunable(const char *name, long value);   // returns 0 if the name is kno
 // can the pass use the cheap addressing path of fft_stage (element offset = n * es, es = 1 for contiguous lines)?
 inline bool pass_is_simple(const KernelKey &key, const PassParams &p)
 {
-    if (!tunables().simple_addr || key.variant != VAR_PLAIN || p.out_peer_on || !simple_built(key.log2n, key.layout)) return false;
+    if (!tunables().simple_addr || p.out_peer_on || !simple_built(key.log2n, key.layout, key.variant)) return false;
     if (p.in_eshift <= kMaxLog2N || p.out_eshift <= kMaxLog2N) return false;   // the element index is split
     if (key.layout == LAYOUT_ROW) return p.in_es == 1 && p.out_es == 1;
     return true;

@@ -94,7 +94,7 @@ template <int LOG2N, int LAYOUT, int DIR, int VARIANT>
 static void body_tpl(const void *p, double2 *sm, unsigned tile, int tid)
 {
     const nrb::PassParams &P = *(const nrb::PassParams *)p;
-    if constexpr (VARIANT == nrb::VAR_PLAIN && nrb::simple_built(LOG2N, LAYOUT)) {
+    if constexpr (nrb::simple_built(LOG2N, LAYOUT, VARIANT)) {
         if (P.simple) { nrb::fft_pass_body<LOG2N, LAYOUT, DIR, VARIANT, true>(P, sm, tile, tid); return; }
     }
     nrb::fft_pass_body<LOG2N, LAYOUT, DIR, VARIANT, false>(P, sm, tile, tid);
