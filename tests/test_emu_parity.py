@@ -599,3 +599,20 @@ def test_thread_contexts_are_released_at_thread_exit_and_by_shutdown(emu):
     assert not errs
     emu.shutdown()
     cases.check_four1(emu, 64)
+
+
+def test_twofft_batch_argument_errors(emu):
+    import ctypes
+    from numrs_b200 import _lib
+    dp = ctypes.POINTER(ctypes.c_double)
+    a = np.zeros(8)
+    f = np.zeros(18)
+    one = lambda x: (dp * 1)(x.ctypes.data_as(dp))      # noqa: E731
+    null = (dp * 1)(None)
+    call = emu.L.nrb_twofft_batch
+    assert call(one(a), one(a), 1, 0, one(f), one(f)) == _lib.NRB_ERR_EMPTY_INPUT        # n = 0
+    assert call(one(a), one(a), 1, 6, one(f), one(f)) == _lib.NRB_ERR_NOT_POW2
+    assert call(one(a), one(a), 0, 8, one(f), one(f)) == 0                               # empty batch
+    assert call(None, one(a), 1, 8, one(f), one(f)) == _lib.NRB_ERR_EMPTY_INPUT
+    assert call(one(a), null, 1, 8, one(f), one(f)) == _lib.NRB_ERR_EMPTY_INPUT          # a null slice inside the batch
+    assert "null" in emu.last_error()
