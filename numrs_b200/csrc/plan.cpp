@@ -1293,28 +1293,37 @@ int build_slab_plan(SlabPlan &sp, size_t nn1, size_t nn2, size_t nn3, int nranks
     AxisMap y_blocks_speq;   // speq part: lines xl, contiguous yl
     y_blocks_speq.on = true; y_blocks_speq.s0 = (i64)Y; y_blocks_speq.es = 1; y_blocks_speq.eshift = ilog2((size_t)Y); y_blocks_speq.es_hi = BLK;
 
+    // speq_side: the speq-plane pass of a stage goes first in program order, on lane 1 (it only depends on what
+    // precedes the stage, or on the z pass), so it runs beside the stage's data pass; run_program joins the lanes
+    // before the z pass of the inverse reads the plane and at the end of every stage (before the exchange barrier)
+    const bool side = tunables().speq_side != 0;
+    auto lane1 = [&](Builder &B, size_t first) { if (side) for (size_t i = first; i < B.prog->steps.size(); ++i) B.prog->steps[i].lane = 1; };
     {   // forward stage 0
         Builder B(&sp.prog[0][0]);
         emit_real(B, SLAB, SLAB, BufRef(), 0, nn1 * Y, p3, +1, REAL_SPEQ, WSPEQ);
+        if (side) { const size_t f0 = B.prog->steps.size(); emit_axis(B, WSPEQ, XCH + SPQ, BufRef(), 1, 0, 1, p1, Y, +1, nullptr, &x_blocks_speq); lane1(B, f0); }
         emit_axis(B, SLAB, XCH, BufRef(), 1, 0, 1, p1, Y * N3, +1, nullptr, &x_blocks);
-        emit_axis(B, WSPEQ, XCH + SPQ, BufRef(), 1, 0, 1, p1, Y, +1, nullptr, &x_blocks_speq);
+        if (!side) emit_axis(B, WSPEQ, XCH + SPQ, BufRef(), 1, 0, 1, p1, Y, +1, nullptr, &x_blocks_speq);
         rc = B.rc ? B.rc : rc;
     }
     {   // forward stage 1
         Builder B(&sp.prog[0][1]);
+        if (side) { emit_axis(B, XCH + SPQ, SPEQ, BufRef(), X, 0, X, p2, 1, +1, &y_blocks_speq, nullptr); lane1(B, 0); }
         emit_axis(B, XCH, SLAB, BufRef(), X, 0, X, p2, N3, +1, &y_blocks, nullptr);
-        emit_axis(B, XCH + SPQ, SPEQ, BufRef(), X, 0, X, p2, 1, +1, &y_blocks_speq, nullptr);
+        if (!side) emit_axis(B, XCH + SPQ, SPEQ, BufRef(), X, 0, X, p2, 1, +1, &y_blocks_speq, nullptr);
         rc = B.rc ? B.rc : rc;
     }
     {   // inverse stage 0
         Builder B(&sp.prog[1][0]);
+        if (side) { emit_axis(B, SPEQ, XCH + SPQ, BufRef(), X, 0, X, p2, 1, -1, nullptr, &y_blocks_speq); lane1(B, 0); }
         emit_axis(B, SLAB, XCH, BufRef(), X, 0, X, p2, N3, -1, nullptr, &y_blocks);
-        emit_axis(B, SPEQ, XCH + SPQ, BufRef(), X, 0, X, p2, 1, -1, nullptr, &y_blocks_speq);
+        if (!side) emit_axis(B, SPEQ, XCH + SPQ, BufRef(), X, 0, X, p2, 1, -1, nullptr, &y_blocks_speq);
         rc = B.rc ? B.rc : rc;
     }
     {   // inverse stage 1
         Builder B(&sp.prog[1][1]);
         emit_axis(B, XCH + SPQ, WSPEQ, BufRef(), 1, 0, 1, p1, Y, -1, &x_blocks_speq, nullptr);
+        lane1(B, 0);
         emit_axis(B, XCH, SLAB, BufRef(), 1, 0, 1, p1, Y * N3, -1, &x_blocks, nullptr);
         emit_real(B, SLAB, SLAB, BufRef(), 0, nn1 * Y, p3, -1, REAL_SPEQ, WSPEQ);
         rc = B.rc ? B.rc : rc;
@@ -1454,6 +1463,7 @@ int slab_set_dma(SlabPlan &sp, int chunks)
 
 void slab_release(SlabPlan &sp)
 {
+    release_side_lane(sp.side);
     if (sp.ws) be_free(sp.ws);
     if (sp.send) be_free(sp.send);
     if (sp.copy_stream) be_stream_destroy(sp.copy_stream);
@@ -1599,11 +1609,11 @@ int exec_slab_stage(SlabPlan &sp, int stage, int isign, double *d_slab, double *
         const i64 BLK = (i64)((sp.nn1 / G) * (sp.nn2 / G) * (sp.nn3 / 2 + 1));
         double2 *const base[4] = {(double2 *)d_slab, (double2 *)d_speq, sp.peers[sp.rank], (double2 *)sp.ws};
         PeerExchange px{sp.peers, (i64)sp.rank * BLK};
-        return run_program(sp.prog[isign == 1 ? 0 : 1][stage], base, 0, stream, nullptr, stage == 0 ? &px : nullptr);
+        return run_program(sp.prog[isign == 1 ? 0 : 1][stage], base, 0, stream, nullptr, stage == 0 ? &px : nullptr, nullptr, &sp.side);
     }
     double2 *const base[4] = {(double2 *)d_slab, (double2 *)d_speq, (double2 *)(stage == 0 ? d_send : d_recv),
                               (double2 *)sp.ws};
-    return run_program(sp.prog[isign == 1 ? 0 : 1][stage], base, 0, stream);
+    return run_program(sp.prog[isign == 1 ? 0 : 1][stage], base, 0, stream, nullptr, nullptr, nullptr, &sp.side);
 }
 
 } // namespace nrb

@@ -185,6 +185,7 @@ struct SlabPlan {
     std::vector<std::string> tl_names;
     size_t ws_elems;
     void *ws;
+    SideLane side;         // speq_side: the small speq-plane passes of a stage run beside its data pass
     double2 *peers[8];     // peer receive buffers (fused exchange); peers[rank] is the local one
     bool fused;
     SlabPlan() : nn1(0), nn2(0), nn3(0), nranks(1), rank(0), chunks(1), dma(false), send(nullptr), copy_stream(nullptr), side_stream(nullptr),

@@ -56,10 +56,12 @@ def run_simulated(L, x, G, isign, speq_in=None, fused=False):
     return slabs, speqs
 
 
+@pytest.mark.parametrize("side", [0, 1])
 @pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("shape,G", [((8, 8, 8), 2), ((16, 16, 8), 4), ((8, 16, 32), 8), ((32, 8, 4), 8), ((4, 4, 2), 4),
                                      ((16, 16, 16), 1)])
-def test_slab_simulated_ranks(emu, shape, G, fused):
+def test_slab_simulated_ranks(emu, shape, G, fused, side):
+    emu.set_option("speq_side", side)      # 1: the speq-plane pass of every stage first, on the side lane
     nn1, nn2, nn3 = shape
     X, Y = nn1 // G, nn2 // G
     x = O.fill_uniform(1006, 0, nn1 * nn2 * nn3).reshape(shape)
