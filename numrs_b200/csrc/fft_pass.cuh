@@ -410,14 +410,14 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
                     w[6] = cmul(w[4], w[2]);
                     w[7] = cmul(w[4], w[3]);
                 } else {
-                w[2] = cmul(w[1], w[1]);
-                w[3] = cmul(w[2], w[1]);
-                if (R >= 8) {
-                    w[4] = cmul(w[2], w[2]);
-                    w[5] = cmul(w[4], w[1]);
-                    w[6] = cmul(w[3], w[3]);
-                    w[7] = cmul(w[4], w[3]);
-                }
+                    w[2] = cmul(w[1], w[1]);
+                    w[3] = cmul(w[2], w[1]);
+                    if (R >= 8) {
+                        w[4] = cmul(w[2], w[2]);
+                        w[5] = cmul(w[4], w[1]);
+                        w[6] = cmul(w[3], w[3]);
+                        w[7] = cmul(w[4], w[3]);
+                    }
                 }
                 if (R >= 16) {
 #pragma unroll
