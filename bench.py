@@ -111,38 +111,52 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     import oracle as O
-    cores = O.num_threads()
+    cores = O.use_all_cores()      # torchrun exports OMP_NUM_THREADS=1: state the thread count instead of inheriting it
     wl = args.workload
-    if wl == "rlft3_512":
-        n = 256
-        x = O.fill_uniform(1006, 0, n ** 3).reshape(n, n, n)
-        s = np.zeros((n, 2 * n))
-        bytes_step = 2 * rlft3_bytes(n, n, n)
+    same_config = True
+    if wl in RLFT3_DIMS:
+        # the full volume the line's config names (a 512^3 forward + inverse takes seconds on the host cores)
+        n1, n2, n3 = RLFT3_DIMS[wl]
+        x = O.fill_uniform(SEEDS[wl], 0, n1 * n2 * n3).reshape(n1, n2, n3)
+        s = np.zeros((n1, 2 * n2))
+        bytes_step = 2 * rlft3_bytes(n1, n2, n3)
 
         def step():
             O.rlft3(x, s, 1, mt=True)
             O.rlft3(x, s, -1, mt=True)
-        sample = f"rlft3 {n}^3 forward+inverse per step (1/8 of the 512^3 volume), oracle port with the reference's loop structure, {cores} OpenMP threads"
+        sample = f"rlft3 {n1}x{n2}x{n3} forward+inverse per step (the full volume), oracle port with the reference's loop structure, {cores} OpenMP threads"
+    elif wl == "fourn3d_512":
+        n = 512
+        x = O.fill_uniform(SEEDS[wl], 0, 2 * n ** 3)
+        bytes_step = 2 * 32.0 * n ** 3
+
+        def step():
+            O.fourn(x, [n, n, n], 1, mt=True)
+            O.fourn(x, [n, n, n], -1, mt=True)
+        sample = f"fourn {n}^3 complex forward+inverse per step (the full volume), {cores} threads"
     elif wl in ("four1_batch", "four1_1m"):
-        nn, cnt = (4096, 1024) if wl == "four1_batch" else (1 << 20, 4)
-        arrs = [O.fill_uniform(1002, b * 2 * nn, 2 * nn) for b in range(cnt)]
+        nn, cnt = (4096, 4096) if wl == "four1_batch" else (1 << 20, 64)
+        arrs = [O.fill_uniform(SEEDS[wl], b * 2 * nn, 2 * nn) for b in range(cnt)]
         bytes_step = 2 * 32.0 * nn * cnt
 
         def step():
             O.fft_batch(arrs, 1, mt=True)
             O.fft_batch(arrs, -1, mt=True)
-        sample = f"fft_batch {cnt} x four1({nn}) forward+inverse per step, {cores} threads (one transform per thread, FFT_1.rs:186)"
+        sample = f"fft_batch {cnt} x four1({nn}) forward+inverse per step (the full batch), {cores} threads (one transform per thread, FFT_1.rs:186)"
     elif wl == "fourn2d":
-        n = 2048
-        x = O.fill_uniform(1003, 0, 2 * n * n)
+        n = 8192
+        x = O.fill_uniform(SEEDS[wl], 0, 2 * n * n)
         bytes_step = 2 * 32.0 * n * n
 
         def step():
             O.fourn(x, [n, n], 1, mt=True)
             O.fourn(x, [n, n], -1, mt=True)
-        sample = f"fourn {n}x{n} forward+inverse per step, {cores} threads"
+        sample = f"fourn {n}x{n} forward+inverse per step (the full matrix), {cores} threads"
     else:
-        n, m, cnt = 1 << 20, 4096, max(2, cores)
+        # 256 signals of 2^22 points would take minutes per step on the host: a bounded sample of full-length signals,
+        # one per thread as the reference's par_iter does (Convolve.rs:246, Correlation.rs:275); GB/s normalises the count
+        n, m, cnt = 1 << 22, 4096, max(2, min(cores, 16))
+        same_config = False
         sigs = [O.fill_uniform(1004, b * n, n) for b in range(cnt)]
         r = O.fill_uniform(1005, 0, m) / 64
         if wl == "convlv":
@@ -156,7 +170,7 @@ def run_reference(args, rank, world):
 
             def step():
                 O.correl_batch(sigs, tm, mt=True)
-        sample = f"{wl}_batch {cnt} x n=2^20, m=4096 per step, {cores} threads (one signal per thread)"
+        sample = f"{wl}_batch {cnt} of the 256 signals, n=2^22, m=4096 per step, {cores} threads (one signal per thread)"
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -167,7 +181,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC[wl], "value": val, "unit": "GB/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": SCALING[wl], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_for(wl, args.gpus),
+            "config": dict(config_for(wl, args.gpus, None), sample_is_full_workload=same_config),
             "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

@@ -55,8 +55,10 @@ const char *nrb_version(void);
 const char *nrb_last_error(void);      /* thread-local, never NULL */
 int  nrb_device_count(void);           /* number of CUDA devices, 0 if none */
 int  nrb_set_device(int device);       /* device used by the calling thread */
-int  nrb_shutdown(void);               /* frees cached plans, twiddle tables and the staging buffers / streams of every
-                                          thread that made host-slice calls; no other nrb_* call may be in flight */
+int  nrb_shutdown(void);               /* frees cached plans, twiddle tables no live plan uses and the staging buffers /
+                                          streams of every thread that made host-slice calls; no other nrb_* call may be
+                                          in flight.  Plans from nrb_plan_create / nrb_slab_create stay valid: each holds a
+                                          reference on the twiddle tables it uses, released by its own destroy call. */
 /* Planner tunables (affect plans created afterwards; cached host-call plans are dropped):
  *   "col_max_log2"   longest strided-axis FFT done in one pass          (default 10)
  *   "row_max_log2"   longest contiguous FFT done in one pass            (default 13)

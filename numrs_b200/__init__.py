@@ -78,6 +78,8 @@ def _panic(L, rc):
 # ---------------------------------------------------------------- FFT_1.rs
 def four1(data, nn, isign, _L=None):
     """FFT_1.rs:5 `four1(data: &mut [f64], nn, isign)`: in place, unnormalised."""
+    # the reference indexes data[..2 * nn] and panics on a shorter slice; the C ABI copies exactly 2 * nn doubles
+    assert data.size >= 2 * nn, "data length must be at least 2 * nn"
     L = _L or lib()
     _panic(L, L.four1(data, nn, isign))
 
@@ -240,6 +242,11 @@ def fourn(data, nn, ndim, isign, _L=None):
     nn = list(nn)
     if ndim == 0 or ndim > len(nn):
         raise ValueError("Invalid dimensions")
+    total = 1
+    for d in nn[:ndim]:
+        total *= int(d)
+    # an in-memory fourn indexes data[..2 * prod(nn)] (panic on a shorter slice); the C ABI copies exactly that many
+    assert total <= 0 or data.size >= 2 * total, "data length must be at least 2 * prod(nn)"
     rc = L.fourn(data, nn, ndim, isign)
     if rc in (_lib.NRB_ERR_INVALID_DIMS, _lib.NRB_ERR_INVALID_ISIGN):
         raise ValueError(L.last_error())
@@ -300,7 +307,11 @@ def rlft3(data, speq, nn1, nn2, nn3, isign, _L=None):
 
 def rlft3_optimized(data, speq, nn1, nn2, nn3, isign, _L=None):
     """Real_FT3.rs:145: flat-slice variant, same result (ledger D5)."""
-    assert isign == 1 or isign == -1 and data.size == nn1 * nn2 * nn3 and speq.size == 2 * nn1 * nn2
+    assert isign in (1, -1), "isign must be 1 or -1"
+    assert data.size == nn1 * nn2 * nn3, "data dimensions mismatch"
+    assert speq.size == 2 * nn1 * nn2, "speq dimensions mismatch"
+    # in place: a non-contiguous view would be transformed in a temporary copy and the result lost
+    assert data.flags["C_CONTIGUOUS"] and speq.flags["C_CONTIGUOUS"], "data and speq must be C-contiguous (as_slice_mut, Real_FT3.rs:33)"
     L = _L or lib()
     _panic(L, L.rlft3(data.reshape(-1), speq.reshape(-1), nn1, nn2, nn3, isign))
 

@@ -1,5 +1,6 @@
 // api.cpp -- the C ABI of include/numrs_b200.h: device-resident plan API and the host-slice
 // drop-in entry points (H2D copy, transform on the device, D2H copy, blocking).
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -82,8 +83,36 @@ struct ThreadCtx {
 };
 thread_local ThreadCtx t_ctx;
 
+// Plan cache of the host-slice entry points: least recently used first out, bounded by entry count and by the device
+// workspace the cached plans own (NRB_PLAN_CACHE_MB, default 16 GiB); plans in use stay alive through their shared_ptr.
+struct CacheEntry { std::shared_ptr<nrb_plan_s> plan; unsigned long long stamp; };
 std::mutex g_cache_mu;
-std::map<std::string, std::shared_ptr<nrb_plan_s>> g_plan_cache;
+std::map<std::string, CacheEntry> g_plan_cache;
+unsigned long long g_cache_clock = 0;
+
+size_t plan_cache_cap_bytes()
+{
+    static const size_t cap = [] {
+        const char *v = getenv("NRB_PLAN_CACHE_MB");
+        const long mb = (v && *v) ? atol(v) : 16384;
+        return (size_t)(mb < 0 ? 0 : mb) << 20;
+    }();
+    return cap;
+}
+
+void cache_evict_locked(size_t incoming_bytes)
+{
+    for (;;) {
+        size_t total = incoming_bytes;
+        auto oldest = g_plan_cache.end();
+        for (auto it = g_plan_cache.begin(); it != g_plan_cache.end(); ++it) {
+            total += it->second.plan->plan.ws_elems * sizeof(double2);
+            if (oldest == g_plan_cache.end() || it->second.stamp < oldest->second.stamp) oldest = it;
+        }
+        if (oldest == g_plan_cache.end() || (g_plan_cache.size() < 64 && total <= plan_cache_cap_bytes())) return;
+        g_plan_cache.erase(oldest);
+    }
+}
 
 int fail(int code, const std::string &msg) { set_error(msg); return code; }
 
@@ -124,13 +153,31 @@ std::shared_ptr<nrb_plan_s> cached_plan(int kind, const size_t *dims, size_t ndi
     for (size_t d = 0; d < ndim; ++d) key += ":" + std::to_string(dims[d]);
     std::lock_guard<std::mutex> lk(g_cache_mu);
     auto it = g_plan_cache.find(key);
-    if (it != g_plan_cache.end()) { *rc = NRB_OK; return it->second; }
+    if (it != g_plan_cache.end()) { *rc = NRB_OK; it->second.stamp = ++g_cache_clock; return it->second.plan; }
     std::shared_ptr<nrb_plan_s> h(new nrb_plan_s());
     *rc = build_plan(h->plan, kind, dims, ndim, batch);
+    if (*rc == NRB_ERR_OOM && !g_plan_cache.empty()) {
+        // the cache itself may be what holds the memory: drop it and try once more
+        g_plan_cache.clear();
+        h.reset(new nrb_plan_s());
+        *rc = build_plan(h->plan, kind, dims, ndim, batch);
+    }
     if (*rc != NRB_OK) return nullptr;
-    if (g_plan_cache.size() >= 64) g_plan_cache.clear();   // bounded; plans in use stay alive through their shared_ptr
-    g_plan_cache[key] = h;
+    cache_evict_locked(h->plan.ws_elems * sizeof(double2));
+    g_plan_cache[key] = CacheEntry{h, ++g_cache_clock};
     return h;
+}
+
+// staging buffer of a host-slice call; on failure the plan cache (which may be what holds the memory) is dropped and the
+// allocation retried once
+int ensure_buf(DevBuf &b, size_t bytes)
+{
+    if (b.ensure(bytes) == 0) return 0;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        g_plan_cache.clear();
+    }
+    return b.ensure(bytes);
 }
 
 int copy_fail(const char *what) { return fail(NRB_ERR_CUDA, std::string(what) + " failed: " + be_last_error()); }
@@ -144,8 +191,8 @@ int run_inplace(int kind, const size_t *dims, size_t ndim, double *const *ptrs, 
     auto h = cached_plan(kind, dims, ndim, count, &rc);
     if (!h) return rc;
     const size_t bytes = doubles * sizeof(double);
-    if (t_ctx.io.ensure(bytes * count) != 0) return fail(NRB_ERR_OOM, std::string("device allocation failed: ") + be_last_error());
-    if (speq && t_ctx.aux.ensure(speq_doubles * sizeof(double)) != 0) return fail(NRB_ERR_OOM, "device allocation failed");
+    if (ensure_buf(t_ctx.io, bytes * count) != 0) return fail(NRB_ERR_OOM, std::string("device allocation failed: ") + be_last_error());
+    if (speq && ensure_buf(t_ctx.aux, speq_doubles * sizeof(double)) != 0) return fail(NRB_ERR_OOM, "device allocation failed");
     void *s = t_ctx.stream;
     char *dio = (char *)t_ctx.io.p;
     // coalesce runs of host slices that are contiguous in memory into one copy
@@ -183,8 +230,8 @@ int run_outofplace(int kind, const size_t *dims, size_t ndim, const double *cons
     auto h = cached_plan(kind, dims, ndim, count, &rc);
     if (!h) return rc;
     const size_t bytes = n * sizeof(double);
-    if (t_ctx.io.ensure(bytes * count) != 0 || t_ctx.out.ensure(bytes * count) != 0 ||
-        t_ctx.aux.ensure(aux_n * sizeof(double) * aux_count) != 0)
+    if (ensure_buf(t_ctx.io, bytes * count) != 0 || ensure_buf(t_ctx.out, bytes * count) != 0 ||
+        ensure_buf(t_ctx.aux, aux_n * sizeof(double) * aux_count) != 0)
         return fail(NRB_ERR_OOM, std::string("device allocation failed: ") + be_last_error());
     void *s = t_ctx.stream;
     for (size_t b = 0; b < count; ++b)
@@ -216,8 +263,8 @@ int run_segments(int kind, const size_t *dims, size_t ndim, size_t batch, const 
     size_t io_d = 0, aux_d = 0;
     for (const Seg &g : io) if (g.dev_off + g.doubles > io_d) io_d = g.dev_off + g.doubles;
     for (const Seg &g : aux) if (g.dev_off + g.doubles > aux_d) aux_d = g.dev_off + g.doubles;
-    if (t_ctx.io.ensure(io_d * sizeof(double)) != 0 || t_ctx.aux.ensure(aux_d * sizeof(double)) != 0 ||
-        t_ctx.out.ensure(out_doubles * sizeof(double)) != 0)
+    if (ensure_buf(t_ctx.io, io_d * sizeof(double)) != 0 || ensure_buf(t_ctx.aux, aux_d * sizeof(double)) != 0 ||
+        ensure_buf(t_ctx.out, out_doubles * sizeof(double)) != 0)
         return fail(NRB_ERR_OOM, std::string("device allocation failed: ") + be_last_error());
     void *s = t_ctx.stream;
     for (const Seg &g : io)

@@ -27,14 +27,20 @@ PassTable &pass_table()
     return t;
 }
 
+// big-tile passes (fft_pass2.cuh, k_big.cu): only in builds made with `make BIG=1`; the shipped library has none, and
+// big_row_mask / big_col_mask then select nothing
+#ifdef NRB_WITH_BIG_TILES
 void register_big(PassTable &);
+#endif
 PassTable &pass2_table()
 {
     static PassTable t;
     static std::once_flag once;
     std::call_once(once, [] {
         memset(&t, 0, sizeof(t));
+#ifdef NRB_WITH_BIG_TILES
         register_big(t);
+#endif
     });
     return t;
 }

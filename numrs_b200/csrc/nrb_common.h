@@ -106,10 +106,10 @@ NRB_HD constexpr int points_per_thread(int layout, int log2n)
 #ifndef NRB_SIMPLE_COL_MASK
 #define NRB_SIMPLE_COL_MASK ((1 << 9) | (1 << 10))
 #endif
-// the transposing (XPOSE) passes: cheap addressing for the strided loads and the line-contiguous store; not measured
-// yet, so no length is built by default (next A/B: -DNRB_SIMPLE_XPOSE_MASK=1024 for the first pass of a 2^20 transform)
+// the transposing (XPOSE) passes: cheap addressing for the strided loads and the line-contiguous store; measured on the
+// first pass of a 2^20 transform: fft_col_xpose_n1024 3 608 -> 3 839 GB/s (profiles/r02_tuning.md #40)
 #ifndef NRB_SIMPLE_XPOSE_MASK
-#define NRB_SIMPLE_XPOSE_MASK 0
+#define NRB_SIMPLE_XPOSE_MASK (1 << 10)
 #endif
 NRB_HD constexpr bool simple_built(int log2n, int layout, int variant = 0 /* VAR_PLAIN */)
 {

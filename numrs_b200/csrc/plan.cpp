@@ -52,8 +52,8 @@ static Tunables &tunables_mut()
         x.prefetch_dist = env_int("NRB_PREFETCH_DIST", -1);
         x.conv_transposed = env_int("NRB_CONV_TRANSPOSED", 1);
         x.simple_addr = env_int("NRB_SIMPLE_ADDR", 1);
-        x.speq_side = env_int("NRB_SPEQ_SIDE", 0);
-        x.conv_fused_mid = env_int("NRB_CONV_FUSED_MID", 0);
+        x.speq_side = env_int("NRB_SPEQ_SIDE", 1);
+        x.conv_fused_mid = env_int("NRB_CONV_FUSED_MID", 1);
         x.big_row_mask = env_int("NRB_BIG_ROW_MASK", 0);
         x.big_col_mask = env_int("NRB_BIG_COL_MASK", 0);
         return x;
@@ -104,7 +104,9 @@ struct TableKey {
     }
 };
 std::mutex g_tab_mu;
-std::map<TableKey, void *> g_tables;
+// never destroyed: at process exit the CUDA context may already be gone, so nothing is freed from a static destructor
+std::map<TableKey, TableRef> &g_tables = *new std::map<TableKey, TableRef>();
+thread_local std::vector<TableRef> *t_table_sink = nullptr;   // the plan being built on this thread (TableScope)
 
 // exp(-2 pi i num / den) with long double trigonometry
 double2 unit_root(u64 num, u64 den)
@@ -129,13 +131,24 @@ const void *get_table(int kind, int log, std::vector<double2> (*gen)(int))
     std::lock_guard<std::mutex> lk(g_tab_mu);
     TableKey key{be_current_device(), kind, log};
     auto it = g_tables.find(key);
-    if (it != g_tables.end()) return it->second;
+    if (it != g_tables.end()) {
+        if (t_table_sink) t_table_sink->push_back(it->second);
+        return it->second.get();
+    }
     std::vector<double2> host = gen(log);
     if (host.empty()) host.push_back(unit_root(0, 1));
     void *d = nullptr;
     if (be_malloc(&d, host.size() * sizeof(double2)) != 0) return nullptr;
-    if (be_h2d(d, host.data(), host.size() * sizeof(double2), nullptr) != 0 || be_sync(nullptr) != 0) return nullptr;
-    g_tables[key] = d;
+    if (be_h2d(d, host.data(), host.size() * sizeof(double2), nullptr) != 0 || be_sync(nullptr) != 0) { be_free(d); return nullptr; }
+    const int dev = key.dev;
+    TableRef ref(d, [dev](void *p) {          // freed when the cache and the last plan using it have let go
+        const int cur = be_current_device();
+        if (cur != dev) be_set_device(dev);
+        be_free(p);
+        if (cur != dev && cur >= 0) be_set_device(cur);
+    });
+    g_tables[key] = ref;
+    if (t_table_sink) t_table_sink->push_back(ref);
     return d;
 }
 
@@ -186,10 +199,13 @@ FourStepTable fourstep_table(int log2m)
 }
 const double2 *real_twiddles(int log2n) { return (const double2 *)get_table(3, log2n, gen_real); }
 
+TableScope::TableScope(std::vector<TableRef> *sink) : prev(t_table_sink) { t_table_sink = sink; }
+TableScope::~TableScope() { t_table_sink = prev; }
+
+// drops the cache's references: tables no live plan points into are freed now, the others with their last plan
 void release_tables()
 {
     std::lock_guard<std::mutex> lk(g_tab_mu);
-    for (auto &kv : g_tables) be_free(kv.second);
     g_tables.clear();
 }
 
@@ -938,6 +954,7 @@ int build_plan(Plan &pl, int kind, const size_t *dims, size_t ndim, size_t batch
     pl.dims.assign(dims, dims + ndim);
     pl.batch = batch;
     pl.device = be_current_device();
+    TableScope tables(&pl.tables);
     int rc = NRB_OK;
     switch (kind) {
     case NRB_KIND_FOUR1:
@@ -1272,6 +1289,7 @@ int build_slab_plan(SlabPlan &sp, size_t nn1, size_t nn2, size_t nn3, int nranks
         return NRB_ERR_INVALID_DIMS;
     }
     sp.nn1 = nn1; sp.nn2 = nn2; sp.nn3 = nn3; sp.nranks = nranks; sp.rank = rank;
+    TableScope tables(&sp.tables);
     const u64 G = (u64)nranks, X = nn1 / G, Y = nn2 / G, N3 = nn3 / 2;
     const int p1 = ilog2(nn1), p2 = ilog2(nn2), p3 = ilog2((size_t)N3);
     if (p1 > tunables().col_max_log2 || p2 > tunables().col_max_log2 || p3 > tunables().row_max_log2) {
@@ -1362,6 +1380,7 @@ int build_chunk_programs(SlabPlan &sp, int chunks, bool dma)
 {
     const u64 G = (u64)sp.nranks, X = sp.nn1 / G, Y = sp.nn2 / G, N3 = sp.nn3 / 2;
     const int p1 = ilog2(sp.nn1), p2 = ilog2(sp.nn2), p3 = ilog2((size_t)N3);
+    TableScope tables(&sp.tables);
     const u64 Zc = N3 / (u64)chunks;
     if (Zc < 1 || Zc * (u64)chunks != N3) { set_error("slab: too many chunks for this nn3"); return NRB_ERR_INVALID_DIMS; }
     const i64 BLK = (i64)(X * Y * (N3 + 1)), SPQ = (i64)(X * Y * N3), PIECE = (i64)(X * Y * Zc);

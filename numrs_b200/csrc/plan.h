@@ -2,6 +2,7 @@
 // Backend-agnostic (the CUDA backend lives in kernels.cu; tests/emu provides a host-thread
 // emulation of the same kernels for index-math validation only).
 #pragma once
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -87,7 +88,15 @@ struct Program {
     std::vector<Step> steps;
 };
 
-// device-resident twiddle tables, cached per device for the life of the process
+// device-resident twiddle tables, cached per device and shared between plans.  A table is reference-counted: the
+// cache holds one reference (dropped by release_tables(), i.e. nrb_shutdown) and every plan built while a TableScope is
+// open holds one for each table its programs point into, so a plan that outlives nrb_shutdown keeps its tables alive.
+typedef std::shared_ptr<void> TableRef;
+struct TableScope {
+    explicit TableScope(std::vector<TableRef> *sink);
+    ~TableScope();
+    std::vector<TableRef> *prev;
+};
 struct FourStepTable { const double2 *lo, *hi; int h; };
 const double2 *stage_twiddles(int log2n);          // packed per-stage tables (nrb_common.h layout)
 FourStepTable fourstep_table(int log2m);           // exp(-2 pi i m / 2^log2m), two-level
@@ -106,8 +115,8 @@ struct Tunables {
                            // transposed order instead of three natural-order passes (NRB_CONV_TRANSPOSED, default 1)
     int prefetch_dist;     // tiles ahead whose input every CTA prefetches into L2 (NRB_PREFETCH_DIST; 0 = off, -1 = per-kernel policy, default)
     int conv_fused_mid;    // long-line convlv / correl: contiguous forward pass + spectral step + contiguous inverse pass in one kernel
-                           // (NRB_CONV_FUSED_MID, default 0: not measured yet)
-    int speq_side;         // rlft3: run the speq-plane passes on the plan's side stream (NRB_SPEQ_SIDE, default 0: not measured yet)
+                           // (NRB_CONV_FUSED_MID, default 1: convlv -3 %, correl -9.5 %, autocorrel_fast -5 % at n = 2^22, profiles/r02_tuning.md #39)
+    int speq_side;         // rlft3: run the speq-plane passes on the plan's side stream (NRB_SPEQ_SIDE, default 1: -0.5 % of the 1-GPU step, profiles/r02_tuning.md #38)
     int simple_addr;       // 1: passes whose element index is not split use the cheap addressing path (NRB_SIMPLE_ADDR, default 1)
     int big_row_mask;      // bit log2n set: contiguous lines of 2^log2n points use the big-tile pass of fft_pass2.cuh (NRB_BIG_ROW_MASK)
     int big_col_mask;      // the same for strided lines (NRB_BIG_COL_MASK)
@@ -150,6 +159,7 @@ struct Plan {
     size_t sched_bytes;
     int device;
     SideLane side;
+    std::vector<TableRef> tables;   // twiddle tables the programs point into
     Plan() : kind(0), batch(1), ws_elems(0), ws(nullptr), sched(nullptr), sched_bytes(0), device(0) {}
 };
 void release_side_lane(SideLane &sl);
@@ -188,6 +198,7 @@ struct SlabPlan {
     SideLane side;         // speq_side: the small speq-plane passes of a stage run beside its data pass
     double2 *peers[8];     // peer receive buffers (fused exchange); peers[rank] is the local one
     bool fused;
+    std::vector<TableRef> tables;   // twiddle tables the programs point into
     SlabPlan() : nn1(0), nn2(0), nn3(0), nranks(1), rank(0), chunks(1), dma(false), send(nullptr), copy_stream(nullptr), side_stream(nullptr),
                  ev_go(nullptr), ev_side(nullptr), ev_copy(nullptr), ev_s0{}, timeline(false), ws_elems(0), ws(nullptr), peers{}, fused(false) {}
 };

@@ -570,6 +570,17 @@ int orc_num_threads(void)
 #endif
 }
 
+/* bench.py's reference arm: launchers such as torchrun export OMP_NUM_THREADS=1 to their children, which
+ * would silently time the "all host cores" baseline on one core; the caller states the count instead. */
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ==========================================================================================
  * "Next" rows of SURVEY.md section 8(f): callers on either side of the hot path.
  * ======================================================================================== */

@@ -78,6 +78,8 @@ def lib():
         L.orc_sinft.restype = None
         L.orc_num_threads.argtypes = []
         L.orc_num_threads.restype = ctypes.c_int
+        L.orc_set_num_threads.argtypes = [ctypes.c_int]
+        L.orc_set_num_threads.restype = None
         _LIB = L
     return _LIB
 
@@ -250,3 +252,13 @@ def sinft(y, n):
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def use_all_cores():
+    """Use every core this process may run on, whatever OMP_NUM_THREADS says (torchrun exports 1); returns the count."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().orc_set_num_threads(n)
+    return num_threads()

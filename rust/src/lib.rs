@@ -70,10 +70,17 @@ pub mod Fourn {
         if ndim == 0 || ndim > nn.len() {
             return Err(Error::new(ErrorKind::InvalidInput, "Invalid dimensions"));
         }
-        let total: usize = nn[..ndim].iter().product();
+        let total = nn[..ndim]
+            .iter()
+            .try_fold(1usize, |acc, &d| acc.checked_mul(d))
+            .ok_or_else(|| Error::new(ErrorKind::InvalidInput, "Invalid dimensions"))?;
         if total == 0 {
             return Err(Error::new(ErrorKind::InvalidInput, "Empty dimensions"));
         }
+        // nrb_fourn copies exactly 2 * total doubles from and to the slice: a shorter slice must panic here (as the
+        // reference's indexing would), never reach the C side
+        let needed = total.checked_mul(2).expect("2 * prod(nn) overflows usize");
+        assert!(data.len() >= needed, "data length must be at least 2 * prod(nn)");
         let rc = unsafe { nrb_fourn(data.as_mut_ptr(), nn.as_ptr(), ndim, isign) };
         match rc {
             NRB_OK => Ok(()),

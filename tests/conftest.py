@@ -48,7 +48,7 @@ def _reset_options(request):
             L.set_option("conv_transposed", 1)
             L.set_option("xchg_grid_cap", 0)
             L.set_option("simple_addr", 1)
-            L.set_option("speq_side", 0)
-            L.set_option("conv_fused_mid", 0)
+            L.set_option("speq_side", 1)
+            L.set_option("conv_fused_mid", 1)
             L.set_option("big_row_mask", 0)
             L.set_option("big_col_mask", 0)

@@ -601,6 +601,26 @@ def test_thread_contexts_are_released_at_thread_exit_and_by_shutdown(emu):
     cases.check_four1(emu, 64)
 
 
+def test_plans_survive_shutdown(emu):
+    """nrb_shutdown drops the cache's twiddle tables; a plan created earlier holds its own references (plan.h TableRef),
+    so executing it afterwards -- with other sizes planned in between, which reallocate tables -- is still exact."""
+    nn = 512
+    plan = emu.plan_create(nb.KIND_FOUR1, [nn])
+    emu.shutdown()
+    for other in (64, 256, 1024, 4096):
+        cases.check_four1(emu, other)
+    x = cases.gen(77, 2 * nn)
+    ref = O.four1(x.copy(), nn, 1)
+    d = emu.device_alloc(16 * nn)
+    emu.upload(d, x)
+    plan.exec(d, isign=1)
+    out = np.empty_like(x)
+    emu.download(out, d)
+    emu.device_free(d)
+    plan.destroy()
+    assert cases.rel(out, ref) <= cases.tol(nn)
+
+
 def test_twofft_batch_argument_errors(emu):
     import ctypes
     from numrs_b200 import _lib

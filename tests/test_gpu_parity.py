@@ -372,34 +372,21 @@ def test_simple_addressing_matches_general_path(gpu, shape):
 
 
 @pytest.mark.gpu
-def test_big_tile_passes(gpu):
-    gpu.set_option("big_row_mask", (1 << 11) | (1 << 12) | (1 << 13))
-    gpu.set_option("big_col_mask", (1 << 9) | (1 << 10))
-    cases.check_four1_batch(gpu, 8192, 301)          # more tiles than persistent CTAs (148), ragged
-    cases.check_four1_batch(gpu, 4096, 700)
-    cases.check_four1_batch(gpu, 2048, 1500)
-    cases.check_fourn(gpu, (1024, 64))
-    cases.check_fourn(gpu, (2, 512, 8))
-    cases.check_four1(gpu, 1 << 20)
-
-
-@pytest.mark.gpu
 def test_twofft_processor_batch(gpu):
     cases.check_twofft_batch(gpu, [64, 4096, 64, 1 << 15, 4096, 2, 1 << 15])
 
 
-# `speq_side` is an experiment that has not been on hardware yet (added after the round's GPU minutes were spent): its
-# GPU tests run when NRB_TEST_EXPERIMENTAL=1 and are the first thing to run before the option is measured.
-experimental = pytest.mark.skipif(os.environ.get("NRB_TEST_EXPERIMENTAL") != "1",
-                                  reason="experimental option not yet validated on hardware; set NRB_TEST_EXPERIMENTAL=1")
+# `speq_side` and `conv_fused_mid` were validated and measured on hardware in round 2 (profiles/r02_tuning.md #38, #39) and are
+# on by default since; these tests pin the option explicitly and also run the other setting, so both code paths stay covered.
 
 
 @pytest.mark.gpu
-@experimental
 @pytest.mark.parametrize("shp", [(8, 8, 8), (16, 8, 32), (64, 128, 256), (256, 256, 256)])
 def test_rlft3_speq_passes_on_the_side_lane(gpu, shp):
     """The speq-plane passes on the plan's side stream (fork after the z pass, join before speq is used again): same
     results as the single-stream program, also when calls follow each other without a synchronise in between."""
+    gpu.set_option("speq_side", 0)
+    cases.check_rlft3(gpu, shp)
     gpu.set_option("speq_side", 1)
     cases.check_rlft3(gpu, shp)
     n = int(np.prod(shp))
@@ -413,7 +400,6 @@ def test_rlft3_speq_passes_on_the_side_lane(gpu, shp):
 
 
 @pytest.mark.gpu
-@experimental
 def test_rlft3_side_lane_device_resident_back_to_back(gpu):
     """Device-resident executions enqueued back to back on one stream with the speq passes on the side lane: the
     fork / join events must order every use of the speq plane (forward writes it, inverse reads it)."""
@@ -436,17 +422,16 @@ def test_rlft3_side_lane_device_resident_back_to_back(gpu):
 
 
 @pytest.mark.gpu
-@experimental
 @pytest.mark.parametrize("n", [1 << 15, 1 << 16, 1 << 20])
 def test_conv_fused_middle_kernel(gpu, n):
-    gpu.set_option("conv_fused_mid", 1)
-    cases.check_convlv(gpu, n, 4096)
-    cases.check_correl(gpu, n)
-    cases.check_autocorrel_fast(gpu, n)
+    for flag in (1, 0):
+        gpu.set_option("conv_fused_mid", flag)
+        cases.check_convlv(gpu, n, 4096)
+        cases.check_correl(gpu, n)
+        cases.check_autocorrel_fast(gpu, n)
 
 
 @pytest.mark.gpu
-@experimental
 def test_conv_fused_middle_matches_three_launch_pipeline_at_full_size(gpu):
     n, m = 1 << 22, 4096
     sigs = [cases.gen(1004, n, b * n) for b in range(2)]
