@@ -70,20 +70,29 @@ int  nrb_shutdown(void);               /* frees cached plans, twiddle tables no 
  *   "conv_transposed"   convlv/correl with lines longer than a tile: two passes per transform, spectrum kept in transposed
  *                       order (default 1); 0 = three natural-order passes per transform
  *   "prefetch_dist"     tiles ahead whose input every CTA prefetches into L2 (-1 = per-kernel policy, 0 = off)
+ *   "num_devices"       GPUs ONE host-slice call is spread over, inside this process: 1 = the calling thread's device
+ *                       (default), 0 = every visible device, n = devices 0 .. n-1 (rounded down to a power of two, <= 8).
+ *                       nrb_rlft3 and 3-D nrb_fourn scatter slabs of the host volume over the devices' PCIe links, exchange
+ *                       over NVLink peer memory and gather the result; the *_batch calls shard contiguous batch ranges.
+ *   "shard_min_kb"      batches smaller than this stay on one device (default 16384)
  *   "xchg_grid_cap"     pipelined slab exchange: CTAs of a peer-store pass (0 = one per tile); fewer CTAs leave SM
  *                       slots to the local pass running beside it on the second stream
  *   "simple_addr"       1 (default): passes whose element index is not split take the cheap addressing code path where it
  *                       is built (contiguous 8192-point lines, strided 512 / 1024-point lines); 0 = general path (A/B)
  *   "conv_fused_mid"    long-line convlv / correl / autocorrel_fast: contiguous forward pass + spectral step + contiguous
- *                       inverse pass of a row pair in ONE kernel, 5 -> 3 passes per signal (default 0: not measured yet)
+ *                       inverse pass of a row pair in ONE kernel, 5 -> 3 passes per signal (default 1)
  *   "speq_side"         rlft3: the four small speq-plane launches run on a second stream beside the data passes
- *                       (default 0: not measured yet)
+ *                       (default 1)
  *   "big_row_mask" / "big_col_mask"  bit log2(n) set: lines of n points use the big-tile prefetching pass (default 0:
  *                       measured no faster, kept as an experiment)
  * Environment overrides at load time: NRB_COL_MAX_LOG2, NRB_ROW_MAX_LOG2, NRB_L2_GROUP_MB, NRB_BATCH_GROUP_MB,
  * NRB_SIMPLE_ADDR, NRB_CONV_FUSED_MID, NRB_SPEQ_SIDE, NRB_BIG_ROW_MASK, NRB_BIG_COL_MASK. */
 int  nrb_set_option(const char *name, long value);
 /* pinned host memory, so host-slice calls copy at full PCIe rate (optional) */
+/* Multi-device introspection: devices one host-slice call is spread over under the current "num_devices" option, and the
+ * number of calls that really took the multi-device path (which = 0: 3-D transforms, 1: sharded batches). */
+int   nrb_num_devices_in_use(void);
+long  nrb_multi_device_calls(int which);
 void *nrb_host_alloc(size_t bytes);
 void  nrb_host_free(void *p);
 
@@ -207,6 +216,10 @@ int    nrb_complex_multiply_device(double *d_a, const double *d_b, size_t ncompl
  * Inverse (isign=-1) runs the mirror image: stage 0 on the nn1-slab, exchange, stage 1. */
 typedef struct nrb_slab_s *nrb_slab_t;
 int    nrb_slab_create(size_t nn1, size_t nn2, size_t nn3, int nranks, int rank, nrb_slab_t *plan);
+/* The same decomposition for the in-memory 3-D complex Fourn(data, [nn1, nn2, nn3], 3, isign) (call shape Real_FT3.rs:35):
+ * slabs of nn3 complex points per line, no speq plane (nrb_slab_speq_doubles = 0, d_speq may be NULL).  isign = +1 takes
+ * nn2-slabs [nn1][nn2/G][nn3] and returns nn1-slabs [nn1/G][nn2][nn3]; isign = -1 is the mirror image. */
+int    nrb_slab_create_fourn(size_t nn1, size_t nn2, size_t nn3, int nranks, int rank, nrb_slab_t *plan);
 size_t nrb_slab_local_doubles(nrb_slab_t plan);   /* doubles in one slab (data)           */
 size_t nrb_slab_speq_doubles(nrb_slab_t plan);    /* doubles in the local speq part        */
 size_t nrb_slab_xchg_doubles(nrb_slab_t plan);    /* doubles in the exchange buffer        */
@@ -226,6 +239,9 @@ size_t nrb_slab_recv_bytes(nrb_slab_t plan);
  * `epoch` into this rank's slot of every peer's flag array; phase 1 (before stage 1) spins on the
  * device until all ranks have published `epoch` locally.  Epochs must increase per receive buffer. */
 int    nrb_slab_barrier(nrb_slab_t plan, int phase, unsigned long long epoch, void *stream);
+/* One whole direction of the fused exchange in one call: stage 0, signal + wait on epoch `epoch`, stage 1. */
+int    nrb_slab_exec(nrb_slab_t plan, int isign, double *d_slab, double *d_speq, unsigned long long epoch, void *stream);
+int    nrb_slab_num_launches(nrb_slab_t plan, int isign);   /* kernels nrb_slab_exec launches (both stages + the flag barrier) */
 /* Pipelined exchange (fused mode only): cut the volume into `chunks` z-ranges (a power of two, at most 16;
  * 1 = off) so that stage 1 of chunk c can run -- on a second stream -- under the NVLink-bound stores of chunk
  * c + 1.  nrb_slab_stage_part runs one piece: part = -1 is the work before the chunks (forward: the z pass),

@@ -36,14 +36,14 @@ KIND_COSFT1, KIND_COSFT2, KIND_SINFT = 12, 13, 14
 # every symbol include/numrs_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "nrb_version", "nrb_last_error", "nrb_device_count", "nrb_set_device", "nrb_shutdown",
-    "nrb_set_option", "nrb_host_alloc", "nrb_host_free",
+    "nrb_set_option", "nrb_host_alloc", "nrb_host_free", "nrb_num_devices_in_use", "nrb_multi_device_calls",
     "nrb_four1", "nrb_four1_batch", "nrb_fourn", "nrb_realft", "nrb_realft_batch", "nrb_rlft3",
     "nrb_convlv", "nrb_convlv_batch", "nrb_correl", "nrb_correl_batch",
     "nrb_correl_normalized", "nrb_autocorrel_fast", "nrb_twofft", "nrb_twofft_batch", "nrb_power_spectrum",
     "nrb_cosft1", "nrb_cosft2", "nrb_sinft",
     "nrb_plan_create", "nrb_plan_workspace_bytes", "nrb_plan_num_launches", "nrb_plan_exec", "nrb_plan_destroy",
     "nrb_plan_profile", "nrb_plan_describe_launch", "nrb_fill_uniform_device",
-    "nrb_slab_create", "nrb_slab_local_doubles", "nrb_slab_speq_doubles", "nrb_slab_xchg_doubles",
+    "nrb_slab_create", "nrb_slab_create_fourn", "nrb_slab_exec", "nrb_slab_num_launches", "nrb_slab_local_doubles", "nrb_slab_speq_doubles", "nrb_slab_xchg_doubles",
     "nrb_slab_stage", "nrb_slab_destroy", "nrb_slab_set_peers", "nrb_slab_recv_bytes", "nrb_slab_barrier",
     "nrb_slab_set_chunks", "nrb_slab_stage_part", "nrb_slab_barrier_chunk",
     "nrb_slab_set_dma", "nrb_slab_exec_dma", "nrb_slab_stage_part_xchg", "nrb_slab_dma_timeline",
@@ -112,6 +112,11 @@ class Library:
         L.nrb_plan_describe_launch.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, _sz, _dp]
         L.nrb_fill_uniform_device.argtypes = [_vp, ctypes.c_ulonglong, ctypes.c_ulonglong, _sz, _vp]
         L.nrb_slab_create.argtypes = [_sz, _sz, _sz, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]
+        L.nrb_multi_device_calls.argtypes = [ctypes.c_int]
+        L.nrb_multi_device_calls.restype = ctypes.c_long
+        L.nrb_slab_create_fourn.argtypes = [_sz, _sz, _sz, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]
+        L.nrb_slab_num_launches.argtypes = [_vp, ctypes.c_int]
+        L.nrb_slab_exec.argtypes = [_vp, ctypes.c_int, _vp, _vp, ctypes.c_ulonglong, _vp]
         for n in ("nrb_slab_local_doubles", "nrb_slab_speq_doubles", "nrb_slab_xchg_doubles"):
             getattr(L, n).argtypes = [_vp]
             getattr(L, n).restype = _sz
@@ -185,6 +190,18 @@ class Library:
         cnt = len(arrays)
         ptrs = (_dp * max(cnt, 1))(*[_f64(a) for a in arrays])
         sizes = (_sz * max(cnt, 1))(*([a.size // 2 for a in arrays] if nn is None else nn))
+        return self.L.nrb_four1_batch(ptrs, sizes, cnt, isign)
+
+    def batch_table(self, arrays):
+        """Pointer / length tables of a four1 batch, built once and reusable across calls (a Rust caller's Vec of
+        pointers costs nothing; 4096 ctypes conversions per call cost more than the PCIe copies)."""
+        cnt = len(arrays)
+        ptrs = (_dp * max(cnt, 1))(*[_f64(a) for a in arrays])
+        sizes = (_sz * max(cnt, 1))(*[a.size // 2 for a in arrays])
+        return (ptrs, sizes, cnt, list(arrays))      # the arrays stay referenced
+
+    def four1_batch_table(self, table, isign):
+        ptrs, sizes, cnt, _ = table
         return self.L.nrb_four1_batch(ptrs, sizes, cnt, isign)
 
     def fourn(self, data, nn, ndim, isign):
@@ -327,9 +344,17 @@ class Library:
         self.check(self.L.nrb_plan_create(kind, dims_c, len(dims), batch, ctypes.byref(h)))
         return Plan(self, h)
 
-    def slab_create(self, nn1, nn2, nn3, nranks, rank):
+    def num_devices_in_use(self):
+        return self.L.nrb_num_devices_in_use()
+
+    def multi_device_calls(self, which=0):
+        return self.L.nrb_multi_device_calls(which)
+
+    def slab_create(self, nn1, nn2, nn3, nranks, rank, kind="rlft3"):
+        """kind "rlft3" (real volume + speq plane) or "fourn" (3-D complex volume of nn3 complex points per line)."""
         h = _vp()
-        self.check(self.L.nrb_slab_create(nn1, nn2, nn3, nranks, rank, ctypes.byref(h)))
+        create = self.L.nrb_slab_create if kind == "rlft3" else self.L.nrb_slab_create_fourn
+        self.check(create(nn1, nn2, nn3, nranks, rank, ctypes.byref(h)))
         return SlabPlan(self, h)
 
 
@@ -396,6 +421,13 @@ class SlabPlan:
 
     def barrier(self, phase, epoch, stream=0):
         self.lib.check(self.lib.L.nrb_slab_barrier(self.h, phase, epoch, stream or None))
+
+    def exec(self, isign, d_slab, d_speq, epoch, stream=0):
+        """One whole direction of the fused exchange (stage 0, flag barrier, stage 1) in one C call."""
+        self.lib.check(self.lib.L.nrb_slab_exec(self.h, isign, d_slab, d_speq or None, epoch, stream or None))
+
+    def num_launches(self, isign):
+        return self.lib.L.nrb_slab_num_launches(self.h, isign)
 
     def set_chunks(self, chunks):
         self.lib.check(self.lib.L.nrb_slab_set_chunks(self.h, chunks))

@@ -15,6 +15,7 @@
 #pragma GCC visibility push(default)
 #include "../../include/numrs_b200.h"
 #pragma GCC visibility pop
+#include "multi.h"
 #include "plan.h"
 
 using namespace nrb;
@@ -284,6 +285,33 @@ int run_segments(int kind, const size_t *dims, size_t ndim, size_t batch, const 
     return NRB_OK;
 }
 
+// ---- batches over several devices (option num_devices): contiguous batch ranges, no communication ----
+// (fft_batch FFT_1.rs:185, convlv_batch Convolve.rs:241, correl_batch Correlation.rs:273 shard by batch)
+size_t shard_min_bytes() { return (size_t)tunables().shard_min_kb << 10; }   // smaller calls stay on the calling thread's device
+
+int run_inplace_batch(int kind, const size_t *dims, size_t ndim, double *const *ptrs, size_t count, size_t doubles, int isign)
+{
+    const int G = multi_device_count();
+    if (G < 2 || count < 2 || count * doubles * sizeof(double) < shard_min_bytes())
+        return run_inplace(kind, dims, ndim, ptrs, count, doubles, isign, nullptr, 0);
+    return multi_shard_batch(count, G, [&](size_t first, size_t cnt) {
+        return run_inplace(kind, dims, ndim, ptrs + first, cnt, doubles, isign, nullptr, 0);
+    });
+}
+
+int run_outofplace_batch(int kind, const size_t *dims, size_t ndim, const double *const *in, const double *const *aux,
+                         size_t aux_count, size_t aux_n, double *const *out, size_t count, size_t n, int isign, int arg)
+{
+    const int G = multi_device_count();
+    if (G < 2 || count < 2 || count * n * sizeof(double) < shard_min_bytes())
+        return run_outofplace(kind, dims, ndim, in, aux, aux_count, aux_n, out, count, n, isign, arg);
+    const bool per_signal_aux = aux_count == count;     // correl: one second operand per pair; convlv: one response for all
+    return multi_shard_batch(count, G, [&](size_t first, size_t cnt) {
+        return run_outofplace(kind, dims, ndim, in + first, per_signal_aux ? aux + first : aux, per_signal_aux ? cnt : aux_count,
+                              aux_n, out + first, cnt, n, isign, arg);
+    });
+}
+
 } // namespace
 
 extern "C" {
@@ -298,6 +326,7 @@ try {
 } catch (...) { return on_exception(); }
 int nrb_shutdown(void)
 {
+    multi_release();
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         g_plan_cache.clear();
@@ -314,10 +343,13 @@ int nrb_shutdown(void)
 int nrb_set_option(const char *name, long value)
 try {
     if (set_tunable(name, value) != 0) return fail(NRB_ERR_INVALID_DIMS, "unknown option");
+    multi_release();
     std::lock_guard<std::mutex> lk(g_cache_mu);
     g_plan_cache.clear();
     return NRB_OK;
 } catch (...) { return on_exception(); }
+long nrb_multi_device_calls(int which) { return multi_calls(which); }
+int nrb_num_devices_in_use(void) { return multi_device_count(); }
 void *nrb_host_alloc(size_t bytes) { return be_host_alloc(bytes); }
 void nrb_host_free(void *p) { if (p) be_host_free(p); }
 
@@ -404,14 +436,31 @@ try {
     *plan = h.release();
     return NRB_OK;
 } catch (...) { return on_exception(); }
-size_t nrb_slab_local_doubles(nrb_slab_t p) { return p ? p->plan.nn1 * p->plan.nn2 * p->plan.nn3 / (size_t)p->plan.nranks : 0; }
-size_t nrb_slab_speq_doubles(nrb_slab_t p) { return p ? 2 * p->plan.nn1 * p->plan.nn2 / (size_t)p->plan.nranks : 0; }
-size_t nrb_slab_xchg_doubles(nrb_slab_t p)
-{
+int nrb_slab_create_fourn(size_t nn1, size_t nn2, size_t nn3, int nranks, int rank, nrb_slab_t *plan)
+try {
+    if (!plan) return fail(NRB_ERR_INVALID_DIMS, "plan pointer is NULL");
+    *plan = nullptr;
+    if (be_device_count() <= 0) return fail(NRB_ERR_CUDA, "no CUDA device available (numrs_b200 has no CPU fallback)");
+    std::unique_ptr<nrb_slab_s> h(new nrb_slab_s());
+    const int rc = build_slab_plan(h->plan, nn1, nn2, nn3, nranks, rank, false);
+    if (rc != NRB_OK) return rc;
+    *plan = h.release();
+    return NRB_OK;
+} catch (...) { return on_exception(); }
+size_t nrb_slab_local_doubles(nrb_slab_t p) { return p ? (p->plan.real ? 1 : 2) * p->plan.nn1 * p->plan.nn2 * p->plan.nn3 / (size_t)p->plan.nranks : 0; }
+size_t nrb_slab_speq_doubles(nrb_slab_t p) { return p && p->plan.real ? 2 * p->plan.nn1 * p->plan.nn2 / (size_t)p->plan.nranks : 0; }
+size_t nrb_slab_xchg_doubles(nrb_slab_t p) { return p ? 2 * p->plan.xchg_elems() : 0; }
+int nrb_slab_num_launches(nrb_slab_t p, int isign)
+try {
     if (!p) return 0;
-    const size_t G = (size_t)p->plan.nranks;
-    return 2 * G * (p->plan.nn1 / G) * (p->plan.nn2 / G) * (p->plan.nn3 / 2 + 1);
-}
+    const int s = isign == 1 ? 0 : 1;
+    return (int)(p->plan.prog[s][0].steps.size() + p->plan.prog[s][1].steps.size()) + (p->plan.nranks > 1 ? 2 : 0);
+} catch (...) { return on_exception(); }
+int nrb_slab_exec(nrb_slab_t p, int isign, double *d_slab, double *d_speq, unsigned long long epoch, void *stream)
+try {
+    if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
+    return exec_slab_fused(p->plan, isign, d_slab, d_speq, epoch, stream);
+} catch (...) { return on_exception(); }
 int nrb_slab_stage(nrb_slab_t p, int stage, int isign, double *d_slab, double *d_speq, double *d_send, double *d_recv,
                    void *stream)
 try {
@@ -524,8 +573,7 @@ try {
     }
     for (auto &g : groups) {
         const size_t dims[1] = {g.first};
-        const int rc = run_inplace(NRB_KIND_FOUR1, dims, 1, g.second.data(), g.second.size(), 2 * g.first, isign,
-                                   nullptr, 0);
+        const int rc = run_inplace_batch(NRB_KIND_FOUR1, dims, 1, g.second.data(), g.second.size(), 2 * g.first, isign);
         if (rc) return rc;
     }
     return NRB_OK;
@@ -542,6 +590,11 @@ try {
         total *= nn[d];
     }
     if (!data) return fail(NRB_ERR_EMPTY_INPUT, "null data");
+    if (ndim == 3 && multi_device_count() > 1) {
+        // slab-decomposed over the devices of the box (multi.cpp); shapes it cannot take fall through to one device
+        const int rc = multi_transform3d(false, data, nullptr, nn[0], nn[1], nn[2], isign, multi_device_count());
+        if (rc != NRB_ERR_UNSUPPORTED) return rc;
+    }
     double *ptrs[1] = {data};
     return run_inplace(NRB_KIND_FOURN, nn, ndim, ptrs, 1, 2 * total, isign, nullptr, 0);
 } catch (...) { return on_exception(); }
@@ -561,7 +614,7 @@ try {
     if (!ptrs) return fail(NRB_ERR_EMPTY_INPUT, "null batch");
     const size_t dims[1] = {n};
     // Real_FT.rs:10,15: isign == 1 is forward, anything else inverse
-    return run_inplace(NRB_KIND_REALFT, dims, 1, ptrs, count, n, isign == 1 ? 1 : -1, nullptr, 0);
+    return run_inplace_batch(NRB_KIND_REALFT, dims, 1, ptrs, count, n, isign == 1 ? 1 : -1);
 } catch (...) { return on_exception(); }
 
 int nrb_rlft3(double *data, double *speq, size_t nn1, size_t nn2, size_t nn3, int isign)
@@ -569,6 +622,10 @@ try {
     if (isign != 1 && isign != -1) return fail(NRB_ERR_INVALID_ISIGN, "isign must be 1 or -1");   // Real_FT3.rs:17
     if (nn1 == 0 || nn2 == 0 || nn3 < 2) return fail(NRB_ERR_INVALID_DIMS, "data dimensions mismatch");
     if (!data || !speq) return fail(NRB_ERR_EMPTY_INPUT, "null data");
+    if (multi_device_count() > 1) {
+        const int rc = multi_transform3d(true, data, speq, nn1, nn2, nn3, isign, multi_device_count());
+        if (rc != NRB_ERR_UNSUPPORTED) return rc;
+    }
     const size_t dims[3] = {nn1, nn2, nn3};
     double *ptrs[1] = {data};
     return run_inplace(NRB_KIND_RLFT3, dims, 3, ptrs, 1, nn1 * nn2 * nn3, isign, speq, 2 * nn1 * nn2);
@@ -594,7 +651,7 @@ try {
     if (!data || !respns || !ans) return fail(NRB_ERR_EMPTY_INPUT, "null pointer");
     const size_t dims[2] = {n, m};
     const double *aux[1] = {respns};
-    return run_outofplace(NRB_KIND_CONVLV, dims, 2, data, aux, 1, m, ans, count, n, isign, pad_mode);
+    return run_outofplace_batch(NRB_KIND_CONVLV, dims, 2, data, aux, 1, m, ans, count, n, isign, pad_mode);
 } catch (...) { return on_exception(); }
 
 int nrb_correl(const double *data1, size_t n1, const double *data2, size_t n2, double *ans)
@@ -614,7 +671,7 @@ try {
     if (count == 0) return NRB_OK;
     if (!data1 || !data2 || !ans) return fail(NRB_ERR_EMPTY_INPUT, "null pointer");
     const size_t dims[1] = {n};
-    return run_outofplace(NRB_KIND_CORREL, dims, 1, data1, data2, count, n, ans, count, n, 1, 0);
+    return run_outofplace_batch(NRB_KIND_CORREL, dims, 1, data1, data2, count, n, ans, count, n, 1, 0);
 } catch (...) { return on_exception(); }
 
 // ------------------------------------------------------------------ "next" rows

@@ -226,6 +226,29 @@ int be_d2d(void *dst, const void *src, size_t bytes, void *stream)
     cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : fail(e);
 }
+int be_h2d_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows, void *stream)
+{
+    cudaError_t e = cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail(e);
+}
+int be_d2h_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows, void *stream)
+{
+    cudaError_t e = cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail(e);
+}
+int be_enable_peer(int dev, int peer)
+{
+    cudaError_t e = cudaSetDevice(dev);
+    if (e != cudaSuccess) return fail(e);
+    if (dev == peer) return 0;
+    int can = 0;
+    e = cudaDeviceCanAccessPeer(&can, dev, peer);
+    if (e != cudaSuccess) return fail(e);
+    if (!can) { g_be_err = "devices " + std::to_string(dev) + " and " + std::to_string(peer) + " have no peer access"; return -1; }
+    e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+    return e == cudaSuccess ? 0 : fail(e);
+}
 int be_sync(void *stream)
 {
     cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);

@@ -56,6 +56,8 @@ static Tunables &tunables_mut()
         x.conv_fused_mid = env_int("NRB_CONV_FUSED_MID", 1);
         x.big_row_mask = env_int("NRB_BIG_ROW_MASK", 0);
         x.big_col_mask = env_int("NRB_BIG_COL_MASK", 0);
+        x.num_devices = env_int("NRB_NUM_DEVICES", 1);
+        x.shard_min_kb = env_int("NRB_SHARD_MIN_KB", 16384);
         return x;
     }();
     if (t.col_max_log2 < 1) t.col_max_log2 = 1;
@@ -87,6 +89,8 @@ int set_tunable(const char *name, long value)
     else if (n == "conv_fused_mid") t.conv_fused_mid = (int)value;
     else if (n == "big_row_mask") t.big_row_mask = (int)value;
     else if (n == "big_col_mask") t.big_col_mask = (int)value;
+    else if (n == "num_devices") t.num_devices = value < 0 ? 1 : (int)value;
+    else if (n == "shard_min_kb") t.shard_min_kb = value < 0 ? 0 : (int)value;
     else return -1;
     tunables_mut();   // re-clamp
     return 0;
@@ -1271,7 +1275,8 @@ int fill_uniform_device(double *d_out, u64 seed, u64 offset, u64 count, void *st
     return NRB_OK;
 }
 
-// ------------------------------------------------------------------ slab-decomposed rlft3
+// ------------------------------------------------------------------ slab-decomposed rlft3 / 3-D complex fourn
+// (fourn: the same programs with a plain complex z pass, N3 = nn3 complex points and no speq part.)
 // Rank r of G.  X = nn1/G, Y = nn2/G, N3 = nn3/2, BLK = X*Y*(N3 + 1) complex per exchange
 // block (data part X*Y*N3 followed by the speq part X*Y).
 //   forward stage 0 : slab [nn1][Y][nn3] real -> z real pass (speq -> ws [nn1][Y]) ->
@@ -1281,25 +1286,25 @@ int fill_uniform_device(double *d_out, u64 seed, u64 offset, u64 count, void *st
 //                     writing the nn1-slab [X][nn2][N3] complex and speq [X][nn2]
 //   inverse         : mirror image (stage 0 = y pass into blocks, stage 1 = x pass + z c2r).
 // buffers: BUF_IO = slab, BUF_AUX = local speq, BUF_OUT = send (stage 0) / recv (stage 1).
-int build_slab_plan(SlabPlan &sp, size_t nn1, size_t nn2, size_t nn3, int nranks, int rank)
+int build_slab_plan(SlabPlan &sp, size_t nn1, size_t nn2, size_t nn3, int nranks, int rank, bool real)
 {
     if (!is_pow2(nn1) || !is_pow2(nn2) || !is_pow2(nn3) || nn3 < 2) { set_error("slab: dims must be powers of two"); return NRB_ERR_NOT_POW2; }
     if (nranks < 1 || !is_pow2((size_t)nranks) || (size_t)nranks > nn1 || (size_t)nranks > nn2 || rank < 0 || rank >= nranks) {
         set_error("slab: nranks must be a power of two dividing nn1 and nn2");
         return NRB_ERR_INVALID_DIMS;
     }
-    sp.nn1 = nn1; sp.nn2 = nn2; sp.nn3 = nn3; sp.nranks = nranks; sp.rank = rank;
+    sp.nn1 = nn1; sp.nn2 = nn2; sp.nn3 = nn3; sp.nranks = nranks; sp.rank = rank; sp.real = real;
     TableScope tables(&sp.tables);
-    const u64 G = (u64)nranks, X = nn1 / G, Y = nn2 / G, N3 = nn3 / 2;
+    const u64 G = (u64)nranks, X = nn1 / G, Y = nn2 / G, N3 = sp.n3c();
     const int p1 = ilog2(nn1), p2 = ilog2(nn2), p3 = ilog2((size_t)N3);
     if (p1 > tunables().col_max_log2 || p2 > tunables().col_max_log2 || p3 > tunables().row_max_log2) {
         set_error("slab: axis too long for a single pass");
         return NRB_ERR_UNSUPPORTED;
     }
-    const i64 BLK = (i64)(X * Y * (N3 + 1));
-    const i64 SPQ = (i64)(X * Y * N3);      // offset of the speq part inside a block
+    const i64 BLK = (i64)sp.blk();
+    const i64 SPQ = (i64)(X * Y * N3);      // offset of the speq part inside a block (rlft3 only)
     const BufRef SLAB(BUF_IO, 0), SPEQ(BUF_AUX, 0), XCH(BUF_OUT, 0), WSPEQ(BUF_WS, 0);
-    sp.ws_elems = (size_t)(nn1 * Y);        // speq of the nn2-slab: [nn1][Y]
+    sp.ws_elems = real ? (size_t)(nn1 * Y) : 0;   // speq of the nn2-slab: [nn1][Y]
     int rc = NRB_OK;
 
     AxisMap x_blocks;   // x index -> block x / X ; data part, lines (y, z)
@@ -1311,44 +1316,48 @@ int build_slab_plan(SlabPlan &sp, size_t nn1, size_t nn2, size_t nn3, int nranks
     AxisMap y_blocks_speq;   // speq part: lines xl, contiguous yl
     y_blocks_speq.on = true; y_blocks_speq.s0 = (i64)Y; y_blocks_speq.es = 1; y_blocks_speq.eshift = ilog2((size_t)Y); y_blocks_speq.es_hi = BLK;
 
+    // z lines of the local slab: real transform with the Nyquist plane in WSPEQ (rlft3) or a plain complex pass (fourn)
+    auto emit_z = [&](Builder &B, int dir) {
+        if (real) emit_real(B, SLAB, SLAB, BufRef(), 0, nn1 * Y, p3, dir, REAL_SPEQ, WSPEQ);
+        else emit_axis(B, SLAB, SLAB, BufRef(), nn1 * Y, 0, nn1 * Y, p3, 1, dir);
+    };
     // speq_side: the speq-plane pass of a stage goes first in program order, on lane 1 (it only depends on what
     // precedes the stage, or on the z pass), so it runs beside the stage's data pass; run_program joins the lanes
     // before the z pass of the inverse reads the plane and at the end of every stage (before the exchange barrier)
-    const bool side = tunables().speq_side != 0;
+    const bool side = real && tunables().speq_side != 0;
     auto lane1 = [&](Builder &B, size_t first) { if (side) for (size_t i = first; i < B.prog->steps.size(); ++i) B.prog->steps[i].lane = 1; };
     {   // forward stage 0
         Builder B(&sp.prog[0][0]);
-        emit_real(B, SLAB, SLAB, BufRef(), 0, nn1 * Y, p3, +1, REAL_SPEQ, WSPEQ);
+        emit_z(B, +1);
         if (side) { const size_t f0 = B.prog->steps.size(); emit_axis(B, WSPEQ, XCH + SPQ, BufRef(), 1, 0, 1, p1, Y, +1, nullptr, &x_blocks_speq); lane1(B, f0); }
         emit_axis(B, SLAB, XCH, BufRef(), 1, 0, 1, p1, Y * N3, +1, nullptr, &x_blocks);
-        if (!side) emit_axis(B, WSPEQ, XCH + SPQ, BufRef(), 1, 0, 1, p1, Y, +1, nullptr, &x_blocks_speq);
+        if (real && !side) emit_axis(B, WSPEQ, XCH + SPQ, BufRef(), 1, 0, 1, p1, Y, +1, nullptr, &x_blocks_speq);
         rc = B.rc ? B.rc : rc;
     }
     {   // forward stage 1
         Builder B(&sp.prog[0][1]);
         if (side) { emit_axis(B, XCH + SPQ, SPEQ, BufRef(), X, 0, X, p2, 1, +1, &y_blocks_speq, nullptr); lane1(B, 0); }
         emit_axis(B, XCH, SLAB, BufRef(), X, 0, X, p2, N3, +1, &y_blocks, nullptr);
-        if (!side) emit_axis(B, XCH + SPQ, SPEQ, BufRef(), X, 0, X, p2, 1, +1, &y_blocks_speq, nullptr);
+        if (real && !side) emit_axis(B, XCH + SPQ, SPEQ, BufRef(), X, 0, X, p2, 1, +1, &y_blocks_speq, nullptr);
         rc = B.rc ? B.rc : rc;
     }
     {   // inverse stage 0
         Builder B(&sp.prog[1][0]);
         if (side) { emit_axis(B, SPEQ, XCH + SPQ, BufRef(), X, 0, X, p2, 1, -1, nullptr, &y_blocks_speq); lane1(B, 0); }
         emit_axis(B, SLAB, XCH, BufRef(), X, 0, X, p2, N3, -1, nullptr, &y_blocks);
-        if (!side) emit_axis(B, SPEQ, XCH + SPQ, BufRef(), X, 0, X, p2, 1, -1, nullptr, &y_blocks_speq);
+        if (real && !side) emit_axis(B, SPEQ, XCH + SPQ, BufRef(), X, 0, X, p2, 1, -1, nullptr, &y_blocks_speq);
         rc = B.rc ? B.rc : rc;
     }
     {   // inverse stage 1
         Builder B(&sp.prog[1][1]);
-        emit_axis(B, XCH + SPQ, WSPEQ, BufRef(), 1, 0, 1, p1, Y, -1, &x_blocks_speq, nullptr);
-        lane1(B, 0);
+        if (real) { emit_axis(B, XCH + SPQ, WSPEQ, BufRef(), 1, 0, 1, p1, Y, -1, &x_blocks_speq, nullptr); lane1(B, 0); }
         emit_axis(B, XCH, SLAB, BufRef(), 1, 0, 1, p1, Y * N3, -1, &x_blocks, nullptr);
-        emit_real(B, SLAB, SLAB, BufRef(), 0, nn1 * Y, p3, -1, REAL_SPEQ, WSPEQ);
+        emit_z(B, -1);
         rc = B.rc ? B.rc : rc;
     }
     if (rc != NRB_OK) { set_error("slab: shape not supported"); return rc; }
     sp.ws = nullptr;
-    if (be_malloc(&sp.ws, sp.ws_elems * sizeof(double2)) != 0) { set_error("slab: workspace allocation failed"); return NRB_ERR_OOM; }
+    if (sp.ws_elems && be_malloc(&sp.ws, sp.ws_elems * sizeof(double2)) != 0) { set_error("slab: workspace allocation failed"); return NRB_ERR_OOM; }
     return NRB_OK;
 }
 
@@ -1378,13 +1387,14 @@ void chunk_lines(Step &st, u64 mid, LineMap in, LineMap out, u64 Zc, int c)
 // piece (peer, chunk) is one contiguous range for a copy engine
 int build_chunk_programs(SlabPlan &sp, int chunks, bool dma)
 {
-    const u64 G = (u64)sp.nranks, X = sp.nn1 / G, Y = sp.nn2 / G, N3 = sp.nn3 / 2;
+    const u64 G = (u64)sp.nranks, X = sp.nn1 / G, Y = sp.nn2 / G, N3 = sp.n3c();
     const int p1 = ilog2(sp.nn1), p2 = ilog2(sp.nn2), p3 = ilog2((size_t)N3);
+    const bool real = sp.real;
     TableScope tables(&sp.tables);
     const u64 Zc = N3 / (u64)chunks;
     if (Zc < 1 || Zc * (u64)chunks != N3) { set_error("slab: too many chunks for this nn3"); return NRB_ERR_INVALID_DIMS; }
-    const i64 BLK = (i64)(X * Y * (N3 + 1)), SPQ = (i64)(X * Y * N3), PIECE = (i64)(X * Y * Zc);
-    const size_t speq_ws = (size_t)(sp.nn1 * Y), work_elems = (size_t)(sp.nn1 * Y * N3);
+    const i64 BLK = (i64)sp.blk(), SPQ = (i64)(X * Y * N3), PIECE = (i64)(X * Y * Zc);
+    const size_t speq_ws = real ? (size_t)(sp.nn1 * Y) : 0, work_elems = (size_t)(sp.nn1 * Y * N3);
     if (sp.ws_elems < speq_ws + work_elems) {
         void *nw = nullptr;
         if (be_malloc(&nw, (speq_ws + work_elems) * sizeof(double2)) != 0) { set_error("slab: work buffer allocation failed"); return NRB_ERR_OOM; }
@@ -1414,7 +1424,8 @@ int build_chunk_programs(SlabPlan &sp, int chunks, bool dma)
         sp.part[s].resize((size_t)(2 * chunks + 2));
         {   // before the chunks
             Builder B(&sp.part[s][0]);
-            if (dir > 0) emit_real(B, SLAB, WORK, BufRef(), 0, sp.nn1 * Y, p3, +1, REAL_SPEQ, WSPEQ);
+            if (dir > 0 && real) emit_real(B, SLAB, WORK, BufRef(), 0, sp.nn1 * Y, p3, +1, REAL_SPEQ, WSPEQ);
+            else if (dir > 0) emit_axis(B, SLAB, WORK, BufRef(), sp.nn1 * Y, 0, sp.nn1 * Y, p3, 1, +1);
             rc = B.rc ? B.rc : rc;
         }
         for (int c = 0; c < chunks; ++c) {
@@ -1422,15 +1433,15 @@ int build_chunk_programs(SlabPlan &sp, int chunks, bool dma)
             if (dir > 0) {
                 emit_axis(B0, WORK, XCH, BufRef(), 1, 0, 1, p1, Y * N3, +1, nullptr, &x_blocks);
                 chunk_lines(B0.prog->steps.back(), Y, work_lines, xch_x_lines, Zc, c);
-                if (c == 0) emit_axis(B0, WSPEQ, XCH + SPQ, BufRef(), 1, 0, 1, p1, Y, +1, nullptr, &x_blocks_speq);
+                if (c == 0 && real) emit_axis(B0, WSPEQ, XCH + SPQ, BufRef(), 1, 0, 1, p1, Y, +1, nullptr, &x_blocks_speq);
                 emit_axis(B1, XCH, SLAB, BufRef(), X, 0, X, p2, N3, +1, &y_blocks, nullptr);
                 chunk_lines(B1.prog->steps.back(), X, xch_y_lines, slab_lines, Zc, c);
-                if (c == 0) emit_axis(B1, XCH + SPQ, SPEQ, BufRef(), X, 0, X, p2, 1, +1, &y_blocks_speq, nullptr);
+                if (c == 0 && real) emit_axis(B1, XCH + SPQ, SPEQ, BufRef(), X, 0, X, p2, 1, +1, &y_blocks_speq, nullptr);
             } else {
                 emit_axis(B0, SLAB, XCH, BufRef(), X, 0, X, p2, N3, -1, nullptr, &y_blocks);
                 chunk_lines(B0.prog->steps.back(), X, slab_lines, xch_y_lines, Zc, c);
-                if (c == 0) emit_axis(B0, SPEQ, XCH + SPQ, BufRef(), X, 0, X, p2, 1, -1, nullptr, &y_blocks_speq);
-                if (c == 0) emit_axis(B1, XCH + SPQ, WSPEQ, BufRef(), 1, 0, 1, p1, Y, -1, &x_blocks_speq, nullptr);
+                if (c == 0 && real) emit_axis(B0, SPEQ, XCH + SPQ, BufRef(), X, 0, X, p2, 1, -1, nullptr, &y_blocks_speq);
+                if (c == 0 && real) emit_axis(B1, XCH + SPQ, WSPEQ, BufRef(), 1, 0, 1, p1, Y, -1, &x_blocks_speq, nullptr);
                 emit_axis(B1, XCH, WORK, BufRef(), 1, 0, 1, p1, Y * N3, -1, &x_blocks, nullptr);
                 chunk_lines(B1.prog->steps.back(), Y, xch_x_lines, work_lines, Zc, c);
             }
@@ -1438,7 +1449,8 @@ int build_chunk_programs(SlabPlan &sp, int chunks, bool dma)
         }
         {   // after the chunks
             Builder B(&sp.part[s][(size_t)(2 * chunks + 1)]);
-            if (dir < 0) emit_real(B, WORK, SLAB, BufRef(), 0, sp.nn1 * Y, p3, -1, REAL_SPEQ, WSPEQ);
+            if (dir < 0 && real) emit_real(B, WORK, SLAB, BufRef(), 0, sp.nn1 * Y, p3, -1, REAL_SPEQ, WSPEQ);
+            else if (dir < 0) emit_axis(B, WORK, SLAB, BufRef(), sp.nn1 * Y, 0, sp.nn1 * Y, p3, 1, -1);
             rc = B.rc ? B.rc : rc;
         }
     }
@@ -1467,8 +1479,7 @@ int slab_set_dma(SlabPlan &sp, int chunks)
     sp.dma = false;
     const int rc = build_chunk_programs(sp, chunks, true);
     if (rc != NRB_OK) return rc;
-    const u64 G = (u64)sp.nranks;
-    const size_t xchg = (size_t)(G * (sp.nn1 / G) * (sp.nn2 / G) * (sp.nn3 / 2 + 1));
+    const size_t xchg = sp.xchg_elems();
     if (!sp.send && be_malloc(&sp.send, xchg * sizeof(double2)) != 0) { set_error("slab: send buffer allocation failed"); return NRB_ERR_OOM; }
     if (!sp.copy_stream) {
         if (be_stream_create_prio(&sp.copy_stream, 0) != 0 || be_stream_create_prio(&sp.side_stream, 1) != 0) { set_error("slab: stream creation failed"); return NRB_ERR_CUDA; }
@@ -1499,8 +1510,7 @@ int exec_slab_part(SlabPlan &sp, int stage, int part, int isign, double *d_slab,
     if (sp.part[0].empty() || (!sp.dma && !sp.fused)) { set_error("slab: the pipelined exchange needs nrb_slab_set_peers and nrb_slab_set_chunks / nrb_slab_set_dma"); return NRB_ERR_INVALID_DIMS; }
     if (part < -1 || part > sp.chunks || ((part >= 0 && part < sp.chunks) && stage != 0 && stage != 1)) { set_error("slab: bad part"); return NRB_ERR_INVALID_DIMS; }
     const size_t idx = part < 0 ? 0 : part == sp.chunks ? (size_t)(2 * sp.chunks + 1) : (size_t)(1 + 2 * part + stage);
-    const u64 G = (u64)sp.nranks;
-    const i64 BLK = (i64)((sp.nn1 / G) * (sp.nn2 / G) * (sp.nn3 / 2 + 1));
+    const i64 BLK = (i64)sp.blk();
     const bool chunk_part = part >= 0 && part < sp.chunks;
     Program &prog = sp.part[isign == 1 ? 0 : 1][idx];
     if (sp.dma) {
@@ -1530,8 +1540,8 @@ int exec_slab_part(SlabPlan &sp, int stage, int part, int isign, double *d_slab,
 int exec_slab_dma(SlabPlan &sp, int isign, double *d_slab, double *d_speq, unsigned long long epoch, void *stream)
 {
     if (!sp.dma || !sp.fused) { set_error("slab: nrb_slab_set_dma and nrb_slab_set_peers first"); return NRB_ERR_INVALID_DIMS; }
-    const u64 G = (u64)sp.nranks, X = sp.nn1 / G, Y = sp.nn2 / G, N3 = sp.nn3 / 2;
-    const i64 BLK = (i64)(X * Y * (N3 + 1)), SPQ = (i64)(X * Y * N3), PIECE = (i64)(X * Y * (N3 / (u64)sp.chunks));
+    const u64 G = (u64)sp.nranks, X = sp.nn1 / G, Y = sp.nn2 / G, N3 = sp.n3c();
+    const i64 BLK = (i64)sp.blk(), SPQ = (i64)(X * Y * N3), PIECE = (i64)(X * Y * (N3 / (u64)sp.chunks));
     double2 *send = (double2 *)sp.send, *recv = sp.peers[sp.rank];
     if (sp.timeline) { for (void *e : sp.tl_events) be_event_destroy(e); sp.tl_events.clear(); sp.tl_names.clear(); }
     auto mark = [&](const char *what, int c, void *s) {
@@ -1554,7 +1564,7 @@ int exec_slab_dma(SlabPlan &sp, int isign, double *d_slab, double *d_speq, unsig
         for (u64 i = 1; i < G; ++i) {                     // rotated so that every rank targets a different peer at a time;
             const u64 p = ((u64)sp.rank + i) % G;         // the own block went straight into the own receive buffer
             if (be_d2d(sp.peers[p] + (i64)sp.rank * BLK + (i64)c * PIECE, send + (i64)p * BLK + (i64)c * PIECE, (size_t)PIECE * sizeof(double2), sp.copy_stream) != 0 ||
-                (c == 0 && be_d2d(sp.peers[p] + (i64)sp.rank * BLK + SPQ, send + (i64)p * BLK + SPQ, (size_t)(X * Y) * sizeof(double2), sp.copy_stream) != 0)) {
+                (c == 0 && sp.real && be_d2d(sp.peers[p] + (i64)sp.rank * BLK + SPQ, send + (i64)p * BLK + SPQ, (size_t)(X * Y) * sizeof(double2), sp.copy_stream) != 0)) {
                 set_error(std::string("peer copy failed: ") + be_last_error());
                 return NRB_ERR_CUDA;
             }
@@ -1604,7 +1614,7 @@ int slab_barrier_chunk(SlabPlan &sp, int phase, int chunk, unsigned long long ep
     if (chunk < 0 || chunk >= kSlabMaxChunks) { set_error("slab: bad chunk"); return NRB_ERR_INVALID_DIMS; }
     if (!sp.fused) { set_error("slab: the flag barrier needs the fused exchange (nrb_slab_set_peers)"); return NRB_ERR_INVALID_DIMS; }
     const u64 G = (u64)sp.nranks;
-    const size_t xchg = (size_t)(G * (sp.nn1 / G) * (sp.nn2 / G) * (sp.nn3 / 2 + 1));   // complex elements
+    const size_t xchg = sp.xchg_elems();   // complex elements
     AuxParams ap;
     memset(&ap, 0, sizeof(ap));
     ap.kind = phase == 0 ? AUX_SIGNAL : AUX_WAIT;
@@ -1624,8 +1634,7 @@ int exec_slab_stage(SlabPlan &sp, int stage, int isign, double *d_slab, double *
     if (stage != 0 && stage != 1) { set_error("stage must be 0 or 1"); return NRB_ERR_INVALID_DIMS; }
     if (sp.fused) {
         // stage 0 stores go straight to the peers; stage 1 reads the local receive buffer
-        const u64 G = (u64)sp.nranks;
-        const i64 BLK = (i64)((sp.nn1 / G) * (sp.nn2 / G) * (sp.nn3 / 2 + 1));
+        const i64 BLK = (i64)sp.blk();
         double2 *const base[4] = {(double2 *)d_slab, (double2 *)d_speq, sp.peers[sp.rank], (double2 *)sp.ws};
         PeerExchange px{sp.peers, (i64)sp.rank * BLK};
         return run_program(sp.prog[isign == 1 ? 0 : 1][stage], base, 0, stream, nullptr, stage == 0 ? &px : nullptr, nullptr, &sp.side);
@@ -1633,6 +1642,18 @@ int exec_slab_stage(SlabPlan &sp, int stage, int isign, double *d_slab, double *
     double2 *const base[4] = {(double2 *)d_slab, (double2 *)d_speq, (double2 *)(stage == 0 ? d_send : d_recv),
                               (double2 *)sp.ws};
     return run_program(sp.prog[isign == 1 ? 0 : 1][stage], base, 0, stream, nullptr, nullptr, nullptr, &sp.side);
+}
+
+int exec_slab_fused(SlabPlan &sp, int isign, double *d_slab, double *d_speq, unsigned long long epoch, void *stream)
+{
+    if (!sp.fused) { set_error("slab: nrb_slab_set_peers first"); return NRB_ERR_INVALID_DIMS; }
+    int rc = exec_slab_stage(sp, 0, isign, d_slab, d_speq, nullptr, nullptr, stream);
+    if (rc == NRB_OK && sp.nranks > 1) {
+        rc = slab_barrier(sp, 0, epoch, stream);            // my stage-0 stores have landed everywhere
+        if (rc == NRB_OK) rc = slab_barrier(sp, 1, epoch, stream);   // ... and so have everybody else's here
+    }
+    if (rc == NRB_OK) rc = exec_slab_stage(sp, 1, isign, d_slab, d_speq, nullptr, nullptr, stream);
+    return rc;
 }
 
 } // namespace nrb

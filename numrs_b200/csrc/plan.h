@@ -31,6 +31,11 @@ int be_ipc_release(void *dptr);
 int be_h2d(void *dst, const void *src, size_t bytes, void *stream);
 int be_d2h(void *dst, const void *src, size_t bytes, void *stream);
 int be_d2d(void *dst, const void *src, size_t bytes, void *stream);
+// strided copies (rows of `width` bytes): host [rows][spitch] -> device [rows][dpitch] and back
+int be_h2d_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows, void *stream);
+int be_d2h_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows, void *stream);
+// lets kernels on `dev` (made current by the call) store into `peer`'s memory; 0 also when it was enabled before
+int be_enable_peer(int dev, int peer);
 int be_sync(void *stream);
 int be_current_device();
 int be_device_count();
@@ -121,6 +126,9 @@ struct Tunables {
     int big_row_mask;      // bit log2n set: contiguous lines of 2^log2n points use the big-tile pass of fft_pass2.cuh (NRB_BIG_ROW_MASK)
     int big_col_mask;      // the same for strided lines (NRB_BIG_COL_MASK)
     int xchg_grid_cap;     // pipelined slab exchange: CTAs of an exchange (peer-store) pass, 0 = one per tile (NRB_XCHG_GRID_CAP)
+    int num_devices;       // GPUs the host-slice entry points spread one call over (NRB_NUM_DEVICES; 1 = the calling thread's
+                           // device only (default), 0 = every visible device, n = devices 0 .. n-1): multi.cpp
+    int shard_min_kb;      // batches smaller than this stay on one device (NRB_SHARD_MIN_KB, default 16 MiB)
 };
 const Tunables &tunables();
 int set_tunable(const char *name, long value);   // returns 0 if the name is known
@@ -178,6 +186,7 @@ int complex_multiply_device(double *d_a, const double *d_b, u64 ncomplex, int co
 // slab-decomposed rlft3 (one rank's share)
 struct SlabPlan {
     size_t nn1, nn2, nn3;
+    bool real;             // true: rlft3 (nn3 real points per line, speq plane); false: 3-D complex fourn (nn3 complex points)
     int nranks, rank;
     Program prog[2][2];    // [isign index][stage]
     // pipelined exchange: the volume is cut into `chunks` z-ranges; part[isign][0] = work that precedes the
@@ -199,10 +208,16 @@ struct SlabPlan {
     double2 *peers[8];     // peer receive buffers (fused exchange); peers[rank] is the local one
     bool fused;
     std::vector<TableRef> tables;   // twiddle tables the programs point into
-    SlabPlan() : nn1(0), nn2(0), nn3(0), nranks(1), rank(0), chunks(1), dma(false), send(nullptr), copy_stream(nullptr), side_stream(nullptr),
+    // N3 = complex points per z line; BLK = complex elements per exchange block (the speq part rides along for rlft3)
+    size_t n3c() const { return real ? nn3 / 2 : nn3; }
+    size_t blk() const { const size_t G = (size_t)nranks; return (nn1 / G) * (nn2 / G) * (n3c() + (real ? 1 : 0)); }
+    size_t xchg_elems() const { return (size_t)nranks * blk(); }
+    SlabPlan() : nn1(0), nn2(0), nn3(0), real(true), nranks(1), rank(0), chunks(1), dma(false), send(nullptr), copy_stream(nullptr), side_stream(nullptr),
                  ev_go(nullptr), ev_side(nullptr), ev_copy(nullptr), ev_s0{}, timeline(false), ws_elems(0), ws(nullptr), peers{}, fused(false) {}
 };
-int build_slab_plan(SlabPlan &sp, size_t nn1, size_t nn2, size_t nn3, int nranks, int rank);
+int build_slab_plan(SlabPlan &sp, size_t nn1, size_t nn2, size_t nn3, int nranks, int rank, bool real = true);
+// one whole direction of the fused exchange on `stream`: stage 0 (stores go to the peers), epoch-flag barrier, stage 1
+int exec_slab_fused(SlabPlan &sp, int isign, double *d_slab, double *d_speq, unsigned long long epoch, void *stream);
 // cut the exchange into `chunks` z-ranges (1 = off); allocates the out-of-place work slab
 int slab_set_chunks(SlabPlan &sp, int chunks);
 // part: -1 = before the chunks, chunks = after them, else stage `stage` of chunk `part` (fused exchange only)

@@ -1,4 +1,5 @@
-"""Slab-decomposed rlft3 across the GPUs of one box: one process per GPU (torch.distributed, NCCL).
+"""Slab-decomposed rlft3 (and 3-D complex fourn, `kind="fourn"`) across the GPUs of one box: one process per GPU
+(torch.distributed for the plumbing: IPC handle exchange, barriers; NCCL only in mode "nccl").
 
 Forward (isign=+1): rank r passes its nn2-slab data[:, r*nn2/G:(r+1)*nn2/G, :] (contiguous
 [nn1][nn2/G][nn3] real) and gets back, in the same buffer, its nn1-slab of the spectrum
@@ -25,11 +26,12 @@ import torch.distributed as dist
 
 
 class SlabRlft3:
-    def __init__(self, lib, nn1, nn2, nn3, mode="fused", barrier="flags", chunks=1):
+    def __init__(self, lib, nn1, nn2, nn3, mode="fused", barrier="flags", chunks=1, kind="rlft3"):
         self.lib = lib
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.dims = (nn1, nn2, nn3)
-        self.plan = lib.slab_create(nn1, nn2, nn3, self.world, self.rank)
+        self.kind = kind
+        self.plan = lib.slab_create(nn1, nn2, nn3, self.world, self.rank, kind=kind)
         self.local_doubles = self.plan.local_doubles()
         self.speq_doubles = self.plan.speq_doubles()
         self.xchg_doubles = self.plan.xchg_doubles()
@@ -67,13 +69,14 @@ class SlabRlft3:
         return 8.0 * self.xchg_doubles * (self.world - 1) / self.world
 
     def transform(self, slab, speq, isign):
-        """slab, speq: torch float64 CUDA tensors (local_doubles / speq_doubles); in place; enqueues on
-        the current stream."""
+        """slab, speq: torch float64 CUDA tensors (local_doubles / speq_doubles; speq = None for kind "fourn"); in
+        place; enqueues on the current stream."""
         st = torch.cuda.current_stream().cuda_stream
+        speq_ptr = speq.data_ptr() if speq is not None else 0
         if self.mode == "dma":
             self.plan.set_peers(self._peers[self._call & 1])
             self._call += 1
-            self.plan.exec_dma(isign, slab.data_ptr(), speq.data_ptr(), (self._call + 1) // 2, st)
+            self.plan.exec_dma(isign, slab.data_ptr(), speq_ptr, (self._call + 1) // 2, st)
         elif self.mode == "fused":
             peers = self._peers[self._call & 1]
             self._call += 1
@@ -81,23 +84,22 @@ class SlabRlft3:
             if self.chunks > 1:
                 self._pipelined(slab, speq, isign, (self._call + 1) // 2)
                 return
-            self.plan.stage(0, isign, slab.data_ptr(), speq.data_ptr(), 0, 0, st)
             if self.barrier == "flags":
-                epoch = (self._call + 1) // 2            # per receive buffer: 1, 2, 3, ...
-                self.plan.barrier(0, epoch, st)          # my stage-0 stores have landed everywhere
-                self.plan.barrier(1, epoch, st)          # ... and so have everybody else's here
-            else:
-                dist.all_reduce(self._flag)              # stream-ordered NCCL barrier
-            self.plan.stage(1, isign, slab.data_ptr(), speq.data_ptr(), 0, 0, st)
+                # stage 0 (stores land in the peers' receive buffers), epoch-flag barrier, stage 1: one C call
+                self.plan.exec(isign, slab.data_ptr(), speq_ptr, (self._call + 1) // 2, st)   # epoch per receive buffer: 1, 2, ...
+                return
+            self.plan.stage(0, isign, slab.data_ptr(), speq_ptr, 0, 0, st)
+            dist.all_reduce(self._flag)                  # stream-ordered NCCL barrier
+            self.plan.stage(1, isign, slab.data_ptr(), speq_ptr, 0, 0, st)
         else:
-            self.plan.stage(0, isign, slab.data_ptr(), speq.data_ptr(), self.send.data_ptr(), 0, st)
+            self.plan.stage(0, isign, slab.data_ptr(), speq_ptr, self.send.data_ptr(), 0, st)
             dist.all_to_all_single(self.recv, self.send)
-            self.plan.stage(1, isign, slab.data_ptr(), speq.data_ptr(), 0, self.recv.data_ptr(), st)
+            self.plan.stage(1, isign, slab.data_ptr(), speq_ptr, 0, self.recv.data_ptr(), st)
 
     def _pipelined(self, slab, speq, isign, epoch):
         main = torch.cuda.current_stream()
         st, sd = main.cuda_stream, self._side.cuda_stream
-        d, q, C = slab.data_ptr(), speq.data_ptr(), self.chunks
+        d, q, C = slab.data_ptr(), (speq.data_ptr() if speq is not None else 0), self.chunks
         self.plan.stage_part(0, -1, isign, d, q, st)              # forward: z pass (slab -> work)
         self._ev_go.record(main)
         self._side.wait_event(self._ev_go)

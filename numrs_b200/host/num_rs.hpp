@@ -369,7 +369,20 @@ inline std::vector<double> autocorrel(const std::vector<double> &a) { return cor
 inline std::vector<std::vector<double>> correl_batch(const std::vector<std::pair<std::vector<double>, std::vector<double>>> &pairs)
 {
     std::vector<std::vector<double>> out;
-    for (const auto &p : pairs) out.push_back(correl(p.first, p.second));
+    if (pairs.empty()) return out;
+    const std::size_t n = pairs[0].first.size();
+    bool uniform = n > 0;
+    for (const auto &p : pairs) uniform = uniform && p.first.size() == n && p.second.size() == n;
+    if (!uniform) {      // mixed lengths (or an error to report per pair): one call each, as the reference's par_iter does
+        for (const auto &p : pairs) out.push_back(correl(p.first, p.second));
+        return out;
+    }
+    // one device batch (sharded over the GPUs when the option num_devices says so)
+    std::vector<const double *> a, b;
+    std::vector<double *> o;
+    out.assign(pairs.size(), std::vector<double>(n));
+    for (std::size_t i = 0; i < pairs.size(); ++i) { a.push_back(pairs[i].first.data()); b.push_back(pairs[i].second.data()); o.push_back(out[i].data()); }
+    raise(nrb_correl_batch(a.data(), b.data(), pairs.size(), n, o.data()));
     return out;
 }
 

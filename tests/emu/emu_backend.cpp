@@ -12,6 +12,7 @@
 #include <time.h>
 #include <ucontext.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -139,11 +140,14 @@ template <int LOG2N, int LAYOUT, int VARIANT> static void reg2()
     g_table2[LOG2N][LAYOUT][0][VARIANT] = Entry2{body2_tpl<LOG2N, LAYOUT, -1, VARIANT>, G::NT, smem, G::L};
 }
 
+static void fill_table();
 static void init_table()
 {
-    static bool done = false;
-    if (done) return;
-    done = true;
+    static std::once_flag once;      // several device workers (multi.cpp) may launch their first kernel at the same time
+    std::call_once(once, fill_table);
+}
+static void fill_table()
+{
     using namespace nrb;
     reg<1, 0>(); reg<2, 0>(); reg<3, 0>(); reg<4, 0>(); reg<5, 0>(); reg<6, 0>(); reg<7, 0>();
     reg<8, 0>(); reg<9, 0>(); reg<10, 0>(); reg<11, 0>(); reg<12, 0>(); reg<13, 0>();
@@ -331,9 +335,26 @@ int be_h2d(void *d, const void *s, size_t n, void *) { memcpy(d, s, n); return 0
 int be_d2h(void *d, const void *s, size_t n, void *) { memcpy(d, s, n); return 0; }
 int be_d2d(void *d, const void *s, size_t n, void *) { memmove(d, s, n); return 0; }
 int be_sync(void *) { return 0; }
-int be_current_device() { return 0; }
-int be_device_count() { return 1; }
-int be_set_device(int dev) { return dev == 0 ? 0 : -1; }
+// NRB_EMU_DEVICES = n pretends there are n devices (all of them host memory) so the multi-device host-slice paths of
+// multi.cpp can run in the CPU test tier; the current device is per thread, as in CUDA
+static int emu_devices()
+{
+    const char *v = getenv("NRB_EMU_DEVICES");
+    const int n = (v && *v) ? atoi(v) : 1;
+    return n < 1 ? 1 : n > 8 ? 8 : n;
+}
+static thread_local int t_emu_device = 0;
+int be_current_device() { return t_emu_device; }
+int be_device_count() { return emu_devices(); }
+int be_set_device(int dev) { if (dev < 0 || dev >= emu_devices()) return -1; t_emu_device = dev; return 0; }
+static int copy_2d(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t rows)
+{
+    for (size_t r = 0; r < rows; ++r) memcpy((char *)d + r * dp, (const char *)s + r * sp, w);
+    return 0;
+}
+int be_h2d_2d(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t rows, void *) { return copy_2d(d, dp, s, sp, w, rows); }
+int be_d2h_2d(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t rows, void *) { return copy_2d(d, dp, s, sp, w, rows); }
+int be_enable_peer(int dev, int peer) { return (be_set_device(dev) == 0 && peer >= 0 && peer < emu_devices()) ? 0 : -1; }
 int be_stream_create(void **s) { *s = (void *)1; return 0; }
 int be_stream_destroy(void *) { return 0; }
 void *be_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 16); }

@@ -8,8 +8,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_json_line():
+    # launched the way torchrun launches its children (OMP_NUM_THREADS=1): the arm must still use every host core
+    env = dict(os.environ, OMP_NUM_THREADS="1")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                         capture_output=True, text=True, timeout=300)
+                         capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stderr
     lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
@@ -20,6 +22,10 @@ def test_reference_arm_json_line():
     assert d["impl"] == "reference" and d["unit"] == "GB/s" and d["dtype"] == "f64" and d["vs_baseline"] is None
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and "workload" in d["config"]
+    # the arm times the configuration it prints: the full 512^3 volume, on all the cores this process may use
+    assert d["config"]["dims"] == [512, 512, 512] and d["config"]["sample_is_full_workload"] is True
+    assert "512x512x512" in d["cpu_baseline"]["sample"] and "full volume" in d["cpu_baseline"]["sample"]
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
 
 
 def test_reference_arm_other_ranks_are_silent():

@@ -447,6 +447,10 @@ def test_convlv_correl_transposed_spectrum_path(emu, n):
 
 def test_convlv_default_plan_uses_two_passes_per_transform(emu):
     plan = emu.plan_create(nb.KIND_CORREL, [1 << 15], batch=1)
+    assert plan.num_launches(1) == 5          # second operand 2 passes; strided pass, fused middle, strided pass (conv_fused_mid)
+    plan.destroy()
+    emu.set_option("conv_fused_mid", 0)
+    plan = emu.plan_create(nb.KIND_CORREL, [1 << 15], batch=1)
     assert plan.num_launches(1) == 7          # 2 + 2 forward, spectral, 2 inverse
     plan.destroy()
     emu.set_option("conv_transposed", 0)

@@ -292,6 +292,57 @@ def test_full_size_rlft3_512_properties(gpu):
     assert cases.rel(d, x) <= cases.tol(n ** 3)
 
 
+def test_full_size_rlft3_512_elementwise_vs_oracle(gpu):
+    """BASELINE config 5 at the benchmarked size, element by element against the oracle (Real_FT3.rs:8-141 semantics,
+    ledger D3/D4): the forward spectrum and its speq plane, the inverse of that spectrum, and the inverse of a spectrum
+    that is NOT Hermitian-consistent (NR's general formula for the DC / Nyquist pair)."""
+    n = 512
+    O.use_all_cores()
+    x = O.fill_uniform(1006, 0, n ** 3).reshape(n, n, n)
+    rd, rs = O.rlft3(x.copy(), np.zeros((n, 2 * n)), 1, mt=True)
+    d, s = x.copy(), np.zeros((n, 2 * n))
+    nb.rlft3(d, s, n, n, n, 1)
+    assert cases.rel(d, rd) <= cases.tol(n ** 3) and cases.rel(s, rs) <= cases.tol(n ** 3)
+    bd, _ = O.rlft3(rd.copy(), rs.copy(), -1, mt=True)
+    nb.rlft3(d, s, n, n, n, -1)
+    assert cases.rel(d, bd) <= cases.tol(n ** 3)
+    assert cases.rel(d * (2.0 / float(n) ** 3), x) <= cases.tol(n ** 3)
+    del rd, bd
+    g = O.fill_uniform(77, 0, n ** 3).reshape(n, n, n)
+    gs = O.fill_uniform(78, 0, 2 * n * n).reshape(n, 2 * n)
+    want, _ = O.rlft3(g.copy(), gs.copy(), -1, mt=True)
+    nb.rlft3(g, gs, n, n, n, -1)
+    assert cases.rel(g, want) <= cases.tol(n ** 3)
+
+
+def test_full_size_fourn_8192x8192_elementwise_vs_oracle(gpu):
+    """BASELINE config 3 at the benchmarked size, element by element against the oracle's in-memory fourn, both signs."""
+    n = 8192
+    O.use_all_cores()
+    x = O.fill_uniform(1003, 0, 2 * n * n)
+    for isign in (1, -1):
+        ref = O.fourn(x.copy(), [n, n], isign, mt=True)
+        y = x.copy()
+        nb.fourn(y, [n, n], 2, isign)
+        assert cases.rel(y, ref) <= cases.tol(n * n), isign
+        del ref, y
+
+
+def test_full_size_fourn3d_512_elementwise_vs_oracle(gpu):
+    """north_star's 3-D complex fourn at 512^3 (2 GiB), element by element against the oracle, isign = +1, and the round trip."""
+    n = 512
+    O.use_all_cores()
+    x = O.fill_uniform(1008, 0, 2 * n ** 3)
+    ref = O.fourn(x.copy(), [n, n, n], 1, mt=True)
+    y = x.copy()
+    nb.fourn(y, [n, n, n], 3, 1)
+    assert cases.rel(y, ref) <= cases.tol(n ** 3)
+    del ref
+    nb.fourn(y, [n, n, n], 3, -1)
+    y /= float(n) ** 3
+    assert cases.rel(y, x) <= cases.tol(n ** 3)
+
+
 def test_full_size_convlv_correl_2pow22(gpu):
     """BASELINE config 4 shape (n = 2^22, m = 4096), reduced batch: oracle parity per signal."""
     n, m, cnt = 1 << 22, 4096, 3

@@ -48,6 +48,73 @@ def test_four1_vs_mpmath():
     assert err < 1e-13
 
 
+# ---- every routine the reference's own tests do not pin is checked against a 50-digit DFT at N <= 64 ----
+def _mp_dft(vals, shape, sign):
+    """Unnormalised DFT of the (possibly N-D) array `vals` (flat, row-major) with exp(sign * 2 pi i sum k_d j_d / n_d), 50 digits."""
+    import itertools
+
+    import mpmath as mp
+    mp.mp.dps = 50
+    idx = list(itertools.product(*[range(n) for n in shape]))
+    roots = [[mp.e ** (sign * 2j * mp.pi * m / n) for m in range(n)] for n in shape]
+    out = []
+    for k in idx:
+        acc = mp.mpc(0)
+        for j, v in zip(idx, vals):
+            w = mp.mpc(1)
+            for d, n in enumerate(shape):
+                w *= roots[d][(k[d] * j[d]) % n]
+            acc += v * w
+        out.append(acc)
+    return out
+
+
+@pytest.mark.parametrize("n", [2, 4, 16, 64])
+def test_realft_vs_mpmath(n):
+    """NR realft (Real_FT.rs:4-21, ledger D1/D2): forward = packed half spectrum of F_k = sum x_j e^{+2 pi i jk/n}; the
+    inverse of that spectrum returns (n/2) x."""
+    import mpmath as mp
+    x = O.fill_uniform(1010, 3, n)
+    F = _mp_dft([mp.mpf(v) for v in x], (n,), +1)
+    got = O.realft(x.copy(), n, 1)
+    want = [F[0].real, F[n // 2].real] + [p for k in range(1, n // 2) for p in (F[k].real, F[k].imag)]
+    assert max(abs(float(w) - g) for w, g in zip(want, got)) < 1e-13 * max(1.0, float(np.linalg.norm(x)))
+    back = O.realft(got.copy(), n, -1)
+    assert np.max(np.abs(back / (n / 2) - x)) < 1e-14 * n
+
+
+@pytest.mark.parametrize("shape", [(4, 8), (2, 4, 8), (8, 8), (4, 4, 4)])
+def test_fourn_vs_mpmath(shape):
+    """NR in-memory fourn (call shape Real_FT3.rs:35, ledger D3): last index fastest, exp(isign * 2 pi i sum k_d j_d / nn_d)."""
+    import mpmath as mp
+    n = int(np.prod(shape))
+    x = O.fill_uniform(1011, 5, 2 * n)
+    z = [mp.mpc(x[2 * k], x[2 * k + 1]) for k in range(n)]
+    for isign in (1, -1):
+        ref = _mp_dft(z, shape, isign)
+        got = c(O.fourn(x.copy(), list(shape), isign))
+        assert max(abs(complex(r) - g) for r, g in zip(ref, got)) < 1e-13 * np.sqrt(n)
+
+
+@pytest.mark.parametrize("shape", [(2, 2, 4), (4, 2, 8), (2, 4, 4), (4, 4, 4)])
+def test_rlft3_vs_mpmath(shape):
+    """NR rlft3 (Real_FT3.rs:8-141, ledger D3/D4): data[i1][i2][2k..2k+1] = F(i1, i2, k) for k < nn3/2 and
+    speq[i1][2 i2 .. 2 i2 + 1] = F(i1, i2, nn3/2) with F = sum x e^{+2 pi i (...)}; the inverse returns (N/2) x."""
+    import mpmath as mp
+    nn1, nn2, nn3 = shape
+    n = nn1 * nn2 * nn3
+    x = O.fill_uniform(1012, 9, n).reshape(shape)
+    F = _mp_dft([mp.mpf(v) for v in x.ravel()], shape, +1)
+    F = np.array([complex(v) for v in F]).reshape(shape)
+    d, s = O.rlft3(x.copy(), np.zeros((nn1, 2 * nn2)), 1)
+    dc = d.reshape(nn1, nn2, nn3 // 2, 2)
+    assert np.max(np.abs((dc[..., 0] + 1j * dc[..., 1]) - F[:, :, :nn3 // 2])) < 1e-13 * np.sqrt(n)
+    sc = s.reshape(nn1, nn2, 2)
+    assert np.max(np.abs((sc[..., 0] + 1j * sc[..., 1]) - F[:, :, nn3 // 2])) < 1e-13 * np.sqrt(n)
+    back, _ = O.rlft3(d.copy(), s.copy(), -1)
+    assert np.max(np.abs(back * (2.0 / n) - x)) < 1e-14 * n
+
+
 def test_four1_reference_round_trip():
     # FFT_1.rs:246-267
     n = 1024

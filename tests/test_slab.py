@@ -76,6 +76,71 @@ def test_slab_simulated_ranks(emu, shape, G, fused, side):
         assert cases.rel(back[r] * (2.0 / x.size), slab_of(x, r, G)) <= cases.tol(x.size), (r, "round trip")
 
 
+def run_simulated_fourn(L, z, G, isign, chunks=1):
+    """3-D complex fourn slabs, all G ranks in one process (fused exchange; chunks > 1: the pipelined pieces).
+    z: complex [nn1][nn2][nn3]; isign=+1 takes nn2-slabs and returns nn1-slabs, isign=-1 the mirror image."""
+    nn1, nn2, nn3 = z.shape
+    X, Y = nn1 // G, nn2 // G
+    plans = [L.slab_create(nn1, nn2, nn3, G, r, kind="fourn") for r in range(G)]
+    assert plans[0].speq_doubles() == 0 and plans[0].local_doubles() == 2 * z.size // G
+    xd = plans[0].xchg_doubles()
+    if isign == 1:
+        slabs = [np.ascontiguousarray(z[:, r * Y:(r + 1) * Y, :]).view(np.float64).ravel().copy() for r in range(G)]
+    else:
+        slabs = [np.ascontiguousarray(z[r * X:(r + 1) * X]).view(np.float64).ravel().copy() for r in range(G)]
+    recvs = [np.zeros(plans[0].recv_bytes() // 8) for _ in range(G)]
+    for r in range(G):
+        plans[r].set_peers([rv.ctypes.data for rv in recvs])
+    if chunks == 1:
+        for r in range(G):
+            plans[r].stage(0, isign, slabs[r].ctypes.data, 0, 0, 0)
+        for r in range(G):
+            plans[r].barrier(0, 1)
+        for r in range(G):
+            plans[r].barrier(1, 1)
+            assert list(recvs[r][xd:xd + G].view(np.uint64)) == [1] * G
+            plans[r].stage(1, isign, slabs[r].ctypes.data, 0, 0, 0)
+    else:
+        for r in range(G):
+            plans[r].set_chunks(chunks)
+            plans[r].stage_part(0, -1, isign, slabs[r].ctypes.data, 0)
+        for c in range(chunks):
+            for r in range(G):
+                plans[r].stage_part(0, c, isign, slabs[r].ctypes.data, 0)
+                plans[r].barrier_chunk(0, c, 1)
+            for r in range(G):
+                plans[r].barrier_chunk(1, c, 1)
+                plans[r].stage_part(1, c, isign, slabs[r].ctypes.data, 0)
+        for r in range(G):
+            plans[r].stage_part(0, chunks, isign, slabs[r].ctypes.data, 0)
+    for p in plans:
+        p.destroy()
+    return [s.view(np.complex128) for s in slabs]
+
+
+@pytest.mark.parametrize("shape,G,chunks", [((8, 8, 8), 2, 1), ((16, 16, 4), 4, 1), ((8, 16, 32), 8, 1), ((64, 128, 32), 8, 1),
+                                            ((4, 4, 2), 4, 1), ((8, 8, 4), 1, 1), ((8, 8, 32), 2, 2), ((16, 16, 64), 4, 4)])
+def test_fourn3d_slabs_simulated_ranks(emu, shape, G, chunks):
+    """Slab-decomposed 3-D complex fourn (call shape Real_FT3.rs:35) against the oracle's in-memory fourn: forward
+    spectrum element-wise (nn1-slabs = row ranges of the reference layout), the inverse, and the round trip."""
+    nn1, nn2, nn3 = shape
+    X, Y = nn1 // G, nn2 // G
+    n = nn1 * nn2 * nn3
+    x = O.fill_uniform(1008, 0, 2 * n)
+    ref = O.fourn(x.copy(), list(shape), 1).view(np.complex128).reshape(shape)
+    z = x.view(np.complex128).reshape(shape)
+    out = run_simulated_fourn(emu, z, G, 1, chunks)
+    for r in range(G):
+        assert cases.rel(out[r].view(np.float64), np.ascontiguousarray(ref[r * X:(r + 1) * X]).view(np.float64)) <= cases.tol(n), (r, "forward")
+    refm = O.fourn(x.copy(), list(shape), -1).view(np.complex128).reshape(shape)
+    outm = run_simulated_fourn(emu, z[:, :, :].copy(), G, -1, chunks)       # isign = -1: input nn1-slabs, output nn2-slabs
+    for r in range(G):
+        assert cases.rel(outm[r].view(np.float64), np.ascontiguousarray(refm[:, r * Y:(r + 1) * Y, :]).view(np.float64)) <= cases.tol(n), (r, "inverse")
+    back = run_simulated_fourn(emu, ref, G, -1, chunks)
+    for r in range(G):
+        assert cases.rel(back[r].view(np.float64) / n, np.ascontiguousarray(z[:, r * Y:(r + 1) * Y, :]).view(np.float64)) <= cases.tol(n), (r, "round trip")
+
+
 def run_simulated_pipelined(L, x, G, isign, chunks, speq_in=None):
     """Pipelined (z-chunked) fused exchange with all G ranks in one process.  The emulated flag wait does not
     block, so the test orders the pieces itself: stage 0 of chunk c on every rank, then stage 1 of chunk c."""
