@@ -72,8 +72,17 @@ static int fail(cudaError_t e)
 }
 const char *be_last_error() { return g_be_err.c_str(); }
 
+// TMA-fed strided pass (fft_tma.cuh, k_tma.cu): taken for the line lengths in the option tma_col_mask when eligible
+bool tma_pass_eligible(const KernelKey &key, const PassParams &p, u64 ntiles);
+int launch_tma_pass(const KernelKey &key, const PassParams &p, u64 ntiles, int persist, cudaStream_t s);
+
 int be_launch_pass(const KernelKey &key, const PassParams &p, u64 ntiles, void *stream)
 {
+    if (((tunables().tma_col_mask >> key.log2n) & 1) && tma_pass_eligible(key, p, ntiles)) {
+        const int rc = launch_tma_pass(key, p, ntiles, tunables().tma_persist, (cudaStream_t)stream);
+        if (rc != 0) return fail((cudaError_t)rc);
+        return 0;
+    }
     if (key.log2n < 1 || key.log2n > kMaxLog2N || key.layout < 0 || key.layout > 1 || key.variant < 0 || key.variant > 2) {
         g_be_err = "no such kernel";
         return -1;

@@ -270,7 +270,10 @@ template <int LOG2N, int LAYOUT> NRB_HD constexpr bool simple_ok()
                                 : (cta_threads(LOG2N, LAYOUT) % lines_per_tile(LOG2N, LAYOUT)) == 0;
 }
 
-template <int LOG2N, int LAYOUT, int DIR, int VARIANT, int S, bool SRC_G, bool DST_G, bool SIMPLE = false>
+// TMA_IO (fft_tma.cuh: the tile is brought into and taken out of shared memory by bulk tensor copies, so every stage
+// runs shared -> shared): bit 0 = this stage reads the tile as it came from global memory, bit 1 = it writes the tile
+// that goes back to global memory; those are the two places where the isign = +1 re/im swap has to happen instead.
+template <int LOG2N, int LAYOUT, int DIR, int VARIANT, int S, bool SRC_G, bool DST_G, bool SIMPLE = false, int TMA_IO = 0>
 NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
 {
     typedef Geo<LOG2N, LAYOUT, VARIANT> G;
@@ -355,7 +358,10 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
             for (int r = 0; r < R; ++r) v[i][r] = sp[r * NB + ((r * NB) >> 3)];
         } else {
 #pragma unroll
-            for (int r = 0; r < R; ++r) v[i][r] = sm[G::phys(ln[i], jj[i] + r * NB)];
+            for (int r = 0; r < R; ++r) {
+                const double2 x = sm[G::phys(ln[i], jj[i] + r * NB)];
+                v[i][r] = (TMA_IO & 1) ? io_swap<DIR>(x) : x;
+            }
         }
     }
     if (SRC_G && FAST) {
@@ -526,14 +532,14 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
             for (int r = 0; r < R; ++r) sp[r * NS + ((r * NS) >> 3)] = v[i][r];
         } else {
 #pragma unroll
-            for (int r = 0; r < R; ++r) sm[G::phys(ln[i], kb + r * NS)] = v[i][r];
+            for (int r = 0; r < R; ++r) sm[G::phys(ln[i], kb + r * NS)] = (TMA_IO & 2) ? io_swap<DIR>(v[i][r]) : v[i][r];
         }
     }
 }
 
 // run stages FIRST..NST-1; stage FIRST reads global iff SRC_G0, the last stage writes global
 // iff DST_GL.  Barriers: after every stage that wrote shared memory.
-template <int LOG2N, int LAYOUT, int DIR, int VARIANT, int S, bool SRC_G0, bool DST_GL, bool SIMPLE = false>
+template <int LOG2N, int LAYOUT, int DIR, int VARIANT, int S, bool SRC_G0, bool DST_GL, bool SIMPLE = false, bool TMA = false>
 struct StageRunner {
     NRB_DEVM static void run(const PassParams &P, double2 *sm, unsigned tile, int tid)
     {
@@ -541,13 +547,14 @@ struct StageRunner {
         constexpr bool last = (S == NST - 1);
         constexpr bool src_g = (S == 0) && SRC_G0;
         constexpr bool dst_g = last && DST_GL;
-        fft_stage<LOG2N, LAYOUT, DIR, VARIANT, S, src_g, dst_g, SIMPLE>(P, sm, tile, tid);
+        constexpr int tma_io = TMA ? ((S == 0 ? 1 : 0) | (last ? 2 : 0)) : 0;
+        fft_stage<LOG2N, LAYOUT, DIR, VARIANT, S, src_g, dst_g, SIMPLE, tma_io>(P, sm, tile, tid);
         if (!dst_g) stage_sync<LOG2N, LAYOUT>();
-        StageRunner<LOG2N, LAYOUT, DIR, VARIANT, last ? -1 : S + 1, SRC_G0, DST_GL, SIMPLE>::run(P, sm, tile, tid);
+        StageRunner<LOG2N, LAYOUT, DIR, VARIANT, last ? -1 : S + 1, SRC_G0, DST_GL, SIMPLE, TMA>::run(P, sm, tile, tid);
     }
 };
-template <int LOG2N, int LAYOUT, int DIR, int VARIANT, bool SRC_G0, bool DST_GL, bool SIMPLE>
-struct StageRunner<LOG2N, LAYOUT, DIR, VARIANT, -1, SRC_G0, DST_GL, SIMPLE> {
+template <int LOG2N, int LAYOUT, int DIR, int VARIANT, bool SRC_G0, bool DST_GL, bool SIMPLE, bool TMA>
+struct StageRunner<LOG2N, LAYOUT, DIR, VARIANT, -1, SRC_G0, DST_GL, SIMPLE, TMA> {
     NRB_DEVM static void run(const PassParams &, double2 *, unsigned, int) {}
 };
 

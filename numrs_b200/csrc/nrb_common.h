@@ -185,9 +185,15 @@ NRB_HD constexpr int stage_tw_total(int log2n)
 #ifndef NRB_TL_ROW
 #define NRB_TL_ROW 9
 #endif
+// COL line lengths (bit log2n) that take 8192-point tiles (twice the lines per tile: global runs of 2 L x 16 bytes, one CTA
+// per SM) instead of 4096-point ones
+#ifndef NRB_TL_COL13_MASK
+#define NRB_TL_COL13_MASK 0
+#endif
 NRB_HD constexpr int tile_log2(int log2n, int layout)
 {
-    return layout == 0 /* ROW */ ? (log2n > NRB_TL_ROW ? log2n : NRB_TL_ROW) : (log2n > 12 ? log2n : 12);
+    return layout == 0 /* ROW */ ? (log2n > NRB_TL_ROW ? log2n : NRB_TL_ROW)
+                                 : (log2n > 12 ? log2n : (((NRB_TL_COL13_MASK >> log2n) & 1) ? 13 : 12));
 }
 NRB_HD constexpr int cta_threads(int log2n, int layout) { return (1 << tile_log2(log2n, layout)) / points_per_thread(layout, log2n); }
 

@@ -56,6 +56,9 @@ static Tunables &tunables_mut()
         x.conv_fused_mid = env_int("NRB_CONV_FUSED_MID", 1);
         x.big_row_mask = env_int("NRB_BIG_ROW_MASK", 0);
         x.big_col_mask = env_int("NRB_BIG_COL_MASK", 0);
+        x.dma_streams = env_int("NRB_DMA_STREAMS", 1);
+        x.tma_col_mask = env_int("NRB_TMA_COL_MASK", 0);
+        x.tma_persist = env_int("NRB_TMA_PERSIST", 0);
         x.num_devices = env_int("NRB_NUM_DEVICES", 1);
         x.shard_min_kb = env_int("NRB_SHARD_MIN_KB", 16384);
         return x;
@@ -89,6 +92,9 @@ int set_tunable(const char *name, long value)
     else if (n == "conv_fused_mid") t.conv_fused_mid = (int)value;
     else if (n == "big_row_mask") t.big_row_mask = (int)value;
     else if (n == "big_col_mask") t.big_col_mask = (int)value;
+    else if (n == "dma_streams") t.dma_streams = value < 1 ? 1 : value > 4 ? 4 : (int)value;
+    else if (n == "tma_col_mask") t.tma_col_mask = (int)value;
+    else if (n == "tma_persist") t.tma_persist = (int)value;
     else if (n == "num_devices") t.num_devices = value < 0 ? 1 : (int)value;
     else if (n == "shard_min_kb") t.shard_min_kb = value < 0 ? 0 : (int)value;
     else return -1;
@@ -1484,6 +1490,10 @@ int slab_set_dma(SlabPlan &sp, int chunks)
     if (!sp.copy_stream) {
         if (be_stream_create_prio(&sp.copy_stream, 0) != 0 || be_stream_create_prio(&sp.side_stream, 1) != 0) { set_error("slab: stream creation failed"); return NRB_ERR_CUDA; }
         sp.ev_go = be_event_create(); sp.ev_side = be_event_create(); sp.ev_copy = be_event_create();
+        for (int k = 0; k < 3; ++k) {
+            if (be_stream_create_prio(&sp.copy_extra[k], 0) != 0) { set_error("slab: stream creation failed"); return NRB_ERR_CUDA; }
+            sp.ev_extra[k] = be_event_create();
+        }
         for (int c = 0; c < kSlabMaxChunks; ++c) sp.ev_s0[c] = be_event_create();
     }
     sp.chunks = chunks;
@@ -1497,6 +1507,11 @@ void slab_release(SlabPlan &sp)
     if (sp.ws) be_free(sp.ws);
     if (sp.send) be_free(sp.send);
     if (sp.copy_stream) be_stream_destroy(sp.copy_stream);
+    for (int k = 0; k < 3; ++k) {
+        if (sp.copy_extra[k]) be_stream_destroy(sp.copy_extra[k]);
+        if (sp.ev_extra[k]) be_event_destroy(sp.ev_extra[k]);
+        sp.copy_extra[k] = sp.ev_extra[k] = nullptr;
+    }
     if (sp.side_stream) be_stream_destroy(sp.side_stream);
     for (void *e : {sp.ev_go, sp.ev_side, sp.ev_copy}) if (e) be_event_destroy(e);
     for (int c = 0; c < kSlabMaxChunks; ++c) if (sp.ev_s0[c]) be_event_destroy(sp.ev_s0[c]);
@@ -1561,14 +1576,23 @@ int exec_slab_dma(SlabPlan &sp, int isign, double *d_slab, double *d_speq, unsig
         if ((rc = exec_slab_part(sp, 0, c, isign, d_slab, d_speq, stream, (double *)send))) return rc;
         mark("s0", c, stream);
         if (be_event_record_on(sp.ev_s0[c], stream) || be_stream_wait(sp.copy_stream, sp.ev_s0[c])) { set_error("stream ordering failed"); return NRB_ERR_CUDA; }
+        int ns = tunables().dma_streams;
+        if (ns > (int)G - 1) ns = (int)G - 1;
+        if (ns < 1) ns = 1;
+        for (int k = 1; k < ns; ++k)
+            if (be_stream_wait(sp.copy_extra[k - 1], sp.ev_s0[c])) { set_error("stream ordering failed"); return NRB_ERR_CUDA; }
         for (u64 i = 1; i < G; ++i) {                     // rotated so that every rank targets a different peer at a time;
             const u64 p = ((u64)sp.rank + i) % G;         // the own block went straight into the own receive buffer
-            if (be_d2d(sp.peers[p] + (i64)sp.rank * BLK + (i64)c * PIECE, send + (i64)p * BLK + (i64)c * PIECE, (size_t)PIECE * sizeof(double2), sp.copy_stream) != 0 ||
-                (c == 0 && sp.real && be_d2d(sp.peers[p] + (i64)sp.rank * BLK + SPQ, send + (i64)p * BLK + SPQ, (size_t)(X * Y) * sizeof(double2), sp.copy_stream) != 0)) {
+            const int k = (int)((i - 1) % (u64)ns);
+            void *cs = k == 0 ? sp.copy_stream : sp.copy_extra[k - 1];
+            if (be_d2d(sp.peers[p] + (i64)sp.rank * BLK + (i64)c * PIECE, send + (i64)p * BLK + (i64)c * PIECE, (size_t)PIECE * sizeof(double2), cs) != 0 ||
+                (c == 0 && sp.real && be_d2d(sp.peers[p] + (i64)sp.rank * BLK + SPQ, send + (i64)p * BLK + SPQ, (size_t)(X * Y) * sizeof(double2), cs) != 0)) {
                 set_error(std::string("peer copy failed: ") + be_last_error());
                 return NRB_ERR_CUDA;
             }
         }
+        for (int k = 1; k < ns; ++k)      // the flag of the chunk follows ALL its copies
+            if (be_event_record_on(sp.ev_extra[k - 1], sp.copy_extra[k - 1]) || be_stream_wait(sp.copy_stream, sp.ev_extra[k - 1])) { set_error("stream ordering failed"); return NRB_ERR_CUDA; }
         mark("copy", c, sp.copy_stream);
         if ((rc = slab_barrier_chunk(sp, 0, c, epoch, sp.copy_stream))) return rc;     // chunk c of this rank has landed everywhere
         if ((rc = slab_barrier_chunk(sp, 1, c, epoch, sp.side_stream))) return rc;     // chunk c of every rank has landed here

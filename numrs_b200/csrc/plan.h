@@ -128,6 +128,11 @@ struct Tunables {
     int xchg_grid_cap;     // pipelined slab exchange: CTAs of an exchange (peer-store) pass, 0 = one per tile (NRB_XCHG_GRID_CAP)
     int num_devices;       // GPUs the host-slice entry points spread one call over (NRB_NUM_DEVICES; 1 = the calling thread's
                            // device only (default), 0 = every visible device, n = devices 0 .. n-1): multi.cpp
+    int dma_streams;       // DMA slab exchange: copy streams the pieces of a chunk are spread over (NRB_DMA_STREAMS, 1 .. 4, default 1)
+    int tma_col_mask;      // bit log2n set: eligible strided PLAIN passes of 2^log2n points use the TMA-fed kernel of fft_tma.cuh
+                           // (NRB_TMA_COL_MASK, default 0: see profiles/r02_tuning.md for the A/B); tma_persist = 1: persistent
+                           // CTAs with two tile buffers (the next tile's bulk load in flight during the stages)
+    int tma_persist;
     int shard_min_kb;      // batches smaller than this stay on one device (NRB_SHARD_MIN_KB, default 16 MiB)
 };
 const Tunables &tunables();
@@ -199,6 +204,9 @@ struct SlabPlan {
     bool dma;
     void *send;                  // owned, xchg size
     void *copy_stream, *side_stream, *ev_go, *ev_side, *ev_copy, *ev_s0[16];
+    // extra copy streams (tunable dma_streams > 1): the pieces for different peers go to different streams so that
+    // several copy engines work at once; copy_stream waits for them before it publishes the chunk's flag
+    void *copy_extra[3], *ev_extra[3];
     bool timeline;               // diagnostics: timing events around every piece of the last exec_slab_dma
     std::vector<void *> tl_events;
     std::vector<std::string> tl_names;
@@ -213,7 +221,7 @@ struct SlabPlan {
     size_t blk() const { const size_t G = (size_t)nranks; return (nn1 / G) * (nn2 / G) * (n3c() + (real ? 1 : 0)); }
     size_t xchg_elems() const { return (size_t)nranks * blk(); }
     SlabPlan() : nn1(0), nn2(0), nn3(0), real(true), nranks(1), rank(0), chunks(1), dma(false), send(nullptr), copy_stream(nullptr), side_stream(nullptr),
-                 ev_go(nullptr), ev_side(nullptr), ev_copy(nullptr), ev_s0{}, timeline(false), ws_elems(0), ws(nullptr), peers{}, fused(false) {}
+                 ev_go(nullptr), ev_side(nullptr), ev_copy(nullptr), ev_s0{}, copy_extra{}, ev_extra{}, timeline(false), ws_elems(0), ws(nullptr), peers{}, fused(false) {}
 };
 int build_slab_plan(SlabPlan &sp, size_t nn1, size_t nn2, size_t nn3, int nranks, int rank, bool real = true);
 // one whole direction of the fused exchange on `stream`: stage 0 (stores go to the peers), epoch-flag barrier, stage 1

@@ -52,3 +52,5 @@ def _reset_options(request):
             L.set_option("conv_fused_mid", 1)
             L.set_option("big_row_mask", 0)
             L.set_option("big_col_mask", 0)
+            L.set_option("tma_col_mask", 0)
+            L.set_option("tma_persist", 0)

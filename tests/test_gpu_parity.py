@@ -423,6 +423,37 @@ def test_simple_addressing_matches_general_path(gpu, shape):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("persist", [0, 1])
+def test_tma_fed_strided_passes(gpu, persist):
+    """fft_tma.cuh: the strided PLAIN passes with their tile moved by bulk tensor copies (cp.async.bulk.tensor + mbarrier)
+    instead of per-thread loads / stores -- same arithmetic, so the results must equal the register-fed kernels' to the
+    last bits, and the oracle's within tolerance.  Shapes cover 128 / 256 / 512 / 1024-point strided lines, several outer
+    indices, both directions, one CTA per tile and the persistent double-buffered form."""
+    shapes = [((8, 128, 64), "fourn"), ((4, 256, 32), "fourn"), ((512, 64), "fourn"), ((1024, 16), "fourn"), ((64, 512, 8), "fourn"),
+              ((128, 256, 64), "rlft3"), ((512, 512, 16), "rlft3")]
+    for shape, kind in shapes:
+        n = int(np.prod(shape))
+        outs = []
+        for mask in (0, 0x780):
+            gpu.set_option("tma_col_mask", mask)
+            gpu.set_option("tma_persist", persist)
+            if kind == "fourn":
+                x = cases.gen(31, 2 * n)
+                nb.fourn(x, list(shape), len(shape), 1, gpu)
+                nb.fourn(x, list(shape), len(shape), -1, gpu)
+                outs.append(x)
+            else:
+                x = cases.gen(32, n).reshape(shape)
+                s = np.zeros((shape[0], 2 * shape[1]))
+                nb.rlft3(x, s, *shape, 1, gpu)
+                outs.append(np.concatenate([x.ravel(), s.ravel()]))
+        assert cases.rel(outs[1], outs[0]) <= 1e-15, (shape, kind)
+        if kind == "fourn":
+            cases.check_fourn(gpu, shape)
+        else:
+            cases.check_rlft3(gpu, shape)
+
+
 def test_twofft_processor_batch(gpu):
     cases.check_twofft_batch(gpu, [64, 4096, 64, 1 << 15, 4096, 2, 1 << 15])
 
