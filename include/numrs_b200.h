@@ -75,6 +75,9 @@ int  nrb_shutdown(void);               /* frees cached plans, twiddle tables no 
  *                       nrb_rlft3 and 3-D nrb_fourn scatter slabs of the host volume over the devices' PCIe links, exchange
  *                       over NVLink peer memory and gather the result; the *_batch calls shard contiguous batch ranges.
  *   "shard_min_kb"      batches smaller than this stay on one device (default 16384)
+ *   "pull_eighths"      push + pull slab exchange: eighths of the z range pulled by stage 1 (0 .. 8, default 4)
+ *   "dma_streams"       DMA slab exchange: copy streams the pieces of a chunk are spread over (1 .. 4, default 1)
+ *   "tma_col_mask"      bit log2 N set: eligible strided passes of N points use the TMA-fed kernel (default 512: the 512-point passes)
  *   "xchg_grid_cap"     pipelined slab exchange: CTAs of a peer-store pass (0 = one per tile); fewer CTAs leave SM
  *                       slots to the local pass running beside it on the second stream
  *   "simple_addr"       1 (default): passes whose element index is not split take the cheap addressing code path where it
@@ -232,6 +235,12 @@ int    nrb_slab_stage(nrb_slab_t plan, int stage, int isign, double *d_slab, dou
  * all-to-all: d_send / d_recv are ignored); the caller only has to put a cross-rank barrier between
  * stage 0 and stage 1.  Passing NULL returns the plan to the explicit send/recv mode. */
 int    nrb_slab_set_peers(nrb_slab_t plan, void *const *peer_recv, int count);
+/* Push + pull exchange (on top of nrb_slab_set_peers): peer_send[i] = rank i's SEND buffer (nrb_slab_xchg_doubles()
+ * doubles, mapped like the receive buffers).  Stage 0 then pushes only the low-z part of every block and leaves the rest
+ * (option "pull_eighths" / 8 of the z range, default half) in its own send buffer, from which the consumer's stage 1 reads
+ * it over NVLink: the link works during both passes of a direction.  NULL switches back to pushing everything.  Like the
+ * receive buffers, send buffers must be double buffered by the caller across calls (dist_rlft3.py). */
+int    nrb_slab_set_send_peers(nrb_slab_t plan, void *const *peer_send, int count);
 /* Size of one receive buffer for the fused mode: the exchange area plus a small flag array used by
  * nrb_slab_barrier (nrb_device_alloc returns zeroed memory). */
 size_t nrb_slab_recv_bytes(nrb_slab_t plan);

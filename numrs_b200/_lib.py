@@ -44,7 +44,7 @@ ABI_SYMBOLS = [
     "nrb_plan_create", "nrb_plan_workspace_bytes", "nrb_plan_num_launches", "nrb_plan_exec", "nrb_plan_destroy",
     "nrb_plan_profile", "nrb_plan_describe_launch", "nrb_fill_uniform_device",
     "nrb_slab_create", "nrb_slab_create_fourn", "nrb_slab_exec", "nrb_slab_num_launches", "nrb_slab_local_doubles", "nrb_slab_speq_doubles", "nrb_slab_xchg_doubles",
-    "nrb_slab_stage", "nrb_slab_destroy", "nrb_slab_set_peers", "nrb_slab_recv_bytes", "nrb_slab_barrier",
+    "nrb_slab_stage", "nrb_slab_destroy", "nrb_slab_set_peers", "nrb_slab_set_send_peers", "nrb_slab_recv_bytes", "nrb_slab_barrier",
     "nrb_slab_set_chunks", "nrb_slab_stage_part", "nrb_slab_barrier_chunk",
     "nrb_slab_set_dma", "nrb_slab_exec_dma", "nrb_slab_stage_part_xchg", "nrb_slab_dma_timeline",
     "nrb_upload", "nrb_download", "nrb_stream_synchronize", "nrb_complex_multiply_device",
@@ -123,6 +123,7 @@ class Library:
         L.nrb_slab_stage.argtypes = [_vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp]
         L.nrb_slab_destroy.argtypes = [_vp]
         L.nrb_slab_set_peers.argtypes = [_vp, ctypes.POINTER(_vp), ctypes.c_int]
+        L.nrb_slab_set_send_peers.argtypes = [_vp, ctypes.POINTER(_vp), ctypes.c_int]
         L.nrb_slab_recv_bytes.argtypes = [_vp]
         L.nrb_slab_recv_bytes.restype = _sz
         L.nrb_slab_barrier.argtypes = [_vp, ctypes.c_int, ctypes.c_ulonglong, _vp]
@@ -415,6 +416,14 @@ class SlabPlan:
             return
         arr = (_vp * len(peer_ptrs))(*peer_ptrs)
         self.lib.check(self.lib.L.nrb_slab_set_peers(self.h, arr, len(peer_ptrs)))
+
+    def set_send_peers(self, peer_ptrs):
+        """Push + pull exchange: peer_ptrs[i] = rank i's send buffer mapped into this process (None to disable)."""
+        if peer_ptrs is None:
+            self.lib.check(self.lib.L.nrb_slab_set_send_peers(self.h, None, 0))
+            return
+        arr = (_vp * len(peer_ptrs))(*peer_ptrs)
+        self.lib.check(self.lib.L.nrb_slab_set_send_peers(self.h, arr, len(peer_ptrs)))
 
     def recv_bytes(self):
         return self.lib.L.nrb_slab_recv_bytes(self.h)

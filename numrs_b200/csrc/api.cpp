@@ -472,6 +472,11 @@ int nrb_slab_set_peers(nrb_slab_t p, void *const *peer_recv, int count)
     if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
     return slab_set_peers(p->plan, peer_recv, count);
 }
+int nrb_slab_set_send_peers(nrb_slab_t p, void *const *peer_send, int count)
+{
+    if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");
+    return slab_set_send_peers(p->plan, peer_send, count);
+}
 int nrb_slab_barrier(nrb_slab_t p, int phase, unsigned long long epoch, void *stream)
 try {
     if (!p) return fail(NRB_ERR_INVALID_DIMS, "plan is NULL");

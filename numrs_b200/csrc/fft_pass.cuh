@@ -345,11 +345,23 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
                     }
                 }
             } else if (!(FAST && SRC_G)) {
+                if (P.in_peer_on) {   // exchange blocks through the pointer table: local receive buffer or a peer's send buffer (NVLink loads)
+                    const i64 lb = line_base(q, P.in_s0, P.in_s1, P.in_s2, P.logA, P.logB);
+                    const int zsel = (((unsigned)q & P.peer_zmask) >= P.peer_zthr) ? 8 : 0;
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    double2 x = make_double2(0.0, 0.0);
-                    if (ok) x = NRB_LDS(src + elem_off(jj[i] + r * NB, P.in_es, P.in_eshift, P.in_es_hi));
-                    v[i][r] = io_swap<DIR>(x);
+                    for (int r = 0; r < R; ++r) {
+                        const int n = jj[i] + r * NB;
+                        double2 x = make_double2(0.0, 0.0);
+                        if (ok) x = NRB_LDS(P.in_peer[zsel + (n >> P.in_eshift)] + lb + (i64)(n & ((1 << P.in_eshift) - 1)) * P.in_es);
+                        v[i][r] = io_swap<DIR>(x);
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        double2 x = make_double2(0.0, 0.0);
+                        if (ok) x = NRB_LDS(src + elem_off(jj[i] + r * NB, P.in_es, P.in_eshift, P.in_es_hi));
+                        v[i][r] = io_swap<DIR>(x);
+                    }
                 }
             }
         } else if (ROW_RD_CONST) {
@@ -517,8 +529,9 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
                     const int k = kb + r * NS;
                     double2 y = v[i][r];
                     if (P.tw_on) { y = cmul(y, tw); tw = cmul(tw, tw_step); }
-                    if (P.out_peer_on) {   // store straight into the owning peer's receive buffer (NVLink)
-                        double2 *pd = P.out_peer[k >> P.out_eshift] + P.out_peer_off + lb +
+                    if (P.out_peer_on) {   // store straight into the owning peer's receive buffer (NVLink), or the local send buffer
+                        const int zsel = (((unsigned)q & P.peer_zmask) >= P.peer_zthr) ? 8 : 0;
+                        double2 *pd = P.out_peer[zsel + (k >> P.out_eshift)] + P.out_peer_off + lb +
                                       (i64)(k & ((1 << P.out_eshift) - 1)) * P.out_es;
                         NRB_STS(pd, io_swap<DIR>(y));
                     } else {

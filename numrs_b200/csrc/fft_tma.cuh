@@ -56,8 +56,19 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, int c0, int
 
 // One CTA per tile (2 CTAs per SM overlap each other's copy and compute phases), or `PERSIST`: a CTA walks tiles
 // blockIdx.x, + gridDim.x, ... with TWO tile buffers, so the bulk load of its next tile is in flight while it computes.
+// Resident CTAs per SM: the tile (64 KiB) allows three; the 256-thread geometries (16 points per thread: N = 512, 64) fit
+// three in the register file at 80 registers per thread, the 512-thread ones two at 64.  Three matter: with two, 35 % of the
+// warp samples sit in the mbarrier wait for the bulk load (ncu, profiles/r02_ncu_full_rlft3_512_tma.md) -- y / x pass of
+// rlft3 512^3 5 416 / 5 296 GB/s with two CTAs, 6 417 / 5 931 GB/s with three (register-fed kernel: 6 272 / 5 613).
+NRB_HD constexpr int tma_ctas_per_sm(int log2n) { return cta_threads(log2n, LAYOUT_COL) <= 256 ? 3 : 2; }
+
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
 template <int LOG2N, int DIR, bool PERSIST>
-__global__ void __launch_bounds__(cta_threads(LOG2N, LAYOUT_COL), PERSIST ? 1 : 2)
+__global__ void __launch_bounds__(cta_threads(LOG2N, LAYOUT_COL), PERSIST ? 1 : tma_ctas_per_sm(LOG2N))
 fft_col_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
                    const __grid_constant__ PassParams P, const unsigned ntiles, const unsigned log2_inner)
 {
@@ -90,6 +101,13 @@ fft_col_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
     unsigned phase[2] = {0u, 0u};
     int buf = 0;
     if (tid == 0 && blockIdx.x < ntiles) issue_load(blockIdx.x, 0);
+    if (!PERSIST && tid == 32 && P.prefetch_dist > 0 && blockIdx.x + (unsigned)P.prefetch_dist < ntiles) {
+        // ask L2 for the tile a later CTA of this SM slot will load (two instructions for 64 KiB)
+        int c0, c2;
+        coords(blockIdx.x + (unsigned)P.prefetch_dist, c0, c2);
+#pragma unroll
+        for (int b = 0; b < NBOX; ++b) tma_prefetch_3d(&tm_in, c0, b * ROWS, c2);
+    }
     for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         double2 *sm = nrb_tma_smem + (size_t)buf * G::TILE;
         if (PERSIST && tid == 0 && tile + gridDim.x < ntiles) {
@@ -113,7 +131,8 @@ fft_col_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         if (PERSIST) buf ^= 1;
         else break;
     }
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the stores must complete before the CTA's smem goes away
+    // the bulk stores must have READ the tile before the CTA's shared memory goes away (the global writes finish on their own)
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 } // namespace nrb

@@ -9,7 +9,7 @@
 namespace nrb {
 
 template <int LOG2R>
-__global__ void __launch_bounds__(GeoM<LOG2R>::NT, 1) conv_mid_kernel(const __grid_constant__ ConvMidParams M)
+__global__ void __launch_bounds__(GeoM<LOG2R>::NT, (LOG2R <= 11 ? 2 : 1)) conv_mid_kernel(const __grid_constant__ ConvMidParams M)
 {
     extern __shared__ double2 nrb_mid_smem[];
     conv_mid_cta<LOG2R>(M, nrb_mid_smem, blockIdx.x, (int)threadIdx.x);
@@ -37,6 +37,7 @@ int launch_conv_mid(int log2rest, const ConvMidParams &m, u64 ntiles, cudaStream
     switch (log2rest) {
     case 4: return launch_mid<4>(m, ntiles, s);
     case 6: return launch_mid<6>(m, ntiles, s);
+    case 11: return launch_mid<11>(m, ntiles, s);
     case 12: return launch_mid<12>(m, ntiles, s);
     default: return (int)cudaErrorInvalidValue;
     }

@@ -30,7 +30,7 @@ static EncodeTiledFn encode_fn()
 // can this launch take the TMA-fed kernel?  (see fft_tma.cuh header)
 bool tma_pass_eligible(const KernelKey &key, const PassParams &p, u64 ntiles)
 {
-    if (key.layout != LAYOUT_COL || key.variant != VAR_PLAIN || p.tw_on || p.out_peer_on || p.grid_cap > 0) return false;
+    if (key.layout != LAYOUT_COL || key.variant != VAR_PLAIN || p.tw_on || p.out_peer_on || p.in_peer_on || p.grid_cap > 0) return false;
     if (key.log2n < 7 || key.log2n > 10) return false;
     if (p.in_eshift <= kMaxLog2N || p.out_eshift <= kMaxLog2N || p.logA != 0 || p.in_s2 != 1 || p.out_s2 != 1) return false;
     const u64 inner = 1ull << p.logB, N = 1ull << key.log2n, L = (u64)lines_per_tile(key.log2n, LAYOUT_COL);

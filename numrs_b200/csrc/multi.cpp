@@ -98,8 +98,8 @@ namespace {
 
 struct SlabDev {
     SlabPlan sp;
-    void *stream, *slab, *speq, *recv, *ev0;
-    SlabDev() : stream(nullptr), slab(nullptr), speq(nullptr), recv(nullptr), ev0(nullptr) {}
+    void *stream, *slab, *speq, *recv, *send, *ev0;
+    SlabDev() : stream(nullptr), slab(nullptr), speq(nullptr), recv(nullptr), send(nullptr), ev0(nullptr) {}
 };
 
 struct MultiSlab {
@@ -129,9 +129,10 @@ struct MultiSlab {
             if (D.slab) be_free(D.slab);
             if (D.speq) be_free(D.speq);
             if (D.recv) be_free(D.recv);
+            if (D.send) be_free(D.send);
             if (D.ev0) be_event_destroy(D.ev0);
             if (D.stream) be_stream_destroy(D.stream);
-            D.slab = D.speq = D.recv = D.ev0 = D.stream = nullptr;
+            D.slab = D.speq = D.recv = D.send = D.ev0 = D.stream = nullptr;
         }
         if (cur >= 0) be_set_device(cur);
         G = 0;
@@ -168,7 +169,7 @@ std::shared_ptr<MultiSlab> get_multi_slab(bool real, size_t nn1, size_t nn2, siz
         D.ev0 = be_event_create();
         if (!D.ev0) { set_error("event creation failed"); return NRB_ERR_CUDA; }
         if (be_malloc(&D.slab, M->local_bytes()) != 0 || (M->real && be_malloc(&D.speq, M->speq_bytes()) != 0) ||
-            be_malloc(&D.recv, M->recv_bytes()) != 0) {
+            be_malloc(&D.recv, M->recv_bytes()) != 0 || be_malloc(&D.send, M->recv_bytes()) != 0) {
             set_error(std::string("device allocation failed: ") + be_last_error());
             return NRB_ERR_OOM;
         }
@@ -176,10 +177,11 @@ std::shared_ptr<MultiSlab> get_multi_slab(bool real, size_t nn1, size_t nn2, siz
         return NRB_OK;
     });
     if (*rc != NRB_OK) return nullptr;     // ~MultiSlab frees what was allocated
-    void *peers[8];
-    for (int g = 0; g < G; ++g) peers[g] = M->d[g].recv;
+    // push + pull exchange (plan.cpp exec_slab_stage): every device's receive AND send buffer is visible to all
+    void *peers[8], *sends[8];
+    for (int g = 0; g < G; ++g) { peers[g] = M->d[g].recv; sends[g] = M->d[g].send; }
     for (int g = 0; g < G; ++g)
-        if ((*rc = slab_set_peers(M->d[g].sp, peers, G)) != NRB_OK) return nullptr;
+        if ((*rc = slab_set_peers(M->d[g].sp, peers, G)) != NRB_OK || (*rc = slab_set_send_peers(M->d[g].sp, sends, G)) != NRB_OK) return nullptr;
     C.push_front(m);
     return m;
 }

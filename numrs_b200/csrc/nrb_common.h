@@ -232,12 +232,20 @@ struct PassParams {
     //   (n & (2^eshift - 1)) * es + (n >> eshift) * es_hi ; eshift = 31 disables the split
     i64 in_es_hi, out_es_hi;
     int in_eshift, out_eshift;
-    // fused exchange (slab rlft3 over NVLink): when out_peer_on, the high part of the output element
-    // index selects a PEER GPU's receive buffer (mapped through CUDA IPC) instead of a stride:
-    //   address = out_peer[n >> out_eshift] + out_peer_off + line offset + (n & mask) * out_es
-    double2 *out_peer[8];
+    // fused exchange (slab transforms over NVLink): when out_peer_on, the high part of the output element
+    // index selects an exchange block through a pointer table instead of a stride:
+    //   address = out_peer[8 * zsel + (n >> out_eshift)] + out_peer_off + line offset + (n & mask) * out_es
+    // and the same on the input side (in_peer_on / in_peer).  A table entry is either local memory or a PEER GPU's buffer
+    // (mapped through CUDA IPC or peer access).  zsel = ((q & peer_zmask) >= peer_zthr) picks the second half of the
+    // tables for the lines whose z index is past a threshold: the "push + pull" split of the exchange -- stage 0 PUSHES the
+    // low-z part of every block into the consumer's receive buffer and writes the high-z part into its own send buffer,
+    // from which the consumer's stage 1 PULLS it, so the link carries half the bytes during each of the two passes instead
+    // of all of them during the first (plan.cpp exec_slab_stage).
+    double2 *out_peer[16];
+    const double2 *in_peer[16];
     i64 out_peer_off;
-    int out_peer_on;
+    int out_peer_on, in_peer_on;
+    unsigned peer_zmask, peer_zthr;
     int prefetch_dist;      // > 0: every CTA first asks L2 for the input of tile (own + prefetch_dist), so DRAM keeps
                             // streaming while the CTAs of an SM are in their shared-memory stages
     int grid_cap;           // > 0: launch at most this many CTAs (they loop over the tiles); used to leave SM slots

@@ -54,10 +54,12 @@ static Tunables &tunables_mut()
         x.simple_addr = env_int("NRB_SIMPLE_ADDR", 1);
         x.speq_side = env_int("NRB_SPEQ_SIDE", 1);
         x.conv_fused_mid = env_int("NRB_CONV_FUSED_MID", 1);
+        x.conv_rest_log2 = env_int("NRB_CONV_REST_LOG2", 12);
         x.big_row_mask = env_int("NRB_BIG_ROW_MASK", 0);
         x.big_col_mask = env_int("NRB_BIG_COL_MASK", 0);
         x.dma_streams = env_int("NRB_DMA_STREAMS", 1);
-        x.tma_col_mask = env_int("NRB_TMA_COL_MASK", 0);
+        x.pull_eighths = env_int("NRB_PULL_EIGHTHS", 4);
+        x.tma_col_mask = env_int("NRB_TMA_COL_MASK", 1 << 9);
         x.tma_persist = env_int("NRB_TMA_PERSIST", 0);
         x.num_devices = env_int("NRB_NUM_DEVICES", 1);
         x.shard_min_kb = env_int("NRB_SHARD_MIN_KB", 16384);
@@ -90,8 +92,10 @@ int set_tunable(const char *name, long value)
     else if (n == "simple_addr") t.simple_addr = (int)value;
     else if (n == "speq_side") t.speq_side = (int)value;
     else if (n == "conv_fused_mid") t.conv_fused_mid = (int)value;
+    else if (n == "conv_rest_log2") t.conv_rest_log2 = value < 1 ? 1 : value > 12 ? 12 : (int)value;
     else if (n == "big_row_mask") t.big_row_mask = (int)value;
     else if (n == "big_col_mask") t.big_col_mask = (int)value;
+    else if (n == "pull_eighths") t.pull_eighths = value < 0 ? 0 : value > 8 ? 8 : (int)value;
     else if (n == "dma_streams") t.dma_streams = value < 1 ? 1 : value > 4 ? 4 : (int)value;
     else if (n == "tma_col_mask") t.tma_col_mask = (int)value;
     else if (n == "tma_persist") t.tma_persist = (int)value;
@@ -247,6 +251,7 @@ void init_pass(PassParams &pp)
     pp.out_eshift = 30;
     pp.logA = 0;
     pp.logB = 40;
+    pp.peer_zthr = 1;      // with peer_zmask = 0: always the first half of the exchange pointer tables
 }
 
 u64 tiles_for(int log2n, int layout, u64 lines)
@@ -445,7 +450,8 @@ int conv_split(int p)
 {
     const Tunables &T = tunables();
     if (!T.conv_transposed || p < 2) return -1;
-    int rest = p - 1 < 12 ? p - 1 : 12;                 // contiguous pass: 4096 points at most (the fast ROW kernels)
+    const int rmax = T.conv_rest_log2;
+    int rest = p - 1 < rmax ? p - 1 : rmax;             // contiguous pass: 4096 points at most (the fast ROW kernels)
     if (rest > T.row_max_log2) rest = T.row_max_log2;
     int f = p - rest;
     if (f > T.col_max_log2) { f = T.col_max_log2; rest = p - f; }
@@ -1054,7 +1060,15 @@ int build_plan(Plan &pl, int kind, const size_t *dims, size_t ndim, size_t batch
     return NRB_OK;
 }
 
-struct PeerExchange { double2 *const *peers; i64 off; };
+// pointer tables of the fused exchange (PassParams::out_peer / in_peer): [0..8) for the pushed (low-z) part of the blocks,
+// [8..16) for the pulled (high-z) part; zthr > zmask = no split (everything through the first half)
+struct PeerExchange {
+    double2 *out[16];
+    const double2 *in[16];
+    bool out_on, in_on;
+    unsigned zmask, zthr;
+    PeerExchange() : out{}, in{}, out_on(false), in_on(false), zmask(0), zthr(1) {}
+};
 
 void release_side_lane(SideLane &sl)
 {
@@ -1139,10 +1153,19 @@ static int run_program(Program &prog, double2 *const base[4], int arg, void *mai
             pp.prefetch_dist = tunables().prefetch_dist >= 0 ? tunables().prefetch_dist
                              : ((st.key.layout == LAYOUT_ROW && st.key.log2n >= 12) || (st.key.layout == LAYOUT_COL && st.key.log2n == 7 && st.key.variant == VAR_PLAIN)) ? 148 : 0;
             pp.speq = st.speq.id == BUF_NONE ? nullptr : base[st.speq.id] + st.speq.off;
-            if (px && st.out.id == BUF_OUT) {   // exchange output: write into the peers' receive buffers
+            if (px && px->out_on && st.out.id == BUF_OUT) {   // exchange output: the peers' receive buffers / the local send buffer
                 pp.out_peer_on = 1;
-                pp.out_peer_off = px->off;
-                for (int i = 0; i < 8; ++i) pp.out_peer[i] = px->peers[i] ? px->peers[i] + st.out.off : nullptr;
+                pp.out_peer_off = 0;
+                for (int i = 0; i < 16; ++i) pp.out_peer[i] = px->out[i] ? px->out[i] + st.out.off : nullptr;
+                pp.peer_zmask = st.zsplit ? px->zmask : 0u;
+                pp.peer_zthr = st.zsplit ? px->zthr : 1u;
+            }
+            if (px && px->in_on && st.in.id == BUF_OUT) {     // exchange input: the local receive buffer / the peers' send buffers
+                pp.in_peer_on = 1;
+                for (int i = 0; i < 16; ++i) pp.in_peer[i] = px->in[i] ? px->in[i] + st.in.off : nullptr;
+                pp.peer_zmask = st.zsplit ? px->zmask : 0u;
+                pp.peer_zthr = st.zsplit ? px->zthr : 1u;
+                pp.prefetch_dist = 0;
             }
             rc = be_launch_pass(st.key, pp, st.ntiles, stream);
         }
@@ -1337,6 +1360,7 @@ int build_slab_plan(SlabPlan &sp, size_t nn1, size_t nn2, size_t nn3, int nranks
         emit_z(B, +1);
         if (side) { const size_t f0 = B.prog->steps.size(); emit_axis(B, WSPEQ, XCH + SPQ, BufRef(), 1, 0, 1, p1, Y, +1, nullptr, &x_blocks_speq); lane1(B, f0); }
         emit_axis(B, SLAB, XCH, BufRef(), 1, 0, 1, p1, Y * N3, +1, nullptr, &x_blocks);
+        B.prog->steps.back().zsplit = true;
         if (real && !side) emit_axis(B, WSPEQ, XCH + SPQ, BufRef(), 1, 0, 1, p1, Y, +1, nullptr, &x_blocks_speq);
         rc = B.rc ? B.rc : rc;
     }
@@ -1344,6 +1368,7 @@ int build_slab_plan(SlabPlan &sp, size_t nn1, size_t nn2, size_t nn3, int nranks
         Builder B(&sp.prog[0][1]);
         if (side) { emit_axis(B, XCH + SPQ, SPEQ, BufRef(), X, 0, X, p2, 1, +1, &y_blocks_speq, nullptr); lane1(B, 0); }
         emit_axis(B, XCH, SLAB, BufRef(), X, 0, X, p2, N3, +1, &y_blocks, nullptr);
+        B.prog->steps.back().zsplit = true;
         if (real && !side) emit_axis(B, XCH + SPQ, SPEQ, BufRef(), X, 0, X, p2, 1, +1, &y_blocks_speq, nullptr);
         rc = B.rc ? B.rc : rc;
     }
@@ -1351,6 +1376,7 @@ int build_slab_plan(SlabPlan &sp, size_t nn1, size_t nn2, size_t nn3, int nranks
         Builder B(&sp.prog[1][0]);
         if (side) { emit_axis(B, SPEQ, XCH + SPQ, BufRef(), X, 0, X, p2, 1, -1, nullptr, &y_blocks_speq); lane1(B, 0); }
         emit_axis(B, SLAB, XCH, BufRef(), X, 0, X, p2, N3, -1, nullptr, &y_blocks);
+        B.prog->steps.back().zsplit = true;
         if (real && !side) emit_axis(B, SPEQ, XCH + SPQ, BufRef(), X, 0, X, p2, 1, -1, nullptr, &y_blocks_speq);
         rc = B.rc ? B.rc : rc;
     }
@@ -1358,6 +1384,7 @@ int build_slab_plan(SlabPlan &sp, size_t nn1, size_t nn2, size_t nn3, int nranks
         Builder B(&sp.prog[1][1]);
         if (real) { emit_axis(B, XCH + SPQ, WSPEQ, BufRef(), 1, 0, 1, p1, Y, -1, &x_blocks_speq, nullptr); lane1(B, 0); }
         emit_axis(B, XCH, SLAB, BufRef(), 1, 0, 1, p1, Y * N3, -1, &x_blocks, nullptr);
+        B.prog->steps.back().zsplit = true;
         emit_z(B, -1);
         rc = B.rc ? B.rc : rc;
     }
@@ -1543,7 +1570,9 @@ int exec_slab_part(SlabPlan &sp, int stage, int part, int isign, double *d_slab,
         return run_program(prog, base, 0, stream);
     }
     double2 *const base[4] = {(double2 *)d_slab, (double2 *)d_speq, sp.peers[sp.rank], (double2 *)sp.ws};
-    PeerExchange px{sp.peers, (i64)sp.rank * BLK};
+    PeerExchange px;       // the pipelined exchange pushes everything
+    px.out_on = true;
+    for (int i = 0; i < 8; ++i) px.out[i] = px.out[8 + i] = sp.peers[i] ? sp.peers[i] + (i64)sp.rank * BLK : nullptr;
     const bool sends = chunk_part && stage == 0;
     for (Step &st : prog.steps) if (!st.is_aux) st.pp.grid_cap = sends ? tunables().xchg_grid_cap : 0;
     return run_program(prog, base, 0, stream, nullptr, sends ? &px : nullptr);
@@ -1628,6 +1657,16 @@ int slab_set_peers(SlabPlan &sp, void *const *peer_recv, int count)
     return NRB_OK;
 }
 
+int slab_set_send_peers(SlabPlan &sp, void *const *peer_send, int count)
+{
+    for (int i = 0; i < 8; ++i) sp.sends[i] = nullptr;
+    if (!peer_send) return NRB_OK;
+    if (count != sp.nranks || count > 8) { set_error("slab: need one send buffer per rank (at most 8)"); return NRB_ERR_INVALID_DIMS; }
+    for (int i = 0; i < count; ++i) if (!peer_send[i]) { set_error("slab: null peer buffer"); return NRB_ERR_INVALID_DIMS; }
+    for (int i = 0; i < count; ++i) sp.sends[i] = (double2 *)peer_send[i];
+    return NRB_OK;
+}
+
 int slab_barrier(SlabPlan &sp, int phase, unsigned long long epoch, void *stream)
 {
     return slab_barrier_chunk(sp, phase, 0, epoch, stream);
@@ -1658,10 +1697,29 @@ int exec_slab_stage(SlabPlan &sp, int stage, int isign, double *d_slab, double *
     if (stage != 0 && stage != 1) { set_error("stage must be 0 or 1"); return NRB_ERR_INVALID_DIMS; }
     if (sp.fused) {
         // stage 0 stores go straight to the peers; stage 1 reads the local receive buffer
+        // Block r -> p of the exchange (BLK elements): its low-z lines are PUSHED by rank r's stage 0 into block r of p's
+        // receive buffer; its high-z lines (pull_eighths / 8 of the z range, when send buffers are set) are written by r
+        // into block p of its own send buffer and PULLED from there by p's stage 1.  The NVLink traffic is thereby spread
+        // over both passes of the step instead of being serialised in front of the second one.
         const i64 BLK = (i64)sp.blk();
+        const u64 N3 = sp.n3c();
         double2 *const base[4] = {(double2 *)d_slab, (double2 *)d_speq, sp.peers[sp.rank], (double2 *)sp.ws};
-        PeerExchange px{sp.peers, (i64)sp.rank * BLK};
-        return run_program(sp.prog[isign == 1 ? 0 : 1][stage], base, 0, stream, nullptr, stage == 0 ? &px : nullptr, nullptr, &sp.side);
+        const bool pull = sp.sends[sp.rank] != nullptr && tunables().pull_eighths > 0 && N3 >= 64;
+        PeerExchange px;
+        px.zmask = (unsigned)(N3 - 1);
+        px.zthr = pull ? (unsigned)(N3 - N3 / 8 * (u64)tunables().pull_eighths) : (unsigned)N3;
+        for (int i = 0; i < sp.nranks; ++i) {
+            if (stage == 0) {
+                px.out[i] = sp.peers[i] + (i64)sp.rank * BLK;
+                px.out[8 + i] = pull ? sp.sends[sp.rank] + (i64)i * BLK : px.out[i];
+            } else {
+                px.in[i] = sp.peers[sp.rank] + (i64)i * BLK;
+                px.in[8 + i] = pull ? sp.sends[i] + (i64)sp.rank * BLK : px.in[i];
+            }
+        }
+        px.out_on = stage == 0;
+        px.in_on = stage == 1;
+        return run_program(sp.prog[isign == 1 ? 0 : 1][stage], base, 0, stream, nullptr, &px, nullptr, &sp.side);
     }
     double2 *const base[4] = {(double2 *)d_slab, (double2 *)d_speq, (double2 *)(stage == 0 ? d_send : d_recv),
                               (double2 *)sp.ws};

@@ -77,6 +77,7 @@ struct Step {
     bool patch_pad_mode;   // AUX_PAD_RESPONSE: op comes from exec's `arg`
     bool is_mid;           // fused conv middle: mp, in = data (in place), b = second operand; key.log2n = log2 REST
     ConvMidParams mp;
+    bool zsplit;           // slab exchange data pass: its lines' low bits are the z index, so the push + pull split applies
     int lane;              // 0 = the caller's stream; 1 = the plan's side stream (small independent work, see SideLane)
     // fused pair: (key, pp, in/out/speq) is pass A, the *2 members are pass B
     bool is_fused;
@@ -85,7 +86,7 @@ struct Step {
     BufRef in2, out2, speq2;
     FuseSched fs;          // counters live in the plan's scheduler scratch (sched_off = element offset)
     size_t sched_off;
-    Step() : is_aux(false), key{0, 0, 0, 0}, pp(), ap(), ntiles(0), patch_pad_mode(false), is_mid(false), mp(), lane(0), is_fused(false),
+    Step() : is_aux(false), key{0, 0, 0, 0}, pp(), ap(), ntiles(0), patch_pad_mode(false), is_mid(false), mp(), zsplit(false), lane(0), is_fused(false),
              key2{0, 0, 0, 0}, pp2(), fs{nullptr, nullptr, 0, 0, 0, 0}, sched_off(0) {}
 };
 
@@ -121,6 +122,9 @@ struct Tunables {
     int prefetch_dist;     // tiles ahead whose input every CTA prefetches into L2 (NRB_PREFETCH_DIST; 0 = off, -1 = per-kernel policy, default)
     int conv_fused_mid;    // long-line convlv / correl: contiguous forward pass + spectral step + contiguous inverse pass in one kernel
                            // (NRB_CONV_FUSED_MID, default 1: convlv -3 %, correl -9.5 %, autocorrel_fast -5 % at n = 2^22, profiles/r02_tuning.md #39)
+    int conv_rest_log2;    // long-line convlv / correl: log2 of the contiguous rows of the two-pass split (NRB_CONV_REST_LOG2, default 12:
+                           // 4096-point rows; 11 halves the fused middle kernel's CTA so that two fit an SM, at the price of a
+                           // 1024-point strided pass)
     int speq_side;         // rlft3: run the speq-plane passes on the plan's side stream (NRB_SPEQ_SIDE, default 1: -0.5 % of the 1-GPU step, profiles/r02_tuning.md #38)
     int simple_addr;       // 1: passes whose element index is not split use the cheap addressing path (NRB_SIMPLE_ADDR, default 1)
     int big_row_mask;      // bit log2n set: contiguous lines of 2^log2n points use the big-tile pass of fft_pass2.cuh (NRB_BIG_ROW_MASK)
@@ -128,9 +132,12 @@ struct Tunables {
     int xchg_grid_cap;     // pipelined slab exchange: CTAs of an exchange (peer-store) pass, 0 = one per tile (NRB_XCHG_GRID_CAP)
     int num_devices;       // GPUs the host-slice entry points spread one call over (NRB_NUM_DEVICES; 1 = the calling thread's
                            // device only (default), 0 = every visible device, n = devices 0 .. n-1): multi.cpp
+    int pull_eighths;      // push + pull exchange: eighths of the z range that stage 1 pulls instead of stage 0 pushing them
+                           // (NRB_PULL_EIGHTHS, 0 .. 8, default 4: half and half)
     int dma_streams;       // DMA slab exchange: copy streams the pieces of a chunk are spread over (NRB_DMA_STREAMS, 1 .. 4, default 1)
     int tma_col_mask;      // bit log2n set: eligible strided PLAIN passes of 2^log2n points use the TMA-fed kernel of fft_tma.cuh
-                           // (NRB_TMA_COL_MASK, default 0: see profiles/r02_tuning.md for the A/B); tma_persist = 1: persistent
+                           // (NRB_TMA_COL_MASK, default 1 << 9: the 512-point passes, +2.3 % / +5.7 % on the y / x pass of rlft3 512^3,
+                           // profiles/r02_tuning.md #47); tma_persist = 1: persistent
                            // CTAs with two tile buffers (the next tile's bulk load in flight during the stages)
     int tma_persist;
     int shard_min_kb;      // batches smaller than this stay on one device (NRB_SHARD_MIN_KB, default 16 MiB)
@@ -140,7 +147,7 @@ int set_tunable(const char *name, long value);   // returns 0 if the name is kno
 // can the pass use the cheap addressing path of fft_stage (element offset = n * es, es = 1 for contiguous lines)?
 inline bool pass_is_simple(const KernelKey &key, const PassParams &p)
 {
-    if (!tunables().simple_addr || p.out_peer_on || !simple_built(key.log2n, key.layout, key.variant)) return false;
+    if (!tunables().simple_addr || p.out_peer_on || p.in_peer_on || !simple_built(key.log2n, key.layout, key.variant)) return false;
     if (p.in_eshift <= kMaxLog2N || p.out_eshift <= kMaxLog2N) return false;   // the element index is split
     if (key.layout == LAYOUT_ROW) return p.in_es == 1 && p.out_es == 1;
     return true;
@@ -148,7 +155,7 @@ inline bool pass_is_simple(const KernelKey &key, const PassParams &p)
 // does this launch go to the big-tile kernel (if the backend has one for the key)?
 inline bool use_big_tiles(const KernelKey &key, const PassParams &p)
 {
-    if (key.variant == VAR_REAL || p.out_peer_on || p.grid_cap > 0) return false;
+    if (key.variant == VAR_REAL || p.out_peer_on || p.in_peer_on || p.grid_cap > 0) return false;
     const int mask = key.layout == LAYOUT_ROW ? tunables().big_row_mask : tunables().big_col_mask;
     return ((mask >> key.log2n) & 1) != 0;
 }
@@ -214,6 +221,8 @@ struct SlabPlan {
     void *ws;
     SideLane side;         // speq_side: the small speq-plane passes of a stage run beside its data pass
     double2 *peers[8];     // peer receive buffers (fused exchange); peers[rank] is the local one
+    double2 *sends[8];     // peer SEND buffers (push + pull exchange: stage 1 pulls the high-z part of every block from the
+                           // producer's send buffer); sends[rank] is the local one; all null = everything is pushed
     bool fused;
     std::vector<TableRef> tables;   // twiddle tables the programs point into
     // N3 = complex points per z line; BLK = complex elements per exchange block (the speq part rides along for rlft3)
@@ -221,7 +230,7 @@ struct SlabPlan {
     size_t blk() const { const size_t G = (size_t)nranks; return (nn1 / G) * (nn2 / G) * (n3c() + (real ? 1 : 0)); }
     size_t xchg_elems() const { return (size_t)nranks * blk(); }
     SlabPlan() : nn1(0), nn2(0), nn3(0), real(true), nranks(1), rank(0), chunks(1), dma(false), send(nullptr), copy_stream(nullptr), side_stream(nullptr),
-                 ev_go(nullptr), ev_side(nullptr), ev_copy(nullptr), ev_s0{}, copy_extra{}, ev_extra{}, timeline(false), ws_elems(0), ws(nullptr), peers{}, fused(false) {}
+                 ev_go(nullptr), ev_side(nullptr), ev_copy(nullptr), ev_s0{}, copy_extra{}, ev_extra{}, timeline(false), ws_elems(0), ws(nullptr), peers{}, sends{}, fused(false) {}
 };
 int build_slab_plan(SlabPlan &sp, size_t nn1, size_t nn2, size_t nn3, int nranks, int rank, bool real = true);
 // one whole direction of the fused exchange on `stream`: stage 0 (stores go to the peers), epoch-flag barrier, stage 1
@@ -240,6 +249,8 @@ void slab_release(SlabPlan &sp);
 std::string slab_dma_timeline(SlabPlan &sp);
 int slab_barrier_chunk(SlabPlan &sp, int phase, int chunk, unsigned long long epoch, void *stream);
 int slab_set_peers(SlabPlan &sp, void *const *peer_recv, int count);
+// push + pull exchange: every rank's send buffer (xchg size), mapped like the receive buffers; nullptr switches it off
+int slab_set_send_peers(SlabPlan &sp, void *const *peer_send, int count);
 // flag barrier of the fused exchange (flags live right after the exchange area of each receive buffer)
 int slab_barrier(SlabPlan &sp, int phase /*0 = signal, 1 = wait*/, unsigned long long epoch, void *stream);
 int exec_slab_stage(SlabPlan &sp, int stage, int isign, double *d_slab, double *d_speq, double *d_send,

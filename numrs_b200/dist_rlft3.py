@@ -8,7 +8,10 @@ Inverse (isign=-1) is the mirror image.  Exactly one exchange per direction:
 
   mode "fused" (default): the last FFT pass of stage 0 stores its output straight into the owning
       peer's receive buffer through NVLink (CUDA IPC mapped peer memory) from the kernel epilogue,
-      so the transfer overlaps the transform tile by tile; the barrier between stage 0 and stage 1
+      so the transfer overlaps the transform tile by tile.  With `pull=True` (default) only the low-z half of every
+      block is pushed that way; the other half is written to the rank's own send buffer and PULLED by the consumer's
+      stage-1 pass with loads over NVLink, so the link carries half the bytes during each of the two passes of a
+      direction instead of all of them in front of the second one.  The barrier between stage 0 and stage 1
       is a pair of one-warp kernels exchanging epoch flags through the same peer mappings
       (`barrier="flags"`, default: no collective at all on the data path) or a stream-ordered
       1-element NCCL all-reduce (`barrier="nccl"`).
@@ -26,7 +29,7 @@ import torch.distributed as dist
 
 
 class SlabRlft3:
-    def __init__(self, lib, nn1, nn2, nn3, mode="fused", barrier="flags", chunks=1, kind="rlft3"):
+    def __init__(self, lib, nn1, nn2, nn3, mode="fused", barrier="flags", chunks=1, kind="rlft3", pull=True):
         self.lib = lib
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.dims = (nn1, nn2, nn3)
@@ -46,18 +49,26 @@ class SlabRlft3:
             self.plan.set_chunks(self.chunks)
             self._side = torch.cuda.Stream(priority=-1)       # stage 1 pieces: short, HBM-bound -> scheduled first
             self._ev_go, self._ev_done = torch.cuda.Event(), torch.cuda.Event()
+        self.pull = bool(pull) and mode == "fused" and self.chunks == 1 and self.world > 1
         if mode in ("fused", "dma"):
             # two receive buffers, alternated per call, so a peer still reading call k's data in its
             # stage 1 is never overwritten by call k+1's stage 0 (ordered by call k+1's barrier)
             self._own, self._peers = [], []
-            for _ in range(2):
-                own = lib.device_alloc(self.plan.recv_bytes())     # zeroed: the flag array starts at epoch 0
-                handle = lib.ipc_export(own)
+            self._own_send, self._send_peers = [], []
+
+            def shared(nbytes):
+                own = lib.device_alloc(nbytes)                     # zeroed: the flag array starts at epoch 0
                 handles = [None] * self.world
-                dist.all_gather_object(handles, handle)
-                peers = [own if r == self.rank else lib.ipc_import(h) for r, h in enumerate(handles)]
+                dist.all_gather_object(handles, lib.ipc_export(own))
+                return own, [own if r == self.rank else lib.ipc_import(h) for r, h in enumerate(handles)]
+            for _ in range(2):
+                own, peers = shared(self.plan.recv_bytes())
                 self._own.append(own)
                 self._peers.append(peers)
+                if self.pull:      # push + pull: the send buffers are read by the peers' stage 1, double buffered the same way
+                    own, peers = shared(8 * self.xchg_doubles)
+                    self._own_send.append(own)
+                    self._send_peers.append(peers)
             dist.barrier()
         elif mode == "nccl":
             self.send = torch.empty(self.xchg_doubles, dtype=torch.float64, device="cuda")
@@ -79,6 +90,8 @@ class SlabRlft3:
             self.plan.exec_dma(isign, slab.data_ptr(), speq_ptr, (self._call + 1) // 2, st)
         elif self.mode == "fused":
             peers = self._peers[self._call & 1]
+            if self.pull:
+                self.plan.set_send_peers(self._send_peers[self._call & 1])
             self._call += 1
             self.plan.set_peers(peers)
             if self.chunks > 1:
@@ -116,11 +129,11 @@ class SlabRlft3:
         torch.cuda.synchronize()
         dist.barrier()
         if self.mode in ("fused", "dma"):
-            for own, peers in zip(self._own, self._peers):
+            for peers in self._peers + self._send_peers:
                 for r, p in enumerate(peers):
                     if r != self.rank:
                         self.lib.ipc_release(p)
             dist.barrier()
-            for own in self._own:
+            for own in self._own + self._own_send:
                 self.lib.device_free(own)
         self.plan.destroy()

@@ -13,6 +13,10 @@ pub const NRB_PAD_LITERAL: c_int = 0;
 
 extern "C" {
     pub fn nrb_last_error() -> *const c_char;
+    /// planner / runtime options, e.g. ("num_devices", 0): spread one host-slice call over every visible GPU
+    pub fn nrb_set_option(name: *const c_char, value: std::os::raw::c_long) -> c_int;
+    pub fn nrb_num_devices_in_use() -> c_int;
+    pub fn nrb_shutdown() -> c_int;
     pub fn nrb_four1(data: *mut c_double, nn: usize, isign: c_int) -> c_int;
     pub fn nrb_four1_batch(ptrs: *const *mut c_double, nn: *const usize, count: usize, isign: c_int) -> c_int;
     pub fn nrb_fourn(data: *mut c_double, nn: *const usize, ndim: usize, isign: c_int) -> c_int;

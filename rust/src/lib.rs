@@ -5,6 +5,14 @@
 
 pub mod ffi;
 
+/// Spread every host-slice call (`rlft3`, 3-D `Fourn`, `fft_batch`, `convlv_batch`, `correl_batch`) over `n` GPUs of the
+/// box inside this process (0 = every visible device, 1 = the calling thread's device: the default).  Not part of the
+/// reference's API: the one knob a deployment sets once; every reference signature stays as it is.
+pub fn set_num_devices(n: usize) {
+    let rc = unsafe { ffi::nrb_set_option(b"num_devices\0".as_ptr() as *const std::os::raw::c_char, n as std::os::raw::c_long) };
+    assert!(rc == ffi::NRB_OK, "nrb_set_option(num_devices) failed");
+}
+
 pub mod FFT_1 {
     use crate::ffi::*;
 

@@ -229,7 +229,7 @@ template <int LOG2R> static void mid_body(const void *p, double2 *sm, unsigned t
 {
     conv_mid_cta<LOG2R>(*(const ConvMidParams *)p, sm, tile, tid);
 }
-bool be_conv_mid_available(int log2rest) { return log2rest == 4 || log2rest == 6 || log2rest == 12; }   // as k_mid.cu
+bool be_conv_mid_available(int log2rest) { return log2rest == 4 || log2rest == 6 || log2rest == 11 || log2rest == 12; }   // as k_mid.cu
 static long g_mid_launches = 0;
 int be_launch_conv_mid(int log2rest, const ConvMidParams &m, u64 ntiles, void *)
 {
@@ -239,6 +239,7 @@ int be_launch_conv_mid(int log2rest, const ConvMidParams &m, u64 ntiles, void *)
     switch (log2rest) {
     case 4: fn = mid_body<4>; nt = GeoM<4>::NT; smem = GeoM<4>::SMEM_BYTES / 16; break;
     case 6: fn = mid_body<6>; nt = GeoM<6>::NT; smem = GeoM<6>::SMEM_BYTES / 16; break;
+    case 11: fn = mid_body<11>; nt = GeoM<11>::NT; smem = GeoM<11>::SMEM_BYTES / 16; break;
     case 12: fn = mid_body<12>; nt = GeoM<12>::NT; smem = GeoM<12>::SMEM_BYTES / 16; break;
     default: g_emu_err = "conv_mid kernel not built for this row length"; return -1;
     }

@@ -23,7 +23,7 @@ def multi(emu):
 
 
 @pytest.mark.parametrize("shape,G", [((8, 8, 8), 2), ((16, 16, 8), 4), ((8, 16, 32), 8), ((32, 8, 4), 0), ((16, 16, 16), 3),
-                                     ((2, 2, 4), 4), ((4, 2, 8), 4)])
+                                     ((2, 2, 4), 4), ((4, 2, 8), 4), ((8, 16, 128), 4), ((8, 8, 256), 8)])   # the last two: push + pull split on
 def test_rlft3_host_call_over_several_devices(multi, shape, G):
     """nrb_rlft3 on whole host arrays (Real_FT3.rs:8 call shape) with num_devices = G: forward spectrum and speq plane
     element-wise against the oracle, then the inverse and the round trip.  G = 0 means every visible device; G = 3
@@ -52,7 +52,7 @@ def test_rlft3_host_call_over_several_devices(multi, shape, G):
     assert multi.multi_device_calls(0) - before == (3 if slab_ok else 0)
 
 
-@pytest.mark.parametrize("shape,G", [((8, 8, 8), 2), ((16, 16, 4), 4), ((8, 16, 32), 8), ((64, 128, 32), 8), ((2, 4, 8), 4)])
+@pytest.mark.parametrize("shape,G", [((8, 8, 8), 2), ((16, 16, 4), 4), ((8, 16, 32), 8), ((64, 128, 32), 8), ((2, 4, 8), 4), ((8, 16, 64), 4)])
 def test_fourn3d_host_call_over_several_devices(multi, shape, G):
     multi.set_option("num_devices", G)
     before = multi.multi_device_calls(0)

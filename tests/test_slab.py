@@ -18,9 +18,10 @@ def slab_of(x, r, G):
     return np.ascontiguousarray(x[:, r * Y:(r + 1) * Y, :])
 
 
-def run_simulated(L, x, G, isign, speq_in=None, fused=False):
+def run_simulated(L, x, G, isign, speq_in=None, fused=False, pull=False):
     """All G ranks in one process; returns per-rank (slab, speq) after one direction.
-    fused=True: stage 0 stores straight into the peers' receive buffers (no explicit exchange)."""
+    fused=True: stage 0 stores straight into the peers' receive buffers (no explicit exchange); pull=True: the
+    push + pull split (the high-z part of every block stays in the producer's send buffer and stage 1 reads it there)."""
     nn1, nn2, nn3 = x.shape
     X, Y = nn1 // G, nn2 // G
     plans = [L.slab_create(nn1, nn2, nn3, G, r) for r in range(G)]
@@ -37,6 +38,8 @@ def run_simulated(L, x, G, isign, speq_in=None, fused=False):
     if fused:
         for r in range(G):
             plans[r].set_peers([rv.ctypes.data for rv in recvs])
+            if pull:
+                plans[r].set_send_peers([sv.ctypes.data for sv in sends])
     for r in range(G):
         plans[r].stage(0, isign, slabs[r].ctypes.data, speqs[r].ctypes.data, sends[r].ctypes.data, 0)
     for r in range(G):          # all-to-all: block p of rank r's send -> block r of rank p's recv
@@ -54,6 +57,27 @@ def run_simulated(L, x, G, isign, speq_in=None, fused=False):
     for p in plans:
         p.destroy()
     return slabs, speqs
+
+
+@pytest.mark.parametrize("eighths", [4, 1, 8])
+@pytest.mark.parametrize("shape,G", [((8, 8, 128), 2), ((16, 16, 256), 4), ((8, 16, 128), 8), ((8, 8, 32), 2)])
+def test_slab_push_pull_exchange(emu, shape, G, eighths):
+    """The push + pull split of the fused exchange: `eighths` / 8 of the z range of every block is left in the
+    producer's send buffer and read from there by the consumer's stage 1; same spectrum as the oracle, element-wise,
+    and the round trip.  (N3 < 64: the split switches itself off and everything is pushed.)"""
+    emu.set_option("pull_eighths", eighths)
+    nn1, nn2, nn3 = shape
+    X = nn1 // G
+    x = O.fill_uniform(1006, 0, nn1 * nn2 * nn3).reshape(shape)
+    rd, rs = O.rlft3(x.copy(), np.zeros((nn1, 2 * nn2)), 1)
+    slabs, speqs = run_simulated(emu, x, G, 1, fused=True, pull=True)
+    for r in range(G):
+        assert cases.rel(slabs[r], rd[r * X:(r + 1) * X]) <= cases.tol(x.size), (r, "data")
+        assert cases.rel(speqs[r], rs[r * X:(r + 1) * X]) <= cases.tol(x.size), (r, "speq")
+    back, _ = run_simulated(emu, rd, G, -1, rs, fused=True, pull=True)
+    for r in range(G):
+        assert cases.rel(back[r] * (2.0 / x.size), slab_of(x, r, G)) <= cases.tol(x.size), (r, "round trip")
+    emu.set_option("pull_eighths", 4)
 
 
 @pytest.mark.parametrize("side", [0, 1])

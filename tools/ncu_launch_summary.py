@@ -16,6 +16,9 @@ for r in data:
     if m:
         lg, lay, d, var = (int(x) for x in m.groups())
         name = f"fft_{'row' if lay == 0 else 'col'}_{['plain', 'real', 'xpose'][var]}_n{1 << lg}_{'p' if d > 0 else 'm'}"
+    m = re.search(r"fft_col_tma_kernel<(?:\(int\))?(-?\d+), (?:\(int\))?(-?\d+)", name)
+    if m:
+        name = f"fft_col_tma_n{1 << int(m.group(1))}_{'p' if int(m.group(2)) > 0 else 'm'}"
     key = f"{name[:60]} grid {r[col['Grid Size']]}"
     if key not in agg:
         agg[key] = [0, 0.0, name.startswith("fft_")]

@@ -5,7 +5,7 @@ copy streams), NCCL all-to-all.  Prints one line per configuration: ms per forwa
 speed-up over the given 1-GPU time, NVLink GB/s if the step were all exchange, and the round-trip error.
 
     torchrun --nproc-per-node 8 tools/slab_modes.py 512 [ms of the 1-GPU step] [kind] [configs ...]
-    config = mode[:chunks[:dma_streams]]   e.g. fused fused:2 dma:2:4 nccl
+    config = mode[:chunks[:dma_streams[:pull_eighths]]]   e.g. fused (push + pull, half and half) fused:1:1:6 push fused:2 dma:2:4 nccl
 """
 import os
 import sys
@@ -22,7 +22,7 @@ rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 t1 = float(sys.argv[2]) if len(sys.argv) > 2 else 0.0
 kind = sys.argv[3] if len(sys.argv) > 3 else "rlft3"
-configs = sys.argv[4:] or ["fused", "fused:2", "fused:4", "dma:1:1", "dma:2:1", "dma:2:4", "dma:4:4", "nccl"]
+configs = sys.argv[4:] or ["push", "fused", "fused:1:1:3", "fused:1:1:5", "fused:2", "dma:2:4", "nccl"]
 torch.cuda.set_device(lr)
 lib = nb.lib()
 lib.set_device(lr)
@@ -38,9 +38,14 @@ for cfg in configs:
     mode = parts[0]
     chunks = int(parts[1]) if len(parts) > 1 else 1
     streams = int(parts[2]) if len(parts) > 2 else 1
+    eighths = int(parts[3]) if len(parts) > 3 else 4
     lib.set_option("dma_streams", streams)
+    lib.set_option("pull_eighths", eighths)
+    pull = mode != "push"
+    if mode == "push":      # the fused exchange with everything pushed by stage 0 (round 1's form)
+        mode = "fused"
     try:
-        S = SlabRlft3(lib, n, n, n, mode=mode, chunks=chunks, kind=kind)
+        S = SlabRlft3(lib, n, n, n, mode=mode, chunks=chunks, kind=kind, pull=pull)
     except Exception as e:      # noqa: BLE001
         if rank == 0:
             print(f"{cfg:12s} unavailable: {e}", flush=True)
