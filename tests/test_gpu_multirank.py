@@ -5,6 +5,9 @@ device by explicit copies; here every rank is its own process, the receive buffe
 store into them and the epoch-flag kernels order the stages -- the code path bench.py --gpus N times.  The forward
 spectrum of every rank's slab is compared element-wise with the oracle (tests/workers/multirank_slab.py).
 
+Shapes with nn3 >= 128 take the push + pull split of the exchange (stage 1 reads half of every block from the producer's
+send buffer over the peer mapping), the others push everything.
+
 Rank counts: 2 and 4 always (on a box with fewer GPUs the ranks share devices, which keeps every piece of the path except
 the NVLink wire), 8 when the box has 8 GPUs; the NCCL exchange mode whenever there is one GPU per rank."""
 import os
@@ -41,7 +44,7 @@ def launch(ranks, *args, timeout=600):
     return out.stdout
 
 
-CASES = [(2, "64x128x32"), (4, "64x128x32"), (2, "256x256x256"), (4, "32x64x512")] + ([(8, "64x128x32"), (8, "256x256x256")] if NDEV >= 8 else [])
+CASES = [(2, "64x128x32"), (4, "64x128x32"), (2, "256x256x256"), (4, "32x64x512")] + ([(8, "64x128x32"), (8, "256x256x256"), (8, "64x128x256")] if NDEV >= 8 else [])
 
 
 @pytest.mark.parametrize("ranks,shape", CASES)
