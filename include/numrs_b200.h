@@ -77,7 +77,7 @@ int  nrb_shutdown(void);               /* frees cached plans, twiddle tables no 
  *   "shard_min_kb"      batches smaller than this stay on one device (default 16384)
  *   "pull_eighths"      push + pull slab exchange: eighths of the z range pulled by stage 1 (0 .. 8, default 4)
  *   "dma_streams"       DMA slab exchange: copy streams the pieces of a chunk are spread over (1 .. 4, default 1)
- *   "tma_col_mask"      bit log2 N set: eligible strided passes of N points use the TMA-fed kernel (default 512: the 512-point passes)
+ *   "tma_col_mask"      bit log2 N set: eligible strided passes of N points use the TMA-fed kernel (default 512 | 1024)
  *   "xchg_grid_cap"     pipelined slab exchange: CTAs of a peer-store pass (0 = one per tile); fewer CTAs leave SM
  *                       slots to the local pass running beside it on the second stream
  *   "simple_addr"       1 (default): passes whose element index is not split take the cheap addressing code path where it

@@ -87,7 +87,7 @@ int launch_tma_pass(const KernelKey &key, const PassParams &p, u64 ntiles, int p
 
 int be_launch_pass(const KernelKey &key, const PassParams &p, u64 ntiles, void *stream)
 {
-    if (((tunables().tma_col_mask >> key.log2n) & 1) && tma_pass_eligible(key, p, ntiles)) {
+    if (tma_pass_eligible(key, p, ntiles)) {
         const int rc = launch_tma_pass(key, p, ntiles, tunables().tma_persist, (cudaStream_t)stream);
         if (rc != 0) return fail((cudaError_t)rc);
         return 0;

@@ -24,17 +24,22 @@
 namespace nrb {
 
 
+// points per thread of the fused middle kernel: 16 = 512 threads of 128 registers for 4096-point rows, 8 = 1024 threads
+// of 64 registers (twice the warps to hide the latency of the kernel's serial phases)
+#ifndef NRB_MID_PPT
+#define NRB_MID_PPT 8      /* measured: 0.670 -> 0.612 ms per 16 signals of 2^22 (profiles/r02_tuning.md #51) */
+#endif
 template <int LOG2R> struct GeoM {
     static constexpr int LOG2N = LOG2R, LAYOUT = LAYOUT_ROW, VARIANT = VAR_PLAIN;
     static constexpr int N = 1 << LOG2R;
     static constexpr int L = 2;
     static constexpr int TILE = 2 * N;
-    static constexpr int PPT = 16;
+    static constexpr int PPT = (2 << LOG2R) / NRB_MID_PPT > 1024 ? 16 : ((1 << LOG2R) >= NRB_MID_PPT ? NRB_MID_PPT : 16);
     static constexpr int NT = TILE / PPT;
     static constexpr int NST = radix_plan(LOG2R).nst;
     static constexpr int LP = N + (N >> 3);
     static constexpr size_t SMEM_BYTES = (size_t)L * LP * sizeof(double2);
-    static_assert(N >= PPT, "conv_mid: rows shorter than 16 points are not built");
+    static_assert(N >= PPT, "conv_mid: rows shorter than the points per thread are not built");
     static_assert(NST >= 2, "conv_mid needs at least two stages");
     NRB_DEVM static int phys(int l, int n) { return l * LP + n + (n >> 3); }
 };
@@ -98,6 +103,20 @@ NRB_DEV void conv_mid_cta(const ConvMidParams &M, double2 *E, unsigned tile, int
     const u64 row0 = t, row1 = t == 0 ? F / 2 : F - t;       // t = 0: the two self-paired rows
     double2 *z = M.data + (i64)sig * M.data_stride;
     double2 v[G::PPT];
+    if (M.prefetch_dist > 0) {
+        // L2 prefetch of a later tile's two rows (and of its second operand's, when that is per signal): one 128-byte
+        // line per thread and row piece
+        const u64 pt = (u64)tile + (u64)M.prefetch_dist;
+        if (pt < M.count * tps) {
+            const u64 psig = pt / tps, ptt = pt % tps;
+            const u64 prow[2] = {ptt, ptt == 0 ? F / 2 : F - ptt};
+            for (int e = tid * 8; e < 2 * G::N; e += G::NT * 8) {
+                const u64 off = prow[e >> LOG2R] * REST + (u64)(e & (G::N - 1));
+                NRB_PREFETCH_L2(M.data + (i64)psig * M.data_stride + off);
+                if (M.b_stride && M.op != SPEC_AUTOCORREL) NRB_PREFETCH_L2(M.b + (i64)psig * M.b_stride + off);
+            }
+        }
+    }
 
     // ---- forward REST-point transforms of both rows (reference isign = +1: re / im swapped on the way in)
 #pragma unroll

@@ -27,16 +27,10 @@ static EncodeTiledFn encode_fn()
     return fn;
 }
 
-// can this launch take the TMA-fed kernel?  (see fft_tma.cuh header)
+// can this launch take the TMA-fed kernel?  (geometry: plan.h pass_takes_tma; here the pointer alignment and the encoder)
 bool tma_pass_eligible(const KernelKey &key, const PassParams &p, u64 ntiles)
 {
-    if (key.layout != LAYOUT_COL || key.variant != VAR_PLAIN || p.tw_on || p.out_peer_on || p.in_peer_on || p.grid_cap > 0) return false;
-    if (key.log2n < 7 || key.log2n > 10) return false;
-    if (p.in_eshift <= kMaxLog2N || p.out_eshift <= kMaxLog2N || p.logA != 0 || p.in_s2 != 1 || p.out_s2 != 1) return false;
-    const u64 inner = 1ull << p.logB, N = 1ull << key.log2n, L = (u64)lines_per_tile(key.log2n, LAYOUT_COL);
-    if (p.logB > 28 || inner < L || (inner % L) != 0) return false;
-    if (p.in_es != (i64)inner || p.out_es != (i64)inner || p.in_s0 != (i64)(N * inner) || p.out_s0 != p.in_s0) return false;
-    if ((p.q_begin % L) != 0 || ((p.q_end - p.q_begin) % L) != 0 || ntiles == 0) return false;
+    if (!pass_takes_tma(key, p) || ntiles == 0) return false;
     if ((((size_t)p.in) | ((size_t)p.out)) & 15) return false;
     return encode_fn() != nullptr;
 }

@@ -333,6 +333,8 @@ struct ConvMidParams {
     int fs_h;
     const double2 *rtw_lo, *rtw_hi; // untangle twiddle exp(-i pi k / N), two-level
     int rtw_h;
+    int prefetch_dist;           // > 0: every CTA first asks L2 for the rows of tile (own + prefetch_dist): one CTA per SM has
+                                 // nothing else to overlap its serial load / transform / store phases with
 };
 
 } // namespace nrb

@@ -55,11 +55,12 @@ static Tunables &tunables_mut()
         x.speq_side = env_int("NRB_SPEQ_SIDE", 1);
         x.conv_fused_mid = env_int("NRB_CONV_FUSED_MID", 1);
         x.conv_rest_log2 = env_int("NRB_CONV_REST_LOG2", 12);
+        x.mid_prefetch = env_int("NRB_MID_PREFETCH", 0);
         x.big_row_mask = env_int("NRB_BIG_ROW_MASK", 0);
         x.big_col_mask = env_int("NRB_BIG_COL_MASK", 0);
         x.dma_streams = env_int("NRB_DMA_STREAMS", 1);
         x.pull_eighths = env_int("NRB_PULL_EIGHTHS", 4);
-        x.tma_col_mask = env_int("NRB_TMA_COL_MASK", 1 << 9);
+        x.tma_col_mask = env_int("NRB_TMA_COL_MASK", (1 << 9) | (1 << 10));
         x.tma_persist = env_int("NRB_TMA_PERSIST", 0);
         x.num_devices = env_int("NRB_NUM_DEVICES", 1);
         x.shard_min_kb = env_int("NRB_SHARD_MIN_KB", 16384);
@@ -92,6 +93,7 @@ int set_tunable(const char *name, long value)
     else if (n == "simple_addr") t.simple_addr = (int)value;
     else if (n == "speq_side") t.speq_side = (int)value;
     else if (n == "conv_fused_mid") t.conv_fused_mid = (int)value;
+    else if (n == "mid_prefetch") t.mid_prefetch = value < 0 ? 0 : (int)value;
     else if (n == "conv_rest_log2") t.conv_rest_log2 = value < 1 ? 1 : value > 12 ? 12 : (int)value;
     else if (n == "big_row_mask") t.big_row_mask = (int)value;
     else if (n == "big_col_mask") t.big_col_mask = (int)value;
@@ -1132,6 +1134,7 @@ static int run_program(Program &prog, double2 *const base[4], int arg, void *mai
             rc = be_launch_fused(st.key, pa, st.key2, pb, fs, stream);
         } else if (st.is_mid) {
             ConvMidParams mp = st.mp;
+            mp.prefetch_dist = tunables().prefetch_dist >= 0 ? tunables().prefetch_dist : tunables().mid_prefetch;
             mp.data = base[st.in.id] + st.in.off;
             mp.b = st.b.id == BUF_NONE ? nullptr : base[st.b.id] + st.b.off;
             rc = be_launch_conv_mid(st.key.log2n, mp, st.ntiles, stream);
@@ -1270,7 +1273,7 @@ int describe_launch(const Plan &pl, int isign, int idx, char *name, size_t cap, 
     } else {
         static const char *var[] = {"plain", "real", "xpose"};
         const double lines = (double)(st.pp.q_end - st.pp.q_begin);
-        snprintf(buf, sizeof(buf), "fft_%s_%s_n%d_%s_L%llu", st.key.layout == LAYOUT_ROW ? "row" : "col", var[st.key.variant],
+        snprintf(buf, sizeof(buf), "fft_%s_%s_n%d_%s_L%llu", st.key.layout == LAYOUT_ROW ? "row" : "col", pass_takes_tma(st.key, st.pp) ? "tma" : var[st.key.variant],
                  1 << st.key.log2n, st.key.dir > 0 ? "p" : "m", (unsigned long long)(st.pp.q_end - st.pp.q_begin));
         b = 2.0 * 16.0 * lines * (double)(1 << st.key.log2n);
         if (st.key.variant == VAR_REAL && st.pp.real_mode == REAL_SPEQ) b += 16.0 * lines;

@@ -122,6 +122,7 @@ struct Tunables {
     int prefetch_dist;     // tiles ahead whose input every CTA prefetches into L2 (NRB_PREFETCH_DIST; 0 = off, -1 = per-kernel policy, default)
     int conv_fused_mid;    // long-line convlv / correl: contiguous forward pass + spectral step + contiguous inverse pass in one kernel
                            // (NRB_CONV_FUSED_MID, default 1: convlv -3 %, correl -9.5 %, autocorrel_fast -5 % at n = 2^22, profiles/r02_tuning.md #39)
+    int mid_prefetch;      // fused conv middle: tiles ahead whose rows every CTA prefetches into L2 (NRB_MID_PREFETCH, default 0)
     int conv_rest_log2;    // long-line convlv / correl: log2 of the contiguous rows of the two-pass split (NRB_CONV_REST_LOG2, default 12:
                            // 4096-point rows; 11 halves the fused middle kernel's CTA so that two fit an SM, at the price of a
                            // 1024-point strided pass)
@@ -136,8 +137,8 @@ struct Tunables {
                            // (NRB_PULL_EIGHTHS, 0 .. 8, default 4: half and half)
     int dma_streams;       // DMA slab exchange: copy streams the pieces of a chunk are spread over (NRB_DMA_STREAMS, 1 .. 4, default 1)
     int tma_col_mask;      // bit log2n set: eligible strided PLAIN passes of 2^log2n points use the TMA-fed kernel of fft_tma.cuh
-                           // (NRB_TMA_COL_MASK, default 1 << 9: the 512-point passes, +2.3 % / +5.7 % on the y / x pass of rlft3 512^3,
-                           // profiles/r02_tuning.md #47); tma_persist = 1: persistent
+                           // (NRB_TMA_COL_MASK, default 512 | 1024: +2.3 % / +5.7 % on the y / x pass of rlft3 512^3, +6 % on the second
+                           // pass of a 2^20 transform, profiles/r02_tuning.md #47); tma_persist = 1: persistent
                            // CTAs with two tile buffers (the next tile's bulk load in flight during the stages)
     int tma_persist;
     int shard_min_kb;      // batches smaller than this stay on one device (NRB_SHARD_MIN_KB, default 16 MiB)
@@ -151,6 +152,21 @@ inline bool pass_is_simple(const KernelKey &key, const PassParams &p)
     if (p.in_eshift <= kMaxLog2N || p.out_eshift <= kMaxLog2N) return false;   // the element index is split
     if (key.layout == LAYOUT_ROW) return p.in_es == 1 && p.out_es == 1;
     return true;
+}
+// does this launch take the TMA-fed strided kernel of fft_tma.cuh (option tma_col_mask)?  Pure function of the launch
+// geometry (the backend additionally needs 16-byte aligned base pointers and the driver's tensor-map encoder): LAYOUT_COL,
+// VAR_PLAIN, no four-step twiddle, no split element index or exchange tables, lines = [outer][inner] with inner a multiple
+// of the tile's line count, the same geometry on both sides.
+inline bool pass_takes_tma(const KernelKey &key, const PassParams &p)
+{
+    if (!((tunables().tma_col_mask >> key.log2n) & 1)) return false;
+    if (key.layout != LAYOUT_COL || key.variant != VAR_PLAIN || p.tw_on || p.out_peer_on || p.in_peer_on || p.grid_cap > 0) return false;
+    if (key.log2n < 7 || key.log2n > 10) return false;
+    if (p.in_eshift <= kMaxLog2N || p.out_eshift <= kMaxLog2N || p.logA != 0 || p.in_s2 != 1 || p.out_s2 != 1) return false;
+    const u64 inner = 1ull << p.logB, N = 1ull << key.log2n, L = (u64)lines_per_tile(key.log2n, LAYOUT_COL);
+    if (p.logB > 28 || inner < L || (inner % L) != 0) return false;
+    if (p.in_es != (i64)inner || p.out_es != (i64)inner || p.in_s0 != (i64)(N * inner) || p.out_s0 != p.in_s0) return false;
+    return (p.q_begin % L) == 0 && ((p.q_end - p.q_begin) % L) == 0 && p.q_end > p.q_begin;
 }
 // does this launch go to the big-tile kernel (if the backend has one for the key)?
 inline bool use_big_tiles(const KernelKey &key, const PassParams &p)
