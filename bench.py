@@ -430,8 +430,8 @@ def run_ours(args, rank, world, local_rank):
             ld, sd, xd = slab.local_doubles, slab.speq_doubles, slab.xchg_doubles
             bufs = [torch.empty(ld, **f64) for _ in range(pool)]
             speq = torch.empty(sd, **f64) if real else None
-            for b in bufs:   # synthetic slab: rank r's share of the seeded sequence
-                lib.fill_uniform_device(b.data_ptr(), seed, rank * ld, ld, st())
+            for i, b in enumerate(bufs):   # synthetic slabs: rank r's share of the seeded sequence, different data in every pool buffer
+                lib.fill_uniform_device(b.data_ptr(), seed, (i * world + rank) * ld, ld, st())
             launches_step = slab.plan.num_launches(1) + slab.plan.num_launches(-1)
             extra["a2a_bytes_per_gpu_per_direction"] = slab.a2a_bytes_per_gpu()
             extra["exchange"] = EXCHANGE_TEXT[args.exchange] + (f" ({slab.chunks} z-chunk(s))" if slab.chunks > 1 else "")

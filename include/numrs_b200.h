@@ -246,7 +246,8 @@ int    nrb_slab_set_send_peers(nrb_slab_t plan, void *const *peer_send, int coun
 size_t nrb_slab_recv_bytes(nrb_slab_t plan);
 /* Collective-free barrier of the fused mode, enqueued on `stream`: phase 0 (after stage 0) publishes
  * `epoch` into this rank's slot of every peer's flag array; phase 1 (before stage 1) spins on the
- * device until all ranks have published `epoch` locally.  Epochs must increase per receive buffer. */
+ * device until all ranks have published `epoch` locally; phase 2 does both in one launch (what nrb_slab_exec uses).
+ * Epochs must increase per receive buffer. */
 int    nrb_slab_barrier(nrb_slab_t plan, int phase, unsigned long long epoch, void *stream);
 /* One whole direction of the fused exchange in one call: stage 0, signal + wait on epoch `epoch`, stage 1. */
 int    nrb_slab_exec(nrb_slab_t plan, int isign, double *d_slab, double *d_speq, unsigned long long epoch, void *stream);

@@ -454,7 +454,7 @@ int nrb_slab_num_launches(nrb_slab_t p, int isign)
 try {
     if (!p) return 0;
     const int s = isign == 1 ? 0 : 1;
-    return (int)(p->plan.prog[s][0].steps.size() + p->plan.prog[s][1].steps.size()) + (p->plan.nranks > 1 ? 2 : 0);
+    return (int)(p->plan.prog[s][0].steps.size() + p->plan.prog[s][1].steps.size()) + (p->plan.nranks > 1 ? 1 : 0);
 } catch (...) { return on_exception(); }
 int nrb_slab_exec(nrb_slab_t p, int isign, double *d_slab, double *d_speq, unsigned long long epoch, void *stream)
 try {

@@ -635,7 +635,15 @@ NRB_DEV void flag_pause() { __nanosleep(200); }
 
 NRB_DEV void aux_signal(const AuxParams &A, u64 gtid, u64)
 {
-    if (gtid < A.count) flag_store(A.peer_flags[gtid] + A.n, A.m);
+    if (gtid < A.count) {
+        flag_store(A.peer_flags[gtid] + A.n, A.m);
+        if (A.op == 1) {      // signal and wait in one launch: A.out = the local flag array
+#if !defined(NRB_EMU)
+            const unsigned long long *local = reinterpret_cast<const unsigned long long *>(A.out);
+            while (flag_load(local + gtid) < A.m) flag_pause();
+#endif
+        }
+    }
 }
 NRB_DEV void aux_wait(const AuxParams &A, u64 gtid, u64)
 {

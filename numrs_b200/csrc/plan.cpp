@@ -1683,12 +1683,14 @@ int slab_barrier_chunk(SlabPlan &sp, int phase, int chunk, unsigned long long ep
     const size_t xchg = sp.xchg_elems();   // complex elements
     AuxParams ap;
     memset(&ap, 0, sizeof(ap));
-    ap.kind = phase == 0 ? AUX_SIGNAL : AUX_WAIT;
+    ap.kind = phase == 1 ? AUX_WAIT : AUX_SIGNAL;      // phase 2: signal, then wait, in ONE launch
+    ap.op = phase == 2 ? 1 : 0;
     ap.m = epoch;
     ap.n = (u64)sp.rank + (u64)chunk * G;       // one flag slot per (chunk, rank)
     ap.count = G;
     for (int i = 0; i < sp.nranks; ++i) ap.peer_flags[i] = (unsigned long long *)(sp.peers[i] + xchg);
-    if (phase != 0) ap.peer_flags[0] = (unsigned long long *)(sp.peers[sp.rank] + xchg) + (u64)chunk * G;
+    ap.out = (double2 *)((unsigned long long *)(sp.peers[sp.rank] + xchg) + (u64)chunk * G);
+    if (phase == 1) ap.peer_flags[0] = (unsigned long long *)(sp.peers[sp.rank] + xchg) + (u64)chunk * G;
     if (be_launch_aux(ap, stream) != 0) { set_error(std::string("kernel launch failed: ") + be_last_error()); return NRB_ERR_CUDA; }
     return NRB_OK;
 }
@@ -1733,10 +1735,9 @@ int exec_slab_fused(SlabPlan &sp, int isign, double *d_slab, double *d_speq, uns
 {
     if (!sp.fused) { set_error("slab: nrb_slab_set_peers first"); return NRB_ERR_INVALID_DIMS; }
     int rc = exec_slab_stage(sp, 0, isign, d_slab, d_speq, nullptr, nullptr, stream);
-    if (rc == NRB_OK && sp.nranks > 1) {
-        rc = slab_barrier(sp, 0, epoch, stream);            // my stage-0 stores have landed everywhere
-        if (rc == NRB_OK) rc = slab_barrier(sp, 1, epoch, stream);   // ... and so have everybody else's here
-    }
+    // one launch: publish my epoch to every peer (my stage-0 stores have landed, my send buffer is complete), then wait
+    // until every peer's epoch has arrived here
+    if (rc == NRB_OK && sp.nranks > 1) rc = slab_barrier(sp, 2, epoch, stream);
     if (rc == NRB_OK) rc = exec_slab_stage(sp, 1, isign, d_slab, d_speq, nullptr, nullptr, stream);
     return rc;
 }

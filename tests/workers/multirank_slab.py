@@ -31,7 +31,7 @@ def main():
     ap.add_argument("--kind", default="rlft3", choices=["rlft3", "fourn"])
     ap.add_argument("--mode", default="fused", choices=["fused", "nccl", "dma"])
     ap.add_argument("--chunks", type=int, default=1)
-    ap.add_argument("--reps", type=int, default=2, help="forward + inverse repetitions (exercises the double-buffered receive buffers)")
+    ap.add_argument("--reps", type=int, default=3, help="forward + inverse repetitions (exercises the double-buffered receive buffers)")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     ndev = torch.cuda.device_count()
@@ -51,27 +51,27 @@ def main():
     X, Y = nn1 // G, nn2 // G
     n = nn1 * nn2 * nn3
     real = a.kind == "rlft3"
-    if real:
-        x = O.fill_uniform(1006, 0, n).reshape(shape)
-        rd, rs = O.rlft3(x.copy(), np.zeros((nn1, 2 * nn2)), 1, mt=False)
-        mine = np.ascontiguousarray(x[:, rank * Y:(rank + 1) * Y, :]).ravel()
-        want = np.ascontiguousarray(rd[rank * X:(rank + 1) * X]).ravel()
-        want_speq = np.ascontiguousarray(rs[rank * X:(rank + 1) * X]).ravel()
-        scale = 2.0 / n
-    else:
-        xf = O.fill_uniform(1008, 0, 2 * n)
+
+    def problem(rep):
+        """Input slab of this rank and the oracle's forward spectrum for repetition `rep`: DIFFERENT data every time, so a
+        stale read of an exchange buffer (they are reused every other call) cannot pass for a fresh one."""
+        if real:
+            x = O.fill_uniform(1006 + rep, 0, n).reshape(shape)
+            rd, rs = O.rlft3(x.copy(), np.zeros((nn1, 2 * nn2)), 1, mt=False)
+            return (np.ascontiguousarray(x[:, rank * Y:(rank + 1) * Y, :]).ravel(), np.ascontiguousarray(rd[rank * X:(rank + 1) * X]).ravel(),
+                    np.ascontiguousarray(rs[rank * X:(rank + 1) * X]).ravel())
+        xf = O.fill_uniform(1008 + rep, 0, 2 * n)
         ref = O.fourn(xf.copy(), list(shape), 1).reshape(nn1, nn2, 2 * nn3)
         xv = xf.reshape(nn1, nn2, 2 * nn3)
-        mine = np.ascontiguousarray(xv[:, rank * Y:(rank + 1) * Y, :]).ravel()
-        want = np.ascontiguousarray(ref[rank * X:(rank + 1) * X]).ravel()
-        want_speq = None
-        scale = 1.0 / n
+        return np.ascontiguousarray(xv[:, rank * Y:(rank + 1) * Y, :]).ravel(), np.ascontiguousarray(ref[rank * X:(rank + 1) * X]).ravel(), None
+    scale = (2.0 / n) if real else (1.0 / n)
     slab = SlabRlft3(lib, nn1, nn2, nn3, mode=a.mode, chunks=a.chunks, kind=a.kind)
-    assert slab.local_doubles == mine.size
-    d = torch.from_numpy(mine.copy()).cuda()
     s = torch.zeros(slab.speq_doubles, dtype=torch.float64, device="cuda") if real else None
     worst = 0.0
     for rep in range(a.reps):
+        mine, want, want_speq = problem(rep)
+        assert slab.local_doubles == mine.size
+        d = torch.from_numpy(mine.copy()).cuda()
         slab.transform(d, s, 1)
         torch.cuda.synchronize()
         e = cases.rel(d.cpu().numpy(), want)
@@ -79,6 +79,11 @@ def main():
             e = max(e, cases.rel(s.cpu().numpy(), want_speq))
         assert e <= cases.tol(n), f"rank {rank} rep {rep}: forward spectrum differs from the oracle: {e:.3e}"
         worst = max(worst, e)
+        if rep % 2 == 1:      # an extra forward call shifts the parity of the double-buffered exchange buffers
+            d2 = torch.from_numpy(mine.copy()).cuda()
+            slab.transform(d2, s, 1)
+            torch.cuda.synchronize()
+            assert cases.rel(d2.cpu().numpy(), want) <= cases.tol(n), f"rank {rank} rep {rep}: repeated forward call differs"
         slab.transform(d, s, -1)
         d.mul_(scale)
         torch.cuda.synchronize()
