@@ -75,6 +75,8 @@ int  nrb_shutdown(void);               /* frees cached plans, twiddle tables no 
  *                       nrb_rlft3 and 3-D nrb_fourn scatter slabs of the host volume over the devices' PCIe links, exchange
  *                       over NVLink peer memory and gather the result; the *_batch calls shard contiguous batch ranges.
  *   "shard_min_kb"      batches smaller than this stay on one device (default 16384)
+ *   "z_chunks"          slab stages: 2 = the z pass and the exchange pass beside it run as two halves of the local y rows,
+ *                       the z pass of one half on a side stream under the exchange pass of the other (default 1 = off)
  *   "pull_eighths"      push + pull slab exchange: eighths of the z range pulled by stage 1 (0 .. 8, default 4)
  *   "dma_streams"       DMA slab exchange: copy streams the pieces of a chunk are spread over (1 .. 4, default 1)
  *   "tma_col_mask"      bit log2 N set: eligible strided passes of N points use the TMA-fed kernel (default 512 | 1024)

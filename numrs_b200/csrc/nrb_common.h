@@ -246,6 +246,10 @@ struct PassParams {
     i64 out_peer_off;
     int out_peer_on, in_peer_on;
     unsigned peer_zmask, peer_zthr;
+    // tile subset (slab stages with the z pass cut into y-chunks, plan.cpp): the launch covers only the tiles whose index
+    // has the bits [tile_run, tile_run + tile_nsel) equal to tile_sel; CTA b works on tile
+    //   (((b >> tile_run) << tile_nsel) | tile_sel) << tile_run | (b & (2^tile_run - 1)).   tile_nsel = 0: all tiles.
+    int tile_run, tile_nsel, tile_sel;
     int prefetch_dist;      // > 0: every CTA first asks L2 for the input of tile (own + prefetch_dist), so DRAM keeps
                             // streaming while the CTAs of an SM are in their shared-memory stages
     int grid_cap;           // > 0: launch at most this many CTAs (they loop over the tiles); used to leave SM slots

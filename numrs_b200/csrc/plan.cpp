@@ -60,6 +60,7 @@ static Tunables &tunables_mut()
         x.big_col_mask = env_int("NRB_BIG_COL_MASK", 0);
         x.dma_streams = env_int("NRB_DMA_STREAMS", 1);
         x.pull_eighths = env_int("NRB_PULL_EIGHTHS", 4);
+        x.z_chunks = env_int("NRB_Z_CHUNKS", 1);
         x.tma_col_mask = env_int("NRB_TMA_COL_MASK", (1 << 9) | (1 << 10));
         x.tma_persist = env_int("NRB_TMA_PERSIST", 0);
         x.num_devices = env_int("NRB_NUM_DEVICES", 1);
@@ -97,6 +98,7 @@ int set_tunable(const char *name, long value)
     else if (n == "conv_rest_log2") t.conv_rest_log2 = value < 1 ? 1 : value > 12 ? 12 : (int)value;
     else if (n == "big_row_mask") t.big_row_mask = (int)value;
     else if (n == "big_col_mask") t.big_col_mask = (int)value;
+    else if (n == "z_chunks") t.z_chunks = (value == 2 || value == 4) ? (int)value : 1;
     else if (n == "pull_eighths") t.pull_eighths = value < 0 ? 0 : value > 8 ? 8 : (int)value;
     else if (n == "dma_streams") t.dma_streams = value < 1 ? 1 : value > 4 ? 4 : (int)value;
     else if (n == "tma_col_mask") t.tma_col_mask = (int)value;
@@ -1103,7 +1105,7 @@ static int run_program(Program &prog, double2 *const base[4], int arg, void *mai
         if (lanes) {
             const bool touches_speq = st.speq.id != BUF_NONE || (st.is_fused && st.speq2.id != BUF_NONE);
             if (st.lane == 1 && (forked || open_side_lane(*side))) {
-                if (!forked) {   // fork: everything enqueued so far precedes the side work
+                if (!forked || st.side_after_main) {   // fork: everything enqueued so far precedes the side work
                     if (be_event_record_on(side->ev_fork, main_stream) != 0 || be_stream_wait(side->stream, side->ev_fork) != 0) {
                         set_error(std::string("side lane fork failed: ") + be_last_error());
                         return NRB_ERR_CUDA;
@@ -1112,7 +1114,7 @@ static int run_program(Program &prog, double2 *const base[4], int arg, void *mai
                 }
                 stream = side->stream;
             } else {
-                if (forked && touches_speq) {   // join before the speq plane is used on the main lane again
+                if (forked && (touches_speq || st.join_side)) {   // join before the speq plane (or a chunk the side lane produced) is used on the main lane again
                     if (be_event_record_on(side->ev_join, side->stream) != 0 || be_stream_wait(main_stream, side->ev_join) != 0) {
                         set_error(std::string("side lane join failed: ") + be_last_error());
                         return NRB_ERR_CUDA;
@@ -1358,6 +1360,41 @@ int build_slab_plan(SlabPlan &sp, size_t nn1, size_t nn2, size_t nn3, int nranks
     // before the z pass of the inverse reads the plane and at the end of every stage (before the exchange barrier)
     const bool side = real && tunables().speq_side != 0;
     auto lane1 = [&](Builder &B, size_t first) { if (side) for (size_t i = first; i < B.prog->steps.size(); ++i) B.prog->steps[i].lane = 1; };
+    // z_chunks = 2: the z pass and the exchange pass beside it are cut into two halves of the local y rows; the z pass of
+    // the second half (forward) / first half (inverse) runs on the side lane under the NVLink-bound exchange pass of the
+    // other half instead of in front of (behind) the whole exchange.  A z launch covers the tiles of its y rows only
+    // (PassParams::tile_run: lines are (x, y), so the rows of a half are every other run of Y/2 lines).
+    const u64 Lz = (u64)lines_per_tile(p3, LAYOUT_ROW);
+    const int ZC = (tunables().z_chunks == 2 && G > 1 && Y >= 2 * Lz && (Y / 2) % Lz == 0) ? 2 : 1;
+    const u64 Yc = Y / (u64)ZC;
+    auto z_chunk = [&](Builder &B, int dir, int c) {
+        emit_z(B, dir);
+        Step &st = B.prog->steps.back();
+        st.pp.tile_run = ilog2((size_t)(Yc / Lz));
+        st.pp.tile_nsel = 1;
+        st.pp.tile_sel = c;
+        st.ntiles /= 2;
+    };
+    auto x_chunk = [&](Builder &B, int dir, int c) {
+        if (dir > 0) emit_axis(B, SLAB, XCH, BufRef(), 1, 0, 1, p1, Y * N3, +1, nullptr, &x_blocks);
+        else emit_axis(B, XCH, SLAB, BufRef(), 1, 0, 1, p1, Y * N3, -1, &x_blocks, nullptr);
+        Step &st = B.prog->steps.back();
+        st.zsplit = true;
+        st.pp.q_begin = (u64)c * Yc * N3;
+        st.pp.q_end = (u64)(c + 1) * Yc * N3;
+        st.ntiles = tiles_for(st.key.log2n, st.key.layout, st.pp.q_end - st.pp.q_begin);
+    };
+    if (ZC == 2) {   // forward stage 0: z0 | x0 beside (z1, speq x pass) | x1
+        Builder B(&sp.prog[0][0]);
+        z_chunk(B, +1, 0);
+        z_chunk(B, +1, 1);
+        B.prog->steps.back().lane = 1;
+        if (real) { emit_axis(B, WSPEQ, XCH + SPQ, BufRef(), 1, 0, 1, p1, Y, +1, nullptr, &x_blocks_speq); B.prog->steps.back().lane = 1; }
+        x_chunk(B, +1, 0);
+        x_chunk(B, +1, 1);
+        B.prog->steps.back().join_side = true;
+        rc = B.rc ? B.rc : rc;
+    } else
     {   // forward stage 0
         Builder B(&sp.prog[0][0]);
         emit_z(B, +1);
@@ -1383,6 +1420,18 @@ int build_slab_plan(SlabPlan &sp, size_t nn1, size_t nn2, size_t nn3, int nranks
         if (real && !side) emit_axis(B, SPEQ, XCH + SPQ, BufRef(), X, 0, X, p2, 1, -1, nullptr, &y_blocks_speq);
         rc = B.rc ? B.rc : rc;
     }
+    if (ZC == 2) {   // inverse stage 1: speq x pass on the side lane | x0 | x1 beside z0 | z1
+        Builder B(&sp.prog[1][1]);
+        if (real) { emit_axis(B, XCH + SPQ, WSPEQ, BufRef(), 1, 0, 1, p1, Y, -1, &x_blocks_speq, nullptr); B.prog->steps.back().lane = 1; }
+        x_chunk(B, -1, 0);
+        z_chunk(B, -1, 0);
+        B.prog->steps.back().lane = 1;
+        B.prog->steps.back().side_after_main = true;      // behind x0
+        x_chunk(B, -1, 1);
+        z_chunk(B, -1, 1);
+        B.prog->steps.back().join_side = true;            // (it reads the speq plane, which the side lane produced)
+        rc = B.rc ? B.rc : rc;
+    } else
     {   // inverse stage 1
         Builder B(&sp.prog[1][1]);
         if (real) { emit_axis(B, XCH + SPQ, WSPEQ, BufRef(), 1, 0, 1, p1, Y, -1, &x_blocks_speq, nullptr); lane1(B, 0); }

@@ -77,6 +77,8 @@ struct Step {
     bool patch_pad_mode;   // AUX_PAD_RESPONSE: op comes from exec's `arg`
     bool is_mid;           // fused conv middle: mp, in = data (in place), b = second operand; key.log2n = log2 REST
     ConvMidParams mp;
+    bool join_side;        // the side lane must have finished before this (lane 0) step starts
+    bool side_after_main;  // this lane-1 step must not start before what the caller's stream holds so far
     bool zsplit;           // slab exchange data pass: its lines' low bits are the z index, so the push + pull split applies
     int lane;              // 0 = the caller's stream; 1 = the plan's side stream (small independent work, see SideLane)
     // fused pair: (key, pp, in/out/speq) is pass A, the *2 members are pass B
@@ -86,7 +88,7 @@ struct Step {
     BufRef in2, out2, speq2;
     FuseSched fs;          // counters live in the plan's scheduler scratch (sched_off = element offset)
     size_t sched_off;
-    Step() : is_aux(false), key{0, 0, 0, 0}, pp(), ap(), ntiles(0), patch_pad_mode(false), is_mid(false), mp(), zsplit(false), lane(0), is_fused(false),
+    Step() : is_aux(false), key{0, 0, 0, 0}, pp(), ap(), ntiles(0), patch_pad_mode(false), is_mid(false), mp(), join_side(false), side_after_main(false), zsplit(false), lane(0), is_fused(false),
              key2{0, 0, 0, 0}, pp2(), fs{nullptr, nullptr, 0, 0, 0, 0}, sched_off(0) {}
 };
 
@@ -133,6 +135,9 @@ struct Tunables {
     int xchg_grid_cap;     // pipelined slab exchange: CTAs of an exchange (peer-store) pass, 0 = one per tile (NRB_XCHG_GRID_CAP)
     int num_devices;       // GPUs the host-slice entry points spread one call over (NRB_NUM_DEVICES; 1 = the calling thread's
                            // device only (default), 0 = every visible device, n = devices 0 .. n-1): multi.cpp
+    int z_chunks;          // slab stages: y-chunks the z pass and the exchange pass beside it are cut into, so that the z pass of
+                           // chunk c + 1 (c - 1) runs on the side stream under the NVLink-bound pass of chunk c
+                           // (NRB_Z_CHUNKS, 1 = off, default; 2 or 4)
     int pull_eighths;      // push + pull exchange: eighths of the z range that stage 1 pulls instead of stage 0 pushing them
                            // (NRB_PULL_EIGHTHS, 0 .. 8, default 4: half and half)
     int dma_streams;       // DMA slab exchange: copy streams the pieces of a chunk are spread over (NRB_DMA_STREAMS, 1 .. 4, default 1)

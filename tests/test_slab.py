@@ -80,6 +80,40 @@ def test_slab_push_pull_exchange(emu, shape, G, eighths):
     emu.set_option("pull_eighths", 4)
 
 
+@pytest.mark.parametrize("shape,G", [((4, 64, 512), 2), ((8, 32, 1024), 2), ((8, 64, 256), 4)])
+def test_slab_z_pass_in_two_y_chunks(emu, shape, G):
+    """z_chunks = 2: the z pass and the exchange pass next to it run as two halves of the local y rows (the z pass of one
+    half on the side lane beside the exchange pass of the other); every launch covers a tile subset
+    (PassParams::tile_run).  rlft3 and fourn, pushed and push + pull, against the oracle element-wise."""
+    emu.set_option("z_chunks", 2)
+    nn1, nn2, nn3 = shape
+    X, Y = nn1 // G, nn2 // G
+    plan = emu.slab_create(nn1, nn2, nn3, G, 0)
+    assert plan.num_launches(1) == 8      # z0, z1, speq x, x0, x1 | barrier | y, speq y
+    plan.destroy()
+    x = O.fill_uniform(1006, 0, nn1 * nn2 * nn3).reshape(shape)
+    rd, rs = O.rlft3(x.copy(), np.zeros((nn1, 2 * nn2)), 1)
+    for pull in (False, True):
+        slabs, speqs = run_simulated(emu, x, G, 1, fused=True, pull=pull)
+        for r in range(G):
+            assert cases.rel(slabs[r], rd[r * X:(r + 1) * X]) <= cases.tol(x.size), (r, "data")
+            assert cases.rel(speqs[r], rs[r * X:(r + 1) * X]) <= cases.tol(x.size), (r, "speq")
+        back, _ = run_simulated(emu, rd, G, -1, rs, fused=True, pull=pull)
+        for r in range(G):
+            assert cases.rel(back[r] * (2.0 / x.size), slab_of(x, r, G)) <= cases.tol(x.size), (r, "round trip")
+    shp = (nn1, nn2, nn3 // 2)
+    n = int(np.prod(shp))
+    xf = O.fill_uniform(1008, 0, 2 * n)
+    ref = O.fourn(xf.copy(), list(shp), 1).view(np.complex128).reshape(shp)
+    z = xf.view(np.complex128).reshape(shp)
+    out = run_simulated_fourn(emu, z, G, 1, 1)
+    for r in range(G):
+        assert cases.rel(out[r].view(np.float64), np.ascontiguousarray(ref[r * X:(r + 1) * X]).view(np.float64)) <= cases.tol(n)
+    back = run_simulated_fourn(emu, ref, G, -1, 1)
+    for r in range(G):
+        assert cases.rel(back[r].view(np.float64) / n, np.ascontiguousarray(z[:, r * Y:(r + 1) * Y, :]).view(np.float64)) <= cases.tol(n)
+
+
 @pytest.mark.parametrize("side", [0, 1])
 @pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("shape,G", [((8, 8, 8), 2), ((16, 16, 8), 4), ((8, 16, 32), 8), ((32, 8, 4), 8), ((4, 4, 2), 4),

@@ -5,7 +5,7 @@ copy streams), NCCL all-to-all.  Prints one line per configuration: ms per forwa
 speed-up over the given 1-GPU time, NVLink GB/s if the step were all exchange, and the round-trip error.
 
     torchrun --nproc-per-node 8 tools/slab_modes.py 512 [ms of the 1-GPU step] [kind] [configs ...]
-    config = mode[:chunks[:dma_streams[:pull_eighths]]]   e.g. fused (push + pull, half and half) fused:1:1:6 push fused:2 dma:2:4 nccl
+    config = mode[:chunks[:dma_streams[:pull_eighths[:z_chunks]]]]   e.g. fused (push + pull, half and half) fused:1:1:6 push fused:2 dma:2:4 nccl
 """
 import os
 import sys
@@ -39,6 +39,7 @@ for cfg in configs:
     chunks = int(parts[1]) if len(parts) > 1 else 1
     streams = int(parts[2]) if len(parts) > 2 else 1
     eighths = int(parts[3]) if len(parts) > 3 else 4
+    lib.set_option("z_chunks", int(parts[4]) if len(parts) > 4 else 1)
     lib.set_option("dma_streams", streams)
     lib.set_option("pull_eighths", eighths)
     pull = mode != "push"
