@@ -74,6 +74,8 @@ int  nrb_shutdown(void);               /* frees cached plans, twiddle tables no 
  *                       (default), 0 = every visible device, n = devices 0 .. n-1 (rounded down to a power of two, <= 8).
  *                       nrb_rlft3 and 3-D nrb_fourn scatter slabs of the host volume over the devices' PCIe links, exchange
  *                       over NVLink peer memory and gather the result; the *_batch calls shard contiguous batch ranges.
+ *   "pipeline_batches"  1 (default): a host-slice batch call of >= 64 MiB runs in chunks over three streams, so the H2D copy
+ *                       of one chunk, the transforms of the previous and the D2H copy of the one before overlap; 0 = one shot
  *   "shard_min_kb"      batches smaller than this stay on one device (default 16384)
  *   "z_chunks"          slab stages: 2 = the z pass and the exchange pass beside it run as two halves of the local y rows,
  *                       the z pass of one half on a side stream under the exchange pass of the other (default 1 = off)
@@ -95,7 +97,8 @@ int  nrb_shutdown(void);               /* frees cached plans, twiddle tables no 
 int  nrb_set_option(const char *name, long value);
 /* pinned host memory, so host-slice calls copy at full PCIe rate (optional) */
 /* Multi-device introspection: devices one host-slice call is spread over under the current "num_devices" option, and the
- * number of calls that really took the multi-device path (which = 0: 3-D transforms, 1: sharded batches). */
+ * number of calls that really took the multi-device path (which = 0: 3-D transforms, 1: sharded batches) or the chunked
+ * three-stream pipeline of the batch calls (which = 2). */
 int   nrb_num_devices_in_use(void);
 long  nrb_multi_device_calls(int which);
 void *nrb_host_alloc(size_t bytes);

@@ -3,6 +3,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -62,9 +63,10 @@ std::set<ThreadCtx *> g_ctxs;
 
 struct ThreadCtx {
     void *stream;
+    void *s_in, *s_out;      // copy streams of the pipelined batch calls (created on first use)
     int device;
     DevBuf io, aux, out;
-    ThreadCtx() : stream(nullptr), device(-1)
+    ThreadCtx() : stream(nullptr), s_in(nullptr), s_out(nullptr), device(-1)
     {
         std::lock_guard<std::mutex> lk(g_ctx_mu);
         g_ctxs.insert(this);
@@ -73,6 +75,8 @@ struct ThreadCtx {
     {
         io.release(); aux.release(); out.release();
         if (stream) { be_stream_destroy(stream); stream = nullptr; }
+        if (s_in) { be_stream_destroy(s_in); s_in = nullptr; }
+        if (s_out) { be_stream_destroy(s_out); s_out = nullptr; }
         device = -1;
     }
     ~ThreadCtx()
@@ -183,15 +187,85 @@ int ensure_buf(DevBuf &b, size_t bytes)
 
 int copy_fail(const char *what) { return fail(NRB_ERR_CUDA, std::string(what) + " failed: " + be_last_error()); }
 
+// ---- batches in chunks over three streams: the H2D copy of chunk c + 1, the transforms of chunk c and the D2H copy of
+// chunk c - 1 overlap, so a batch call keeps both directions of the PCIe link busy instead of using them one after the
+// other (the transforms themselves are a few per cent of the call).  Units of a batch are independent (fft_batch
+// FFT_1.rs:185, convlv_batch Convolve.rs:241, correl_batch Correlation.rs:273), so any split gives the same results.
+size_t pipeline_chunk(size_t count, size_t unit_bytes)
+{
+    const size_t total = count * unit_bytes, min_chunk = (size_t)tunables().pipeline_min_kb << 10;
+    if (!tunables().pipeline_batches || min_chunk == 0 || count < 4 || total < 4 * min_chunk) return 0;   // not worth it: one shot
+    size_t want = total / 8 > min_chunk ? total / 8 : min_chunk;
+    size_t per = (want + unit_bytes - 1) / unit_bytes;
+    if (per < 1) per = 1;
+    return per >= count ? 0 : per;
+}
+
+// runs h2d(first, n, stream), exec(first, n, stream), d2h(first, n, stream) for every chunk with the ordering above
+std::atomic<long> g_pipelined_calls{0};
+
+template <class H2D, class EXEC, class D2H>
+int run_pipelined(size_t count, size_t per, H2D h2d, EXEC exec, D2H d2h)
+{
+    ++g_pipelined_calls;
+    if (!t_ctx.s_in && (be_stream_create(&t_ctx.s_in) != 0 || be_stream_create(&t_ctx.s_out) != 0))
+        return fail(NRB_ERR_CUDA, std::string("stream creation failed: ") + be_last_error());
+    const size_t nchunks = (count + per - 1) / per;
+    std::vector<void *> ev(2 * nchunks, nullptr);
+    int rc = NRB_OK;
+    for (size_t c = 0; c < nchunks && rc == NRB_OK; ++c) {
+        const size_t first = c * per, n = first + per <= count ? per : count - first;
+        void *e_in = ev[2 * c] = be_event_create(), *e_cmp = ev[2 * c + 1] = be_event_create();
+        if (!e_in || !e_cmp) { rc = fail(NRB_ERR_CUDA, "event creation failed"); break; }
+        if ((rc = h2d(first, n, t_ctx.s_in)) != NRB_OK) break;
+        if (be_event_record_on(e_in, t_ctx.s_in) != 0 || be_stream_wait(t_ctx.stream, e_in) != 0) { rc = copy_fail("stream ordering"); break; }
+        if ((rc = exec(first, n, t_ctx.stream)) != NRB_OK) break;
+        if (be_event_record_on(e_cmp, t_ctx.stream) != 0 || be_stream_wait(t_ctx.s_out, e_cmp) != 0) { rc = copy_fail("stream ordering"); break; }
+        rc = d2h(first, n, t_ctx.s_out);
+    }
+    // everything enqueued must have finished before the buffers, the plans or the caller's memory are touched again
+    const int s1 = be_sync(t_ctx.s_in), s2 = be_sync(t_ctx.stream), s3 = be_sync(t_ctx.s_out);
+    if (rc == NRB_OK && (s1 != 0 || s2 != 0 || s3 != 0)) rc = copy_fail("pipelined batch execution");
+    for (void *e : ev) if (e) be_event_destroy(e);
+    return rc;
+}
+
 // in-place transform of `count` host slices of `doubles` doubles each
 int run_inplace(int kind, const size_t *dims, size_t ndim, double *const *ptrs, size_t count, size_t doubles,
                 int isign, double *speq, size_t speq_doubles)
 {
     int rc = ensure_ctx();
     if (rc) return rc;
+    const size_t bytes = doubles * sizeof(double);
+    const size_t per = speq ? 0 : pipeline_chunk(count, bytes);
+    if (per) {
+        // chunks of `per` slices (and a shorter last one): one plan each, both held for the whole call
+        const size_t tail = count % per;
+        auto hp = cached_plan(kind, dims, ndim, per, &rc);
+        if (!hp) return rc;
+        std::shared_ptr<nrb_plan_s> ht = hp;
+        if (tail && !(ht = cached_plan(kind, dims, ndim, tail, &rc))) return rc;
+        if (ensure_buf(t_ctx.io, bytes * count) != 0) return fail(NRB_ERR_OOM, std::string("device allocation failed: ") + be_last_error());
+        char *dio = (char *)t_ctx.io.p;
+        std::unique_lock<std::mutex> l1(hp->mu), l2;
+        if (ht != hp) l2 = std::unique_lock<std::mutex>(ht->mu);
+        auto copy = [&](bool in, size_t first, size_t n, void *st) -> int {
+            for (size_t b = first; b < first + n;) {
+                size_t e = b + 1;
+                while (e < first + n && ptrs[e] == ptrs[b] + (e - b) * doubles) ++e;
+                const int r = in ? be_h2d(dio + b * bytes, ptrs[b], bytes * (e - b), st) : be_d2h(ptrs[b], dio + b * bytes, bytes * (e - b), st);
+                if (r != 0) return copy_fail(in ? "host-to-device copy" : "device-to-host copy");
+                b = e;
+            }
+            return NRB_OK;
+        };
+        return run_pipelined(count, per,
+                             [&](size_t f, size_t n, void *st) { return copy(true, f, n, st); },
+                             [&](size_t f, size_t n, void *st) { return exec_plan((n == per ? hp : ht)->plan, (double *)(dio + f * bytes), nullptr, nullptr, isign == 1 ? 1 : -1, 0, st); },
+                             [&](size_t f, size_t n, void *st) { return copy(false, f, n, st); });
+    }
     auto h = cached_plan(kind, dims, ndim, count, &rc);
     if (!h) return rc;
-    const size_t bytes = doubles * sizeof(double);
     if (ensure_buf(t_ctx.io, bytes * count) != 0) return fail(NRB_ERR_OOM, std::string("device allocation failed: ") + be_last_error());
     if (speq && ensure_buf(t_ctx.aux, speq_doubles * sizeof(double)) != 0) return fail(NRB_ERR_OOM, "device allocation failed");
     void *s = t_ctx.stream;
@@ -228,9 +302,46 @@ int run_outofplace(int kind, const size_t *dims, size_t ndim, const double *cons
 {
     int rc = ensure_ctx();
     if (rc) return rc;
+    const size_t bytes = n * sizeof(double);
+    const size_t per = pipeline_chunk(count, bytes);
+    if (per) {
+        const size_t tail = count % per;
+        const bool per_signal_aux = aux_count == count;
+        auto hp = cached_plan(kind, dims, ndim, per, &rc);
+        if (!hp) return rc;
+        std::shared_ptr<nrb_plan_s> ht = hp;
+        if (tail && !(ht = cached_plan(kind, dims, ndim, tail, &rc))) return rc;
+        if (ensure_buf(t_ctx.io, bytes * count) != 0 || ensure_buf(t_ctx.out, bytes * count) != 0 ||
+            ensure_buf(t_ctx.aux, aux_n * sizeof(double) * aux_count) != 0)
+            return fail(NRB_ERR_OOM, std::string("device allocation failed: ") + be_last_error());
+        std::unique_lock<std::mutex> l1(hp->mu), l2;
+        if (ht != hp) l2 = std::unique_lock<std::mutex>(ht->mu);
+        const size_t aux_bytes = aux_n * sizeof(double);
+        if (!per_signal_aux) {      // one operand for the whole batch (convlv's response): up front, on the compute stream
+            for (size_t b = 0; b < aux_count; ++b)
+                if (be_h2d((char *)t_ctx.aux.p + b * aux_bytes, aux[b], aux_bytes, t_ctx.stream) != 0) return copy_fail("host-to-device copy");
+        }
+        return run_pipelined(count, per,
+                             [&](size_t f, size_t cnt, void *st) -> int {
+                                 for (size_t b = f; b < f + cnt; ++b) {
+                                     if (be_h2d((char *)t_ctx.io.p + b * bytes, in[b], bytes, st) != 0) return copy_fail("host-to-device copy");
+                                     if (per_signal_aux && be_h2d((char *)t_ctx.aux.p + b * aux_bytes, aux[b], aux_bytes, st) != 0) return copy_fail("host-to-device copy");
+                                 }
+                                 return NRB_OK;
+                             },
+                             [&](size_t f, size_t cnt, void *st) {
+                                 return exec_plan((cnt == per ? hp : ht)->plan, (double *)((char *)t_ctx.io.p + f * bytes),
+                                                  (double *)((char *)t_ctx.aux.p + (per_signal_aux ? f * aux_bytes : 0)),
+                                                  (double *)((char *)t_ctx.out.p + f * bytes), isign, arg, st);
+                             },
+                             [&](size_t f, size_t cnt, void *st) -> int {
+                                 for (size_t b = f; b < f + cnt; ++b)
+                                     if (be_d2h(out[b], (char *)t_ctx.out.p + b * bytes, bytes, st) != 0) return copy_fail("device-to-host copy");
+                                 return NRB_OK;
+                             });
+    }
     auto h = cached_plan(kind, dims, ndim, count, &rc);
     if (!h) return rc;
-    const size_t bytes = n * sizeof(double);
     if (ensure_buf(t_ctx.io, bytes * count) != 0 || ensure_buf(t_ctx.out, bytes * count) != 0 ||
         ensure_buf(t_ctx.aux, aux_n * sizeof(double) * aux_count) != 0)
         return fail(NRB_ERR_OOM, std::string("device allocation failed: ") + be_last_error());
@@ -348,7 +459,7 @@ try {
     g_plan_cache.clear();
     return NRB_OK;
 } catch (...) { return on_exception(); }
-long nrb_multi_device_calls(int which) { return multi_calls(which); }
+long nrb_multi_device_calls(int which) { return which == 2 ? g_pipelined_calls.load() : multi_calls(which); }
 int nrb_num_devices_in_use(void) { return multi_device_count(); }
 void *nrb_host_alloc(size_t bytes) { return be_host_alloc(bytes); }
 void nrb_host_free(void *p) { if (p) be_host_free(p); }

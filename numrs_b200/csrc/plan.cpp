@@ -65,6 +65,8 @@ static Tunables &tunables_mut()
         x.tma_persist = env_int("NRB_TMA_PERSIST", 0);
         x.num_devices = env_int("NRB_NUM_DEVICES", 1);
         x.shard_min_kb = env_int("NRB_SHARD_MIN_KB", 16384);
+        x.pipeline_batches = env_int("NRB_PIPELINE_BATCHES", 1);
+        x.pipeline_min_kb = env_int("NRB_PIPELINE_MIN_KB", 16384);
         return x;
     }();
     if (t.col_max_log2 < 1) t.col_max_log2 = 1;
@@ -104,6 +106,8 @@ int set_tunable(const char *name, long value)
     else if (n == "tma_col_mask") t.tma_col_mask = (int)value;
     else if (n == "tma_persist") t.tma_persist = (int)value;
     else if (n == "num_devices") t.num_devices = value < 0 ? 1 : (int)value;
+    else if (n == "pipeline_batches") t.pipeline_batches = value != 0;
+    else if (n == "pipeline_min_kb") t.pipeline_min_kb = value < 1 ? 1 : (int)value;
     else if (n == "shard_min_kb") t.shard_min_kb = value < 0 ? 0 : (int)value;
     else return -1;
     tunables_mut();   // re-clamp

@@ -146,6 +146,9 @@ struct Tunables {
                            // pass of a 2^20 transform, profiles/r02_tuning.md #47); tma_persist = 1: persistent
                            // CTAs with two tile buffers (the next tile's bulk load in flight during the stages)
     int tma_persist;
+    int pipeline_batches;  // host-slice batch calls run in chunks over three streams (H2D | transforms | D2H overlap): 1 (default) / 0
+                           // (NRB_PIPELINE_BATCHES)
+    int pipeline_min_kb;   // smallest chunk of a pipelined batch call (NRB_PIPELINE_MIN_KB, default 16 MiB; calls under 4 chunks stay one shot)
     int shard_min_kb;      // batches smaller than this stay on one device (NRB_SHARD_MIN_KB, default 16 MiB)
 };
 const Tunables &tunables();

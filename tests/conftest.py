@@ -56,6 +56,8 @@ def _reset_options(request):
             L.set_option("mid_prefetch", 0)
             L.set_option("pull_eighths", 4)
             L.set_option("z_chunks", 1)
+            L.set_option("pipeline_batches", 1)
+            L.set_option("pipeline_min_kb", 16384)
             L.set_option("dma_streams", 1)
             L.set_option("tma_col_mask", (1 << 9) | (1 << 10))
             L.set_option("tma_persist", 0)

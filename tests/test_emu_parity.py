@@ -605,6 +605,42 @@ def test_thread_contexts_are_released_at_thread_exit_and_by_shutdown(emu):
     cases.check_four1(emu, 64)
 
 
+@pytest.mark.parametrize("count", [4, 9, 23])
+def test_batch_calls_pipelined_in_chunks(emu, count):
+    """Host-slice batch calls run in chunks over three streams (H2D | transforms | D2H): same results as the oracle per
+    signal for ragged chunk counts (a shorter last chunk has its own plan), for fft_batch, realft batches, convlv_batch
+    (one response for all chunks) and correl_batch (one second operand per pair), and the same as the one-shot path."""
+    emu.set_option("pipeline_min_kb", 4)      # 4 KiB chunks: these small batches split into several
+    before = emu.multi_device_calls(2)
+    nn = 256
+    arrs = [cases.gen(10 + b, 2 * nn) for b in range(count)]
+    refs = [O.four1(a.copy(), nn, -1) for a in arrs]
+    nb.FFTProcessor(emu).fft_batch(arrs, -1)
+    for a, r in zip(arrs, refs):
+        assert cases.rel(a, r) <= cases.tol(nn)
+    n, m = 1024, 9
+    sigs = [cases.gen(40 + b, n) for b in range(count)]
+    resp = cases.gen(99, m)
+    piped = nb.convlv_batch(sigs, resp, 1, 0, emu)
+    for sg, o in zip(sigs, piped):
+        assert cases.rel(o, O.convlv(sg, resp, 1)[1]) <= cases.tol(n)
+    pairs = [(cases.gen(60 + b, n), cases.gen(80 + b, n)) for b in range(count)]
+    pc = nb.correl_batch(pairs, emu)
+    for (a, b), o in zip(pairs, pc):
+        assert cases.rel(o, O.correl(a, b)[1]) <= cases.tol(n)
+    reals = [cases.gen(120 + b, n) for b in range(count)]
+    rrefs = [O.realft(r.copy(), n, 1) for r in reals]
+    nb.RealFTProcessor(emu).process_batch([(r, n, 1) for r in reals])
+    for r, rr in zip(reals, rrefs):
+        assert cases.rel(r, rr) <= cases.tol(n)
+    assert emu.multi_device_calls(2) - before == 4      # all four batch calls took the pipeline
+    emu.set_option("pipeline_batches", 0)
+    for a, b in zip(nb.convlv_batch(sigs, resp, 1, 0, emu), piped):
+        assert np.array_equal(a, b)
+    for a, b in zip(nb.correl_batch(pairs, emu), pc):
+        assert np.array_equal(a, b)
+
+
 def test_plans_survive_shutdown(emu):
     """nrb_shutdown drops the cache's twiddle tables; a plan created earlier holds its own references (plan.h TableRef),
     so executing it afterwards -- with other sizes planned in between, which reallocate tables -- is still exact."""
