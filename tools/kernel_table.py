@@ -11,7 +11,7 @@ import torch  # noqa: E402
 
 import numrs_b200 as nb  # noqa: E402
 
-PEAK = 6551.7
+PEAK = 6650.0   # fallback of B200_PROFILING.md; MEASURED_PEAKS.json wins when present
 try:
     PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
