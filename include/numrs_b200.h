@@ -81,6 +81,7 @@ int  nrb_shutdown(void);               /* frees cached plans, twiddle tables no 
  *                       the z pass of one half on a side stream under the exchange pass of the other (default 1 = off)
  *   "pull_eighths"      push + pull slab exchange: eighths of the z range pulled by stage 1 (0 .. 8, default 4)
  *   "dma_streams"       DMA slab exchange: copy streams the pieces of a chunk are spread over (1 .. 4, default 1)
+ *   "tma_xpose"         1 (default): the transposing 1024-point pass of a multi-step transform loads its tile by TMA
  *   "tma_col_mask"      bit log2 N set: eligible strided passes of N points use the TMA-fed kernel (default 512 | 1024)
  *   "xchg_grid_cap"     pipelined slab exchange: CTAs of a peer-store pass (0 = one per tile); fewer CTAs leave SM
  *                       slots to the local pass running beside it on the second stream

@@ -88,7 +88,9 @@ int launch_tma_pass(const KernelKey &key, const PassParams &p, u64 ntiles, int p
 int be_launch_pass(const KernelKey &key, const PassParams &p, u64 ntiles, void *stream)
 {
     if (tma_pass_eligible(key, p, ntiles)) {
-        const int rc = launch_tma_pass(key, p, ntiles, tunables().tma_persist, (cudaStream_t)stream);
+        PassParams pt = p;
+        pt.simple = pass_is_simple(key, p) ? 1 : 0;
+        const int rc = launch_tma_pass(key, pt, ntiles, tunables().tma_persist, (cudaStream_t)stream);
         if (rc != 0) return fail((cudaError_t)rc);
         return 0;
     }

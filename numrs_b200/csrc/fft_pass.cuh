@@ -556,7 +556,9 @@ NRB_DEV void fft_stage(const PassParams &P, double2 *sm, unsigned tile, int tid)
 
 // run stages FIRST..NST-1; stage FIRST reads global iff SRC_G0, the last stage writes global
 // iff DST_GL.  Barriers: after every stage that wrote shared memory.
-template <int LOG2N, int LAYOUT, int DIR, int VARIANT, int S, bool SRC_G0, bool DST_GL, bool SIMPLE = false, bool TMA = false>
+// TMA: mask of the re/im swaps a TMA-fed pass needs inside its stages (fft_tma.cuh): 1 = on the first stage's shared read
+// (the tile came from global memory as is), 2 = on the last stage's shared write (the tile goes back to global as is)
+template <int LOG2N, int LAYOUT, int DIR, int VARIANT, int S, bool SRC_G0, bool DST_GL, bool SIMPLE = false, int TMA = 0>
 struct StageRunner {
     NRB_DEVM static void run(const PassParams &P, double2 *sm, unsigned tile, int tid)
     {
@@ -564,13 +566,13 @@ struct StageRunner {
         constexpr bool last = (S == NST - 1);
         constexpr bool src_g = (S == 0) && SRC_G0;
         constexpr bool dst_g = last && DST_GL;
-        constexpr int tma_io = TMA ? ((S == 0 ? 1 : 0) | (last ? 2 : 0)) : 0;
+        constexpr int tma_io = ((S == 0 && (TMA & 1)) ? 1 : 0) | ((last && (TMA & 2)) ? 2 : 0);
         fft_stage<LOG2N, LAYOUT, DIR, VARIANT, S, src_g, dst_g, SIMPLE, tma_io>(P, sm, tile, tid);
         if (!dst_g) stage_sync<LOG2N, LAYOUT>();
         StageRunner<LOG2N, LAYOUT, DIR, VARIANT, last ? -1 : S + 1, SRC_G0, DST_GL, SIMPLE, TMA>::run(P, sm, tile, tid);
     }
 };
-template <int LOG2N, int LAYOUT, int DIR, int VARIANT, bool SRC_G0, bool DST_GL, bool SIMPLE, bool TMA>
+template <int LOG2N, int LAYOUT, int DIR, int VARIANT, bool SRC_G0, bool DST_GL, bool SIMPLE, int TMA>
 struct StageRunner<LOG2N, LAYOUT, DIR, VARIANT, -1, SRC_G0, DST_GL, SIMPLE, TMA> {
     NRB_DEVM static void run(const PassParams &, double2 *, unsigned, int) {}
 };
@@ -627,7 +629,9 @@ NRB_DEV void prefetch_tile(const PassParams &P, unsigned tile, int tid)
 }
 
 // ------------------------------------------------------------------ the pass body
-template <int LOG2N, int LAYOUT, int DIR, int VARIANT, bool SIMPLE = false>
+// TILE_IN_SMEM (XPOSE only, fft_tma.cuh): the tile has already been brought into shared memory by a bulk tensor copy, in
+// the layout of Geo::phys, so the first stage reads shared memory too; the transposing epilogue is unchanged.
+template <int LOG2N, int LAYOUT, int DIR, int VARIANT, bool SIMPLE = false, bool TILE_IN_SMEM = false>
 NRB_DEV void fft_pass_body(const PassParams &P, double2 *sm, unsigned tile, int tid)
 {
     typedef Geo<LOG2N, LAYOUT, VARIANT> G;
@@ -643,7 +647,7 @@ NRB_DEV void fft_pass_body(const PassParams &P, double2 *sm, unsigned tile, int 
         // COL layout; last stage to shared memory, then row-like (line-contiguous) store with the
         // four-step twiddle W^(q1(l)*k).  A thread's elements share k (C distinct values when N > NT)
         // and walk the lines with a fixed step D, so the twiddle is a geometric sequence per k.
-        StageRunner<LOG2N, LAYOUT, DIR, VARIANT, 0, true, false, SIMPLE>::run(P, sm, tile, tid);
+        StageRunner<LOG2N, LAYOUT, DIR, VARIANT, 0, !TILE_IN_SMEM, false, SIMPLE, TILE_IN_SMEM ? 1 : 0>::run(P, sm, tile, tid);
         constexpr int C = (G::N > G::NT) ? G::N / G::NT : 1;
         constexpr int D = (G::NT >= G::N) ? G::NT / G::N : 1;
         constexpr int E = G::PPT / C;

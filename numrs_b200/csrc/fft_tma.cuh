@@ -117,7 +117,7 @@ fft_col_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         }
         tma_mbar_wait(&bar[buf], phase[buf]);
         phase[buf] ^= 1u;
-        StageRunner<LOG2N, LAYOUT_COL, DIR, VAR_PLAIN, 0, false, false, false, true>::run(P, sm, tile, tid);
+        StageRunner<LOG2N, LAYOUT_COL, DIR, VAR_PLAIN, 0, false, false, false, 3>::run(P, sm, tile, tid);
         // generic-proxy writes of the last stage -> visible to the async proxy, then one thread hands the tile to TMA
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
@@ -133,6 +133,39 @@ fft_col_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
     }
     // the bulk stores must have READ the tile before the CTA's shared memory goes away (the global writes finish on their own)
     if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// The TRANSPOSING pass of a multi-step transform (VAR_XPOSE) with its strided loads done by TMA: only for 1024-point lines,
+// whose 4-lines-per-tile shared layout is XOR-swizzled (Geo::phys: a ^ ((a >> 3) & 3) in 16-byte units) -- exactly the
+// TMA's 64-byte swizzle for a 64-byte inner box, so the bulk copy can write the layout the stages expect.  The line-
+// contiguous store with the four-step twiddle stays as it is (fft_pass_body's epilogue).
+template <int DIR>
+__global__ void __launch_bounds__(cta_threads(10, LAYOUT_COL), 2)
+fft_xpose_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ PassParams P, const unsigned ntiles, const unsigned log2_inner)
+{
+    typedef Geo<10, LAYOUT_COL, VAR_XPOSE> G;
+    static_assert(G::L == 4, "the 64-byte swizzle matches the 4-lines-per-tile layout only");
+    constexpr int ROWS = 256, NBOX = G::N / ROWS;
+    extern __shared__ __align__(1024) double2 nrb_tma_smem[];
+    __shared__ __align__(8) unsigned long long bar;
+    const int tid = (int)threadIdx.x;
+    const unsigned tile = blockIdx.x;
+    if (tile >= ntiles) return;
+    if (tid == 0) {
+        tma_mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned long long q0 = P.q_begin + (unsigned long long)tile * G::L;
+        const int c0 = 2 * (int)((unsigned)q0 & ((1u << log2_inner) - 1u)), c2 = (int)(q0 >> log2_inner);
+        tma_mbar_expect_tx(&bar, (unsigned)G::TILE * 16u);
+#pragma unroll
+        for (int b = 0; b < NBOX; ++b) tma_load_3d(nrb_tma_smem + (size_t)b * ROWS * G::L, &tm_in, c0, b * ROWS, c2, &bar);
+    }
+    __syncthreads();
+    tma_mbar_wait(&bar, 0u);
+    if constexpr (simple_built(10, LAYOUT_COL, VAR_XPOSE)) {
+        if (P.simple) { fft_pass_body<10, LAYOUT_COL, DIR, VAR_XPOSE, true, true>(P, nrb_tma_smem, tile, tid); return; }
+    }
+    fft_pass_body<10, LAYOUT_COL, DIR, VAR_XPOSE, false, true>(P, nrb_tma_smem, tile, tid);
 }
 
 } // namespace nrb

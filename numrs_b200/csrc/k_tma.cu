@@ -35,7 +35,7 @@ bool tma_pass_eligible(const KernelKey &key, const PassParams &p, u64 ntiles)
     return encode_fn() != nullptr;
 }
 
-static int make_map(CUtensorMap *m, const double2 *base, u64 inner, u64 N, u64 outer, int log2n)
+static int make_map(CUtensorMap *m, const double2 *base, u64 inner, u64 N, u64 outer, int log2n, bool swizzle64 = false)
 {
     const u64 L = (u64)lines_per_tile(log2n, LAYOUT_COL);
     const cuuint64_t gdim[3] = {2 * inner, N, outer};
@@ -43,7 +43,7 @@ static int make_map(CUtensorMap *m, const double2 *base, u64 inner, u64 N, u64 o
     const cuuint32_t box[3] = {(cuuint32_t)(2 * L), (cuuint32_t)(N < 256 ? N : 256), 1};
     const cuuint32_t est[3] = {1, 1, 1};
     const CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)base, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                   swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
@@ -77,8 +77,31 @@ static int launch_tma_t(const PassParams &p, u64 ntiles, cudaStream_t s)
     return (int)cudaGetLastError();
 }
 
+template <int DIR> static int launch_xpose_tma_t(const PassParams &p, u64 ntiles, cudaStream_t s)
+{
+    typedef Geo<10, LAYOUT_COL, VAR_XPOSE> G;
+    constexpr size_t smem = (size_t)G::TILE * 16;
+    auto kern = fft_xpose_tma_kernel<DIR>;
+    static bool ready[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!ready[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        ready[dev & 63] = true;
+    }
+    const u64 rest = 1ull << p.logA;
+    const u64 outer = (p.q_end + rest - 1) >> p.logA;
+    CUtensorMap tin;
+    const int rc = make_map(&tin, p.in, rest, 1024, outer, 10, true);
+    if (rc != 0) return rc;
+    kern<<<(unsigned)ntiles, G::NT, smem, s>>>(tin, p, (unsigned)ntiles, (unsigned)p.logA);
+    return (int)cudaGetLastError();
+}
+
 int launch_tma_pass(const KernelKey &key, const PassParams &p, u64 ntiles, int persist, cudaStream_t s)
 {
+    if (key.variant == VAR_XPOSE) return key.dir > 0 ? launch_xpose_tma_t<+1>(p, ntiles, s) : launch_xpose_tma_t<-1>(p, ntiles, s);
 #define NRB_TMA_CASE(LG) \
     case LG: \
         if (key.dir > 0) return persist ? launch_tma_t<LG, +1, true>(p, ntiles, s) : launch_tma_t<LG, +1, false>(p, ntiles, s); \

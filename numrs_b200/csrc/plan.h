@@ -146,6 +146,7 @@ struct Tunables {
                            // pass of a 2^20 transform, profiles/r02_tuning.md #47); tma_persist = 1: persistent
                            // CTAs with two tile buffers (the next tile's bulk load in flight during the stages)
     int tma_persist;
+    int tma_xpose;         // the transposing 1024-point pass loads its tile by TMA (64-byte swizzle) (NRB_TMA_XPOSE, default 1: +4.3 % on the first pass of a 2^20 transform, profiles/r02_tuning.md #56)
     int pipeline_batches;  // host-slice batch calls run in chunks over three streams (H2D | transforms | D2H overlap): 1 (default) / 0
                            // (NRB_PIPELINE_BATCHES)
     int pipeline_min_kb;   // smallest chunk of a pipelined batch call (NRB_PIPELINE_MIN_KB, default 16 MiB; calls under 4 chunks stay one shot)
@@ -165,8 +166,20 @@ inline bool pass_is_simple(const KernelKey &key, const PassParams &p)
 // geometry (the backend additionally needs 16-byte aligned base pointers and the driver's tensor-map encoder): LAYOUT_COL,
 // VAR_PLAIN, no four-step twiddle, no split element index or exchange tables, lines = [outer][inner] with inner a multiple
 // of the tile's line count, the same geometry on both sides.
+// the transposing 1024-point pass with TMA loads (fft_xpose_tma_kernel): tma_xpose option, geometry of emit_axis's first
+// multi-step pass (lines = [outer][rest] with the rest index contiguous, element stride rest)
+inline bool pass_takes_tma_xpose(const KernelKey &key, const PassParams &p)
+{
+    if (!tunables().tma_xpose || key.layout != LAYOUT_COL || key.variant != VAR_XPOSE || key.log2n != 10) return false;
+    if (p.out_peer_on || p.in_peer_on || p.grid_cap > 0 || p.tile_nsel > 0 || p.in_eshift <= kMaxLog2N) return false;
+    if (p.logB != 0 || p.logA < 2 || p.logA > 28 || p.in_s1 != 1) return false;
+    const u64 rest = 1ull << p.logA, L = 4;
+    if (p.in_es != (i64)rest || p.in_s0 != (i64)(rest << 10)) return false;
+    return (p.q_begin % L) == 0 && ((p.q_end - p.q_begin) % L) == 0 && p.q_end > p.q_begin;
+}
 inline bool pass_takes_tma(const KernelKey &key, const PassParams &p)
 {
+    if (pass_takes_tma_xpose(key, p)) return true;
     if (!((tunables().tma_col_mask >> key.log2n) & 1)) return false;
     if (key.layout != LAYOUT_COL || key.variant != VAR_PLAIN || p.tw_on || p.out_peer_on || p.in_peer_on || p.grid_cap > 0) return false;
     if (key.log2n < 7 || key.log2n > 10) return false;

@@ -61,3 +61,4 @@ def _reset_options(request):
             L.set_option("dma_streams", 1)
             L.set_option("tma_col_mask", (1 << 9) | (1 << 10))
             L.set_option("tma_persist", 0)
+            L.set_option("tma_xpose", 1)

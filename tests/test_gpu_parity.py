@@ -454,6 +454,24 @@ def test_tma_fed_strided_passes(gpu, persist):
             cases.check_rlft3(gpu, shape)
 
 
+def test_tma_loaded_transposing_pass(gpu):
+    """The first pass of a 2^20 transform (transposing 1024-point pass) with its strided loads done by TMA into the
+    XOR-swizzled tile layout (64-byte TMA swizzle): same results as the register-fed pass to the last bit, and the oracle's."""
+    for nn, cnt in ((1 << 20, 3), (1 << 20, 1)):
+        outs = []
+        for flag in (0, 1):
+            gpu.set_option("tma_xpose", flag)
+            x = cases.gen(33, 2 * nn * cnt)
+            arrs = [x[2 * nn * b:2 * nn * (b + 1)] for b in range(cnt)]
+            nb.FFTProcessor(gpu).fft_batch(arrs, 1)
+            nb.FFTProcessor(gpu).fft_batch(arrs, -1)
+            outs.append(x)
+        assert cases.rel(outs[1], outs[0]) <= 1e-15
+    gpu.set_option("tma_xpose", 1)
+    cases.check_four1(gpu, 1 << 20)
+    cases.check_realft(gpu, 1 << 21)
+
+
 def test_twofft_processor_batch(gpu):
     cases.check_twofft_batch(gpu, [64, 4096, 64, 1 << 15, 4096, 2, 1 << 15])
 
