@@ -629,7 +629,7 @@ NRB_DEV void prefetch_tile(const PassParams &P, unsigned tile, int tid)
 }
 
 // ------------------------------------------------------------------ the pass body
-// TILE_IN_SMEM (XPOSE only, fft_tma.cuh): the tile has already been brought into shared memory by a bulk tensor copy, in
+// TILE_IN_SMEM (PLAIN and XPOSE, fft_tma.cuh): the tile has already been brought into shared memory by a bulk tensor copy, in
 // the layout of Geo::phys, so the first stage reads shared memory too; the transposing epilogue is unchanged.
 template <int LOG2N, int LAYOUT, int DIR, int VARIANT, bool SIMPLE = false, bool TILE_IN_SMEM = false>
 NRB_DEV void fft_pass_body(const PassParams &P, double2 *sm, unsigned tile, int tid)
@@ -639,7 +639,7 @@ NRB_DEV void fft_pass_body(const PassParams &P, double2 *sm, unsigned tile, int 
         tile = (((((tile >> P.tile_run) << P.tile_nsel) | (unsigned)P.tile_sel) << P.tile_run) | (tile & ((1u << P.tile_run) - 1u)));
 
     if (VARIANT == VAR_PLAIN) {
-        StageRunner<LOG2N, LAYOUT, DIR, VARIANT, 0, true, true, SIMPLE>::run(P, sm, tile, tid);
+        StageRunner<LOG2N, LAYOUT, DIR, VARIANT, 0, !TILE_IN_SMEM, true, SIMPLE, TILE_IN_SMEM ? 1 : 0>::run(P, sm, tile, tid);
         return;
     }
 

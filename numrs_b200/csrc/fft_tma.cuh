@@ -135,6 +135,38 @@ fft_col_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
     if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// TMA on the INPUT side only: the tile is loaded by bulk tensor copies, the stages run shared -> shared except the last,
+// which stores to global memory from registers as in fft_pass.cuh -- so the output side may be anything the generic pass
+// can address (four-step twiddle + transposed strides, split element index, exchange pointer tables), and the pass makes
+// NST shared-memory round trips instead of the NST + 1 of the load-and-store version.
+template <int LOG2N, int DIR, int CTAS>
+__global__ void __launch_bounds__(cta_threads(LOG2N, LAYOUT_COL), CTAS)
+fft_col_tma_in_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ PassParams P, const unsigned ntiles, const unsigned log2_inner)
+{
+    typedef Geo<LOG2N, LAYOUT_COL, VAR_PLAIN> G;
+    constexpr int ROWS = G::N < 256 ? G::N : 256, NBOX = G::N / ROWS;
+    extern __shared__ __align__(128) double2 nrb_tma_smem[];
+    __shared__ __align__(8) unsigned long long bar;
+    const int tid = (int)threadIdx.x;
+    const unsigned tile = blockIdx.x;
+    if (tile >= ntiles) return;
+    if (tid == 0) {
+        tma_mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned long long q0 = P.q_begin + (unsigned long long)tile * G::L;
+        const int c0 = 2 * (int)((unsigned)q0 & ((1u << log2_inner) - 1u)), c2 = (int)(q0 >> log2_inner);
+        tma_mbar_expect_tx(&bar, (unsigned)G::TILE * 16u);
+#pragma unroll
+        for (int b = 0; b < NBOX; ++b) tma_load_3d(nrb_tma_smem + (size_t)b * ROWS * G::L, &tm_in, c0, b * ROWS, c2, &bar);
+    }
+    __syncthreads();
+    tma_mbar_wait(&bar, 0u);
+    if constexpr (simple_built(LOG2N, LAYOUT_COL, VAR_PLAIN)) {
+        if (P.simple) { fft_pass_body<LOG2N, LAYOUT_COL, DIR, VAR_PLAIN, true, true>(P, nrb_tma_smem, tile, tid); return; }
+    }
+    fft_pass_body<LOG2N, LAYOUT_COL, DIR, VAR_PLAIN, false, true>(P, nrb_tma_smem, tile, tid);
+}
+
 // The TRANSPOSING pass of a multi-step transform (VAR_XPOSE) with its strided loads done by TMA: only for 1024-point lines,
 // whose 4-lines-per-tile shared layout is XOR-swizzled (Geo::phys: a ^ ((a >> 3) & 3) in 16-byte units) -- exactly the
 // TMA's 64-byte swizzle for a 64-byte inner box, so the bulk copy can write the layout the stages expect.  The line-

@@ -31,6 +31,7 @@ static EncodeTiledFn encode_fn()
 bool tma_pass_eligible(const KernelKey &key, const PassParams &p, u64 ntiles)
 {
     if (!pass_takes_tma(key, p) || ntiles == 0) return false;
+    if (p.out_peer_on && !pass_takes_tma_in(key, p)) return false;
     if ((((size_t)p.in) | ((size_t)p.out)) & 15) return false;
     return encode_fn() != nullptr;
 }
@@ -77,6 +78,28 @@ static int launch_tma_t(const PassParams &p, u64 ntiles, cudaStream_t s)
     return (int)cudaGetLastError();
 }
 
+template <int LOG2N, int DIR, int CTAS = 2> static int launch_tma_in_t(const PassParams &p, u64 ntiles, int log2_inner, cudaStream_t s)
+{
+    typedef Geo<LOG2N, LAYOUT_COL, VAR_PLAIN> G;
+    constexpr size_t smem = (size_t)G::TILE * 16;
+    auto kern = fft_col_tma_in_kernel<LOG2N, DIR, CTAS>;
+    static bool ready[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!ready[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        ready[dev & 63] = true;
+    }
+    const u64 inner = 1ull << log2_inner;
+    const u64 outer = (p.q_end + inner - 1) >> log2_inner;
+    CUtensorMap tin;
+    const int rc = make_map(&tin, p.in, inner, 1ull << LOG2N, outer, LOG2N);
+    if (rc != 0) return rc;
+    kern<<<(unsigned)ntiles, G::NT, smem, s>>>(tin, p, (unsigned)ntiles, (unsigned)log2_inner);
+    return (int)cudaGetLastError();
+}
+
 template <int DIR> static int launch_xpose_tma_t(const PassParams &p, u64 ntiles, cudaStream_t s)
 {
     typedef Geo<10, LAYOUT_COL, VAR_XPOSE> G;
@@ -102,6 +125,18 @@ template <int DIR> static int launch_xpose_tma_t(const PassParams &p, u64 ntiles
 int launch_tma_pass(const KernelKey &key, const PassParams &p, u64 ntiles, int persist, cudaStream_t s)
 {
     if (key.variant == VAR_XPOSE) return key.dir > 0 ? launch_xpose_tma_t<+1>(p, ntiles, s) : launch_xpose_tma_t<-1>(p, ntiles, s);
+    int li = 0;
+    if (pass_takes_tma_in(key, p, &li)) {
+        switch (key.log2n) {
+        case 7: return key.dir > 0 ? launch_tma_in_t<7, +1>(p, ntiles, li, s) : launch_tma_in_t<7, -1>(p, ntiles, li, s);
+        case 8: return key.dir > 0 ? launch_tma_in_t<8, +1>(p, ntiles, li, s) : launch_tma_in_t<8, -1>(p, ntiles, li, s);
+        case 9:
+            if (tunables().tma_in_ctas >= 3) return key.dir > 0 ? launch_tma_in_t<9, +1, 3>(p, ntiles, li, s) : launch_tma_in_t<9, -1, 3>(p, ntiles, li, s);
+            return key.dir > 0 ? launch_tma_in_t<9, +1>(p, ntiles, li, s) : launch_tma_in_t<9, -1>(p, ntiles, li, s);
+        case 10: return key.dir > 0 ? launch_tma_in_t<10, +1>(p, ntiles, li, s) : launch_tma_in_t<10, -1>(p, ntiles, li, s);
+        default: return (int)cudaErrorInvalidValue;
+        }
+    }
 #define NRB_TMA_CASE(LG) \
     case LG: \
         if (key.dir > 0) return persist ? launch_tma_t<LG, +1, true>(p, ntiles, s) : launch_tma_t<LG, +1, false>(p, ntiles, s); \

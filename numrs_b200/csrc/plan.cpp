@@ -64,6 +64,8 @@ static Tunables &tunables_mut()
         x.tma_col_mask = env_int("NRB_TMA_COL_MASK", (1 << 9) | (1 << 10));
         x.tma_persist = env_int("NRB_TMA_PERSIST", 0);
         x.tma_xpose = env_int("NRB_TMA_XPOSE", 1);
+        x.tma_in_mask = env_int("NRB_TMA_IN_MASK", 0);
+        x.tma_in_ctas = env_int("NRB_TMA_IN_CTAS", 2);
         x.num_devices = env_int("NRB_NUM_DEVICES", 1);
         x.shard_min_kb = env_int("NRB_SHARD_MIN_KB", 16384);
         x.pipeline_batches = env_int("NRB_PIPELINE_BATCHES", 1);
@@ -107,6 +109,8 @@ int set_tunable(const char *name, long value)
     else if (n == "tma_col_mask") t.tma_col_mask = (int)value;
     else if (n == "tma_persist") t.tma_persist = (int)value;
     else if (n == "tma_xpose") t.tma_xpose = value != 0;
+    else if (n == "tma_in_mask") t.tma_in_mask = (int)value;
+    else if (n == "tma_in_ctas") t.tma_in_ctas = value >= 3 ? 3 : 2;
     else if (n == "num_devices") t.num_devices = value < 0 ? 1 : (int)value;
     else if (n == "pipeline_batches") t.pipeline_batches = value != 0;
     else if (n == "pipeline_min_kb") t.pipeline_min_kb = value < 1 ? 1 : (int)value;
@@ -1281,7 +1285,7 @@ int describe_launch(const Plan &pl, int isign, int idx, char *name, size_t cap, 
     } else {
         static const char *var[] = {"plain", "real", "xpose"};
         const double lines = (double)(st.pp.q_end - st.pp.q_begin);
-        snprintf(buf, sizeof(buf), "fft_%s_%s_n%d_%s_L%llu", st.key.layout == LAYOUT_ROW ? "row" : "col", pass_takes_tma_xpose(st.key, st.pp) ? "xpose_tma" : pass_takes_tma(st.key, st.pp) ? "tma" : var[st.key.variant],
+        snprintf(buf, sizeof(buf), "fft_%s_%s_n%d_%s_L%llu", st.key.layout == LAYOUT_ROW ? "row" : "col", pass_takes_tma_xpose(st.key, st.pp) ? "xpose_tma" : pass_takes_tma_in(st.key, st.pp) ? "tma_in" : pass_takes_tma(st.key, st.pp) ? "tma" : var[st.key.variant],
                  1 << st.key.log2n, st.key.dir > 0 ? "p" : "m", (unsigned long long)(st.pp.q_end - st.pp.q_begin));
         b = 2.0 * 16.0 * lines * (double)(1 << st.key.log2n);
         if (st.key.variant == VAR_REAL && st.pp.real_mode == REAL_SPEQ) b += 16.0 * lines;

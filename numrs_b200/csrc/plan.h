@@ -146,6 +146,9 @@ struct Tunables {
                            // pass of a 2^20 transform, profiles/r02_tuning.md #47); tma_persist = 1: persistent
                            // CTAs with two tile buffers (the next tile's bulk load in flight during the stages)
     int tma_persist;
+    int tma_in_mask;       // bit log2n set: strided PLAIN passes of 2^log2n points whose input side is regular load their tile by TMA and
+                           // store from registers (NRB_TMA_IN_MASK); takes precedence over tma_col_mask
+    int tma_in_ctas;       // resident CTAs per SM the input-only TMA pass of 512-point lines is compiled for: 2 (no spills) or 3 (80 registers)
     int tma_xpose;         // the transposing 1024-point pass loads its tile by TMA (64-byte swizzle) (NRB_TMA_XPOSE, default 1: +4.3 % on the first pass of a 2^20 transform, profiles/r02_tuning.md #56)
     int pipeline_batches;  // host-slice batch calls run in chunks over three streams (H2D | transforms | D2H overlap): 1 (default) / 0
                            // (NRB_PIPELINE_BATCHES)
@@ -177,9 +180,27 @@ inline bool pass_takes_tma_xpose(const KernelKey &key, const PassParams &p)
     if (p.in_es != (i64)rest || p.in_s0 != (i64)(rest << 10)) return false;
     return (p.q_begin % L) == 0 && ((p.q_end - p.q_begin) % L) == 0 && p.q_end > p.q_begin;
 }
+// TMA on the input side only (fft_col_tma_in_kernel, option tma_in_mask): any strided PLAIN pass whose INPUT is the regular
+// [outer][N][inner] geometry -- expressed either through (logB, in_s2) as emit_axis does or through (logA, in_s1) as the
+// conv passes do; *log2_inner tells which.  The output side is unconstrained.
+inline bool pass_takes_tma_in(const KernelKey &key, const PassParams &p, int *log2_inner = nullptr)
+{
+    if (!((tunables().tma_in_mask >> key.log2n) & 1)) return false;
+    if (key.layout != LAYOUT_COL || key.variant != VAR_PLAIN || p.in_peer_on || p.grid_cap > 0 || p.tile_nsel > 0) return false;
+    if (key.log2n < 7 || key.log2n > 10 || p.in_eshift <= kMaxLog2N) return false;
+    int li = -1;
+    if (p.logA == 0 && p.in_s2 == 1 && p.logB <= 28) li = p.logB;
+    else if (p.logB == 0 && p.in_s1 == 1 && p.logA <= 28) li = p.logA;
+    if (li < 0) return false;
+    const u64 inner = 1ull << li, N = 1ull << key.log2n, L = (u64)lines_per_tile(key.log2n, LAYOUT_COL);
+    if (inner < L || (inner % L) != 0 || p.in_es != (i64)inner || p.in_s0 != (i64)(N * inner)) return false;
+    if ((p.q_begin % L) != 0 || ((p.q_end - p.q_begin) % L) != 0 || p.q_end <= p.q_begin) return false;
+    if (log2_inner) *log2_inner = li;
+    return true;
+}
 inline bool pass_takes_tma(const KernelKey &key, const PassParams &p)
 {
-    if (pass_takes_tma_xpose(key, p)) return true;
+    if (pass_takes_tma_xpose(key, p) || pass_takes_tma_in(key, p)) return true;
     if (!((tunables().tma_col_mask >> key.log2n) & 1)) return false;
     if (key.layout != LAYOUT_COL || key.variant != VAR_PLAIN || p.tw_on || p.out_peer_on || p.in_peer_on || p.grid_cap > 0) return false;
     if (key.log2n < 7 || key.log2n > 10) return false;

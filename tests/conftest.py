@@ -62,3 +62,5 @@ def _reset_options(request):
             L.set_option("tma_col_mask", (1 << 9) | (1 << 10))
             L.set_option("tma_persist", 0)
             L.set_option("tma_xpose", 1)
+            L.set_option("tma_in_mask", 0)
+            L.set_option("tma_in_ctas", 2)

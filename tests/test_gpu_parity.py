@@ -454,6 +454,38 @@ def test_tma_fed_strided_passes(gpu, persist):
             cases.check_rlft3(gpu, shape)
 
 
+@pytest.mark.parametrize("ctas", [2, 3])
+def test_tma_input_only_strided_passes(gpu, ctas):
+    """fft_col_tma_in_kernel: TMA on the input side only, register stores on the output side -- so also for passes with a
+    four-step twiddle / transposed output (multi-step transforms, the conv passes): bit-identical to the register-fed
+    kernels, and the oracle's results."""
+    gpu.set_option("tma_in_ctas", ctas)
+    outs = []
+    for mask in (0, 0x780):
+        gpu.set_option("tma_in_mask", mask)
+        res = []
+        x = cases.gen(34, 2 * (1 << 22))
+        nb.four1(x, 1 << 22, 1, gpu)                     # 256 x 128 x 128: two transposing passes + a plain one
+        res.append(x)
+        y = cases.gen(35, 2 * 8192 * 512)
+        nb.fourn(y, [8192, 512], 2, -1, gpu)              # strided 8192 = 128 x 64 with twiddle, then 512 strided? (rows)
+        res.append(y)
+        v = cases.gen(36, 64 * 512 * 32).reshape(64, 512, 32)
+        s = np.zeros((64, 1024))
+        nb.rlft3(v, s, 64, 512, 32, 1, gpu)
+        res.append(np.concatenate([v.ravel(), s.ravel()]))
+        sig = [cases.gen(37 + b, 1 << 20) for b in range(2)]
+        res.append(np.concatenate(nb.convlv_batch(sig, cases.gen(40, 33), 1, 0, gpu)))
+        outs.append(res)
+    for a, b in zip(outs[0], outs[1]):
+        assert cases.rel(b, a) <= 1e-15
+    gpu.set_option("tma_in_mask", 0x780)
+    cases.check_convlv(gpu, 1 << 20, 4096)
+    cases.check_correl(gpu, 1 << 20)
+    cases.check_fourn(gpu, (1024, 64))
+    cases.check_rlft3(gpu, (16, 512, 32))
+
+
 def test_tma_loaded_transposing_pass(gpu):
     """The first pass of a 2^20 transform (transposing 1024-point pass) with its strided loads done by TMA into the
     XOR-swizzled tile layout (64-byte TMA swizzle): same results as the register-fed pass to the last bit, and the oracle's."""
