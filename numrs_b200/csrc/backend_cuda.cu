@@ -113,6 +113,23 @@ int be_launch_pass(const KernelKey &key, const PassParams &p, u64 ntiles, void *
 }
 
 int launch_conv_mid(int log2rest, const ConvMidParams &m, u64 ntiles, cudaStream_t s);   // k_mid.cu
+int launch_trig(int log2n, const TrigParams &t, cudaStream_t s);                           // k_trig.cu
+int launch_twofft(int log2n, const TwoFFTParams &t, cudaStream_t s);
+bool be_trig_available(int log2n) { return log2n >= kTrigMinLog2 && log2n <= kTrigMaxLog2; }
+int be_launch_trig(int log2n, const TrigParams &t, void *stream)
+{
+    if (!be_trig_available(log2n)) { g_be_err = "trig kernel not built for this line length"; return -1; }
+    const int rc = launch_trig(log2n, t, (cudaStream_t)stream);
+    if (rc != 0) { g_be_err = cudaGetErrorString((cudaError_t)rc); return -1; }
+    return 0;
+}
+int be_launch_twofft(int log2n, const TwoFFTParams &t, void *stream)
+{
+    if (!be_trig_available(log2n)) { g_be_err = "twofft kernel not built for this line length"; return -1; }
+    const int rc = launch_twofft(log2n, t, (cudaStream_t)stream);
+    if (rc != 0) { g_be_err = cudaGetErrorString((cudaError_t)rc); return -1; }
+    return 0;
+}
 bool be_conv_mid_available(int log2rest) { return log2rest == 4 || log2rest == 6 || log2rest == 11 || log2rest == 12; }
 int be_launch_conv_mid(int log2rest, const ConvMidParams &m, u64 ntiles, void *stream)
 {

@@ -75,7 +75,7 @@ NRB_DEV void mid_gather(const double2 *E, int tid, double2 *v)
 
 // stages S .. NST-1 on registers with the exchanges between them; leaves the last stage's outputs in v
 template <class G, int S> struct ChainM {
-    NRB_DEVM static void run(const ConvMidParams &M, double2 *E, int tid, double2 *v)
+    template <class PP> NRB_DEVM static void run(const PP &M, double2 *E, int tid, double2 *v)
     {
         v2_compute<G, S>(M, tid, v);
         if (S + 1 < G::NST) {
@@ -88,7 +88,7 @@ template <class G, int S> struct ChainM {
     }
 };
 template <class G> struct ChainM<G, -1> {
-    NRB_DEVM static void run(const ConvMidParams &, double2 *, int, double2 *) {}
+    template <class PP> NRB_DEVM static void run(const PP &, double2 *, int, double2 *) {}
 };
 
 template <int LOG2R>

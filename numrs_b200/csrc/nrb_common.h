@@ -341,4 +341,25 @@ struct ConvMidParams {
                                  // nothing else to overlap its serial load / transform / store phases with
 };
 
+// ---- cosft1 / cosft2 / sinft and twofft in one kernel for lines that fit on chip (trig_fused.cuh) ----
+// complex points per line: 8 .. 4096 (real lines of 16 .. 8192 points; twofft lines of 8 .. 4096 points)
+constexpr int kTrigMinLog2 = 3, kTrigMaxLog2 = 12;
+struct TrigParams {
+    double *io;                      // lines of the reference's 1-based arrays (element 0 of a line unused), transformed in place
+    i64 ld;                          // doubles per line
+    u64 count;                       // lines
+    int mode;                        // COS1, COS2F, SINFT (forward) or COS2I_PRE (= the whole inverse cosft2)
+    const double2 *tw;               // stage twiddles of the N = n/2 point transform
+    const double2 *rtw;              // exp(-i pi k / N), k < N (realft untangling)
+    const double2 *ctw_lo, *ctw_hi;  // exp(-2 pi i m / M), two-level: M = 2n (cosft1, sinft) or 4n (cosft2)
+    int ctw_h;
+};
+
+struct TwoFFTParams {
+    const double *d1, *d2;           // [count][n] real signals
+    double2 *f1, *f2;                // [count][n + 1] complex spectra (element n: the reference's two extra doubles, set to 0)
+    u64 count;
+    const double2 *tw;               // stage twiddles of the n-point transform
+};
+
 } // namespace nrb

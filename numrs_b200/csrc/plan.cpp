@@ -70,6 +70,7 @@ static Tunables &tunables_mut()
         x.shard_min_kb = env_int("NRB_SHARD_MIN_KB", 16384);
         x.pipeline_batches = env_int("NRB_PIPELINE_BATCHES", 1);
         x.pipeline_min_kb = env_int("NRB_PIPELINE_MIN_KB", 16384);
+        x.trig_fused = env_int("NRB_TRIG_FUSED", 1);
         return x;
     }();
     if (t.col_max_log2 < 1) t.col_max_log2 = 1;
@@ -115,6 +116,7 @@ int set_tunable(const char *name, long value)
     else if (n == "pipeline_batches") t.pipeline_batches = value != 0;
     else if (n == "pipeline_min_kb") t.pipeline_min_kb = value < 1 ? 1 : (int)value;
     else if (n == "shard_min_kb") t.shard_min_kb = value < 0 ? 0 : (int)value;
+    else if (n == "trig_fused") t.trig_fused = value != 0;
     else return -1;
     tunables_mut();   // re-clamp
     return 0;
@@ -897,6 +899,18 @@ int build_twofft(Plan &pl, Builder &B)
     const u64 n = pl.dims[0], per = n + 1;
     const BufRef F1(BUF_OUT, 0), F2(BUF_OUT, (i64)(pl.batch * per));
     const int p = ilog2((size_t)n);
+    if (tunables().trig_fused && be_trig_available(p)) {        // pack, four1 and separation in one kernel (trig_fused.cuh)
+        Step st;
+        st.trig = 2;
+        st.key = KernelKey{p, LAYOUT_ROW, +1, VAR_PLAIN};
+        memset(&st.fp, 0, sizeof(st.fp));
+        st.fp.count = pl.batch;
+        st.fp.tw = stage_twiddles(p);
+        st.in = BufRef(BUF_IO, 0); st.b = BufRef(BUF_AUX, 0); st.out = F1; st.speq = F2;
+        st.ntiles = pl.batch;
+        B.prog->steps.push_back(st);
+        return B.rc;
+    }
     // short lines: transform in place in fft1 (lines n + 1 complex apart); multi-step transforms need densely
     // packed lines and go through the workspace
     const bool dense = p > tunables().row_max_log2;
@@ -926,6 +940,21 @@ int build_cosft(Plan &pl, Builder &B, int kind, int dir)
     const i64 ld = (i64)(kind == NRB_KIND_COSFT1 ? n + 2 : n + 1);
     const int mode = kind == NRB_KIND_COSFT1 ? COS1 : kind == NRB_KIND_SINFT ? SINFT : COS2F;
     const bool inverse = kind == NRB_KIND_COSFT2 && dir < 0;
+    if (tunables().trig_fused && n >= 2 && be_trig_available(p)) {   // the whole routine in one kernel (trig_fused.cuh)
+        Step st;
+        st.trig = 1;
+        st.key = KernelKey{p, LAYOUT_ROW, dir, VAR_REAL};
+        memset(&st.tp, 0, sizeof(st.tp));
+        st.tp.ld = ld; st.tp.count = L; st.tp.mode = inverse ? COS2I_PRE : mode;
+        st.tp.tw = stage_twiddles(p);
+        st.tp.rtw = real_twiddles(p);
+        const FourStepTable ct = fourstep_table(ilog2((size_t)n) + (kind == NRB_KIND_COSFT2 ? 2 : 1));
+        st.tp.ctw_lo = ct.lo; st.tp.ctw_hi = ct.hi; st.tp.ctw_h = ct.h;
+        st.in = BufRef(BUF_IO, 0);
+        st.ntiles = L;
+        B.prog->steps.push_back(st);
+        return B.rc;
+    }
     const u64 C = N + 1 < 16384 ? N + 1 : 16384;        // pre-pass accumulators per line
     const u64 C1 = C > 256 ? 128 : 0;
     const u64 K = (u64)kScanChunk, nch = (N + K - 1) / K;   // running sum: positions per chunk (one CTA each)
@@ -1058,7 +1087,7 @@ int build_plan(Plan &pl, int kind, const size_t *dims, size_t ndim, size_t batch
         }
         if (rc != NRB_OK) { set_error("shape not supported by this build"); return rc; }
         for (const Step &st : pl.prog[s].steps) {
-            if (!st.is_aux && (!(st.is_mid ? st.mp.tw : st.pp.tw) && radix_plan(st.key.log2n).nst > 1)) { set_error(std::string("twiddle table allocation failed: ") + be_last_error()); return NRB_ERR_CUDA; }
+            if (!st.is_aux && (!(st.trig == 1 ? st.tp.tw : st.trig == 2 ? st.fp.tw : st.is_mid ? st.mp.tw : st.pp.tw) && radix_plan(st.key.log2n).nst > 1)) { set_error(std::string("twiddle table allocation failed: ") + be_last_error()); return NRB_ERR_CUDA; }
         }
         if (B.ws_used > ws) ws = B.ws_used;
         if (B.sched_used > pl.sched_bytes) pl.sched_bytes = B.sched_used;
@@ -1144,6 +1173,17 @@ static int run_program(Program &prog, double2 *const base[4], int arg, void *mai
             fs.ticket = (unsigned long long *)((char *)sched + st.sched_off);
             fs.done = (unsigned *)((char *)sched + st.sched_off + 16);
             rc = be_launch_fused(st.key, pa, st.key2, pb, fs, stream);
+        } else if (st.trig == 1) {
+            TrigParams tp = st.tp;
+            tp.io = reinterpret_cast<double *>(base[st.in.id] + st.in.off);
+            rc = be_launch_trig(st.key.log2n, tp, stream);
+        } else if (st.trig == 2) {
+            TwoFFTParams fp = st.fp;
+            fp.d1 = reinterpret_cast<const double *>(base[st.in.id] + st.in.off);
+            fp.d2 = reinterpret_cast<const double *>(base[st.b.id] + st.b.off);
+            fp.f1 = base[st.out.id] + st.out.off;
+            fp.f2 = base[st.speq.id] + st.speq.off;
+            rc = be_launch_twofft(st.key.log2n, fp, stream);
         } else if (st.is_mid) {
             ConvMidParams mp = st.mp;
             mp.prefetch_dist = tunables().prefetch_dist >= 0 ? tunables().prefetch_dist : tunables().mid_prefetch;
@@ -1253,6 +1293,15 @@ int describe_launch(const Plan &pl, int isign, int idx, char *name, size_t cap, 
         // the pair reads the volume once and writes it once (the intermediate stays in L2)
         const double vol = (double)st.fs.units * (double)st.fs.ta * (double)(1 << tile_log2(st.key.log2n, st.key.layout));
         b = 2.0 * 16.0 * vol + 16.0 * (double)(st.key.layout == LAYOUT_ROW ? st.pp.q_end - st.pp.q_begin : st.pp2.q_end - st.pp2.q_begin);
+    } else if (st.trig == 1) {
+        static const char *tn[] = {"cosft1", "cosft2", "sinft", "cosft2_inv", "?"};
+        const double n = (double)(2 << st.key.log2n);
+        snprintf(buf, sizeof(buf), "trig_%s_n%d_L%llu", tn[st.tp.mode >= 0 && st.tp.mode <= 3 ? st.tp.mode : 4], 2 << st.key.log2n, (unsigned long long)st.tp.count);
+        b = 2.0 * 8.0 * (double)st.tp.count * (st.tp.mode == COS1 ? n + 1.0 : n);      // every real read once and written once
+    } else if (st.trig == 2) {
+        const double n = (double)(1 << st.key.log2n);
+        snprintf(buf, sizeof(buf), "trig_twofft_n%d_L%llu", 1 << st.key.log2n, (unsigned long long)st.fp.count);
+        b = (double)st.fp.count * (16.0 * n + 32.0 * (n + 1.0));                         // two real lines in, two spectra out
     } else if (st.is_mid) {
         snprintf(buf, sizeof(buf), "conv_mid_n%d_f%d_op%d", 1 << st.key.log2n, st.mp.f, st.mp.op);
         const double pts = (double)st.mp.count * (double)((u64)1 << (st.key.log2n + st.mp.f));

@@ -22,6 +22,10 @@ int be_launch_fused(const KernelKey &ka, const PassParams &pa, const KernelKey &
 // fused middle of the long-line convlv / correl pipeline (rows of 2^log2rest points); available for the built lengths
 bool be_conv_mid_available(int log2rest);
 int be_launch_conv_mid(int log2rest, const ConvMidParams &m, u64 ntiles, void *stream);
+// cosft1 / cosft2 / sinft and twofft in one kernel (trig_fused.cuh): lines of 2^log2n complex points, kTrigMinLog2 <= log2n <= kTrigMaxLog2
+bool be_trig_available(int log2n);
+int be_launch_trig(int log2n, const TrigParams &t, void *stream);
+int be_launch_twofft(int log2n, const TwoFFTParams &t, void *stream);
 int be_malloc(void **p, size_t bytes);
 int be_free(void *p);
 int be_memset(void *p, int value, size_t bytes, void *stream);
@@ -77,6 +81,10 @@ struct Step {
     bool patch_pad_mode;   // AUX_PAD_RESPONSE: op comes from exec's `arg`
     bool is_mid;           // fused conv middle: mp, in = data (in place), b = second operand; key.log2n = log2 REST
     ConvMidParams mp;
+    int trig;              // 1: one-kernel cosft1 / cosft2 / sinft (tp, in = io); 2: one-kernel twofft (fp, in = data1, b = data2,
+                           // out = fft1, speq = fft2); key.log2n = log2 of the complex points per line
+    TrigParams tp;
+    TwoFFTParams fp;
     bool join_side;        // the side lane must have finished before this (lane 0) step starts
     bool side_after_main;  // this lane-1 step must not start before what the caller's stream holds so far
     bool zsplit;           // slab exchange data pass: its lines' low bits are the z index, so the push + pull split applies
@@ -88,7 +96,7 @@ struct Step {
     BufRef in2, out2, speq2;
     FuseSched fs;          // counters live in the plan's scheduler scratch (sched_off = element offset)
     size_t sched_off;
-    Step() : is_aux(false), key{0, 0, 0, 0}, pp(), ap(), ntiles(0), patch_pad_mode(false), is_mid(false), mp(), join_side(false), side_after_main(false), zsplit(false), lane(0), is_fused(false),
+    Step() : is_aux(false), key{0, 0, 0, 0}, pp(), ap(), ntiles(0), patch_pad_mode(false), is_mid(false), mp(), trig(0), tp(), fp(), join_side(false), side_after_main(false), zsplit(false), lane(0), is_fused(false),
              key2{0, 0, 0, 0}, pp2(), fs{nullptr, nullptr, 0, 0, 0, 0}, sched_off(0) {}
 };
 
@@ -154,6 +162,8 @@ struct Tunables {
                            // (NRB_PIPELINE_BATCHES)
     int pipeline_min_kb;   // smallest chunk of a pipelined batch call (NRB_PIPELINE_MIN_KB, default 16 MiB; calls under 4 chunks stay one shot)
     int shard_min_kb;      // batches smaller than this stay on one device (NRB_SHARD_MIN_KB, default 16 MiB)
+    int trig_fused;        // cosft1 / cosft2 / sinft of 16 .. 8192 points and twofft of 8 .. 4096 points per line: the whole routine in
+                           // one kernel, one HBM pass (trig_fused.cuh) instead of 5-7 launches (NRB_TRIG_FUSED, default 1)
 };
 const Tunables &tunables();
 int set_tunable(const char *name, long value);   // returns 0 if the name is known

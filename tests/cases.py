@@ -237,3 +237,69 @@ def check_device_resident_chain(L, shape=(8, 16, 8), seed=1017):
         s.reshape(-1)[0::2], s.reshape(-1)[1::2] = sz.real, sz.imag
         O.rlft3(d, s, -1)
     assert rel(got, d) <= tol(n), rel(got, d)
+
+
+def _plan_run(L, kind, n, cnt, io, aux=None, out_count=0, isign=1):
+    """Device-resident plan call on `cnt` batched lines; returns (io after, out, launches)."""
+    from numrs_b200.device import DeviceArray
+    plan = L.plan_create(kind, [n], batch=cnt)
+    launches = plan.num_launches(isign)
+    d_io = DeviceArray.from_host(L, io)
+    d_aux = DeviceArray.from_host(L, aux) if aux is not None else None
+    d_out = DeviceArray(L, out_count) if out_count else None
+    plan.exec(d_io.ptr, d_aux.ptr if d_aux else 0, d_out.ptr if d_out else 0, isign=isign)
+    got_io = d_io.to_host()
+    got_out = d_out.to_host() if d_out else None
+    for d in (d_io, d_aux, d_out):
+        if d is not None:
+            d.free()
+    plan.destroy()
+    return got_io, got_out, launches
+
+
+def check_trig_batch(L, n, cnt, seed=1040):
+    """cosft1 / cosft2 (both signs) / sinft on `cnt` batched lines of the reference's 1-based arrays through the plan API:
+    the one-kernel path (trig_fused.cuh) against the oracle line by line and against the multi-launch path; element 0 of
+    every line (unused by the reference) must stay untouched.  cnt lines of odd length put the lines on alternating
+    16-byte alignments."""
+    routines = ((nb.KIND_COSFT1, n + 2, 1, lambda y: O.cosft1(y, n)),
+                (nb.KIND_COSFT2, n + 1, 1, lambda y: O.cosft2(y, n, 1)[1]),
+                (nb.KIND_COSFT2, n + 1, -1, lambda y: O.cosft2(y, n, -1)[1]),
+                (nb.KIND_SINFT, n + 1, 1, lambda y: O.sinft(y, n)))
+    for kind, ld, isign, ref_fn in routines:
+        y = gen(seed + kind, cnt * ld)
+        y[0::ld] = 123.0 + np.arange(cnt)
+        L.set_option("trig_fused", 1)
+        got, _, launches = _plan_run(L, kind, n, cnt, y, isign=isign)
+        assert launches == 1, (kind, n, launches)
+        L.set_option("trig_fused", 0)
+        old, _, launches0 = _plan_run(L, kind, n, cnt, y, isign=isign)
+        L.set_option("trig_fused", 1)
+        assert launches0 > 1
+        for i in range(cnt):
+            ref = ref_fn(y[i * ld:(i + 1) * ld].copy())
+            nd = n + 1 if kind == nb.KIND_COSFT1 else n
+            g = got[i * ld:(i + 1) * ld]
+            assert g[0] == y[i * ld], (kind, n, i)
+            assert rel(g[1:1 + nd], ref[1:1 + nd]) <= tol(n), (kind, isign, n, i, rel(g[1:1 + nd], ref[1:1 + nd]))
+            assert rel(g[1:1 + nd], old[i * ld + 1:i * ld + 1 + nd]) <= 1e-13, (kind, isign, n, i)
+            if ld > nd + 1:                                   # cosft1's line has no tail; keep the check generic
+                assert np.array_equal(g[1 + nd:], y[i * ld + 1 + nd:(i + 1) * ld])
+
+
+def check_twofft_plan(L, n, cnt, seed=1050):
+    """twofft on `cnt` batched signal pairs through the plan API: one-kernel path against the oracle and the three-launch path."""
+    a, b = gen(seed, n * cnt) + 0.25, gen(seed + 1, n * cnt)
+    per = 2 * n + 2
+    res = {}
+    for flag in (1, 0):
+        L.set_option("trig_fused", flag)
+        _, f, launches = _plan_run(L, nb.KIND_TWOFFT, n, cnt, a, aux=b, out_count=2 * cnt * per)
+        assert (launches == 1) == (flag == 1), (n, flag, launches)
+        res[flag] = f
+    L.set_option("trig_fused", 1)
+    for i in range(cnt):
+        r1, r2 = O.twofft(a[i * n:(i + 1) * n], b[i * n:(i + 1) * n])
+        assert rel(res[1][i * per:(i + 1) * per], r1) <= tol(n), (n, i)
+        assert rel(res[1][(cnt + i) * per:(cnt + i + 1) * per], r2) <= tol(n), (n, i)
+    assert rel(res[1], res[0]) <= 1e-14

@@ -64,3 +64,4 @@ def _reset_options(request):
             L.set_option("tma_xpose", 1)
             L.set_option("tma_in_mask", 0)
             L.set_option("tma_in_ctas", 2)
+            L.set_option("trig_fused", 1)

@@ -19,6 +19,7 @@
 #include "../../numrs_b200/csrc/aux_kernels.cuh"
 #include "../../numrs_b200/csrc/fft_pass2.cuh"
 #include "../../numrs_b200/csrc/conv_mid.cuh"
+#include "../../numrs_b200/csrc/trig_fused.cuh"
 #include "../../numrs_b200/csrc/plan.h"
 
 namespace nrb_emu {
@@ -264,6 +265,64 @@ int be_launch_conv_mid(int log2rest, const ConvMidParams &m, u64 ntiles, void *)
     return 0;
 }
 
+// one-kernel cosft1 / cosft2 / sinft and twofft (trig_fused.cuh): same set of lengths as k_trig.cu
+template <int LOG2N> static void trig_body(const void *p, double2 *sm, unsigned tile, int tid)
+{
+    trig_cta<LOG2N>(*(const TrigParams *)p, sm, tile, tid);
+}
+template <int LOG2N> static void twofft_body(const void *p, double2 *sm, unsigned tile, int tid)
+{
+    twofft_cta<LOG2N>(*(const TwoFFTParams *)p, sm, tile, tid);
+}
+bool be_trig_available(int log2n) { return log2n >= kTrigMinLog2 && log2n <= kTrigMaxLog2; }
+static long g_trig_launches = 0;
+template <int LOG2N> static void trig_geo(bool two, nrb_emu::BodyFn &fn, int &nt, size_t &smem, int &lines)
+{
+    fn = two ? twofft_body<LOG2N> : trig_body<LOG2N>;
+    nt = GeoT<LOG2N>::NT; smem = (GeoT<LOG2N>::SMEM_BYTES + 15) / 16; lines = GeoT<LOG2N>::L;
+}
+static int emu_launch_trig(int log2n, bool two, const void *params, u64 count)
+{
+    nrb_emu::BodyFn fn = nullptr;
+    int nt = 0, lines = 1;
+    size_t smem = 0;
+    switch (log2n) {
+    case 3: trig_geo<3>(two, fn, nt, smem, lines); break;
+    case 4: trig_geo<4>(two, fn, nt, smem, lines); break;
+    case 5: trig_geo<5>(two, fn, nt, smem, lines); break;
+    case 6: trig_geo<6>(two, fn, nt, smem, lines); break;
+    case 7: trig_geo<7>(two, fn, nt, smem, lines); break;
+    case 8: trig_geo<8>(two, fn, nt, smem, lines); break;
+    case 9: trig_geo<9>(two, fn, nt, smem, lines); break;
+    case 10: trig_geo<10>(two, fn, nt, smem, lines); break;
+    case 11: trig_geo<11>(two, fn, nt, smem, lines); break;
+    case 12: trig_geo<12>(two, fn, nt, smem, lines); break;
+    default: g_emu_err = "trig kernel not built for this line length"; return -1;
+    }
+    ++g_trig_launches;
+    const long long ntiles = (long long)((count + (u64)lines - 1) / (u64)lines);
+#pragma omp parallel
+    {
+        nrb_emu::Cta c;
+        c.fibers.resize(nt);
+        c.stacks.resize((size_t)nt * nrb_emu::kStack);
+        c.done.resize(nt);
+        std::vector<double> shfl_buf(nt + 32, 0.0);
+        nrb_emu::t_shfl = &shfl_buf;
+        c.body = fn;
+        c.params = params;
+#pragma omp for schedule(dynamic)
+        for (long long t = 0; t < ntiles; ++t) {
+            c.tile = (unsigned)t;
+            c.smem.assign(smem, make_double2(__builtin_nan(""), __builtin_nan("")));
+            nrb_emu::run_cta(c, nt);
+        }
+    }
+    return 0;
+}
+int be_launch_trig(int log2n, const TrigParams &t, void *) { return emu_launch_trig(log2n, false, &t, t.count); }
+int be_launch_twofft(int log2n, const TwoFFTParams &t, void *) { return emu_launch_trig(log2n, true, &t, t.count); }
+
 bool be_fused_available(const KernelKey &a, const KernelKey &b)
 {
     // same set as the CUDA build (k_fused_*.cu): z in {128,256,512} (ROW REAL), y in {256,512,1024} (COL PLAIN)
@@ -363,4 +422,4 @@ void be_host_free(void *p) { free(p); }
 
 } // namespace nrb
 
-extern "C" long nrb_emu_launch_count(int aux) { return aux == 4 ? nrb::g_mid_launches : aux == 3 ? nrb::g_simple_launches : aux == 2 ? nrb::g_big_launches : aux ? nrb::g_aux_launches : nrb::g_pass_launches; }
+extern "C" long nrb_emu_launch_count(int aux) { return aux == 5 ? nrb::g_trig_launches : aux == 4 ? nrb::g_mid_launches : aux == 3 ? nrb::g_simple_launches : aux == 2 ? nrb::g_big_launches : aux ? nrb::g_aux_launches : nrb::g_pass_launches; }

@@ -406,6 +406,45 @@ def test_cosft_long_line_path_batch_and_errors(emu):
         assert cases.rel(y[i * (n + 1) + 1:(i + 1) * (n + 1)], refs[i][1:]) <= cases.tol(n)
 
 
+# one-kernel cosft1 / cosft2 / sinft and twofft (trig_fused.cuh): every built line length, ragged last tiles, lines on
+# both 16-byte alignments, against the oracle and against the multi-launch path
+@pytest.mark.parametrize("n,cnt", [(16, 300), (32, 17), (64, 40), (128, 33), (256, 9), (512, 5), (1024, 5), (2048, 3), (4096, 3),
+                                   (8192, 2)])
+def test_trig_fused_one_kernel(emu, n, cnt):
+    before = _emu_count(emu, 5)
+    cases.check_trig_batch(emu, n, cnt)
+    assert _emu_count(emu, 5) == before + 4          # cosft1, cosft2 (+1 / -1), sinft: one launch each
+
+
+@pytest.mark.parametrize("n,cnt", [(8, 300), (16, 130), (32, 70), (64, 33), (128, 17), (256, 9), (512, 5), (1024, 3), (2048, 2),
+                                   (4096, 2)])
+def test_twofft_fused_one_kernel(emu, n, cnt):
+    before = _emu_count(emu, 5)
+    cases.check_twofft_plan(emu, n, cnt)
+    assert _emu_count(emu, 5) == before + 1
+
+
+def test_trig_fused_limits_and_unaligned_signals(emu):
+    # lines the one-kernel path is not built for keep the multi-launch programs
+    for kind, n in ((nb.KIND_COSFT1, 8), (nb.KIND_COSFT1, 1 << 14), (nb.KIND_TWOFFT, 4), (nb.KIND_TWOFFT, 8192)):
+        plan = emu.plan_create(kind, [n], batch=2)
+        assert plan.num_launches(1) > 1
+        plan.destroy()
+    # twofft on signals that are only 8-byte aligned (plan API, caller's pointers)
+    n, cnt = 64, 3
+    a, b = O.fill_uniform(41, 0, n * cnt + 1)[1:], O.fill_uniform(42, 0, n * cnt + 1)[1:]
+    f = np.zeros(2 * cnt * (2 * n + 2))
+    plan = emu.plan_create(nb.KIND_TWOFFT, [n], batch=cnt)
+    assert plan.num_launches(1) == 1
+    plan.exec(a.ctypes.data, b.ctypes.data, f.ctypes.data)
+    plan.destroy()
+    per = 2 * n + 2
+    for i in range(cnt):
+        r1, r2 = O.twofft(a[i * n:(i + 1) * n], b[i * n:(i + 1) * n])
+        assert cases.rel(f[i * per:(i + 1) * per], r1) <= cases.tol(n)
+        assert cases.rel(f[(cnt + i) * per:(cnt + i + 1) * per], r2) <= cases.tol(n)
+
+
 def test_device_resident_chain(emu):
     """SURVEY.md 8f N1 (under emulation 'device' memory is host memory)."""
     cases.check_device_resident_chain(emu)
