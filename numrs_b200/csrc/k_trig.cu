@@ -1,4 +1,4 @@
-// k_trig.cu -- the one-kernel cosft1 / cosft2 / sinft and twofft of trig_fused.cuh, built for 8 .. 4096 complex points per line
+// k_trig.cu -- the one-kernel cosft1 / cosft2 / sinft and twofft of trig_fused.cuh, built for 8 .. 8192 complex points per line
 #include <cuda_runtime.h>
 
 #include "trig_fused.cuh"
@@ -7,14 +7,14 @@
 namespace nrb {
 
 template <int LOG2N>
-__global__ void __launch_bounds__(GeoT<LOG2N>::NT, (LOG2N <= kTrigTileLog2 ? 4 : 2)) trig_kernel(const __grid_constant__ TrigParams T)
+__global__ void __launch_bounds__(GeoT<LOG2N>::NT, (LOG2N <= kTrigTileLog2 ? 4 : LOG2N == 12 ? 2 : 1)) trig_kernel(const __grid_constant__ TrigParams T)
 {
     extern __shared__ double2 nrb_trig_smem[];
     trig_cta<LOG2N>(T, nrb_trig_smem, blockIdx.x, (int)threadIdx.x);
 }
 
 template <int LOG2N>
-__global__ void __launch_bounds__(GeoT<LOG2N>::NT, (LOG2N <= kTrigTileLog2 ? 4 : 2)) twofft_kernel(const __grid_constant__ TwoFFTParams T)
+__global__ void __launch_bounds__(GeoT<LOG2N>::NT, (LOG2N <= kTrigTileLog2 ? 4 : LOG2N == 12 ? 2 : 1)) twofft_kernel(const __grid_constant__ TwoFFTParams T)
 {
     extern __shared__ double2 nrb_trig_smem[];
     twofft_cta<LOG2N>(T, nrb_trig_smem, blockIdx.x, (int)threadIdx.x);
@@ -68,6 +68,7 @@ template <int LOG2N> static int launch_twofft_n(const TwoFFTParams &t, cudaStrea
     case 10: return F<10>(arg, s);                                                                                     \
     case 11: return F<11>(arg, s);                                                                                     \
     case 12: return F<12>(arg, s);                                                                                     \
+    case 13: return F<13>(arg, s);                                                                                     \
     default: return (int)cudaErrorInvalidValue;                                                                        \
     }
 

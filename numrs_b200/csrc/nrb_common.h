@@ -342,8 +342,8 @@ struct ConvMidParams {
 };
 
 // ---- cosft1 / cosft2 / sinft and twofft in one kernel for lines that fit on chip (trig_fused.cuh) ----
-// complex points per line: 8 .. 4096 (real lines of 16 .. 8192 points; twofft lines of 8 .. 4096 points)
-constexpr int kTrigMinLog2 = 3, kTrigMaxLog2 = 12;
+// complex points per line: 8 .. 8192 (real lines of 16 .. 16384 points; twofft lines of 8 .. 8192 points)
+constexpr int kTrigMinLog2 = 3, kTrigMaxLog2 = 13;
 struct TrigParams {
     double *io;                      // lines of the reference's 1-based arrays (element 0 of a line unused), transformed in place
     i64 ld;                          // doubles per line

@@ -899,7 +899,7 @@ int build_twofft(Plan &pl, Builder &B)
     const u64 n = pl.dims[0], per = n + 1;
     const BufRef F1(BUF_OUT, 0), F2(BUF_OUT, (i64)(pl.batch * per));
     const int p = ilog2((size_t)n);
-    if (tunables().trig_fused && be_trig_available(p)) {        // pack, four1 and separation in one kernel (trig_fused.cuh)
+    if (tunables().trig_fused && p <= tunables().row_max_log2 && be_trig_available(p)) {   // pack, four1 and separation in one kernel (trig_fused.cuh)
         Step st;
         st.trig = 2;
         st.key = KernelKey{p, LAYOUT_ROW, +1, VAR_PLAIN};
@@ -940,7 +940,7 @@ int build_cosft(Plan &pl, Builder &B, int kind, int dir)
     const i64 ld = (i64)(kind == NRB_KIND_COSFT1 ? n + 2 : n + 1);
     const int mode = kind == NRB_KIND_COSFT1 ? COS1 : kind == NRB_KIND_SINFT ? SINFT : COS2F;
     const bool inverse = kind == NRB_KIND_COSFT2 && dir < 0;
-    if (tunables().trig_fused && n >= 2 && be_trig_available(p)) {   // the whole routine in one kernel (trig_fused.cuh)
+    if (tunables().trig_fused && p <= tunables().row_max_log2 && be_trig_available(p)) {   // the whole routine in one kernel (trig_fused.cuh)
         Step st;
         st.trig = 1;
         st.key = KernelKey{p, LAYOUT_ROW, dir, VAR_REAL};

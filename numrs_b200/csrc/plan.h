@@ -162,7 +162,7 @@ struct Tunables {
                            // (NRB_PIPELINE_BATCHES)
     int pipeline_min_kb;   // smallest chunk of a pipelined batch call (NRB_PIPELINE_MIN_KB, default 16 MiB; calls under 4 chunks stay one shot)
     int shard_min_kb;      // batches smaller than this stay on one device (NRB_SHARD_MIN_KB, default 16 MiB)
-    int trig_fused;        // cosft1 / cosft2 / sinft of 16 .. 8192 points and twofft of 8 .. 4096 points per line: the whole routine in
+    int trig_fused;        // cosft1 / cosft2 / sinft of 16 .. 16384 points and twofft of 8 .. 8192 points per line: the whole routine in
                            // one kernel, one HBM pass (trig_fused.cuh) instead of 5-7 launches (NRB_TRIG_FUSED, default 1)
 };
 const Tunables &tunables();

@@ -4,7 +4,7 @@
 // README.md:72; oracle ledger D11), twofft is a packing step, four1 and a separation step (FFT_2.rs:3-90, ledger D9).
 // As separate launches that is 5-7 sweeps over HBM per call (aux_cosft, aux_reduce, the ROW-REAL pass, three scan
 // phases; aux_pack2, the pass, aux_twofft_split): 0.10-0.15 (0.33 for twofft) of the measured copy bandwidth
-// (profiles/r02_kernel_table_next.txt).  Here a CTA owns L whole lines (2048 complex points per tile, or one line) and
+// (profiles/r02_kernel_table_next.txt).  Here a CTA owns L whole lines (2048 complex points per tile, or one line of up to 8192) and
 // does every step while the lines are in shared memory:
 //
 //   cosft1 / cosft2 forward / sinft:  load the line with aligned 16-byte accesses (the reference's arrays are 1-based,

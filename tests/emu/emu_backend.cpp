@@ -297,6 +297,7 @@ static int emu_launch_trig(int log2n, bool two, const void *params, u64 count)
     case 10: trig_geo<10>(two, fn, nt, smem, lines); break;
     case 11: trig_geo<11>(two, fn, nt, smem, lines); break;
     case 12: trig_geo<12>(two, fn, nt, smem, lines); break;
+    case 13: trig_geo<13>(two, fn, nt, smem, lines); break;
     default: g_emu_err = "trig kernel not built for this line length"; return -1;
     }
     ++g_trig_launches;

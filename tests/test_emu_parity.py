@@ -409,7 +409,7 @@ def test_cosft_long_line_path_batch_and_errors(emu):
 # one-kernel cosft1 / cosft2 / sinft and twofft (trig_fused.cuh): every built line length, ragged last tiles, lines on
 # both 16-byte alignments, against the oracle and against the multi-launch path
 @pytest.mark.parametrize("n,cnt", [(16, 300), (32, 17), (64, 40), (128, 33), (256, 9), (512, 5), (1024, 5), (2048, 3), (4096, 3),
-                                   (8192, 2)])
+                                   (8192, 2), (16384, 2)])
 def test_trig_fused_one_kernel(emu, n, cnt):
     before = _emu_count(emu, 5)
     cases.check_trig_batch(emu, n, cnt)
@@ -417,7 +417,7 @@ def test_trig_fused_one_kernel(emu, n, cnt):
 
 
 @pytest.mark.parametrize("n,cnt", [(8, 300), (16, 130), (32, 70), (64, 33), (128, 17), (256, 9), (512, 5), (1024, 3), (2048, 2),
-                                   (4096, 2)])
+                                   (4096, 2), (8192, 2)])
 def test_twofft_fused_one_kernel(emu, n, cnt):
     before = _emu_count(emu, 5)
     cases.check_twofft_plan(emu, n, cnt)
@@ -426,7 +426,7 @@ def test_twofft_fused_one_kernel(emu, n, cnt):
 
 def test_trig_fused_limits_and_unaligned_signals(emu):
     # lines the one-kernel path is not built for keep the multi-launch programs
-    for kind, n in ((nb.KIND_COSFT1, 8), (nb.KIND_COSFT1, 1 << 14), (nb.KIND_TWOFFT, 4), (nb.KIND_TWOFFT, 8192)):
+    for kind, n in ((nb.KIND_COSFT1, 8), (nb.KIND_COSFT1, 1 << 15), (nb.KIND_TWOFFT, 4), (nb.KIND_TWOFFT, 1 << 14)):
         plan = emu.plan_create(kind, [n], batch=2)
         assert plan.num_launches(1) > 1
         plan.destroy()

@@ -183,12 +183,12 @@ def test_cosft_sinft(gpu, n):
 # oracle line by line, against the multi-launch path, element 0 of every line untouched; ragged last tiles, both alignments,
 # and batches of several waves of CTAs
 @pytest.mark.parametrize("n,cnt", [(16, 300), (32, 2049), (64, 1000), (128, 517), (256, 129), (512, 600), (1024, 37), (2048, 301),
-                                   (4096, 600), (8192, 297)])
+                                   (4096, 600), (8192, 297), (16384, 149)])
 def test_trig_fused_one_kernel(gpu, n, cnt):
     cases.check_trig_batch(gpu, n, cnt)
 
 
-@pytest.mark.parametrize("n,cnt", [(8, 300), (16, 4097), (64, 1000), (256, 129), (512, 600), (1024, 37), (2048, 301), (4096, 600)])
+@pytest.mark.parametrize("n,cnt", [(8, 300), (16, 4097), (64, 1000), (256, 129), (512, 600), (1024, 37), (2048, 301), (4096, 600), (8192, 149)])
 def test_twofft_fused_one_kernel(gpu, n, cnt):
     cases.check_twofft_plan(gpu, n, cnt)
 

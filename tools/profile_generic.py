@@ -32,5 +32,21 @@ elif wl.startswith("convlv_"):
     plan = lib.plan_create(nb.KIND_CONVLV, [n, m], batch=cnt)
     for _ in range(2):
         plan.exec(a.data_ptr(), aux.data_ptr(), o.data_ptr(), isign=1, stream=st)
+elif wl.split("_")[0] in ("cosft1", "cosft2", "sinft", "twofft"):
+    kind, lg, cnt = wl.split("_")
+    n, cnt = 1 << int(lg), int(cnt)
+    a = torch.empty((n + 2) * cnt, **f64)
+    b = torch.empty(n * cnt, **f64)
+    lib.fill_uniform_device(a.data_ptr(), 1010, 0, a.numel(), st)
+    lib.fill_uniform_device(b.data_ptr(), 1011, 0, b.numel(), st)
+    if kind == "twofft":
+        o = torch.empty(2 * (2 * n + 2) * cnt, **f64)
+        plan = lib.plan_create(nb.KIND_TWOFFT, [n], batch=cnt)
+        for _ in range(2):
+            plan.exec(a.data_ptr(), b.data_ptr(), o.data_ptr(), isign=1, stream=st)
+    else:
+        plan = lib.plan_create({"cosft1": nb.KIND_COSFT1, "cosft2": nb.KIND_COSFT2, "sinft": nb.KIND_SINFT}[kind], [n], batch=cnt)
+        for _ in range(2):
+            plan.exec(a.data_ptr(), isign=1, stream=st)
 torch.cuda.synchronize()
 print("launches:", plan.num_launches(1))
