@@ -91,6 +91,9 @@ int  nrb_shutdown(void);               /* frees cached plans, twiddle tables no 
  *                       inverse pass of a row pair in ONE kernel, 5 -> 3 passes per signal (default 1)
  *   "speq_side"         rlft3: the four small speq-plane launches run on a second stream beside the data passes
  *                       (default 1)
+ *   "trig_fused"        1 (default): cosft1 / cosft2 / sinft of 16 .. 16384 points and twofft of 8 .. 8192 points per line run
+ *                       as ONE kernel and one HBM pass (pre-processing, realft, running sums / packing, four1, separation
+ *                       all on chip); 0 = the multi-launch programs (A/B, tests)
  *   "big_row_mask" / "big_col_mask"  bit log2(n) set: lines of n points use the big-tile prefetching pass (default 0:
  *                       measured no faster, kept as an experiment)
  * Environment overrides at load time: NRB_COL_MAX_LOG2, NRB_ROW_MAX_LOG2, NRB_L2_GROUP_MB, NRB_BATCH_GROUP_MB,

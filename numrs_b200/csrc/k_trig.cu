@@ -7,14 +7,14 @@
 namespace nrb {
 
 template <int LOG2N>
-__global__ void __launch_bounds__(GeoT<LOG2N>::NT, (LOG2N <= kTrigTileLog2 ? 4 : LOG2N == 12 ? 2 : 1)) trig_kernel(const __grid_constant__ TrigParams T)
+__global__ void __launch_bounds__(GeoT<LOG2N>::NT, trig_min_ctas(LOG2N)) trig_kernel(const __grid_constant__ TrigParams T)
 {
     extern __shared__ double2 nrb_trig_smem[];
     trig_cta<LOG2N>(T, nrb_trig_smem, blockIdx.x, (int)threadIdx.x);
 }
 
 template <int LOG2N>
-__global__ void __launch_bounds__(GeoT<LOG2N>::NT, (LOG2N <= kTrigTileLog2 ? 4 : LOG2N == 12 ? 2 : 1)) twofft_kernel(const __grid_constant__ TwoFFTParams T)
+__global__ void __launch_bounds__(GeoT<LOG2N>::NT, trig_min_ctas(LOG2N)) twofft_kernel(const __grid_constant__ TwoFFTParams T)
 {
     extern __shared__ double2 nrb_trig_smem[];
     twofft_cta<LOG2N>(T, nrb_trig_smem, blockIdx.x, (int)threadIdx.x);

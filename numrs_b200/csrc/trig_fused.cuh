@@ -26,7 +26,21 @@
 namespace nrb {
 
 // complex points per line: 2^kTrigMinLog2 .. 2^kTrigMaxLog2 (nrb_common.h)
-constexpr int kTrigTileLog2 = 11;       // 2048 complex points per CTA: 256 threads, 36 KiB of shared memory, four CTAs per SM
+// complex points per CTA tile (lines longer than that take one CTA each): 2^11 = 256 threads, 36 KiB of shared memory, four
+// CTAs per SM.  NRB_TRIG_TILE_LOG2 / NRB_TRIG_MINB (resident CTAs per SM the kernel is compiled for) are A/B switches.
+#ifndef NRB_TRIG_TILE_LOG2
+#define NRB_TRIG_TILE_LOG2 11
+#endif
+constexpr int kTrigTileLog2 = NRB_TRIG_TILE_LOG2;
+NRB_HD constexpr int trig_min_ctas(int log2n)
+{
+#ifdef NRB_TRIG_MINB
+    return log2n <= kTrigTileLog2 ? NRB_TRIG_MINB : (log2n >= 13 ? 1 : log2n == 12 ? 2 : 4);
+#else
+    return (log2n > kTrigTileLog2 ? log2n : kTrigTileLog2) >= 13 ? 1 : (log2n > kTrigTileLog2 ? log2n : kTrigTileLog2) == 12 ? 2
+         : (log2n > kTrigTileLog2 ? log2n : kTrigTileLog2) == 11 ? 4 : 8;
+#endif
+}
 
 template <int LOG2N_> struct GeoT {
     static constexpr int LOG2N = LOG2N_, LAYOUT = LAYOUT_ROW, VARIANT = VAR_PLAIN;
@@ -97,28 +111,47 @@ NRB_DEV void trig_cta(const TrigParams &T, double2 *E, unsigned tile, int tid)
     const u64 q_own = (u64)tile * G::L + (u64)ln;
     const int nd = mode == COS1 ? n + 1 : n;                   // doubles of a line that carry data
 
-    // ---- load: aligned 16-byte chunks of every line into the tile, natural order, no padding (line l at 2 * l * LP) ----
-    for (int it = tid; it < G::L * (N + 1); it += G::NT) {
-        const int l = it / (N + 1), c = it - l * (N + 1);
-        const u64 q = (u64)tile * G::L + (u64)l;
-        if (q >= T.count) continue;
-        const double *gb = T.io + (i64)q * T.ld + 1;
-        const int par = (int)((reinterpret_cast<size_t>(gb) >> 3) & 1);
-        const int d0 = 2 * c - par;
-        double *S = Ed + 2 * l * G::LP;
-        if (d0 >= 0 && d0 + 1 < nd) {
-            const double2 v = NRB_LDS(reinterpret_cast<const double2 *>(gb + d0));
-            S[d0] = v.x;
-            S[d0 + 1] = v.y;
-        } else {
-            if (d0 >= 0 && d0 < nd) S[d0] = NRB_LDS(gb + d0);
-            if (d0 + 1 >= 0 && d0 + 1 < nd) S[d0 + 1] = NRB_LDS(gb + d0 + 1);
+    // ---- load: aligned 16-byte chunks of every line into the tile (natural order, no padding: line l at 2 * l * LP doubles,
+    // shifted by the line's alignment so that chunk c of the global line is chunk c of the staging area).  All of a thread's
+    // loads are issued before the first of them is used (one DRAM latency per tile, not one per chunk).
+    constexpr int CH = N + 1;                                  // chunks that cover a line on either alignment
+    constexpr int ITER = (G::L * CH + G::NT - 1) / G::NT;
+    {
+        double2 buf[ITER];
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) {
+            const int it = tid + i * G::NT;
+            const int l = it / CH, c = it - l * CH;
+            const u64 q = (u64)tile * G::L + (u64)l;
+            buf[i] = make_double2(0.0, 0.0);
+            if (it < G::L * CH && q < T.count) {
+                const double *gb = T.io + (i64)q * T.ld + 1;
+                const int par = (int)((reinterpret_cast<size_t>(gb) >> 3) & 1);
+                const int d0 = 2 * c - par;
+                if (d0 >= 0 && d0 + 1 < nd) buf[i] = NRB_LDS(reinterpret_cast<const double2 *>(gb + d0));
+                else {
+                    if (d0 >= 0 && d0 < nd) buf[i].x = NRB_LDS(gb + d0);
+                    if (d0 + 1 >= 0 && d0 + 1 < nd) buf[i].y = NRB_LDS(gb + d0 + 1);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) {
+            const int it = tid + i * G::NT;
+            const int l = it / CH, c = it - l * CH;
+            if (it < G::L * CH) E[l * G::LP + c] = buf[i];
         }
     }
     NRB_SYNC();
 
     // ---- pre-processing: all of a thread's inputs into registers, barrier, then the work array in the padded layout ----
-    const double *S = Ed + 2 * ln * G::LP;
+    const int par_own = (int)((reinterpret_cast<size_t>(T.io + (i64)q_own * T.ld + 1) >> 3) & 1);
+    const double *S = Ed + 2 * ln * G::LP + par_own;
+    // exp(-2 pi i m / M) of the thread's items: m advances by TPL (M = 2n: cosft1, sinft, the inverse's pre-rotation) or by
+    // 2 TPL (M = 4n, m odd: cosft2), i.e. by the fixed angle pi / 16 -- one table look-up and the rotations exp(-i pi i / 16)
+    // instead of a look-up per item (the kernel is L1-bound: ncu, profiles/r02_ncu_full_trig.md)
+    const u64 m0 = mode == COS2F ? (u64)(2 * lt + 1) : mode == COS2I_PRE ? (u64)(2 * lt) : (u64)lt;
+    const double2 t0 = two_level_tw(T.ctw_lo, T.ctw_hi, T.ctw_h, m0);
     double fa[G::PPT], fb[G::PPT], fc = 0.0;
 #pragma unroll
     for (int i = 0; i < G::PPT; ++i) {
@@ -141,14 +174,14 @@ NRB_DEV void trig_cta(const TrigParams &T, double2 *E, unsigned tile, int tid)
                 acc += 0.5 * (fa[i] - fb[i]);
                 Ed[trig_ri<G>(ln, N)] = fc;
             } else {
-                const double2 t = two_level_tw(T.ctw_lo, T.ctw_hi, T.ctw_h, (u64)j);        // (cos, -sin)(j pi / n)
+                const double2 t = i ? cmul(t0, unit_rot<16>(i)) : t0;                      // (cos, -sin)(j pi / n)
                 const double y1 = 0.5 * (fa[i] + fb[i]), y2 = fa[i] - fb[i];
                 Ed[trig_ri<G>(ln, j)] = y1 + t.y * y2;
                 Ed[trig_ri<G>(ln, n - j)] = y1 - t.y * y2;
                 acc += t.x * y2;
             }
         } else if (mode == COS2F) {                            // Cos_FT2.rs:26-36
-            const double2 t = two_level_tw(T.ctw_lo, T.ctw_hi, T.ctw_h, (u64)(2 * j + 1));
+            const double2 t = i ? cmul(t0, unit_rot<16>(i)) : t0;                          // exp(-i (2j+1) pi / (2n))
             const double y1 = 0.5 * (fa[i] + fb[i]), y2 = -t.y * (fa[i] - fb[i]);
             Ed[trig_ri<G>(ln, j)] = y1 + y2;
             Ed[trig_ri<G>(ln, n - 1 - j)] = y1 - y2;
@@ -158,7 +191,7 @@ NRB_DEV void trig_cta(const TrigParams &T, double2 *E, unsigned tile, int tid)
                 const double2 t = two_level_tw(T.ctw_lo, T.ctw_hi, T.ctw_h, (u64)N);
                 Ed[trig_ri<G>(ln, N)] = -t.y * (fc + fc);      // j = N: y2 = 0
             } else {
-                const double2 t = two_level_tw(T.ctw_lo, T.ctw_hi, T.ctw_h, (u64)j);
+                const double2 t = i ? cmul(t0, unit_rot<16>(i)) : t0;
                 const double y1 = -t.y * (fa[i] + fb[i]), y2 = 0.5 * (fa[i] - fb[i]);
                 Ed[trig_ri<G>(ln, j)] = y1 + y2;
                 Ed[trig_ri<G>(ln, n - j)] = y1 - y2;
@@ -166,7 +199,7 @@ NRB_DEV void trig_cta(const TrigParams &T, double2 *E, unsigned tile, int tid)
         } else {
             if (j == 0) E[G::phys(ln, 0)] = make_double2(fa[i], 2.0 * fb[i]);
             else {
-                const double2 t = two_level_tw(T.ctw_lo, T.ctw_hi, T.ctw_h, (u64)(2 * j)); // (cos, -sin)(j pi / n)
+                const double2 t = i ? cmul(t0, unit_rot<16>(i)) : t0;                      // (cos, -sin)(j pi / n)
                 E[G::phys(ln, j)] = make_double2(fa[i] * t.x - fb[i] * t.y, fb[i] * t.x + fa[i] * t.y);
             }
         }
@@ -216,10 +249,11 @@ NRB_DEV void trig_cta(const TrigParams &T, double2 *E, unsigned tile, int tid)
 
     if (inverse) {
         // ---- cosft2 inverse post-processing (Cos_FT2.rs:142-162) in place: a pair (i, n - 1 - i) has one owner ----
+        const double2 tp0 = two_level_tw(T.ctw_lo, T.ctw_hi, T.ctw_h, (u64)(2 * lt + 1));
 #pragma unroll
         for (int i = 0; i < G::PPT; ++i) {
             const int j = lt + i * TPL;
-            const double2 t = two_level_tw(T.ctw_lo, T.ctw_hi, T.ctw_h, (u64)(2 * j + 1));  // sin((2j+1) pi/(2n)) = -t.y
+            const double2 t = i ? cmul(tp0, unit_rot<16>(i)) : tp0;                          // sin((2j+1) pi/(2n)) = -t.y
             const double gi = Ed[trig_ri<G>(ln, j)], gm = Ed[trig_ri<G>(ln, n - 1 - j)];
             const double y1 = gi + gm, y2 = (0.5 / -t.y) * (gi - gm);
             Ed[trig_ri<G>(ln, j)] = 0.5 * (y1 + y2);
@@ -247,6 +281,12 @@ NRB_DEV void trig_cta(const TrigParams &T, double2 *E, unsigned tile, int tid)
         double term[G::PPT], even[G::PPT];
         double loc = 0.0;
         const double g0y = E[G::phys(ln, 0)].y;
+        // cosft2: exp(-i k pi / n) for k = N - 1 - pos walks down by one per position: one look-up and the step exp(+i pi / n)
+        double2 tk = make_double2(1.0, 0.0), tstep = tk;
+        if (mode == COS2F) {
+            tk = two_level_tw(T.ctw_lo, T.ctw_hi, T.ctw_h, (u64)(2 * (N - 1 - lt * G::PPT)));
+            tstep = cconj(two_level_tw(T.ctw_lo, T.ctw_hi, T.ctw_h, 2));
+        }
 #pragma unroll
         for (int i = 0; i < G::PPT; ++i) {
             const int pos = lt * G::PPT + i;
@@ -255,7 +295,8 @@ NRB_DEV void trig_cta(const TrigParams &T, double2 *E, unsigned tile, int tid)
             if (mode == COS1) { term[i] = k ? z.y : 0.0; even[i] = z.x; }                    // Cos_FT.rs:64-67
             else if (mode == SINFT) { term[i] = k ? z.x : 0.5 * z.x; even[i] = k ? z.y : 0.0; }
             else {                                                                            // Cos_FT2.rs:54-85
-                if (k) { const double2 t = two_level_tw(T.ctw_lo, T.ctw_hi, T.ctw_h, (u64)(2 * k)); z = make_double2(z.x * t.x + z.y * t.y, z.y * t.x - z.x * t.y); }
+                if (k) z = make_double2(z.x * tk.x + z.y * tk.y, z.y * tk.x - z.x * tk.y);
+                tk = cmul(tk, tstep);
                 term[i] = z.y; even[i] = z.x;
             }
             loc += term[i];
@@ -277,21 +318,29 @@ NRB_DEV void trig_cta(const TrigParams &T, double2 *E, unsigned tile, int tid)
     }
     NRB_SYNC();
 
-    // ---- store: f[2k] = E[k].x, f[2k+1] = E[k].y, aligned 16-byte chunks with a scalar head / tail on odd lines ----
-    for (int it = tid; it < G::L * (N + 1); it += G::NT) {
-        const int l = it / (N + 1), c = it - l * (N + 1);
+    // ---- store: f[2k] = E[k].x, f[2k+1] = E[k].y in aligned 16-byte chunks.  On an odd line chunk c is (E[c-1].y, E[c].x):
+    // the left half comes from the neighbouring lane (chunk c - 1 of the same line) by a shuffle, so every chunk costs one
+    // 16-byte shared-memory read; scalar head / tail.
+#pragma unroll
+    for (int i = 0; i < ITER; ++i) {
+        const int it = tid + i * G::NT;
+        const int l = it / CH, c = it - l * CH;
         const u64 q = (u64)tile * G::L + (u64)l;
-        if (q >= T.count) continue;
+        const bool ok = it < G::L * CH && q < T.count;
+        double2 own = make_double2(0.0, 0.0);
+        if (it < G::L * CH && c < N) own = E[G::phys(l, c)];
+        double left = NRB_SHFL(own.y, (tid - 1) & 31);
+        if (!ok) continue;
         double *gb = T.io + (i64)q * T.ld + 1;
         const int par = (int)((reinterpret_cast<size_t>(gb) >> 3) & 1);
         if (par == 0) {
-            if (c < N) NRB_STS(reinterpret_cast<double2 *>(gb) + c, E[G::phys(l, c)]);
+            if (c < N) NRB_STS(reinterpret_cast<double2 *>(gb) + c, own);
         } else if (c == 0) {
-            gb[0] = E[G::phys(l, 0)].x;
-        } else if (c == N) {
-            gb[n - 1] = E[G::phys(l, N - 1)].y;
+            gb[0] = own.x;
         } else {
-            NRB_STS(reinterpret_cast<double2 *>(gb + 2 * c - 1), make_double2(E[G::phys(l, c - 1)].y, E[G::phys(l, c)].x));
+            if ((tid & 31) == 0) left = E[G::phys(l, c - 1)].y;   // the neighbour is in another warp
+            if (c == N) gb[n - 1] = left;
+            else NRB_STS(reinterpret_cast<double2 *>(gb + 2 * c - 1), make_double2(left, own.x));
         }
     }
 }
@@ -305,19 +354,33 @@ NRB_DEV void twofft_cta(const TwoFFTParams &T, double2 *E, unsigned tile, int ti
     typedef Stage2<G, 0> S0;
     constexpr int N = G::N;                                    // complex points per line = the real length n
     // ---- pack (FFT_2.rs:33-37): point j = (d1[j], d2[j]); 16-byte loads of two points' worth of each signal ----
-    // (a caller of the plan API may hand over signals that are only 8-byte aligned: scalar loads then)
+    // (a caller of the plan API may hand over signals that are only 8-byte aligned: scalar loads then); all of a thread's
+    // loads are issued before the first of them is used
     const bool vec = ((reinterpret_cast<size_t>(T.d1) | reinterpret_cast<size_t>(T.d2)) & 15) == 0;
-    for (int it = tid; it < G::L * (N / 2); it += G::NT) {
-        const int l = it / (N / 2), c = it - l * (N / 2);
-        const u64 q = (u64)tile * G::L + (u64)l;
-        double2 a = make_double2(0.0, 0.0), b = a;
-        if (q < T.count) {
-            const double *p1 = T.d1 + (i64)q * N + 2 * c, *p2 = T.d2 + (i64)q * N + 2 * c;
-            if (vec) { a = NRB_LDS(reinterpret_cast<const double2 *>(p1)); b = NRB_LDS(reinterpret_cast<const double2 *>(p2)); }
-            else { a = make_double2(NRB_LDS(p1), NRB_LDS(p1 + 1)); b = make_double2(NRB_LDS(p2), NRB_LDS(p2 + 1)); }
+    constexpr int PITER = (G::L * (N / 2)) / G::NT;            // = 4: TILE / 2 chunks of two points over TILE / 8 threads
+    static_assert(PITER * G::NT == G::L * (N / 2), "twofft: the chunks of a tile divide evenly over the threads");
+    {
+        double2 a[PITER], b[PITER];
+#pragma unroll
+        for (int i = 0; i < PITER; ++i) {
+            const int it = tid + i * G::NT;
+            const int l = it / (N / 2), c = it - l * (N / 2);
+            const u64 q = (u64)tile * G::L + (u64)l;
+            a[i] = make_double2(0.0, 0.0);
+            b[i] = a[i];
+            if (q < T.count) {
+                const double *p1 = T.d1 + (i64)q * N + 2 * c, *p2 = T.d2 + (i64)q * N + 2 * c;
+                if (vec) { a[i] = NRB_LDS(reinterpret_cast<const double2 *>(p1)); b[i] = NRB_LDS(reinterpret_cast<const double2 *>(p2)); }
+                else { a[i] = make_double2(NRB_LDS(p1), NRB_LDS(p1 + 1)); b[i] = make_double2(NRB_LDS(p2), NRB_LDS(p2 + 1)); }
+            }
         }
-        E[G::phys(l, 2 * c)] = make_double2(a.x, b.x);
-        E[G::phys(l, 2 * c + 1)] = make_double2(a.y, b.y);
+#pragma unroll
+        for (int i = 0; i < PITER; ++i) {
+            const int it = tid + i * G::NT;
+            const int l = it / (N / 2), c = it - l * (N / 2);
+            E[G::phys(l, 2 * c)] = make_double2(a[i].x, b[i].x);
+            E[G::phys(l, 2 * c + 1)] = make_double2(a[i].y, b[i].y);
+        }
     }
     NRB_SYNC();
     // ---- four1(fft1, n, 1) (FFT_2.rs:13) ----
