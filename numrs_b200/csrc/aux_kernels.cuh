@@ -349,12 +349,17 @@ NRB_DEV void aux_normalize(const AuxParams &A, u64 gtid, u64 gthreads)
 {
     double *out = reinterpret_cast<double *>(A.out);
     if (A.op == 1) {
+        // (the kernel was bound by its two 64-bit integer divisions and two FP64 divisions per 32 bytes, not by HBM: a shift
+        // when n is a power of two -- always on the FFT path --, and one reciprocal per item: <= 1 ulp from the quotient)
         const u64 n2 = A.n / 2, items = A.count * n2;
+        int sh = -1;
+        if ((n2 & (n2 - 1)) == 0) { sh = 0; while ((1ull << sh) < n2) ++sh; }
         for (u64 it = gtid; it < items; it += gthreads) {
-            const u64 i = it % n2, s = it / n2;
+            const u64 s = sh >= 0 ? it >> sh : it / n2, i = it - s * n2;
             const double2 st = A.speq[s];
+            const double inv = 1.0 / st.y;
             const double2 v = NRB_LDS(reinterpret_cast<const double2 *>(signal_src(A, s)) + i);
-            reinterpret_cast<double2 *>(out + (i64)s * A.out_stride)[i] = make_double2((v.x - st.x) / st.y, (v.y - st.x) / st.y);
+            reinterpret_cast<double2 *>(out + (i64)s * A.out_stride)[i] = make_double2((v.x - st.x) * inv, (v.y - st.x) * inv);
         }
         return;
     }

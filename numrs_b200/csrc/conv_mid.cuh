@@ -73,22 +73,85 @@ NRB_DEV void mid_gather(const double2 *E, int tid, double2 *v)
     }
 }
 
+// NRB_TW_PREFETCH = 1: the table look-ups of stage S + 1 (one twiddle per butterfly) are issued before the exchange that
+// precedes it, so their L1 / L2 latency hides behind the scatter, the two barriers and the gather (ncu on conv_mid: the first
+// FP64 instruction of every stage waits on that load, 9 % of the warp samples; profiles/r02_ncu_full_conv_mid.md)
+#ifndef NRB_TW_PREFETCH
+#define NRB_TW_PREFETCH 0
+#endif
+template <class G, int S, class PP>
+NRB_DEV void v2_tw_load(const PP &P, int tid, double2 *w1)
+{
+    typedef Stage2<G, S> T;
+#pragma unroll
+    for (int i = 0; i < T::BPT; ++i) {
+        int ln, jj;
+        T::coords(tid, i, ln, jj);
+        const int jm = jj & (T::NS - 1);
+        w1[i] = NRB_LDG(P.tw + stage_tw_off(G::LOG2N, S) + jm * (T::R - 1));
+    }
+}
+// v2_compute with the first twiddle of every butterfly already in registers (radix >= 4 stages with NS > 1)
+template <class G, int S, class PP>
+NRB_DEV void v2_compute_pre(const PP &P, int tid, double2 *v, const double2 *w1)
+{
+    typedef Stage2<G, S> T;
+    constexpr int R = T::R;
+#pragma unroll
+    for (int i = 0; i < T::BPT; ++i) {
+        double2 w[R];
+        w[1] = w1[i];
+        w[2] = cmul(w[1], w[1]);
+        w[3] = cmul(w[2], w[1]);
+        if (R >= 8) {
+            w[4] = cmul(w[2], w[2]);
+            w[5] = cmul(w[4], w[1]);
+            w[6] = cmul(w[3], w[3]);
+            w[7] = cmul(w[4], w[3]);
+        }
+#pragma unroll
+        for (int r = 1; r < R; ++r) v[i * R + r] = cmul(v[i * R + r], w[r]);
+        Bfly<R>::run(v + i * R);
+    }
+}
 // stages S .. NST-1 on registers with the exchanges between them; leaves the last stage's outputs in v
 template <class G, int S> struct ChainM {
+    static constexpr int SN = S + 1 < G::NST ? S + 1 : 0;
+    // prefetch applies when the next stage exists, is radix 4 or 8 and has twiddles (NS > 1 always holds for S + 1 >= 1)
+    static constexpr bool PRE = NRB_TW_PREFETCH && S + 1 < G::NST && Stage2<G, SN>::R >= 4 && Stage2<G, SN>::R <= 8;
     template <class PP> NRB_DEVM static void run(const PP &M, double2 *E, int tid, double2 *v)
     {
         v2_compute<G, S>(M, tid, v);
         if (S + 1 < G::NST) {
+            double2 w1[Stage2<G, SN>::BPT];
+            if (PRE) v2_tw_load<G, SN>(M, tid, w1);
             mid_scatter<G, S>(E, tid, v);
             NRB_SYNC();
-            mid_gather<G, (S + 1 < G::NST ? S + 1 : 0)>(E, tid, v);
+            mid_gather<G, SN>(E, tid, v);
             NRB_SYNC();
-            ChainM<G, (S + 1 < G::NST ? S + 1 : -1)>::run(M, E, tid, v);
+            if (PRE) ChainM<G, (S + 1 < G::NST ? S + 1 : -1)>::run_pre(M, E, tid, v, w1);
+            else ChainM<G, (S + 1 < G::NST ? S + 1 : -1)>::run(M, E, tid, v);
+        }
+    }
+    // the same with this stage's first twiddles already loaded
+    template <class PP> NRB_DEVM static void run_pre(const PP &M, double2 *E, int tid, double2 *v, const double2 *w1_this)
+    {
+        v2_compute_pre<G, S>(M, tid, v, w1_this);
+        if (S + 1 < G::NST) {
+            double2 w1[Stage2<G, SN>::BPT];
+            if (PRE) v2_tw_load<G, SN>(M, tid, w1);
+            mid_scatter<G, S>(E, tid, v);
+            NRB_SYNC();
+            mid_gather<G, SN>(E, tid, v);
+            NRB_SYNC();
+            if (PRE) ChainM<G, (S + 1 < G::NST ? S + 1 : -1)>::run_pre(M, E, tid, v, w1);
+            else ChainM<G, (S + 1 < G::NST ? S + 1 : -1)>::run(M, E, tid, v);
         }
     }
 };
 template <class G> struct ChainM<G, -1> {
     template <class PP> NRB_DEVM static void run(const PP &, double2 *, int, double2 *) {}
+    template <class PP> NRB_DEVM static void run_pre(const PP &, double2 *, int, double2 *, const double2 *) {}
 };
 
 template <int LOG2R>
