@@ -208,7 +208,7 @@ template <class H2D, class EXEC, class D2H>
 int run_pipelined(size_t count, size_t per, H2D h2d, EXEC exec, D2H d2h)
 {
     ++g_pipelined_calls;
-    if (!t_ctx.s_in && (be_stream_create(&t_ctx.s_in) != 0 || be_stream_create(&t_ctx.s_out) != 0))
+    if ((!t_ctx.s_in && be_stream_create(&t_ctx.s_in) != 0) || (!t_ctx.s_out && be_stream_create(&t_ctx.s_out) != 0))
         return fail(NRB_ERR_CUDA, std::string("stream creation failed: ") + be_last_error());
     const size_t nchunks = (count + per - 1) / per;
     std::vector<void *> ev(2 * nchunks, nullptr);
@@ -703,6 +703,7 @@ try {
     size_t total = 1;
     for (size_t d = 0; d < ndim; ++d) {
         if (nn[d] <= 1) return fail(NRB_ERR_INVALID_DIMS, "Invalid dimension size");
+        if (total > ((size_t)1 << 60) / nn[d]) return fail(NRB_ERR_INVALID_DIMS, "Invalid dimension size");   // product overflows
         total *= nn[d];
     }
     if (!data) return fail(NRB_ERR_EMPTY_INPUT, "null data");
