@@ -1,0 +1,528 @@
+"""The reference's own unit tests for the hot path, replayed one by one.
+
+Every `#[test]` of FFT_1.rs, Fourn.rs, Real_FT.rs, Real_FT3.rs, Convolve.rs, Correlation.rs and of the next rows FFT_2.rs,
+Cos_FT.rs, Cos_FT2.rs has one test here with the same name, the same inputs and the same assertions, run three times:
+
+  oracle  the CPU restatement (oracle/nr_oracle.c)                        CPU tier
+  emu     the product's planner + kernels under the test-only emulator      CPU tier
+  gpu     the product's CUDA path through the C ABI on a real device        GPU tier (-m gpu)
+
+None of these tests can run in the reference itself (its FFT modules are commented out of lib.rs and do not type-check,
+SURVEY.md section 0 / 4).  Where a reference assertion is contradicted by the reference's OWN code, the test states so, cites
+the lines, and asserts what the literal code computes instead (deviation ledger of SURVEY.md 8c / oracle/nr_oracle.c);
+everything else is asserted exactly as the reference writes it.  The file-system `Fourn` object tests (tempdir, mmap) are
+outside the path (Four_FS / out-of-core); their validation part is replayed on the in-memory fourn.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import numrs_b200 as nb
+import oracle as O
+
+PI = math.pi
+
+
+class _LibApi:
+    """The reference-shaped Python mirror on a given library build (emulator or CUDA)."""
+
+    def __init__(self, L, kind):
+        self.L, self.kind = L, kind
+
+    def four1(self, d, nn, isign): nb.four1(d, nn, isign, self.L)
+    def fft_batch(self, arrs, isign): nb.FFTProcessor(self.L).fft_batch(arrs, isign)
+    def magnitude_spectrum(self, c): return nb.magnitude_spectrum(c, self.L)
+    def power_spectrum(self, c): return nb.power_spectrum(c, self.L)
+    def fourn(self, d, nn, ndim, isign): nb.fourn(d, nn, ndim, isign, self.L)
+    def realft(self, d, n, isign): nb.realft(d, n, isign, self.L)
+    def realft_optimized(self, d, n, isign): nb.realft_optimized(d, n, isign, self.L)
+    def realft_batch(self, batches): nb.RealFTProcessor(self.L).process_batch(batches)
+    def rlft3(self, d, s, a, b, c, isign): nb.rlft3(d, s, a, b, c, isign, self.L)
+    def convlv(self, d, r, isign): return nb.convlv(np.asarray(d, float), np.asarray(r, float), isign, _L=self.L)
+    def convlv_batch(self, ds, r, isign): return nb.convlv_batch(ds, np.asarray(r, float), isign, _L=self.L)
+    def convlv_processor(self, d, r, isign): return nb.ConvlvProcessor(self.L).process(np.asarray(d, float), np.asarray(r, float), isign)
+    def correl(self, a, b): return nb.correl(np.asarray(a, float), np.asarray(b, float), self.L)
+    def correl_batch(self, pairs): return nb.correl_batch(pairs, self.L)
+    def autocorrel(self, a): return nb.autocorrel(np.asarray(a, float), self.L)
+    def correl_normalized(self, a, b): return nb.correl_normalized(np.asarray(a, float), np.asarray(b, float), self.L)
+    def correl_normalized_fast(self, a, b): return nb.correl_normalized_fast(np.asarray(a, float), np.asarray(b, float), self.L)
+    def twofft(self, a, b, f1, f2): nb.twofft(a, b, f1, f2, self.L)
+    def twofft_optimized(self, a, b, f1, f2): nb.twofft_optimized(a, b, f1, f2, self.L)
+    def twofft_batch(self, batches): nb.TwoFFTProcessor(self.L).process_batch(batches)
+    def cosft1(self, y, n): nb.cosft1(y, n, self.L)
+    def cosft2(self, y, n, isign): nb.cosft2(y, n, isign, self.L)
+
+
+class _OracleApi:
+    """The same calls on the CPU oracle, with the reference's error behaviour mapped the way the mirrors map it."""
+    kind = "oracle"
+
+    @staticmethod
+    def _conv(rc, ans):
+        if rc != 0:
+            raise nb.ConvlvError({-1: "EmptyInput", -2: "ResponseTooLong", -3: "InvalidIsign"}.get(rc, "FftError"))
+        return ans
+
+    @staticmethod
+    def _corr(rc, ans):
+        if rc != 0:
+            raise nb.CorrelError({-1: "EmptyInput", -4: "LengthMismatch", -8: "ZeroStdDev"}.get(rc, "FftError"))
+        return ans
+
+    def four1(self, d, nn, isign): O.four1(d, nn, isign)
+    def fft_batch(self, arrs, isign): O.fft_batch(arrs, isign)
+    def magnitude_spectrum(self, c): return O.power_spectrum(c, True)
+    def power_spectrum(self, c): return O.power_spectrum(c, False)
+
+    def fourn(self, d, nn, ndim, isign):
+        if O.fourn_validate(list(nn), ndim, isign) != 0:
+            raise ValueError("InvalidInput")
+        O.fourn(d, list(nn)[:ndim], isign)
+
+    def realft(self, d, n, isign): O.realft(d, n, isign)
+    def realft_optimized(self, d, n, isign): O.realft(d, n, isign)
+
+    def realft_batch(self, batches):
+        for d, n, isign in batches:
+            O.realft(d, n, isign)
+
+    def rlft3(self, d, s, a, b, c, isign): O.rlft3(d, s, isign)
+    def convlv(self, d, r, isign): return self._conv(*O.convlv(d, r, isign))
+    def convlv_batch(self, ds, r, isign): return [self.convlv(d, r, isign) for d in ds]
+    def convlv_processor(self, d, r, isign): return self.convlv(d, r, isign)
+    def correl(self, a, b): return self._corr(*O.correl(a, b))
+    def correl_batch(self, pairs): return [self.correl(a, b) for a, b in pairs]
+    def autocorrel(self, a): return self.correl(a, a)
+    def correl_normalized(self, a, b): return self._corr(*O.correl_normalized(a, b, False))
+    def correl_normalized_fast(self, a, b): return self._corr(*O.correl_normalized(a, b, True))
+
+    def twofft(self, a, b, f1, f2):
+        assert len(b) == len(a) and f1.size == 2 * len(a) + 2 and f2.size == 2 * len(a) + 2      # FFT_2.rs:5-7
+        r1, r2 = O.twofft(a, b)
+        f1[:], f2[:] = r1, r2
+
+    twofft_optimized = twofft
+
+    def twofft_batch(self, batches):
+        for a, b, f1, f2 in batches:
+            self.twofft(a, b, f1, f2)
+
+    def cosft1(self, y, n): O.cosft1(y, n)
+
+    def cosft2(self, y, n, isign):
+        rc, _ = O.cosft2(y, n, isign)
+        if rc != 0:
+            raise nb.NrbError(rc, "Invalid isign value. Must be 1 or -1")
+
+
+@pytest.fixture(params=["oracle", "emu", pytest.param("gpu", marks=pytest.mark.gpu)])
+def api(request):
+    if request.param == "oracle":
+        return _OracleApi()
+    return _LibApi(request.getfixturevalue(request.param), request.param)
+
+
+def close(a, b, eps=1e-10):
+    """approx::assert_relative_eq!(a, b, epsilon = eps) for the magnitudes these tests use"""
+    return abs(a - b) <= eps
+
+
+# ====================================================================================== FFT_1.rs:231-322
+def fft1_signal():       # FFT_1.rs:236-243
+    t = np.arange(1024) / 1024.0
+    return np.sin(2 * PI * 5 * t) + 0.5 * np.cos(2 * PI * 20 * t)
+
+
+def test_FFT_1__test_fft_correctness(api):          # FFT_1.rs:246-267
+    signal = fft1_signal()
+    c = nb.real_to_complex(signal)
+    api.four1(c, signal.size, 1)
+    api.four1(c, signal.size, -1)
+    c /= signal.size
+    rec = nb.complex_to_real(c)
+    assert np.all(np.abs(signal - rec) < 1e-10), "FFT reconstruction error"
+
+
+def test_FFT_1__test_fft_performance(api):          # FFT_1.rs:270-283 (runs and prints timings; here: runs, and is right)
+    for size in (256, 1024, 4096, 16384):
+        signal = np.sin(2 * PI * np.arange(size) / size)
+        c = nb.real_to_complex(signal)
+        api.four1(c, size, 1)
+        z = c[0::2] + 1j * c[1::2]
+        # a unit sine of one period: bins 1 and size-1 hold -+ i size/2 (e^{+i} forward convention)
+        assert abs(z[1] - 0.5j * size) < 1e-9 * size and abs(z[size - 1] + 0.5j * size) < 1e-9 * size
+        z[1] = z[size - 1] = 0
+        assert np.max(np.abs(z)) < 1e-9 * size
+
+
+def test_FFT_1__test_parallel_fft(api):             # FFT_1.rs:286-302 (8 signals of 1024 points through fft_batch)
+    sigs = [np.sin(2 * PI * (i + 1) * np.arange(1024) / 1024.0) for i in range(8)]
+    cs = [nb.real_to_complex(s) for s in sigs]
+    singles = [c.copy() for c in cs]
+    api.fft_batch(cs, 1)
+    for i, (c, s) in enumerate(zip(cs, singles)):
+        api.four1(s, 1024, 1)
+        assert np.array_equal(c, s) or np.max(np.abs(c - s)) < 1e-12 * 1024      # a batch is the same transform per slice
+        z = c[0::2] + 1j * c[1::2]
+        assert abs(z[i + 1] - 512j) < 1e-9                                          # the tone of signal i sits in bin i + 1
+
+
+def test_FFT_1__test_spectrum_functions(api):       # FFT_1.rs:305-321
+    signal = fft1_signal()
+    c = nb.real_to_complex(signal)
+    api.four1(c, signal.size, 1)
+    magnitude = api.magnitude_spectrum(c)
+    power = api.power_spectrum(c)
+    assert len(magnitude) == signal.size and len(power) == signal.size
+    assert np.all(np.abs(magnitude * magnitude - power) < 1e-10)
+
+
+# ====================================================================================== Fourn.rs:451-487
+def test_Fourn__test_fourn_basic(api):              # Fourn.rs:456-464: fourn(&[8, 8], 2, 1) succeeds (in-memory call shape)
+    d = O.fill_uniform(77, 0, 2 * 64)
+    ref = np.fft.ifft2((d[0::2] + 1j * d[1::2]).reshape(8, 8)) * 64     # e^{+i} forward, unnormalised
+    api.fourn(d, [8, 8], 2, 1)
+    assert np.max(np.abs((d[0::2] + 1j * d[1::2]).reshape(8, 8) - ref)) < 1e-12
+
+
+def test_Fourn__test_invalid_inputs(api):           # Fourn.rs:467-476
+    d = np.zeros(16)
+    with pytest.raises(ValueError):
+        api.fourn(d, [1], 1, 1)          # invalid dimension
+    with pytest.raises(ValueError):
+        api.fourn(d, [8], 1, 0)          # invalid isign
+
+
+def test_Fourn__test_memory_mapping():              # Fourn.rs:479-486
+    pytest.skip("out of the path: the file / mmap-backed Fourn object is Four_FS territory (SURVEY.md section 2, out of scope)")
+
+
+# ====================================================================================== Real_FT.rs:488-595
+def realft_signal(n):    # Real_FT.rs:492-498
+    t = np.arange(n) / n
+    return np.sin(2 * PI * 5 * t) + 0.5 * np.cos(2 * PI * 10 * t)
+
+
+def test_Real_FT__test_realft_correctness(api):     # Real_FT.rs:501-521
+    n = 256
+    data = realft_signal(n)
+    copy = data.copy()
+    api.realft(data, n, 1)
+    api.realft(data, n, -1)
+    # the reference divides by n; NR's realft round trip is (n/2) x (ledger D2: the reference's own loop gives n/2 as well, so
+    # its assertion cannot hold as written) -- asserted with the true factor
+    data /= n / 2
+    assert np.all(np.abs(copy - data) < 1e-10), "RealFT reconstruction error"
+
+
+def test_Real_FT__test_realft_optimized_correctness(api):     # Real_FT.rs:524-545
+    n = 256
+    d1 = realft_signal(n)
+    d2 = d1.copy()
+    api.realft(d1, n, 1)
+    api.realft_optimized(d2, n, 1)
+    assert np.all(np.abs(d1 - d2) < 1e-10), "Optimized version mismatch"
+    api.realft(d1, n, -1)
+    api.realft_optimized(d2, n, -1)
+    assert np.all(np.abs(d1 - d2) < 1e-10), "Optimized inverse version mismatch"
+
+
+def test_Real_FT__test_four1_function(api):         # Real_FT.rs:548-556: four1 of 8 ones completes; and is 8 delta_k
+    data = np.array([1.0, 0.0] * 8)
+    api.four1(data, 8, 1)
+    assert data.size == 16
+    assert np.allclose(data, [8.0] + [0.0] * 15, atol=1e-12)
+
+
+def test_Real_FT__test_realft_performance(api):     # Real_FT.rs:559-571 (runs 256 / 1024 / 4096; here also checked)
+    for size in (256, 1024, 4096):
+        data = realft_signal(size)
+        ref = np.conj(np.fft.rfft(data))            # F_k = sum x_j e^{+2 pi i jk/n}
+        api.realft(data, size, 1)
+        assert abs(data[0] - ref[0].real) < 1e-9 and abs(data[1] - ref[size // 2].real) < 1e-9     # F_0 and F_{n/2} packed
+        z = data[2::2] + 1j * data[3::2]
+        assert np.max(np.abs(z - ref[1:size // 2])) < 1e-9 * size
+
+
+def test_Real_FT__test_batch_processing(api):       # Real_FT.rs:574-594: RealFTProcessor::process_batch, 4 x 512
+    batches = [(realft_signal(512), 512, 1) for _ in range(4)]
+    single = realft_signal(512)
+    api.realft(single, 512, 1)
+    api.realft_batch(batches)
+    for d, _, _ in batches:
+        assert np.max(np.abs(d - single)) < 1e-12 * 512
+
+
+# ====================================================================================== Real_FT3.rs:261-328
+def test_Real_FT3__test_rlft3_round_trip(api):      # Real_FT3.rs:268-311
+    nn1 = nn2 = nn3 = 8
+    i, j, k = np.meshgrid(np.arange(nn1), np.arange(nn2), np.arange(nn3), indexing="ij")
+    data = (i + j + k).astype(np.float64)
+    speq = np.zeros((nn1, 2 * nn2))
+    original = data.copy()
+    api.rlft3(data, speq, nn1, nn2, nn3, 1)
+    api.rlft3(data, speq, nn1, nn2, nn3, -1)
+    # the reference divides by nn1 nn2 nn3; NR's rlft3 round trip is (nn1 nn2 nn3 / 2) x (ledger D8) -- true factor
+    data /= nn1 * nn2 * nn3 / 2
+    assert np.all(np.abs(data - original) <= 1e-10)
+
+
+def test_Real_FT3__test_performance(api):           # Real_FT3.rs:314-327: rlft3 of a 32^3 volume of zeros completes
+    data = np.zeros((32, 32, 32))
+    speq = np.zeros((32, 64))
+    api.rlft3(data, speq, 32, 32, 32, 1)
+    assert not data.any() and not speq.any()
+
+
+# ====================================================================================== Convolve.rs:341-456
+def test_Convolve__test_convolution_basic(api):     # Convolve.rs:347-360
+    result = api.convlv([1.0, 2.0, 3.0, 4.0], [1.0, 1.0], 1)
+    # the reference expects [1, 3, 5, 7] (a LINEAR convolution); its code is circular (Convolve.rs:41-63 wraps the response,
+    # :90-138 multiplies n-point spectra), so element 0 also receives 4 * 1: 5.  Elements 1..3 hold as written.
+    assert close(result[0], 5.0)
+    assert close(result[1], 3.0)
+    assert close(result[2], 5.0)
+    assert close(result[3], 7.0)
+
+
+def test_Convolve__test_deconvolution(api):         # Convolve.rs:363-376
+    result = api.convlv([1.0, 3.0, 5.0, 7.0], [1.0, 1.0], -1)
+    # the reference expects [1, 2, 3, 4]; the spectrum of [1, 1] vanishes at the Nyquist bin, which the code zeroes
+    # (Convolve.rs:118-122, |R|^2 < 1e-12), and [1, 3, 5, 7] is not a circular convolution with [1, 1] to begin with: the
+    # literal code returns [0, 2, 4, 2] (oracle ledger D6 / D7)
+    assert np.allclose(result, [0.0, 2.0, 4.0, 2.0], atol=1e-10)
+
+
+def test_Convolve__test_complex_divide_and_multiply(api):     # Convolve.rs:379-403 (private helpers of the spectral step)
+    # exercised through the public call: convolving with the unit impulse multiplies every bin by (1 + 0i), deconvolving
+    # divides by it: both are the identity
+    x = O.fill_uniform(78, 0, 64)
+    assert np.max(np.abs(api.convlv(x, [1.0], 1) - x)) < 1e-12
+    assert np.max(np.abs(api.convlv(x, [1.0], -1) - x)) < 1e-12
+
+
+def test_Convolve__test_error_handling(api):        # Convolve.rs:406-424
+    with pytest.raises(nb.ConvlvError) as e:
+        api.convlv([], [1.0], 1)
+    assert e.value.kind == "EmptyInput"
+    with pytest.raises(nb.ConvlvError) as e:
+        api.convlv([1.0, 2.0], [1.0, 2.0, 3.0], 1)
+    assert e.value.kind == "ResponseTooLong"
+    with pytest.raises(nb.ConvlvError) as e:
+        api.convlv([1.0, 2.0], [1.0], 0)
+    assert e.value.kind == "InvalidIsign"
+
+
+def test_Convolve__test_batch_processing(api):      # Convolve.rs:427-442
+    # the reference convolves signals of THREE points: realft(n = 3) hits `assert!(n % 2 == 0)` (Real_FT.rs:5) and panics, so
+    # the expectations (results[0][1] == 3, results[1][1] == 9) are unreachable; here the call is an FftError, and the same
+    # batch padded to four points gives the values the test names
+    with pytest.raises(nb.ConvlvError) as e:
+        api.convlv_batch([np.array([1.0, 2.0, 3.0]), np.array([4.0, 5.0, 6.0])], [1.0, 1.0], 1)
+    assert e.value.kind == "FftError"
+    results = api.convlv_batch([np.array([1.0, 2.0, 3.0, 0.0]), np.array([4.0, 5.0, 6.0, 0.0])], [1.0, 1.0], 1)
+    assert len(results) == 2
+    assert close(results[0][1], 3.0)      # 1 + 2
+    assert close(results[1][1], 9.0)      # 4 + 5
+
+
+def test_Convolve__test_processor(api):             # Convolve.rs:445-454
+    result = api.convlv_processor([1.0, 2.0, 3.0, 4.0], [1.0, 1.0], 1)
+    assert close(result[1], 3.0)
+
+
+# ====================================================================================== Correlation.rs:401-513
+def test_Correlation__test_correlation_basic(api):  # Correlation.rs:407-418
+    result = api.correl([1.0, 2.0, 3.0, 4.0], [1.0, 2.0, 3.0, 4.0])
+    assert close(result[0], 30.0)
+    assert result[0] > result[1]
+
+
+def test_Correlation__test_correlation_shifted(api):     # Correlation.rs:421-432
+    result = api.correl([1.0, 2.0, 3.0, 4.0], [0.0, 1.0, 2.0, 3.0])
+    # the reference expects the peak at lag 1; its n <= 32 branch computes ans[lag] = sum_i d1[i + lag] d2[i]
+    # (Correlation.rs:37-50), which for these inputs is [20, 11, 4, 0]: the peak is at lag 0 -- literal
+    assert np.allclose(result, [20.0, 11.0, 4.0, 0.0], atol=1e-10)
+
+
+def test_Correlation__test_normalized_correlation(api):  # Correlation.rs:435-449
+    result = api.correl_normalized([1.0, 2.0, 3.0, 4.0], [1.0, 2.0, 3.0, 4.0])
+    # the reference expects 1.0 at lag 0 and |values| <= 1; only the `_fast` variant divides by n (Correlation.rs:251-263),
+    # the plain one returns the raw direct lags of the normalised signals: 4 at lag 0 -- literal
+    assert np.allclose(result, [4.0, 1.0, -1.2, -1.8], atol=1e-10)
+
+
+def test_Correlation__test_error_handling(api):     # Correlation.rs:453-462
+    with pytest.raises(nb.CorrelError) as e:
+        api.correl([], [1.0])
+    assert e.value.kind == "EmptyInput"
+    with pytest.raises(nb.CorrelError) as e:
+        api.correl([1.0, 2.0], [1.0])
+    assert e.value.kind == "LengthMismatch"
+
+
+def test_Correlation__test_batch_correlation(api):  # Correlation.rs:465-478
+    pairs = [(np.array([1.0, 2.0]), np.array([1.0, 2.0])), (np.array([3.0, 4.0]), np.array([3.0, 4.0]))]
+    results = api.correl_batch(pairs)
+    assert len(results) == 2
+    assert close(results[0][0], 5.0)
+    assert close(results[1][0], 25.0)
+
+
+def test_Correlation__test_autocorrelation(api):    # Correlation.rs:481-491
+    result = api.autocorrel([1.0, 2.0, 1.0, 2.0])
+    assert close(result[0], 10.0)
+    # the reference expects 8 at lag 2 (a circular lag); the n <= 32 branch is linear: 1*1 + 2*2 = 5 -- literal
+    assert close(result[2], 5.0)
+
+
+def test_Correlation__test_direct_correlation_small(api):     # Correlation.rs:494-502 (correl_direct = the n <= 32 branch)
+    result = api.correl([1.0, 2.0], [1.0, 2.0])
+    assert close(result[0], 5.0)
+    assert close(result[1], 2.0)
+
+
+def test_Correlation__test_fast_normalized_correlation(api):  # Correlation.rs:505-512
+    result = api.correl_normalized_fast([1.0, 2.0, 3.0, 4.0], [1.0, 2.0, 3.0, 4.0])
+    assert close(result[0], 1.0)
+
+
+# ====================================================================================== FFT_2.rs:387-519 (next row N2)
+def twofft_signals(n):   # FFT_2.rs:392-403
+    t = np.arange(n) / n
+    return np.sin(2 * PI * 5 * t), np.cos(2 * PI * 10 * t)
+
+
+def test_FFT_2__test_twofft_correctness(api):       # FFT_2.rs:406-428
+    n = 256
+    d1, d2 = twofft_signals(n)
+    f1, f2 = np.zeros(2 * n + 2), np.zeros(2 * n + 2)
+    api.twofft(d1, d2, f1, f2)
+    assert abs(f1[1]) < 1e-10, "fft1[1] should be zero"
+    assert abs(f2[1]) < 1e-10, "fft2[1] should be zero"
+    for k in range(1, n // 2):
+        j = 2 * k
+        # the reference mirrors bin k at 2n + 2 - j, i.e. bin n - k + 1: the 1-based NR index carried into 0-based code
+        # (ledger D9); Hermitian symmetry of a real signal's spectrum pairs k with n - k
+        j_rev = 2 * n - j
+        assert abs(f1[j] - f1[j_rev]) < 1e-10, "Real part symmetry"
+        assert abs(f1[j + 1] + f1[j_rev + 1]) < 1e-10, "Imag part symmetry"
+
+
+def test_FFT_2__test_twofft_optimized_correctness(api):       # FFT_2.rs:431-450
+    n = 256
+    d1, d2 = twofft_signals(n)
+    s1, s2, o1, o2 = (np.zeros(2 * n + 2) for _ in range(4))
+    api.twofft(d1, d2, s1, s2)
+    api.twofft_optimized(d1, d2, o1, o2)
+    assert np.all(np.abs(s1 - o1) < 1e-10) and np.all(np.abs(s2 - o2) < 1e-10)
+
+
+def test_FFT_2__test_four1_function(api):           # FFT_2.rs:453-461 (18 doubles, nn = 8: the two trailing doubles untouched)
+    data = np.array([1.0, 0.0] * 8 + [0.0, 0.0])
+    api.four1(data, 8, 1)
+    assert data.size == 18
+    assert np.allclose(data, [8.0] + [0.0] * 17, atol=1e-12)
+
+
+def test_FFT_2__test_extract_combine_real_imag():   # FFT_2.rs:464-473 (host-side reshuffles of the shim)
+    real, imag = np.array([1.0, 2.0, 3.0]), np.array([4.0, 5.0, 6.0])
+    rb, ib = nb.extract_real_imag(nb.combine_real_imag(real, imag))
+    assert np.array_equal(real, rb) and np.array_equal(imag, ib)
+
+
+def test_FFT_2__test_twofft_performance(api):       # FFT_2.rs:476-490 (runs 256 / 1024 / 4096; here also checked)
+    for size in (256, 1024, 4096):
+        d1, d2 = twofft_signals(size)
+        f1, f2 = np.zeros(2 * size + 2), np.zeros(2 * size + 2)
+        api.twofft(d1, d2, f1, f2)
+        r1, r2 = np.conj(np.fft.fft(d1)), np.conj(np.fft.fft(d2))        # e^{+i} forward
+        assert np.max(np.abs(f1[0:2 * size:2] + 1j * f1[1:2 * size:2] - r1)) < 1e-9 * size
+        assert np.max(np.abs(f2[0:2 * size:2] + 1j * f2[1:2 * size:2] - r2)) < 1e-9 * size
+
+
+def test_FFT_2__test_batch_processing(api):         # FFT_2.rs:493-518: TwoFFTProcessor::process_batch, 4 x 512
+    batches = []
+    for _ in range(4):
+        d1, d2 = twofft_signals(512)
+        batches.append((d1, d2, np.zeros(2 * 512 + 2), np.zeros(2 * 512 + 2)))
+    api.twofft_batch(batches)
+    d1, d2 = twofft_signals(512)
+    s1, s2 = np.zeros(2 * 512 + 2), np.zeros(2 * 512 + 2)
+    api.twofft(d1, d2, s1, s2)
+    for _, _, f1, f2 in batches:
+        assert np.max(np.abs(f1 - s1)) < 1e-12 * 512 and np.max(np.abs(f2 - s2)) < 1e-12 * 512
+
+
+# ====================================================================================== Cos_FT.rs:142-175, Cos_FT2.rs:218-275 (N3)
+def dct1_nr(x):
+    """NR cosft1 of y[1..=n+1] (0-based x[0..n]): F_k = x_0 / 2 + (-1)^k x_n / 2 + sum_{j=1}^{n-1} x_j cos(pi j k / n)"""
+    n = x.size - 1
+    j = np.arange(1, n)
+    return np.array([0.5 * (x[0] + (-1) ** k * x[n]) + np.sum(x[1:n] * np.cos(PI * j * k / n)) for k in range(n + 1)])
+
+
+def dct2_nr(x):
+    """NR cosft2 forward of y[1..=n] (0-based x[0..n-1]): F_k = sum_j x_j cos(pi k (j + 1/2) / n)"""
+    n = x.size
+    j = np.arange(n)
+    return np.array([np.sum(x * np.cos(PI * k * (j + 0.5) / n)) for k in range(n)])
+
+
+def test_Cos_FT__test_cosft1_basic(api):            # Cos_FT.rs:147-156 (no assertions in the reference: "Add specific test ...")
+    n = 8
+    data = np.zeros(n + 2)
+    data[1:n + 1] = np.arange(1, n + 1)
+    x = data[1:n + 2].copy()
+    api.cosft1(data, n)
+    # the reference body ends in unimplemented!() (Cos_FT.rs:70-74); NR semantics (ledger D11) against the DCT-I definition
+    assert np.max(np.abs(data[1:n + 2] - dct1_nr(x))) < 1e-12 * 8 * 8
+
+
+def test_Cos_FT__test_cosft1_performance(api):      # Cos_FT.rs:159-174: cosft1 of 1024 zeros, repeatedly
+    n = 1024
+    data = np.zeros(n + 2)
+    for _ in range(3):
+        api.cosft1(data, n)
+    assert not data.any()
+
+
+def test_Cos_FT2__test_cosft2_forward(api):         # Cos_FT2.rs:224-233 (no assertions in the reference)
+    n = 8
+    data = np.zeros(n + 1)
+    data[1:] = np.arange(1, n + 1)
+    x = data[1:].copy()
+    api.cosft2(data, n, 1)
+    assert np.max(np.abs(data[1:] - dct2_nr(x))) < 1e-12 * 8 * 8
+
+
+def test_Cos_FT2__test_cosft2_inverse(api):         # Cos_FT2.rs:236-245 (no assertions in the reference)
+    n = 8
+    data = np.zeros(n + 1)
+    data[1:] = np.arange(1, n + 1)
+    x = data[1:].copy()
+    api.cosft2(data, n, -1)
+    # NR: the inverse of the forward transform up to the factor n / 2
+    back = np.zeros(n + 1)
+    back[1:] = data[1:]
+    api.cosft2(back, n, 1)
+    assert np.max(np.abs(back[1:] * (2.0 / n) - x)) < 1e-12 * 8 * 8
+
+
+def test_Cos_FT2__test_cosft2_round_trip(api):      # Cos_FT2.rs:248-264
+    n = 16
+    original = np.array([0.0 if i == 0 else math.sin(i) for i in range(n + 1)])
+    t = original.copy()
+    api.cosft2(t, n, 1)
+    api.cosft2(t, n, -1)
+    # the reference compares without any scaling; NR's cosft2 pair returns (n / 2) x (Numerical Recipes 12.3) -- true factor
+    t[1:] *= 2.0 / n
+    assert np.all(np.abs(t[1:] - original[1:]) <= 1e-10)
+
+
+def test_Cos_FT2__test_invalid_isign(api):          # Cos_FT2.rs:266-272  #[should_panic(expected = "Invalid isign value")]
+    data = np.zeros(9)
+    with pytest.raises(nb.NrbError) as e:
+        api.cosft2(data, 8, 0)
+    assert "Invalid isign value" in str(e.value)
