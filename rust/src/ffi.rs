@@ -1,4 +1,6 @@
-//! 1:1 declaration of include/numrs_b200.h (host-slice entry points only).
+//! 1:1 declaration of include/numrs_b200.h: the host-slice entry points, the device-buffer helpers and the
+//! device-resident plan API.  The slab / IPC entry points are for the one-process-per-GPU
+//! launchers (numrs_b200/dist_rlft3.py) and are not bound here: a Rust caller gets multi-GPU through "num_devices".
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_double, c_int};
 
@@ -10,6 +12,20 @@ pub const NRB_ERR_LENGTH_MISMATCH: c_int = -4;
 pub const NRB_ERR_INVALID_DIMS: c_int = -5;
 pub const NRB_ERR_ZERO_STDDEV: c_int = -8;
 pub const NRB_PAD_LITERAL: c_int = 0;
+pub const NRB_PAD_NR: c_int = 1;
+pub const NRB_KIND_FOUR1: c_int = 1;
+pub const NRB_KIND_FOURN: c_int = 2;
+pub const NRB_KIND_REALFT: c_int = 3;
+pub const NRB_KIND_RLFT3: c_int = 4;
+pub const NRB_KIND_CONVLV: c_int = 5;
+pub const NRB_KIND_CORREL: c_int = 6;
+
+/// opaque plan handle (`nrb_plan_t`)
+#[repr(C)]
+pub struct nrb_plan_s {
+    _private: [u8; 0],
+}
+pub type nrb_plan_t = *mut nrb_plan_s;
 
 extern "C" {
     pub fn nrb_last_error() -> *const c_char;
@@ -17,6 +33,18 @@ extern "C" {
     pub fn nrb_set_option(name: *const c_char, value: std::os::raw::c_long) -> c_int;
     pub fn nrb_num_devices_in_use() -> c_int;
     pub fn nrb_shutdown() -> c_int;
+    pub fn nrb_version() -> *const c_char;
+    pub fn nrb_device_count() -> c_int;
+    pub fn nrb_set_device(device: c_int) -> c_int;
+    /// pinned host memory: host-slice calls and nrb_upload / nrb_download copy at full PCIe rate from / to it
+    pub fn nrb_host_alloc(bytes: usize) -> *mut std::os::raw::c_void;
+    pub fn nrb_host_free(p: *mut std::os::raw::c_void);
+    /// device-resident plan API: `kind` = NRB_KIND_*, device pointers, caller's stream (null = default stream)
+    pub fn nrb_plan_create(kind: c_int, dims: *const usize, ndim: usize, batch: usize, plan: *mut nrb_plan_t) -> c_int;
+    pub fn nrb_plan_workspace_bytes(plan: nrb_plan_t) -> usize;
+    pub fn nrb_plan_exec(plan: nrb_plan_t, d_io: *mut c_double, d_aux: *mut c_double, d_out: *mut c_double, isign: c_int,
+                         arg: c_int, stream: *mut std::os::raw::c_void) -> c_int;
+    pub fn nrb_plan_destroy(plan: nrb_plan_t) -> c_int;
     pub fn nrb_four1(data: *mut c_double, nn: usize, isign: c_int) -> c_int;
     pub fn nrb_four1_batch(ptrs: *const *mut c_double, nn: *const usize, count: usize, isign: c_int) -> c_int;
     pub fn nrb_fourn(data: *mut c_double, nn: *const usize, ndim: usize, isign: c_int) -> c_int;

@@ -67,3 +67,46 @@ def test_product_package_never_imports_oracle_or_emulator():
             if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(root, f)).read()
                 assert "import oracle" not in src and "liboracle" not in src and "libnrb_emu" not in src, f
+
+
+def _c_prototypes():
+    """name -> number of parameters, from include/numrs_b200.h"""
+    hdr = open(os.path.join(ROOT, "include", "numrs_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {}
+    for name, args in re.findall(r"\b(nrb_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr):
+        args = args.strip()
+        protos[name] = 0 if args in ("", "void") else len(args.split(","))
+    return protos
+
+
+def test_rust_shim_declarations_match_the_header():
+    """rust/src/ffi.rs cannot be compiled here (no cargo): check it textually against the C header -- every extern fn it
+    declares exists in the header with the same number of parameters, every constant has the header's value, and every
+    host-slice entry point a reference function binds to is declared."""
+    src = open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read()
+    ext = src[src.index('extern "C" {'):]
+    ext = ext[:ext.index("\n}\n")]
+    ext = re.sub(r"//[^\n]*", "", ext)
+    rust = {}
+    for name, args in re.findall(r"pub fn (nrb_[a-z0-9_]+)\s*\(([^)]*)\)", ext, flags=re.S):
+        args = args.strip()
+        rust[name] = 0 if not args else len([a for a in args.split(",") if a.strip()])
+    protos = _c_prototypes()
+    assert len(rust) >= 35
+    for name, nargs in rust.items():
+        assert name in protos, f"{name} is declared in ffi.rs but not in the header"
+        assert nargs == protos[name], (name, nargs, protos[name])
+    for name in ("nrb_four1", "nrb_four1_batch", "nrb_fourn", "nrb_realft", "nrb_realft_batch", "nrb_rlft3", "nrb_convlv",
+                 "nrb_convlv_batch", "nrb_correl", "nrb_correl_batch", "nrb_correl_normalized", "nrb_autocorrel_fast",
+                 "nrb_twofft", "nrb_twofft_batch", "nrb_cosft1", "nrb_cosft2", "nrb_sinft", "nrb_power_spectrum",
+                 "nrb_set_option", "nrb_last_error", "nrb_plan_create", "nrb_plan_exec", "nrb_plan_destroy"):
+        assert name in rust, name
+    hdr = open(os.path.join(ROOT, "include", "numrs_b200.h")).read()
+    cdefs = {k: int(v) for k, v in re.findall(r"#define\s+(NRB_[A-Z0-9_]+)\s+\(?(-?\d+)\)?", hdr)}
+    for k, v in re.findall(r"pub const (NRB_[A-Z0-9_]+): c_int = (-?\d+);", src):
+        assert cdefs.get(k) == int(v), (k, v, cdefs.get(k))
+    # every nrb_* call in the shim's modules is declared in ffi.rs
+    lib_rs = open(os.path.join(ROOT, "rust", "src", "lib.rs")).read()
+    for name in set(re.findall(r"\b(nrb_[a-z0-9_]+)\s*\(", lib_rs)):
+        assert name in rust, f"rust/src/lib.rs calls {name}, which ffi.rs does not declare"
