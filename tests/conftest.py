@@ -18,7 +18,12 @@ def emu():
     """TEST-ONLY host emulation of the kernels (tests/emu); validates planner + index math on CPU."""
     from numrs_b200 import _lib
     d = os.path.join(ROOT, "tests", "emu")
-    subprocess.check_call(["make", "-C", d, "-s"])
+    # one build at a time: under pytest-xdist every worker runs this fixture, and a worker must not load a library that
+    # another one is still linking
+    import fcntl
+    with open(os.path.join(d, ".build.lock"), "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        subprocess.check_call(["make", "-C", d, "-s"])
     return _lib.Library(os.path.join(d, "libnrb_emu.so"))
 
 
