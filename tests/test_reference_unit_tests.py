@@ -194,8 +194,15 @@ def test_Fourn__test_invalid_inputs(api):           # Fourn.rs:467-476
         api.fourn(d, [8], 1, 0)          # invalid isign
 
 
-def test_Fourn__test_memory_mapping():              # Fourn.rs:479-486
-    pytest.skip("out of the path: the file / mmap-backed Fourn object is Four_FS territory (SURVEY.md section 2, out of scope)")
+def test_Fourn__test_memory_mapping(api):           # Fourn.rs:479-486
+    # the reference asserts that `with_memory_mapping()` gives the file-backed Fourn object mmap buffers: the out-of-core /
+    # file machinery is out of the path (Four_FS); what the in-memory call keeps of it is that the
+    # caller's buffer IS the working storage: transformed in place, nothing beyond 2 * prod(nn) doubles touched
+    d = np.concatenate([O.fill_uniform(79, 0, 2 * 16), [123.0, 456.0]])
+    api.fourn(d, [4, 4], 2, 1)
+    assert d[-2] == 123.0 and d[-1] == 456.0
+    api.fourn(d, [4, 4], 2, -1)
+    assert np.max(np.abs(d[:32] / 16 - O.fill_uniform(79, 0, 32))) < 1e-14
 
 
 # ====================================================================================== Real_FT.rs:488-595
