@@ -76,6 +76,7 @@ int  nrb_shutdown(void);               /* frees cached plans, twiddle tables no 
  *                       over NVLink peer memory and gather the result; the *_batch calls shard contiguous batch ranges.
  *   "pipeline_batches"  1 (default): a host-slice batch call of >= 64 MiB runs in chunks over three streams, so the H2D copy
  *                       of one chunk, the transforms of the previous and the D2H copy of the one before overlap; 0 = one shot
+ *   "pipeline_min_kb"   smallest chunk of a pipelined batch call in KiB (default 16384; a call needs at least four of them)
  *   "shard_min_kb"      batches smaller than this stay on one device (default 16384)
  *   "z_chunks"          slab stages: 2 = the z pass and the exchange pass beside it run as two halves of the local y rows,
  *                       the z pass of one half on a side stream under the exchange pass of the other (default 1 = off)
@@ -83,12 +84,19 @@ int  nrb_shutdown(void);               /* frees cached plans, twiddle tables no 
  *   "dma_streams"       DMA slab exchange: copy streams the pieces of a chunk are spread over (1 .. 4, default 1)
  *   "tma_xpose"         1 (default): the transposing 1024-point pass of a multi-step transform loads its tile by TMA
  *   "tma_col_mask"      bit log2 N set: eligible strided passes of N points use the TMA-fed kernel (default 512 | 1024)
+ *   "tma_persist"       1: the TMA-fed strided pass as a persistent CTA with two tile buffers (default 0: measured no faster)
+ *   "tma_in_mask" / "tma_in_ctas"  bit log2 N set: strided passes of N points load their tile by TMA and store from registers
+ *                       (also eligible with a four-step twiddle or a transposed output), 2 or 3 CTAs per SM (default 0 / 2:
+ *                       measured within noise of the fully TMA-fed pass, kept for A/B)
  *   "xchg_grid_cap"     pipelined slab exchange: CTAs of a peer-store pass (0 = one per tile); fewer CTAs leave SM
  *                       slots to the local pass running beside it on the second stream
  *   "simple_addr"       1 (default): passes whose element index is not split take the cheap addressing code path where it
  *                       is built (contiguous 8192-point lines, strided 512 / 1024-point lines); 0 = general path (A/B)
  *   "conv_fused_mid"    long-line convlv / correl / autocorrel_fast: contiguous forward pass + spectral step + contiguous
  *                       inverse pass of a row pair in ONE kernel, 5 -> 3 passes per signal (default 1)
+ *   "conv_rest_log2"    log2 of the contiguous row length of the long-line convlv / correl pipeline (default 12 = 4096-point
+ *                       rows, one fused-middle CTA per SM; 11 = 2048-point rows, two CTAs per SM: measured slower overall)
+ *   "mid_prefetch"      fused conv middle: tiles ahead whose rows a CTA prefetches into L2 (default 0 = off: measured slower)
  *   "speq_side"         rlft3: the four small speq-plane launches run on a second stream beside the data passes
  *                       (default 1)
  *   "trig_fused"        1 (default): cosft1 / cosft2 / sinft of 16 .. 16384 points and twofft of 8 .. 8192 points per line run

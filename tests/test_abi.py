@@ -110,3 +110,13 @@ def test_rust_shim_declarations_match_the_header():
     lib_rs = open(os.path.join(ROOT, "rust", "src", "lib.rs")).read()
     for name in set(re.findall(r"\b(nrb_[a-z0-9_]+)\s*\(", lib_rs)):
         assert name in rust, f"rust/src/lib.rs calls {name}, which ffi.rs does not declare"
+
+
+def test_every_option_is_documented_in_the_header():
+    """nrb_set_option's names (plan.cpp set_tunable) all appear in the option list of include/numrs_b200.h"""
+    src = open(os.path.join(ROOT, "numrs_b200", "csrc", "plan.cpp")).read()
+    names = set(re.findall(r'n == "([a-z0-9_]+)"', src))
+    assert len(names) >= 25
+    hdr = open(os.path.join(ROOT, "include", "numrs_b200.h")).read()
+    missing = sorted(n for n in names if f'"{n}"' not in hdr)
+    assert not missing, missing
