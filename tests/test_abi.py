@@ -120,3 +120,35 @@ def test_every_option_is_documented_in_the_header():
     hdr = open(os.path.join(ROOT, "include", "numrs_b200.h")).read()
     missing = sorted(n for n in names if f'"{n}"' not in hdr)
     assert not missing, missing
+
+
+def test_headline_kernels_keep_their_register_budget():
+    """The occupancy the measured numbers rest on is a property of the build: the z pass of rlft3 512^3
+    (ROW-REAL, 256 complex points) and the register-fed strided pass run with <= 64 registers (2 CTAs of 512 threads or 4+ of
+    256 per SM), the TMA-fed 512-point strided pass with <= 85 (three 256-thread CTAs per SM), the fused conv middle with
+    <= 64 (one 1024-thread CTA), and none of them has a local-memory frame worth a spill."""
+    import subprocess
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "--dump-resource-usage", nb.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    items = re.findall(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", out.stdout)
+    assert len(items) > 100
+    dem = subprocess.run(["c++filt"], input="\n".join(i[0] for i in items), capture_output=True, text=True).stdout.split("\n")
+    usage = {d: (int(r), int(s), int(l)) for d, (_, r, s, _, l) in zip(dem, items)}
+
+    def find(prefix):
+        hits = [v for k, v in usage.items() if k.replace("void nrb::", "").startswith(prefix)]
+        assert hits, prefix
+        return hits
+    budget = {
+        "fft_pass_kernel<8, 0, 1, 1>": 64, "fft_pass_kernel<8, 0, -1, 1>": 64,          # ROW-REAL 256 (z pass)
+        "fft_pass_kernel<9, 1, 1, 0>": 128, "fft_pass_kernel<9, 1, -1, 0>": 128,        # strided 512, register-fed (16 points / thread)
+        "fft_col_tma_kernel<9, 1, false>": 85, "fft_col_tma_kernel<9, -1, false>": 85,  # strided 512, TMA-fed, 3 CTAs / SM
+        "fft_col_tma_kernel<10, 1, false>": 85, "fft_col_tma_kernel<10, -1, false>": 85,
+        "conv_mid_kernel<12>": 64,
+        "trig_kernel<11>": 64, "twofft_kernel<12>": 64,
+    }
+    for prefix, regs in budget.items():
+        for r, stack, local in find(prefix):
+            assert r <= regs, (prefix, r, regs)
+            assert stack <= 16 and local == 0, (prefix, stack, local)
